@@ -1,0 +1,71 @@
+"""ctypes loader of libgibbs_b200.so (the C ABI declared in include/gibbs_b200.h).
+
+There is no CPU fallback: if the CUDA library has not been built the import of any compute
+entry point fails loudly.  Build it with ``python -c "import __graft_entry__ as g; g.build()"``
+or ``make -C gibbssampler_b200/csrc``.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "_build", "libgibbs_b200.so")
+
+GS_ALM_COMPLEX = 0
+GS_ALM_REAL = 1
+
+_lib = None
+
+_vp = C.c_void_p
+_i = C.c_int
+_d = C.c_double
+_i64 = C.c_int64
+
+# name -> (restype, argtypes); mirrors include/gibbs_b200.h one to one
+SIGNATURES = {
+    "gs_last_error_string": (C.c_char_p, []),
+    "gs_version": (_i, []),
+    "gs_plan_create": (_i, [C.POINTER(_vp), _i, _i, _i]),
+    "gs_plan_destroy": (_i, [_vp]),
+    "gs_plan_nside": (_i, [_vp]),
+    "gs_plan_lmax": (_i, [_vp]),
+    "gs_plan_npix": (_i64, [_vp]),
+    "gs_plan_nalm": (_i64, [_vp]),
+    "gs_plan_nreal": (_i64, [_vp]),
+    "gs_alm2map_spin0": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "gs_alm2map_spin2": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "gs_map2alm_spin0": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
+    "gs_map2alm_spin2": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "gs_real_to_complex": (_i, [_vp, _vp, _i, _vp]),
+    "gs_complex_to_real": (_i, [_vp, _vp, _i, _vp]),
+    "gs_expand_per_l": (_i, [_vp, _i, _i, _vp, _vp]),
+    "gs_unfold_bins": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    "gs_almxfl": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
+    "gs_alm2cl": (_i, [_vp, _i, _i, _vp, _vp]),
+}
+
+
+class GibbsB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded C-ABI library; raises if it was never built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GibbsB200Error(
+                "libgibbs_b200.so not found at %s: the CUDA extension is not built "
+                "(run __graft_entry__.build()); gibbssampler_b200 has no CPU fallback" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = lib().gs_last_error_string()
+        raise GibbsB200Error("libgibbs_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))

@@ -1,0 +1,118 @@
+// Internal declarations shared by the CUDA translation units of libgibbs_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/gibbs_b200.h"
+
+// ---------------------------------------------------------------- errors
+void gs_set_error(const char* fmt, ...);
+#define GS_CHECK_CUDA(expr)                                                                  \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            gs_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return GS_E_CUDA;                                                                \
+        }                                                                                    \
+    } while (0)
+#define GS_CHECK_LAUNCH() GS_CHECK_CUDA(cudaGetLastError())
+#define GS_REQUIRE(cond, msg)                                \
+    do {                                                     \
+        if (!(cond)) {                                       \
+            gs_set_error("%s: %s", __func__, msg);           \
+            return GS_E_BADARG;                              \
+        }                                                    \
+    } while (0)
+
+// ---------------------------------------------------------------- scaled-recurrence constants
+// true lambda = v * 2^(-GS_SC_K * scale); contributions with true |lambda| < 2^GS_SC_LO are dropped.
+#define GS_SC_LO (-900)
+#define GS_SC_K 256
+
+struct ScaledSeed {  // value = mant * 2^ex
+    double mant;
+    int ex;
+    int pad;
+};
+
+// One Bluestein descriptor per distinct non-power-of-two ring length.
+struct BluesteinDesc {
+    int n;            // ring length
+    int M;            // power-of-two convolution length >= 2n-1
+    int64_t chirp_off;  // offset (in double2) of c_j = exp(i pi j^2 / n), j < n
+    int64_t bhat_off;   // offset (in double2) of DIF-ordered FFT_M(conj chirp, wrapped) / M
+};
+
+struct RingJob {  // one complex DFT = two real ring sequences of equal length
+    int ringA, compA;  // 0-based ring index, component (0 = Q/T, 1 = U)
+    int ringB, compB;  // ringB = -1: no second sequence
+};
+
+// Device-side view of a plan (plain pointers; passed by value to kernels).
+struct PlanDev {
+    int nside, lmax, nring, npair;
+    int64_t npix, nalm;
+    // ring pairs p = 0..npair-1 <-> north ring p+1 (p = npair-1 is the equator)
+    const double* cth;   // cos(theta)
+    const double* sth;   // sin(theta)
+    const double* c2;    // cos^2(theta/2)
+    const double* s2;    // sin^2(theta/2)
+    const int* mlim0;    // last m with a non-negligible lambda_lm on this ring pair (spin 0)
+    const int* mlim2;    // same for spin 2
+    // per-m seed factors
+    const ScaledSeed* seed0;  // (-1)^m prod sqrt((2k-1)/2k) sqrt((2m+1)/4pi)
+    const ScaledSeed* seed2;  // ... * sqrt(m(m-1)/((m+1)(m+2)))  (m >= 2)
+    // recurrence tables indexed like healpy alm: idx(l,m) = m(2L+1-m)/2 + l
+    const double* rec0;   // a_l (spin 0)
+    const double* alpha0; // alpha_l (spin 0)
+    const double2* rec2;  // (a_l, b_l) (spin 2)
+    const double* alpha2; // alpha_l (spin 2)
+    // rings 0..nring-1
+    const int* ring_nphi;
+    const int64_t* ring_start;
+    const int* ring_phq;   // phi0 = pi * ring_phq / ring_phden
+    const int* ring_phden;
+    const int* ring_bs;    // Bluestein descriptor index or -1 (power-of-two ring)
+    const BluesteinDesc* bs;
+    const double2* bs_tab; // pooled chirp / bhat tables
+    const double2* tw;     // exp(-2 pi i k / tw_n), k < tw_n
+    int tw_n;
+    int max_M;
+};
+
+struct gs_plan {
+    int device;
+    PlanDev d;
+    std::vector<void*> owned;  // device allocations to free
+    // job lists (device) for the ring-FFT stage
+    RingJob* jobs2;  // spin 2: (Q,U) of each ring, heavy first
+    int njobs2;
+    RingJob* jobs0;  // spin 0: (north, south) ring of each pair
+    int njobs0;
+    // workspace
+    double2* Fm;        // [2][nring][lmax+1] ring spectra
+    double* partial;    // analysis partial sums [nchunk][nalm][4]
+    int anal_chunks;
+    size_t ring_smem;   // dynamic shared memory of the ring-FFT kernels
+    // scratch maps / alms for iter>0 analysis and solvers
+    double* mapQ_tmp;
+    double* mapU_tmp;
+    double* almE_tmp;
+    double* almB_tmp;
+    double* almE_tmp2;
+    double* almB_tmp2;
+};
+
+static inline int64_t gs_nalm(int lmax) { return (int64_t)(lmax + 1) * (lmax + 2) / 2; }
+
+// legendre.cu
+int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, int layout, const double* fl,
+                 cudaStream_t st);
+int gs_leg_anal(gs_plan* p, int spin, double* almE, double* almB, int layout, const double* fl, double scale,
+                int accumulate, cudaStream_t st);
+// ringfft.cu
+int gs_ring_setup(gs_plan* p);
+int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st);
+int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, const double* pixw, cudaStream_t st);

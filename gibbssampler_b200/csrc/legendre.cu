@@ -1,0 +1,583 @@
+// Legendre stage of the spin-0 / spin-2 spherical-harmonic transforms (sm_100a, FP64).
+//
+// Replaces the libsharp Legendre loops behind hp.alm2map / hp.map2alm.
+//
+// One thread owns R north/south ring pairs and walks l = max(m,spin) .. lmax for ONE m with the
+// normalised Wigner-d recurrence  mu_{l+1} = (a_l x -+ b_l) mu_l - mu_{l-1}  (2 DFMA per chain and
+// step; table built in long double by plan.cu).  All threads of a block share m, so the a_lm
+// tile (pre-multiplied by alpha_lm, the -1/2 of the E/B convention, an optional per-l filter and
+// the real-layout 1/sqrt2) and the recurrence coefficients are staged once per block in shared
+// memory and read back as warp-broadcast LDS.128.  The north/south symmetry
+// lam^{+-}_{lm}(pi - theta) = (-1)^(l+m) lam^{-+}_{lm}(theta) halves the work: terms are
+// accumulated into a symmetric and an antisymmetric part (unrolled by two in l so that the
+// parity is static), north = S + A, south = S - A.
+// Range: seeds ~ sin(theta)^m underflow FP64 near the poles, so every ring carries an integer
+// scale (true value = v * 2^(-256 scale)); a warp runs (A) recurrence only while all its lanes are
+// below 2^-900, (B) predicated accumulation while some are, (C) the unchecked fast loop.
+// Analysis is the exact transpose; its sum over rings is a register fold + warp shuffle
+// reduce-scatter (9 SHFL.64 per two l for 8 values), then a shared-memory sum over the warps of
+// the block and one deterministic partial per 256-ring-pair chunk, combined by leg_finish_kernel.
+#include "gs_internal.h"
+
+#define LEG_NT 128   // threads per block
+#define LEG_NW (LEG_NT / 32)
+#define LEG_TL 128   // l-tile (even)
+#define LEG_R 2      // ring pairs per thread  (LEG_NT * LEG_R = 256 = ring pairs per analysis chunk)
+#define FULL 0xffffffffu
+
+__device__ __forceinline__ double pow2i(int e) { return __hiloint2double((e + 1023) << 20, 0); }
+
+// v != 0 normal -> mantissa in [0.5,1) (sign kept), e += exponent
+__device__ __forceinline__ void renorm(double& v, int& e)
+{
+    int hi = __double2hiint(v), lo = __double2loint(v);
+    e += ((hi >> 20) & 0x7ff) - 1022;
+    v = __hiloint2double((hi & 0x800fffff) | (1022 << 20), lo);
+}
+
+// x^n = mant * 2^ex for 0 < x <= 1 (binary exponentiation with exponent tracking)
+__device__ __forceinline__ void pow_scaled(double x, int n, double& mant, int& ex)
+{
+    double r = 0.5, b = x;
+    int er = 1, eb = 0;
+    renorm(b, eb);
+    while (n > 0) {
+        if (n & 1) { r *= b; er += eb; renorm(r, er); }
+        b *= b; eb *= 2; renorm(b, eb);
+        n >>= 1;
+    }
+    mant = r; ex = er;
+}
+
+// Seeds of the recurrence at l0 = max(m, SPIN) for one ring: vp = mu^+ (m' = -2, or the spin-0
+// chain), vm = mu^- (m' = +2), common scale sc.
+template <int SPIN>
+__device__ __forceinline__ void seed_ring(const PlanDev& P, int p, int m, double& vp, double& vm, int& sc)
+{
+    const double sth = P.sth[p];
+    double mant; int ex;
+    double fp, fm;  // plain factors multiplying mant * 2^ex
+    if (SPIN == 0) {
+        pow_scaled(sth, m, mant, ex);
+        ScaledSeed s = P.seed0[m];
+        mant *= s.mant; ex += s.ex; fp = 1.0; fm = 0.0;
+    } else {
+        const double c2 = P.c2[p], s2 = P.s2[p];
+        if (m >= 2) {
+            pow_scaled(sth, m, mant, ex);
+            ScaledSeed s = P.seed2[m];
+            mant *= s.mant; ex += s.ex;
+            fp = s2 / c2; fm = c2 / s2;
+        } else {
+            const double n5 = 0.63078313050504001;  // sqrt(5 / (4 pi))
+            mant = 1.0; ex = 0;
+            if (m == 0) { fp = fm = n5 * 0.61237243569579452 * sth * sth; }  // sqrt(6)/4 sin^2
+            else { fp = -n5 * sth * s2; fm = n5 * sth * c2; }
+        }
+    }
+    // common scale from the larger chain
+    double big = fmax(fabs(fp), fabs(fm)) * fabs(mant);
+    int eb = ex;
+    if (big == 0.0) { vp = vm = 0.0; sc = 0; return; }
+    renorm(big, eb);  // true magnitude ~ 2^eb
+    int shift;
+    if (eb >= GS_SC_LO) { sc = 0; shift = ex; }
+    else { sc = (GS_SC_LO - eb + GS_SC_K - 1) / GS_SC_K; shift = ex + GS_SC_K * sc; }
+    // mant in [0.25,1], factors plain doubles: apply 2^shift in two halves to stay in range
+    int h1 = shift / 2, h2 = shift - h1;
+    vp = (mant * pow2i(h1)) * fp * pow2i(h2);
+    vm = (mant * pow2i(h1)) * fm * pow2i(h2);
+}
+
+#define RESCALE_THR 0x1p-644   // 2^(GS_SC_LO + GS_SC_K)
+#define RESCALE_MUL 0x1p-256
+
+template <int SPIN>
+struct RingState {
+    double x;
+    double pc, pp;  // mu^+ current / previous
+    double mc, mp;  // mu^- current / previous (spin 2)
+    int sc;
+};
+
+// one recurrence step with coefficients (a, b): (pc,pp) <- (new, pc)
+template <int SPIN>
+__device__ __forceinline__ void rec_step(RingState<SPIN>& s, double a, double b)
+{
+    if (SPIN == 0) {
+        double t = a * s.x;
+        double n = fma(t, s.pc, -s.pp);
+        s.pp = s.pc; s.pc = n;
+    } else {
+        double tp = fma(a, s.x, b), tm = fma(a, s.x, -b);
+        double np = fma(tp, s.pc, -s.pp), nm = fma(tm, s.mc, -s.mp);
+        s.pp = s.pc; s.pc = np; s.mp = s.mc; s.mc = nm;
+    }
+}
+
+template <int SPIN>
+__device__ __forceinline__ void rescale_check(RingState<SPIN>& s)
+{
+    if (s.sc > 0) {
+        bool big = fabs(s.pc) > RESCALE_THR;
+        if (SPIN) big = big || fabs(s.mc) > RESCALE_THR;
+        if (big) {
+            s.pc *= RESCALE_MUL; s.pp *= RESCALE_MUL;
+            if (SPIN) { s.mc *= RESCALE_MUL; s.mp *= RESCALE_MUL; }
+            s.sc--;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ staging of one l-tile
+template <int SPIN>
+__device__ __forceinline__ void stage_alm_tile(const PlanDev& P, int m, int lt, int64_t base, const double* almE,
+                                               const double* almB, int layout, const double* fl, double2* sE,
+                                               double2* sB, double2* sR)
+{
+    const int L = P.lmax;
+    for (int i = threadIdx.x; i < LEG_TL; i += LEG_NT) {
+        const int l = lt + i;
+        double2 e = make_double2(0.0, 0.0), b = e, r = e;
+        if (l <= L) {
+            const int64_t id = base + l;
+            double pre = SPIN ? -0.5 * P.alpha2[id] : P.alpha0[id];
+            if (fl) pre *= fl[l];
+            if (layout == GS_ALM_COMPLEX) {
+                e = reinterpret_cast<const double2*>(almE)[id];
+                if (SPIN) b = reinterpret_cast<const double2*>(almB)[id];
+            } else if (m == 0) {
+                e.x = almE[l];
+                if (SPIN) b.x = almB[l];
+            } else {
+                const int64_t off = 2 * id - (L + 1);
+                pre *= 0.70710678118654752440;
+                e.x = almE[off]; e.y = almE[off + 1];
+                if (SPIN) { b.x = almB[off]; b.y = almB[off + 1]; }
+            }
+            e.x *= pre; e.y *= pre; b.x *= pre; b.y *= pre;
+            if (SPIN) r = P.rec2[id]; else r.x = P.rec0[id];
+        }
+        sE[i] = e;
+        if (SPIN) sB[i] = b;
+        sR[i] = r;
+    }
+}
+
+// ------------------------------------------------------------------ synthesis
+template <int SPIN>
+struct SynthAcc {  // first-l parity part (S) and the other one (A); q = Q or T, u = U
+    double sqr, sqi, aqr, aqi;
+    double sur, sui, aur, aui;
+};
+
+// accumulate l with "F1 -> s*, F2 -> a*" (FIRST = true) or swapped roles
+template <int SPIN, bool FIRST>
+__device__ __forceinline__ void synth_acc(SynthAcc<SPIN>& A, double pc, double mc, double2 e, double2 b)
+{
+    if (SPIN == 0) {
+        if (FIRST) { A.sqr = fma(e.x, pc, A.sqr); A.sqi = fma(e.y, pc, A.sqi); }
+        else       { A.aqr = fma(e.x, pc, A.aqr); A.aqi = fma(e.y, pc, A.aqi); }
+    } else {
+        const double f1 = pc + mc, f2 = pc - mc;
+        // Q_m += E' F1 + i B' F2 ; U_m += B' F1 - i E' F2   (E', B' carry -alpha/2)
+        if (FIRST) {
+            A.sqr = fma(e.x, f1, A.sqr); A.sqi = fma(e.y, f1, A.sqi);
+            A.sur = fma(b.x, f1, A.sur); A.sui = fma(b.y, f1, A.sui);
+            A.aqr = fma(-b.y, f2, A.aqr); A.aqi = fma(b.x, f2, A.aqi);
+            A.aur = fma(e.y, f2, A.aur); A.aui = fma(-e.x, f2, A.aui);
+        } else {
+            A.aqr = fma(e.x, f1, A.aqr); A.aqi = fma(e.y, f1, A.aqi);
+            A.aur = fma(b.x, f1, A.aur); A.aui = fma(b.y, f1, A.aui);
+            A.sqr = fma(-b.y, f2, A.sqr); A.sqi = fma(b.x, f2, A.sqi);
+            A.sur = fma(e.y, f2, A.sur); A.sui = fma(-e.x, f2, A.sui);
+        }
+    }
+}
+
+template <int SPIN, int R>
+__global__ void __launch_bounds__(LEG_NT)
+leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __restrict__ almB, int layout,
+                 const double* __restrict__ fl, double2* __restrict__ Fm)
+{
+    __shared__ double2 sE[LEG_TL], sB[SPIN ? LEG_TL : 1], sR[LEG_TL];
+    const int L = P.lmax, m = blockIdx.y, tid = threadIdx.x;
+    const int l0 = m > SPIN ? m : SPIN;
+    const int64_t base = (int64_t)m * (2 * L + 1 - m) / 2;
+    const int chunk = blockIdx.x * (LEG_NT * R);
+
+    RingState<SPIN> st[R];
+    SynthAcc<SPIN> acc[R];
+    bool any_act = false;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const int p = chunk + j * LEG_NT + tid;
+        st[j].x = 0.0; st[j].pc = st[j].pp = st[j].mc = st[j].mp = 0.0; st[j].sc = 0;
+        acc[j].sqr = acc[j].sqi = acc[j].aqr = acc[j].aqi = 0.0;
+        acc[j].sur = acc[j].sui = acc[j].aur = acc[j].aui = 0.0;
+        if (p < P.npair && m <= (SPIN ? P.mlim2[p] : P.mlim0[p])) {
+            st[j].x = P.cth[p];
+            seed_ring<SPIN>(P, p, m, st[j].pc, st[j].mc, st[j].sc);
+            any_act = true;
+        }
+    }
+    const bool warp_act = __any_sync(FULL, any_act);
+
+    for (int lt = l0; lt <= L; lt += LEG_TL) {
+        __syncthreads();
+        stage_alm_tile<SPIN>(P, m, lt, base, almE, almB, layout, fl, sE, sB, sR);
+        __syncthreads();
+        if (!warp_act) continue;
+        const int ni = min(LEG_TL, L - lt + 1);
+        const int npr = (ni + 1) >> 1;
+        int ip = 0;
+        // (A) every lane still below range: recurrence only
+        while (ip < npr) {
+            bool alls = true;
+#pragma unroll
+            for (int j = 0; j < R; ++j) alls = alls && (st[j].sc > 0 || st[j].pc == 0.0);
+            if (!__all_sync(FULL, alls)) break;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double2 r = sR[2 * ip + h];
+#pragma unroll
+                for (int j = 0; j < R; ++j) { rec_step<SPIN>(st[j], r.x, r.y); rescale_check<SPIN>(st[j]); }
+            }
+            ++ip;
+        }
+        // (B) mixed: predicated accumulation + range checks
+        while (ip < npr) {
+            bool anys = false;
+#pragma unroll
+            for (int j = 0; j < R; ++j) anys = anys || st[j].sc > 0;
+            if (!__any_sync(FULL, anys)) break;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int i = 2 * ip + h;
+                const double2 r = sR[i], e = sE[i];
+                const double2 b = SPIN ? sB[i] : e;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const double pc = st[j].sc ? 0.0 : st[j].pc, mc = st[j].sc ? 0.0 : st[j].mc;
+                    if (h == 0) synth_acc<SPIN, true>(acc[j], pc, mc, e, b);
+                    else synth_acc<SPIN, false>(acc[j], pc, mc, e, b);
+                    rec_step<SPIN>(st[j], r.x, r.y);
+                    rescale_check<SPIN>(st[j]);
+                }
+            }
+            ++ip;
+        }
+        // (C) fast path
+#pragma unroll 2
+        for (; ip < npr; ++ip) {
+            const int i = 2 * ip;
+            const double2 r0 = sR[i], e0 = sE[i], r1 = sR[i + 1], e1 = sE[i + 1];
+            const double2 b0 = SPIN ? sB[i] : e0, b1 = SPIN ? sB[i + 1] : e1;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                synth_acc<SPIN, true>(acc[j], st[j].pc, st[j].mc, e0, b0);
+                rec_step<SPIN>(st[j], r0.x, r0.y);
+                synth_acc<SPIN, false>(acc[j], st[j].pc, st[j].mc, e1, b1);
+                rec_step<SPIN>(st[j], r1.x, r1.y);
+            }
+        }
+    }
+
+    // north = S + A ; south = +-(S - A), sign from the parity of the first l
+    const double sg = ((l0 + m) & 1) ? -1.0 : 1.0;
+    const int64_t nm = L + 1;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const int p = chunk + j * LEG_NT + tid;
+        if (p >= P.npair) continue;
+        const int rn = p, rs = P.nring - 1 - p;
+        Fm[(int64_t)rn * nm + m] = make_double2(acc[j].sqr + acc[j].aqr, acc[j].sqi + acc[j].aqi);
+        if (rs != rn) Fm[(int64_t)rs * nm + m] = make_double2(sg * (acc[j].sqr - acc[j].aqr), sg * (acc[j].sqi - acc[j].aqi));
+        if (SPIN) {
+            double2* Fu = Fm + (int64_t)P.nring * nm;
+            Fu[(int64_t)rn * nm + m] = make_double2(acc[j].sur + acc[j].aur, acc[j].sui + acc[j].aui);
+            if (rs != rn) Fu[(int64_t)rs * nm + m] = make_double2(sg * (acc[j].sur - acc[j].aur), sg * (acc[j].sui - acc[j].aui));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ analysis
+template <int SPIN>
+struct AnalIn {  // ring spectra combined for the first-l parity (1) and the other parity (2)
+    double q1r, q1i, q2r, q2i;
+    double u1r, u1i, u2r, u2i;
+};
+
+// contributions of one ring to (E.re, E.im, B.re, B.im) [spin 2] or (re, im) [spin 0] at one l
+template <int SPIN, bool FIRST, bool INIT>
+__device__ __forceinline__ void anal_acc(double* o, const AnalIn<SPIN>& G, double pc, double mc)
+{
+    if (SPIN == 0) {
+        const double gr = FIRST ? G.q1r : G.q2r, gi = FIRST ? G.q1i : G.q2i;
+        o[0] = INIT ? gr * pc : fma(gr, pc, o[0]);
+        o[1] = INIT ? gi * pc : fma(gi, pc, o[1]);
+    } else {
+        const double f1 = pc + mc, f2 = pc - mc;
+        // E = F1 Gq + i F2 Gu ; B = F1 Gu - i F2 Gq  (times -alpha/2 in the finish kernel);
+        // F1 pairs with this l's parity, F2 with the opposite one
+        const double aqr = FIRST ? G.q1r : G.q2r, aqi = FIRST ? G.q1i : G.q2i;
+        const double aur = FIRST ? G.u1r : G.u2r, aui = FIRST ? G.u1i : G.u2i;
+        const double bqr = FIRST ? G.q2r : G.q1r, bqi = FIRST ? G.q2i : G.q1i;
+        const double bur = FIRST ? G.u2r : G.u1r, bui = FIRST ? G.u2i : G.u1i;
+        if (INIT) { o[0] = aqr * f1; o[1] = aqi * f1; o[2] = aur * f1; o[3] = aui * f1; }
+        else { o[0] = fma(aqr, f1, o[0]); o[1] = fma(aqi, f1, o[1]); o[2] = fma(aur, f1, o[2]); o[3] = fma(aui, f1, o[3]); }
+        o[0] = fma(-bui, f2, o[0]);
+        o[1] = fma(bur, f2, o[1]);
+        o[2] = fma(bqi, f2, o[2]);
+        o[3] = fma(-bqr, f2, o[3]);
+    }
+}
+
+// reduce-scatter of NVAL values over the warp: afterwards lane holds the full sum of value
+// index lane >> (5 - log2(NVAL)); all lanes sharing that index hold the same number.
+template <int NVAL>
+__device__ __forceinline__ double warp_fold(double* v, int lane)
+{
+    if (NVAL == 8) {
+        const bool h4 = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const double keep = h4 ? v[i + 4] : v[i], send = h4 ? v[i] : v[i + 4];
+            v[i] = keep + __shfl_xor_sync(FULL, send, 16);
+        }
+        const bool h3 = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double keep = h3 ? v[i + 2] : v[i], send = h3 ? v[i] : v[i + 2];
+            v[i] = keep + __shfl_xor_sync(FULL, send, 8);
+        }
+        const bool h2 = lane & 4;
+        const double keep = h2 ? v[1] : v[0], send = h2 ? v[0] : v[1];
+        double r = keep + __shfl_xor_sync(FULL, send, 4);
+        r += __shfl_xor_sync(FULL, r, 2);
+        r += __shfl_xor_sync(FULL, r, 1);
+        return r;
+    } else {  // 4 values
+        const bool h4 = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const double keep = h4 ? v[i + 2] : v[i], send = h4 ? v[i] : v[i + 2];
+            v[i] = keep + __shfl_xor_sync(FULL, send, 16);
+        }
+        const bool h3 = lane & 8;
+        const double keep = h3 ? v[1] : v[0], send = h3 ? v[0] : v[1];
+        double r = keep + __shfl_xor_sync(FULL, send, 8);
+        r += __shfl_xor_sync(FULL, r, 4);
+        r += __shfl_xor_sync(FULL, r, 2);
+        r += __shfl_xor_sync(FULL, r, 1);
+        return r;
+    }
+}
+
+template <int SPIN, int R>
+__global__ void __launch_bounds__(LEG_NT)
+leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ partial)
+{
+    constexpr int NV = SPIN ? 4 : 2;   // doubles per (l,m)
+    constexpr int NVAL = 2 * NV;       // values reduced per pair of l
+    __shared__ double2 sR[LEG_TL];
+    __shared__ double sPart[LEG_NW][LEG_TL * NV];
+    const int L = P.lmax, m = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int l0 = m > SPIN ? m : SPIN;
+    const int64_t base = (int64_t)m * (2 * L + 1 - m) / 2;
+    const int chunk = blockIdx.x * (LEG_NT * R);
+    const bool odd0 = (l0 + m) & 1;
+    const int64_t nm = L + 1;
+
+    RingState<SPIN> st[R];
+    AnalIn<SPIN> G[R];
+    bool any_act = false;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const int p = chunk + j * LEG_NT + tid;
+        st[j].x = 0.0; st[j].pc = st[j].pp = st[j].mc = st[j].mp = 0.0; st[j].sc = 0;
+        G[j].q1r = G[j].q1i = G[j].q2r = G[j].q2i = 0.0;
+        G[j].u1r = G[j].u1i = G[j].u2r = G[j].u2i = 0.0;
+        if (p < P.npair && m <= (SPIN ? P.mlim2[p] : P.mlim0[p])) {
+            st[j].x = P.cth[p];
+            seed_ring<SPIN>(P, p, m, st[j].pc, st[j].mc, st[j].sc);
+            any_act = true;
+            const int rn = p, rs = P.nring - 1 - p;
+            const double2 z = make_double2(0.0, 0.0);
+            const double2 qn = Fm[(int64_t)rn * nm + m], qs = (rs != rn) ? Fm[(int64_t)rs * nm + m] : z;
+            double2 sy = make_double2(qn.x + qs.x, qn.y + qs.y), an = make_double2(qn.x - qs.x, qn.y - qs.y);
+            G[j].q1r = odd0 ? an.x : sy.x; G[j].q1i = odd0 ? an.y : sy.y;
+            G[j].q2r = odd0 ? sy.x : an.x; G[j].q2i = odd0 ? sy.y : an.y;
+            if (SPIN) {
+                const double2* Fu = Fm + (int64_t)P.nring * nm;
+                const double2 un = Fu[(int64_t)rn * nm + m], us = (rs != rn) ? Fu[(int64_t)rs * nm + m] : z;
+                sy = make_double2(un.x + us.x, un.y + us.y); an = make_double2(un.x - us.x, un.y - us.y);
+                G[j].u1r = odd0 ? an.x : sy.x; G[j].u1i = odd0 ? an.y : sy.y;
+                G[j].u2r = odd0 ? sy.x : an.x; G[j].u2i = odd0 ? sy.y : an.y;
+            }
+        }
+    }
+    const bool warp_act = __any_sync(FULL, any_act);
+    const int vidx = lane >> (SPIN ? 2 : 3);           // value index this lane ends up owning
+    const bool writer = (lane & (SPIN ? 3 : 7)) == 0;
+
+    for (int lt = l0; lt <= L; lt += LEG_TL) {
+        __syncthreads();
+        for (int i = tid; i < LEG_TL; i += LEG_NT) {
+            const int l = lt + i;
+            double2 r = make_double2(0.0, 0.0);
+            if (l <= L) { if (SPIN) r = P.rec2[base + l]; else r.x = P.rec0[base + l]; }
+            sR[i] = r;
+        }
+        __syncthreads();
+        const int ni = min(LEG_TL, L - lt + 1);
+        const int npr = (ni + 1) >> 1;
+        int ip = 0;
+        double* myPart = sPart[w];
+        if (!warp_act) {
+            for (int i = lane; i < LEG_TL * NV; i += 32) myPart[i] = 0.0;
+            ip = npr;
+        }
+        while (ip < npr) {  // (A)
+            bool alls = true;
+#pragma unroll
+            for (int j = 0; j < R; ++j) alls = alls && (st[j].sc > 0 || st[j].pc == 0.0);
+            if (!__all_sync(FULL, alls)) break;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double2 r = sR[2 * ip + h];
+#pragma unroll
+                for (int j = 0; j < R; ++j) { rec_step<SPIN>(st[j], r.x, r.y); rescale_check<SPIN>(st[j]); }
+            }
+            if (lane < NVAL) myPart[ip * NVAL + lane] = 0.0;
+            ++ip;
+        }
+        while (ip < npr) {  // (B)
+            bool anys = false;
+#pragma unroll
+            for (int j = 0; j < R; ++j) anys = anys || st[j].sc > 0;
+            if (!__any_sync(FULL, anys)) break;
+            double v[NVAL];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double2 r = sR[2 * ip + h];
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const double pc = st[j].sc ? 0.0 : st[j].pc, mc = st[j].sc ? 0.0 : st[j].mc;
+                    if (h == 0) { if (j == 0) anal_acc<SPIN, true, true>(v, G[j], pc, mc); else anal_acc<SPIN, true, false>(v, G[j], pc, mc); }
+                    else { if (j == 0) anal_acc<SPIN, false, true>(v + NV, G[j], pc, mc); else anal_acc<SPIN, false, false>(v + NV, G[j], pc, mc); }
+                    rec_step<SPIN>(st[j], r.x, r.y);
+                    rescale_check<SPIN>(st[j]);
+                }
+            }
+            const double s = warp_fold<NVAL>(v, lane);
+            if (writer) myPart[ip * NVAL + vidx] = s;
+            ++ip;
+        }
+        for (; ip < npr; ++ip) {  // (C)
+            double v[NVAL];
+            const double2 r0 = sR[2 * ip], r1 = sR[2 * ip + 1];
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                if (j == 0) anal_acc<SPIN, true, true>(v, G[j], st[j].pc, st[j].mc);
+                else anal_acc<SPIN, true, false>(v, G[j], st[j].pc, st[j].mc);
+                rec_step<SPIN>(st[j], r0.x, r0.y);
+                if (j == 0) anal_acc<SPIN, false, true>(v + NV, G[j], st[j].pc, st[j].mc);
+                else anal_acc<SPIN, false, false>(v + NV, G[j], st[j].pc, st[j].mc);
+                rec_step<SPIN>(st[j], r1.x, r1.y);
+            }
+            const double s = warp_fold<NVAL>(v, lane);
+            if (writer) myPart[ip * NVAL + vidx] = s;
+        }
+        __syncthreads();
+        // sum over the warps of the block, one deterministic partial per chunk
+        for (int i = tid; i < ni * NV; i += LEG_NT) {
+            double s = 0.0;
+#pragma unroll
+            for (int ww = 0; ww < LEG_NW; ++ww) s += sPart[ww][i];
+            partial[((int64_t)blockIdx.x * P.nalm + base + lt) * NV + i] = s;
+        }
+    }
+}
+
+// Combine the per-chunk partials: alm = post(l,m) * sum_chunks, converted to the requested layout.
+template <int SPIN>
+__global__ void leg_finish_kernel(PlanDev P, const double* __restrict__ partial, int nchunk, double* __restrict__ almE,
+                                  double* __restrict__ almB, int layout, const double* __restrict__ fl, double scale,
+                                  int accumulate)
+{
+    constexpr int NV = SPIN ? 4 : 2;
+    const int L = P.lmax, m = blockIdx.y;
+    const int l = m + blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > L) return;
+    const int64_t id = (int64_t)m * (2 * L + 1 - m) / 2 + l;
+    double v[NV];
+#pragma unroll
+    for (int c = 0; c < NV; ++c) v[c] = 0.0;
+    if (l >= SPIN) {
+        for (int k = 0; k < nchunk; ++k) {
+            const double* q = partial + ((int64_t)k * P.nalm + id) * NV;
+#pragma unroll
+            for (int c = 0; c < NV; ++c) v[c] += q[c];
+        }
+        double post = scale * (SPIN ? -0.5 * P.alpha2[id] : P.alpha0[id]);
+        if (fl) post *= fl[l];
+        if (layout == GS_ALM_REAL && m > 0) post *= 1.41421356237309504880;
+#pragma unroll
+        for (int c = 0; c < NV; ++c) v[c] *= post;
+    }
+    if (layout == GS_ALM_COMPLEX) {
+        double2* E = reinterpret_cast<double2*>(almE);
+        double2 e = make_double2(v[0], v[1]);
+        if (accumulate) { double2 o = E[id]; e.x += o.x; e.y += o.y; }
+        E[id] = e;
+        if (SPIN) {
+            double2* B = reinterpret_cast<double2*>(almB);
+            double2 b = make_double2(v[2], v[3]);
+            if (accumulate) { double2 o = B[id]; b.x += o.x; b.y += o.y; }
+            B[id] = b;
+        }
+    } else if (m == 0) {
+        almE[l] = accumulate ? almE[l] + v[0] : v[0];
+        if (SPIN) almB[l] = accumulate ? almB[l] + v[2] : v[2];
+    } else {
+        const int64_t off = 2 * id - (L + 1);
+        almE[off] = accumulate ? almE[off] + v[0] : v[0];
+        almE[off + 1] = accumulate ? almE[off + 1] + v[1] : v[1];
+        if (SPIN) {
+            almB[off] = accumulate ? almB[off] + v[2] : v[2];
+            almB[off + 1] = accumulate ? almB[off + 1] + v[3] : v[3];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ host launchers
+int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, int layout, const double* fl,
+                 cudaStream_t st)
+{
+    dim3 grid((p->d.npair + LEG_NT * LEG_R - 1) / (LEG_NT * LEG_R), p->d.lmax + 1);
+    if (spin == 0) leg_synth_kernel<0, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, p->Fm);
+    else leg_synth_kernel<2, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, p->Fm);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+int gs_leg_anal(gs_plan* p, int spin, double* almE, double* almB, int layout, const double* fl, double scale,
+                int accumulate, cudaStream_t st)
+{
+    const int nchunk = (p->d.npair + LEG_NT * LEG_R - 1) / (LEG_NT * LEG_R);
+    if (nchunk > p->anal_chunks) { gs_set_error("gs_leg_anal: workspace too small"); return GS_E_BADARG; }
+    dim3 grid(nchunk, p->d.lmax + 1);
+    dim3 fgrid((p->d.lmax + 256) / 256, p->d.lmax + 1);
+    if (spin == 0) {
+        leg_anal_kernel<0, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial);
+        GS_CHECK_LAUNCH();
+        leg_finish_kernel<0><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate);
+    } else {
+        leg_anal_kernel<2, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial);
+        GS_CHECK_LAUNCH();
+        leg_finish_kernel<2><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate);
+    }
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}

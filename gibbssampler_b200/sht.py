@@ -1,0 +1,118 @@
+"""Device-resident spherical-harmonic transforms: thin torch-tensor front-end of the C ABI.
+
+The methods mirror the healpy calls of the reference but take and return CUDA
+float64 / complex128 tensors that stay in HBM; nothing here computes on the CPU.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import GS_ALM_COMPLEX, GS_ALM_REAL, check
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Plan:
+    """Geometry + recurrence tables + workspace for one (nside, lmax) on one GPU."""
+
+    _cache = {}
+
+    def __init__(self, nside, lmax, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.GibbsB200Error("gibbssampler_b200 needs a CUDA device (no CPU fallback)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.nside, self.lmax = int(nside), int(lmax)
+        self._h = C.c_void_p()
+        check(_lib.lib().gs_plan_create(C.byref(self._h), self.nside, self.lmax, self.device.index))
+        self.npix = 12 * self.nside ** 2
+        self.nalm = (self.lmax + 1) * (self.lmax + 2) // 2
+        self.nreal = (self.lmax + 1) ** 2
+
+    @classmethod
+    def get(cls, nside, lmax, device=None):
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        key = (int(nside), int(lmax), dev.index)
+        if key not in cls._cache:
+            cls._cache[key] = cls(nside, lmax, dev)
+        return cls._cache[key]
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().gs_plan_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _alm_in(self, a):
+        """-> (contiguous tensor, layout flag)"""
+        if a.dtype == torch.complex128:
+            assert a.numel() == self.nalm, "complex alm must have (L+1)(L+2)/2 entries"
+            return a.contiguous(), GS_ALM_COMPLEX
+        assert a.dtype == torch.float64 and a.numel() == self.nreal, "real-layout alm must have (L+1)^2 float64 entries"
+        return a.contiguous(), GS_ALM_REAL
+
+    def _alm_out(self, layout):
+        if layout == GS_ALM_COMPLEX:
+            return torch.empty(self.nalm, dtype=torch.complex128, device=self.device)
+        return torch.empty(self.nreal, dtype=torch.float64, device=self.device)
+
+    def _fl(self, fl):
+        if fl is None:
+            return None
+        fl = torch.as_tensor(fl, dtype=torch.float64, device=self.device).contiguous()
+        assert fl.numel() == self.lmax + 1
+        return fl
+
+    # ------------------------------------------------------------------ transforms
+    def alm2map(self, alm, fl=None, out=None):
+        """hp.alm2map(alm, nside, lmax) of one spin-0 field (complex or real-layout alm)."""
+        a, lay = self._alm_in(alm)
+        fl = self._fl(fl)
+        m = torch.empty(self.npix, dtype=torch.float64, device=self.device) if out is None else out
+        check(_lib.lib().gs_alm2map_spin0(self._h, _ptr(a), lay, _ptr(fl), _ptr(m), _stream()))
+        return m
+
+    def alm2map_spin2(self, almE, almB, fl=None, out=None):
+        """(Q, U) of hp.alm2map([0, E, B], pol=True)."""
+        e, lay = self._alm_in(almE)
+        b, lay2 = self._alm_in(almB)
+        assert lay == lay2
+        fl = self._fl(fl)
+        if out is None:
+            q = torch.empty(self.npix, dtype=torch.float64, device=self.device)
+            u = torch.empty(self.npix, dtype=torch.float64, device=self.device)
+        else:
+            q, u = out
+        check(_lib.lib().gs_alm2map_spin2(self._h, _ptr(e), _ptr(b), lay, _ptr(fl), _ptr(q), _ptr(u), _stream()))
+        return q, u
+
+    def map2alm(self, m, iter=0, adjoint=False, pixw=None, fl=None, real_layout=False):
+        """hp.map2alm(m, lmax, iter=iter, use_weights=False); adjoint=True -> A^T m."""
+        m = m.contiguous()
+        assert m.dtype == torch.float64 and m.numel() == self.npix
+        lay = GS_ALM_REAL if real_layout else GS_ALM_COMPLEX
+        a = self._alm_out(lay)
+        fl = self._fl(fl)
+        check(_lib.lib().gs_map2alm_spin0(self._h, _ptr(m), _ptr(pixw), int(iter), int(bool(adjoint)), _ptr(fl),
+                                          _ptr(a), lay, _stream()))
+        return a
+
+    def map2alm_spin2(self, q, u, iter=0, adjoint=False, pixw=None, fl=None, real_layout=False):
+        """(E, B) of hp.map2alm([0, Q, U], lmax, pol=True, iter=iter, use_weights=False)."""
+        q, u = q.contiguous(), u.contiguous()
+        assert q.dtype == torch.float64 and q.numel() == self.npix and u.numel() == self.npix
+        lay = GS_ALM_REAL if real_layout else GS_ALM_COMPLEX
+        e, b = self._alm_out(lay), self._alm_out(lay)
+        fl = self._fl(fl)
+        check(_lib.lib().gs_map2alm_spin2(self._h, _ptr(q), _ptr(u), _ptr(pixw), int(iter), int(bool(adjoint)),
+                                          _ptr(fl), _ptr(e), _ptr(b), lay, _stream()))
+        return e, b
