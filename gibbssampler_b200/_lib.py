@@ -41,6 +41,19 @@ SIGNATURES = {
     "gs_unfold_bins": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
     "gs_almxfl": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "gs_alm2cl": (_i, [_vp, _i, _i, _vp, _vp]),
+    "gs_alm2map_spin2_fl2": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp]),
+    "gs_cr_rhs_pol": (_i, [_vp] * 14 + [_i, _vp, _vp, _vp]),
+    "gs_cr_pcg_pol": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp, _i, _d, _i, _i,
+                           C.POINTER(_i), C.POINTER(_d), _vp]),
+    "gs_cr_apply_q_pol": (_i, [_vp] * 10),
+    "gs_cr_direct": (_i, [_vp, _vp, _vp, _vp, _d, _i, _i, _vp, _vp]),
+    "gs_cls_invgamma": (_i, [_vp, _vp, _i, _vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]),
+    "gs_truncnorm_propose": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "gs_truncnorm_logpdf": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "gs_loglik_pix": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "gs_randn": (_i, [_vp, _i64, C.c_uint64, C.c_uint64, _vp]),
+    "gs_randu": (_i, [_vp, _i64, C.c_uint64, C.c_uint64, _vp]),
+    "gs_sum": (_i, [_vp, _i64, _vp, _vp, _vp]),
 }
 
 

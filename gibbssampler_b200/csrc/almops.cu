@@ -153,6 +153,13 @@ extern "C" int gs_complex_to_real(const double* complex_alm, double* real_alm, i
     return GS_OK;
 }
 
+int gs_launch_expand_per_l(const double* x, int lmax, int mode, double* out, cudaStream_t st)
+{
+    expand_per_l_kernel<<<ew_blocks((int64_t)(lmax + 1) * (lmax + 1)), EW_NT, 0, st>>>(x, out, lmax, mode);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
 extern "C" int gs_expand_per_l(const double* x, int lmax, int mode, double* out, void* stream)
 {
     GS_REQUIRE(x && out && lmax >= 0 && mode >= 0 && mode <= 4, "bad arguments");
@@ -212,6 +219,16 @@ extern "C" int gs_alm2map_spin2(gs_plan* p, const double* almE, const double* al
     if (rc) return rc;
     GS_REQUIRE(almE && almB && mapQ && mapU && (layout == GS_ALM_COMPLEX || layout == GS_ALM_REAL), "bad arguments");
     if ((rc = gs_leg_synth(p, 2, almE, almB, layout, fl, STREAM(stream)))) return rc;
+    return gs_ring_synth(p, 2, mapQ, mapU, STREAM(stream));
+}
+
+extern "C" int gs_alm2map_spin2_fl2(gs_plan* p, const double* almE, const double* almB, int layout, const double* flE,
+                                    const double* flB, double* mapQ, double* mapU, void* stream)
+{
+    int rc = check_plan(p);
+    if (rc) return rc;
+    GS_REQUIRE(almE && almB && mapQ && mapU && flE && flB && (layout == GS_ALM_COMPLEX || layout == GS_ALM_REAL), "bad arguments");
+    if ((rc = gs_leg_synth(p, 2, almE, almB, layout, flE, STREAM(stream), nullptr, flB))) return rc;
     return gs_ring_synth(p, 2, mapQ, mapU, STREAM(stream));
 }
 

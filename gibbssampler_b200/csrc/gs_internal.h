@@ -108,11 +108,15 @@ struct gs_plan {
 static inline int64_t gs_nalm(int lmax) { return (int64_t)(lmax + 1) * (lmax + 2) / 2; }
 
 // legendre.cu
+// `skip` (nullable device int): when *skip != 0 the kernels return immediately (device-side early exit)
 int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, int layout, const double* fl,
-                 cudaStream_t st);
+                 cudaStream_t st, const int* skip = nullptr, const double* flB = nullptr);
 int gs_leg_anal(gs_plan* p, int spin, double* almE, double* almB, int layout, const double* fl, double scale,
-                int accumulate, cudaStream_t st);
+                int accumulate, cudaStream_t st, const int* skip = nullptr);
 // ringfft.cu
 int gs_ring_setup(gs_plan* p);
-int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st);
-int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, const double* pixw, cudaStream_t st);
+int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st, const int* skip = nullptr);
+int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, const double* pixw, cudaStream_t st,
+                 const int* skip = nullptr);
+// almops.cu
+int gs_launch_expand_per_l(const double* x, int lmax, int mode, double* out, cudaStream_t st);

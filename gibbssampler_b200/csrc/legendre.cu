@@ -132,8 +132,8 @@ __device__ __forceinline__ void rescale_check(RingState<SPIN>& s)
 // ------------------------------------------------------------------ staging of one l-tile
 template <int SPIN>
 __device__ __forceinline__ void stage_alm_tile(const PlanDev& P, int m, int lt, int64_t base, const double* almE,
-                                               const double* almB, int layout, const double* fl, double2* sE,
-                                               double2* sB, double2* sR)
+                                               const double* almB, int layout, const double* fl, const double* flB,
+                                               double2* sE, double2* sB, double2* sR)
 {
     const int L = P.lmax;
     for (int i = threadIdx.x; i < LEG_TL; i += LEG_NT) {
@@ -142,7 +142,9 @@ __device__ __forceinline__ void stage_alm_tile(const PlanDev& P, int m, int lt, 
         if (l <= L) {
             const int64_t id = base + l;
             double pre = SPIN ? -0.5 * P.alpha2[id] : P.alpha0[id];
+            double preb = pre;
             if (fl) pre *= fl[l];
+            if (flB) preb *= flB[l]; else preb = pre;
             if (layout == GS_ALM_COMPLEX) {
                 e = reinterpret_cast<const double2*>(almE)[id];
                 if (SPIN) b = reinterpret_cast<const double2*>(almB)[id];
@@ -152,10 +154,11 @@ __device__ __forceinline__ void stage_alm_tile(const PlanDev& P, int m, int lt, 
             } else {
                 const int64_t off = 2 * id - (L + 1);
                 pre *= 0.70710678118654752440;
+                preb *= 0.70710678118654752440;
                 e.x = almE[off]; e.y = almE[off + 1];
                 if (SPIN) { b.x = almB[off]; b.y = almB[off + 1]; }
             }
-            e.x *= pre; e.y *= pre; b.x *= pre; b.y *= pre;
+            e.x *= pre; e.y *= pre; b.x *= preb; b.y *= preb;
             if (SPIN) r = P.rec2[id]; else r.x = P.rec0[id];
         }
         sE[i] = e;
@@ -198,8 +201,10 @@ __device__ __forceinline__ void synth_acc(SynthAcc<SPIN>& A, double pc, double m
 template <int SPIN, int R>
 __global__ void __launch_bounds__(LEG_NT)
 leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __restrict__ almB, int layout,
-                 const double* __restrict__ fl, double2* __restrict__ Fm)
+                 const double* __restrict__ fl, const double* __restrict__ flB, double2* __restrict__ Fm,
+                 const int* __restrict__ skip)
 {
+    if (skip && *skip) return;
     __shared__ double2 sE[LEG_TL], sB[SPIN ? LEG_TL : 1], sR[LEG_TL];
     const int L = P.lmax, m = blockIdx.y, tid = threadIdx.x;
     const int l0 = m > SPIN ? m : SPIN;
@@ -225,7 +230,7 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
 
     for (int lt = l0; lt <= L; lt += LEG_TL) {
         __syncthreads();
-        stage_alm_tile<SPIN>(P, m, lt, base, almE, almB, layout, fl, sE, sB, sR);
+        stage_alm_tile<SPIN>(P, m, lt, base, almE, almB, layout, fl, flB, sE, sB, sR);
         __syncthreads();
         if (!warp_act) continue;
         const int ni = min(LEG_TL, L - lt + 1);
@@ -376,8 +381,9 @@ __device__ __forceinline__ double warp_fold(double* v, int lane)
 
 template <int SPIN, int R>
 __global__ void __launch_bounds__(LEG_NT)
-leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ partial)
+leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ partial, const int* __restrict__ skip)
 {
+    if (skip && *skip) return;
     constexpr int NV = SPIN ? 4 : 2;   // doubles per (l,m)
     constexpr int NVAL = 2 * NV;       // values reduced per pair of l
     __shared__ double2 sR[LEG_TL];
@@ -504,8 +510,9 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
 template <int SPIN>
 __global__ void leg_finish_kernel(PlanDev P, const double* __restrict__ partial, int nchunk, double* __restrict__ almE,
                                   double* __restrict__ almB, int layout, const double* __restrict__ fl, double scale,
-                                  int accumulate)
+                                  int accumulate, const int* __restrict__ skip)
 {
+    if (skip && *skip) return;
     constexpr int NV = SPIN ? 4 : 2;
     const int L = P.lmax, m = blockIdx.y;
     const int l = m + blockIdx.x * blockDim.x + threadIdx.x;
@@ -553,30 +560,30 @@ __global__ void leg_finish_kernel(PlanDev P, const double* __restrict__ partial,
 
 // ------------------------------------------------------------------ host launchers
 int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, int layout, const double* fl,
-                 cudaStream_t st)
+                 cudaStream_t st, const int* skip, const double* flB)
 {
     dim3 grid((p->d.npair + LEG_NT * LEG_R - 1) / (LEG_NT * LEG_R), p->d.lmax + 1);
-    if (spin == 0) leg_synth_kernel<0, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, p->Fm);
-    else leg_synth_kernel<2, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, p->Fm);
+    if (spin == 0) leg_synth_kernel<0, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip);
+    else leg_synth_kernel<2, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip);
     GS_CHECK_LAUNCH();
     return GS_OK;
 }
 
 int gs_leg_anal(gs_plan* p, int spin, double* almE, double* almB, int layout, const double* fl, double scale,
-                int accumulate, cudaStream_t st)
+                int accumulate, cudaStream_t st, const int* skip)
 {
     const int nchunk = (p->d.npair + LEG_NT * LEG_R - 1) / (LEG_NT * LEG_R);
     if (nchunk > p->anal_chunks) { gs_set_error("gs_leg_anal: workspace too small"); return GS_E_BADARG; }
     dim3 grid(nchunk, p->d.lmax + 1);
     dim3 fgrid((p->d.lmax + 256) / 256, p->d.lmax + 1);
     if (spin == 0) {
-        leg_anal_kernel<0, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial);
+        leg_anal_kernel<0, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip);
         GS_CHECK_LAUNCH();
-        leg_finish_kernel<0><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate);
+        leg_finish_kernel<0><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip);
     } else {
-        leg_anal_kernel<2, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial);
+        leg_anal_kernel<2, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip);
         GS_CHECK_LAUNCH();
-        leg_finish_kernel<2><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate);
+        leg_finish_kernel<2><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip);
     }
     GS_CHECK_LAUNCH();
     return GS_OK;

@@ -155,8 +155,9 @@ __device__ __forceinline__ double2 ring_phase(const PlanDev& P, int ring, int m)
 
 __global__ void __launch_bounds__(RF_NT)
 ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __restrict__ Fm, double* __restrict__ mapQ,
-                  double* __restrict__ mapU)
+                  double* __restrict__ mapU, const int* __restrict__ skip)
 {
+    if (skip && *skip) return;
     extern __shared__ double2 smem[];
     const int L = P.lmax, nm = L + 1;
     const RingJob job = jobs[blockIdx.x];
@@ -201,8 +202,9 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __
 
 __global__ void __launch_bounds__(RF_NT)
 ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double* __restrict__ mapQ, const double* __restrict__ mapU,
-                 const double* __restrict__ pixw, double2* __restrict__ Fm)
+                 const double* __restrict__ pixw, double2* __restrict__ Fm, const int* __restrict__ skip)
 {
+    if (skip && *skip) return;
     extern __shared__ double2 smem[];
     const int L = P.lmax, nm = L + 1;
     const RingJob job = jobs[blockIdx.x];
@@ -308,18 +310,19 @@ int gs_ring_setup(gs_plan* p)
     return GS_OK;
 }
 
-int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st)
+int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st, const int* skip)
 {
-    if (spin == 0) ring_synth_kernel<<<p->njobs0, RF_NT, p->ring_smem, st>>>(p->d, p->jobs0, p->Fm, mapQ, mapQ);
-    else ring_synth_kernel<<<p->njobs2, RF_NT, p->ring_smem, st>>>(p->d, p->jobs2, p->Fm, mapQ, mapU);
+    if (spin == 0) ring_synth_kernel<<<p->njobs0, RF_NT, p->ring_smem, st>>>(p->d, p->jobs0, p->Fm, mapQ, mapQ, skip);
+    else ring_synth_kernel<<<p->njobs2, RF_NT, p->ring_smem, st>>>(p->d, p->jobs2, p->Fm, mapQ, mapU, skip);
     GS_CHECK_LAUNCH();
     return GS_OK;
 }
 
-int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, const double* pixw, cudaStream_t st)
+int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, const double* pixw, cudaStream_t st,
+                 const int* skip)
 {
-    if (spin == 0) ring_anal_kernel<<<p->njobs0, RF_NT, p->ring_smem, st>>>(p->d, p->jobs0, mapQ, mapQ, pixw, p->Fm);
-    else ring_anal_kernel<<<p->njobs2, RF_NT, p->ring_smem, st>>>(p->d, p->jobs2, mapQ, mapU, pixw, p->Fm);
+    if (spin == 0) ring_anal_kernel<<<p->njobs0, RF_NT, p->ring_smem, st>>>(p->d, p->jobs0, mapQ, mapQ, pixw, p->Fm, skip);
+    else ring_anal_kernel<<<p->njobs2, RF_NT, p->ring_smem, st>>>(p->d, p->jobs2, mapQ, mapU, pixw, p->Fm, skip);
     GS_CHECK_LAUNCH();
     return GS_OK;
 }

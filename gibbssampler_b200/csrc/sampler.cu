@@ -1,0 +1,318 @@
+// Random draws, diagonal (full-sky isotropic) constrained realizations and the C_l conditional
+// samplers.  All HBM-bound single-pass kernels; every
+// reduction uses a fixed summation order.
+#include <math.h>
+
+#include <algorithm>
+
+#include "gs_internal.h"
+
+#define SM_NT 256
+#define SM_GRID (148 * 4)
+
+// ------------------------------------------------------------------ Philox4x32-10 counter RNG
+struct Philox {
+    uint32_t k0, k1;
+    __device__ Philox(uint64_t seed) : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)) {}
+    __device__ uint4 operator()(uint64_t ctr, uint64_t stream) const
+    {
+        uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = (uint32_t)stream, c3 = (uint32_t)(stream >> 32);
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+            const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+            const uint32_t n0 = hi1 ^ c1 ^ a, n2 = hi0 ^ c3 ^ b;
+            c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        return make_uint4(c0, c1, c2, c3);
+    }
+};
+
+__device__ __forceinline__ double u01(uint32_t hi, uint32_t lo)
+{  // uniform in (0,1): 53 random bits, centred
+    const uint64_t x = (((uint64_t)hi << 32) | lo) >> 11;
+    return ((double)x + 0.5) * 0x1p-53;
+}
+
+__device__ __forceinline__ void box_muller(uint4 r, double& n0, double& n1)
+{
+    const double u1 = u01(r.x, r.y), u2 = u01(r.z, r.w);
+    const double rad = sqrt(-2.0 * log(u1));
+    double s, c;
+    sincospi(2.0 * u2, &s, &c);
+    n0 = rad * c;
+    n1 = rad * s;
+}
+
+__global__ void randn_kernel(double* __restrict__ out, int64_t n, uint64_t seed, uint64_t stream)
+{
+    const Philox ph(seed);
+    const int64_t npair = (n + 1) >> 1;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npair; i += (int64_t)gridDim.x * blockDim.x) {
+        double a, b;
+        box_muller(ph((uint64_t)i, stream), a, b);
+        out[2 * i] = a;
+        if (2 * i + 1 < n) out[2 * i + 1] = b;
+    }
+}
+
+__global__ void randu_kernel(double* __restrict__ out, int64_t n, uint64_t seed, uint64_t stream)
+{
+    const Philox ph(seed);
+    const int64_t npair = (n + 1) >> 1;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < npair; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 r = ph((uint64_t)i, stream);
+        out[2 * i] = u01(r.x, r.y);
+        if (2 * i + 1 < n) out[2 * i + 1] = u01(r.z, r.w);
+    }
+}
+
+// ------------------------------------------------------------------ deterministic reductions
+// out[k] = sum_i f_k(i), NR values, two launches (partials, then a single block)
+template <int NR>
+__device__ __forceinline__ void block_sum(double (&v)[NR], double* dst)
+{
+    __shared__ double sm[NR][SM_NT / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+        double s = v[k];
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) sm[k][w] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NR) {
+        double s = 0.0;
+        for (int i = 0; i < SM_NT / 32; ++i) s += sm[threadIdx.x][i];
+        dst[threadIdx.x] = s;
+    }
+}
+
+__global__ void __launch_bounds__(SM_NT) sum_partial_kernel(const double* __restrict__ a, int64_t n, double* __restrict__ partials)
+{
+    double v[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) v[0] += a[i];
+    block_sum<1>(v, partials + blockIdx.x);
+}
+
+// -1/2 sum_p N^-1_p [ (dQ - mQ)^2 + (dU - mU)^2 ]   (NonCenteredGibbs.py:353-355); mU/dU nullable (TT: ClsSampler.py:107-108)
+__global__ void __launch_bounds__(SM_NT)
+chi2_partial_kernel(const double* __restrict__ dQ, const double* __restrict__ dU, const double* __restrict__ mQ,
+                    const double* __restrict__ mU, const double* __restrict__ invn, int64_t n, double* __restrict__ partials)
+{
+    double v[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = dQ[i] - mQ[i];
+        double s = a * a;
+        if (dU) { const double b = dU[i] - mU[i]; s = fma(b, b, s); }
+        v[0] = fma(s, invn[i], v[0]);
+    }
+    block_sum<1>(v, partials + blockIdx.x);
+}
+
+__global__ void __launch_bounds__(SM_NT) final_sum_kernel(const double* __restrict__ partials, int np, double scale, double* __restrict__ out)
+{
+    double v[1] = {0.0};
+    for (int i = threadIdx.x; i < np; i += blockDim.x) v[0] += partials[i];
+    __shared__ double res[1];
+    block_sum<1>(v, res);
+    __syncthreads();
+    if (threadIdx.x == 0) out[0] = scale * res[0];
+}
+
+// ------------------------------------------------------------------ diagonal constrained realizations
+// l of real-layout index (same mapping as almops.cu)
+__device__ __forceinline__ int l_of_real(int64_t i, int L)
+{
+    if (i <= L) return (int)i;
+    const int64_t id = (i + L + 1) >> 1;
+    const double b = 2.0 * L + 3.0;
+    int mm = (int)floor((b - sqrt(b * b - 8.0 * (double)id)) * 0.5);
+    if (mm < 0) mm = 0;
+    if (mm > L) mm = L;
+    while (mm > 0 && (int64_t)mm * (2 * L + 1 - mm) / 2 + mm > id) --mm;
+    while (mm < L && (int64_t)(mm + 1) * (2 * L + 1 - (mm + 1)) / 2 + (mm + 1) <= id) ++mm;
+    return (int)(id - (int64_t)mm * (2 * L + 1 - mm) / 2);
+}
+
+// mode 0: PolarizedCenteredConstrainedRealization.sample_no_mask (CenteredGibbs.py:317-353)
+//         sigma = 1/(Npix/(noise 4pi) b^2 + 1/C); s = sigma b (Npix/(noise 4pi)) d + xi sqrt(sigma)
+// mode 1: PolarizedNonCenteredConstrainedRealization.sample_no_mask, all_sph (NonCenteredGibbs.py:138-176)
+//         sigma = 1/(1 + b^2 C Npix/(noise 4pi)); s = sigma sqrt(C) b (Npix/(noise 4pi)) d + xi sqrt(sigma)
+__global__ void cr_direct_kernel(const double* __restrict__ dl, const double* __restrict__ bl, const double* __restrict__ d_alm,
+                                 const double* __restrict__ xi, double w, int L, int mode, double* __restrict__ out)
+{
+    const int64_t n = (int64_t)(L + 1) * (L + 1);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int l = l_of_real(i, L);
+        double c = dl[l];
+        if (l) c = c * 2.0 * 3.14159265358979323846 / ((double)l * (double)(l + 1));
+        const double b = bl[l];
+        if (mode == 0) {
+            const double ic = c != 0.0 ? 1.0 / c : 0.0;
+            const double sigma = 1.0 / (w * b * b + ic);
+            out[i] = sigma * (b * (w * d_alm[i])) + xi[i] * sqrt(sigma);
+        } else {
+            const double sigma = 1.0 / (1.0 + b * b * c * w);
+            out[i] = sigma * (sqrt(c) * b * (w * d_alm[i])) + xi[i] * sqrt(sigma);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ inverse-gamma C_l draw
+// Marsaglia-Tsang Gamma(a,1), a > 0, one thread per draw with its own Philox stream
+__device__ double gamma_mt(double a, const Philox& ph, uint64_t stream)
+{
+    uint64_t ctr = 0;
+    double boost = 1.0;
+    if (a < 1.0) {
+        const uint4 r = ph(ctr++, stream);
+        boost = pow(u01(r.x, r.y), 1.0 / a);
+        a += 1.0;
+    }
+    const double d = a - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (int it = 0; it < 1000; ++it) {
+        double x, x2;
+        box_muller(ph(ctr++, stream), x, x2);
+        const uint4 r = ph(ctr++, stream);
+        const double u = u01(r.x, r.y);
+        double v = 1.0 + c * x;
+        if (v <= 0.0) { x = x2; v = 1.0 + c * x; if (v <= 0.0) continue; }
+        v = v * v * v;
+        if (log(u) < 0.5 * x * x + d * (1.0 - v + log(v))) return boost * d * v;
+    }
+    return boost * d;
+}
+
+// PolarizedCenteredClsSampler.sample_one_pol / CenteredClsSampler.sample (CenteredGibbs.py:24-79):
+//   beta_l = (2l+1) l (l+1) Chat_l / (4 pi); per bin: beta = sum beta_l, alpha = sum (2l+1)/2 - 1;
+//   alpha[0] := 1; D_bin = beta / Gamma(alpha, 1); D[:2] := 0.
+// gamma_inject (nullable): Gamma(alpha,1) variates drawn by the caller (parity with numpy's stream).
+__global__ void cls_invgamma_kernel(const double* __restrict__ cl_hat, const int* __restrict__ bins, int nbins,
+                                    const double* __restrict__ gamma_inject, uint64_t seed, uint64_t call,
+                                    double* __restrict__ out, double* __restrict__ alpha_out, double* __restrict__ beta_out)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbins) return;
+    double beta = 0.0, ex = 0.0;
+    for (int l = bins[b]; l < bins[b + 1]; ++l) {
+        beta += (2.0 * l + 1.0) * (double)l * (double)(l + 1) * (cl_hat[l] / (4.0 * 3.14159265358979323846));
+        ex += (2.0 * l + 1.0) / 2.0;
+    }
+    double alpha = ex - 1.0;
+    if (b == 0) alpha = 1.0;
+    if (alpha_out) alpha_out[b] = alpha;
+    if (beta_out) beta_out[b] = beta;
+    double g;
+    if (gamma_inject) g = gamma_inject[b];
+    else g = alpha > 0.0 ? gamma_mt(alpha, Philox(seed), (call << 20) + (uint64_t)b) : 1.0;
+    out[b] = (b < 2) ? 0.0 : beta / g;
+}
+
+// ------------------------------------------------------------------ truncated-normal proposals
+// scipy.stats.truncnorm(a = -loc/scale, b = inf, loc, scale) on [0, inf): rvs by inverse CDF of a
+// uniform, and logpdf (ClsSampler.py:79-92, NonCenteredGibbs.py:292-330).  Entry j <-> bin j + 2.
+__global__ void truncnorm_propose_kernel(const double* __restrict__ dl_old, const double* __restrict__ prop_var, int nbins,
+                                         const double* __restrict__ u, double* __restrict__ dl_new)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbins) return;
+    if (b < 2) { dl_new[b] = 0.0; return; }
+    const double loc = dl_old[b], sc = sqrt(prop_var[b - 2]), a = -loc / sc, q = u[b - 2];
+    double t;
+    if (a < 0.0) { const double pa = normcdf(a); t = normcdfinv(fma(q, 1.0 - pa, pa)); }
+    else { const double sa = normcdf(-a); t = -normcdfinv((1.0 - q) * sa); }
+    dl_new[b] = fmax(loc + sc * t, 0.0);
+}
+
+// logpdf(x; loc = from, scale) - used as log q(from -> x); out[0], out[1] = 0
+__global__ void truncnorm_logpdf_kernel(const double* __restrict__ x, const double* __restrict__ from,
+                                        const double* __restrict__ prop_var, int nbins, double* __restrict__ out)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbins) return;
+    if (b < 2) { out[b] = 0.0; return; }
+    const double loc = from[b], sc = sqrt(prop_var[b - 2]), a = -loc / sc, t = (x[b] - loc) / sc;
+    const double logz = log(normcdf(-a));  // log(1 - Phi(a))
+    out[b] = (x[b] < 0.0) ? -INFINITY : -0.5 * t * t - 0.91893853320467274178 - log(sc) - logz;
+}
+
+// ------------------------------------------------------------------ C ABI
+#define STREAM(s) ((cudaStream_t)(s))
+static inline int nblk(int64_t n) { return (int)std::min<int64_t>((n + SM_NT - 1) / SM_NT, SM_GRID); }
+
+extern "C" int gs_randn(double* out, int64_t n, uint64_t seed, uint64_t stream_id, void* stream)
+{
+    GS_REQUIRE(out && n >= 0, "bad arguments");
+    if (n == 0) return GS_OK;
+    randn_kernel<<<nblk((n + 1) / 2), SM_NT, 0, STREAM(stream)>>>(out, n, seed, stream_id);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+extern "C" int gs_randu(double* out, int64_t n, uint64_t seed, uint64_t stream_id, void* stream)
+{
+    GS_REQUIRE(out && n >= 0, "bad arguments");
+    if (n == 0) return GS_OK;
+    randu_kernel<<<nblk((n + 1) / 2), SM_NT, 0, STREAM(stream)>>>(out, n, seed, stream_id);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+extern "C" int gs_sum(const double* a, int64_t n, double* scratch, double* out, void* stream)
+{
+    GS_REQUIRE(a && scratch && out && n >= 0, "bad arguments (scratch needs 592 doubles)");
+    sum_partial_kernel<<<SM_GRID, SM_NT, 0, STREAM(stream)>>>(a, n, scratch);
+    final_sum_kernel<<<1, SM_NT, 0, STREAM(stream)>>>(scratch, SM_GRID, 1.0, out);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+extern "C" int gs_loglik_pix(const double* d_Q, const double* d_U, const double* m_Q, const double* m_U,
+                             const double* inv_noise, int64_t npix, double* scratch, double* out, void* stream)
+{
+    GS_REQUIRE(d_Q && m_Q && inv_noise && scratch && out && npix > 0 && ((d_U == nullptr) == (m_U == nullptr)), "bad arguments");
+    chi2_partial_kernel<<<SM_GRID, SM_NT, 0, STREAM(stream)>>>(d_Q, d_U, m_Q, m_U, inv_noise, npix, scratch);
+    final_sum_kernel<<<1, SM_NT, 0, STREAM(stream)>>>(scratch, SM_GRID, -0.5, out);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+extern "C" int gs_cr_direct(const double* dl, const double* bl, const double* d_alm, const double* xi, double npix_over_noise_4pi,
+                            int lmax, int mode, double* out, void* stream)
+{
+    GS_REQUIRE(dl && bl && d_alm && xi && out && lmax >= 0 && (mode == 0 || mode == 1), "bad arguments");
+    cr_direct_kernel<<<nblk((int64_t)(lmax + 1) * (lmax + 1)), SM_NT, 0, STREAM(stream)>>>(dl, bl, d_alm, xi, npix_over_noise_4pi, lmax, mode, out);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+extern "C" int gs_cls_invgamma(const double* cl_hat, const int* bins, int nbins, const double* gamma_inject,
+                               uint64_t seed, uint64_t call, double* dl_binned, double* alpha_out, double* beta_out,
+                               void* stream)
+{
+    GS_REQUIRE(cl_hat && bins && dl_binned && nbins >= 1, "bad arguments");
+    cls_invgamma_kernel<<<(nbins + 127) / 128, 128, 0, STREAM(stream)>>>(cl_hat, bins, nbins, gamma_inject, seed, call, dl_binned, alpha_out, beta_out);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+extern "C" int gs_truncnorm_propose(const double* dl_old, const double* prop_var, int nbins, const double* u,
+                                    double* dl_new, void* stream)
+{
+    GS_REQUIRE(dl_old && prop_var && u && dl_new && nbins >= 2, "bad arguments");
+    truncnorm_propose_kernel<<<(nbins + 127) / 128, 128, 0, STREAM(stream)>>>(dl_old, prop_var, nbins, u, dl_new);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+extern "C" int gs_truncnorm_logpdf(const double* x, const double* from, const double* prop_var, int nbins, double* out,
+                                   void* stream)
+{
+    GS_REQUIRE(x && from && prop_var && out && nbins >= 2, "bad arguments");
+    truncnorm_logpdf_kernel<<<(nbins + 127) / 128, 128, 0, STREAM(stream)>>>(x, from, prop_var, nbins, out);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}

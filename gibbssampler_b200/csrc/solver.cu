@@ -1,0 +1,375 @@
+// Constrained-realization solves.
+//
+//   Q x = b,  Q = C^-1 + B A^T N^-1 A B   (CenteredGibbs.py:448-491 + the forked qcinv's
+//   multigrid_chain.sample / opfilt_pp.fwd_op / diag_cl preconditioner / cd_solve, not vendored)
+//
+// Everything lives in the reference's real alm layout so that dot products are plain sums
+// (= qcinv's (2 - delta_m0)-weighted complex dot).  The mat-vec is the spin-2 SHT pair of
+// legendre.cu / ringfft.cu with b_l fused into the Legendre staging on both sides and N^-1 fused
+// into the ring-analysis load; the vector updates are three fused HBM-bound kernels whose
+// reductions finish on the device (last-block pattern, fixed summation order => bit-reproducible),
+// so alpha/beta and the convergence flag never travel to the host inside the loop; once the flag
+// is set every later kernel (SHT stages included) returns immediately.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "gs_internal.h"
+
+#define SV_NT 256
+#define SV_GRID (148 * 4)
+
+struct PcgState {
+    double delta, pq, rr, rz, d0, alpha, beta, eps2;
+    int iter, itermax, done;
+    unsigned counter;
+};
+
+struct gs_pcg_ws {
+    double *r[2], *p[2], *q[2], *invc[2], *pre[2];
+    double* partials;  // SV_GRID * 2
+    PcgState* state;
+    PcgState* host_state;  // pinned
+};
+
+// block-level sum of NR values, then the last block to finish adds the per-block partials in a
+// fixed order.  Returns true (in every thread of that last block) with the totals in tot[].
+template <int NR>
+__device__ bool grid_reduce(double (&v)[NR], double* partials, unsigned* counter, double (&tot)[NR])
+{
+    __shared__ double sm[NR][SV_NT / 32];
+    __shared__ bool last;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+        double s = v[k];
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) sm[k][w] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+            double s = 0.0;
+            for (int i = 0; i < SV_NT / 32; ++i) s += sm[k][i];
+            partials[blockIdx.x * NR + k] = s;
+        }
+        __threadfence();
+        const unsigned t = atomicInc(counter, gridDim.x - 1);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return false;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += partials[i * NR + k];
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        __syncthreads();
+        if (lane == 0) sm[k][w] = s;
+        __syncthreads();
+        double t = 0.0;
+        for (int i = 0; i < SV_NT / 32; ++i) t += sm[k][i];
+        tot[k] = t;
+    }
+    return true;
+}
+
+// diag_cl preconditioner of qcinv's opfilt_pp: M_l = 1 / (1/C_l + b_l^2 sum(N^-1)/(4 pi))
+__global__ void precond_kernel(const double* __restrict__ dl, const double* __restrict__ bl, double ninv, int L,
+                               double* __restrict__ invc_l, double* __restrict__ pre_l)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > L) return;
+    double c = dl[l];
+    if (l) c = c * 2.0 * 3.14159265358979323846 / ((double)l * (double)(l + 1));
+    const double ic = c != 0.0 ? 1.0 / c : 0.0;
+    const double d = ic + bl[l] * bl[l] * ninv;
+    invc_l[l] = ic;
+    pre_l[l] = d != 0.0 ? 1.0 / d : 0.0;
+}
+
+__device__ __forceinline__ void pick(int64_t i, int64_t n, int& c, int64_t& j)
+{
+    c = i >= n;
+    j = c ? i - n : i;
+}
+
+// r = b - q (q = Q x0, or q absent for x0 = 0), p = M r, delta = <r, M r>, d0 = rr = <r, r>
+__global__ void __launch_bounds__(SV_NT)
+pcg_init_kernel(gs_pcg_ws W, const double* bE, const double* bB, int have_q, int64_t n)
+{
+    double v[2] = {0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 2 * n; i += (int64_t)gridDim.x * blockDim.x) {
+        int c; int64_t j;
+        pick(i, n, c, j);
+        double r = (c ? bB : bE)[j];
+        if (have_q) r -= W.q[c][j];
+        const double z = W.pre[c][j] * r;
+        W.r[c][j] = r;
+        W.p[c][j] = z;
+        v[0] += r * r;
+        v[1] += r * z;
+    }
+    double tot[2];
+    if (grid_reduce<2>(v, W.partials, &W.state->counter, tot) && threadIdx.x == 0) {
+        PcgState* s = W.state;
+        s->rr = tot[0]; s->d0 = tot[0]; s->delta = tot[1]; s->iter = 0;
+        s->done = (tot[0] <= 0.0 || s->itermax <= 0) ? 1 : 0;
+    }
+}
+
+// q += C^-1 p ; pq = <p, q> ; alpha = delta / pq
+__global__ void __launch_bounds__(SV_NT) pcg_apq_kernel(gs_pcg_ws W, int64_t n)
+{
+    if (W.state->done) return;
+    double v[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 2 * n; i += (int64_t)gridDim.x * blockDim.x) {
+        int c; int64_t j;
+        pick(i, n, c, j);
+        const double p = W.p[c][j];
+        const double q = fma(W.invc[c][j], p, W.q[c][j]);
+        W.q[c][j] = q;
+        v[0] += p * q;
+    }
+    double tot[1];
+    if (grid_reduce<1>(v, W.partials, &W.state->counter, tot) && threadIdx.x == 0) {
+        PcgState* s = W.state;
+        s->pq = tot[0];
+        s->alpha = tot[0] != 0.0 ? s->delta / tot[0] : 0.0;
+    }
+}
+
+// x += alpha p ; r -= alpha q ; rr = <r,r> ; rz = <r, M r> ; beta = rz/delta ; convergence test
+__global__ void __launch_bounds__(SV_NT) pcg_update_kernel(gs_pcg_ws W, double* xE, double* xB, int64_t n)
+{
+    if (W.state->done) return;
+    const double alpha = W.state->alpha;
+    double v[2] = {0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 2 * n; i += (int64_t)gridDim.x * blockDim.x) {
+        int c; int64_t j;
+        pick(i, n, c, j);
+        double* x = c ? xB : xE;
+        x[j] = fma(alpha, W.p[c][j], x[j]);
+        const double r = fma(-alpha, W.q[c][j], W.r[c][j]);
+        W.r[c][j] = r;
+        v[0] += r * r;
+        v[1] += r * r * W.pre[c][j];
+    }
+    double tot[2];
+    if (grid_reduce<2>(v, W.partials, &W.state->counter, tot) && threadIdx.x == 0) {
+        PcgState* s = W.state;
+        s->rr = tot[0]; s->rz = tot[1];
+        s->beta = s->delta != 0.0 ? tot[1] / s->delta : 0.0;
+        s->delta = tot[1];
+        s->iter += 1;
+        // qcinv cd_monitors.monitor_basic: stop when <r,r> <= eps^2 <r0,r0> or iter >= iter_max
+        if (tot[0] <= s->eps2 * s->d0 || s->iter >= s->itermax) s->done = 1;
+    }
+}
+
+// p = M r + beta p
+__global__ void __launch_bounds__(SV_NT) pcg_dir_kernel(gs_pcg_ws W, int64_t n)
+{
+    if (W.state->done) return;
+    const double beta = W.state->beta;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 2 * n; i += (int64_t)gridDim.x * blockDim.x) {
+        int c; int64_t j;
+        pick(i, n, c, j);
+        W.p[c][j] = fma(beta, W.p[c][j], W.pre[c][j] * W.r[c][j]);
+    }
+}
+
+__global__ void zero2_kernel(double* a, double* b, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        a[i] = 0.0;
+        b[i] = 0.0;
+    }
+}
+
+// out = a + x * y   (per coefficient, real layout)
+__global__ void axy_kernel(const double* a, const double* __restrict__ x, const double* __restrict__ y, double* out, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = fma(x[i], y[i], a ? a[i] : 0.0);
+}
+
+__global__ void scale_map_kernel(const double* __restrict__ a, const double* __restrict__ w, double* __restrict__ out, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = a[i] * w[i];
+}
+
+__global__ void rhs_combine_kernel(double* rhs, const double* sic, const double* xi, const double* bdata, double resc, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        rhs[i] = fma(resc, rhs[i], fma(sic[i], xi[i], bdata[i]));
+}
+
+// ------------------------------------------------------------------ workspace
+static gs_pcg_ws* get_ws(gs_plan* p)
+{
+    static thread_local std::vector<std::pair<gs_plan*, gs_pcg_ws*>> cache;
+    for (auto& kv : cache) if (kv.first == p) return kv.second;
+    gs_pcg_ws* w = new gs_pcg_ws();
+    const size_t n = (size_t)(p->d.lmax + 1) * (p->d.lmax + 1);
+    auto alloc = [&](double** q, size_t cnt) { void* d = nullptr; if (cudaMalloc(&d, cnt * sizeof(double)) != cudaSuccess) return false; p->owned.push_back(d); *q = (double*)d; return true; };
+    bool ok = true;
+    for (int c = 0; c < 2 && ok; ++c) ok = alloc(&w->r[c], n) && alloc(&w->p[c], n) && alloc(&w->q[c], n) && alloc(&w->invc[c], n) && alloc(&w->pre[c], n);
+    ok = ok && alloc(&w->partials, SV_GRID * 2 + 4 * (size_t)(p->d.lmax + 1));
+    void* d = nullptr;
+    ok = ok && cudaMalloc(&d, sizeof(PcgState)) == cudaSuccess;
+    if (ok) { p->owned.push_back(d); w->state = (PcgState*)d; }
+    ok = ok && cudaMallocHost((void**)&w->host_state, sizeof(PcgState)) == cudaSuccess;
+    if (!ok) { gs_set_error("PCG workspace allocation failed: %s", cudaGetErrorString(cudaGetLastError())); delete w; return nullptr; }
+    cache.push_back({p, w});
+    return w;
+}
+
+// q = B A^T N^-1 A B v   (C^-1 v is added by pcg_apq_kernel / the caller)
+static int apply_noise_op(gs_plan* p, const double* vE, const double* vB, const double* bl, const double* inv_noise,
+                          double* qE, double* qB, cudaStream_t st, const int* skip)
+{
+    int rc;
+    if ((rc = gs_leg_synth(p, 2, vE, vB, GS_ALM_REAL, bl, st, skip))) return rc;
+    if ((rc = gs_ring_synth(p, 2, p->mapQ_tmp, p->mapU_tmp, st, skip))) return rc;
+    if ((rc = gs_ring_anal(p, 2, p->mapQ_tmp, p->mapU_tmp, inv_noise, st, skip))) return rc;
+    return gs_leg_anal(p, 2, qE, qB, GS_ALM_REAL, bl, 1.0, 0, st, skip);
+}
+
+extern "C" int gs_cr_pcg_pol(gs_plan* p, const double* dl_EE, const double* dl_BB, const double* bl,
+                             const double* inv_noise, double ninv_sum_over_4pi, const double* rhs_E,
+                             const double* rhs_B, double* x_E, double* x_B, int warm_start, double eps, int itermax,
+                             int check_every, int* n_iter_out, double* resid_out, void* stream)
+{
+    if (!p) { gs_set_error("null plan"); return GS_E_BADARG; }
+    GS_REQUIRE(dl_EE && dl_BB && bl && inv_noise && rhs_E && rhs_B && x_E && x_B, "null pointer argument");
+    GS_REQUIRE(eps > 0.0 && itermax >= 0, "eps must be > 0 and itermax >= 0");
+    GS_CHECK_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    gs_pcg_ws* w = get_ws(p);
+    if (!w) return GS_E_NOMEM;
+    const int L = p->d.lmax;
+    const int64_t n = (int64_t)(L + 1) * (L + 1);
+    if (check_every < 1) check_every = 8;
+
+    // per-l C^-1 and preconditioner, expanded to the real layout
+    double* tmp_l = w->partials + SV_GRID * 2;  // 4 (L+1) doubles of scratch
+    const int lb = (L + 256) / 256;
+    precond_kernel<<<lb, 256, 0, st>>>(dl_EE, bl, ninv_sum_over_4pi, L, tmp_l, tmp_l + (L + 1));
+    precond_kernel<<<lb, 256, 0, st>>>(dl_BB, bl, ninv_sum_over_4pi, L, tmp_l + 2 * (L + 1), tmp_l + 3 * (L + 1));
+    GS_CHECK_LAUNCH();
+    int rc;
+    if ((rc = gs_launch_expand_per_l(tmp_l, L, 0, w->invc[0], st))) return rc;
+    if ((rc = gs_launch_expand_per_l(tmp_l + (L + 1), L, 0, w->pre[0], st))) return rc;
+    if ((rc = gs_launch_expand_per_l(tmp_l + 2 * (L + 1), L, 0, w->invc[1], st))) return rc;
+    if ((rc = gs_launch_expand_per_l(tmp_l + 3 * (L + 1), L, 0, w->pre[1], st))) return rc;
+
+    PcgState h;
+    memset(&h, 0, sizeof(h));
+    h.eps2 = eps * eps;
+    h.itermax = itermax;
+    *w->host_state = h;
+    GS_CHECK_CUDA(cudaMemcpyAsync(w->state, w->host_state, sizeof(PcgState), cudaMemcpyHostToDevice, st));
+    if (warm_start) {  // r0 = b - Q x0
+        if ((rc = apply_noise_op(p, x_E, x_B, bl, inv_noise, w->q[0], w->q[1], st, nullptr))) return rc;
+        axy_kernel<<<SV_GRID, SV_NT, 0, st>>>(w->q[0], w->invc[0], x_E, w->q[0], n);
+        axy_kernel<<<SV_GRID, SV_NT, 0, st>>>(w->q[1], w->invc[1], x_B, w->q[1], n);
+    } else {
+        zero2_kernel<<<SV_GRID, SV_NT, 0, st>>>(x_E, x_B, n);
+    }
+    pcg_init_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, rhs_E, rhs_B, warm_start ? 1 : 0, n);
+    GS_CHECK_LAUNCH();
+
+    const int* done = &w->state->done;
+    int launched = 0;
+    bool finished = false;
+    while (!finished) {
+        for (int k = 0; k < check_every && launched < itermax; ++k, ++launched) {
+            if ((rc = apply_noise_op(p, w->p[0], w->p[1], bl, inv_noise, w->q[0], w->q[1], st, done))) return rc;
+            pcg_apq_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, n);
+            pcg_update_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, x_E, x_B, n);
+            pcg_dir_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, n);
+            GS_CHECK_LAUNCH();
+        }
+        GS_CHECK_CUDA(cudaMemcpyAsync(w->host_state, w->state, sizeof(PcgState), cudaMemcpyDeviceToHost, st));
+        GS_CHECK_CUDA(cudaStreamSynchronize(st));
+        finished = w->host_state->done || launched >= itermax;
+    }
+    const PcgState& s = *w->host_state;
+    if (n_iter_out) *n_iter_out = s.iter;
+    if (resid_out) *resid_out = s.d0 > 0.0 ? sqrt(s.rr / s.d0) : 0.0;
+    if (s.d0 > 0.0 && s.rr > s.eps2 * s.d0) {
+        gs_set_error("PCG stopped at iter_max = %d with |r|/|r0| = %.3e > eps = %.1e", itermax, sqrt(s.rr / s.d0), eps);
+        return GS_E_NOTCONVERGED;
+    }
+    return GS_OK;
+}
+
+// y = Q x = C^-1 x + B A^T N^-1 A B x   (qcinv opfilt_pp.fwd_op; CenteredGibbs.py:629, 651-656)
+extern "C" int gs_cr_apply_q_pol(gs_plan* p, const double* dl_EE, const double* dl_BB, const double* bl,
+                                 const double* inv_noise, const double* x_E, const double* x_B, double* y_E,
+                                 double* y_B, void* stream)
+{
+    if (!p) { gs_set_error("null plan"); return GS_E_BADARG; }
+    GS_REQUIRE(dl_EE && dl_BB && bl && inv_noise && x_E && x_B && y_E && y_B, "null pointer argument");
+    GS_CHECK_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    gs_pcg_ws* w = get_ws(p);
+    if (!w) return GS_E_NOMEM;
+    const int L = p->d.lmax;
+    const int64_t n = (int64_t)(L + 1) * (L + 1);
+    int rc;
+    if ((rc = gs_launch_expand_per_l(dl_EE, L, 2, w->invc[0], st))) return rc;
+    if ((rc = gs_launch_expand_per_l(dl_BB, L, 2, w->invc[1], st))) return rc;
+    if ((rc = apply_noise_op(p, x_E, x_B, bl, inv_noise, w->q[0], w->q[1], st, nullptr))) return rc;
+    axy_kernel<<<SV_GRID, SV_NT, 0, st>>>(w->q[0], w->invc[0], x_E, y_E, n);
+    axy_kernel<<<SV_GRID, SV_NT, 0, st>>>(w->q[1], w->invc[1], x_B, y_B, n);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+// Right-hand side of the masked-sky system (CenteredGibbs.py:469-483, RNG order xi_Q, xi_U, xi_E, xi_B):
+//   b = B A^T N^-1 d  +  B (Npix/4pi) map2alm_{iter}(N^-1/2 xi_pix)  +  C^-1/2 xi_alm
+// The first term is what qcinv's calc_prep adds inside chain.sample; it equals the reference's
+// second_part_grad (CenteredGibbs.py:298-308) and may be passed precomputed (bdata_*).
+extern "C" int gs_cr_rhs_pol(gs_plan* p, const double* dl_EE, const double* dl_BB, const double* bl,
+                             const double* inv_noise, const double* sqrt_inv_noise, const double* bdata_E,
+                             const double* bdata_B, const double* d_Q, const double* d_U, const double* xi_Q,
+                             const double* xi_U, const double* xi_E, const double* xi_B, int fluct_iter,
+                             double* rhs_E, double* rhs_B, void* stream)
+{
+    if (!p) { gs_set_error("null plan"); return GS_E_BADARG; }
+    GS_REQUIRE(dl_EE && dl_BB && bl && inv_noise && sqrt_inv_noise && xi_Q && xi_U && xi_E && xi_B && rhs_E && rhs_B,
+               "null pointer argument");
+    GS_REQUIRE((bdata_E && bdata_B) || (d_Q && d_U), "need either the precomputed data term or the data maps");
+    GS_REQUIRE(fluct_iter >= 0, "fluct_iter must be >= 0");
+    GS_CHECK_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    gs_pcg_ws* w = get_ws(p);
+    if (!w) return GS_E_NOMEM;
+    const int L = p->d.lmax;
+    const int64_t n = (int64_t)(L + 1) * (L + 1);
+    int rc;
+    // fluctuation term 1: utils.adjoint_synthesis_hp (utils.py:79-111) = bl * (Npix/4pi) * map2alm(iter=3)
+    if ((rc = gs_map2alm_spin2(p, xi_Q, xi_U, sqrt_inv_noise, fluct_iter, 0, bl, rhs_E, rhs_B, GS_ALM_REAL, stream))) return rc;
+    const double resc = (double)p->d.npix / (4.0 * 3.14159265358979323846);
+    // fluctuation term 2 and data term; use r[] / p[] of the PCG workspace as scratch
+    if ((rc = gs_launch_expand_per_l(dl_EE, L, 4, w->r[0], st))) return rc;
+    if ((rc = gs_launch_expand_per_l(dl_BB, L, 4, w->r[1], st))) return rc;
+    const double* bdE = bdata_E;
+    const double* bdB = bdata_B;
+    if (!bdE) {
+        if ((rc = gs_map2alm_spin2(p, d_Q, d_U, inv_noise, 0, 1, bl, w->p[0], w->p[1], GS_ALM_REAL, stream))) return rc;
+        bdE = w->p[0];
+        bdB = w->p[1];
+    }
+    // rhs = resc * rhs + sqrt(C^-1) xi + bdata
+    rhs_combine_kernel<<<SV_GRID, SV_NT, 0, st>>>(rhs_E, w->r[0], xi_E, bdE, resc, n);
+    rhs_combine_kernel<<<SV_GRID, SV_NT, 0, st>>>(rhs_B, w->r[1], xi_B, bdB, resc, n);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+

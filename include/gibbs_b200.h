@@ -108,6 +108,90 @@ int gs_almxfl(const double* alm, int layout, int lmax, const double* fl, double*
 /* hp.alm2cl(alm, lmax) (CenteredGibbs.py:30, 61): (|a_l0|^2 + 2 sum_m |a_lm|^2) / (2l+1). */
 int gs_alm2cl(const double* alm, int layout, int lmax, double* cl, void* stream);
 
+/* Same as gs_alm2map_spin2 with separate per-l filters for E and B: the non-centred likelihood
+ * synthesises A (b_l sqrt(C^EE_l) s^E, b_l sqrt(C^BB_l) s^B)  (NonCenteredGibbs.py:346-351). */
+int gs_alm2map_spin2_fl2(gs_plan* plan, const double* almE, const double* almB, int layout,
+                         const double* flE, const double* flB, double* mapQ, double* mapU,
+                         void* stream);
+
+/* ---- constrained realization (masked sky: PCG; full sky isotropic: direct) ------------- */
+/* Right-hand side of Q x = b for the polarised masked-sky draw (CenteredGibbs.py:469-483):
+ *   b = B A^T N^-1 d + B (Npix/4pi) map2alm_{iter=fluct_iter}(N^-1/2 xi_pix) + C^-1/2 xi_alm,
+ * RNG order of the reference: xi_Q[Npix], xi_U[Npix], xi_E[(L+1)^2], xi_B[(L+1)^2] (standard
+ * normals supplied by the caller: injected numpy draws for parity, gs_randn in production).
+ * The data term is what the forked qcinv adds in multigrid_chain.sample (opfilt_pp.calc_prep) and
+ * equals second_part_grad (CenteredGibbs.py:298-308); pass it precomputed in bdata_E/B (real
+ * layout) or pass d_Q/d_U to have it computed.  dl_* are unbinned D_l (L+1), bl the beam b_l,
+ * inv_noise = mask / noise_pol and sqrt_inv_noise its square root (Npix).  fluct_iter = 3
+ * reproduces utils.adjoint_synthesis_hp (utils.py:89). */
+int gs_cr_rhs_pol(gs_plan* plan, const double* dl_EE, const double* dl_BB, const double* bl,
+                  const double* inv_noise, const double* sqrt_inv_noise, const double* bdata_E,
+                  const double* bdata_B, const double* d_Q, const double* d_U, const double* xi_Q,
+                  const double* xi_U, const double* xi_E, const double* xi_B, int fluct_iter,
+                  double* rhs_E, double* rhs_B, void* stream);
+
+/* Preconditioned conjugate gradient for Q x = b, Q = C^-1 + B A^T N^-1 A B, real alm layout:
+ * qcinv.multigrid.multigrid_chain(opfilt_pp, [[0, ["diag_cl"], lmax, nside, itermax, eps, tr_cg,
+ * cache_mem()]], ...) as configured at ConstrainedRealization.py:40-41 / CenteredGibbs.py:280-282
+ * and run at CenteredGibbs.py:486-488.  Preconditioner 1/(1/C_l + b_l^2 sum(N^-1)/(4pi))
+ * (ninv_sum_over_4pi = sum(inv_noise)/(4 pi)); stop when <r,r> <= eps^2 <r0,r0> or after itermax
+ * iterations.  warm_start = 0 starts from x = 0 (x_E/x_B are overwritten), otherwise from the
+ * contents of x_E/x_B (RJPO, CenteredGibbs.py:642-651).  The convergence flag lives on the device;
+ * the host polls it every `check_every` iterations (<= 0: 8).  Synchronous on return:
+ * *n_iter_out / *resid_out (host, nullable) receive the iteration count and |r|/|r0|.
+ * Returns GS_E_NOTCONVERGED if itermax was hit first (x holds the last iterate). */
+int gs_cr_pcg_pol(gs_plan* plan, const double* dl_EE, const double* dl_BB, const double* bl,
+                  const double* inv_noise, double ninv_sum_over_4pi, const double* rhs_E,
+                  const double* rhs_B, double* x_E, double* x_B, int warm_start, double eps,
+                  int itermax, int check_every, int* n_iter_out, double* resid_out, void* stream);
+
+/* y = Q x (qcinv opfilt_pp.fwd_op; CenteredGibbs.py:629, 653). */
+int gs_cr_apply_q_pol(gs_plan* plan, const double* dl_EE, const double* dl_BB, const double* bl,
+                      const double* inv_noise, const double* x_E, const double* x_B, double* y_E,
+                      double* y_B, void* stream);
+
+/* Diagonal draw for full sky + isotropic noise, one field, real layout, w = Npix/(noise 4 pi):
+ *   mode 0 centred     (CenteredGibbs.py:317-353): sigma = 1/(w b^2 + 1/C), s = sigma b w d + xi sqrt(sigma)
+ *   mode 1 non-centred (NonCenteredGibbs.py:138-176, all_sph): sigma = 1/(1 + b^2 C w),
+ *                      s = sigma sqrt(C) b w d + xi sqrt(sigma)
+ * dl = unbinned D_l, d_alm = data in harmonic space (pix_map["EE"/"BB"]), xi = standard normals. */
+int gs_cr_direct(const double* dl, const double* bl, const double* d_alm, const double* xi,
+                 double npix_over_noise_4pi, int lmax, int mode, double* out, void* stream);
+
+/* ---- C_l conditional samplers ------------------------------------------------------------ */
+/* PolarizedCenteredClsSampler.sample_one_pol / CenteredClsSampler.sample (CenteredGibbs.py:24-79):
+ * cl_hat = alm2cl(s) (L+1); bins = nbins + 1 int32 edges; D_bin = beta / Gamma(alpha, 1) with
+ * beta = sum_l (2l+1) l (l+1) cl_hat_l / 4pi, alpha = sum_l (2l+1)/2 - 1, alpha[0] := 1, D[:2] := 0.
+ * gamma_inject (nullable, nbins): Gamma(alpha,1) variates from the caller (numpy parity); NULL:
+ * Marsaglia-Tsang on a Philox4x32-10 stream keyed by (seed, call, bin).  alpha_out / beta_out
+ * (nullable, nbins) return the shape / scale per bin. */
+int gs_cls_invgamma(const double* cl_hat, const int* bins, int nbins, const double* gamma_inject,
+                    uint64_t seed, uint64_t call, double* dl_binned, double* alpha_out,
+                    double* beta_out, void* stream);
+
+/* Truncated-normal proposal on [0, inf) around the current binned D_l (ClsSampler.py:79-92,
+ * NonCenteredGibbs.py:292-309): dl_new[b] = ppf(u[b-2]; loc = dl_old[b], scale = sqrt(prop_var[b-2]))
+ * for b >= 2, dl_new[0] = dl_new[1] = 0.  u: nbins - 2 uniforms. */
+int gs_truncnorm_propose(const double* dl_old, const double* prop_var, int nbins, const double* u,
+                         double* dl_new, void* stream);
+/* out[b] = truncnorm.logpdf(x[b]; a = -from[b]/scale, b = inf, loc = from[b], scale) for b >= 2,
+ * 0 for b < 2 (NonCenteredGibbs.py:313-330). */
+int gs_truncnorm_logpdf(const double* x, const double* from, const double* prop_var, int nbins,
+                        double* out, void* stream);
+/* -1/2 sum_p inv_noise_p [(d_Q - m_Q)^2 + (d_U - m_U)^2] -> out[0] (device); d_U = m_U = NULL
+ * for temperature (NonCenteredGibbs.py:353-355; ClsSampler.py:107-108).  scratch: 592 doubles. */
+int gs_loglik_pix(const double* d_Q, const double* d_U, const double* m_Q, const double* m_U,
+                  const double* inv_noise, int64_t npix, double* scratch, double* out, void* stream);
+
+/* ---- random numbers / reductions --------------------------------------------------------- */
+/* n standard normals (Philox4x32-10 keyed by (seed, stream_id), Box-Muller); replaces
+ * np.random.normal in production runs. */
+int gs_randn(double* out, int64_t n, uint64_t seed, uint64_t stream_id, void* stream);
+/* n uniforms on (0,1). */
+int gs_randu(double* out, int64_t n, uint64_t seed, uint64_t stream_id, void* stream);
+/* out[0] = sum(a[0..n)) in a fixed order; scratch: 592 doubles. */
+int gs_sum(const double* a, int64_t n, double* scratch, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,200 @@
+"""numpy restatement of the reference's Python logic on the hot path (TEST INFRASTRUCTURE ONLY).
+
+Every function cites the reference lines it follows.  healpy calls go to oracle.sht; the forked
+qcinv (not vendored, no version recorded -- SURVEY.md 8c) is restated from upstream dhanson/qcinv
+semantics: opfilt_pp.fwd_op / calc_prep / pre_op_diag, cd_solve with tr_cg, monitor_basic.
+tests/golden/make_golden.py checks these restatements against the reference's own modules
+imported with stubbed third-party packages."""
+import numpy as np
+
+from . import sht
+
+
+# ---------------------------------------------------------------- layouts (utils.py / variance_expension.pyx)
+def real_to_complex(alms):
+    """utils.py:49-60"""
+    lmax = int(np.sqrt(len(alms))) - 1
+    m_0 = alms[:lmax + 1] + 0j
+    m_pos = alms[lmax + 1:]
+    m_pos = (m_pos[::2] + 1j * m_pos[1::2]) / np.sqrt(2)
+    return np.concatenate([m_0, m_pos])
+
+
+def complex_to_real(alms):
+    """utils.py:63-76"""
+    lmax = int((-3 + np.sqrt(9 + 8 * (len(alms) - 1))) / 2)
+    out = np.empty((lmax + 1) ** 2)
+    out[:lmax + 1] = alms[:lmax + 1].real
+    out[lmax + 1::2] = alms[lmax + 1:].real * np.sqrt(2)
+    out[lmax + 2::2] = alms[lmax + 1:].imag * np.sqrt(2)
+    return out
+
+
+def generate_var_cl(dls):
+    """utils.py:114-147 / variance_expension.pyx:8-33 (takes D_l; l = 0 copied unscaled)"""
+    lmax = len(dls) - 1
+    size_complex = (lmax + 1) * (lmax + 2) // 2
+    alms_shape = np.zeros(size_complex)
+    for l in range(lmax + 1):
+        for m in range(l + 1):
+            idx = m * (2 * lmax + 1 - m) // 2 + l
+            alms_shape[idx] = dls[l] if l == 0 else dls[l] * 2 * np.pi / (l * (l + 1))
+    var = np.zeros((lmax + 1) ** 2)
+    var[:lmax + 1] = alms_shape[:lmax + 1]
+    var[lmax + 1::2] = alms_shape[lmax + 1:]
+    var[lmax + 2::2] = alms_shape[lmax + 1:]
+    return var
+
+
+def expand_per_l(x):
+    """GibbsSampler.py:73 / config.py:81-83"""
+    lmax = len(x) - 1
+    return np.concatenate([x, np.array([c for m in range(1, lmax + 1) for c in x[m:] for _ in range(2)])])
+
+
+def unfold_bins(binned, bins):
+    """utils.py:150-162"""
+    bins = np.asarray(bins)
+    return np.repeat(binned, bins[1:] - bins[:-1])
+
+
+def safe_inv(v):
+    out = np.zeros(len(v))
+    out[v != 0] = 1 / v[v != 0]
+    return out
+
+
+# ---------------------------------------------------------------- SHT wrappers in the real layout
+def synth_pol(eE, eB, nside, lmax, kind="ld"):
+    return sht.alm2map_spin2(real_to_complex(eE), real_to_complex(eB), nside, lmax, kind)
+
+
+def adjoint_pol(q, u, nside, lmax, iter=0, kind="ld"):
+    """(Npix/4pi) map2alm_iter (utils.py:87-100 with iter=3; iter=0 is the exact transpose)"""
+    npix = 12 * nside * nside
+    e, b = sht.map2alm_spin2(q, u, nside, lmax, iter=iter, kind=kind)
+    return complex_to_real(e) * npix / (4 * np.pi), complex_to_real(b) * npix / (4 * np.pi)
+
+
+class PolProblem:
+    """Inputs of the polarised masked-sky CR step (CenteredGibbs.py:243-314)."""
+
+    def __init__(self, nside, lmax, d_Q, d_U, inv_noise_pol, fwhm_deg, kind="ld"):
+        self.nside, self.lmax, self.kind = nside, lmax, kind
+        self.npix = 12 * nside * nside
+        self.d_Q, self.d_U = d_Q, d_U
+        self.inv_noise = inv_noise_pol
+        self.bl_gauss = sht.gauss_beam(np.radians(fwhm_deg), lmax)
+        self.bl_map = expand_per_l(self.bl_gauss)
+        # second_part_grad (CenteredGibbs.py:298-308)
+        e, b = adjoint_pol(d_Q * inv_noise_pol, d_U * inv_noise_pol, nside, lmax, 0, kind)
+        self.bdata_E, self.bdata_B = e * self.bl_map, b * self.bl_map
+
+    def rhs(self, dl_EE, dl_BB, xi_Q, xi_U, xi_E, xi_B, fluct_iter=3):
+        """CenteredGibbs.py:469-483 + the data term qcinv's calc_prep adds in chain.sample"""
+        ivE, ivB = safe_inv(generate_var_cl(dl_EE)), safe_inv(generate_var_cl(dl_BB))
+        fe, fb = adjoint_pol(xi_Q * np.sqrt(self.inv_noise), xi_U * np.sqrt(self.inv_noise), self.nside, self.lmax,
+                             fluct_iter, self.kind)
+        bE = fe * self.bl_map + np.sqrt(ivE) * xi_E + self.bdata_E
+        bB = fb * self.bl_map + np.sqrt(ivB) * xi_B + self.bdata_B
+        return bE, bB
+
+    def apply_Q(self, dl_EE, dl_BB, xE, xB):
+        """qcinv opfilt_pp.fwd_op: C^-1 x + b (Npix/4pi) map2alm0(N^-1 alm2map(b x))"""
+        ivE, ivB = safe_inv(generate_var_cl(dl_EE)), safe_inv(generate_var_cl(dl_BB))
+        q, u = synth_pol(xE * self.bl_map, xB * self.bl_map, self.nside, self.lmax, self.kind)
+        e, b = adjoint_pol(q * self.inv_noise, u * self.inv_noise, self.nside, self.lmax, 0, self.kind)
+        return ivE * xE + e * self.bl_map, ivB * xB + b * self.bl_map
+
+    def precond(self, dl_EE, dl_BB):
+        """qcinv opfilt_pp.pre_op_diag: 1 / (1/C_l + b_l^2 sum(N^-1)/(4 pi))"""
+        ninv = np.sum(self.inv_noise) / (4 * np.pi)
+        out = []
+        for dl in (dl_EE, dl_BB):
+            cl = dl * np.array([2 * np.pi / (l * (l + 1)) if l else 0 for l in range(self.lmax + 1)])
+            cl[0] = dl[0]
+            d = safe_inv(cl) + self.bl_gauss ** 2 * ninv
+            out.append(expand_per_l(safe_inv(d)))
+        return out
+
+    def pcg(self, dl_EE, dl_BB, bE, bB, eps=1e-5, itermax=4000, x0=None):
+        """qcinv cd_solve with tr_cg (= plain PCG) and monitor_basic: stop when <r,r> <= eps^2 <r0,r0>."""
+        ME, MB = self.precond(dl_EE, dl_BB)
+        b = np.concatenate([bE, bB])
+        M = np.concatenate([ME, MB])
+        n = len(bE)
+        A = lambda v: np.concatenate(self.apply_Q(dl_EE, dl_BB, v[:n], v[n:]))
+        x = np.zeros(2 * n) if x0 is None else np.concatenate(x0)
+        r = b - A(x) if x0 is not None else b.copy()
+        d0 = r @ r
+        z = M * r
+        p = z.copy()
+        delta = r @ z
+        it = 0
+        while it < itermax and r @ r > eps ** 2 * d0:
+            q = A(p)
+            alpha = delta / (p @ q)
+            x += alpha * p
+            r -= alpha * q
+            z = M * r
+            dn = r @ z
+            p = z + (dn / delta) * p
+            delta = dn
+            it += 1
+        return x[:n], x[n:], it, np.sqrt((r @ r) / d0) if d0 > 0 else 0.0
+
+    def dense_Q(self, dl_EE, dl_BB):
+        n = (self.lmax + 1) ** 2
+        Q = np.zeros((2 * n, 2 * n))
+        for i in range(2 * n):
+            v = np.zeros(2 * n)
+            v[i] = 1
+            Q[:, i] = np.concatenate(self.apply_Q(dl_EE, dl_BB, v[:n], v[n:]))
+        return Q
+
+
+# ---------------------------------------------------------------- diagonal CR (full sky, isotropic)
+def sample_no_mask(dl, bl_map, d_alm, xi, npix, noise0):
+    """CenteredGibbs.py:317-353 for one spectrum"""
+    inv_var = safe_inv(generate_var_cl(dl))
+    sigma = 1 / ((npix / (noise0 * 4 * np.pi)) * bl_map ** 2 + inv_var)
+    r = bl_map * ((npix * (1 / noise0) / (4 * np.pi)) * d_alm)
+    return sigma * r + xi * np.sqrt(sigma)
+
+
+def sample_no_mask_nc(dl, bl_map, d_alm, xi, npix, noise0):
+    """NonCenteredGibbs.py:138-176 (all_sph) for one spectrum"""
+    var = generate_var_cl(dl)
+    sigma = 1 / (1 + (1 / noise0) * bl_map ** 2 * var * npix / (4 * np.pi))
+    r = np.sqrt(var) * bl_map * ((npix * (1 / noise0) / (4 * np.pi)) * d_alm)
+    return sigma * r + xi * np.sqrt(sigma)
+
+
+# ---------------------------------------------------------------- C_l conditional (CenteredGibbs.py:54-79)
+def cls_alpha_beta(alms_real, bins, lmax):
+    observed = sht.alm2cl(real_to_complex(alms_real), lmax)
+    exponent = np.array([(2 * l + 1) / 2 for l in range(lmax + 1)])
+    betas = np.array([(2 * l + 1) * l * (l + 1) * (c / (4 * np.pi)) for l, c in enumerate(observed)])
+    ba, bb = [], []
+    for i, l in enumerate(bins[:-1]):
+        bb.append(np.sum(betas[l:bins[i + 1]]))
+        ba.append(np.sum(exponent[l:bins[i + 1]]) - 1)
+    ba[0] = 1
+    return np.array(ba), np.array(bb)
+
+
+def cls_sample(alms_real, bins, lmax, gamma_draws):
+    """D = beta * invgamma.rvs(alpha) = beta / Gamma(alpha,1); D[:2] = 0"""
+    a, b = cls_alpha_beta(alms_real, bins, lmax)
+    d = b / gamma_draws
+    d[:2] = 0
+    return d
+
+
+# ---------------------------------------------------------------- non-centred likelihood (NonCenteredGibbs.py:333-355)
+def nc_loglik(binned, bins, s_nc, prob):
+    dlE, dlB = unfold_bins(binned["EE"], bins["EE"]), unfold_bins(binned["BB"], bins["BB"])
+    vE, vB = generate_var_cl(dlE), generate_var_cl(dlB)
+    q, u = synth_pol(prob.bl_map * np.sqrt(vE) * s_nc["EE"], prob.bl_map * np.sqrt(vB) * s_nc["BB"], prob.nside, prob.lmax,
+                     prob.kind)
+    return -0.5 * (np.sum((prob.d_Q - q) ** 2 * prob.inv_noise) + np.sum((prob.d_U - u) ** 2 * prob.inv_noise))
