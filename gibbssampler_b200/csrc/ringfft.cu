@@ -286,9 +286,9 @@ int gs_ring_setup(gs_plan* p)
     GS_CHECK_CUDA(cudaMalloc(&d, std::max<int64_t>(1, off) * sizeof(double2))); p->owned.push_back(d);
     p->d.bs_tab = (const double2*)d;
 
-    GS_CHECK_CUDA(cudaFuncSetAttribute(bluestein_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ring_smem));
-    GS_CHECK_CUDA(cudaFuncSetAttribute(ring_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ring_smem));
-    GS_CHECK_CUDA(cudaFuncSetAttribute(ring_anal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ring_smem));
+    GS_CHECK_CUDA(cudaFuncSetAttribute(bluestein_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GS_CHECK_CUDA(cudaFuncSetAttribute(ring_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GS_CHECK_CUDA(cudaFuncSetAttribute(ring_anal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (!descs.empty()) {
         bluestein_setup_kernel<<<(int)descs.size(), RF_NT, p->ring_smem>>>(p->d, (double2*)d, (int)descs.size());
         GS_CHECK_LAUNCH();
