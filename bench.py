@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- Gibbs iterations/s (and spin-2 SHT pairs/s) of the constrained-realization +
+C_l-sampling Gibbs step on synthetic CMB polarisation skies (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W          # this repo (sm_100a kernels)
+  python bench.py --impl reference --gpus N ...          # the reference CPU path (oracle port) on host cores
+
+A step = one Gibbs iteration of the centred polarised masked-sky sampler
+(PolarizedCenteredConstrainedRealization.sample_mask: RHS draw + PCG solve, then
+PolarizedCenteredClsSampler.sample), one independent chain per GPU (weak scaling, no data-path
+collective).  Workload: NSIDE 512, lmax 1024, analytic fiducial spectra
+D^EE_l = exp(-(l/1200)^2) + 0.02, D^BB_l = 0.05 (l/80)^-0.5 exp(-(l/1500)^2) + 1e-3 (l >= 2),
+Gaussian 0.5 deg beam, white noise sigma^2_pol = 0.04 uK^2 (NSIDE 256) scaled with Npix, galactic
+band mask f_sky = 0.8 with a 2 deg cosine edge; data synthetic, seeds fixed.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# PCG iterations to eps = 1e-5 of the benchmark system (fixed seed).  The count is a property of the
+# linear system and stopping rule, not of the implementation (tests/test_cr_gpu.py shows the oracle and
+# the GPU agree to +-1); the CPU reference arm uses it to extrapolate its bounded sample.
+PCG_ITERS = {512: None, 256: None, 128: None, 64: None}
+RHS_SHT_EQUIV = 8  # data term is precomputed; fluctuation term = map2alm(iter=3) = 1 + 3 x 2 transforms, +1 spare
+
+
+def pixel_z(nside):
+    """cos(theta) of every RING pixel (HEALPix geometry, vectorised)."""
+    npix = 12 * nside * nside
+    z = np.empty(npix)
+    i = np.arange(1, nside)
+    start = 2 * i * (i - 1)
+    zc = 1 - i * i / (3.0 * nside * nside)
+    for ii, s, zz in zip(i, start, zc):
+        z[s:s + 4 * ii] = zz
+        z[npix - s - 4 * ii:npix - s] = -zz
+    ib = np.arange(nside, 3 * nside + 1)
+    ncap = 2 * nside * (nside - 1)
+    zb = 4.0 / 3 - 2 * ib / (3.0 * nside)
+    z[ncap:npix - ncap] = np.repeat(zb, 4 * nside)
+    return z
+
+
+def fiducial(lmax):
+    ell = np.arange(lmax + 1, dtype=np.float64)
+    dlE = np.where(ell >= 2, np.exp(-(ell / 1200.0) ** 2) + 0.02, 0.0)
+    dlB = np.where(ell >= 2, 0.05 * (np.maximum(ell, 1) / 80.0) ** -0.5 * np.exp(-(ell / 1500.0) ** 2) + 1e-3, 0.0)
+    return dlE, dlB
+
+
+def make_mask(nside, fsky=0.8, edge_deg=2.0):
+    z = pixel_z(nside)
+    b = np.degrees(np.arcsin(np.abs(z)))        # |latitude|
+    b0 = np.degrees(np.arcsin(1.0 - fsky))      # band |b| < b0 removes 1 - fsky of the sky
+    t = np.clip((b - b0) / edge_deg + 0.5, 0.0, 1.0)
+    return 0.5 * (1 - np.cos(np.pi * t))
+
+
+def bins_for(lmax):
+    """EE: one multipole per bin; BB: the shipped Planck-like scheme (config.py:45-46) scaled to lmax."""
+    ee = np.arange(0, lmax + 2)
+    cut = int(round(396 * lmax / 512))
+    tail = np.unique(np.round(np.array([396, 398, 400, 402, 406, 410, 415, 420, 425, 430, 435, 440, 445, 460, 475, 495, 513])
+                              * lmax / 512).astype(int))
+    tail = tail[tail > cut]
+    bb = np.concatenate([np.arange(0, cut + 1), tail])
+    bb[-1] = lmax + 1
+    return {"EE": ee, "BB": bb}
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples = index, False, []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(s) > 2 + k and s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def cpu_pair_seconds(nside, lmax, reps, seed=0):
+    """Seconds per spin-2 SHT pair (alm2map_spin2 + adjoint) of the CPU oracle port on all host cores."""
+    from oracle import sht as O
+    rng = np.random.default_rng(seed)
+    n = O.nalm(lmax)
+    e = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        q, u = O.alm2map_spin2(e, b, nside, lmax, kind="f64")
+        O.map2alm_spin2(q, u, nside, lmax, adjoint=True, kind="f64")
+        ts.append(time.perf_counter() - t0)
+    return float(np.median(ts)), O._lib("f64").orc_num_threads()
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path.  healpy/qcinv cannot be installed
+    here, so this is the oracle port (C + OpenMP, FP64) of the same algorithm on the box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nside, lmax = args.nside, args.lmax
+    n_pcg = args.pcg_iters or PCG_ITERS.get(nside) or 300
+    t_pairs = []
+    for _ in range(args.warmup + args.steps):
+        t, cores = cpu_pair_seconds(nside, lmax, 1)
+        t_pairs.append(t)
+    t_pair = float(np.median(t_pairs[args.warmup:]))
+    t_iter = t_pair * (n_pcg + RHS_SHT_EQUIV / 2.0)
+    val = 1.0 / t_iter
+    line = {
+        "impl": "reference", "metric": "gibbs_iters_per_s", "value": val, "unit": "it/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t_iter, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, n_pcg),
+        "sht_pairs_per_s": 1.0 / t_pair,
+        "cpu_baseline": {"value": val, "unit": "it/s", "cores": cores, "kind": "port",
+                         "sample": "each step times 1 spin-2 SHT pair (alm2map_spin2 + A^T) of the oracle port at the full NSIDE/lmax on all host "
+                                   "cores; a Gibbs iteration is extrapolated as (n_pcg + %g) pairs with n_pcg = %d" % (RHS_SHT_EQUIV / 2.0, n_pcg)},
+        "e2e": {"value": val, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, n_pcg):
+    return {"workload": "CenteredGibbs polarised masked sky: PCG constrained realization (eps 1e-5, diag_cl precond) + inverse-gamma C_l draw; "
+                        "one independent chain per GPU",
+            "nside": args.nside, "lmax": args.lmax, "fsky": 0.8, "beam_fwhm_deg": 0.5 * max(1, 512 // args.nside) if args.nside < 512 else 0.5,
+            "pcg_iterations": n_pcg, "chains_per_gpu": 1,
+            "l2_policy": "inputs larger than L2: each PCG iteration streams the 67 MB ring-spectra intermediate, 50 MB of maps and 100 MB of "
+                         "recurrence/alm vectors (126 MB L2)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--nside", type=int, default=512)
+    ap.add_argument("--lmax", type=int, default=1024)
+    ap.add_argument("--pcg-iters", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from gibbssampler_b200 import _dev, _lib, utils
+    from gibbssampler_b200.CenteredGibbs import PolarizedCenteredClsSampler, PolarizedCenteredConstrainedRealization
+    from gibbssampler_b200.sht import Plan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nside, lmax = args.nside, args.lmax
+    npix, nre = 12 * nside * nside, (lmax + 1) ** 2
+    L = _lib.lib()
+    dev = torch.device("cuda", local)
+
+    # ---- synthetic sky (generated with the library's own kernels; same data on every rank, different chains)
+    plan = Plan.get(nside, lmax)
+    dlE, dlB = fiducial(lmax)
+    fwhm = 0.5 * (512 // nside) if nside < 512 else 0.5
+    bl = _dev.gauss_beam(np.radians(fwhm), lmax)
+    noise_var = 0.04 * npix / 786432.0
+    mask = make_mask(nside)
+    data_rng = _dev.Rng("philox", seed=1234)
+    sE = data_rng.normal(nre) * utils.expand_per_l(_dev.f64(dlE), 3)
+    sB = data_rng.normal(nre) * utils.expand_per_l(_dev.f64(dlB), 3)
+    q, u = plan.alm2map_spin2(sE, sB, fl=_dev.f64(bl))
+    mask_d = _dev.f64(mask)
+    dQ = (q + data_rng.normal(npix) * np.sqrt(noise_var)) * mask_d
+    dU = (u + data_rng.normal(npix) * np.sqrt(noise_var)) * mask_d
+    bins = bins_for(lmax)
+    bl_map = utils.expand_per_l(_dev.f64(bl), 0)
+    noise_pol = torch.full((npix,), noise_var, dtype=torch.float64, device=dev)
+    cr = PolarizedCenteredConstrainedRealization({"Q": dQ, "U": dU}, noise_pol * 1e4, noise_pol, bl_map, lmax, npix, fwhm,
+                                                 mask=mask, rng="philox", seed=1000 + rank)
+    cls = PolarizedCenteredClsSampler({"Q": dQ, "U": dU}, lmax, nside, bins, bl_map, noise_pol, mask=mask, rng=cr.rng)
+
+    def binned_init():
+        out = {}
+        for pol, dl in (("EE", dlE), ("BB", dlB)):
+            e = bins[pol]
+            out[pol] = _dev.f64(np.array([dl[e[i]:e[i + 1]].mean() for i in range(len(e) - 1)]))
+        return out
+
+    state = {"binned": binned_init()}
+    pcg_its = []
+
+    def step_device():
+        b = state["binned"]
+        dls = {"EE": utils.unfold_bins(b["EE"], bins["EE"]), "BB": utils.unfold_bins(b["BB"], bins["BB"])}
+        sky, _ = cr.sample_mask(dls)
+        pcg_its.append(cr.last_pcg_iterations)
+        state["binned"] = cls.sample(sky)
+
+    h2d = d2h = 0
+
+    def step_e2e():
+        """The same iteration through the reference-facing sample() calls with HOST (numpy) arrays."""
+        nonlocal h2d, d2h
+        b = state["binned_host"]
+        dls = {"EE": np.repeat(b["EE"], np.diff(bins["EE"])), "BB": np.repeat(b["BB"], np.diff(bins["BB"]))}
+        sky, _ = cr.sample_mask(dls)                  # H2D: D_l; D2H: alms (numpy out)
+        state["binned_host"] = cls.sample(sky)        # H2D: alms; D2H: binned D_l
+        h2d = 8 * (2 * (lmax + 1) + 2 * nre)
+        d2h = 8 * (2 * nre + len(b["EE"]) + len(b["BB"]))
+
+    def timed(fn, nwarm, nsteps):
+        for _ in range(nwarm):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(nsteps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0 = L.gs_launch_count()
+    pcg_its.clear()
+    ms_total = timed(step_device, args.warmup, args.steps)
+    launches = L.gs_launch_count() - launches0
+    its_timed = pcg_its[args.warmup:]
+    launches = int(launches * args.steps / (args.warmup + args.steps))
+    clocks.stop_flag = True
+    clocks.join(timeout=2)
+
+    state["binned_host"] = {k: v.cpu().numpy() for k, v in state["binned"].items()}
+    ms_e2e = timed(step_e2e, 1, max(1, args.steps))
+    e2e_val = world * max(1, args.steps) / (ms_e2e * 1e-3)
+
+    value = world * args.steps / (ms_total * 1e-3)
+    n_pcg = int(round(float(np.mean(its_timed)))) if its_timed else 0
+
+    # ---- per-kernel timing of one PCG mat-vec (CUDA events on the launching stream) + roofline
+    x_e, x_b = data_rng.normal(nre), data_rng.normal(nre)
+    y_e, y_b = torch.empty_like(x_e), torch.empty_like(x_b)
+    ms4 = (C.c_float * 4)()
+    _lib.check(L.gs_profile_matvec(plan._h, _dev.ptr(x_e), _dev.ptr(x_b), _dev.ptr(cr.bl_gauss_d), _dev.ptr(cr.inv_noise_pol),
+                                   _dev.ptr(y_e), _dev.ptr(y_b), 3, ms4, _dev.stream()))
+    _lib.check(L.gs_profile_matvec(plan._h, _dev.ptr(x_e), _dev.ptr(x_b), _dev.ptr(cr.bl_gauss_d), _dev.ptr(cr.inv_noise_pol),
+                                   _dev.ptr(y_e), _dev.ptr(y_b), 20, ms4, _dev.stream()))
+    stage_ms = {"leg_synth": ms4[0], "ring_synth": ms4[1], "ring_anal": ms4[2], "leg_anal": ms4[3]}
+    pair_ms = sum(stage_ms.values())
+    peak = C.c_double(0.0)
+    _lib.check(L.gs_measure_fp64_peak(C.byref(peak), _dev.stream()))
+    nring = 4 * nside - 1
+    n_lm2 = sum(lmax - max(m, 2) + 1 for m in range(lmax + 1))
+    f2 = 26.0 * ((nring + 1) // 2) * n_lm2                 # flops of one spin-2 Legendre transform (unpruned)
+    dom = max(("leg_synth", "leg_anal"), key=lambda k: stage_ms[k])
+    ach = f2 / (stage_ms[dom] * 1e-3) * 1e-12
+    roofline = {"kernel": "leg_anal_kernel<2,2>" if dom == "leg_anal" else "leg_synth_kernel<2,2>", "bound": "fp64",
+                "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value if peak.value else None,
+                "traffic": None,
+                "peak_source": "DFMA microkernel measured in this run (MEASURED_PEAKS.json has no FP64 figure; nominal 37.2 TFLOP/s)",
+                "algorithmic_flops_per_launch": f2, "ms_per_launch": stage_ms[dom],
+                "both_legendre_kernels_tflops": 2 * f2 / ((stage_ms["leg_synth"] + stage_ms["leg_anal"]) * 1e-3) * 1e-12}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        hbm_peak, hbm_src = peaks["hbm_gbs"], "MEASURED_PEAKS.json"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback"
+    ring_bytes = 2 * 16.0 * nring * (lmax + 1) + 2 * 8.0 * npix      # ring spectra (Q,U) + maps (Q,U), one direction
+    ring_ms = max(stage_ms["ring_synth"], stage_ms["ring_anal"])
+    roofline_hbm = {"kernel": "ring_synth_kernel/ring_anal_kernel", "bound": "hbm", "achieved": ring_bytes / (ring_ms * 1e-3) * 1e-9,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": ring_bytes / (ring_ms * 1e-3) * 1e-9 / hbm_peak, "traffic": None,
+                    "peak_source": hbm_src, "algorithmic_bytes_per_launch": ring_bytes}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        reps = 2 if nside >= 512 else 3
+        t_pair, cores = cpu_pair_seconds(nside, lmax, reps)
+        t_iter = t_pair * (n_pcg + RHS_SHT_EQUIV / 2.0)
+        cpu_baseline = {"value": 1.0 / t_iter, "unit": "it/s", "cores": cores, "kind": "port",
+                        "pairs_per_s": 1.0 / t_pair,
+                        "sample": "%d spin-2 SHT pairs of the oracle port (C + OpenMP, FP64) at the same NSIDE/lmax; one Gibbs iteration "
+                                  "extrapolated as (n_pcg + %g) pairs with the n_pcg = %d of this run" % (reps, RHS_SHT_EQUIV / 2.0, n_pcg)}
+
+    if rank == 0:
+        line = {
+            "metric": "gibbs_iters_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args, n_pcg),
+            "e2e": {"value": e2e_val, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "sht_pairs_per_s": world * 1e3 / pair_ms, "sht_pair_ms": pair_ms, "stage_ms": stage_ms,
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline, "clocks": clocks.summary(),
+            "pcg_iterations_per_step": its_timed,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

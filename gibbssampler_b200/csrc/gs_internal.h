@@ -105,6 +105,7 @@ struct gs_plan {
     double* almB_tmp2;
 };
 
+extern long long g_gs_launches;  // kernels launched by this library (bench.py's gpu_launches)
 static inline int64_t gs_nalm(int lmax) { return (int64_t)(lmax + 1) * (lmax + 2) / 2; }
 
 // legendre.cu

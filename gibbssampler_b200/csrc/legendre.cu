@@ -566,6 +566,7 @@ int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, i
     if (spin == 0) leg_synth_kernel<0, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip);
     else leg_synth_kernel<2, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip);
     GS_CHECK_LAUNCH();
+    g_gs_launches += 1;
     return GS_OK;
 }
 
@@ -586,5 +587,6 @@ int gs_leg_anal(gs_plan* p, int spin, double* almE, double* almB, int layout, co
         leg_finish_kernel<2><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip);
     }
     GS_CHECK_LAUNCH();
+    g_gs_launches += 2;
     return GS_OK;
 }

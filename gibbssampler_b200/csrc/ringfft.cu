@@ -315,6 +315,7 @@ int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t
     if (spin == 0) ring_synth_kernel<<<p->njobs0, RF_NT, p->ring_smem, st>>>(p->d, p->jobs0, p->Fm, mapQ, mapQ, skip);
     else ring_synth_kernel<<<p->njobs2, RF_NT, p->ring_smem, st>>>(p->d, p->jobs2, p->Fm, mapQ, mapU, skip);
     GS_CHECK_LAUNCH();
+    g_gs_launches += 1;
     return GS_OK;
 }
 
@@ -324,5 +325,6 @@ int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, c
     if (spin == 0) ring_anal_kernel<<<p->njobs0, RF_NT, p->ring_smem, st>>>(p->d, p->jobs0, mapQ, mapQ, pixw, p->Fm, skip);
     else ring_anal_kernel<<<p->njobs2, RF_NT, p->ring_smem, st>>>(p->d, p->jobs2, mapQ, mapU, pixw, p->Fm, skip);
     GS_CHECK_LAUNCH();
+    g_gs_launches += 1;
     return GS_OK;
 }

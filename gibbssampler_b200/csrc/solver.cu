@@ -293,6 +293,7 @@ extern "C" int gs_cr_pcg_pol(gs_plan* p, const double* dl_EE, const double* dl_B
             pcg_update_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, x_E, x_B, n);
             pcg_dir_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, n);
             GS_CHECK_LAUNCH();
+            g_gs_launches += 3;
         }
         GS_CHECK_CUDA(cudaMemcpyAsync(w->host_state, w->state, sizeof(PcgState), cudaMemcpyDeviceToHost, st));
         GS_CHECK_CUDA(cudaStreamSynchronize(st));
@@ -373,3 +374,83 @@ extern "C" int gs_cr_rhs_pol(gs_plan* p, const double* dl_EE, const double* dl_B
     return GS_OK;
 }
 
+
+// ------------------------------------------------------------------ measurement helpers (bench.py)
+long long g_gs_launches = 0;
+extern "C" long long gs_launch_count(void) { return g_gs_launches; }
+
+// Times the four kernels of one PCG mat-vec (Legendre synthesis, ring synthesis, ring analysis with
+// fused N^-1, Legendre analysis + finish) with CUDA events on the launching stream; ms_out[0..3]
+// receive the average duration of each stage over nrep repetitions.
+extern "C" int gs_profile_matvec(gs_plan* p, const double* x_E, const double* x_B, const double* bl,
+                                 const double* inv_noise, double* y_E, double* y_B, int nrep, float* ms_out,
+                                 void* stream)
+{
+    if (!p) { gs_set_error("null plan"); return GS_E_BADARG; }
+    GS_REQUIRE(x_E && x_B && bl && inv_noise && y_E && y_B && ms_out && nrep >= 1, "bad arguments");
+    GS_CHECK_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t ev[5];
+    for (int i = 0; i < 5; ++i) GS_CHECK_CUDA(cudaEventCreate(&ev[i]));
+    double acc[4] = {0, 0, 0, 0};
+    int rc = GS_OK;
+    for (int r = 0; r < nrep && rc == GS_OK; ++r) {
+        cudaEventRecord(ev[0], st);
+        rc = gs_leg_synth(p, 2, x_E, x_B, GS_ALM_REAL, bl, st);
+        cudaEventRecord(ev[1], st);
+        if (!rc) rc = gs_ring_synth(p, 2, p->mapQ_tmp, p->mapU_tmp, st);
+        cudaEventRecord(ev[2], st);
+        if (!rc) rc = gs_ring_anal(p, 2, p->mapQ_tmp, p->mapU_tmp, inv_noise, st);
+        cudaEventRecord(ev[3], st);
+        if (!rc) rc = gs_leg_anal(p, 2, y_E, y_B, GS_ALM_REAL, bl, 1.0, 0, st);
+        cudaEventRecord(ev[4], st);
+        GS_CHECK_CUDA(cudaEventSynchronize(ev[4]));
+        for (int i = 0; i < 4; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); acc[i] += ms; }
+    }
+    for (int i = 0; i < 4; ++i) ms_out[i] = (float)(acc[i] / nrep);
+    for (int i = 0; i < 5; ++i) cudaEventDestroy(ev[i]);
+    return rc;
+}
+
+// FP64 FMA throughput of the device (MEASURED_PEAKS.json holds no FP64 figure): 8 independent DFMA
+// chains per thread, 148 x 8 CTAs of 256 threads; returns TFLOP/s (2 flops per FMA), best of 5.
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b)
+{
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = threadIdx.x * 1e-3 + k;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fma(v[k], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+    if (s == 123.456) out[0] = s;
+}
+
+extern "C" int gs_measure_fp64_peak(double* tflops_out, void* stream)
+{
+    GS_REQUIRE(tflops_out, "null output");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* d = nullptr;
+    GS_CHECK_CUDA(cudaMalloc(&d, 8));
+    cudaEvent_t e0, e1;
+    GS_CHECK_CUDA(cudaEventCreate(&e0));
+    GS_CHECK_CUDA(cudaEventCreate(&e1));
+    const int iters = 1 << 15, grid = 148 * 8;
+    double best = 0.0;
+    for (int r = 0; r < 6; ++r) {
+        cudaEventRecord(e0, st);
+        dfma_peak_kernel<<<grid, 256, 0, st>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1, st);
+        GS_CHECK_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 8.0 * iters * (double)grid * 256.0 / (ms * 1e-3) * 1e-12;
+        if (r > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops_out = best;
+    return GS_OK;
+}

@@ -192,6 +192,19 @@ int gs_randu(double* out, int64_t n, uint64_t seed, uint64_t stream_id, void* st
 /* out[0] = sum(a[0..n)) in a fixed order; scratch: 592 doubles. */
 int gs_sum(const double* a, int64_t n, double* scratch, double* out, void* stream);
 
+/* ---- measurement helpers used by bench.py ------------------------------------------------ */
+/* Number of kernels this library has launched so far in the SHT stages and PCG vector updates. */
+long long gs_launch_count(void);
+/* Average duration (ms, CUDA events on `stream`) of the four kernels of one PCG mat-vec
+ * y = B A^T N^-1 A B x: ms_out[0] Legendre synthesis, [1] ring synthesis, [2] ring analysis,
+ * [3] Legendre analysis + finish.  Synchronous. */
+int gs_profile_matvec(gs_plan* plan, const double* x_E, const double* x_B, const double* bl,
+                      const double* inv_noise, double* y_E, double* y_B, int nrep, float* ms_out,
+                      void* stream);
+/* FP64 FMA throughput of the current device in TFLOP/s (DFMA microkernel; the roofline
+ * denominator of the Legendre kernels).  Synchronous. */
+int gs_measure_fp64_peak(double* tflops_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
