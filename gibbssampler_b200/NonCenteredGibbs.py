@@ -1,0 +1,207 @@
+"""Non-centred parametrisation (mirror of NonCenteredGibbs.py): CR step = centred draw times C^-1/2,
+C_l step = blocked Metropolis-within-Gibbs whose likelihood costs one spin-2 synthesis per block.
+The whole Metropolis sweep (filters -> synthesis -> chi^2 reduction -> accept/commit) runs on the
+device without host synchronisation; only the accept flags are read back at the end."""
+import numpy as np
+import torch
+
+from . import _dev, _lib, utils
+from ._dev import f64, ptr, stream
+from ._lib import check, GS_ALM_REAL
+from .CenteredGibbs import PolarizedCenteredConstrainedRealization
+from .ClsSampler import MHClsSampler
+from .ConstrainedRealization import ConstrainedRealization
+from .GibbsSampler import GibbsSampler
+
+
+class PolarizedNonCenteredConstrainedRealization(ConstrainedRealization):
+    def __init__(self, pix_map, noise_temp, noise_pol, bl_map, lmax, Npix, bl_fwhm, mask_path=None, all_sph=False, *,
+                 mask=None, rng="philox", seed=None):
+        """Mirror of NonCenteredGibbs.py:106-135."""
+        super().__init__(pix_map, noise_temp, bl_map, bl_fwhm, lmax, Npix, mask=None, rng=rng, seed=seed)
+        self.noise_temp = noise_temp
+        self.noise_pol = noise_pol
+        self.mask_path = mask_path
+        self.masked = mask is not None or mask_path is not None
+        self.all_sph = all_sph
+        self.bl_fwhm = bl_fwhm
+        self.pol_centered_constraint_realizer = PolarizedCenteredConstrainedRealization(
+            pix_map, noise_temp, noise_pol, bl_map, lmax, Npix, bl_fwhm, mask_path=mask_path, mask=mask, rng=self.rng)
+        self.noise_pol0 = self.pol_centered_constraint_realizer.noise_pol0
+
+    def sample_no_mask(self, all_dls):
+        """Full sky, isotropic noise, everything in harmonic space (NonCenteredGibbs.py:138-176, all_sph branch)."""
+        c = self.pol_centered_constraint_realizer
+        if c.d_E is None:
+            raise _lib.GibbsB200Error("sample_no_mask needs pix_map['EE'] and pix_map['BB']")
+        dle, dlb = c._dls(all_dls)
+        w = self.Npix / (self.noise_pol0 * 4 * np.pi)
+        n = self.dimension_alm
+        xe, xb = self.rng.normal(n), self.rng.normal(n)
+        oe, ob = torch.empty_like(xe), torch.empty_like(xb)
+        L = _lib.lib()
+        check(L.gs_cr_direct(ptr(dle), ptr(self.bl_gauss_d), ptr(c.d_E), ptr(xe), w, self.lmax, 1, ptr(oe), stream()))
+        check(L.gs_cr_direct(ptr(dlb), ptr(self.bl_gauss_d), ptr(c.d_B), ptr(xb), w, self.lmax, 1, ptr(ob), stream()))
+        return c._ret({"EE": oe, "BB": ob}, all_dls["EE"]), 0
+
+    def sample_mask(self, all_dls):
+        """Centred PCG draw, then s_nc = C^-1/2 s (NonCenteredGibbs.py:178-195)."""
+        c = self.pol_centered_constraint_realizer
+        dle, dlb = c._dls(all_dls)
+        alms, _ = c.sample_mask({"EE": dle, "BB": dlb})
+        for pol, dl in (("EE", dle), ("BB", dlb)):
+            sq = utils.expand_per_l(dl, 4)
+            check(_lib.lib().gs_mul(ptr(alms[pol]), ptr(sq), ptr(alms[pol]), alms[pol].numel(), stream()))
+        return c._ret(alms, all_dls["EE"]), 1
+
+    def sample(self, all_dls):
+        if not self.masked:
+            return self.sample_no_mask(all_dls)
+        return self.sample_mask(all_dls)
+
+
+class PolarizationNonCenteredClsSampler(MHClsSampler):
+    def __init__(self, pix_map, lmax, nside, bins, bl_map, noise_I, noise_Q, metropolis_blocks, proposal_variances, n_iter=1,
+                 mask_path=None, polarization=True, all_sph=False, *, mask=None, rng="philox", seed=None, l_cut=0):
+        """Mirror of NonCenteredGibbs.py:256-289.  l_cut > 0 keeps l < l_cut centred (PNCP)."""
+        super().__init__(pix_map, lmax, nside, bins, bl_map, noise_I, metropolis_blocks, proposal_variances, n_iter=n_iter,
+                         polarization=polarization, mask=None, rng=rng, seed=seed)
+        self.noise_temp = noise_I
+        self.noise_pol = noise_Q
+        self.mask_path = mask_path
+        m = _dev.load_mask(mask_path, self.nside, mask)
+        self.inv_noise_pol = 1.0 / f64(noise_Q)
+        if self.inv_noise_pol.numel() == 1:
+            self.inv_noise_pol = self.inv_noise_pol.expand(12 * self.nside ** 2).contiguous()
+        if m is not None:
+            self.inv_noise_pol = self.inv_noise_pol * f64(m)
+        self.sigma = 0.8
+        self.Npix = 12 * nside ** 2
+        self.all_sph = all_sph
+        self.l_cut = int(l_cut)
+        if all_sph:
+            raise NotImplementedError("all_sph likelihood (NonCenteredGibbs.py:357-377) is not provided; use all_sph=False")
+        from .sht import Plan
+        self.plan = Plan.get(self.nside, self.lmax)
+        self.d_Q, self.d_U = f64(pix_map["Q"]), f64(pix_map["U"])
+        fw = getattr(self, "bl_gauss", None)
+        # b_l from the expanded bl_map: entries 0..lmax are the m = 0 column
+        self.bl_gauss_d = f64(bl_map)[: self.lmax + 1].contiguous()
+        self.bins_d = {p: _dev.i32(np.asarray(self.bins[p])) for p in ("EE", "BB")}
+        self.nb = {p: len(self.bins[p]) - 1 for p in ("EE", "BB")}
+        self.pv_d = {p: f64(self.proposal_variances[p]) for p in ("EE", "BB")}
+        self._mq = torch.empty(self.Npix, dtype=torch.float64, device=self.dev)
+        self._mu = torch.empty_like(self._mq)
+        self._flE = torch.empty(self.lmax + 1, dtype=torch.float64, device=self.dev)
+        self._flB = torch.empty_like(self._flE)
+        self._scratch = torch.empty(592, dtype=torch.float64, device=self.dev)
+
+    # ---- reference-named helpers -----------------------------------------------------------------
+    def propose_dl(self, dls_old):
+        """NonCenteredGibbs.py:292-309 (EE drawn first, then BB)."""
+        ee = self._propose(f64(dls_old["EE"]), self.pv_d["EE"])
+        bb = self._propose(f64(dls_old["BB"]), self.pv_d["BB"])
+        return {"EE": ee, "BB": bb}
+
+    def compute_log_proposal(self, dl_old, dl_new):
+        """NonCenteredGibbs.py:313-330: log q(dl_new | dl_old) per bin."""
+        return {p: self._log_proposal(f64(dl_new[p]), f64(dl_old[p]), self.pv_d[p]) for p in ("EE", "BB")}
+
+    def _loglik_device(self, cur, prop, pol, b0, b1, s_nc, out):
+        """log-likelihood of (cur with block [b0,b1) of `pol` replaced by prop) -> out[0] on the device."""
+        L = _lib.lib()
+        pe = prop["EE"] if prop is not None else None
+        pb = prop["BB"] if prop is not None else None
+        check(L.gs_mwg_filters(ptr(cur["EE"]), ptr(cur["BB"]), ptr(pe), ptr(pb), ptr(self.bins_d["EE"]), self.nb["EE"],
+                               ptr(self.bins_d["BB"]), self.nb["BB"], pol, b0, b1, ptr(self.bl_gauss_d), self.lmax, self.l_cut,
+                               ptr(self._flE), ptr(self._flB), stream()))
+        check(L.gs_alm2map_spin2_fl2(self.plan._h, ptr(s_nc["EE"]), ptr(s_nc["BB"]), GS_ALM_REAL, ptr(self._flE), ptr(self._flB),
+                                     ptr(self._mq), ptr(self._mu), stream()))
+        check(L.gs_loglik_pix(ptr(self.d_Q), ptr(self.d_U), ptr(self._mq), ptr(self._mu), ptr(self.inv_noise_pol), self.Npix,
+                              ptr(self._scratch), ptr(out), stream()))
+
+    def compute_log_likelihood(self, dls, s_nonCentered):
+        """NonCenteredGibbs.py:333-355 -> python float."""
+        cur = {p: f64(dls[p]) for p in ("EE", "BB")}
+        s = {p: f64(s_nonCentered[p]) for p in ("EE", "BB")}
+        out = torch.empty(1, dtype=torch.float64, device=self.dev)
+        self._loglik_device(cur, None, -1, 0, 0, s, out)
+        return float(out.item())
+
+    def sample(self, s_nonCentered, binned_dls_old):
+        """Blocked Metropolis-within-Gibbs sweep (NonCenteredGibbs.py:401-445); same return values."""
+        host = not isinstance(binned_dls_old["EE"], torch.Tensor)
+        L = _lib.lib()
+        s = {p: f64(s_nonCentered[p]) for p in ("EE", "BB")}
+        cur = {p: f64(binned_dls_old[p]).clone() for p in ("EE", "BB")}
+        prop = self.propose_dl(cur)
+        num = self.compute_log_proposal(prop, cur)
+        den = self.compute_log_proposal(cur, prop)
+        logr = {p: (num[p] - den[p]).contiguous() for p in ("EE", "BB")}
+        old_lik = torch.empty(1, dtype=torch.float64, device=self.dev)
+        new_lik = torch.empty(1, dtype=torch.float64, device=self.dev)
+        self._loglik_device(cur, None, -1, 0, 0, s, old_lik)
+        nblk = {p: len(self.metropolis_blocks[p]) - 1 for p in ("EE", "BB")}
+        ntot = (nblk["EE"] + nblk["BB"]) * self.n_iter
+        if self.rng.mode == "numpy":
+            u = f64(np.array([np.random.uniform() for _ in range(ntot)]))
+        else:
+            u = self.rng.uniform(max(ntot, 2))
+        acc = torch.zeros(max(ntot, 1), dtype=torch.int32, device=self.dev)
+        k = 0
+        for ip, pol in enumerate(("EE", "BB")):
+            blocks = self.metropolis_blocks[pol]
+            for i in range(nblk[pol]):
+                b0, b1 = int(blocks[i]), int(blocks[i + 1])
+                for _ in range(self.n_iter):
+                    self._loglik_device(cur, prop, ip, b0, b1, s, new_lik)
+                    check(L.gs_mwg_accept(ptr(cur[pol]), ptr(prop[pol]), ptr(logr[pol]), b0, b1, ptr(new_lik), ptr(old_lik),
+                                          ptr(u[k:]), ptr(acc[k:]), stream()))
+                    k += 1
+        a = acc.cpu().numpy()
+        ne = nblk["EE"] * self.n_iter
+        accept = {"EE": [int(x) for x in a[:ne]], "BB": [int(x) for x in a[ne:ntot]]}
+        if host:
+            return {p: cur[p].cpu().numpy() for p in cur}, accept
+        return cur, accept
+
+
+class NonCenteredGibbs(GibbsSampler):
+    def __init__(self, pix_map, noise_I, noise_Q, beam, nside, lmax, Npix, proposal_variances, metropolis_blocks=None,
+                 polarization=False, bins=None, n_iter=10000, n_iter_metropolis=1, mask_path=None, all_sph=False, *,
+                 mask=None, rng="philox", seed=None, verbose=False):
+        """Mirror of NonCenteredGibbs.__init__ (NonCenteredGibbs.py:450-486)."""
+        super().__init__(pix_map, noise_I, beam, nside, lmax, polarization=polarization, bins=bins, n_iter=n_iter, verbose=verbose)
+        if not polarization:
+            raise NotImplementedError("temperature-only samplers are not provided (reference TT path is dead at HEAD)")
+        shared = _dev.Rng(rng, seed)
+        self.constrained_sampler = PolarizedNonCenteredConstrainedRealization(pix_map, noise_I, noise_Q, self.bl_map, lmax, Npix, beam,
+                                                                              mask_path=mask_path, all_sph=all_sph, mask=mask, rng=shared)
+        self.cls_sampler = PolarizationNonCenteredClsSampler(pix_map, lmax, nside, self.bins, self.bl_map, noise_I, noise_Q,
+                                                             metropolis_blocks, proposal_variances, n_iter=n_iter_metropolis,
+                                                             mask_path=mask_path, all_sph=all_sph, mask=mask, rng=shared)
+
+    def run_polarization(self, dls_init):
+        """Mirror of NonCenteredGibbs.run_polarization (NonCenteredGibbs.py:529-571); same return tuple."""
+        h_duration_cr, h_duration_cls_sampling = [], []
+        total_accept = {"EE": [], "BB": []}
+        h_dls = {"EE": [], "BB": []}
+        binned_dls = {k: f64(v) for k, v in dls_init.items()}
+        dls_unbinned = {"EE": self._unfold(binned_dls, "EE"), "BB": self._unfold(binned_dls, "BB")}
+        h_dls["EE"].append(_dev.to_host(binned_dls["EE"]))
+        h_dls["BB"].append(_dev.to_host(binned_dls["BB"]))
+        for i in range(self.n_iter):
+            if self.verbose:
+                print("Non centered gibbs")
+                print(i)
+            s_nonCentered, _ = self.constrained_sampler.sample(dls_unbinned)
+            binned_dls, accept = self.cls_sampler.sample(s_nonCentered, binned_dls)
+            dls_unbinned = {"EE": self._unfold(binned_dls, "EE"), "BB": self._unfold(binned_dls, "BB")}
+            total_accept["EE"].append(accept["EE"])
+            total_accept["BB"].append(accept["BB"])
+            h_dls["EE"].append(_dev.to_host(binned_dls["EE"]))
+            h_dls["BB"].append(_dev.to_host(binned_dls["BB"]))
+        total_accept = {"EE": np.array(total_accept["EE"]), "BB": np.array(total_accept["BB"])}
+        h_dls["EE"] = np.array(h_dls["EE"])
+        h_dls["BB"] = np.array(h_dls["BB"])
+        return h_dls, total_accept, np.array(h_duration_cr), np.array(h_duration_cls_sampling)

@@ -54,6 +54,9 @@ SIGNATURES = {
     "gs_randn": (_i, [_vp, _i64, C.c_uint64, C.c_uint64, _vp]),
     "gs_randu": (_i, [_vp, _i64, C.c_uint64, C.c_uint64, _vp]),
     "gs_sum": (_i, [_vp, _i64, _vp, _vp, _vp]),
+    "gs_mwg_filters": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "gs_mwg_accept": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "gs_mul": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "gs_launch_count": (C.c_longlong, []),
     "gs_profile_matvec": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(C.c_float), _vp]),
     "gs_measure_fp64_peak": (_i, [C.POINTER(_d), _vp]),

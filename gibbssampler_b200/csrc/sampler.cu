@@ -316,3 +316,82 @@ extern "C" int gs_truncnorm_logpdf(const double* x, const double* from, const do
     GS_CHECK_LAUNCH();
     return GS_OK;
 }
+
+// ------------------------------------------------------------------ Metropolis-within-Gibbs on binned D_l
+// (PolarizationNonCenteredClsSampler.sample, NonCenteredGibbs.py:401-445; blocks index the BINNED arrays)
+__device__ __forceinline__ double binned_value(const double* cur, const double* prop, const int* bins, int nbins,
+                                               int l, bool use_prop, int b0, int b1)
+{
+    if (l < bins[0] || l >= bins[nbins]) return 0.0;
+    int lo = 0, hi = nbins - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (bins[mid] <= l) lo = mid; else hi = mid - 1; }
+    return (use_prop && lo >= b0 && lo < b1) ? prop[lo] : cur[lo];
+}
+
+// Per-l synthesis filters of the candidate state: cand = cur with bins [b0,b1) of spectrum `pol` (0 = EE,
+// 1 = BB, -1 = none) replaced by the proposal.  fl_X[l] = b_l sqrt(C^X_l), C_l = D_l 2pi/(l(l+1)); for
+// l < l_cut (partially non-centred parametrisation) fl_X[l] = b_l.
+__global__ void mwg_filters_kernel(const double* cur_E, const double* cur_B, const double* prop_E, const double* prop_B,
+                                   const int* bins_E, int nb_E, const int* bins_B, int nb_B, int pol, int b0, int b1,
+                                   const double* bl, int L, int l_cut, double* flE, double* flB)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > L) return;
+    double dE = binned_value(cur_E, prop_E, bins_E, nb_E, l, pol == 0, b0, b1);
+    double dB = binned_value(cur_B, prop_B, bins_B, nb_B, l, pol == 1, b0, b1);
+    const double f = l ? 2.0 * 3.14159265358979323846 / ((double)l * (double)(l + 1)) : 1.0;
+    flE[l] = bl[l] * (l < l_cut ? 1.0 : sqrt(dE * f));
+    flB[l] = bl[l] * (l < l_cut ? 1.0 : sqrt(dB * f));
+}
+
+// One Metropolis accept/reject of block [b0,b1) of spectrum pol, entirely on the device:
+//   log r = sum_{b in block} logr[b] + new_lik - old_lik ; accept iff log(u) < log r
+__global__ void mwg_accept_kernel(double* cur, const double* prop, const double* logr, int b0, int b1,
+                                  const double* new_lik, double* old_lik, const double* u, int* accept_out)
+{
+    if (blockIdx.x || threadIdx.x) return;
+    double s = 0.0;
+    for (int b = b0; b < b1; ++b) s += logr[b];
+    const double log_r = s + (new_lik[0] - old_lik[0]);
+    const bool acc = log(u[0]) < log_r;
+    if (acc) {
+        for (int b = b0; b < b1; ++b) cur[b] = prop[b];
+        old_lik[0] = new_lik[0];
+    }
+    accept_out[0] = acc ? 1 : 0;
+}
+
+__global__ void mul_kernel(const double* a, const double* b, double* out, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = a[i] * b[i];
+}
+
+extern "C" int gs_mwg_filters(const double* cur_E, const double* cur_B, const double* prop_E, const double* prop_B,
+                              const int* bins_E, int nbins_E, const int* bins_B, int nbins_B, int pol, int b_start,
+                              int b_end, const double* bl, int lmax, int l_cut, double* flE, double* flB, void* stream)
+{
+    GS_REQUIRE(cur_E && cur_B && bins_E && bins_B && bl && flE && flB && nbins_E >= 1 && nbins_B >= 1 && lmax >= 0, "bad arguments");
+    GS_REQUIRE(pol == -1 || ((pol == 0 || pol == 1) && prop_E && prop_B && b_start >= 0 && b_end >= b_start), "bad block");
+    mwg_filters_kernel<<<(lmax + 128) / 128, 128, 0, STREAM(stream)>>>(cur_E, cur_B, prop_E, prop_B, bins_E, nbins_E, bins_B, nbins_B,
+                                                                       pol, b_start, b_end, bl, lmax, l_cut, flE, flB);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+extern "C" int gs_mwg_accept(double* cur, const double* prop, const double* logr, int b_start, int b_end,
+                             const double* new_lik, double* old_lik, const double* u, int* accept_out, void* stream)
+{
+    GS_REQUIRE(cur && prop && logr && new_lik && old_lik && u && accept_out && b_start >= 0 && b_end >= b_start, "bad arguments");
+    mwg_accept_kernel<<<1, 32, 0, STREAM(stream)>>>(cur, prop, logr, b_start, b_end, new_lik, old_lik, u, accept_out);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+extern "C" int gs_mul(const double* a, const double* b, double* out, int64_t n, void* stream)
+{
+    GS_REQUIRE(a && b && out && n >= 0, "bad arguments");
+    if (n == 0) return GS_OK;
+    mul_kernel<<<nblk(n), SM_NT, 0, STREAM(stream)>>>(a, b, out, n);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}

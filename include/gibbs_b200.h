@@ -183,6 +183,24 @@ int gs_truncnorm_logpdf(const double* x, const double* from, const double* prop_
 int gs_loglik_pix(const double* d_Q, const double* d_U, const double* m_Q, const double* m_U,
                   const double* inv_noise, int64_t npix, double* scratch, double* out, void* stream);
 
+/* ---- Metropolis-within-Gibbs on the binned D_l, device resident ---------------------------- */
+/* Per-l synthesis filters fl_X[l] = b_l sqrt(C^X_l) of the candidate state = current binned D_l
+ * with bins [b_start, b_end) of spectrum pol (0 EE, 1 BB, -1 none) replaced by the proposal; they feed
+ * gs_alm2map_spin2_fl2 for the likelihood of NonCenteredGibbs.py:333-355 (unfold_bins +
+ * generate_var_cl + bl_map * sqrt(var_cls) fused per l).  l < l_cut keeps fl = b_l (partially
+ * non-centred parametrisation, PNCP); pass l_cut = 0 for the fully non-centred sampler. */
+int gs_mwg_filters(const double* cur_E, const double* cur_B, const double* prop_E, const double* prop_B,
+                   const int* bins_E, int nbins_E, const int* bins_B, int nbins_B, int pol, int b_start,
+                   int b_end, const double* bl, int lmax, int l_cut, double* flE, double* flB,
+                   void* stream);
+/* Accept/reject of one block (NonCenteredGibbs.py:421-442) without leaving the device:
+ * log r = sum_{b in block} logr[b] + new_lik - old_lik; if log(u[0]) < log r the block of `cur` is
+ * overwritten with the proposal and old_lik[0] = new_lik[0]; accept_out[0] = 0/1. */
+int gs_mwg_accept(double* cur, const double* prop, const double* logr, int b_start, int b_end,
+                  const double* new_lik, double* old_lik, const double* u, int* accept_out, void* stream);
+/* out = a * b elementwise (re-centring s = sqrt(C) s_nc, ASIS.py:181-203; NonCenteredGibbs.py:192-194). */
+int gs_mul(const double* a, const double* b, double* out, int64_t n, void* stream);
+
 /* ---- random numbers / reductions --------------------------------------------------------- */
 /* n standard normals (Philox4x32-10 keyed by (seed, stream_id), Box-Muller); replaces
  * np.random.normal in production runs. */

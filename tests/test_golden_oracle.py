@@ -1,0 +1,76 @@
+"""CPU: pins the oracle's numpy restatement (oracle/reference_logic.py) to golden vectors produced by the
+REFERENCE'S OWN modules (tests/golden/make_golden.py ran /root/reference/*.py unmodified, with healpy /
+qcinv stubbed by the oracle SHT).  Integer/index work must be bit-exact, FP64 within 1e-12."""
+import os
+
+import numpy as np
+import pytest
+from scipy.stats import invgamma, truncnorm
+
+from oracle import reference_logic as R
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_nside4.npz"))
+NSIDE, LMAX = 4, 8
+NPIX, NRE = 12 * NSIDE ** 2, (LMAX + 1) ** 2
+
+
+def test_layout_helpers_bit_exact():
+    for L in (2, 3, 4, 7, 8):
+        assert np.array_equal(R.real_to_complex(G["r2c_in_%d" % L]), G["r2c_out_%d" % L])
+        assert np.array_equal(R.complex_to_real(G["r2c_out_%d" % L]), G["c2r_out_%d" % L])
+        assert np.array_equal(R.generate_var_cl(G["varcl_in_%d" % L]), G["varcl_out_%d" % L])
+    assert np.array_equal(R.unfold_bins(G["unfold_in"], G["bins_BB"]), G["unfold_out"])
+    from oracle import sht as O
+    assert np.array_equal(R.expand_per_l(O.gauss_beam(np.radians(float(G["fwhm"])), LMAX)), G["bl_map"])
+
+
+def problem():
+    return R.PolProblem(NSIDE, LMAX, G["dQ"], G["dU"], G["mask"] / G["noise_pol"], float(G["fwhm"]))
+
+
+def test_rhs_and_pcg_solution_match_reference_sample_mask():
+    prob = problem()
+    assert np.allclose(prob.bdata_E, G["second_part_grad_E"], rtol=1e-12, atol=1e-14)
+    np.random.seed(int(G["sample_mask_seed"]))
+    xi_Q, xi_U = np.random.normal(size=NPIX), np.random.normal(size=NPIX)        # RNG order of CenteredGibbs.py:471-479
+    xi_E, xi_B = np.random.normal(size=NRE), np.random.normal(size=NRE)
+    bE, bB = prob.rhs(G["dls_EE"], G["dls_BB"], xi_Q, xi_U, xi_E, xi_B)
+    assert np.allclose(bE, G["sample_mask_rhs_E"], rtol=1e-12, atol=1e-13)
+    assert np.allclose(bB, G["sample_mask_rhs_B"], rtol=1e-12, atol=1e-13)
+    xE, xB, it, res = prob.pcg(G["dls_EE"], G["dls_BB"], bE, bB, eps=1e-13)
+    assert np.allclose(xE, G["sample_mask_E"], rtol=1e-9, atol=1e-11)
+    assert np.allclose(xB, G["sample_mask_B"], rtol=1e-9, atol=1e-11)
+
+
+def test_direct_solve_matches_reference_sample_no_mask():
+    np.random.seed(int(G["sample_no_mask_seed"]))
+    xiE, xiB = np.random.normal(size=NRE), np.random.normal(size=NRE)
+    e = R.sample_no_mask(G["dls_EE"], G["bl_map"], G["dE"], xiE, NPIX, G["noise_pol"][0])
+    b = R.sample_no_mask(G["dls_BB"], G["bl_map"], G["dB"], xiB, NPIX, G["noise_pol"][0])
+    assert np.allclose(e, G["sample_no_mask_E"], rtol=1e-13, atol=0) and np.allclose(b, G["sample_no_mask_B"], rtol=1e-13, atol=0)
+
+
+def test_cls_draw_matches_reference():
+    np.random.seed(int(G["cls_sample_seed"]))
+    for pol, key in (("EE", "sample_mask_E"), ("BB", "sample_mask_B")):
+        a, b = R.cls_alpha_beta(G[key], G["bins_" + pol], LMAX)
+        d = b * invgamma.rvs(a=a)
+        d[:2] = 0
+        assert np.allclose(d, G["cls_sample_" + pol], rtol=1e-12, atol=0)
+
+
+def test_noncentred_likelihood_and_proposals_match_reference():
+    prob = problem()
+    bins = {"EE": G["bins_EE"], "BB": G["bins_BB"]}
+    old = {"EE": G["binned_old_EE"], "BB": G["binned_old_BB"]}
+    s_nc = {"EE": G["s_nc_E"], "BB": G["s_nc_B"]}
+    assert abs(R.nc_loglik(old, bins, s_nc, prob) - float(G["loglik_old"])) < 1e-10 * abs(float(G["loglik_old"]))
+    prop = {"EE": G["propose_EE"], "BB": G["propose_BB"]}
+    assert abs(R.nc_loglik(prop, bins, s_nc, prob) - float(G["loglik_prop"])) < 1e-10 * abs(float(G["loglik_prop"]))
+    np.random.seed(int(G["propose_seed"]))
+    for pol in ("EE", "BB"):
+        sc = np.sqrt(G["prop_var_" + pol])
+        new = np.concatenate([np.zeros(2), truncnorm.rvs(a=-old[pol][2:] / sc, b=np.inf, loc=old[pol][2:], scale=sc)])
+        assert np.array_equal(new, prop[pol])
+        lp = np.concatenate([np.zeros(2), truncnorm.logpdf(prop[pol][2:], a=-old[pol][2:] / sc, b=np.inf, loc=old[pol][2:], scale=sc)])
+        assert np.allclose(lp, G["logprop_" + pol], rtol=1e-13)
