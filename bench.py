@@ -151,6 +151,24 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def chain_seed(rank):
+    """Philox seed of the chain owned by `rank` (same data on every rank, independent chains)."""
+    return 1000 + rank
+
+
+def reduce_max_ms(ms_tensor, world):
+    """Max over ranks of the device-timed duration (ms); no-op for one rank."""
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(ms_tensor, op=dist.ReduceOp.MAX)
+    return float(ms_tensor.item())
+
+
+def whole_job_value(world, steps, ms):
+    """Whole-job throughput: steps of all ranks / max-over-ranks time."""
+    return world * steps / (ms * 1e-3)
+
+
 def workload_config(args, n_pcg):
     return {"workload": "CenteredGibbs polarised masked sky: PCG constrained realization (eps 1e-5, diag_cl precond) + inverse-gamma C_l draw; "
                         "one independent chain per GPU",
@@ -209,7 +227,7 @@ def main():
     bl_map = utils.expand_per_l(_dev.f64(bl), 0)
     noise_pol = torch.full((npix,), noise_var, dtype=torch.float64, device=dev)
     cr = PolarizedCenteredConstrainedRealization({"Q": dQ, "U": dU}, noise_pol * 1e4, noise_pol, bl_map, lmax, npix, fwhm,
-                                                 mask=mask, rng="philox", seed=1000 + rank)
+                                                 mask=mask, rng="philox", seed=chain_seed(rank))
     cls = PolarizedCenteredClsSampler({"Q": dQ, "U": dU}, lmax, nside, bins, bl_map, noise_pol, mask=mask, rng=cr.rng)
 
     def binned_init():
@@ -257,8 +275,7 @@ def main():
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.barrier()
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return reduce_max_ms(ms, world)
 
     clocks = ClockSampler(local)
     clocks.start()
@@ -273,9 +290,9 @@ def main():
 
     state["binned_host"] = {k: v.cpu().numpy() for k, v in state["binned"].items()}
     ms_e2e = timed(step_e2e, 1, max(1, args.steps))
-    e2e_val = world * max(1, args.steps) / (ms_e2e * 1e-3)
+    e2e_val = whole_job_value(world, max(1, args.steps), ms_e2e)
 
-    value = world * args.steps / (ms_total * 1e-3)
+    value = whole_job_value(world, args.steps, ms_total)
     n_pcg = int(round(float(np.mean(its_timed)))) if its_timed else 0
 
     # ---- per-kernel timing of one PCG mat-vec (CUDA events on the launching stream) + roofline

@@ -38,7 +38,10 @@ __global__ void real_to_complex_kernel(const double* __restrict__ r, double2* __
         if (i <= L) c[i] = make_double2(r[i], 0.0);
         else {
             const int64_t o = 2 * i - (L + 1);
-            c[i] = make_double2(r[o] * 0.70710678118654752440, r[o + 1] * 0.70710678118654752440);
+            // utils.py:59 divides a complex array by np.sqrt(2): numpy's complex division multiplies by the
+            // rounded reciprocal 1.0 / sqrt(2) (one ulp below the correctly rounded 1/sqrt2)
+            const double scl = 1.0 / 1.4142135623730951;
+            c[i] = make_double2(r[o] * scl, r[o + 1] * scl);
         }
     }
 }
