@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "_build", "libgibbs_b200.so")
+LIB_PATH = os.environ.get("GIBBS_B200_LIB") or os.path.join(_HERE, "csrc", "_build", "libgibbs_b200.so")
 
 GS_ALM_COMPLEX = 0
 GS_ALM_REAL = 1

@@ -22,8 +22,17 @@
 #define LEG_NT 128   // threads per block
 #define LEG_NW (LEG_NT / 32)
 #define LEG_TL 128   // l-tile (even)
-#define LEG_R 2      // ring pairs per thread  (LEG_NT * LEG_R = 256 = ring pairs per analysis chunk)
+#ifndef LEG_R
+#define LEG_R 2      // ring pairs per thread (synthesis)
+#endif
+#ifndef LEG_RA
+#define LEG_RA 4     // ring pairs per thread (analysis); LEG_NT * LEG_RA ring pairs per partial chunk
+#endif
+#ifndef LEG_UA
+#define LEG_UA 1     // unroll of the analysis fast loop
+#endif
 #define FULL 0xffffffffu
+constexpr int kUnrollA = LEG_UA;
 
 __device__ __forceinline__ double pow2i(int e) { return __hiloint2double((e + 1023) << 20, 0); }
 
@@ -159,7 +168,13 @@ __device__ __forceinline__ void stage_alm_tile(const PlanDev& P, int m, int lt, 
                 if (SPIN) { b.x = almB[off]; b.y = almB[off + 1]; }
             }
             e.x *= pre; e.y *= pre; b.x *= preb; b.y *= preb;
-            if (SPIN) r = P.rec2[id]; else r.x = P.rec0[id];
+            if (SPIN) {
+                // lambda^+- basis: Q_m = sum l+ (E' + iB') + l- (E' - iB'), U_m = -i [l+ (E' + iB') - l- (E' - iB')]
+                // -> c1 = E'r - B'i, c2 = E'r + B'i, c3 = E'i + B'r, c4 = E'i - B'r
+                const double2 c12 = make_double2(e.x - b.y, e.x + b.y), c34 = make_double2(e.y + b.x, e.y - b.x);
+                e = c12; b = c34;
+                r = P.rec2[id];
+            } else r.x = P.rec0[id];
         }
         sE[i] = e;
         if (SPIN) sB[i] = b;
@@ -169,12 +184,16 @@ __device__ __forceinline__ void stage_alm_tile(const PlanDev& P, int m, int lt, 
 
 // ------------------------------------------------------------------ synthesis
 template <int SPIN>
-struct SynthAcc {  // first-l parity part (S) and the other one (A); q = Q or T, u = U
+struct SynthAcc {
+    // spin 0: (sqr,sqi) first-l-parity part, (aqr,aqi) other parity.
+    // spin 2: north sums x1..x4 = sum l+ c1, l- c2, l+ c3, l- c4 ; south sums z1..z4 = sum s (l- c1, l+ c2, l- c3, l+ c4),
+    //         s = +-1 alternating with l (lam^+-(pi - theta) = (-1)^(l+m) lam^-+(theta)); Q, U follow from
+    //         Qr = 1+2, Qi = 3+4, Ur = 3-4, Ui = 2-1: 8 FMAs per l serve both hemispheres, no F1/F2 adds.
     double sqr, sqi, aqr, aqi;
     double sur, sui, aur, aui;
 };
 
-// accumulate l with "F1 -> s*, F2 -> a*" (FIRST = true) or swapped roles
+// accumulate one l; FIRST = same parity as the first l of this m
 template <int SPIN, bool FIRST>
 __device__ __forceinline__ void synth_acc(SynthAcc<SPIN>& A, double pc, double mc, double2 e, double2 b)
 {
@@ -182,18 +201,15 @@ __device__ __forceinline__ void synth_acc(SynthAcc<SPIN>& A, double pc, double m
         if (FIRST) { A.sqr = fma(e.x, pc, A.sqr); A.sqi = fma(e.y, pc, A.sqi); }
         else       { A.aqr = fma(e.x, pc, A.aqr); A.aqi = fma(e.y, pc, A.aqi); }
     } else {
-        const double f1 = pc + mc, f2 = pc - mc;
-        // Q_m += E' F1 + i B' F2 ; U_m += B' F1 - i E' F2   (E', B' carry -alpha/2)
+        // e = (c1, c2), b = (c3, c4); north: sqr=x1 sqi=x2 sur=x3 sui=x4 ; south: aqr=z1 aqi=z2 aur=z3 aui=z4
+        A.sqr = fma(pc, e.x, A.sqr); A.sqi = fma(mc, e.y, A.sqi);
+        A.sur = fma(pc, b.x, A.sur); A.sui = fma(mc, b.y, A.sui);
         if (FIRST) {
-            A.sqr = fma(e.x, f1, A.sqr); A.sqi = fma(e.y, f1, A.sqi);
-            A.sur = fma(b.x, f1, A.sur); A.sui = fma(b.y, f1, A.sui);
-            A.aqr = fma(-b.y, f2, A.aqr); A.aqi = fma(b.x, f2, A.aqi);
-            A.aur = fma(e.y, f2, A.aur); A.aui = fma(-e.x, f2, A.aui);
+            A.aqr = fma(mc, e.x, A.aqr); A.aqi = fma(pc, e.y, A.aqi);
+            A.aur = fma(mc, b.x, A.aur); A.aui = fma(pc, b.y, A.aui);
         } else {
-            A.aqr = fma(e.x, f1, A.aqr); A.aqi = fma(e.y, f1, A.aqi);
-            A.aur = fma(b.x, f1, A.aur); A.aui = fma(b.y, f1, A.aui);
-            A.sqr = fma(-b.y, f2, A.sqr); A.sqi = fma(b.x, f2, A.sqi);
-            A.sur = fma(e.y, f2, A.sur); A.sui = fma(-e.x, f2, A.sui);
+            A.aqr = fma(-mc, e.x, A.aqr); A.aqi = fma(-pc, e.y, A.aqi);
+            A.aur = fma(-mc, b.x, A.aur); A.aui = fma(-pc, b.y, A.aui);
         }
     }
 }
@@ -288,7 +304,8 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
         }
     }
 
-    // north = S + A ; south = +-(S - A), sign from the parity of the first l
+    // spin 0: north = S + A, south = +-(S - A); spin 2: combine the lambda^+- sums; the south sign follows the
+    // parity of the first l
     const double sg = ((l0 + m) & 1) ? -1.0 : 1.0;
     const int64_t nm = L + 1;
 #pragma unroll
@@ -296,24 +313,35 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
         const int p = chunk + j * LEG_NT + tid;
         if (p >= P.npair) continue;
         const int rn = p, rs = P.nring - 1 - p;
-        Fm[(int64_t)rn * nm + m] = make_double2(acc[j].sqr + acc[j].aqr, acc[j].sqi + acc[j].aqi);
-        if (rs != rn) Fm[(int64_t)rs * nm + m] = make_double2(sg * (acc[j].sqr - acc[j].aqr), sg * (acc[j].sqi - acc[j].aqi));
-        if (SPIN) {
+        const SynthAcc<SPIN>& a = acc[j];
+        if (SPIN == 0) {
+            Fm[(int64_t)rn * nm + m] = make_double2(a.sqr + a.aqr, a.sqi + a.aqi);
+            if (rs != rn) Fm[(int64_t)rs * nm + m] = make_double2(sg * (a.sqr - a.aqr), sg * (a.sqi - a.aqi));
+        } else {
             double2* Fu = Fm + (int64_t)P.nring * nm;
-            Fu[(int64_t)rn * nm + m] = make_double2(acc[j].sur + acc[j].aur, acc[j].sui + acc[j].aui);
-            if (rs != rn) Fu[(int64_t)rs * nm + m] = make_double2(sg * (acc[j].sur - acc[j].aur), sg * (acc[j].sui - acc[j].aui));
+            Fm[(int64_t)rn * nm + m] = make_double2(a.sqr + a.sqi, a.sur + a.sui);
+            Fu[(int64_t)rn * nm + m] = make_double2(a.sur - a.sui, a.sqi - a.sqr);
+            if (rs != rn) {
+                Fm[(int64_t)rs * nm + m] = make_double2(sg * (a.aqr + a.aqi), sg * (a.aur + a.aui));
+                Fu[(int64_t)rs * nm + m] = make_double2(sg * (a.aur - a.aui), sg * (a.aqi - a.aqr));
+            }
         }
     }
 }
 
 // ------------------------------------------------------------------ analysis
 template <int SPIN>
-struct AnalIn {  // ring spectra combined for the first-l parity (1) and the other parity (2)
+struct AnalIn {
+    // spin 0: (q1r,q1i) ring spectrum combined for the first-l parity, (q2r,q2i) for the other one.
+    // spin 2 (lambda^+- basis): k1 = Gq.r - Gu.i, k2 = Gq.r + Gu.i, k3 = Gq.i + Gu.r, k4 = Gq.i - Gu.r of the
+    //         north ring (q1r,q1i,q2r,q2i) and of the south ring (u1r,u1i,u2r,u2i; sign of the first l folded in).
     double q1r, q1i, q2r, q2i;
     double u1r, u1i, u2r, u2i;
 };
 
-// contributions of one ring to (E.re, E.im, B.re, B.im) [spin 2] or (re, im) [spin 0] at one l
+// contributions of one ring pair at one l: spin 0 -> (re, im); spin 2 -> (Y1..Y4) with
+//   Y1 = l+ k1n + s l- k1s, Y2 = l- k2n + s l+ k2s, Y3 = l+ k3n + s l- k3s, Y4 = l- k4n + s l+ k4s
+// (E.re = Y1+Y2, E.im = Y3+Y4, B.re = Y3-Y4, B.im = Y2-Y1 are formed once per (l,m) in the finish kernel)
 template <int SPIN, bool FIRST, bool INIT>
 __device__ __forceinline__ void anal_acc(double* o, const AnalIn<SPIN>& G, double pc, double mc)
 {
@@ -322,19 +350,13 @@ __device__ __forceinline__ void anal_acc(double* o, const AnalIn<SPIN>& G, doubl
         o[0] = INIT ? gr * pc : fma(gr, pc, o[0]);
         o[1] = INIT ? gi * pc : fma(gi, pc, o[1]);
     } else {
-        const double f1 = pc + mc, f2 = pc - mc;
-        // E = F1 Gq + i F2 Gu ; B = F1 Gu - i F2 Gq  (times -alpha/2 in the finish kernel);
-        // F1 pairs with this l's parity, F2 with the opposite one
-        const double aqr = FIRST ? G.q1r : G.q2r, aqi = FIRST ? G.q1i : G.q2i;
-        const double aur = FIRST ? G.u1r : G.u2r, aui = FIRST ? G.u1i : G.u2i;
-        const double bqr = FIRST ? G.q2r : G.q1r, bqi = FIRST ? G.q2i : G.q1i;
-        const double bur = FIRST ? G.u2r : G.u1r, bui = FIRST ? G.u2i : G.u1i;
-        if (INIT) { o[0] = aqr * f1; o[1] = aqi * f1; o[2] = aur * f1; o[3] = aui * f1; }
-        else { o[0] = fma(aqr, f1, o[0]); o[1] = fma(aqi, f1, o[1]); o[2] = fma(aur, f1, o[2]); o[3] = fma(aui, f1, o[3]); }
-        o[0] = fma(-bui, f2, o[0]);
-        o[1] = fma(bur, f2, o[1]);
-        o[2] = fma(bqi, f2, o[2]);
-        o[3] = fma(-bqr, f2, o[3]);
+        if (INIT) { o[0] = pc * G.q1r; o[1] = mc * G.q1i; o[2] = pc * G.q2r; o[3] = mc * G.q2i; }
+        else { o[0] = fma(pc, G.q1r, o[0]); o[1] = fma(mc, G.q1i, o[1]); o[2] = fma(pc, G.q2r, o[2]); o[3] = fma(mc, G.q2i, o[3]); }
+        if (FIRST) {
+            o[0] = fma(mc, G.u1r, o[0]); o[1] = fma(pc, G.u1i, o[1]); o[2] = fma(mc, G.u2r, o[2]); o[3] = fma(pc, G.u2i, o[3]);
+        } else {
+            o[0] = fma(-mc, G.u1r, o[0]); o[1] = fma(-pc, G.u1i, o[1]); o[2] = fma(-mc, G.u2r, o[2]); o[3] = fma(-pc, G.u2i, o[3]);
+        }
     }
 }
 
@@ -411,15 +433,17 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
             const int rn = p, rs = P.nring - 1 - p;
             const double2 z = make_double2(0.0, 0.0);
             const double2 qn = Fm[(int64_t)rn * nm + m], qs = (rs != rn) ? Fm[(int64_t)rs * nm + m] : z;
-            double2 sy = make_double2(qn.x + qs.x, qn.y + qs.y), an = make_double2(qn.x - qs.x, qn.y - qs.y);
-            G[j].q1r = odd0 ? an.x : sy.x; G[j].q1i = odd0 ? an.y : sy.y;
-            G[j].q2r = odd0 ? sy.x : an.x; G[j].q2i = odd0 ? sy.y : an.y;
-            if (SPIN) {
+            if (SPIN == 0) {
+                const double2 sy = make_double2(qn.x + qs.x, qn.y + qs.y), an = make_double2(qn.x - qs.x, qn.y - qs.y);
+                G[j].q1r = odd0 ? an.x : sy.x; G[j].q1i = odd0 ? an.y : sy.y;
+                G[j].q2r = odd0 ? sy.x : an.x; G[j].q2i = odd0 ? sy.y : an.y;
+            } else {
                 const double2* Fu = Fm + (int64_t)P.nring * nm;
                 const double2 un = Fu[(int64_t)rn * nm + m], us = (rs != rn) ? Fu[(int64_t)rs * nm + m] : z;
-                sy = make_double2(un.x + us.x, un.y + us.y); an = make_double2(un.x - us.x, un.y - us.y);
-                G[j].u1r = odd0 ? an.x : sy.x; G[j].u1i = odd0 ? an.y : sy.y;
-                G[j].u2r = odd0 ? sy.x : an.x; G[j].u2i = odd0 ? sy.y : an.y;
+                const double sg = odd0 ? -1.0 : 1.0;
+                G[j].q1r = qn.x - un.y; G[j].q1i = qn.x + un.y; G[j].q2r = qn.y + un.x; G[j].q2i = qn.y - un.x;
+                G[j].u1r = sg * (qs.x - us.y); G[j].u1i = sg * (qs.x + us.y);
+                G[j].u2r = sg * (qs.y + us.x); G[j].u2i = sg * (qs.y - us.x);
             }
         }
     }
@@ -480,6 +504,7 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
             if (writer) myPart[ip * NVAL + vidx] = s;
             ++ip;
         }
+#pragma unroll kUnrollA
         for (; ip < npr; ++ip) {  // (C)
             double v[NVAL];
             const double2 r0 = sR[2 * ip], r1 = sR[2 * ip + 1];
@@ -527,6 +552,10 @@ __global__ void leg_finish_kernel(PlanDev P, const double* __restrict__ partial,
 #pragma unroll
             for (int c = 0; c < NV; ++c) v[c] += q[c];
         }
+        if (SPIN) {  // E.re = Y1+Y2, E.im = Y3+Y4, B.re = Y3-Y4, B.im = Y2-Y1
+            const double y1 = v[0], y2 = v[1], y3 = v[2], y4 = v[3];
+            v[0] = y1 + y2; v[1] = y3 + y4; v[2] = y3 - y4; v[3] = y2 - y1;
+        }
         double post = scale * (SPIN ? -0.5 * P.alpha2[id] : P.alpha0[id]);
         if (fl) post *= fl[l];
         if (layout == GS_ALM_REAL && m > 0) post *= 1.41421356237309504880;
@@ -573,16 +602,16 @@ int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, i
 int gs_leg_anal(gs_plan* p, int spin, double* almE, double* almB, int layout, const double* fl, double scale,
                 int accumulate, cudaStream_t st, const int* skip)
 {
-    const int nchunk = (p->d.npair + LEG_NT * LEG_R - 1) / (LEG_NT * LEG_R);
+    const int nchunk = (p->d.npair + LEG_NT * LEG_RA - 1) / (LEG_NT * LEG_RA);
     if (nchunk > p->anal_chunks) { gs_set_error("gs_leg_anal: workspace too small"); return GS_E_BADARG; }
     dim3 grid(nchunk, p->d.lmax + 1);
     dim3 fgrid((p->d.lmax + 256) / 256, p->d.lmax + 1);
     if (spin == 0) {
-        leg_anal_kernel<0, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip);
+        leg_anal_kernel<0, LEG_RA><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip);
         GS_CHECK_LAUNCH();
         leg_finish_kernel<0><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip);
     } else {
-        leg_anal_kernel<2, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip);
+        leg_anal_kernel<2, LEG_RA><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip);
         GS_CHECK_LAUNCH();
         leg_finish_kernel<2><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip);
     }

@@ -225,8 +225,8 @@ extern "C" int gs_plan_create(gs_plan** out, int nside, int lmax, int device)
     if (rc == GS_OK) {
         const int64_t nm = lmax + 1;
         rc = dev_alloc(p, (size_t)2 * p->d.nring * nm, &p->Fm);
-        // analysis: ring pairs are split in chunks of 256 per block (see legendre.cu)
-        p->anal_chunks = (p->d.npair + 255) / 256;
+        // analysis: ring pairs are split in chunks of >= 128 per block (see legendre.cu)
+        p->anal_chunks = (p->d.npair + 127) / 128;
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->anal_chunks * p->d.nalm * 4, &p->partial);
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->d.npix, &p->mapQ_tmp);
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->d.npix, &p->mapU_tmp);

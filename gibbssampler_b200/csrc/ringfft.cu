@@ -25,69 +25,132 @@ __device__ __forceinline__ double2 cmulc(double2 a, double2 b) { return make_dou
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 
-// In-place forward DIF FFT (kernel exp(-2 pi i jk/M)), natural order in, bit-reversed order out.
-__device__ void fft_dif(double2* buf, int M, const double2* __restrict__ tw, int twn)
+// ---- shared-memory FFT core -------------------------------------------------------------------
+// Twiddles: quarter table twq[k] = exp(-2 pi i k / twn), k <= twn/4, staged in shared memory by the
+// caller; W^(k + twn/4) = -i W^k gives the second quadrant (all the radix-4 butterflies need).
+// Every pass loads up to RF_U radix-4 butterflies per thread before computing any of them, so the
+// shared-memory round trips of the butterflies overlap instead of serialising (the compiler cannot
+// hoist loads above stores to the same buffer by itself).
+#define RF_U 2
+
+__device__ __forceinline__ double2 tw_get(const double2* twq, int idx, int quarter)
 {
+    if (idx < quarter) return twq[idx];
+    const double2 w = twq[idx - quarter];
+    return make_double2(w.y, -w.x);  // -i w
+}
+
+// one radix-4 DIF pass (sub-transform size N) of an M-point transform; POST: multiply outputs by post[index]
+template <bool POST>
+__device__ __forceinline__ void dif4_pass(double2* buf, int M, int N, const double2* twq, int twn,
+                                          const double2* __restrict__ post)
+{
+    const int q = N >> 2, lq = 31 - __clz(q), ts = twn / N, quarter = twn >> 2, nq = M >> 2;
+    for (int t0 = 0; t0 < nq; t0 += RF_NT * RF_U) {
+        double2 a[RF_U][4], w1[RF_U], w2[RF_U];
+        int i0[RF_U];
+#pragma unroll
+        for (int u = 0; u < RF_U; ++u) {
+            const int t = t0 + u * RF_NT + threadIdx.x;
+            i0[u] = -1;
+            if (t < nq) {
+                const int g = t >> lq, j = t & (q - 1);
+                i0[u] = g * N + j;
+                a[u][0] = buf[i0[u]]; a[u][1] = buf[i0[u] + q]; a[u][2] = buf[i0[u] + 2 * q]; a[u][3] = buf[i0[u] + 3 * q];
+                w1[u] = twq[j * ts];
+                w2[u] = tw_get(twq, 2 * j * ts, quarter);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RF_U; ++u) {
+            if (i0[u] < 0) continue;
+            const double2 b0 = cadd(a[u][0], a[u][2]), b2 = cmul(csub(a[u][0], a[u][2]), w1[u]), b1 = cadd(a[u][1], a[u][3]);
+            const double2 d13 = csub(a[u][1], a[u][3]);
+            const double2 b3 = cmul(make_double2(d13.y, -d13.x), w1[u]);  // (a1 - a3) (-i) W^j
+            double2 c0 = cadd(b0, b1), c1 = cmul(csub(b0, b1), w2[u]), c2 = cadd(b2, b3), c3 = cmul(csub(b2, b3), w2[u]);
+            if (POST) {
+                c0 = cmul(c0, __ldg(&post[i0[u]])); c1 = cmul(c1, __ldg(&post[i0[u] + q]));
+                c2 = cmul(c2, __ldg(&post[i0[u] + 2 * q])); c3 = cmul(c3, __ldg(&post[i0[u] + 3 * q]));
+            }
+            buf[i0[u]] = c0; buf[i0[u] + q] = c1; buf[i0[u] + 2 * q] = c2; buf[i0[u] + 3 * q] = c3;
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void dit4_pass(double2* buf, int M, int N, const double2* twq, int twn)
+{
+    const int q = N >> 2, lq = 31 - __clz(q), ts = twn / N, quarter = twn >> 2, nq = M >> 2;
+    for (int t0 = 0; t0 < nq; t0 += RF_NT * RF_U) {
+        double2 c[RF_U][4], w1[RF_U], w2[RF_U];
+        int i0[RF_U];
+#pragma unroll
+        for (int u = 0; u < RF_U; ++u) {
+            const int t = t0 + u * RF_NT + threadIdx.x;
+            i0[u] = -1;
+            if (t < nq) {
+                const int g = t >> lq, j = t & (q - 1);
+                i0[u] = g * N + j;
+                c[u][0] = buf[i0[u]]; c[u][1] = buf[i0[u] + q]; c[u][2] = buf[i0[u] + 2 * q]; c[u][3] = buf[i0[u] + 3 * q];
+                w1[u] = twq[j * ts];
+                w2[u] = tw_get(twq, 2 * j * ts, quarter);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RF_U; ++u) {
+            if (i0[u] < 0) continue;
+            const double2 t1 = cmulc(c[u][1], w2[u]), t3 = cmulc(c[u][3], w2[u]);
+            const double2 b0 = cadd(c[u][0], t1), b1 = csub(c[u][0], t1), b2 = cadd(c[u][2], t3), b3 = csub(c[u][2], t3);
+            const double2 t2 = cmulc(b2, w1[u]), v3 = cmulc(b3, w1[u]);
+            const double2 u3 = make_double2(-v3.y, v3.x);  // (+i) conj(W)^j b3
+            buf[i0[u]] = cadd(b0, t2); buf[i0[u] + 2 * q] = csub(b0, t2);
+            buf[i0[u] + q] = cadd(b1, u3); buf[i0[u] + 3 * q] = csub(b1, u3);
+        }
+    }
+    __syncthreads();
+}
+
+template <bool POST>
+__device__ __forceinline__ void r2_pass(double2* buf, int M, const double2* __restrict__ post)
+{
+    for (int t = threadIdx.x; t < (M >> 1); t += RF_NT) {
+        const double2 a = buf[2 * t], b = buf[2 * t + 1];
+        double2 s = cadd(a, b), d = csub(a, b);
+        if (POST) { s = cmul(s, __ldg(&post[2 * t])); d = cmul(d, __ldg(&post[2 * t + 1])); }
+        buf[2 * t] = s; buf[2 * t + 1] = d;
+    }
+    __syncthreads();
+}
+
+// In-place forward DIF FFT (kernel exp(-2 pi i jk/M)), natural order in, bit-reversed order out;
+// POST: the bit-reversed-order output is multiplied by post[] inside the last pass.
+template <bool POST>
+__device__ void fft_dif(double2* buf, int M, const double2* twq, int twn, const double2* __restrict__ post)
+{
+    const int lg = 31 - __clz(M);
     int N = M;
     while (N >= 4) {
-        const int q = N >> 2, lq = 31 - __clz(q), ts = twn / N;
-        for (int t = threadIdx.x; t < (M >> 2); t += blockDim.x) {
-            const int g = t >> lq, j = t & (q - 1), i0 = g * N + j;
-            const double2 a0 = buf[i0], a1 = buf[i0 + q], a2 = buf[i0 + 2 * q], a3 = buf[i0 + 3 * q];
-            const double2 w1 = __ldg(&tw[j * ts]), w2 = __ldg(&tw[2 * j * ts]);
-            const double2 b0 = cadd(a0, a2), b2 = cmul(csub(a0, a2), w1), b1 = cadd(a1, a3);
-            const double2 d13 = csub(a1, a3);
-            const double2 b3 = cmul(make_double2(d13.y, -d13.x), w1);  // (a1 - a3) (-i) W^j
-            buf[i0] = cadd(b0, b1);
-            buf[i0 + q] = cmul(csub(b0, b1), w2);
-            buf[i0 + 2 * q] = cadd(b2, b3);
-            buf[i0 + 3 * q] = cmul(csub(b2, b3), w2);
-        }
-        __syncthreads();
+        const bool last = !(lg & 1) && N == 4;
+        if (POST && last) dif4_pass<true>(buf, M, N, twq, twn, post);
+        else dif4_pass<false>(buf, M, N, twq, twn, post);
         N >>= 2;
     }
-    if (N == 2) {
-        for (int t = threadIdx.x; t < (M >> 1); t += blockDim.x) {
-            const double2 a = buf[2 * t], b = buf[2 * t + 1];
-            buf[2 * t] = cadd(a, b);
-            buf[2 * t + 1] = csub(a, b);
-        }
-        __syncthreads();
-    }
+    if (N == 2) r2_pass<POST>(buf, M, post);
 }
 
 // In-place inverse DIT FFT (kernel exp(+2 pi i jk/M), unnormalised), bit-reversed in, natural out.
-__device__ void fft_dit_inv(double2* buf, int M, const double2* __restrict__ tw, int twn)
+__device__ void fft_dit_inv(double2* buf, int M, const double2* twq, int twn)
 {
     const int lg = 31 - __clz(M);
     int N = 4;
-    if (lg & 1) {
-        for (int t = threadIdx.x; t < (M >> 1); t += blockDim.x) {
-            const double2 a = buf[2 * t], b = buf[2 * t + 1];
-            buf[2 * t] = cadd(a, b);
-            buf[2 * t + 1] = csub(a, b);
-        }
-        __syncthreads();
-        N = 8;
-    }
-    while (N <= M) {
-        const int q = N >> 2, lq = 31 - __clz(q), ts = twn / N;
-        for (int t = threadIdx.x; t < (M >> 2); t += blockDim.x) {
-            const int g = t >> lq, j = t & (q - 1), i0 = g * N + j;
-            const double2 c0 = buf[i0], c1 = buf[i0 + q], c2 = buf[i0 + 2 * q], c3 = buf[i0 + 3 * q];
-            const double2 w1 = __ldg(&tw[j * ts]), w2 = __ldg(&tw[2 * j * ts]);
-            const double2 t1 = cmulc(c1, w2), t3 = cmulc(c3, w2);
-            const double2 b0 = cadd(c0, t1), b1 = csub(c0, t1), b2 = cadd(c2, t3), b3 = csub(c2, t3);
-            const double2 t2 = cmulc(b2, w1), v3 = cmulc(b3, w1);
-            const double2 u3 = make_double2(-v3.y, v3.x);  // (+i) conj(W)^j b3
-            buf[i0] = cadd(b0, t2);
-            buf[i0 + 2 * q] = csub(b0, t2);
-            buf[i0 + q] = cadd(b1, u3);
-            buf[i0 + 3 * q] = csub(b1, u3);
-        }
-        __syncthreads();
-        N <<= 2;
-    }
+    if (lg & 1) { r2_pass<false>(buf, M, nullptr); N = 8; }
+    while (N <= M) { dit4_pass(buf, M, N, twq, twn); N <<= 2; }
+}
+
+__device__ __forceinline__ void load_twq(const PlanDev& P, double2* twq)
+{
+    const int nq = (P.tw_n >> 2) + 1;
+    for (int k = threadIdx.x; k < nq; k += RF_NT) twq[k] = __ldg(&P.tw[k]);
 }
 
 __device__ __forceinline__ double2 chirp_val(int t, int n)
@@ -98,33 +161,26 @@ __device__ __forceinline__ double2 chirp_val(int t, int n)
     return make_double2(c, s);
 }
 
-// z_j = sum_{k<n} Z_k exp(+2 pi i jk / n), in place in buf[0..n).  Input must already be stored as
-// the caller found convenient: bit-reversed positions for power-of-two n (bsi < 0), natural order
-// otherwise (Bluestein pads to M itself).  All threads of the CTA must call; ends synchronised.
-__device__ void ring_idft(const PlanDev& P, double2* buf, int n, int bsi)
+// z_j = sum_{k<n} Z_k exp(+2 pi i jk / n), in place in buf[0..n).
+// Power-of-two n (bsi < 0): the caller stored Z_k at the bit-reversed position of k.
+// Otherwise (Bluestein): the caller stored Z_k * chirp[k] at k < n and zeros at n <= k < M; the result
+// still has to be multiplied by chirp[j] by the caller (fused into its output pass).
+// All threads of the CTA must call; begins and ends with a barrier.
+__device__ void ring_idft(const PlanDev& P, double2* buf, const double2* twq, int n, int bsi)
 {
-    if (bsi < 0) {
-        __syncthreads();
-        fft_dit_inv(buf, n, P.tw, P.tw_n);
-        return;
-    }
+    __syncthreads();
+    if (bsi < 0) { fft_dit_inv(buf, n, twq, P.tw_n); return; }
     const BluesteinDesc d = P.bs[bsi];
-    const double2* chirp = P.bs_tab + d.chirp_off;
-    const double2* bhat = P.bs_tab + d.bhat_off;
-    __syncthreads();
-    for (int k = threadIdx.x; k < d.M; k += blockDim.x) buf[k] = (k < n) ? cmul(buf[k], __ldg(&chirp[k])) : make_double2(0.0, 0.0);
-    __syncthreads();
-    fft_dif(buf, d.M, P.tw, P.tw_n);
-    for (int k = threadIdx.x; k < d.M; k += blockDim.x) buf[k] = cmul(buf[k], __ldg(&bhat[k]));
-    __syncthreads();
-    fft_dit_inv(buf, d.M, P.tw, P.tw_n);
-    for (int k = threadIdx.x; k < n; k += blockDim.x) buf[k] = cmul(buf[k], __ldg(&chirp[k]));
-    __syncthreads();
+    fft_dif<true>(buf, d.M, twq, P.tw_n, P.bs_tab + d.bhat_off);
+    fft_dit_inv(buf, d.M, twq, P.tw_n);
 }
 
 __global__ void __launch_bounds__(RF_NT) bluestein_setup_kernel(PlanDev P, double2* tab, int nbs)
 {
-    extern __shared__ double2 smem[];
+    extern __shared__ double2 smem_all[];
+    double2* twq = smem_all;
+    double2* smem = smem_all + (P.tw_n >> 2) + 1;
+    load_twq(P, twq);
     const BluesteinDesc d = P.bs[blockIdx.x];
     double2* chirp = tab + d.chirp_off;
     double2* bhat = tab + d.bhat_off;
@@ -138,7 +194,7 @@ __global__ void __launch_bounds__(RF_NT) bluestein_setup_kernel(PlanDev P, doubl
         if (t > 0) smem[d.M - t] = cc;
     }
     __syncthreads();
-    fft_dif(smem, d.M, P.tw, P.tw_n);
+    fft_dif<false>(smem, d.M, twq, P.tw_n, nullptr);
     const double inv = 1.0 / (double)d.M;
     for (int k = threadIdx.x; k < d.M; k += blockDim.x) bhat[k] = make_double2(smem[k].x * inv, smem[k].y * inv);
     (void)nbs;
@@ -153,7 +209,7 @@ __device__ __forceinline__ double2 ring_phase(const PlanDev& P, int ring, int m)
     return make_double2(c, s);
 }
 
-__global__ void __launch_bounds__(RF_NT)
+__global__ void __launch_bounds__(RF_NT, 2)
 ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __restrict__ Fm, double* __restrict__ mapQ,
                   double* __restrict__ mapU, const int* __restrict__ skip)
 {
@@ -162,25 +218,32 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __
     const int L = P.lmax, nm = L + 1;
     const RingJob job = jobs[blockIdx.x];
     const int n = P.ring_nphi[job.ringA], bsi = P.ring_bs[job.ringA];
-    double2* stA = smem;
-    double2* stB = smem + nm;
-    double2* buf = smem + 2 * nm;
+    double2* twq = smem;
+    double2* stA = twq + (P.tw_n >> 2) + 1;
+    double2* stB = stA + nm;
+    double2* buf = stB + nm;
+    load_twq(P, twq);
     const double2* FA = Fm + ((int64_t)job.compA * P.nring + job.ringA) * nm;
     const double2* FB = job.ringB >= 0 ? Fm + ((int64_t)job.compB * P.nring + job.ringB) * nm : nullptr;
-    for (int m = threadIdx.x; m <= L; m += blockDim.x) {
+    const bool same_phase = job.ringB == job.ringA ||
+                            (job.ringB >= 0 && P.ring_phq[job.ringB] == P.ring_phq[job.ringA] && P.ring_phden[job.ringB] == P.ring_phden[job.ringA]);
+    for (int m = threadIdx.x; m <= L; m += RF_NT) {
         const double w = m ? 1.0 : 0.5;  // (2 - delta_m0) / 2
         double2 ph = ring_phase(P, job.ringA, m);
         ph.x *= w; ph.y *= w;
         stA[m] = cmul(FA[m], ph);
         if (FB) {
-            double2 phb = ring_phase(P, job.ringB, m);
-            phb.x *= w; phb.y *= w;
+            double2 phb = ph;
+            if (!same_phase) { phb = ring_phase(P, job.ringB, m); phb.x *= w; phb.y *= w; }
             stB[m] = cmul(FB[m], phb);
         } else stB[m] = make_double2(0.0, 0.0);
     }
     __syncthreads();
     const int lg = 31 - __clz(n);
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const double2* chirp = bsi >= 0 ? P.bs_tab + P.bs[bsi].chirp_off : nullptr;
+    const int M = bsi >= 0 ? P.bs[bsi].M : n;
+    for (int k = threadIdx.x; k < M; k += RF_NT) {
+        if (k >= n) { buf[k] = make_double2(0.0, 0.0); continue; }
         const int kk = (n - k) % n;
         double2 ga = make_double2(0.0, 0.0), gb = ga, ha = ga, hb = ga;
         for (int m = k; m <= L; m += n) { ga = cadd(ga, stA[m]); gb = cadd(gb, stB[m]); }
@@ -188,19 +251,21 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __
         // X = G[k] + conj G[n-k] (the 1/2 is in w);  Z = Xa + i Xb
         const double2 xa = make_double2(ga.x + ha.x, ga.y - ha.y), xb = make_double2(gb.x + hb.x, gb.y - hb.y);
         const double2 z = make_double2(xa.x - xb.y, xa.y + xb.x);
-        buf[bsi < 0 ? (int)(__brev((unsigned)k) >> (32 - lg)) : k] = z;
+        if (bsi < 0) buf[(int)(__brev((unsigned)k) >> (32 - lg))] = z;
+        else buf[k] = cmul(z, __ldg(&chirp[k]));
     }
-    ring_idft(P, buf, n, bsi);
+    ring_idft(P, buf, twq, n, bsi);
     double* oa = (job.compA ? mapU : mapQ) + P.ring_start[job.ringA];
     double* ob = job.ringB >= 0 ? (job.compB ? mapU : mapQ) + P.ring_start[job.ringB] : nullptr;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        const double2 z = buf[j];
+    for (int j = threadIdx.x; j < n; j += RF_NT) {
+        double2 z = buf[j];
+        if (bsi >= 0) z = cmul(z, __ldg(&chirp[j]));
         oa[j] = z.x;
         if (ob) ob[j] = z.y;
     }
 }
 
-__global__ void __launch_bounds__(RF_NT)
+__global__ void __launch_bounds__(RF_NT, 2)
 ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double* __restrict__ mapQ, const double* __restrict__ mapU,
                  const double* __restrict__ pixw, double2* __restrict__ Fm, const int* __restrict__ skip)
 {
@@ -209,21 +274,34 @@ ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double* __re
     const int L = P.lmax, nm = L + 1;
     const RingJob job = jobs[blockIdx.x];
     const int n = P.ring_nphi[job.ringA], bsi = P.ring_bs[job.ringA];
-    double2* buf = smem;
+    double2* twq = smem;
+    double2* buf = twq + (P.tw_n >> 2) + 1;
+    load_twq(P, twq);
     const int64_t sa = P.ring_start[job.ringA], sb = job.ringB >= 0 ? P.ring_start[job.ringB] : 0;
     const double* ia = (job.compA ? mapU : mapQ) + sa;
     const double* ib = job.ringB >= 0 ? (job.compB ? mapU : mapQ) + sb : nullptr;
     const int lg = 31 - __clz(n);
+    const double2* chirp = bsi >= 0 ? P.bs_tab + P.bs[bsi].chirp_off : nullptr;
+    const int M = bsi >= 0 ? P.bs[bsi].M : n;
     // Z[k] = sum_j z_j exp(-2 pi i jk/n) = conj( idft( conj z ) )
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    for (int j = threadIdx.x; j < M; j += RF_NT) {
+        if (j >= n) { buf[j] = make_double2(0.0, 0.0); continue; }
         double a = ia[j], b = ib ? ib[j] : 0.0;
         if (pixw) { a *= pixw[sa + j]; if (ib) b *= pixw[sb + j]; }
-        buf[bsi < 0 ? (int)(__brev((unsigned)j) >> (32 - lg)) : j] = make_double2(a, -b);
+        const double2 z = make_double2(a, -b);
+        if (bsi < 0) buf[(int)(__brev((unsigned)j) >> (32 - lg))] = z;
+        else buf[j] = cmul(z, __ldg(&chirp[j]));
     }
-    ring_idft(P, buf, n, bsi);
+    ring_idft(P, buf, twq, n, bsi);
+    if (bsi >= 0) {  // finish Bluestein in place: every m below reads two entries
+        for (int k = threadIdx.x; k < n; k += RF_NT) buf[k] = cmul(buf[k], __ldg(&chirp[k]));
+        __syncthreads();
+    }
     double2* FA = Fm + ((int64_t)job.compA * P.nring + job.ringA) * nm;
     double2* FB = job.ringB >= 0 ? Fm + ((int64_t)job.compB * P.nring + job.ringB) * nm : nullptr;
-    for (int m = threadIdx.x; m <= L; m += blockDim.x) {
+    const bool same_phase = job.ringB == job.ringA ||
+                            (job.ringB >= 0 && P.ring_phq[job.ringB] == P.ring_phq[job.ringA] && P.ring_phden[job.ringB] == P.ring_phden[job.ringA]);
+    for (int m = threadIdx.x; m <= L; m += RF_NT) {
         const int k = m % n, kk = (n - k) % n;
         const double2 c1 = buf[k], c2 = buf[kk];
         const double2 z1 = make_double2(c1.x, -c1.y);  // Z[k]
@@ -233,7 +311,7 @@ ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double* __re
         const double2 xb = make_double2(0.5 * d.y, -0.5 * d.x);
         const double2 pa = ring_phase(P, job.ringA, m);
         FA[m] = cmulc(xa, pa);
-        if (FB) { const double2 pb = ring_phase(P, job.ringB, m); FB[m] = cmulc(xb, pb); }
+        if (FB) { const double2 pb = same_phase ? pa : ring_phase(P, job.ringB, m); FB[m] = cmulc(xb, pb); }
     }
 }
 
@@ -263,7 +341,7 @@ int gs_ring_setup(gs_plan* p)
     for (int r = 0; r < nring; ++r) rbs[r] = n2bs.count(rn[r]) ? n2bs[rn[r]] : -1;
     p->d.max_M = maxM;
     p->d.tw_n = maxM;
-    p->ring_smem = (size_t)(2 * (L + 1) + maxM) * sizeof(double2);
+    p->ring_smem = (size_t)(2 * (L + 1) + maxM + maxM / 4 + 1) * sizeof(double2);
     if (p->ring_smem > 227 * 1024) {
         gs_set_error("ring FFT needs %zu bytes of shared memory (> 227 KB): nside/lmax too large for this build", p->ring_smem);
         return GS_E_BADARG;
