@@ -57,6 +57,14 @@ SIGNATURES = {
     "gs_mwg_filters": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "gs_mwg_accept": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "gs_mul": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "gs_aux_v_update": (_i, [_vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _i64, _vp]),
+    "gs_aux_s_update": (_i, [_vp, _vp, _vp, _vp, _d, _d, _i, _vp, _vp]),
+    "gs_pncp_factor": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "gs_mala_sigma": (_i, [_vp, _vp, _d, _i, _vp, _vp]),
+    "gs_mala_grad": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "gs_mala_propose": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _i64, _vp]),
+    "gs_mala_logq": (_i, [_vp, _vp, _vp, _vp, _d, _i64, _vp, _vp, _vp]),
+    "gs_dot3": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
     "gs_launch_count": (C.c_longlong, []),
     "gs_profile_matvec": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(C.c_float), _vp]),
     "gs_measure_fp64_peak": (_i, [C.POINTER(_d), _vp]),

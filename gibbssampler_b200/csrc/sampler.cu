@@ -395,3 +395,179 @@ extern "C" int gs_mul(const double* a, const double* b, double* out, int64_t n, 
     GS_CHECK_LAUNCH();
     return GS_OK;
 }
+
+// ------------------------------------------------------------------ auxiliary-variable CR sampler (pixel / alm updates)
+// sample_gibbs_change_variable / overrelaxation_sampler (CenteredGibbs.py:676-825):
+//   v | s : v = mean_v + [alpha (v_old - mean_v)] + sqrt(1 - alpha^2) sqrt(gamma) xi,  gamma = mu - N^-1, mean_v = gamma (A B s)
+//   out   = v + N^-1 d  (the map handed to map2alm for the s | v step); v itself is kept in v_io
+__global__ void aux_v_kernel(const double* __restrict__ map, const double* __restrict__ inv_noise, const double* __restrict__ d,
+                             const double* __restrict__ xi, double mu, double alpha, double* v_io, double* __restrict__ out, int64_t n)
+{
+    const double sq = sqrt(1.0 - alpha * alpha);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double g = mu - inv_noise[i];
+        const double mean = g * map[i];
+        double v = mean + sq * xi[i] * sqrt(g);
+        if (alpha != 0.0) v += alpha * (v_io[i] - mean);
+        v_io[i] = v;
+        out[i] = v + inv_noise[i] * d[i];
+    }
+}
+
+//   s | v : var_s = 1 / ((mu/w) b_l^2 + 1/C_l), mean_s = var_s * badj  (badj = b_l A^T (v + N^-1 d), real layout)
+//           s = mean_s + alpha (s_old - mean_s) + sqrt(1 - alpha^2) sqrt(var_s) xi
+__global__ void aux_s_kernel(const double* __restrict__ badj, const double* __restrict__ dl, const double* __restrict__ bl,
+                             const double* __restrict__ xi, double mu_over_w, double alpha, int L, double* s_io)
+{
+    const int64_t n = (int64_t)(L + 1) * (L + 1);
+    const double sq = sqrt(1.0 - alpha * alpha);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int l = l_of_real(i, L);
+        double c = dl[l];
+        if (l) c = c * 2.0 * 3.14159265358979323846 / ((double)l * (double)(l + 1));
+        const double ic = c != 0.0 ? 1.0 / c : 0.0;
+        const double var = 1.0 / (mu_over_w * bl[l] * bl[l] + ic);
+        const double mean = var * badj[i];
+        double s = mean + sq * xi[i] * sqrt(var);
+        if (alpha != 0.0) s += alpha * (s_io[i] - mean);
+        s_io[i] = s;
+    }
+}
+
+// per-l factor of the partially non-centred parametrisation: f_l = 1 for l < l_cut, sqrt(1/C_l) (mode 0) or
+// sqrt(C_l) (mode 1) for l >= l_cut (0 where C_l = 0)
+__global__ void pncp_factor_kernel(const double* __restrict__ dl, int L, int l_cut, int mode, double* __restrict__ out)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > L) return;
+    double c = dl[l];
+    if (l) c = c * 2.0 * 3.14159265358979323846 / ((double)l * (double)(l + 1));
+    double f = 1.0;
+    if (l >= l_cut) f = mode ? sqrt(c) : (c != 0.0 ? sqrt(1.0 / c) : 0.0);
+    out[l] = f;
+}
+
+extern "C" int gs_aux_v_update(const double* map, const double* inv_noise, const double* d, const double* xi, double mu,
+                               double alpha, double* v_io, double* out, int64_t npix, void* stream)
+{
+    GS_REQUIRE(map && inv_noise && d && xi && v_io && out && npix > 0 && alpha > -1.0 && alpha < 1.0, "bad arguments");
+    aux_v_kernel<<<nblk(npix), SM_NT, 0, STREAM(stream)>>>(map, inv_noise, d, xi, mu, alpha, v_io, out, npix);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+extern "C" int gs_aux_s_update(const double* badj, const double* dl, const double* bl, const double* xi, double mu_over_w,
+                               double alpha, int lmax, double* s_io, void* stream)
+{
+    GS_REQUIRE(badj && dl && bl && xi && s_io && lmax >= 0 && alpha > -1.0 && alpha < 1.0, "bad arguments");
+    aux_s_kernel<<<nblk((int64_t)(lmax + 1) * (lmax + 1)), SM_NT, 0, STREAM(stream)>>>(badj, dl, bl, xi, mu_over_w, alpha, lmax, s_io);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+extern "C" int gs_pncp_factor(const double* dl, int lmax, int l_cut, int mode, double* out, void* stream)
+{
+    GS_REQUIRE(dl && out && lmax >= 0 && l_cut >= 0 && (mode == 0 || mode == 1), "bad arguments");
+    pncp_factor_kernel<<<(lmax + 128) / 128, 128, 0, STREAM(stream)>>>(dl, lmax, l_cut, mode, out);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+// ------------------------------------------------------------------ MALA pieces (CenteredGibbs.py:494-603)
+// sigma = 1 / (w b_l^2 + 1/C_l) per coefficient (the diagonal preconditioner of the Langevin proposal)
+__global__ void mala_sigma_kernel(const double* __restrict__ dl, const double* __restrict__ bl, double w, int L, double* __restrict__ out)
+{
+    const int64_t n = (int64_t)(L + 1) * (L + 1);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int l = l_of_real(i, L);
+        double c = dl[l];
+        if (l) c = c * 2.0 * 3.14159265358979323846 / ((double)l * (double)(l + 1));
+        const double ic = c != 0.0 ? 1.0 / c : 0.0;
+        out[i] = 1.0 / (w * bl[l] * bl[l] + ic);
+    }
+}
+
+// grad = bdata - C^-1 s - y   (y = B A^T N^-1 A B s);  invc = 1/C expanded
+__global__ void mala_grad_kernel(const double* __restrict__ bdata, const double* __restrict__ invc, const double* __restrict__ s,
+                                 const double* __restrict__ y, double* __restrict__ g, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        g[i] = bdata[i] - invc[i] * s[i] - y[i];
+}
+
+// s_new = s + tau sigma g + sqrt(2 tau sigma) xi   (CenteredGibbs.py:523-527)
+__global__ void mala_propose_kernel(const double* __restrict__ s, const double* __restrict__ g, const double* __restrict__ sigma,
+                                    const double* __restrict__ xi, double tau, double* __restrict__ out, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = s[i] + tau * sigma[i] * g[i] + sqrt(2.0 * tau * sigma[i]) * xi[i];
+}
+
+// partial sums of (to - from - tau sigma g)^2 / (2 tau sigma)   (compute_log_proposal, CenteredGibbs.py:530-532)
+__global__ void __launch_bounds__(SM_NT)
+mala_logq_partial_kernel(const double* __restrict__ to, const double* __restrict__ from, const double* __restrict__ g,
+                         const double* __restrict__ sigma, double tau, int64_t n, double* __restrict__ partials)
+{
+    double v[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double r = to[i] - from[i] - tau * sigma[i] * g[i];
+        v[0] += r * r / (2.0 * tau * sigma[i]);
+    }
+    block_sum<1>(v, partials + blockIdx.x);
+}
+
+// partial sums of a * b * c (c nullable)
+__global__ void __launch_bounds__(SM_NT)
+dot3_partial_kernel(const double* __restrict__ a, const double* __restrict__ b, const double* __restrict__ c, int64_t n,
+                    double* __restrict__ partials)
+{
+    double v[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        v[0] = fma(a[i] * b[i], c ? c[i] : 1.0, v[0]);
+    block_sum<1>(v, partials + blockIdx.x);
+}
+
+extern "C" int gs_mala_sigma(const double* dl, const double* bl, double npix_over_noise_4pi, int lmax, double* out, void* stream)
+{
+    GS_REQUIRE(dl && bl && out && lmax >= 0, "bad arguments");
+    mala_sigma_kernel<<<nblk((int64_t)(lmax + 1) * (lmax + 1)), SM_NT, 0, STREAM(stream)>>>(dl, bl, npix_over_noise_4pi, lmax, out);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+extern "C" int gs_mala_grad(const double* bdata, const double* invc, const double* s, const double* y, double* g, int64_t n,
+                            void* stream)
+{
+    GS_REQUIRE(bdata && invc && s && y && g && n > 0, "bad arguments");
+    mala_grad_kernel<<<nblk(n), SM_NT, 0, STREAM(stream)>>>(bdata, invc, s, y, g, n);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+extern "C" int gs_mala_propose(const double* s, const double* g, const double* sigma, const double* xi, double tau, double* out,
+                               int64_t n, void* stream)
+{
+    GS_REQUIRE(s && g && sigma && xi && out && n > 0 && tau > 0.0, "bad arguments");
+    mala_propose_kernel<<<nblk(n), SM_NT, 0, STREAM(stream)>>>(s, g, sigma, xi, tau, out, n);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+extern "C" int gs_mala_logq(const double* to, const double* from, const double* g_from, const double* sigma, double tau, int64_t n,
+                            double* scratch, double* out, void* stream)
+{
+    GS_REQUIRE(to && from && g_from && sigma && scratch && out && n > 0 && tau > 0.0, "bad arguments");
+    mala_logq_partial_kernel<<<SM_GRID, SM_NT, 0, STREAM(stream)>>>(to, from, g_from, sigma, tau, n, scratch);
+    final_sum_kernel<<<1, SM_NT, 0, STREAM(stream)>>>(scratch, SM_GRID, -0.5, out);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+extern "C" int gs_dot3(const double* a, const double* b, const double* c, int64_t n, double* scratch, double* out, void* stream)
+{
+    GS_REQUIRE(a && b && scratch && out && n > 0, "bad arguments");
+    dot3_partial_kernel<<<SM_GRID, SM_NT, 0, STREAM(stream)>>>(a, b, c, n, scratch);
+    final_sum_kernel<<<1, SM_NT, 0, STREAM(stream)>>>(scratch, SM_GRID, 1.0, out);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}

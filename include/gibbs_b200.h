@@ -201,6 +201,39 @@ int gs_mwg_accept(double* cur, const double* prop, const double* logr, int b_sta
 /* out = a * b elementwise (re-centring s = sqrt(C) s_nc, ASIS.py:181-203; NonCenteredGibbs.py:192-194). */
 int gs_mul(const double* a, const double* b, double* out, int64_t n, void* stream);
 
+/* ---- auxiliary-variable constrained realization (CenteredGibbs.py:676-825) --------------- */
+/* v | s in pixel space, one component: gamma = mu - N^-1, mean = gamma * map (map = A B s),
+ * v = mean + alpha (v_io - mean) + sqrt(1 - alpha^2) sqrt(gamma) xi; v_io <- v; out <- v + N^-1 d
+ * (the map whose adjoint transform gives the mean of s | v).  alpha = 0: plain Gibbs draw
+ * (CenteredGibbs.py:701-705); alpha = -0.995: over-relaxation (CenteredGibbs.py:796-797). */
+int gs_aux_v_update(const double* map, const double* inv_noise, const double* d, const double* xi,
+                    double mu, double alpha, double* v_io, double* out, int64_t npix, void* stream);
+/* s | v in the real alm layout, one spectrum: var = 1/((mu/w) b_l^2 + 1/C_l), mean = var * badj with
+ * badj = b_l A^T (v + N^-1 d); s_io <- mean + alpha (s_io - mean) + sqrt(1 - alpha^2) sqrt(var) xi
+ * (CenteredGibbs.py:708-725, 763-781). */
+int gs_aux_s_update(const double* badj, const double* dl, const double* bl, const double* xi,
+                    double mu_over_w, double alpha, int lmax, double* s_io, void* stream);
+/* per-l factor of the partially non-centred parametrisation (PNCP): out[l] = 1 for l < l_cut, else
+ * sqrt(1/C_l) (mode 0) or sqrt(C_l) (mode 1). */
+int gs_pncp_factor(const double* dl, int lmax, int l_cut, int mode, double* out, void* stream);
+
+/* ---- MALA constrained realization (CenteredGibbs.py:494-603), real alm layout ---------------- */
+/* sigma = 1/(w b_l^2 + 1/C_l), w = Npix/(noise 4 pi) (CenteredGibbs.py:569-570). */
+int gs_mala_sigma(const double* dl, const double* bl, double npix_over_noise_4pi, int lmax, double* out,
+                  void* stream);
+/* g = bdata - C^-1 s - y with y = B A^T N^-1 A B s (compute_gradient_mala, CenteredGibbs.py:494-520). */
+int gs_mala_grad(const double* bdata, const double* invc, const double* s, const double* y, double* g,
+                 int64_t n, void* stream);
+/* out = s + tau sigma g + sqrt(2 tau sigma) xi (propose_new_mala, CenteredGibbs.py:523-527). */
+int gs_mala_propose(const double* s, const double* g, const double* sigma, const double* xi, double tau,
+                    double* out, int64_t n, void* stream);
+/* out[0] = -1/2 sum (to - from - tau sigma g_from)^2 / (2 tau sigma) (compute_log_proposal, :530-532). */
+int gs_mala_logq(const double* to, const double* from, const double* g_from, const double* sigma,
+                 double tau, int64_t n, double* scratch, double* out, void* stream);
+/* out[0] = sum a b c (c nullable), fixed summation order; scratch: 592 doubles. */
+int gs_dot3(const double* a, const double* b, const double* c, int64_t n, double* scratch, double* out,
+            void* stream);
+
 /* ---- random numbers / reductions --------------------------------------------------------- */
 /* n standard normals (Philox4x32-10 keyed by (seed, stream_id), Box-Muller); replaces
  * np.random.normal in production runs. */

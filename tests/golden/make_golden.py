@@ -78,6 +78,27 @@ def main():
     out["sample_no_mask_seed"] = 102
     out["sample_no_mask_E"], out["sample_no_mask_B"] = sol["EE"], sol["BB"]
 
+    # ---- alternative CR kernels (CenteredGibbs.py:494-825) from a fixed starting map
+    s_old = {"EE": out["sample_mask_E"].copy(), "BB": out["sample_mask_B"].copy()}
+    cr.n_gibbs = 2
+    np.random.seed(110)
+    sol, _ = cr.sample_gibbs_change_variable({k: v.copy() for k, v in dls.items()}, {k: v.copy() for k, v in s_old.items()})
+    out["aux_seed"] = 110
+    out["aux_E"], out["aux_B"] = sol["EE"], sol["BB"]
+    np.random.seed(111)
+    sol, _ = cr.overrelaxation_sampler({k: v.copy() for k, v in dls.items()}, {k: v.copy() for k, v in s_old.items()})
+    out["overrelax_seed"] = 111
+    out["overrelax_E"], out["overrelax_B"] = sol["EE"], sol["BB"]
+    for seed in (112, 113, 114):
+        np.random.seed(seed)
+        sol, acc = cr.sample_mala({k: v.copy() for k, v in dls.items()}, {k: v.copy() for k, v in s_old.items()})
+        out["mala_E_%d" % seed], out["mala_B_%d" % seed], out["mala_acc_%d" % seed] = sol["EE"], sol["BB"], acc
+    cr.chain_descr[0][5] = 1e-3                                # truncated PCG: the RJPO accept test is non-trivial
+    np.random.seed(115)
+    sol, acc = cr.sample_mask_rj({k: v.copy() for k, v in dls.items()}, {k: v.copy() for k, v in s_old.items()})
+    out["rj_E"], out["rj_B"], out["rj_acc"] = sol["EE"], sol["BB"], acc
+    cr.chain_descr[0][5] = 1e-13
+
     # ---- PolarizedCenteredClsSampler (CenteredGibbs.py:51-93)
     cs = ref_C.PolarizedCenteredClsSampler(pix_map, LMAX, NSIDE, bins, g.bl_map, noise_temp, mask_path=mask_path)
     np.random.seed(103)

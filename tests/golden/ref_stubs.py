@@ -65,7 +65,7 @@ def install(nside, lmax, mask_path=None, bins=None, blocks=None):
         log = []
 
         def __init__(self, opfilt, chain_descr, s_cls, n_inv_filt, debug_log_prefix=None):
-            self.opfilt, self.descr, self.s_cls, self.f = opfilt, chain_descr[0], s_cls, n_inv_filt
+            self.opfilt, self.descr, self.s_cls, self.f = qc.opfilt_pp, chain_descr[0], s_cls, n_inv_filt
 
         def sample(self, soltn, pix_map, fluctuations, pol=False):
             """b = calc_prep(d) + fluctuations; PCG with diag_cl preconditioner; solution written into soltn."""
@@ -90,11 +90,29 @@ def install(nside, lmax, mask_path=None, bins=None, blocks=None):
             multigrid_chain.log.append(dict(bE=bE, bB=bB, it=it, res=res))
             return eblm(np.array([R.real_to_complex(bE), R.real_to_complex(bB)]))
 
+    class fwd_op:
+        """opfilt_pp.fwd_op(s_cls, n_inv_filt)(alm) = Q alm (CenteredGibbs.py:629, 653)"""
+
+        def __init__(self, s_cls, n_inv_filt):
+            self.s_cls, self.f = s_cls, n_inv_filt
+
+        def __call__(self, x):
+            prob = R.PolProblem.__new__(R.PolProblem)
+            prob.nside, prob.lmax, prob.kind, prob.npix = nside, lmax, "ld", 12 * nside * nside
+            prob.inv_noise, prob.bl_gauss = self.f.n_inv, self.f.b_transf
+            prob.bl_map = R.expand_per_l(prob.bl_gauss)
+            ell = np.arange(lmax + 1)
+            dlE = np.where(ell > 0, self.s_cls.clee * ell * (ell + 1) / (2 * np.pi), self.s_cls.clee)
+            dlB = np.where(ell > 0, self.s_cls.clbb * ell * (ell + 1) / (2 * np.pi), self.s_cls.clbb)
+            yE, yB = prob.apply_Q(dlE, dlB, R.complex_to_real(x.elm), R.complex_to_real(x.blm))
+            return eblm(np.array([R.real_to_complex(yE), R.real_to_complex(yB)]))
+
     for name in ("opfilt_pp", "opfilt_tt", "cd_solve", "multigrid", "util_alm"):
         setattr(qc, name, types.ModuleType("qcinv." + name))
     qc.opfilt_pp.alm_filter_ninv = alm_filter_ninv
     qc.opfilt_tt.alm_filter_ninv = alm_filter_ninv
     qc.opfilt_pp.eblm = eblm
+    qc.opfilt_pp.fwd_op = fwd_op
     qc.cd_solve.tr_cg = "tr_cg"
     qc.cd_solve.cache_mem = lambda: {}
     qc.multigrid.multigrid_chain = multigrid_chain

@@ -130,3 +130,33 @@ def test_full_gibbs_loops_reproduce_reference_chains():
     res = ncg.run(init)
     assert np.array_equal(res[1]["EE"], G["nc_accept_EE"]) and np.array_equal(res[1]["BB"], G["nc_accept_BB"])
     assert close(res[0]["EE"], G["nc_run_EE"], 1e-7) and close(res[0]["BB"], G["nc_run_BB"], 1e-7)
+
+
+def test_alternative_cr_kernels_match_reference():
+    """Auxiliary-variable Gibbs, over-relaxation, MALA and RJPO (CenteredGibbs.py:494-825) on the reference's stream."""
+    from gibbssampler_b200 import cr_extra
+    from gibbssampler_b200.CenteredGibbs import PolarizedCenteredConstrainedRealization
+    pix_map, bins, blocks, pv, dls, nt, npol, fwhm = common()
+    cr = PolarizedCenteredConstrainedRealization(pix_map, nt, npol, G["bl_map"], LMAX, NPIX, fwhm, mask=G["mask"], rng="numpy", n_gibbs=2)
+    s_old = {"EE": G["sample_mask_E"].copy(), "BB": G["sample_mask_B"].copy()}
+    np.random.seed(int(G["aux_seed"]))
+    sol, acc = cr_extra.sample_gibbs_change_variable(cr, dls, s_old)
+    assert close(sol["EE"], G["aux_E"]) and close(sol["BB"], G["aux_B"])
+    np.random.seed(int(G["overrelax_seed"]))
+    sol, acc = cr_extra.overrelaxation_sampler(cr, dls, s_old)
+    assert close(sol["EE"], G["overrelax_E"], 1e-8) and close(sol["BB"], G["overrelax_B"], 1e-8)
+    for seed in (112, 113, 114):
+        np.random.seed(seed)
+        sol, acc = cr_extra.sample_mala(cr, dls, s_old)
+        assert acc == int(G["mala_acc_%d" % seed])
+        assert close(sol["EE"], G["mala_E_%d" % seed]) and close(sol["BB"], G["mala_B_%d" % seed])
+    cr.pcg_accuracy = 1e-3
+    np.random.seed(115)
+    sol, acc = cr.sample_mask_rj(dls, s_old)
+    assert acc == int(G["rj_acc"])
+    assert close(sol["EE"], G["rj_E"], 1e-6) and close(sol["BB"], G["rj_B"], 1e-6)
+    # dispatcher: gibbs_cr + overrelaxation / ula combinations route like CenteredGibbs.py:828-850
+    cr.gibbs_cr, cr.overrelaxation, cr.ula = True, True, False
+    np.random.seed(int(G["overrelax_seed"]))
+    sol, _ = cr.sample(dls, s_old)
+    assert close(sol["EE"], G["overrelax_E"], 1e-8)

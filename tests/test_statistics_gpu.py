@@ -1,0 +1,142 @@
+"""Statistical parity: long chains of the device samplers against exact posteriors and
+against each other, within Monte-Carlo error (ESS-corrected z-tests; thresholds at 5 sigma so that the
+tests are deterministic for the fixed Philox seeds used)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_logic as R
+from oracle import sht as O
+
+pytestmark = pytest.mark.gpu
+
+
+def ess(x):
+    x = np.asarray(x, float) - np.mean(x)
+    n = len(x)
+    if np.all(x == 0):
+        return n
+    acf = np.correlate(x, x, "full")[n - 1:] / (np.arange(n, 0, -1) * np.var(x))
+    tau = 1.0
+    for k in range(1, n // 3):
+        if acf[k] < 0.05:
+            break
+        tau += 2 * acf[k]
+    return n / tau
+
+
+def test_philox_normals_and_gamma_draws():
+    from gibbssampler_b200 import _dev, _lib
+    rng = _dev.Rng("philox", seed=7)
+    x = rng.normal(2_000_001).cpu().numpy()
+    n = len(x)
+    assert abs(x.mean()) < 5 / np.sqrt(n) and abs(x.var() - 1) < 5 * np.sqrt(2 / n)
+    assert abs(np.mean(x ** 3)) < 5 * np.sqrt(15 / n) and abs(np.mean(x ** 4) - 3) < 5 * np.sqrt(96 / n)
+    assert abs(np.corrcoef(x[:-1], x[1:])[0, 1]) < 5 / np.sqrt(n)
+    u = rng.uniform(1_000_000).cpu().numpy()
+    assert 0 < u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 5 / np.sqrt(12 * len(u))
+    # Marsaglia-Tsang inverse-gamma draws through gs_cls_invgamma: D_bin = beta / Gamma(alpha), one l per bin
+    lmax = 40
+    bins = np.arange(0, lmax + 2)
+    cl = torch.ones(lmax + 1, dtype=torch.float64, device="cuda")
+    draws = []
+    out = torch.empty(lmax + 1, dtype=torch.float64, device="cuda")
+    for call in range(4000):
+        _lib.check(_lib.lib().gs_cls_invgamma(_dev.ptr(cl), _dev.ptr(_dev.i32(bins)), lmax + 1, None, 99, call, _dev.ptr(out), None, None,
+                                              _dev.stream()))
+        draws.append(out.cpu().numpy().copy())
+    d = np.array(draws)
+    for l in (2, 3, 5, 10, 40):
+        alpha = (2 * l + 1) / 2 - 1
+        beta = (2 * l + 1) * l * (l + 1) / (4 * np.pi)
+        g = beta / d[:, l]                                   # should be Gamma(alpha, 1)
+        assert abs(g.mean() - alpha) < 5 * np.sqrt(alpha / len(g))
+        assert abs(g.var() - alpha) < 5 * alpha * np.sqrt((2 + 6 / alpha) / len(g))
+
+
+def test_full_sky_isotropic_chain_vs_exact_posterior():
+    """Full sky + isotropic noise: D_l | d is a shifted, truncated inverse-gamma in C_l b_l^2 w + 1 (w = Npix/(4 pi noise));
+    compare the chain's posterior mean of D_l with 1-D quadrature of the exact marginal."""
+    from gibbssampler_b200.CenteredGibbs import CenteredGibbs
+    nside, lmax = 8, 16
+    npix, n = 12 * nside ** 2, (lmax + 1) ** 2
+    rng = np.random.default_rng(3)
+    ell = np.arange(lmax + 1)
+    dl_true = np.where(ell >= 2, 1.0, 0.0)
+    fwhm, noise0 = 5.0, 0.01
+    bl = O.gauss_beam(np.radians(fwhm), lmax)
+    bl_map = R.expand_per_l(bl)
+    w = npix / (4 * np.pi * noise0)
+    var = R.generate_var_cl(dl_true)
+    # data directly in harmonic space: d = b s + n, n ~ N(0, 1/w)  (so that (4pi/Npix) A^T A = 1 exactly)
+    d_alm = bl_map * rng.standard_normal(n) * np.sqrt(var) + rng.standard_normal(n) / np.sqrt(w)
+    for i in (0, 1, lmax + 1, lmax + 2):
+        d_alm[i] = 0
+    pix_map = {"EE": d_alm, "BB": d_alm.copy(), "Q": np.zeros(npix), "U": np.zeros(npix)}
+    bins = {"EE": np.arange(0, lmax + 2), "BB": np.arange(0, lmax + 2)}
+    g = CenteredGibbs(pix_map, np.full(npix, 1.0), np.full(npix, noise0), fwhm, nside, lmax, npix, polarization=True, bins=bins, n_iter=6000,
+                      rng="philox", seed=11)
+    h, _, _, _ = g.run({"EE": dl_true.copy(), "BB": dl_true.copy()})
+    chain = h["EE"][500:]
+    sig = np.array([np.sum(d_alm[np.array([i for i in range(n) if (i <= lmax and i == l) or
+                                           (i > lmax and False)])] ** 2) if False else 0 for l in range(lmax + 1)])
+    # sigma_l = sum of d^2 over the 2l+1 real coefficients of multipole l
+    lidx = np.concatenate([ell, np.array([c for m in range(1, lmax + 1) for c in ell[m:] for _ in range(2)])]).astype(int)
+    sig = np.bincount(lidx, weights=d_alm ** 2, minlength=lmax + 1)
+    for l in (2, 4, 8, 12, 16):
+        f = 2 * np.pi / (l * (l + 1))
+        D = np.linspace(1e-6, 60.0, 600001)
+        v = D * f * bl[l] ** 2 + 1 / w
+        logp = -(2 * l + 1) / 2 * np.log(v) - sig[l] / (2 * v)
+        p = np.exp(logp - logp.max())
+        mean_exact = np.sum(D * p) / np.sum(p)
+        sd_exact = np.sqrt(np.sum(D ** 2 * p) / np.sum(p) - mean_exact ** 2)
+        x = chain[:, l]
+        z = (x.mean() - mean_exact) / (sd_exact / np.sqrt(ess(x)))
+        assert abs(z) < 5, (l, x.mean(), mean_exact, z)
+        assert abs(x.std() / sd_exact - 1) < 0.25, (l, x.std(), sd_exact)
+
+
+def test_masked_chains_agree_centered_asis_pncp():
+    """Masked sky: CenteredGibbs (PCG), ASIS and PNCP target the same posterior; bin means agree within MC error."""
+    from gibbssampler_b200.ASIS import ASIS
+    from gibbssampler_b200.CenteredGibbs import CenteredGibbs
+    from gibbssampler_b200.PNCP import PNCPGibbs
+    nside, lmax = 4, 8
+    npix, n = 12 * nside ** 2, (lmax + 1) ** 2
+    rng = np.random.default_rng(5)
+    ell = np.arange(lmax + 1)
+    dl_true = np.where(ell >= 2, 1.0, 0.0)
+    fwhm, noise0 = 10.0, 0.05
+    bl_map = R.expand_per_l(O.gauss_beam(np.radians(fwhm), lmax))
+    th, ph = O.pix_angles(nside)
+    mask = (np.abs(np.cos(th)) > 0.25).astype(float)
+    sE = rng.standard_normal(n) * np.sqrt(R.generate_var_cl(dl_true))
+    sB = rng.standard_normal(n) * np.sqrt(R.generate_var_cl(dl_true))
+    q, u = R.synth_pol(sE * bl_map, sB * bl_map, nside, lmax)
+    pix_map = {"Q": (q + rng.standard_normal(npix) * np.sqrt(noise0)) * mask, "U": (u + rng.standard_normal(npix) * np.sqrt(noise0)) * mask}
+    bins = {"EE": np.arange(0, lmax + 2), "BB": np.arange(0, lmax + 2)}
+    blocks = {"EE": [2, 4, 6, lmax + 1], "BB": [2, 4, 6, lmax + 1]}
+    pv = {"EE": np.full(lmax - 1, 0.3), "BB": np.full(lmax - 1, 0.3)}
+    nt, npol = np.full(npix, 1.0), np.full(npix, noise0)
+    init = {"EE": dl_true.copy(), "BB": dl_true.copy()}
+    n_iter = 2500
+    cg = CenteredGibbs(pix_map, nt, npol, fwhm, nside, lmax, npix, mask=mask, polarization=True, bins=bins, n_iter=n_iter, seed=21)
+    cg.constrained_sampler.pcg_accuracy = 1e-8
+    hc = cg.run(init)[0]
+    asis = ASIS(pix_map, nt, npol, fwhm, nside, lmax, npix, pv, metropolis_blocks=blocks, polarization=True, bins=bins, n_iter=n_iter,
+                mask=mask, seed=22)
+    asis.constrained_sampler.pcg_accuracy = 1e-8
+    ha = asis.run(init)[0]
+    blocks_p = {"EE": [4, 6, lmax + 1], "BB": [4, 6, lmax + 1]}
+    pn = PNCPGibbs(pix_map, nt, fwhm, nside, lmax, npix, pv, 4, metropolis_blocks=blocks_p, polarization=True, bins=bins, n_iter=n_iter,
+                   noise_Q=npol, mask=mask, seed=23)
+    pn.constrained_sampler.pcg_accuracy = 1e-8
+    hp_ = pn.run(init)[0]
+    for pol in ("EE", "BB"):
+        for l in (2, 3, 5, 8):
+            # compare medians of log D (heavy-tailed inverse-gamma marginals): z-test on log D
+            xs = [np.log(h[pol][300:, l]) for h in (hc, ha, hp_)]
+            for other in xs[1:]:
+                se = np.sqrt(xs[0].var() / ess(xs[0]) + other.var() / ess(other))
+                assert abs(xs[0].mean() - other.mean()) < 5 * se, (pol, l, xs[0].mean(), other.mean(), se)
