@@ -26,12 +26,15 @@ __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_doub
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 
 // ---- shared-memory FFT core -------------------------------------------------------------------
-// Twiddles: quarter table twq[k] = exp(-2 pi i k / twn), k <= twn/4, staged in shared memory by the
-// caller; W^(k + twn/4) = -i W^k gives the second quadrant (all the radix-4 butterflies need).
-// Every pass loads up to RF_U radix-4 butterflies per thread before computing any of them, so the
-// shared-memory round trips of the butterflies overlap instead of serialising (the compiler cannot
-// hoist loads above stores to the same buffer by itself).
-#define RF_U 2
+// Layout: element i of the transform lives at buf[PADI(i)], PADI(i) = i + (i >> 4): one 16-byte pad per
+// 16 elements makes the stride-16 accesses of the final radix-16 pass bank-conflict free and leaves the
+// unit-stride passes (consecutive lanes -> consecutive elements) conflict free as well.
+// Passes: a radix-16 butterfly (= two radix-4 levels) is done entirely in registers, so a 4096-point
+// transform makes 3 trips through shared memory (6 with radix-4); leftover stages (log2 M mod 4) are a
+// radix-2 and/or radix-4 pass at the top (DIF) / bottom (DIT).
+// Twiddles: quarter table twq[k] = exp(-2 pi i k / twn), k <= twn/4, in shared memory;
+// W^(k + twn/4) = -i W^k covers the second quadrant (indices stay below twn/2).
+#define PADI(i) ((i) + ((i) >> 4))
 
 __device__ __forceinline__ double2 tw_get(const double2* twq, int idx, int quarter)
 {
@@ -40,111 +43,130 @@ __device__ __forceinline__ double2 tw_get(const double2* twq, int idx, int quart
     return make_double2(w.y, -w.x);  // -i w
 }
 
-// one radix-4 DIF pass (sub-transform size N) of an M-point transform; POST: multiply outputs by post[index]
-template <bool POST>
-__device__ __forceinline__ void dif4_pass(double2* buf, int M, int N, const double2* twq, int twn,
-                                          const double2* __restrict__ post)
+// radix-4 DIF butterfly in registers: twiddles w1 = W^x, w2 = W^2x (forward kernel exp(-2 pi i ..))
+__device__ __forceinline__ void bf4_dif(double2& a0, double2& a1, double2& a2, double2& a3, double2 w1, double2 w2)
 {
-    const int q = N >> 2, lq = 31 - __clz(q), ts = twn / N, quarter = twn >> 2, nq = M >> 2;
-    for (int t0 = 0; t0 < nq; t0 += RF_NT * RF_U) {
-        double2 a[RF_U][4], w1[RF_U], w2[RF_U];
-        int i0[RF_U];
+    const double2 b0 = cadd(a0, a2), b2 = cmul(csub(a0, a2), w1), b1 = cadd(a1, a3);
+    const double2 d13 = csub(a1, a3);
+    const double2 b3 = cmul(make_double2(d13.y, -d13.x), w1);  // (a1 - a3) (-i) W^x
+    a0 = cadd(b0, b1); a1 = cmul(csub(b0, b1), w2); a2 = cadd(b2, b3); a3 = cmul(csub(b2, b3), w2);
+}
+// its transpose-conjugate (inverse DIT butterfly, kernel exp(+2 pi i ..))
+__device__ __forceinline__ void bf4_dit(double2& c0, double2& c1, double2& c2, double2& c3, double2 w1, double2 w2)
+{
+    const double2 t1 = cmulc(c1, w2), t3 = cmulc(c3, w2);
+    const double2 b0 = cadd(c0, t1), b1 = csub(c0, t1), b2 = cadd(c2, t3), b3 = csub(c2, t3);
+    const double2 t2 = cmulc(b2, w1), v3 = cmulc(b3, w1);
+    const double2 u3 = make_double2(-v3.y, v3.x);  // (+i) conj(W)^x b3
+    c0 = cadd(b0, t2); c2 = csub(b0, t2); c1 = cadd(b1, u3); c3 = csub(b1, u3);
+}
+
+// exp(-2 pi i a / 16) and exp(-2 pi i a / 8), a = 0..3
+__device__ __forceinline__ double2 w16c(int a)
+{
+    const double c1 = 0.92387953251128675613, s1 = 0.38268343236508977173, h = 0.70710678118654752440;
+    return a == 0 ? make_double2(1.0, 0.0) : a == 1 ? make_double2(c1, -s1) : a == 2 ? make_double2(h, -h) : make_double2(s1, -c1);
+}
+__device__ __forceinline__ double2 w8c(int a)
+{
+    const double h = 0.70710678118654752440;
+    return a == 0 ? make_double2(1.0, 0.0) : a == 1 ? make_double2(h, -h) : a == 2 ? make_double2(0.0, -1.0) : make_double2(-h, -h);
+}
+
+// radix-16 pass over sub-transforms of size N (N >= 16).  INV = false: DIF (forward), true: DIT (inverse).
+// POST (DIF only): outputs are multiplied by post[position].
+template <bool INV, bool POST>
+__device__ __forceinline__ void pass16(double2* buf, int M, int N, const double2* twq, int twn, const double2* __restrict__ post)
+{
+    const int s = N >> 4, ls = 31 - __clz(s), ts = twn / N, quarter = twn >> 2, ng = M >> 4;
+    for (int t = threadIdx.x; t < ng; t += RF_NT) {
+        const int g = t >> ls, j = t & (s - 1), i0 = g * N + j;
+        double2 x[16];
 #pragma unroll
-        for (int u = 0; u < RF_U; ++u) {
-            const int t = t0 + u * RF_NT + threadIdx.x;
-            i0[u] = -1;
-            if (t < nq) {
-                const int g = t >> lq, j = t & (q - 1);
-                i0[u] = g * N + j;
-                a[u][0] = buf[i0[u]]; a[u][1] = buf[i0[u] + q]; a[u][2] = buf[i0[u] + 2 * q]; a[u][3] = buf[i0[u] + 3 * q];
-                w1[u] = twq[j * ts];
-                w2[u] = tw_get(twq, 2 * j * ts, quarter);
-            }
+        for (int k = 0; k < 16; ++k) x[k] = buf[PADI(i0 + k * s)];
+        double2 wj = make_double2(1.0, 0.0), w2j = wj, w4j = wj, w8j = wj;
+        if (s > 1) {
+            wj = twq[j * ts];
+            w2j = tw_get(twq, 2 * j * ts, quarter);
+            w4j = tw_get(twq, 4 * j * ts, quarter);
+            w8j = tw_get(twq, 8 * j * ts, quarter);
+        }
+        if (!INV) {
+#pragma unroll
+            for (int a = 0; a < 4; ++a) bf4_dif(x[a], x[a + 4], x[a + 8], x[a + 12], cmul(wj, w16c(a)), cmul(w2j, w8c(a)));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bf4_dif(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3], w4j, w8j);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bf4_dit(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3], w4j, w8j);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) bf4_dit(x[a], x[a + 4], x[a + 8], x[a + 12], cmul(wj, w16c(a)), cmul(w2j, w8c(a)));
         }
 #pragma unroll
-        for (int u = 0; u < RF_U; ++u) {
-            if (i0[u] < 0) continue;
-            const double2 b0 = cadd(a[u][0], a[u][2]), b2 = cmul(csub(a[u][0], a[u][2]), w1[u]), b1 = cadd(a[u][1], a[u][3]);
-            const double2 d13 = csub(a[u][1], a[u][3]);
-            const double2 b3 = cmul(make_double2(d13.y, -d13.x), w1[u]);  // (a1 - a3) (-i) W^j
-            double2 c0 = cadd(b0, b1), c1 = cmul(csub(b0, b1), w2[u]), c2 = cadd(b2, b3), c3 = cmul(csub(b2, b3), w2[u]);
-            if (POST) {
-                c0 = cmul(c0, __ldg(&post[i0[u]])); c1 = cmul(c1, __ldg(&post[i0[u] + q]));
-                c2 = cmul(c2, __ldg(&post[i0[u] + 2 * q])); c3 = cmul(c3, __ldg(&post[i0[u] + 3 * q]));
-            }
-            buf[i0[u]] = c0; buf[i0[u] + q] = c1; buf[i0[u] + 2 * q] = c2; buf[i0[u] + 3 * q] = c3;
+        for (int k = 0; k < 16; ++k) {
+            double2 v = x[k];
+            if (POST) v = cmul(v, __ldg(&post[i0 + k * s]));
+            buf[PADI(i0 + k * s)] = v;
         }
     }
     __syncthreads();
 }
 
-__device__ __forceinline__ void dit4_pass(double2* buf, int M, int N, const double2* twq, int twn)
+// radix-4 pass over sub-transforms of size N (N >= 4)
+template <bool INV>
+__device__ __forceinline__ void pass4(double2* buf, int M, int N, const double2* twq, int twn)
 {
     const int q = N >> 2, lq = 31 - __clz(q), ts = twn / N, quarter = twn >> 2, nq = M >> 2;
-    for (int t0 = 0; t0 < nq; t0 += RF_NT * RF_U) {
-        double2 c[RF_U][4], w1[RF_U], w2[RF_U];
-        int i0[RF_U];
-#pragma unroll
-        for (int u = 0; u < RF_U; ++u) {
-            const int t = t0 + u * RF_NT + threadIdx.x;
-            i0[u] = -1;
-            if (t < nq) {
-                const int g = t >> lq, j = t & (q - 1);
-                i0[u] = g * N + j;
-                c[u][0] = buf[i0[u]]; c[u][1] = buf[i0[u] + q]; c[u][2] = buf[i0[u] + 2 * q]; c[u][3] = buf[i0[u] + 3 * q];
-                w1[u] = twq[j * ts];
-                w2[u] = tw_get(twq, 2 * j * ts, quarter);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < RF_U; ++u) {
-            if (i0[u] < 0) continue;
-            const double2 t1 = cmulc(c[u][1], w2[u]), t3 = cmulc(c[u][3], w2[u]);
-            const double2 b0 = cadd(c[u][0], t1), b1 = csub(c[u][0], t1), b2 = cadd(c[u][2], t3), b3 = csub(c[u][2], t3);
-            const double2 t2 = cmulc(b2, w1[u]), v3 = cmulc(b3, w1[u]);
-            const double2 u3 = make_double2(-v3.y, v3.x);  // (+i) conj(W)^j b3
-            buf[i0[u]] = cadd(b0, t2); buf[i0[u] + 2 * q] = csub(b0, t2);
-            buf[i0[u] + q] = cadd(b1, u3); buf[i0[u] + 3 * q] = csub(b1, u3);
-        }
+    for (int t = threadIdx.x; t < nq; t += RF_NT) {
+        const int g = t >> lq, j = t & (q - 1), i0 = g * N + j;
+        double2 a0 = buf[PADI(i0)], a1 = buf[PADI(i0 + q)], a2 = buf[PADI(i0 + 2 * q)], a3 = buf[PADI(i0 + 3 * q)];
+        const double2 w1 = twq[j * ts], w2 = tw_get(twq, 2 * j * ts, quarter);
+        if (!INV) bf4_dif(a0, a1, a2, a3, w1, w2); else bf4_dit(a0, a1, a2, a3, w1, w2);
+        buf[PADI(i0)] = a0; buf[PADI(i0 + q)] = a1; buf[PADI(i0 + 2 * q)] = a2; buf[PADI(i0 + 3 * q)] = a3;
     }
     __syncthreads();
 }
 
-template <bool POST>
-__device__ __forceinline__ void r2_pass(double2* buf, int M, const double2* __restrict__ post)
+// radix-2 pass over sub-transforms of size N (N >= 2)
+template <bool INV>
+__device__ __forceinline__ void pass2(double2* buf, int M, int N, const double2* twq, int twn)
 {
+    const int h = N >> 1, lh = 31 - __clz(h), ts = twn / N;
     for (int t = threadIdx.x; t < (M >> 1); t += RF_NT) {
-        const double2 a = buf[2 * t], b = buf[2 * t + 1];
-        double2 s = cadd(a, b), d = csub(a, b);
-        if (POST) { s = cmul(s, __ldg(&post[2 * t])); d = cmul(d, __ldg(&post[2 * t + 1])); }
-        buf[2 * t] = s; buf[2 * t + 1] = d;
+        const int g = t >> lh, j = t & (h - 1), i0 = g * N + j;
+        const double2 a = buf[PADI(i0)], b = buf[PADI(i0 + h)];
+        const double2 w = tw_get(twq, j * ts, twn >> 2);
+        if (!INV) { buf[PADI(i0)] = cadd(a, b); buf[PADI(i0 + h)] = cmul(csub(a, b), w); }
+        else { const double2 tb = cmulc(b, w); buf[PADI(i0)] = cadd(a, tb); buf[PADI(i0 + h)] = csub(a, tb); }
     }
     __syncthreads();
 }
 
 // In-place forward DIF FFT (kernel exp(-2 pi i jk/M)), natural order in, bit-reversed order out;
-// POST: the bit-reversed-order output is multiplied by post[] inside the last pass.
+// POST: the bit-reversed-order output is multiplied by post[] inside the last pass (needs M >= 16).
 template <bool POST>
 __device__ void fft_dif(double2* buf, int M, const double2* twq, int twn, const double2* __restrict__ post)
 {
-    const int lg = 31 - __clz(M);
+    const int lg = 31 - __clz(M), r = lg & 3;
     int N = M;
-    while (N >= 4) {
-        const bool last = !(lg & 1) && N == 4;
-        if (POST && last) dif4_pass<true>(buf, M, N, twq, twn, post);
-        else dif4_pass<false>(buf, M, N, twq, twn, post);
-        N >>= 2;
+    if (r & 1) { pass2<false>(buf, M, N, twq, twn); N >>= 1; }
+    if (r & 2) { pass4<false>(buf, M, N, twq, twn); N >>= 2; }
+    while (N >= 16) {
+        if (POST && N == 16) pass16<false, true>(buf, M, N, twq, twn, post);
+        else pass16<false, false>(buf, M, N, twq, twn, post);
+        N >>= 4;
     }
-    if (N == 2) r2_pass<POST>(buf, M, post);
 }
 
 // In-place inverse DIT FFT (kernel exp(+2 pi i jk/M), unnormalised), bit-reversed in, natural out.
 __device__ void fft_dit_inv(double2* buf, int M, const double2* twq, int twn)
 {
-    const int lg = 31 - __clz(M);
-    int N = 4;
-    if (lg & 1) { r2_pass<false>(buf, M, nullptr); N = 8; }
-    while (N <= M) { dit4_pass(buf, M, N, twq, twn); N <<= 2; }
+    const int lg = 31 - __clz(M), r = lg & 3;
+    const int Ntop = M >> r;  // largest radix-16 sub-transform size
+    for (int N = 16; N <= Ntop; N <<= 4) pass16<true, false>(buf, M, N, twq, twn, nullptr);
+    int N = Ntop;
+    if (r & 2) { N <<= 2; pass4<true>(buf, M, N, twq, twn); }
+    if (r & 1) { N <<= 1; pass2<true>(buf, M, N, twq, twn); }
 }
 
 __device__ __forceinline__ void load_twq(const PlanDev& P, double2* twq)
@@ -179,31 +201,31 @@ __global__ void __launch_bounds__(RF_NT) bluestein_setup_kernel(PlanDev P, doubl
 {
     extern __shared__ double2 smem_all[];
     double2* twq = smem_all;
-    double2* smem = smem_all + (P.tw_n >> 2) + 1;
+    double2* buf = smem_all + (P.tw_n >> 2) + 1;
     load_twq(P, twq);
     const BluesteinDesc d = P.bs[blockIdx.x];
     double2* chirp = tab + d.chirp_off;
     double2* bhat = tab + d.bhat_off;
-    for (int k = threadIdx.x; k < d.M; k += blockDim.x) smem[k] = make_double2(0.0, 0.0);
+    for (int k = threadIdx.x; k < d.M; k += blockDim.x) buf[PADI(k)] = make_double2(0.0, 0.0);
     __syncthreads();
     for (int t = threadIdx.x; t < d.n; t += blockDim.x) {
         const double2 c = chirp_val(t, d.n);
         chirp[t] = c;
         const double2 cc = make_double2(c.x, -c.y);
-        smem[t] = cc;
-        if (t > 0) smem[d.M - t] = cc;
+        buf[PADI(t)] = cc;
+        if (t > 0) buf[PADI(d.M - t)] = cc;
     }
     __syncthreads();
-    fft_dif<false>(smem, d.M, twq, P.tw_n, nullptr);
+    fft_dif<false>(buf, d.M, twq, P.tw_n, nullptr);
     const double inv = 1.0 / (double)d.M;
-    for (int k = threadIdx.x; k < d.M; k += blockDim.x) bhat[k] = make_double2(smem[k].x * inv, smem[k].y * inv);
+    for (int k = threadIdx.x; k < d.M; k += blockDim.x) { const double2 v = buf[PADI(k)]; bhat[k] = make_double2(v.x * inv, v.y * inv); }
     (void)nbs;
 }
 
 __device__ __forceinline__ double2 ring_phase(const PlanDev& P, int ring, int m)
 {  // exp(i m phi0), phi0 = pi q / den
     const int q = P.ring_phq[ring], den = P.ring_phden[ring];
-    const int r = (int)(((long long)m * q) % (2 * den));
+    const unsigned r = ((unsigned)m * (unsigned)q) % (2u * (unsigned)den);  // m q < 2^31 for every supported size
     double s, c;
     sincospi((double)r / (double)den, &s, &c);
     return make_double2(c, s);
@@ -219,46 +241,58 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __
     const RingJob job = jobs[blockIdx.x];
     const int n = P.ring_nphi[job.ringA], bsi = P.ring_bs[job.ringA];
     double2* twq = smem;
-    double2* stA = twq + (P.tw_n >> 2) + 1;
-    double2* stB = stA + nm;
-    double2* buf = stB + nm;
+    double2* st = twq + (P.tw_n >> 2) + 1;   // one component of the phased ring spectrum at a time
+    double2* buf = st + nm;
     load_twq(P, twq);
-    const double2* FA = Fm + ((int64_t)job.compA * P.nring + job.ringA) * nm;
-    const double2* FB = job.ringB >= 0 ? Fm + ((int64_t)job.compB * P.nring + job.ringB) * nm : nullptr;
-    const bool same_phase = job.ringB == job.ringA ||
-                            (job.ringB >= 0 && P.ring_phq[job.ringB] == P.ring_phq[job.ringA] && P.ring_phden[job.ringB] == P.ring_phden[job.ringA]);
-    for (int m = threadIdx.x; m <= L; m += RF_NT) {
-        const double w = m ? 1.0 : 0.5;  // (2 - delta_m0) / 2
-        double2 ph = ring_phase(P, job.ringA, m);
-        ph.x *= w; ph.y *= w;
-        stA[m] = cmul(FA[m], ph);
-        if (FB) {
-            double2 phb = ph;
-            if (!same_phase) { phb = ring_phase(P, job.ringB, m); phb.x *= w; phb.y *= w; }
-            stB[m] = cmul(FB[m], phb);
-        } else stB[m] = make_double2(0.0, 0.0);
-    }
-    __syncthreads();
     const int lg = 31 - __clz(n);
     const double2* chirp = bsi >= 0 ? P.bs_tab + P.bs[bsi].chirp_off : nullptr;
     const int M = bsi >= 0 ? P.bs[bsi].M : n;
-    for (int k = threadIdx.x; k < M; k += RF_NT) {
-        if (k >= n) { buf[k] = make_double2(0.0, 0.0); continue; }
-        const int kk = (n - k) % n;
-        double2 ga = make_double2(0.0, 0.0), gb = ga, ha = ga, hb = ga;
-        for (int m = k; m <= L; m += n) { ga = cadd(ga, stA[m]); gb = cadd(gb, stB[m]); }
-        for (int m = kk; m <= L; m += n) { ha = cadd(ha, stA[m]); hb = cadd(hb, stB[m]); }
-        // X = G[k] + conj G[n-k] (the 1/2 is in w);  Z = Xa + i Xb
-        const double2 xa = make_double2(ga.x + ha.x, ga.y - ha.y), xb = make_double2(gb.x + hb.x, gb.y - hb.y);
-        const double2 z = make_double2(xa.x - xb.y, xa.y + xb.x);
-        if (bsi < 0) buf[(int)(__brev((unsigned)k) >> (32 - lg))] = z;
-        else buf[k] = cmul(z, __ldg(&chirp[k]));
+    const bool same_phase = job.ringB == job.ringA ||
+                            (job.ringB >= 0 && P.ring_phq[job.ringB] == P.ring_phq[job.ringA] && P.ring_phden[job.ringB] == P.ring_phden[job.ringA]);
+    // Z[k] = Xa[k] + i Xb[k], X[k] = G[k] + conj G[n-k], G[k] = sum_{m = k mod n} w_m F_m e^{i m phi0} (alias fold),
+    // built in two sweeps (A, then B) through one staging buffer; stored bit-reversed (power-of-two n) or
+    // chirp-multiplied and zero-padded (Bluestein)
+    for (int comp = 0; comp < 2; ++comp) {
+        const int ring = comp ? job.ringB : job.ringA;
+        if (comp) __syncthreads();
+        if (ring >= 0) {
+            const double2* F = Fm + ((int64_t)(comp ? job.compB : job.compA) * P.nring + ring) * nm;
+            // e^{i m phi0} for m = tid, tid + 256, ...: one sincospi, then multiply by e^{i 256 phi0}
+            const int pr = (comp && !same_phase) ? job.ringB : job.ringA;
+            double2 ph = ring_phase(P, pr, threadIdx.x);
+            const double2 step = ring_phase(P, pr, RF_NT);
+            for (int m = threadIdx.x; m <= L; m += RF_NT) {
+                const double w = m ? 1.0 : 0.5;  // (2 - delta_m0) / 2
+                st[m] = cmul(F[m], make_double2(ph.x * w, ph.y * w));
+                ph = cmul(ph, step);
+            }
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < M; k += RF_NT) {
+            const int pos = PADI(bsi < 0 ? (int)(__brev((unsigned)k) >> (32 - lg)) : k);
+            if (k >= n) { if (!comp) buf[pos] = make_double2(0.0, 0.0); continue; }
+            double2 x = make_double2(0.0, 0.0);
+            if (ring >= 0) {
+                const int kk = (n - k) % n;
+                double2 g = make_double2(0.0, 0.0), h = g;
+                for (int m = k; m <= L; m += n) g = cadd(g, st[m]);
+                for (int m = kk; m <= L; m += n) h = cadd(h, st[m]);
+                x = make_double2(g.x + h.x, g.y - h.y);
+            }
+            if (!comp) buf[pos] = x;
+            else {
+                double2 z = buf[pos];
+                z = make_double2(z.x - x.y, z.y + x.x);   // + i Xb
+                if (bsi >= 0) z = cmul(z, __ldg(&chirp[k]));
+                buf[pos] = z;
+            }
+        }
     }
     ring_idft(P, buf, twq, n, bsi);
     double* oa = (job.compA ? mapU : mapQ) + P.ring_start[job.ringA];
     double* ob = job.ringB >= 0 ? (job.compB ? mapU : mapQ) + P.ring_start[job.ringB] : nullptr;
     for (int j = threadIdx.x; j < n; j += RF_NT) {
-        double2 z = buf[j];
+        double2 z = buf[PADI(j)];
         if (bsi >= 0) z = cmul(z, __ldg(&chirp[j]));
         oa[j] = z.x;
         if (ob) ob[j] = z.y;
@@ -285,33 +319,37 @@ ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double* __re
     const int M = bsi >= 0 ? P.bs[bsi].M : n;
     // Z[k] = sum_j z_j exp(-2 pi i jk/n) = conj( idft( conj z ) )
     for (int j = threadIdx.x; j < M; j += RF_NT) {
-        if (j >= n) { buf[j] = make_double2(0.0, 0.0); continue; }
+        const int pos = PADI(bsi < 0 ? (int)(__brev((unsigned)j) >> (32 - lg)) : j);
+        if (j >= n) { buf[pos] = make_double2(0.0, 0.0); continue; }
         double a = ia[j], b = ib ? ib[j] : 0.0;
         if (pixw) { a *= pixw[sa + j]; if (ib) b *= pixw[sb + j]; }
-        const double2 z = make_double2(a, -b);
-        if (bsi < 0) buf[(int)(__brev((unsigned)j) >> (32 - lg))] = z;
-        else buf[j] = cmul(z, __ldg(&chirp[j]));
+        double2 z = make_double2(a, -b);
+        if (bsi >= 0) z = cmul(z, __ldg(&chirp[j]));
+        buf[pos] = z;
     }
     ring_idft(P, buf, twq, n, bsi);
     if (bsi >= 0) {  // finish Bluestein in place: every m below reads two entries
-        for (int k = threadIdx.x; k < n; k += RF_NT) buf[k] = cmul(buf[k], __ldg(&chirp[k]));
+        for (int k = threadIdx.x; k < n; k += RF_NT) buf[PADI(k)] = cmul(buf[PADI(k)], __ldg(&chirp[k]));
         __syncthreads();
     }
     double2* FA = Fm + ((int64_t)job.compA * P.nring + job.ringA) * nm;
     double2* FB = job.ringB >= 0 ? Fm + ((int64_t)job.compB * P.nring + job.ringB) * nm : nullptr;
     const bool same_phase = job.ringB == job.ringA ||
                             (job.ringB >= 0 && P.ring_phq[job.ringB] == P.ring_phq[job.ringA] && P.ring_phden[job.ringB] == P.ring_phden[job.ringA]);
+    double2 pa = ring_phase(P, job.ringA, threadIdx.x), pb = same_phase ? pa : ring_phase(P, job.ringB, threadIdx.x);
+    const double2 stepa = ring_phase(P, job.ringA, RF_NT), stepb = same_phase ? stepa : ring_phase(P, job.ringB, RF_NT);
     for (int m = threadIdx.x; m <= L; m += RF_NT) {
         const int k = m % n, kk = (n - k) % n;
-        const double2 c1 = buf[k], c2 = buf[kk];
+        const double2 c1 = buf[PADI(k)], c2 = buf[PADI(kk)];
         const double2 z1 = make_double2(c1.x, -c1.y);  // Z[k]
         const double2 z2c = c2;                         // conj Z[n-k]
         const double2 xa = make_double2(0.5 * (z1.x + z2c.x), 0.5 * (z1.y + z2c.y));
         const double2 d = csub(z1, z2c);
         const double2 xb = make_double2(0.5 * d.y, -0.5 * d.x);
-        const double2 pa = ring_phase(P, job.ringA, m);
         FA[m] = cmulc(xa, pa);
-        if (FB) { const double2 pb = same_phase ? pa : ring_phase(P, job.ringB, m); FB[m] = cmulc(xb, pb); }
+        if (FB) FB[m] = cmulc(xb, pb);
+        pa = cmul(pa, stepa);
+        pb = cmul(pb, stepb);
     }
 }
 
@@ -341,7 +379,7 @@ int gs_ring_setup(gs_plan* p)
     for (int r = 0; r < nring; ++r) rbs[r] = n2bs.count(rn[r]) ? n2bs[rn[r]] : -1;
     p->d.max_M = maxM;
     p->d.tw_n = maxM;
-    p->ring_smem = (size_t)(2 * (L + 1) + maxM + maxM / 4 + 1) * sizeof(double2);
+    p->ring_smem = (size_t)((L + 1) + (maxM + maxM / 16 + 2) + maxM / 4 + 1) * sizeof(double2);
     if (p->ring_smem > 227 * 1024) {
         gs_set_error("ring FFT needs %zu bytes of shared memory (> 227 KB): nside/lmax too large for this build", p->ring_smem);
         return GS_E_BADARG;
