@@ -139,46 +139,42 @@ __device__ __forceinline__ void rescale_check(RingState<SPIN>& s)
 }
 
 // ------------------------------------------------------------------ staging of one l-tile
+// Each thread fetches the (pre-scaled) a_lm pair and the recurrence coefficients of ONE l of the tile into
+// registers (LEG_TL == LEG_NT); the values are stored to the other half of a double-buffered shared-memory
+// tile after the current tile has been consumed, so the global-memory latency hides behind the recurrence.
 template <int SPIN>
-__device__ __forceinline__ void stage_alm_tile(const PlanDev& P, int m, int lt, int64_t base, const double* almE,
-                                               const double* almB, int layout, const double* fl, const double* flB,
-                                               double2* sE, double2* sB, double2* sR)
+__device__ __forceinline__ void fetch_alm(const PlanDev& P, int m, int l, int64_t base, const double* almE, const double* almB,
+                                          int layout, const double* fl, const double* flB, double2& e, double2& b, double2& r)
 {
     const int L = P.lmax;
-    for (int i = threadIdx.x; i < LEG_TL; i += LEG_NT) {
-        const int l = lt + i;
-        double2 e = make_double2(0.0, 0.0), b = e, r = e;
-        if (l <= L) {
-            const int64_t id = base + l;
-            double pre = SPIN ? -0.5 * P.alpha2[id] : P.alpha0[id];
-            double preb = pre;
-            if (fl) pre *= fl[l];
-            if (flB) preb *= flB[l]; else preb = pre;
-            if (layout == GS_ALM_COMPLEX) {
-                e = reinterpret_cast<const double2*>(almE)[id];
-                if (SPIN) b = reinterpret_cast<const double2*>(almB)[id];
-            } else if (m == 0) {
-                e.x = almE[l];
-                if (SPIN) b.x = almB[l];
-            } else {
-                const int64_t off = 2 * id - (L + 1);
-                pre *= 0.70710678118654752440;
-                preb *= 0.70710678118654752440;
-                e.x = almE[off]; e.y = almE[off + 1];
-                if (SPIN) { b.x = almB[off]; b.y = almB[off + 1]; }
-            }
-            e.x *= pre; e.y *= pre; b.x *= preb; b.y *= preb;
-            if (SPIN) {
-                // lambda^+- basis: Q_m = sum l+ (E' + iB') + l- (E' - iB'), U_m = -i [l+ (E' + iB') - l- (E' - iB')]
-                // -> c1 = E'r - B'i, c2 = E'r + B'i, c3 = E'i + B'r, c4 = E'i - B'r
-                const double2 c12 = make_double2(e.x - b.y, e.x + b.y), c34 = make_double2(e.y + b.x, e.y - b.x);
-                e = c12; b = c34;
-                r = P.rec2[id];
-            } else r.x = P.rec0[id];
+    e = make_double2(0.0, 0.0); b = e; r = e;
+    if (l <= L) {
+        const int64_t id = base + l;
+        double pre = SPIN ? -0.5 * P.alpha2[id] : P.alpha0[id];
+        double preb = pre;
+        if (fl) pre *= fl[l];
+        if (flB) preb *= flB[l]; else preb = pre;
+        if (layout == GS_ALM_COMPLEX) {
+            e = reinterpret_cast<const double2*>(almE)[id];
+            if (SPIN) b = reinterpret_cast<const double2*>(almB)[id];
+        } else if (m == 0) {
+            e.x = almE[l];
+            if (SPIN) b.x = almB[l];
+        } else {
+            const int64_t off = 2 * id - (L + 1);
+            pre *= 0.70710678118654752440;
+            preb *= 0.70710678118654752440;
+            e.x = almE[off]; e.y = almE[off + 1];
+            if (SPIN) { b.x = almB[off]; b.y = almB[off + 1]; }
         }
-        sE[i] = e;
-        if (SPIN) sB[i] = b;
-        sR[i] = r;
+        e.x *= pre; e.y *= pre; b.x *= preb; b.y *= preb;
+        if (SPIN) {
+            // lambda^+- basis: Q_m = sum l+ (E' + iB') + l- (E' - iB'), U_m = -i [l+ (E' + iB') - l- (E' - iB')]
+            // -> c1 = E'r - B'i, c2 = E'r + B'i, c3 = E'i + B'r, c4 = E'i - B'r
+            const double2 c12 = make_double2(e.x - b.y, e.x + b.y), c34 = make_double2(e.y + b.x, e.y - b.x);
+            e = c12; b = c34;
+            r = P.rec2[id];
+        } else r.x = P.rec0[id];
     }
 }
 
@@ -221,7 +217,8 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
                  const int* __restrict__ skip)
 {
     if (skip && *skip) return;
-    __shared__ double2 sE[LEG_TL], sB[SPIN ? LEG_TL : 1], sR[LEG_TL];
+    static_assert(LEG_TL == LEG_NT, "one staged l per thread");
+    __shared__ double2 sEb[2][LEG_TL], sBb[2][SPIN ? LEG_TL : 1], sRb[2][LEG_TL];
     const int L = P.lmax, m = blockIdx.y, tid = threadIdx.x;
     const int l0 = m > SPIN ? m : SPIN;
     const int64_t base = (int64_t)m * (2 * L + 1 - m) / 2;
@@ -244,12 +241,21 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
     }
     const bool warp_act = __any_sync(FULL, any_act);
 
-    for (int lt = l0; lt <= L; lt += LEG_TL) {
-        __syncthreads();
-        stage_alm_tile<SPIN>(P, m, lt, base, almE, almB, layout, fl, flB, sE, sB, sR);
-        __syncthreads();
-        if (!warp_act) continue;
-        const int ni = min(LEG_TL, L - lt + 1);
+    {
+        double2 e, b, r;
+        fetch_alm<SPIN>(P, m, l0 + tid, base, almE, almB, layout, fl, flB, e, b, r);
+        sEb[0][tid] = e; if (SPIN) sBb[0][tid] = b; sRb[0][tid] = r;
+    }
+    __syncthreads();
+    int cur = 0;
+    for (int lt = l0; lt <= L; lt += LEG_TL, cur ^= 1) {
+        const bool has_next = lt + LEG_TL <= L;
+        double2 ne, nb, nr;
+        if (has_next) fetch_alm<SPIN>(P, m, lt + LEG_TL + tid, base, almE, almB, layout, fl, flB, ne, nb, nr);
+        const double2* sE = sEb[cur];
+        const double2* sB = sBb[cur];
+        const double2* sR = sRb[cur];
+        const int ni = warp_act ? min(LEG_TL, L - lt + 1) : 0;
         const int npr = (ni + 1) >> 1;
         int ip = 0;
         // (A) every lane still below range: recurrence only
@@ -302,6 +308,8 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
                 rec_step<SPIN>(st[j], r1.x, r1.y);
             }
         }
+        if (has_next) { sEb[cur ^ 1][tid] = ne; if (SPIN) sBb[cur ^ 1][tid] = nb; sRb[cur ^ 1][tid] = nr; }
+        __syncthreads();
     }
 
     // spin 0: north = S + A, south = +-(S - A); spin 2: combine the lambda^+- sums; the south sign follows the
@@ -401,8 +409,11 @@ __device__ __forceinline__ double warp_fold(double* v, int lane)
     }
 }
 
+#ifndef LEG_MINB_A
+#define LEG_MINB_A 1
+#endif
 template <int SPIN, int R>
-__global__ void __launch_bounds__(LEG_NT)
+__global__ void __launch_bounds__(LEG_NT, LEG_MINB_A)
 leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ partial, const int* __restrict__ skip)
 {
     if (skip && *skip) return;
