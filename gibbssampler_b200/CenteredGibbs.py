@@ -42,9 +42,9 @@ class PolarizedCenteredConstrainedRealization(ConstrainedRealization):
 
     def __init__(self, pix_map, noise_temp, noise_pol, bl_map, lmax, Npix, bl_fwhm, mask_path=None,
                  gibbs_cr=False, n_gibbs=1, alpha=-0.995, overrelaxation=False, ula=True, *, mask=None,
-                 rng="philox", seed=None, direct_when_isotropic=True):
+                 rng="philox", seed=None, direct_when_isotropic=True, plan=None):
         super().__init__(pix_map, noise_temp, bl_map, bl_fwhm, lmax, Npix, mask_path=mask_path, mask=mask, rng=rng,
-                         seed=seed)
+                         seed=seed, plan=plan)
         self.noise_temp = noise_temp
         self.noise_pol = noise_pol
         self.n_gibbs = n_gibbs
@@ -52,7 +52,7 @@ class PolarizedCenteredConstrainedRealization(ConstrainedRealization):
         self.inv_noise_pol = self._inv_noise_from(noise_pol)          # mask / noise_pol (CenteredGibbs.py:261-274)
         self.sqrt_inv_noise_pol = torch.sqrt(self.inv_noise_pol)
         self.inv_noise = [self.inv_noise_pol]
-        self.mu = float(self.inv_noise_pol.max().item()) + 1e-14       # CenteredGibbs.py:276
+        self.mu = float(self.inv_noise_pol.max().item()) + 1e-14       # CenteredGibbs.py:276 (local max on sharded plans)
         self.gibbs_cr = gibbs_cr
         self.overrelaxation = overrelaxation
         self.pcg_accuracy = 1.0e-5                                      # CenteredGibbs.py:280
@@ -64,12 +64,12 @@ class PolarizedCenteredConstrainedRealization(ConstrainedRealization):
         self.bl_fwhm = bl_fwhm
         self.tau = 0.02
         self.direct_when_isotropic = direct_when_isotropic
-        self.ninv_sum_over_4pi = _dev.dsum(self.inv_noise_pol) / (4 * np.pi)
+        self.ninv_sum_over_4pi = self.plan.allreduce_sum(_dev.dsum(self.inv_noise_pol)) / (4 * np.pi)
         self.noise_pol0 = float(f64(noise_pol).reshape(-1)[0].item())
-        self.d_Q = f64(pix_map["Q"]) if "Q" in pix_map else None
-        self.d_U = f64(pix_map["U"]) if "U" in pix_map else None
-        self.d_E = f64(pix_map["EE"]) if "EE" in pix_map else None
-        self.d_B = f64(pix_map["BB"]) if "BB" in pix_map else None
+        self.d_Q = self.plan.local_map(f64(pix_map["Q"])) if "Q" in pix_map else None
+        self.d_U = self.plan.local_map(f64(pix_map["U"])) if "U" in pix_map else None
+        self.d_E = self.plan.local_alm(f64(pix_map["EE"])) if "EE" in pix_map else None
+        self.d_B = self.plan.local_alm(f64(pix_map["BB"])) if "BB" in pix_map else None
         # second_part_grad = b (Npix/4pi) map2alm_iter0(N^-1 d) = B A^T N^-1 d (CenteredGibbs.py:298-308):
         # constant data term of every right-hand side
         if self.d_Q is not None:
@@ -109,9 +109,15 @@ class PolarizedCenteredConstrainedRealization(ConstrainedRealization):
         """b of Q x = b (CenteredGibbs.py:469-483).  xi = (xi_Q, xi_U, xi_E, xi_B) may be injected."""
         dle, dlb = self._dls(all_dls)
         if xi is None:
-            xi = (self.rng.normal(self.Npix), self.rng.normal(self.Npix),
-                  self.rng.normal(self.dimension_alm), self.rng.normal(self.dimension_alm))
+            if self.plan.world > 1 and self.rng.mode == "numpy":
+                # reference order on the full arrays (every rank draws the same stream), then cut to the shard
+                xi = (self.rng.normal(self.plan.npix_global), self.rng.normal(self.plan.npix_global),
+                      self.rng.normal(self.plan.nreal_global), self.rng.normal(self.plan.nreal_global))
+            else:
+                xi = (self.rng.normal(self.npix_local), self.rng.normal(self.npix_local),
+                      self.rng.normal(self.dimension_alm), self.rng.normal(self.dimension_alm))
         xq, xu, xe, xb = [f64(x) for x in xi]
+        xq, xu, xe, xb = self.plan.local_map(xq), self.plan.local_map(xu), self.plan.local_alm(xe), self.plan.local_alm(xb)
         rhs_e = torch.empty(self.dimension_alm, dtype=torch.float64, device=self.dev)
         rhs_b = torch.empty_like(rhs_e)
         check(_lib.lib().gs_cr_rhs_pol(self.plan._h, ptr(dle), ptr(dlb), ptr(self.bl_gauss_d), ptr(self.inv_noise_pol),
@@ -192,14 +198,22 @@ class PolarizedCenteredConstrainedRealization(ConstrainedRealization):
 class CenteredGibbs(GibbsSampler):
     def __init__(self, pix_map, noise_temp, noise_pol, beam, nside, lmax, Npix, mask_path=None,
                  polarization=False, bins=None, n_iter=100000, rj_step=False, all_sph=False, gibbs_cr=False,
-                 overrelaxation=False, ula=False, *, mask=None, rng="philox", seed=None, verbose=False):
+                 overrelaxation=False, ula=False, *, mask=None, rng="philox", seed=None, verbose=False, plan=None):
+        """`plan` = a gibbssampler_b200.sharded.ShardedPlan runs this single chain m-sharded over the GPUs of the
+        plan's process group (BASELINE config #4); inputs are full-sky arrays as usual, sky maps returned by the
+        constrained sampler are local alm shards (plan.gather_alm reassembles them)."""
         super().__init__(pix_map, noise_temp, beam, nside, lmax, polarization=polarization, bins=bins, n_iter=n_iter,
                          rj_step=rj_step, gibbs_cr=gibbs_cr, verbose=verbose)
         shared = _dev.Rng(rng, seed)
+        # the C_l draw must be identical on every rank of a sharded chain (same seed); the pixel / alm draws of
+        # the constrained realization are per shard and must differ between ranks
+        cr_rng = shared
+        if plan is not None and plan.world > 1 and shared.mode == "philox":
+            cr_rng = _dev.Rng(rng, shared.seed + 7919 * (plan.rank + 1))
         if not polarization:
             raise NotImplementedError("temperature-only samplers are not provided (reference TT path is dead at HEAD)")
         self.cls_sampler = PolarizedCenteredClsSampler(pix_map, lmax, nside, self.bins, self.bl_map, noise_temp,
-                                                       mask_path=mask_path, mask=mask, rng=shared)
+                                                       mask_path=mask_path, mask=mask, rng=shared, plan=plan)
         self.constrained_sampler = PolarizedCenteredConstrainedRealization(
             pix_map, noise_temp, noise_pol, self.bl_map, lmax, Npix, beam, mask_path=mask_path, gibbs_cr=gibbs_cr,
-            overrelaxation=overrelaxation, ula=ula, mask=mask, rng=shared)
+            overrelaxation=overrelaxation, ula=ula, mask=mask, rng=cr_rng, plan=plan)

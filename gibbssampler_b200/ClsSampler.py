@@ -10,7 +10,7 @@ from .sht import Plan
 
 class ClsSampler():
     def __init__(self, pix_map, lmax, nside, bins, bl_map, noise, mask_path=None, *, mask=None, rng="philox",
-                 seed=None):
+                 seed=None, plan=None):
         """Same arguments as ClsSampler.__init__ (ClsSampler.py:9); mask/rng as in ConstrainedRealization."""
         self.lmax = int(lmax)
         self.bins = bins
@@ -27,12 +27,15 @@ class ClsSampler():
             self.inv_noise = self.inv_noise * f64(self._mask_arr)  # ClsSampler.py:28-33
         self.rng = rng if isinstance(rng, _dev.Rng) else _dev.Rng(rng, seed)
         self._call = 0
+        self.plan = plan  # a ShardedPlan: alms are local m shards, alm2cl all-reduces (gs_shard_alm2cl)
 
     def sample(self, alm_map):
         return None
 
     # ---- shared device helpers -------------------------------------------------------------
     def _alm2cl_real(self, alms_real_d):
+        if self.plan is not None:
+            return self.plan.alm2cl(alms_real_d)
         cl = torch.empty(self.lmax + 1, dtype=torch.float64, device=self.dev)
         check(_lib.lib().gs_alm2cl(ptr(alms_real_d), GS_ALM_REAL, self.lmax, ptr(cl), stream()))
         return cl

@@ -18,18 +18,21 @@ class ConstrainedRealization():
     replaced by the device-resident N^-1, b_l and PCG settings below."""
 
     def __init__(self, pix_map, noise, bl_map, fwhm_deg, lmax, Npix, mask_path=None, isotropic=True,
-                 *, mask=None, rng="philox", seed=None):
+                 *, mask=None, rng="philox", seed=None, plan=None):
         self.pix_map = pix_map
         self.isotropic = isotropic
         self.noise = noise
         self.dev = _dev.device()
         self.lmax = int(lmax)
-        self.dimension_alm = (self.lmax + 1) ** 2
         self.Npix = int(Npix)
         self.nside = int(round(math.sqrt(self.Npix / 12)))
         if 12 * self.nside ** 2 != self.Npix:
             raise ValueError("Npix = %d is not 12 nside^2" % self.Npix)
-        self.plan = Plan.get(self.nside, self.lmax)
+        # `plan` = a gibbssampler_b200.sharded.ShardedPlan runs the single chain m-sharded over the ranks of
+        # its process group: full-sky inputs are cut to the local ring shard, alms are local m shards
+        self.plan = plan if plan is not None else Plan.get(self.nside, self.lmax)
+        self.dimension_alm = self.plan.nreal     # (lmax+1)^2 on one GPU
+        self.npix_local = self.plan.npix         # Npix on one GPU
         self.fwhm_radians = (np.pi / 180) * fwhm_deg
         self.bl_gauss = _dev.gauss_beam(self.fwhm_radians, self.lmax)  # hp.gauss_beam (ConstrainedRealization.py:31)
         self.bl_gauss_d = f64(self.bl_gauss)
@@ -56,7 +59,7 @@ class ConstrainedRealization():
         inv.copy_(1.0 / n)
         if self._mask_arr is not None:
             inv.mul_(f64(self._mask_arr))
-        return inv
+        return self.plan.local_map(inv)
 
     def sample(self, cls, var_cls):
         return None

@@ -65,6 +65,22 @@ SIGNATURES = {
     "gs_mala_propose": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _i64, _vp]),
     "gs_mala_logq": (_i, [_vp, _vp, _vp, _vp, _d, _i64, _vp, _vp, _vp]),
     "gs_dot3": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "gs_nccl_unique_id": (_i, [C.c_char_p]),
+    "gs_plan_create_sharded": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, C.c_char_p]),
+    "gs_local_group_create": (_i, [C.POINTER(_vp), _i]),
+    "gs_local_group_destroy": (_i, [_vp]),
+    "gs_plan_create_sharded_local": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _vp]),
+    "gs_plan_world": (_i, [_vp]),
+    "gs_plan_rank": (_i, [_vp]),
+    "gs_plan_nreal_local": (_i64, [_vp]),
+    "gs_plan_npix_local": (_i64, [_vp]),
+    "gs_shard_partition_m": (_i, [_i, _i, _i, _vp]),
+    "gs_shard_partition_rings": (_i, [_i, _i, _i, _vp]),
+    "gs_shard_real_index": (_i64, [_i, _i, _i, _vp]),
+    "gs_shard_pixel_index": (_i64, [_i, _i, _i, _vp]),
+    "gs_shard_expand_per_l": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "gs_shard_alm2cl": (_i, [_vp, _vp, _vp, _vp]),
+    "gs_shard_allreduce_sum": (_i, [_vp, _vp, _i, _vp]),
     "gs_launch_count": (C.c_longlong, []),
     "gs_profile_matvec": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(C.c_float), _vp]),
     "gs_measure_fp64_peak": (_i, [C.POINTER(_d), _vp]),

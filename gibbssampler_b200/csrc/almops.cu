@@ -95,10 +95,10 @@ __global__ void unfold_bins_kernel(const double* __restrict__ binned, const int*
 
 // ---- hp.almxfl: a_lm * f_l, either layout, out may alias in
 __global__ void almxfl_kernel(const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ fl, int L,
-                              int layout, int64_t n)
+                              int layout, int64_t n, const int* __restrict__ lof)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        if (layout == GS_ALM_REAL) out[i] = in[i] * fl[l_of_real_index(i, L)];
+        if (layout == GS_ALM_REAL) out[i] = in[i] * fl[lof ? lof[i] : l_of_real_index(i, L)];
         else {
             int l, m;
             lm_of_index(i, L, l, m);
@@ -184,7 +184,7 @@ extern "C" int gs_almxfl(const double* alm, int layout, int lmax, const double* 
 {
     GS_REQUIRE(alm && fl && out && lmax >= 0 && (layout == GS_ALM_COMPLEX || layout == GS_ALM_REAL), "bad arguments");
     const int64_t n = layout == GS_ALM_REAL ? (int64_t)(lmax + 1) * (lmax + 1) : gs_nalm(lmax);
-    almxfl_kernel<<<ew_blocks(n), EW_NT, 0, STREAM(stream)>>>(alm, out, fl, lmax, layout, n);
+    almxfl_kernel<<<ew_blocks(n), EW_NT, 0, STREAM(stream)>>>(alm, out, fl, lmax, layout, n, nullptr);
     GS_CHECK_LAUNCH();
     return GS_OK;
 }
@@ -247,16 +247,17 @@ static int map2alm_impl(gs_plan* p, int spin, const double* mapQ, const double* 
     for (int it = 0; it < iter; ++it) {  // a += map2alm0(f - alm2map(a))
         if ((rc = gs_leg_synth(p, spin, almE, almB, layout, nullptr, st))) return rc;
         if ((rc = gs_ring_synth(p, spin, p->mapQ_tmp, p->mapU_tmp, st))) return rc;
-        map_residual_kernel<<<ew_blocks(p->d.npix), EW_NT, 0, st>>>(mapQ, pixw, p->mapQ_tmp, p->mapQ_tmp, p->d.npix);
-        if (spin) map_residual_kernel<<<ew_blocks(p->d.npix), EW_NT, 0, st>>>(mapU, pixw, p->mapU_tmp, p->mapU_tmp, p->d.npix);
+        map_residual_kernel<<<ew_blocks(p->npix_loc), EW_NT, 0, st>>>(mapQ, pixw, p->mapQ_tmp, p->mapQ_tmp, p->npix_loc);
+        if (spin) map_residual_kernel<<<ew_blocks(p->npix_loc), EW_NT, 0, st>>>(mapU, pixw, p->mapU_tmp, p->mapU_tmp, p->npix_loc);
         GS_CHECK_LAUNCH();
         if ((rc = gs_ring_anal(p, spin, p->mapQ_tmp, p->mapU_tmp, nullptr, st))) return rc;
         if ((rc = gs_leg_anal(p, spin, almE, almB, layout, nullptr, scale, 1, st))) return rc;
     }
     if (iter > 0 && fl) {
-        const int64_t n = layout == GS_ALM_REAL ? (int64_t)(p->d.lmax + 1) * (p->d.lmax + 1) : p->d.nalm;
-        almxfl_kernel<<<ew_blocks(n), EW_NT, 0, st>>>(almE, almE, fl, p->d.lmax, layout, n);
-        if (spin) almxfl_kernel<<<ew_blocks(n), EW_NT, 0, st>>>(almB, almB, fl, p->d.lmax, layout, n);
+        const int64_t n = layout == GS_ALM_REAL ? p->nreal_loc : p->d.nalm;
+        const int* lof = p->world > 1 ? p->d.sh.l_of_loc : nullptr;
+        almxfl_kernel<<<ew_blocks(n), EW_NT, 0, st>>>(almE, almE, fl, p->d.lmax, layout, n, lof);
+        if (spin) almxfl_kernel<<<ew_blocks(n), EW_NT, 0, st>>>(almB, almB, fl, p->d.lmax, layout, n, lof);
         GS_CHECK_LAUNCH();
     }
     return GS_OK;

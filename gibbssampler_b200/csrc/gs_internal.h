@@ -50,6 +50,28 @@ struct RingJob {  // one complex DFT = two real ring sequences of equal length
     int ringB, compB;  // ringB = -1: no second sequence
 };
 
+// m-sharded transform over `world` GPUs (BASELINE config #4): every rank owns a set of m
+// (Legendre stage, all rings) and a set of ring pairs (ring-FFT / pixel stage, all m); the ring spectra
+// F_m(theta_r) travel between the two partitions in buffers laid out [peer][comp][RL][ML] (double2), so
+// that one all-to-all of equal-sized chunks performs the ring <-> m transpose:
+//   element (ring, m) lives at ((peer * 2 + comp) * RL + ring_loc[ring]) * ML + m_loc[m]
+//   with peer = ring_owner[ring] on the m-sharded side and peer = m_owner[m] on the ring-sharded side.
+struct ShardDev {
+    int world, rank;
+    int nm_loc;       // m owned by this rank
+    int ML, RL;       // per-rank m / ring counts, padded to the maximum over ranks
+    int64_t nalm_loc; // complex coefficients owned: sum over owned m of (L - m + 1)
+    const int* mlist;        // [nm_loc] owned m, ascending
+    const int64_t* cbase;    // [nm_loc] index of (l = m) in the local complex numbering
+    const int64_t* rbase;    // [nm_loc] offset of (l = m) in the local real layout
+    const int* m_owner;      // [L+1]
+    const int* m_loc;        // [L+1] index of m in its owner's mlist
+    const int* ring_owner;   // [nring]
+    const int* ring_loc;     // [nring] index of the ring in its owner's ring list
+    const int64_t* ring_start_loc;  // [nring] first pixel of the ring in its owner's local map
+    const int* l_of_loc;     // [nreal_loc] multipole of every entry of the local real layout
+};
+
 // Device-side view of a plan (plain pointers; passed by value to kernels).
 struct PlanDev {
     int nside, lmax, nring, npair;
@@ -80,11 +102,20 @@ struct PlanDev {
     const double2* tw;     // exp(-2 pi i k / tw_n), k < tw_n
     int tw_n;
     int max_M;
+    ShardDev sh;           // world == 1: unused
 };
 
 struct gs_plan {
     int device;
     PlanDev d;
+    // sharding (world == 1: nreal_loc = (L+1)^2, npix_loc = npix, no communicator)
+    int world, rank;
+    int64_t nreal_loc, npix_loc;
+    void* comm;         // ncclComm_t
+    void* lgroup;       // gs_local_group* (in-process test group) or NULL
+    double2* Fx;        // second spectra buffer (all-to-all peer of Fm) on sharded plans
+    double* red_loc;    // 4 doubles: local partial sums / all-reduced sums of the sharded PCG
+    std::vector<int> h_mlist, h_rings;
     std::vector<void*> owned;  // device allocations to free
     // job lists (device) for the ring-FFT stage
     RingJob* jobs2;  // spin 2: (Q,U) of each ring, heavy first
@@ -121,3 +152,12 @@ int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, c
                  const int* skip = nullptr);
 // almops.cu
 int gs_launch_expand_per_l(const double* x, int lmax, int mode, double* out, cudaStream_t st);
+// expansion over the plan's (possibly sharded) real layout
+int gs_plan_expand_per_l(gs_plan* p, const double* x, int mode, double* out, cudaStream_t st);
+// shard.cu
+int gs_shard_build(gs_plan* p, int rank, int world, const char* nccl_id);
+void gs_shard_free(gs_plan* p);
+// all-to-all of the spectra buffers (ring <-> m transpose): send -> recv, chunk = 2 RL ML double2 per peer
+int gs_shard_exchange(gs_plan* p, const double2* send, double2* recv, cudaStream_t st);
+// in-place sum over ranks of n doubles (device)
+int gs_shard_allreduce(gs_plan* p, double* buf, int n, cudaStream_t st);

@@ -143,7 +143,7 @@ __device__ __forceinline__ void rescale_check(RingState<SPIN>& s)
 // registers (LEG_TL == LEG_NT); the values are stored to the other half of a double-buffered shared-memory
 // tile after the current tile has been consumed, so the global-memory latency hides behind the recurrence.
 template <int SPIN>
-__device__ __forceinline__ void fetch_alm(const PlanDev& P, int m, int l, int64_t base, const double* almE, const double* almB,
+__device__ __forceinline__ void fetch_alm(const PlanDev& P, int m, int l, int64_t base, int64_t roff, const double* almE, const double* almB,
                                           int layout, const double* fl, const double* flB, double2& e, double2& b, double2& r)
 {
     const int L = P.lmax;
@@ -158,10 +158,10 @@ __device__ __forceinline__ void fetch_alm(const PlanDev& P, int m, int l, int64_
             e = reinterpret_cast<const double2*>(almE)[id];
             if (SPIN) b = reinterpret_cast<const double2*>(almB)[id];
         } else if (m == 0) {
-            e.x = almE[l];
-            if (SPIN) b.x = almB[l];
+            e.x = almE[roff + l];
+            if (SPIN) b.x = almB[roff + l];
         } else {
-            const int64_t off = 2 * id - (L + 1);
+            const int64_t off = roff + 2 * l;
             pre *= 0.70710678118654752440;
             preb *= 0.70710678118654752440;
             e.x = almE[off]; e.y = almE[off + 1];
@@ -176,6 +176,22 @@ __device__ __forceinline__ void fetch_alm(const PlanDev& P, int m, int l, int64_
             r = P.rec2[id];
         } else r.x = P.rec0[id];
     }
+}
+
+// Position of F_m(ring) of component comp in the ring-spectra buffer.  Unsharded: [comp][ring][m].
+// Sharded (SH): [peer = owner of the ring][comp][ring_loc][mk], mk = index of m in this rank's m list.
+template <bool SH>
+__device__ __forceinline__ int64_t fm_index(const PlanDev& P, int comp, int ring, int m, int mk)
+{
+    if (SH) return (((int64_t)P.sh.ring_owner[ring] * 2 + comp) * P.sh.RL + P.sh.ring_loc[ring]) * P.sh.ML + mk;
+    return ((int64_t)comp * P.nring + ring) * (P.lmax + 1) + m;
+}
+// offset such that entry (l, m) of the real layout sits at roff + (m ? 2 : 1) * l
+template <bool SH>
+__device__ __forceinline__ int64_t real_off(const PlanDev& P, int m, int mk, int64_t base)
+{
+    if (SH) return P.sh.rbase[mk] - (m ? 2 : 1) * (int64_t)m;
+    return m ? 2 * base - (P.lmax + 1) : 0;
 }
 
 // ------------------------------------------------------------------ synthesis
@@ -210,7 +226,7 @@ __device__ __forceinline__ void synth_acc(SynthAcc<SPIN>& A, double pc, double m
     }
 }
 
-template <int SPIN, int R>
+template <int SPIN, int R, bool SH>
 __global__ void __launch_bounds__(LEG_NT)
 leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __restrict__ almB, int layout,
                  const double* __restrict__ fl, const double* __restrict__ flB, double2* __restrict__ Fm,
@@ -219,9 +235,10 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
     if (skip && *skip) return;
     static_assert(LEG_TL == LEG_NT, "one staged l per thread");
     __shared__ double2 sEb[2][LEG_TL], sBb[2][SPIN ? LEG_TL : 1], sRb[2][LEG_TL];
-    const int L = P.lmax, m = blockIdx.y, tid = threadIdx.x;
+    const int L = P.lmax, mk = blockIdx.y, m = SH ? P.sh.mlist[mk] : mk, tid = threadIdx.x;
     const int l0 = m > SPIN ? m : SPIN;
     const int64_t base = (int64_t)m * (2 * L + 1 - m) / 2;
+    const int64_t roff = real_off<SH>(P, m, mk, base);
     const int chunk = blockIdx.x * (LEG_NT * R);
 
     RingState<SPIN> st[R];
@@ -243,7 +260,7 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
 
     {
         double2 e, b, r;
-        fetch_alm<SPIN>(P, m, l0 + tid, base, almE, almB, layout, fl, flB, e, b, r);
+        fetch_alm<SPIN>(P, m, l0 + tid, base, roff, almE, almB, layout, fl, flB, e, b, r);
         sEb[0][tid] = e; if (SPIN) sBb[0][tid] = b; sRb[0][tid] = r;
     }
     __syncthreads();
@@ -251,7 +268,7 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
     for (int lt = l0; lt <= L; lt += LEG_TL, cur ^= 1) {
         const bool has_next = lt + LEG_TL <= L;
         double2 ne, nb, nr;
-        if (has_next) fetch_alm<SPIN>(P, m, lt + LEG_TL + tid, base, almE, almB, layout, fl, flB, ne, nb, nr);
+        if (has_next) fetch_alm<SPIN>(P, m, lt + LEG_TL + tid, base, roff, almE, almB, layout, fl, flB, ne, nb, nr);
         const double2* sE = sEb[cur];
         const double2* sB = sBb[cur];
         const double2* sR = sRb[cur];
@@ -315,23 +332,23 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
     // spin 0: north = S + A, south = +-(S - A); spin 2: combine the lambda^+- sums; the south sign follows the
     // parity of the first l
     const double sg = ((l0 + m) & 1) ? -1.0 : 1.0;
-    const int64_t nm = L + 1;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
         const int p = chunk + j * LEG_NT + tid;
         if (p >= P.npair) continue;
         const int rn = p, rs = P.nring - 1 - p;
         const SynthAcc<SPIN>& a = acc[j];
+        const int64_t in = fm_index<SH>(P, 0, rn, m, mk), is = fm_index<SH>(P, 0, rs, m, mk);
         if (SPIN == 0) {
-            Fm[(int64_t)rn * nm + m] = make_double2(a.sqr + a.aqr, a.sqi + a.aqi);
-            if (rs != rn) Fm[(int64_t)rs * nm + m] = make_double2(sg * (a.sqr - a.aqr), sg * (a.sqi - a.aqi));
+            Fm[in] = make_double2(a.sqr + a.aqr, a.sqi + a.aqi);
+            if (rs != rn) Fm[is] = make_double2(sg * (a.sqr - a.aqr), sg * (a.sqi - a.aqi));
         } else {
-            double2* Fu = Fm + (int64_t)P.nring * nm;
-            Fm[(int64_t)rn * nm + m] = make_double2(a.sqr + a.sqi, a.sur + a.sui);
-            Fu[(int64_t)rn * nm + m] = make_double2(a.sur - a.sui, a.sqi - a.sqr);
+            const int64_t cs = SH ? (int64_t)P.sh.RL * P.sh.ML : (int64_t)P.nring * (L + 1);  // component stride
+            Fm[in] = make_double2(a.sqr + a.sqi, a.sur + a.sui);
+            Fm[in + cs] = make_double2(a.sur - a.sui, a.sqi - a.sqr);
             if (rs != rn) {
-                Fm[(int64_t)rs * nm + m] = make_double2(sg * (a.aqr + a.aqi), sg * (a.aur + a.aui));
-                Fu[(int64_t)rs * nm + m] = make_double2(sg * (a.aur - a.aui), sg * (a.aqi - a.aqr));
+                Fm[is] = make_double2(sg * (a.aqr + a.aqi), sg * (a.aur + a.aui));
+                Fm[is + cs] = make_double2(sg * (a.aur - a.aui), sg * (a.aqi - a.aqr));
             }
         }
     }
@@ -412,7 +429,7 @@ __device__ __forceinline__ double warp_fold(double* v, int lane)
 #ifndef LEG_MINB_A
 #define LEG_MINB_A 1
 #endif
-template <int SPIN, int R>
+template <int SPIN, int R, bool SH>
 __global__ void __launch_bounds__(LEG_NT, LEG_MINB_A)
 leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ partial, const int* __restrict__ skip)
 {
@@ -421,12 +438,14 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
     constexpr int NVAL = 2 * NV;       // values reduced per pair of l
     __shared__ double2 sR[LEG_TL];
     __shared__ double sPart[LEG_NW][LEG_TL * NV];
-    const int L = P.lmax, m = blockIdx.y, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int L = P.lmax, mk = blockIdx.y, m = SH ? P.sh.mlist[mk] : mk, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int l0 = m > SPIN ? m : SPIN;
     const int64_t base = (int64_t)m * (2 * L + 1 - m) / 2;
+    // first entry (l = lt) of this block's partial sums is pbase + lt
+    const int64_t pbase = SH ? (int64_t)blockIdx.x * P.sh.nalm_loc + P.sh.cbase[mk] - m : (int64_t)blockIdx.x * P.nalm + base;
     const int chunk = blockIdx.x * (LEG_NT * R);
     const bool odd0 = (l0 + m) & 1;
-    const int64_t nm = L + 1;
+    const int64_t cs = SH ? (int64_t)P.sh.RL * P.sh.ML : (int64_t)P.nring * (L + 1);  // component stride
 
     RingState<SPIN> st[R];
     AnalIn<SPIN> G[R];
@@ -443,14 +462,14 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
             any_act = true;
             const int rn = p, rs = P.nring - 1 - p;
             const double2 z = make_double2(0.0, 0.0);
-            const double2 qn = Fm[(int64_t)rn * nm + m], qs = (rs != rn) ? Fm[(int64_t)rs * nm + m] : z;
+            const int64_t in = fm_index<SH>(P, 0, rn, m, mk), is = fm_index<SH>(P, 0, rs, m, mk);
+            const double2 qn = Fm[in], qs = (rs != rn) ? Fm[is] : z;
             if (SPIN == 0) {
                 const double2 sy = make_double2(qn.x + qs.x, qn.y + qs.y), an = make_double2(qn.x - qs.x, qn.y - qs.y);
                 G[j].q1r = odd0 ? an.x : sy.x; G[j].q1i = odd0 ? an.y : sy.y;
                 G[j].q2r = odd0 ? sy.x : an.x; G[j].q2i = odd0 ? sy.y : an.y;
             } else {
-                const double2* Fu = Fm + (int64_t)P.nring * nm;
-                const double2 un = Fu[(int64_t)rn * nm + m], us = (rs != rn) ? Fu[(int64_t)rs * nm + m] : z;
+                const double2 un = Fm[in + cs], us = (rs != rn) ? Fm[is + cs] : z;
                 const double sg = odd0 ? -1.0 : 1.0;
                 G[j].q1r = qn.x - un.y; G[j].q1i = qn.x + un.y; G[j].q2r = qn.y + un.x; G[j].q2i = qn.y - un.x;
                 G[j].u1r = sg * (qs.x - us.y); G[j].u1i = sg * (qs.x + us.y);
@@ -537,29 +556,31 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
             double s = 0.0;
 #pragma unroll
             for (int ww = 0; ww < LEG_NW; ++ww) s += sPart[ww][i];
-            partial[((int64_t)blockIdx.x * P.nalm + base + lt) * NV + i] = s;
+            partial[(pbase + lt) * NV + i] = s;
         }
     }
 }
 
 // Combine the per-chunk partials: alm = post(l,m) * sum_chunks, converted to the requested layout.
-template <int SPIN>
+template <int SPIN, bool SH>
 __global__ void leg_finish_kernel(PlanDev P, const double* __restrict__ partial, int nchunk, double* __restrict__ almE,
                                   double* __restrict__ almB, int layout, const double* __restrict__ fl, double scale,
                                   int accumulate, const int* __restrict__ skip)
 {
     if (skip && *skip) return;
     constexpr int NV = SPIN ? 4 : 2;
-    const int L = P.lmax, m = blockIdx.y;
+    const int L = P.lmax, mk = blockIdx.y, m = SH ? P.sh.mlist[mk] : mk;
     const int l = m + blockIdx.x * blockDim.x + threadIdx.x;
     if (l > L) return;
-    const int64_t id = (int64_t)m * (2 * L + 1 - m) / 2 + l;
+    const int64_t base = (int64_t)m * (2 * L + 1 - m) / 2, id = base + l;
+    const int64_t pid = SH ? P.sh.cbase[mk] + (l - m) : id, pn = SH ? P.sh.nalm_loc : P.nalm;
+    const int64_t roff = real_off<SH>(P, m, mk, base);
     double v[NV];
 #pragma unroll
     for (int c = 0; c < NV; ++c) v[c] = 0.0;
     if (l >= SPIN) {
         for (int k = 0; k < nchunk; ++k) {
-            const double* q = partial + ((int64_t)k * P.nalm + id) * NV;
+            const double* q = partial + ((int64_t)k * pn + pid) * NV;
 #pragma unroll
             for (int c = 0; c < NV; ++c) v[c] += q[c];
         }
@@ -585,10 +606,10 @@ __global__ void leg_finish_kernel(PlanDev P, const double* __restrict__ partial,
             B[id] = b;
         }
     } else if (m == 0) {
-        almE[l] = accumulate ? almE[l] + v[0] : v[0];
-        if (SPIN) almB[l] = accumulate ? almB[l] + v[2] : v[2];
+        almE[roff + l] = accumulate ? almE[roff + l] + v[0] : v[0];
+        if (SPIN) almB[roff + l] = accumulate ? almB[roff + l] + v[2] : v[2];
     } else {
-        const int64_t off = 2 * id - (L + 1);
+        const int64_t off = roff + 2 * l;
         almE[off] = accumulate ? almE[off] + v[0] : v[0];
         almE[off + 1] = accumulate ? almE[off + 1] + v[1] : v[1];
         if (SPIN) {
@@ -602,29 +623,57 @@ __global__ void leg_finish_kernel(PlanDev P, const double* __restrict__ partial,
 int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, int layout, const double* fl,
                  cudaStream_t st, const int* skip, const double* flB)
 {
-    dim3 grid((p->d.npair + LEG_NT * LEG_R - 1) / (LEG_NT * LEG_R), p->d.lmax + 1);
-    if (spin == 0) leg_synth_kernel<0, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip);
-    else leg_synth_kernel<2, LEG_R><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip);
+    const bool sh = p->world > 1;
+    if (sh && layout != GS_ALM_REAL) { gs_set_error("sharded plans take the (local) real alm layout only"); return GS_E_BADARG; }
+    dim3 grid((p->d.npair + LEG_NT * LEG_R - 1) / (LEG_NT * LEG_R), sh ? p->d.sh.nm_loc : p->d.lmax + 1);
+    if (!sh) {
+        if (spin == 0) leg_synth_kernel<0, LEG_R, false><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip);
+        else leg_synth_kernel<2, LEG_R, false><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip);
+    } else {
+        if (spin == 0) leg_synth_kernel<0, LEG_R, true><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip);
+        else leg_synth_kernel<2, LEG_R, true><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip);
+    }
     GS_CHECK_LAUNCH();
     g_gs_launches += 1;
+    // m-sharded -> ring-sharded: the ring stage reads p->Fx
+    if (sh) return gs_shard_exchange(p, p->Fm, p->Fx, st);
     return GS_OK;
 }
 
 int gs_leg_anal(gs_plan* p, int spin, double* almE, double* almB, int layout, const double* fl, double scale,
                 int accumulate, cudaStream_t st, const int* skip)
 {
+    const bool sh = p->world > 1;
+    if (sh && layout != GS_ALM_REAL) { gs_set_error("sharded plans take the (local) real alm layout only"); return GS_E_BADARG; }
     const int nchunk = (p->d.npair + LEG_NT * LEG_RA - 1) / (LEG_NT * LEG_RA);
     if (nchunk > p->anal_chunks) { gs_set_error("gs_leg_anal: workspace too small"); return GS_E_BADARG; }
-    dim3 grid(nchunk, p->d.lmax + 1);
-    dim3 fgrid((p->d.lmax + 256) / 256, p->d.lmax + 1);
-    if (spin == 0) {
-        leg_anal_kernel<0, LEG_RA><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip);
-        GS_CHECK_LAUNCH();
-        leg_finish_kernel<0><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip);
+    const int nmy = sh ? p->d.sh.nm_loc : p->d.lmax + 1;
+    dim3 grid(nchunk, nmy);
+    dim3 fgrid((p->d.lmax + 256) / 256, nmy);
+    if (sh) {  // ring-sharded (p->Fx, written by the ring analysis) -> m-sharded
+        int rc = gs_shard_exchange(p, p->Fx, p->Fm, st);
+        if (rc) return rc;
+    }
+    if (!sh) {
+        if (spin == 0) {
+            leg_anal_kernel<0, LEG_RA, false><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip);
+            GS_CHECK_LAUNCH();
+            leg_finish_kernel<0, false><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip);
+        } else {
+            leg_anal_kernel<2, LEG_RA, false><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip);
+            GS_CHECK_LAUNCH();
+            leg_finish_kernel<2, false><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip);
+        }
     } else {
-        leg_anal_kernel<2, LEG_RA><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip);
-        GS_CHECK_LAUNCH();
-        leg_finish_kernel<2><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip);
+        if (spin == 0) {
+            leg_anal_kernel<0, LEG_RA, true><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip);
+            GS_CHECK_LAUNCH();
+            leg_finish_kernel<0, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip);
+        } else {
+            leg_anal_kernel<2, LEG_RA, true><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip);
+            GS_CHECK_LAUNCH();
+            leg_finish_kernel<2, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip);
+        }
     }
     GS_CHECK_LAUNCH();
     g_gs_launches += 2;

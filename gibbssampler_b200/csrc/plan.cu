@@ -205,12 +205,15 @@ static int build_tables(gs_plan* p)
     return GS_OK;
 }
 
-extern "C" int gs_plan_create(gs_plan** out, int nside, int lmax, int device)
+static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int rank, int world, const char* nccl_id,
+                            void* lgroup = nullptr)
 {
     if (!out) { gs_set_error("gs_plan_create: null output"); return GS_E_BADARG; }
     *out = nullptr;
     GS_REQUIRE(nside >= 1 && nside <= 8192, "nside out of range [1, 8192]");
     GS_REQUIRE(lmax >= 2 && lmax <= 4 * nside, "lmax must satisfy 2 <= lmax <= 4 nside");
+    GS_REQUIRE(world >= 1 && rank >= 0 && rank < world, "need 0 <= rank < world");
+    GS_REQUIRE(world <= 2 * nside && world <= (lmax + 2) / 2, "more ranks than ring pairs or m pairs");
     if (device >= 0) GS_CHECK_CUDA(cudaSetDevice(device));
     int dev = 0;
     GS_CHECK_CUDA(cudaGetDevice(&dev));
@@ -220,17 +223,33 @@ extern "C" int gs_plan_create(gs_plan** out, int nside, int lmax, int device)
     p->d.nside = nside;
     p->d.lmax = lmax;
     p->jobs0 = p->jobs2 = nullptr;
+    p->world = world;
+    p->rank = rank;
+    p->comm = nullptr;
+    p->lgroup = lgroup;
+    p->Fx = nullptr;
+    p->red_loc = nullptr;
+    p->d.sh.world = 1;
     int rc = build_tables(p);
+    const int64_t nm = lmax + 1;
+    p->nreal_loc = nm * nm;
+    p->npix_loc = p->d.npix;
+    if (rc == GS_OK && world > 1) rc = gs_shard_build(p, rank, world, nccl_id);
     if (rc == GS_OK) rc = gs_ring_setup(p);
     if (rc == GS_OK) {
-        const int64_t nm = lmax + 1;
-        rc = dev_alloc(p, (size_t)2 * p->d.nring * nm, &p->Fm);
+        const size_t nfm = world > 1 ? (size_t)world * 2 * p->d.sh.RL * p->d.sh.ML : (size_t)2 * p->d.nring * nm;
+        rc = dev_alloc(p, nfm, &p->Fm);
+        if (rc == GS_OK && world > 1) rc = dev_alloc(p, nfm, &p->Fx);
+        // the padding entries of the spectra buffers are exchanged but never read; keep them finite
+        if (rc == GS_OK) cudaMemset(p->Fm, 0, nfm * sizeof(double2));
+        if (rc == GS_OK && world > 1) cudaMemset(p->Fx, 0, nfm * sizeof(double2));
         // analysis: ring pairs are split in chunks of >= 128 per block (see legendre.cu)
         p->anal_chunks = (p->d.npair + 127) / 128;
-        if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->anal_chunks * p->d.nalm * 4, &p->partial);
-        if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->d.npix, &p->mapQ_tmp);
-        if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->d.npix, &p->mapU_tmp);
-        const size_t nre = (size_t)nm * nm;  // big enough for either layout
+        const size_t nalm_part = world > 1 ? (size_t)p->d.sh.nalm_loc : (size_t)p->d.nalm;
+        if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->anal_chunks * nalm_part * 4, &p->partial);
+        if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->npix_loc, &p->mapQ_tmp);
+        if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->npix_loc, &p->mapU_tmp);
+        const size_t nre = (size_t)p->nreal_loc;  // big enough for either layout
         if (rc == GS_OK) rc = dev_alloc(p, nre, &p->almE_tmp);
         if (rc == GS_OK) rc = dev_alloc(p, nre, &p->almB_tmp);
         if (rc == GS_OK) rc = dev_alloc(p, nre, &p->almE_tmp2);
@@ -245,9 +264,28 @@ extern "C" int gs_plan_create(gs_plan** out, int nside, int lmax, int device)
     return GS_OK;
 }
 
+extern "C" int gs_plan_create(gs_plan** out, int nside, int lmax, int device)
+{
+    return plan_create_impl(out, nside, lmax, device, 0, 1, nullptr);
+}
+
+extern "C" int gs_plan_create_sharded(gs_plan** out, int nside, int lmax, int device, int rank, int world,
+                                      const char* nccl_id128_host)
+{
+    return plan_create_impl(out, nside, lmax, device, rank, world, nccl_id128_host);
+}
+
+extern "C" int gs_plan_create_sharded_local(gs_plan** out, int nside, int lmax, int device, int rank, int world,
+                                            void* local_group)
+{
+    if (!local_group) { gs_set_error("null local group"); return GS_E_BADARG; }
+    return plan_create_impl(out, nside, lmax, device, rank, world, nullptr, local_group);
+}
+
 extern "C" int gs_plan_destroy(gs_plan* p)
 {
     if (!p) return GS_OK;
+    gs_shard_free(p);
     for (void* d : p->owned) cudaFree(d);
     delete p;
     return GS_OK;

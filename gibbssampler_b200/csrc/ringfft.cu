@@ -231,6 +231,20 @@ __device__ __forceinline__ double2 ring_phase(const PlanDev& P, int ring, int m)
     return make_double2(c, s);
 }
 
+// Position of F_m(ring) in the ring-spectra buffer as seen from the ring-sharded side (see ShardDev).
+template <bool SH>
+__device__ __forceinline__ int64_t fm_ring_index(const PlanDev& P, int comp, int ring, int m)
+{
+    if (SH) return (((int64_t)P.sh.m_owner[m] * 2 + comp) * P.sh.RL + P.sh.ring_loc[ring]) * P.sh.ML + P.sh.m_loc[m];
+    return ((int64_t)comp * P.nring + ring) * (P.lmax + 1) + m;
+}
+template <bool SH>
+__device__ __forceinline__ int64_t ring_first_pixel(const PlanDev& P, int ring)
+{
+    return SH ? P.sh.ring_start_loc[ring] : P.ring_start[ring];
+}
+
+template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
 ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __restrict__ Fm, double* __restrict__ mapQ,
                   double* __restrict__ mapU, const int* __restrict__ skip)
@@ -256,14 +270,16 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __
         const int ring = comp ? job.ringB : job.ringA;
         if (comp) __syncthreads();
         if (ring >= 0) {
-            const double2* F = Fm + ((int64_t)(comp ? job.compB : job.compA) * P.nring + ring) * nm;
+            const int cc = comp ? job.compB : job.compA;
+            const double2* F = Fm + ((int64_t)cc * P.nring + ring) * nm;
             // e^{i m phi0} for m = tid, tid + 256, ...: one sincospi, then multiply by e^{i 256 phi0}
             const int pr = (comp && !same_phase) ? job.ringB : job.ringA;
             double2 ph = ring_phase(P, pr, threadIdx.x);
             const double2 step = ring_phase(P, pr, RF_NT);
             for (int m = threadIdx.x; m <= L; m += RF_NT) {
                 const double w = m ? 1.0 : 0.5;  // (2 - delta_m0) / 2
-                st[m] = cmul(F[m], make_double2(ph.x * w, ph.y * w));
+                const double2 f = SH ? Fm[fm_ring_index<true>(P, cc, ring, m)] : F[m];
+                st[m] = cmul(f, make_double2(ph.x * w, ph.y * w));
                 ph = cmul(ph, step);
             }
         }
@@ -289,8 +305,8 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __
         }
     }
     ring_idft(P, buf, twq, n, bsi);
-    double* oa = (job.compA ? mapU : mapQ) + P.ring_start[job.ringA];
-    double* ob = job.ringB >= 0 ? (job.compB ? mapU : mapQ) + P.ring_start[job.ringB] : nullptr;
+    double* oa = (job.compA ? mapU : mapQ) + ring_first_pixel<SH>(P, job.ringA);
+    double* ob = job.ringB >= 0 ? (job.compB ? mapU : mapQ) + ring_first_pixel<SH>(P, job.ringB) : nullptr;
     for (int j = threadIdx.x; j < n; j += RF_NT) {
         double2 z = buf[PADI(j)];
         if (bsi >= 0) z = cmul(z, __ldg(&chirp[j]));
@@ -299,6 +315,7 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __
     }
 }
 
+template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
 ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double* __restrict__ mapQ, const double* __restrict__ mapU,
                  const double* __restrict__ pixw, double2* __restrict__ Fm, const int* __restrict__ skip)
@@ -311,7 +328,7 @@ ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double* __re
     double2* twq = smem;
     double2* buf = twq + (P.tw_n >> 2) + 1;
     load_twq(P, twq);
-    const int64_t sa = P.ring_start[job.ringA], sb = job.ringB >= 0 ? P.ring_start[job.ringB] : 0;
+    const int64_t sa = ring_first_pixel<SH>(P, job.ringA), sb = job.ringB >= 0 ? ring_first_pixel<SH>(P, job.ringB) : 0;
     const double* ia = (job.compA ? mapU : mapQ) + sa;
     const double* ib = job.ringB >= 0 ? (job.compB ? mapU : mapQ) + sb : nullptr;
     const int lg = 31 - __clz(n);
@@ -346,8 +363,13 @@ ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double* __re
         const double2 xa = make_double2(0.5 * (z1.x + z2c.x), 0.5 * (z1.y + z2c.y));
         const double2 d = csub(z1, z2c);
         const double2 xb = make_double2(0.5 * d.y, -0.5 * d.x);
-        FA[m] = cmulc(xa, pa);
-        if (FB) FB[m] = cmulc(xb, pb);
+        if (SH) {
+            Fm[fm_ring_index<true>(P, job.compA, job.ringA, m)] = cmulc(xa, pa);
+            if (FB) Fm[fm_ring_index<true>(P, job.compB, job.ringB, m)] = cmulc(xb, pb);
+        } else {
+            FA[m] = cmulc(xa, pa);
+            if (FB) FB[m] = cmulc(xb, pb);
+        }
         pa = cmul(pa, stepa);
         pb = cmul(pb, stepb);
     }
@@ -403,8 +425,10 @@ int gs_ring_setup(gs_plan* p)
     p->d.bs_tab = (const double2*)d;
 
     GS_CHECK_CUDA(cudaFuncSetAttribute(bluestein_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    GS_CHECK_CUDA(cudaFuncSetAttribute(ring_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    GS_CHECK_CUDA(cudaFuncSetAttribute(ring_anal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GS_CHECK_CUDA(cudaFuncSetAttribute(ring_synth_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GS_CHECK_CUDA(cudaFuncSetAttribute(ring_anal_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GS_CHECK_CUDA(cudaFuncSetAttribute(ring_synth_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GS_CHECK_CUDA(cudaFuncSetAttribute(ring_anal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (!descs.empty()) {
         bluestein_setup_kernel<<<(int)descs.size(), RF_NT, p->ring_smem>>>(p->d, (double2*)d, (int)descs.size());
         GS_CHECK_LAUNCH();
@@ -412,15 +436,17 @@ int gs_ring_setup(gs_plan* p)
 
     // job lists, heaviest transforms first
     auto cost = [&](int ring) { int n = rn[ring]; return rbs[ring] < 0 ? n : 3 * descs[rbs[ring]].M; };
-    std::vector<RingJob> j2(nring), j0;
-    for (int r = 0; r < nring; ++r) j2[r] = RingJob{r, 0, r, 1};
-    for (int r = 0; r < npair; ++r) { int rs = nring - 1 - r; j0.push_back(RingJob{r, 0, rs != r ? rs : -1, 0}); }
+    // sharded plans transform only the rings of the owned ring pairs
+    auto owned = [&](int ring) { return p->world <= 1 || std::min(ring, nring - 1 - ring) % p->world == p->rank; };
+    std::vector<RingJob> j2, j0;
+    for (int r = 0; r < nring; ++r) if (owned(r)) j2.push_back(RingJob{r, 0, r, 1});
+    for (int r = 0; r < npair; ++r) { int rs = nring - 1 - r; if (owned(r)) j0.push_back(RingJob{r, 0, rs != r ? rs : -1, 0}); }
     std::stable_sort(j2.begin(), j2.end(), [&](const RingJob& a, const RingJob& b) { return cost(a.ringA) > cost(b.ringA); });
     std::stable_sort(j0.begin(), j0.end(), [&](const RingJob& a, const RingJob& b) { return cost(a.ringA) > cost(b.ringA); });
-    GS_CHECK_CUDA(cudaMalloc(&d, j2.size() * sizeof(RingJob))); p->owned.push_back(d);
+    GS_CHECK_CUDA(cudaMalloc(&d, std::max<size_t>(1, j2.size()) * sizeof(RingJob))); p->owned.push_back(d);
     GS_CHECK_CUDA(cudaMemcpy(d, j2.data(), j2.size() * sizeof(RingJob), cudaMemcpyHostToDevice));
     p->jobs2 = (RingJob*)d; p->njobs2 = (int)j2.size();
-    GS_CHECK_CUDA(cudaMalloc(&d, j0.size() * sizeof(RingJob))); p->owned.push_back(d);
+    GS_CHECK_CUDA(cudaMalloc(&d, std::max<size_t>(1, j0.size()) * sizeof(RingJob))); p->owned.push_back(d);
     GS_CHECK_CUDA(cudaMemcpy(d, j0.data(), j0.size() * sizeof(RingJob), cudaMemcpyHostToDevice));
     p->jobs0 = (RingJob*)d; p->njobs0 = (int)j0.size();
     return GS_OK;
@@ -428,9 +454,14 @@ int gs_ring_setup(gs_plan* p)
 
 int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st, const int* skip)
 {
-    if (spin == 0) ring_synth_kernel<<<p->njobs0, RF_NT, p->ring_smem, st>>>(p->d, p->jobs0, p->Fm, mapQ, mapQ, skip);
-    else ring_synth_kernel<<<p->njobs2, RF_NT, p->ring_smem, st>>>(p->d, p->jobs2, p->Fm, mapQ, mapU, skip);
-    GS_CHECK_LAUNCH();
+    const int nj = spin == 0 ? p->njobs0 : p->njobs2;
+    const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
+    double* mu = spin == 0 ? mapQ : mapU;
+    if (nj > 0) {
+        if (p->world > 1) ring_synth_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, p->Fx, mapQ, mu, skip);
+        else ring_synth_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, p->Fm, mapQ, mu, skip);
+        GS_CHECK_LAUNCH();
+    }
     g_gs_launches += 1;
     return GS_OK;
 }
@@ -438,9 +469,14 @@ int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t
 int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, const double* pixw, cudaStream_t st,
                  const int* skip)
 {
-    if (spin == 0) ring_anal_kernel<<<p->njobs0, RF_NT, p->ring_smem, st>>>(p->d, p->jobs0, mapQ, mapQ, pixw, p->Fm, skip);
-    else ring_anal_kernel<<<p->njobs2, RF_NT, p->ring_smem, st>>>(p->d, p->jobs2, mapQ, mapU, pixw, p->Fm, skip);
-    GS_CHECK_LAUNCH();
+    const int nj = spin == 0 ? p->njobs0 : p->njobs2;
+    const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
+    const double* mu = spin == 0 ? mapQ : mapU;
+    if (nj > 0) {
+        if (p->world > 1) ring_anal_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, mapQ, mu, pixw, p->Fx, skip);
+        else ring_anal_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, mapQ, mu, pixw, p->Fm, skip);
+        GS_CHECK_LAUNCH();
+    }
     g_gs_launches += 1;
     return GS_OK;
 }

@@ -29,6 +29,7 @@ struct PcgState {
 struct gs_pcg_ws {
     double *r[2], *p[2], *q[2], *invc[2], *pre[2];
     double* partials;  // SV_GRID * 2
+    double* red;       // sharded plans: local sums in, all-reduced sums out (NULL on one GPU)
     PcgState* state;
     PcgState* host_state;  // pinned
 };
@@ -97,6 +98,37 @@ __device__ __forceinline__ void pick(int64_t i, int64_t n, int& c, int64_t& j)
     j = c ? i - n : i;
 }
 
+// scalar updates that follow each reduction.  One GPU: run by the last block of the reducing kernel.
+// Sharded: that block stores its local sums in W.red, the host enqueues the all-reduce and then
+// pcg_scalar_kernel, so every rank applies the same update to the same numbers.
+__device__ __forceinline__ void fin_init(PcgState* s, double rr, double rz)
+{
+    s->rr = rr; s->d0 = rr; s->delta = rz; s->iter = 0;
+    s->done = (rr <= 0.0 || s->itermax <= 0) ? 1 : 0;
+}
+__device__ __forceinline__ void fin_apq(PcgState* s, double pq)
+{
+    s->pq = pq;
+    s->alpha = pq != 0.0 ? s->delta / pq : 0.0;
+}
+__device__ __forceinline__ void fin_update(PcgState* s, double rr, double rz)
+{
+    s->rr = rr; s->rz = rz;
+    s->beta = s->delta != 0.0 ? rz / s->delta : 0.0;
+    s->delta = rz;
+    s->iter += 1;
+    // qcinv cd_monitors.monitor_basic: stop when <r,r> <= eps^2 <r0,r0> or iter >= iter_max
+    if (rr <= s->eps2 * s->d0 || s->iter >= s->itermax) s->done = 1;
+}
+__global__ void pcg_scalar_kernel(gs_pcg_ws W, int stage)
+{
+    PcgState* s = W.state;
+    if (stage == 0) fin_init(s, W.red[0], W.red[1]);
+    else if (s->done) return;
+    else if (stage == 1) fin_apq(s, W.red[0]);
+    else fin_update(s, W.red[0], W.red[1]);
+}
+
 // r = b - q (q = Q x0, or q absent for x0 = 0), p = M r, delta = <r, M r>, d0 = rr = <r, r>
 __global__ void __launch_bounds__(SV_NT)
 pcg_init_kernel(gs_pcg_ws W, const double* bE, const double* bB, int have_q, int64_t n)
@@ -115,9 +147,8 @@ pcg_init_kernel(gs_pcg_ws W, const double* bE, const double* bB, int have_q, int
     }
     double tot[2];
     if (grid_reduce<2>(v, W.partials, &W.state->counter, tot) && threadIdx.x == 0) {
-        PcgState* s = W.state;
-        s->rr = tot[0]; s->d0 = tot[0]; s->delta = tot[1]; s->iter = 0;
-        s->done = (tot[0] <= 0.0 || s->itermax <= 0) ? 1 : 0;
+        if (W.red) { W.red[0] = tot[0]; W.red[1] = tot[1]; }
+        else fin_init(W.state, tot[0], tot[1]);
     }
 }
 
@@ -136,9 +167,8 @@ __global__ void __launch_bounds__(SV_NT) pcg_apq_kernel(gs_pcg_ws W, int64_t n)
     }
     double tot[1];
     if (grid_reduce<1>(v, W.partials, &W.state->counter, tot) && threadIdx.x == 0) {
-        PcgState* s = W.state;
-        s->pq = tot[0];
-        s->alpha = tot[0] != 0.0 ? s->delta / tot[0] : 0.0;
+        if (W.red) W.red[0] = tot[0];
+        else fin_apq(W.state, tot[0]);
     }
 }
 
@@ -160,13 +190,8 @@ __global__ void __launch_bounds__(SV_NT) pcg_update_kernel(gs_pcg_ws W, double* 
     }
     double tot[2];
     if (grid_reduce<2>(v, W.partials, &W.state->counter, tot) && threadIdx.x == 0) {
-        PcgState* s = W.state;
-        s->rr = tot[0]; s->rz = tot[1];
-        s->beta = s->delta != 0.0 ? tot[1] / s->delta : 0.0;
-        s->delta = tot[1];
-        s->iter += 1;
-        // qcinv cd_monitors.monitor_basic: stop when <r,r> <= eps^2 <r0,r0> or iter >= iter_max
-        if (tot[0] <= s->eps2 * s->d0 || s->iter >= s->itermax) s->done = 1;
+        if (W.red) { W.red[0] = tot[0]; W.red[1] = tot[1]; }
+        else fin_update(W.state, tot[0], tot[1]);
     }
 }
 
@@ -214,7 +239,8 @@ static gs_pcg_ws* get_ws(gs_plan* p)
     static thread_local std::vector<std::pair<gs_plan*, gs_pcg_ws*>> cache;
     for (auto& kv : cache) if (kv.first == p) return kv.second;
     gs_pcg_ws* w = new gs_pcg_ws();
-    const size_t n = (size_t)(p->d.lmax + 1) * (p->d.lmax + 1);
+    const size_t n = (size_t)p->nreal_loc;
+    w->red = p->world > 1 ? p->red_loc : nullptr;
     auto alloc = [&](double** q, size_t cnt) { void* d = nullptr; if (cudaMalloc(&d, cnt * sizeof(double)) != cudaSuccess) return false; p->owned.push_back(d); *q = (double*)d; return true; };
     bool ok = true;
     for (int c = 0; c < 2 && ok; ++c) ok = alloc(&w->r[c], n) && alloc(&w->p[c], n) && alloc(&w->q[c], n) && alloc(&w->invc[c], n) && alloc(&w->pre[c], n);
@@ -252,7 +278,7 @@ extern "C" int gs_cr_pcg_pol(gs_plan* p, const double* dl_EE, const double* dl_B
     gs_pcg_ws* w = get_ws(p);
     if (!w) return GS_E_NOMEM;
     const int L = p->d.lmax;
-    const int64_t n = (int64_t)(L + 1) * (L + 1);
+    const int64_t n = p->nreal_loc;
     if (check_every < 1) check_every = 8;
 
     // per-l C^-1 and preconditioner, expanded to the real layout
@@ -262,10 +288,11 @@ extern "C" int gs_cr_pcg_pol(gs_plan* p, const double* dl_EE, const double* dl_B
     precond_kernel<<<lb, 256, 0, st>>>(dl_BB, bl, ninv_sum_over_4pi, L, tmp_l + 2 * (L + 1), tmp_l + 3 * (L + 1));
     GS_CHECK_LAUNCH();
     int rc;
-    if ((rc = gs_launch_expand_per_l(tmp_l, L, 0, w->invc[0], st))) return rc;
-    if ((rc = gs_launch_expand_per_l(tmp_l + (L + 1), L, 0, w->pre[0], st))) return rc;
-    if ((rc = gs_launch_expand_per_l(tmp_l + 2 * (L + 1), L, 0, w->invc[1], st))) return rc;
-    if ((rc = gs_launch_expand_per_l(tmp_l + 3 * (L + 1), L, 0, w->pre[1], st))) return rc;
+    if ((rc = gs_plan_expand_per_l(p, tmp_l, 0, w->invc[0], st))) return rc;
+    if ((rc = gs_plan_expand_per_l(p, tmp_l + (L + 1), 0, w->pre[0], st))) return rc;
+    if ((rc = gs_plan_expand_per_l(p, tmp_l + 2 * (L + 1), 0, w->invc[1], st))) return rc;
+    if ((rc = gs_plan_expand_per_l(p, tmp_l + 3 * (L + 1), 0, w->pre[1], st))) return rc;
+    const bool dist = p->world > 1;
 
     PcgState h;
     memset(&h, 0, sizeof(h));
@@ -282,6 +309,10 @@ extern "C" int gs_cr_pcg_pol(gs_plan* p, const double* dl_EE, const double* dl_B
     }
     pcg_init_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, rhs_E, rhs_B, warm_start ? 1 : 0, n);
     GS_CHECK_LAUNCH();
+    if (dist) {
+        if ((rc = gs_shard_allreduce(p, w->red, 2, st))) return rc;
+        pcg_scalar_kernel<<<1, 1, 0, st>>>(*w, 0);
+    }
 
     const int* done = &w->state->done;
     int launched = 0;
@@ -290,7 +321,15 @@ extern "C" int gs_cr_pcg_pol(gs_plan* p, const double* dl_EE, const double* dl_B
         for (int k = 0; k < check_every && launched < itermax; ++k, ++launched) {
             if ((rc = apply_noise_op(p, w->p[0], w->p[1], bl, inv_noise, w->q[0], w->q[1], st, done))) return rc;
             pcg_apq_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, n);
+            if (dist) {
+                if ((rc = gs_shard_allreduce(p, w->red, 1, st))) return rc;
+                pcg_scalar_kernel<<<1, 1, 0, st>>>(*w, 1);
+            }
             pcg_update_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, x_E, x_B, n);
+            if (dist) {
+                if ((rc = gs_shard_allreduce(p, w->red, 2, st))) return rc;
+                pcg_scalar_kernel<<<1, 1, 0, st>>>(*w, 2);
+            }
             pcg_dir_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, n);
             GS_CHECK_LAUNCH();
             g_gs_launches += 3;
@@ -321,10 +360,10 @@ extern "C" int gs_cr_apply_q_pol(gs_plan* p, const double* dl_EE, const double* 
     gs_pcg_ws* w = get_ws(p);
     if (!w) return GS_E_NOMEM;
     const int L = p->d.lmax;
-    const int64_t n = (int64_t)(L + 1) * (L + 1);
+    const int64_t n = p->nreal_loc;
     int rc;
-    if ((rc = gs_launch_expand_per_l(dl_EE, L, 2, w->invc[0], st))) return rc;
-    if ((rc = gs_launch_expand_per_l(dl_BB, L, 2, w->invc[1], st))) return rc;
+    if ((rc = gs_plan_expand_per_l(p, dl_EE, 2, w->invc[0], st))) return rc;
+    if ((rc = gs_plan_expand_per_l(p, dl_BB, 2, w->invc[1], st))) return rc;
     if ((rc = apply_noise_op(p, x_E, x_B, bl, inv_noise, w->q[0], w->q[1], st, nullptr))) return rc;
     axy_kernel<<<SV_GRID, SV_NT, 0, st>>>(w->q[0], w->invc[0], x_E, y_E, n);
     axy_kernel<<<SV_GRID, SV_NT, 0, st>>>(w->q[1], w->invc[1], x_B, y_B, n);
@@ -352,14 +391,14 @@ extern "C" int gs_cr_rhs_pol(gs_plan* p, const double* dl_EE, const double* dl_B
     gs_pcg_ws* w = get_ws(p);
     if (!w) return GS_E_NOMEM;
     const int L = p->d.lmax;
-    const int64_t n = (int64_t)(L + 1) * (L + 1);
+    const int64_t n = p->nreal_loc;
     int rc;
     // fluctuation term 1: utils.adjoint_synthesis_hp (utils.py:79-111) = bl * (Npix/4pi) * map2alm(iter=3)
     if ((rc = gs_map2alm_spin2(p, xi_Q, xi_U, sqrt_inv_noise, fluct_iter, 0, bl, rhs_E, rhs_B, GS_ALM_REAL, stream))) return rc;
     const double resc = (double)p->d.npix / (4.0 * 3.14159265358979323846);
     // fluctuation term 2 and data term; use r[] / p[] of the PCG workspace as scratch
-    if ((rc = gs_launch_expand_per_l(dl_EE, L, 4, w->r[0], st))) return rc;
-    if ((rc = gs_launch_expand_per_l(dl_BB, L, 4, w->r[1], st))) return rc;
+    if ((rc = gs_plan_expand_per_l(p, dl_EE, 4, w->r[0], st))) return rc;
+    if ((rc = gs_plan_expand_per_l(p, dl_BB, 4, w->r[1], st))) return rc;
     const double* bdE = bdata_E;
     const double* bdB = bdata_B;
     if (!bdE) {

@@ -34,6 +34,7 @@ class Plan:
         self.npix = 12 * self.nside ** 2
         self.nalm = (self.lmax + 1) * (self.lmax + 2) // 2
         self.nreal = (self.lmax + 1) ** 2
+        self.npix_global, self.nreal_global = self.npix, self.nreal
 
     @classmethod
     def get(cls, nside, lmax, device=None):
@@ -50,6 +51,34 @@ class Plan:
                 self._h = C.c_void_p()
         except Exception:
             pass
+
+    # ------------------------------------------------------------------ single-GPU versions of the shard helpers
+    # (gibbssampler_b200.sharded.ShardedPlan overrides them; the sampler classes are written against these)
+    world, rank = 1, 0
+
+    def local_map(self, full):
+        return full
+
+    def local_alm(self, full_real):
+        return full_real
+
+    def gather_alm(self, local):
+        return local
+
+    def gather_map(self, local):
+        return local
+
+    def allreduce_sum(self, value):
+        return float(value)
+
+    def expand_per_l(self, x, mode=0):
+        from . import utils
+        return utils.expand_per_l(torch.as_tensor(x, dtype=torch.float64, device=self.device), mode)
+
+    def alm2cl(self, alm_real):
+        cl = torch.empty(self.lmax + 1, dtype=torch.float64, device=self.device)
+        check(_lib.lib().gs_alm2cl(_ptr(alm_real.contiguous()), GS_ALM_REAL, self.lmax, _ptr(cl), _stream()))
+        return cl
 
     # ------------------------------------------------------------------ helpers
     def _alm_in(self, a):

@@ -243,6 +243,46 @@ int gs_randu(double* out, int64_t n, uint64_t seed, uint64_t stream_id, void* st
 /* out[0] = sum(a[0..n)) in a fixed order; scratch: 592 doubles. */
 int gs_sum(const double* a, int64_t n, double* scratch, double* out, void* stream);
 
+/* ---- m-sharded transforms over the GPUs of one node (BASELINE config #4) --------------
+ * The reference has no multi-GPU transform (one chain per SLURM task, job-script.sh:6); this is the
+ * single-chain strategy for NSIDE >= 1024.  Rank r of `world` owns the m pairs {j, L-j} with j mod world = r
+ * (Legendre stage) and the ring pairs p with p mod world = r (ring-FFT / pixel stage); one NCCL all-to-all
+ * per transform moves the ring spectra between the two partitions.  On a sharded plan every plan-based
+ * entry point above (gs_alm2map_spin2, gs_map2alm_spin2, gs_cr_rhs_pol, gs_cr_pcg_pol, gs_cr_apply_q_pol, ...)
+ * takes LOCAL shards: alm in the local real layout (owned m ascending; m = 0: a_l0, l = 0..L; m > 0:
+ * (sqrt2 Re, sqrt2 Im) for l = m..L; layout flag GS_ALM_REAL), maps as the owned rings in ascending RING
+ * order; per-l arrays (dl, bl, fl) are replicated.  Scalars that are sums over pixels
+ * (ninv_sum_over_4pi) must be global.  All ranks must make the same calls in the same order. */
+/* 128-byte NCCL unique id for a new group: call on one rank, broadcast, pass to gs_plan_create_sharded. */
+int gs_nccl_unique_id(char* id128_host);
+/* Collective over the `world` ranks (each on its own device).  world == 1 is gs_plan_create. */
+int gs_plan_create_sharded(gs_plan** plan, int nside, int lmax, int device, int rank, int world,
+                           const char* nccl_id128_host);
+/* In-process group for verification on ONE GPU: `world` sharded plans on the same device, each driven by
+ * its own host thread and stream; the all-to-all / all-reduce are host barriers + device copies. */
+int gs_local_group_create(void** group, int world);
+int gs_local_group_destroy(void* group);
+int gs_plan_create_sharded_local(gs_plan** plan, int nside, int lmax, int device, int rank, int world,
+                                 void* local_group);
+int gs_plan_world(const gs_plan* plan);
+int gs_plan_rank(const gs_plan* plan);
+int64_t gs_plan_nreal_local(const gs_plan* plan);  /* doubles in a local alm shard */
+int64_t gs_plan_npix_local(const gs_plan* plan);   /* pixels in a local map shard */
+/* The partition as pure host functions (no GPU): owned m / owned rings (0-based, ascending) of `rank`;
+ * out may be NULL to query the count, which is the return value (negative = error). */
+int gs_shard_partition_m(int lmax, int world, int rank, int* out);
+int gs_shard_partition_rings(int nside, int world, int rank, int* out);
+/* Global index (reference real layout, utils.py:49-76 / RING pixel number) of every entry of the local
+ * alm / map shard; out may be NULL to query the length, which is the return value. */
+int64_t gs_shard_real_index(int lmax, int world, int rank, int64_t* out);
+int64_t gs_shard_pixel_index(int nside, int world, int rank, int64_t* out);
+/* gs_expand_per_l over the plan's local real layout. */
+int gs_shard_expand_per_l(gs_plan* plan, const double* x, int mode, double* out, void* stream);
+/* hp.alm2cl of a sharded real-layout alm: local sums, all-reduce, / (2l+1); cl (L+1) on every rank. */
+int gs_shard_alm2cl(gs_plan* plan, const double* alm_local, double* cl, void* stream);
+/* In-place sum over the ranks of the plan of n device doubles. */
+int gs_shard_allreduce_sum(gs_plan* plan, double* buf, int n, void* stream);
+
 /* ---- measurement helpers used by bench.py ------------------------------------------------ */
 /* Number of kernels this library has launched so far in the SHT stages and PCG vector updates. */
 long long gs_launch_count(void);
