@@ -178,6 +178,116 @@ def workload_config(args, n_pcg):
                          "recurrence/alm vectors (126 MB L2)"}
 
 
+def run_sharded(args):
+    """BASELINE config #4: a single CenteredGibbs chain with the m-sharded SHT (NCCL all-to-all ring<->m transpose)
+    over all ranks; strong scaling, value = iterations/s of that one chain."""
+    import torch
+    import torch.distributed as dist
+    from gibbssampler_b200 import _dev, _lib, utils
+    from gibbssampler_b200.CenteredGibbs import PolarizedCenteredClsSampler, PolarizedCenteredConstrainedRealization
+    from gibbssampler_b200.sharded import ShardedPlan
+    from gibbssampler_b200.sht import Plan
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    nside, lmax = args.nside, args.lmax
+    npix, nre = 12 * nside * nside, (lmax + 1) ** 2
+    L = _lib.lib()
+    plan = ShardedPlan(nside, lmax) if world > 1 else Plan.get(nside, lmax)
+    dlE, dlB = fiducial(lmax)
+    fwhm = 0.5 * (512 / nside)
+    bl = _dev.gauss_beam(np.radians(fwhm), lmax)
+    noise_var = 0.04 * npix / 786432.0
+    mask = make_mask(nside)
+    # synthetic sky generated shard-locally with the sharded transform (same construction as the chains mode)
+    data_rng = _dev.Rng("philox", seed=1234 + 17 * rank)
+    sE = data_rng.normal(plan.nreal) * plan.expand_per_l(_dev.f64(dlE), 3)
+    sB = data_rng.normal(plan.nreal) * plan.expand_per_l(_dev.f64(dlB), 3)
+    q, u = plan.alm2map_spin2(sE, sB, fl=_dev.f64(bl))
+    mask_loc = plan.local_map(_dev.f64(mask))
+    dQ = (q + data_rng.normal(plan.npix) * np.sqrt(noise_var)) * mask_loc
+    dU = (u + data_rng.normal(plan.npix) * np.sqrt(noise_var)) * mask_loc
+    bins = bins_for(lmax)
+    bl_map = plan.expand_per_l(_dev.f64(bl), 0)
+    cr = PolarizedCenteredConstrainedRealization({"Q": dQ, "U": dU}, noise_var * 1e4, noise_var, bl_map, lmax, npix, fwhm,
+                                                 mask=mask, rng="philox", seed=5000 + rank, plan=plan)
+    cls = PolarizedCenteredClsSampler({"Q": dQ, "U": dU}, lmax, nside, bins, bl_map, noise_var, rng="philox", seed=99,
+                                      plan=plan if world > 1 else None)
+    state = {"binned": {pol: _dev.f64(np.array([dl[bins[pol][i]:bins[pol][i + 1]].mean() for i in range(len(bins[pol]) - 1)]))
+                        for pol, dl in (("EE", dlE), ("BB", dlB))}}
+    pcg_its = []
+
+    def step():
+        b = state["binned"]
+        dls = {"EE": utils.unfold_bins(b["EE"], bins["EE"]), "BB": utils.unfold_bins(b["BB"], bins["BB"])}
+        sky, _ = cr.sample_mask(dls)
+        pcg_its.append(cr.last_pcg_iterations)
+        state["binned"] = cls.sample(sky)
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = L.gs_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.barrier()
+    ms_total = reduce_max_ms(ms, world)
+    launches = int(L.gs_launch_count() - launches0)
+    clocks.stop_flag = True
+    clocks.join(timeout=2)
+    # stage timing of one mat-vec (the all-to-alls are inside the Legendre-stage calls on sharded plans)
+    x_e, x_b = data_rng.normal(plan.nreal), data_rng.normal(plan.nreal)
+    y_e, y_b = torch.empty_like(x_e), torch.empty_like(x_b)
+    ms4 = (C.c_float * 4)()
+    for nrep in (3, 20):
+        _lib.check(L.gs_profile_matvec(plan._h, _dev.ptr(x_e), _dev.ptr(x_b), _dev.ptr(cr.bl_gauss_d), _dev.ptr(cr.inv_noise_pol),
+                                       _dev.ptr(y_e), _dev.ptr(y_b), nrep, ms4, _dev.stream()))
+    st = torch.tensor(list(ms4), device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(st, op=dist.ReduceOp.MAX)
+    st = [float(x) for x in st.tolist()]
+    its = pcg_its[args.warmup:]
+    n_pcg = int(round(float(np.mean(its)))) if its else 0
+    nring = 4 * nside - 1
+    n_lm2 = sum(lmax - max(m, 2) + 1 for m in range(lmax + 1))
+    f2 = 26.0 * ((nring + 1) // 2) * n_lm2
+    exch_bytes = 2 * 16.0 * nring * (lmax + 1) * (world - 1) / max(world, 1) / max(world, 1)  # sent per GPU and transform
+    if rank == 0:
+        line = {
+            "metric": "gibbs_iters_per_s", "value": args.steps / (ms_total * 1e-3), "unit": "it/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "CenteredGibbs polarised masked sky, ONE chain, m-sharded SHT with NCCL all-to-all ring<->m transpose "
+                                   "(PCG eps 1e-5, diag_cl precond) + inverse-gamma C_l draw", "nside": nside, "lmax": lmax, "fsky": 0.8,
+                       "beam_fwhm_deg": fwhm, "pcg_iterations": n_pcg, "parallelism": "m-shard x%d" % world,
+                       "l2_policy": "inputs larger than L2"},
+            "gpu_launches": launches, "sht_pair_ms": sum(st), "sht_pairs_per_s": 1e3 / sum(st),
+            "stage_ms": {"leg_synth+a2a": st[0], "ring_synth": st[1], "ring_anal": st[2], "a2a+leg_anal": st[3]},
+            "legendre_tflops_all_gpus": 2 * f2 / ((st[0] + st[3]) * 1e-3) * 1e-12,
+            "a2a_bytes_sent_per_gpu_per_transform": exch_bytes,
+            "clocks": clocks.summary(), "pcg_iterations_per_step": its,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -188,9 +298,14 @@ def main():
     ap.add_argument("--lmax", type=int, default=1024)
     ap.add_argument("--pcg-iters", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="chains", choices=["chains", "sharded"],
+                    help="chains: one independent chain per GPU (weak scaling, the default and the driver's contract); "
+                         "sharded: ONE chain whose SHTs are m-sharded over the GPUs (BASELINE config #4, strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "sharded":
+        return run_sharded(args)
 
     import torch
     import torch.distributed as dist

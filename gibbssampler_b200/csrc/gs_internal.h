@@ -72,6 +72,15 @@ struct ShardDev {
     const int* l_of_loc;     // [nreal_loc] multipole of every entry of the local real layout
 };
 
+// A ring too long for one CTA's shared memory (nside >= 2048) is transformed as 4 interleaved
+// sub-transforms of length n/4 (one CTA each, decimation by 4) that meet in a global scratch buffer.
+struct SplitJob {
+    int ringA, compA, ringB, compB;
+    int bs2;       // Bluestein descriptor of the sub-length n/4, or -1 (power of two)
+    int pad;
+    int64_t off;   // offset (double2) of this job's n scratch entries
+};
+
 // Device-side view of a plan (plain pointers; passed by value to kernels).
 struct PlanDev {
     int nside, lmax, nring, npair;
@@ -122,6 +131,12 @@ struct gs_plan {
     int njobs2;
     RingJob* jobs0;  // spin 0: (north, south) ring of each pair
     int njobs0;
+    SplitJob* sjobs2;   // rings of the spin-2 / spin-0 lists that take the split path (empty below nside 2048)
+    int nsjobs2;
+    SplitJob* sjobs0;
+    int nsjobs0;
+    double2* ring_scratch;
+    size_t split_smem;
     // workspace
     double2* Fm;        // [2][nring][lmax+1] ring spectra
     double* partial;    // analysis partial sums [nchunk][nalm][4]

@@ -223,6 +223,9 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
     p->d.nside = nside;
     p->d.lmax = lmax;
     p->jobs0 = p->jobs2 = nullptr;
+    p->sjobs0 = p->sjobs2 = nullptr;
+    p->nsjobs0 = p->nsjobs2 = 0;
+    p->ring_scratch = nullptr;
     p->world = world;
     p->rank = rank;
     p->comm = nullptr;

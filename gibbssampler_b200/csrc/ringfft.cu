@@ -12,6 +12,7 @@
 // the same kernel: DIF forward -> pointwise product with a precomputed table stored in DIF
 // (bit-reversed) order -> DIT inverse, so no permutation pass is ever executed.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <map>
@@ -375,34 +376,222 @@ ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double* __re
     }
 }
 
+// ------------------------------------------------------------------ split path (rings longer than one CTA can hold)
+// n = 4 n2.  Synthesis (z_j = sum_k Z_k e^{+2 pi i jk/n}, j = j2 + n2 q, k = 4a + b):
+//   z_{j2 + n2 q} = sum_b i^{qb} e^{2 pi i j2 b/n} Y_b[j2],   Y_b[j2] = sum_a Z_{4a+b} e^{2 pi i j2 a/n2}
+// CTA (job, b) computes Y_b with the shared-memory transform of length n2 and stores it in the scratch;
+// ring_synth_combine_kernel applies the twiddles and the radix-4 butterfly and writes the pixels.
+// Analysis is the transpose: CTA (job, b) loads v_b[j2] = e^{2 pi i j2 b/n} sum_q i^{qb} c_{j2 + n2 q}, transforms
+// it to C_{4a+b}, and ring_anal_finish_kernel unpacks the two real sequences into F_m.
+template <bool SH>
+__device__ __forceinline__ double2 fold_spectrum(const PlanDev& P, const double2* __restrict__ Fm, int comp, int ring, int k, int n)
+{  // X_k = G_k + conj G_{n-k},  G_k = sum_{m = k mod n} w_m F_m e^{i m phi0}
+    const int L = P.lmax, kk = (n - k) % n;
+    double2 g = make_double2(0.0, 0.0), h = g;
+    for (int m = k; m <= L; m += n) {
+        const double w = m ? 1.0 : 0.5;
+        const double2 ph = ring_phase(P, ring, m);
+        g = cadd(g, cmul(Fm[fm_ring_index<SH>(P, comp, ring, m)], make_double2(ph.x * w, ph.y * w)));
+    }
+    for (int m = kk; m <= L; m += n) {
+        const double w = m ? 1.0 : 0.5;
+        const double2 ph = ring_phase(P, ring, m);
+        h = cadd(h, cmul(Fm[fm_ring_index<SH>(P, comp, ring, m)], make_double2(ph.x * w, ph.y * w)));
+    }
+    return make_double2(g.x + h.x, g.y - h.y);
+}
+
+__device__ __forceinline__ double2 mul_ipow(double2 v, int p)
+{  // v * i^p
+    p &= 3;
+    return p == 0 ? v : p == 1 ? make_double2(-v.y, v.x) : p == 2 ? make_double2(-v.x, -v.y) : make_double2(v.y, -v.x);
+}
+
+__device__ __forceinline__ double2 unit_root(int num, int n)
+{  // exp(2 pi i num / n), 0 <= num
+    const int r = (int)((2LL * num) % (2LL * n));
+    double s, c;
+    sincospi((double)r / (double)n, &s, &c);
+    return make_double2(c, s);
+}
+
+template <bool SH>
+__global__ void __launch_bounds__(RF_NT, 2)
+ring_synth_split_kernel(PlanDev P, const SplitJob* __restrict__ jobs, const double2* __restrict__ Fm, double2* __restrict__ scratch,
+                        const int* __restrict__ skip)
+{
+    if (skip && *skip) return;
+    extern __shared__ double2 smem[];
+    const SplitJob job = jobs[blockIdx.x >> 2];
+    const int b = blockIdx.x & 3;
+    const int n = P.ring_nphi[job.ringA], n2 = n >> 2, bsi = job.bs2;
+    double2* twq = smem;
+    double2* buf = twq + (P.tw_n >> 2) + 1;
+    load_twq(P, twq);
+    const int lg = 31 - __clz(n2);
+    const double2* chirp = bsi >= 0 ? P.bs_tab + P.bs[bsi].chirp_off : nullptr;
+    const int M = bsi >= 0 ? P.bs[bsi].M : n2;
+    for (int a = threadIdx.x; a < M; a += RF_NT) {
+        const int pos = PADI(bsi < 0 ? (int)(__brev((unsigned)a) >> (32 - lg)) : a);
+        if (a >= n2) { buf[pos] = make_double2(0.0, 0.0); continue; }
+        const int k = 4 * a + b;
+        const double2 xa = fold_spectrum<SH>(P, Fm, job.compA, job.ringA, k, n);
+        double2 z = xa;
+        if (job.ringB >= 0) {
+            const double2 xb = fold_spectrum<SH>(P, Fm, job.compB, job.ringB, k, n);
+            z = make_double2(xa.x - xb.y, xa.y + xb.x);  // + i Xb
+        }
+        if (bsi >= 0) z = cmul(z, __ldg(&chirp[a]));
+        buf[pos] = z;
+    }
+    ring_idft(P, buf, twq, n2, bsi);
+    double2* out = scratch + job.off + (int64_t)b * n2;
+    for (int j = threadIdx.x; j < n2; j += RF_NT) {
+        double2 z = buf[PADI(j)];
+        if (bsi >= 0) z = cmul(z, __ldg(&chirp[j]));
+        out[j] = z;
+    }
+}
+
+template <bool SH>
+__global__ void __launch_bounds__(RF_NT)
+ring_synth_combine_kernel(PlanDev P, const SplitJob* __restrict__ jobs, const double2* __restrict__ scratch, double* __restrict__ mapQ,
+                          double* __restrict__ mapU, const int* __restrict__ skip)
+{
+    if (skip && *skip) return;
+    const SplitJob job = jobs[blockIdx.x];
+    const int n = P.ring_nphi[job.ringA], n2 = n >> 2;
+    const double2* Y = scratch + job.off;
+    double* oa = (job.compA ? mapU : mapQ) + ring_first_pixel<SH>(P, job.ringA);
+    double* ob = job.ringB >= 0 ? (job.compB ? mapU : mapQ) + ring_first_pixel<SH>(P, job.ringB) : nullptr;
+    for (int j = threadIdx.x; j < n2; j += RF_NT) {
+        const double2 t1 = unit_root(j, n), t2 = cmul(t1, t1), t3 = cmul(t2, t1);
+        const double2 y0 = Y[j], y1 = cmul(Y[n2 + j], t1), y2 = cmul(Y[2 * n2 + j], t2), y3 = cmul(Y[3 * n2 + j], t3);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double2 z = cadd(cadd(y0, mul_ipow(y1, q)), cadd(mul_ipow(y2, 2 * q), mul_ipow(y3, 3 * q)));
+            oa[j + q * n2] = z.x;
+            if (ob) ob[j + q * n2] = z.y;
+        }
+    }
+}
+
+template <bool SH>
+__global__ void __launch_bounds__(RF_NT, 2)
+ring_anal_split_kernel(PlanDev P, const SplitJob* __restrict__ jobs, const double* __restrict__ mapQ, const double* __restrict__ mapU,
+                       const double* __restrict__ pixw, double2* __restrict__ scratch, const int* __restrict__ skip)
+{
+    if (skip && *skip) return;
+    extern __shared__ double2 smem[];
+    const SplitJob job = jobs[blockIdx.x >> 2];
+    const int b = blockIdx.x & 3;
+    const int n = P.ring_nphi[job.ringA], n2 = n >> 2, bsi = job.bs2;
+    double2* twq = smem;
+    double2* buf = twq + (P.tw_n >> 2) + 1;
+    load_twq(P, twq);
+    const int64_t sa = ring_first_pixel<SH>(P, job.ringA), sb = job.ringB >= 0 ? ring_first_pixel<SH>(P, job.ringB) : 0;
+    const double* ia = (job.compA ? mapU : mapQ) + sa;
+    const double* ib = job.ringB >= 0 ? (job.compB ? mapU : mapQ) + sb : nullptr;
+    const int lg = 31 - __clz(n2);
+    const double2* chirp = bsi >= 0 ? P.bs_tab + P.bs[bsi].chirp_off : nullptr;
+    const int M = bsi >= 0 ? P.bs[bsi].M : n2;
+    for (int j = threadIdx.x; j < M; j += RF_NT) {
+        const int pos = PADI(bsi < 0 ? (int)(__brev((unsigned)j) >> (32 - lg)) : j);
+        if (j >= n2) { buf[pos] = make_double2(0.0, 0.0); continue; }
+        double2 v = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int jj = j + q * n2;
+            double x = ia[jj], y = ib ? ib[jj] : 0.0;
+            if (pixw) { x *= pixw[sa + jj]; if (ib) y *= pixw[sb + jj]; }
+            v = cadd(v, mul_ipow(make_double2(x, -y), q * b));   // c_j = conj(z_j)
+        }
+        if (b) v = cmul(v, unit_root(j * b, n));
+        if (bsi >= 0) v = cmul(v, __ldg(&chirp[j]));
+        buf[pos] = v;
+    }
+    ring_idft(P, buf, twq, n2, bsi);
+    double2* out = scratch + job.off + (int64_t)b * n2;   // C_{4a+b} at [b][a]
+    for (int a = threadIdx.x; a < n2; a += RF_NT) {
+        double2 z = buf[PADI(a)];
+        if (bsi >= 0) z = cmul(z, __ldg(&chirp[a]));
+        out[a] = z;
+    }
+}
+
+template <bool SH>
+__global__ void __launch_bounds__(RF_NT)
+ring_anal_finish_kernel(PlanDev P, const SplitJob* __restrict__ jobs, const double2* __restrict__ scratch, double2* __restrict__ Fm,
+                        const int* __restrict__ skip)
+{
+    if (skip && *skip) return;
+    const SplitJob job = jobs[blockIdx.x];
+    const int L = P.lmax, n = P.ring_nphi[job.ringA], n2 = n >> 2;
+    const double2* Cs = scratch + job.off;
+    for (int m = threadIdx.x; m <= L; m += RF_NT) {
+        const int k = m % n, kk = (n - k) % n;
+        const double2 c1 = Cs[(int64_t)(k & 3) * n2 + (k >> 2)], c2 = Cs[(int64_t)(kk & 3) * n2 + (kk >> 2)];
+        const double2 z1 = make_double2(c1.x, -c1.y);  // Z[k]
+        const double2 z2c = c2;                         // conj Z[n-k]
+        const double2 xa = make_double2(0.5 * (z1.x + z2c.x), 0.5 * (z1.y + z2c.y));
+        const double2 d = csub(z1, z2c);
+        const double2 xb = make_double2(0.5 * d.y, -0.5 * d.x);
+        Fm[fm_ring_index<SH>(P, job.compA, job.ringA, m)] = cmulc(xa, ring_phase(P, job.ringA, m));
+        if (job.ringB >= 0) Fm[fm_ring_index<SH>(P, job.compB, job.ringB, m)] = cmulc(xb, ring_phase(P, job.ringB, m));
+    }
+}
+
 // ------------------------------------------------------------------ host side
 static int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+static int ring_M(int n) { return (n & (n - 1)) == 0 ? n : next_pow2(2 * n - 1); }
 
 int gs_ring_setup(gs_plan* p)
 {
     const int nside = p->d.nside, nring = p->d.nring, npair = p->d.npair, L = p->d.lmax;
+    const size_t smem_max = 227 * 1024;
     std::vector<int> rn(nring);
     for (int r = 0; r < nring; ++r) { int i = std::min(r + 1, 4 * nside - (r + 1)); rn[r] = i < nside ? 4 * i : 4 * nside; }
+    // direct path: staging (L+1) + transform buffer + quarter twiddle table in one CTA; Mcap = largest
+    // power-of-two transform length for which that fits.  Longer rings take the split path (n/4 per CTA).
+    auto direct_smem = [&](int M, int twn) { return (size_t)((L + 1) + (M + M / 16 + 2) + twn / 4 + 1) * sizeof(double2); };
+    int Mcap = 4;
+    while (direct_smem(2 * Mcap, 2 * Mcap) <= smem_max) Mcap *= 2;
+    if (const char* e = getenv("GS_RING_MCAP")) {  // test knob: exercise the split path at small nside
+        const int v = atoi(e);
+        if (v >= 4 && v < Mcap && (v & (v - 1)) == 0) Mcap = v;
+    }
+    auto is_split = [&](int ring) { return ring_M(rn[ring]) > Mcap; };
     std::map<int, int> n2bs;
     std::vector<BluesteinDesc> descs;
     int64_t off = 0;
-    int maxM = 4;
-    for (int r = 0; r < npair; ++r) {
-        const int n = rn[r];
-        if ((n & (n - 1)) == 0) { maxM = std::max(maxM, n); continue; }
-        if (n2bs.count(n)) continue;
+    int maxMd = 4, maxMs = 4;
+    auto need_len = [&](int n, int& maxM) {
+        maxM = std::max(maxM, ring_M(n));
+        if ((n & (n - 1)) == 0 || n2bs.count(n)) return;
         BluesteinDesc d;
         d.n = n; d.M = next_pow2(2 * n - 1); d.chirp_off = off; off += n; d.bhat_off = off; off += d.M;
         n2bs[n] = (int)descs.size();
         descs.push_back(d);
-        maxM = std::max(maxM, d.M);
+    };
+    for (int r = 0; r < npair; ++r) {
+        if (!is_split(r)) need_len(rn[r], maxMd);
+        else {
+            if (ring_M(rn[r] / 4) > Mcap) {
+                gs_set_error("ring FFT: nside %d / lmax %d needs a deeper ring split than this build provides", nside, L);
+                return GS_E_BADARG;
+            }
+            need_len(rn[r] / 4, maxMs);
+        }
     }
+    const int maxM = std::max(maxMd, maxMs);
     std::vector<int> rbs(nring);
-    for (int r = 0; r < nring; ++r) rbs[r] = n2bs.count(rn[r]) ? n2bs[rn[r]] : -1;
+    for (int r = 0; r < nring; ++r) rbs[r] = (!is_split(r) && n2bs.count(rn[r])) ? n2bs[rn[r]] : -1;
     p->d.max_M = maxM;
     p->d.tw_n = maxM;
-    p->ring_smem = (size_t)((L + 1) + (maxM + maxM / 16 + 2) + maxM / 4 + 1) * sizeof(double2);
-    if (p->ring_smem > 227 * 1024) {
+    p->ring_smem = direct_smem(maxMd, maxM);
+    p->split_smem = (size_t)((maxMs + maxMs / 16 + 2) + maxM / 4 + 1) * sizeof(double2);
+    if (p->ring_smem > smem_max || p->split_smem > smem_max) {
         gs_set_error("ring FFT needs %zu bytes of shared memory (> 227 KB): nside/lmax too large for this build", p->ring_smem);
         return GS_E_BADARG;
     }
@@ -429,37 +618,81 @@ int gs_ring_setup(gs_plan* p)
     GS_CHECK_CUDA(cudaFuncSetAttribute(ring_anal_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GS_CHECK_CUDA(cudaFuncSetAttribute(ring_synth_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GS_CHECK_CUDA(cudaFuncSetAttribute(ring_anal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GS_CHECK_CUDA(cudaFuncSetAttribute(ring_synth_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GS_CHECK_CUDA(cudaFuncSetAttribute(ring_anal_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GS_CHECK_CUDA(cudaFuncSetAttribute(ring_synth_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GS_CHECK_CUDA(cudaFuncSetAttribute(ring_anal_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (!descs.empty()) {
-        bluestein_setup_kernel<<<(int)descs.size(), RF_NT, p->ring_smem>>>(p->d, (double2*)d, (int)descs.size());
+        const size_t bsm = (size_t)((maxM + maxM / 16 + 2) + maxM / 4 + 1) * sizeof(double2);
+        bluestein_setup_kernel<<<(int)descs.size(), RF_NT, bsm>>>(p->d, (double2*)d, (int)descs.size());
         GS_CHECK_LAUNCH();
     }
 
-    // job lists, heaviest transforms first
+    // job lists, heaviest transforms first; sharded plans transform only the rings of the owned ring pairs
     auto cost = [&](int ring) { int n = rn[ring]; return rbs[ring] < 0 ? n : 3 * descs[rbs[ring]].M; };
-    // sharded plans transform only the rings of the owned ring pairs
     auto owned = [&](int ring) { return p->world <= 1 || std::min(ring, nring - 1 - ring) % p->world == p->rank; };
     std::vector<RingJob> j2, j0;
-    for (int r = 0; r < nring; ++r) if (owned(r)) j2.push_back(RingJob{r, 0, r, 1});
-    for (int r = 0; r < npair; ++r) { int rs = nring - 1 - r; if (owned(r)) j0.push_back(RingJob{r, 0, rs != r ? rs : -1, 0}); }
+    std::vector<SplitJob> s2, s0;
+    int64_t so2 = 0, so0 = 0;
+    auto bs2_of = [&](int ring) { const int n2 = rn[ring] / 4; return n2bs.count(n2) ? n2bs[n2] : -1; };
+    for (int r = 0; r < nring; ++r) {
+        if (!owned(r)) continue;
+        if (!is_split(r)) j2.push_back(RingJob{r, 0, r, 1});
+        else { s2.push_back(SplitJob{r, 0, r, 1, bs2_of(r), 0, so2}); so2 += rn[r]; }
+    }
+    for (int r = 0; r < npair; ++r) {
+        const int rs = nring - 1 - r;
+        if (!owned(r)) continue;
+        if (!is_split(r)) j0.push_back(RingJob{r, 0, rs != r ? rs : -1, 0});
+        else { s0.push_back(SplitJob{r, 0, rs != r ? rs : -1, 0, bs2_of(r), 0, so0}); so0 += rn[r]; }
+    }
     std::stable_sort(j2.begin(), j2.end(), [&](const RingJob& a, const RingJob& b) { return cost(a.ringA) > cost(b.ringA); });
     std::stable_sort(j0.begin(), j0.end(), [&](const RingJob& a, const RingJob& b) { return cost(a.ringA) > cost(b.ringA); });
-    GS_CHECK_CUDA(cudaMalloc(&d, std::max<size_t>(1, j2.size()) * sizeof(RingJob))); p->owned.push_back(d);
-    GS_CHECK_CUDA(cudaMemcpy(d, j2.data(), j2.size() * sizeof(RingJob), cudaMemcpyHostToDevice));
-    p->jobs2 = (RingJob*)d; p->njobs2 = (int)j2.size();
-    GS_CHECK_CUDA(cudaMalloc(&d, std::max<size_t>(1, j0.size()) * sizeof(RingJob))); p->owned.push_back(d);
-    GS_CHECK_CUDA(cudaMemcpy(d, j0.data(), j0.size() * sizeof(RingJob), cudaMemcpyHostToDevice));
-    p->jobs0 = (RingJob*)d; p->njobs0 = (int)j0.size();
+    auto put = [&](const void* h, size_t bytes, void** out) -> int {
+        void* q = nullptr;
+        GS_CHECK_CUDA(cudaMalloc(&q, std::max<size_t>(16, bytes)));
+        p->owned.push_back(q);
+        if (bytes) GS_CHECK_CUDA(cudaMemcpy(q, h, bytes, cudaMemcpyHostToDevice));
+        *out = q;
+        return GS_OK;
+    };
+    int rc;
+    if ((rc = put(j2.data(), j2.size() * sizeof(RingJob), (void**)&p->jobs2))) return rc;
+    if ((rc = put(j0.data(), j0.size() * sizeof(RingJob), (void**)&p->jobs0))) return rc;
+    if ((rc = put(s2.data(), s2.size() * sizeof(SplitJob), (void**)&p->sjobs2))) return rc;
+    if ((rc = put(s0.data(), s0.size() * sizeof(SplitJob), (void**)&p->sjobs0))) return rc;
+    p->njobs2 = (int)j2.size(); p->njobs0 = (int)j0.size();
+    p->nsjobs2 = (int)s2.size(); p->nsjobs0 = (int)s0.size();
+    if (so2 || so0) {
+        GS_CHECK_CUDA(cudaMalloc(&d, (size_t)std::max(so2, so0) * sizeof(double2)));
+        p->owned.push_back(d);
+        p->ring_scratch = (double2*)d;
+    }
     return GS_OK;
 }
 
 int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st, const int* skip)
 {
-    const int nj = spin == 0 ? p->njobs0 : p->njobs2;
+    const int nj = spin == 0 ? p->njobs0 : p->njobs2, ns = spin == 0 ? p->nsjobs0 : p->nsjobs2;
     const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
+    const SplitJob* sj = spin == 0 ? p->sjobs0 : p->sjobs2;
     double* mu = spin == 0 ? mapQ : mapU;
+    const bool sh = p->world > 1;
+    const double2* F = sh ? p->Fx : p->Fm;
+    if (ns > 0) {  // long rings first: they are the heavy ones
+        if (sh) {
+            ring_synth_split_kernel<true><<<4 * ns, RF_NT, p->split_smem, st>>>(p->d, sj, F, p->ring_scratch, skip);
+            ring_synth_combine_kernel<true><<<ns, RF_NT, 0, st>>>(p->d, sj, p->ring_scratch, mapQ, mu, skip);
+        } else {
+            ring_synth_split_kernel<false><<<4 * ns, RF_NT, p->split_smem, st>>>(p->d, sj, F, p->ring_scratch, skip);
+            ring_synth_combine_kernel<false><<<ns, RF_NT, 0, st>>>(p->d, sj, p->ring_scratch, mapQ, mu, skip);
+        }
+        GS_CHECK_LAUNCH();
+        g_gs_launches += 2;
+    }
     if (nj > 0) {
-        if (p->world > 1) ring_synth_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, p->Fx, mapQ, mu, skip);
-        else ring_synth_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, p->Fm, mapQ, mu, skip);
+        if (sh) ring_synth_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, F, mapQ, mu, skip);
+        else ring_synth_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, F, mapQ, mu, skip);
         GS_CHECK_LAUNCH();
     }
     g_gs_launches += 1;
@@ -469,12 +702,26 @@ int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t
 int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, const double* pixw, cudaStream_t st,
                  const int* skip)
 {
-    const int nj = spin == 0 ? p->njobs0 : p->njobs2;
+    const int nj = spin == 0 ? p->njobs0 : p->njobs2, ns = spin == 0 ? p->nsjobs0 : p->nsjobs2;
     const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
+    const SplitJob* sj = spin == 0 ? p->sjobs0 : p->sjobs2;
     const double* mu = spin == 0 ? mapQ : mapU;
+    const bool sh = p->world > 1;
+    double2* F = sh ? p->Fx : p->Fm;
+    if (ns > 0) {
+        if (sh) {
+            ring_anal_split_kernel<true><<<4 * ns, RF_NT, p->split_smem, st>>>(p->d, sj, mapQ, mu, pixw, p->ring_scratch, skip);
+            ring_anal_finish_kernel<true><<<ns, RF_NT, 0, st>>>(p->d, sj, p->ring_scratch, F, skip);
+        } else {
+            ring_anal_split_kernel<false><<<4 * ns, RF_NT, p->split_smem, st>>>(p->d, sj, mapQ, mu, pixw, p->ring_scratch, skip);
+            ring_anal_finish_kernel<false><<<ns, RF_NT, 0, st>>>(p->d, sj, p->ring_scratch, F, skip);
+        }
+        GS_CHECK_LAUNCH();
+        g_gs_launches += 2;
+    }
     if (nj > 0) {
-        if (p->world > 1) ring_anal_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, mapQ, mu, pixw, p->Fx, skip);
-        else ring_anal_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, mapQ, mu, pixw, p->Fm, skip);
+        if (sh) ring_anal_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, mapQ, mu, pixw, F, skip);
+        else ring_anal_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, mapQ, mu, pixw, F, skip);
         GS_CHECK_LAUNCH();
     }
     g_gs_launches += 1;

@@ -117,11 +117,12 @@ def test_analytic_known_answers_on_gpu():
     assert np.abs(u.cpu().numpy()).max() < 1e-13
 
 
-@pytest.mark.parametrize("nside,lmax", [(256, 512), (512, 1024)])
+@pytest.mark.parametrize("nside,lmax", [(256, 512), (512, 1024), (1024, 2048), (2048, 4096)])
 def test_adjointness_at_bench_sizes(nside, lmax):
-    """<A x, y> = <x, A^T y> in the real layout; size-independent property."""
+    """<A x, y> = <x, A^T y> in the real layout; size-independent property, checked at every
+    BASELINE.json size (configs #2, #3, #4; nside 2048 exercises the split ring path)."""
     from gibbssampler_b200.sht import Plan
-    plan = Plan.get(nside, lmax)
+    plan = Plan.get(nside, lmax) if nside <= 512 else Plan(nside, lmax)
     g = torch.Generator(device="cuda").manual_seed(7)
     nre, npix = (lmax + 1) ** 2, 12 * nside ** 2
     x0 = torch.randn(nre, generator=g, device="cuda", dtype=torch.float64)
@@ -156,3 +157,29 @@ def test_large_size_vs_double_oracle():
     re_, rb_ = O.map2alm_spin2(rq, ru, nside, lmax, kind="f64")
     ge, gb = plan.map2alm_spin2(q, u)
     assert relerr(ge.cpu().numpy(), re_) < RTOL and relerr(gb.cpu().numpy(), rb_) < RTOL
+
+
+@pytest.mark.parametrize("nside,lmax,mcap", [(16, 32, 32), (32, 64, 64), (64, 160, 128), (128, 256, 256)])
+def test_split_ring_path_matches_direct_path(nside, lmax, mcap, monkeypatch):
+    """Rings too long for one CTA (nside >= 2048 in production) are transformed as 4 sub-transforms of length
+    n/4 through a global scratch buffer; GS_RING_MCAP forces that path at small sizes.  Same results as the
+    single-CTA path to rounding, spin 0 and spin 2, both directions."""
+    from gibbssampler_b200.sht import Plan
+    ref = Plan.get(nside, lmax)
+    monkeypatch.setenv("GS_RING_MCAP", str(mcap))
+    plan = Plan(nside, lmax)
+    monkeypatch.delenv("GS_RING_MCAP")
+    rng = np.random.default_rng(3 + nside)
+    e, b = rand_alm(lmax, rng, lmin=2), rand_alm(lmax, rng, lmin=2)
+    q0, u0 = ref.alm2map_spin2(dev(e), dev(b))
+    q1, u1 = plan.alm2map_spin2(dev(e), dev(b))
+    assert relerr(q1.cpu().numpy(), q0.cpu().numpy()) < 1e-12 and relerr(u1.cpu().numpy(), u0.cpu().numpy()) < 1e-12
+    w = dev(rng.random(12 * nside ** 2) + 0.5)
+    fq, fu = dev(rng.standard_normal(12 * nside ** 2)), dev(rng.standard_normal(12 * nside ** 2))
+    e0, b0 = ref.map2alm_spin2(fq, fu, pixw=w, iter=1)
+    e1, b1 = plan.map2alm_spin2(fq, fu, pixw=w, iter=1)
+    assert relerr(e1.cpu().numpy(), e0.cpu().numpy()) < 1e-12 and relerr(b1.cpu().numpy(), b0.cpu().numpy()) < 1e-12
+    t0, t1 = ref.alm2map(dev(e)), plan.alm2map(dev(e))
+    assert relerr(t1.cpu().numpy(), t0.cpu().numpy()) < 1e-12
+    a0, a1 = ref.map2alm(fq, adjoint=True), plan.map2alm(fq, adjoint=True)
+    assert relerr(a1.cpu().numpy(), a0.cpu().numpy()) < 1e-12
