@@ -65,6 +65,11 @@ SIGNATURES = {
     "gs_mala_propose": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _i64, _vp]),
     "gs_mala_logq": (_i, [_vp, _vp, _vp, _vp, _d, _i64, _vp, _vp, _vp]),
     "gs_dot3": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "gs_expand_var_cl_3x3": (_i, [_vp, _i, _vp, _vp]),
+    "gs_inv_chol_3x3": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "gs_matvec_3x3": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    "gs_alm2cl_cross": (_i, [_vp, _vp, _i, _vp, _vp]),
+    "gs_cls_invwishart": (_i, [_vp, _vp, _vp, _i, _vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]),
     "gs_nccl_unique_id": (_i, [C.c_char_p]),
     "gs_plan_create_sharded": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, C.c_char_p]),
     "gs_local_group_create": (_i, [C.POINTER(_vp), _i]),

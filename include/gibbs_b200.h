@@ -243,6 +243,32 @@ int gs_randu(double* out, int64_t n, uint64_t seed, uint64_t stream_id, void* st
 /* out[0] = sum(a[0..n)) in a fixed order; scratch: 592 doubles. */
 int gs_sum(const double* a, int64_t n, double* scratch, double* out, void* stream);
 
+/* ---- per-multipole 3x3 TT/TE/EE/BB machinery (one thread per l / per coefficient) -----------------
+ * Row-major arrays: per-l matrices (L+1,3,3), per-coefficient matrices ((L+1)^2,3,3), vectors ((L+1)^2,3),
+ * component order (T, E, B). */
+/* variance_expension.generate_polarization_var_cl_cython (variance_expension.pyx:36-61): D_l (L+1,3,3) ->
+ * C_l = D_l 2pi/(l(l+1)) expanded over the real alm layout ((L+1)^2,3,3); l = 0 copied.  The reference
+ * indexes cls_[idx] for cls_[l] at :51 (IndexError); the intended per-l lookup is implemented. */
+int gs_expand_var_cl_3x3(const double* dls, int lmax, double* out, void* stream);
+/* utils.compute_inverse_and_cholesky (recovered from utils.cpython-38.pyc; native twin linear_algebra.pyx
+ * compute_inverse_matrices / compute_cholesky, LAPACK dgesv/dpotrf/dpotri): for l >= 2
+ * Sigma_l = (blockdiag(inv(C_l[:2,:2]), 1/C_l[2,2]) + diag(pix_part_l))^-1 and its lower Cholesky factor;
+ * l < 2 -> zeros.  pix_part is (L+1,3); chol nullable. */
+int gs_inv_chol_3x3(const double* all_cls, const double* pix_part, int lmax, double* sigma, double* chol,
+                    void* stream);
+/* utils.matrix_product (recovered; native twin compute_matrix_product): out[i] = mats[l(i)] v[i] (+ add[i])
+ * for every coefficient i of the real layout; add nullable; out may alias add. */
+int gs_matvec_3x3(const double* mats, const double* v, const double* add, int lmax, double* out, void* stream);
+/* hp.alm2cl(alm1, alm2) in the real layout: cl[l] = sum x y / (2l+1) (TE cross spectrum). */
+int gs_alm2cl_cross(const double* alm_x, const double* alm_y, int lmax, double* cl, void* stream);
+/* Inverse-Wishart draw of the (TT, TE; TE, EE) block per l >= 2 with df = 2l - 2 and scale (2l+1) Chat_l
+ * (.ipynb_checkpoints/main-checkpoint.py:39-44, 333-346) by Bartlett decomposition, one thread per l.
+ * cl_* are the empirical spectra (L+1); inject (nullable, (L+1,3)) = (chi2_df, chi2_{df-1}, N(0,1)) from the
+ * caller for parity; outputs are C_l (0 for l < 2). */
+int gs_cls_invwishart(const double* cl_tt, const double* cl_te, const double* cl_ee, int lmax,
+                      const double* inject, uint64_t seed, uint64_t call, double* out_tt, double* out_te,
+                      double* out_ee, void* stream);
+
 /* ---- m-sharded transforms over the GPUs of one node (BASELINE config #4) --------------
  * The reference has no multi-GPU transform (one chain per SLURM task, job-script.sh:6); this is the
  * single-chain strategy for NSIDE >= 1024.  Rank r of `world` owns the m pairs {j, L-j} with j mod world = r

@@ -198,3 +198,72 @@ def nc_loglik(binned, bins, s_nc, prob):
     q, u = synth_pol(prob.bl_map * np.sqrt(vE) * s_nc["EE"], prob.bl_map * np.sqrt(vB) * s_nc["BB"], prob.nside, prob.lmax,
                      prob.kind)
     return -0.5 * (np.sum((prob.d_Q - q) ** 2 * prob.inv_noise) + np.sum((prob.d_U - u) ** 2 * prob.inv_noise))
+
+
+# ---------------------------------------------------------------- per-l 3x3 TT/TE/EE/BB machinery
+def expand_var_cl_3x3(dls):
+    """variance_expension.pyx:36-61 with the :51 index bug fixed (cls_[l], not cls_[idx]): (L+1,3,3) D_l ->
+    ((L+1)^2,3,3) C_l over the real alm layout; l = 0 copied unscaled."""
+    lmax = len(dls) - 1
+    size_complex = (lmax + 1) * (lmax + 2) // 2
+    alms_shape = np.zeros((size_complex, 3, 3))
+    for l in range(lmax + 1):
+        for m in range(l + 1):
+            idx = m * (2 * lmax + 1 - m) // 2 + l
+            alms_shape[idx] = dls[l] if l == 0 else dls[l] * 2 * np.pi / (l * (l + 1))
+    variance = np.zeros(((lmax + 1) ** 2, 3, 3))
+    variance[:lmax + 1] = alms_shape[:lmax + 1]
+    for i in range(lmax + 1, size_complex):
+        variance[2 * i - (lmax + 1)] = alms_shape[i]
+        variance[2 * i - (lmax + 1) + 1] = alms_shape[i]
+    return variance
+
+
+def compute_inverse_and_cholesky(all_cls, pix_part_variance):
+    """utils.compute_inverse_and_cholesky recovered from __pycache__/utils.cpython-38.pyc: for l >= 2
+    M = blockdiag(inv(C[:2,:2]), 1/C[2,2]) + diag(pix_part); Sigma = inv(M); L = chol(Sigma)."""
+    lmax = len(all_cls) - 1
+    sig = np.zeros((lmax + 1, 3, 3))
+    cho = np.zeros((lmax + 1, 3, 3))
+    for l in range(2, lmax + 1):
+        m = np.zeros((3, 3))
+        m[:2, :2] = np.linalg.inv(all_cls[l, :2, :2])
+        m[2, 2] = 1.0 / all_cls[l, 2, 2]
+        m += np.diag(pix_part_variance[l])
+        sig[l] = np.linalg.inv(m)
+        cho[l] = np.linalg.cholesky(sig[l])
+    return sig, cho
+
+
+def l_of_real_layout(lmax):
+    """multipole of every entry of the real layout (utils.py:49-76 ordering)."""
+    out = np.empty((lmax + 1) ** 2, dtype=np.int64)
+    out[:lmax + 1] = np.arange(lmax + 1)
+    pos = lmax + 1
+    for m in range(1, lmax + 1):
+        ls = np.arange(m, lmax + 1)
+        out[pos:pos + 2 * ls.size:2] = ls
+        out[pos + 1:pos + 2 * ls.size:2] = ls
+        pos += 2 * ls.size
+    return out
+
+
+def matrix_product(mats, b):
+    """utils.matrix_product recovered from bytecode: per-l (L+1,3,3) matrices applied to ((L+1)^2,3) vectors."""
+    lmax = len(mats) - 1
+    ell = l_of_real_layout(lmax)
+    return np.einsum("iab,ib->ia", mats[ell], b)
+
+
+def invwishart_bartlett(cl_tt, cl_te, cl_ee, draws):
+    """IW(df = 2l-2, scale = (2l+1) Chat_l) for the (TT,TE;TE,EE) block (.ipynb_checkpoints/main-checkpoint.py:333-346)
+    from supplied (chi2_df, chi2_{df-1}, N(0,1)) per l: X^-1 = (G A)(G A)^T with Psi^-1 = G G^T."""
+    lmax = len(cl_tt) - 1
+    out = np.zeros((lmax + 1, 2, 2))
+    for l in range(2, lmax + 1):
+        psi = (2 * l + 1) * np.array([[cl_tt[l], cl_te[l]], [cl_te[l], cl_ee[l]]])
+        g = np.linalg.cholesky(np.linalg.inv(psi))
+        a = np.array([[np.sqrt(draws[l, 0]), 0.0], [draws[l, 2], np.sqrt(draws[l, 1])]])
+        h = g @ a
+        out[l] = np.linalg.inv(h @ h.T)
+    return out
