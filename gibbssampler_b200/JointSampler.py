@@ -70,9 +70,10 @@ class JointClsSampler():
     def empirical(self, alms):
         L = _lib.lib()
         out = {}
+        dev_alms = {k: f64(alms[k]) for k in ("TT", "EE", "BB")}   # held until the launches below are queued
         for key, (a, b) in {"TT": ("TT", "TT"), "EE": ("EE", "EE"), "BB": ("BB", "BB"), "TE": ("TT", "EE")}.items():
             cl = torch.empty(self.lmax + 1, dtype=torch.float64, device=self.dev)
-            check(L.gs_alm2cl_cross(ptr(f64(alms[a])), ptr(f64(alms[b])), self.lmax, ptr(cl), stream()))
+            check(L.gs_alm2cl_cross(ptr(dev_alms[a]), ptr(dev_alms[b]), self.lmax, ptr(cl), stream()))
             out[key] = cl
         return out
 

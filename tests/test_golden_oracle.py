@@ -74,3 +74,40 @@ def test_noncentred_likelihood_and_proposals_match_reference():
         assert np.array_equal(new, prop[pol])
         lp = np.concatenate([np.zeros(2), truncnorm.logpdf(prop[pol][2:], a=-old[pol][2:] / sc, b=np.inf, loc=old[pol][2:], scale=sc)])
         assert np.allclose(lp, G["logprop_" + pol], rtol=1e-13)
+
+
+def test_3x3_restatements_self_consistent_and_reference_expansion_is_broken():
+    """The 3x3 helpers of the reference exist only as bytecode / a buggy Cython function: pin the
+    restatement by its defining identities, and record that the reference's own expansion cannot run."""
+    import numpy as np
+    from oracle import reference_logic as R
+    rng = np.random.default_rng(1)
+    lmax = 9
+    a = rng.standard_normal((lmax + 1, 3, 3))
+    cls = np.einsum("lab,lcb->lac", a, a) + 3 * np.eye(3)
+    cls[:, 0, 2] = cls[:, 2, 0] = cls[:, 1, 2] = cls[:, 2, 1] = 0
+    pix = rng.random((lmax + 1, 3)) + 0.1
+    sig, cho = R.compute_inverse_and_cholesky(cls, pix)
+    for l in range(2, lmax + 1):
+        m = np.linalg.inv(cls[l]) + np.diag(pix[l])     # blockdiag(inv(2x2), 1/BB) == inv(C) for TB = EB = 0
+        assert np.allclose(sig[l] @ m, np.eye(3), atol=1e-12)
+        assert np.allclose(cho[l] @ cho[l].T, sig[l], atol=1e-14)
+    assert np.all(sig[:2] == 0)
+    exp = R.expand_var_cl_3x3(cls)
+    ell = R.l_of_real_layout(lmax)
+    for i in (0, 1, lmax, lmax + 1, lmax + 2, (lmax + 1) ** 2 - 1):
+        l = ell[i]
+        assert np.allclose(exp[i], cls[l] if l == 0 else cls[l] * 2 * np.pi / (l * (l + 1)))
+    # scalar twin agrees entry by entry (variance_expension.pyx:8-33 == utils.py:114-147)
+    assert np.array_equal(exp[:, 0, 0], R.generate_var_cl(cls[:, 0, 0]))
+    try:
+        import importlib
+        import os
+        import sys
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref"))
+        ref = importlib.import_module("variance_expension")
+    except Exception:
+        ref = None
+    if ref is not None:
+        with pytest.raises(IndexError):  # variance_expension.pyx:51 indexes cls_[idx] with idx up to (L+1)(L+2)/2 - 1
+            ref.generate_polarization_var_cl_cython(np.asfortranarray(cls))

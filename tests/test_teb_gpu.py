@@ -34,7 +34,8 @@ def test_expand_inverse_cholesky_and_matvec_vs_oracle(lmax):
     n = (lmax + 1) ** 2
     # expansion: index map bit-exact, values to rounding of the D_l -> C_l scaling
     out = torch.empty(n, 3, 3, dtype=torch.float64, device="cuda")
-    _lib.check(L.gs_expand_var_cl_3x3(ptr(dev(cls)), lmax, ptr(out), stream()))
+    cls_d = dev(cls)   # keep device inputs alive: a temporary's memory may be reused before the kernel runs
+    _lib.check(L.gs_expand_var_cl_3x3(ptr(cls_d), lmax, ptr(out), stream()))
     ref = R.expand_var_cl_3x3(cls)
     assert np.array_equal(out.cpu().numpy() != 0, ref != 0)
     assert np.allclose(out.cpu().numpy(), ref, rtol=1e-15, atol=0)
@@ -42,7 +43,8 @@ def test_expand_inverse_cholesky_and_matvec_vs_oracle(lmax):
     tag = np.zeros((lmax + 1, 3, 3))
     tag[:, 0, 0] = np.arange(lmax + 1)
     tag[0, 0, 0] = -1.0
-    _lib.check(L.gs_expand_var_cl_3x3(ptr(dev(tag)), lmax, ptr(out), stream()))
+    tag_d = dev(tag)
+    _lib.check(L.gs_expand_var_cl_3x3(ptr(tag_d), lmax, ptr(out), stream()))
     ell = R.l_of_real_layout(lmax)
     got = out[:, 0, 0].cpu().numpy()
     assert np.array_equal(np.round(got[ell > 0] * ell[ell > 0] * (ell[ell > 0] + 1) / (2 * np.pi)).astype(int), ell[ell > 0])
@@ -51,16 +53,21 @@ def test_expand_inverse_cholesky_and_matvec_vs_oracle(lmax):
     pix = rng.random((lmax + 1, 3)) * 50 + 1
     sig = torch.empty(lmax + 1, 3, 3, dtype=torch.float64, device="cuda")
     cho = torch.empty_like(sig)
-    _lib.check(L.gs_inv_chol_3x3(ptr(dev(cls)), ptr(dev(pix)), lmax, ptr(sig), ptr(cho), stream()))
+    pix_d = dev(pix)
+    _lib.check(L.gs_inv_chol_3x3(ptr(cls_d), ptr(pix_d), lmax, ptr(sig), ptr(cho), stream()))
     rs, rc = R.compute_inverse_and_cholesky(cls, pix)
-    assert np.allclose(sig.cpu().numpy(), rs, rtol=1e-12, atol=1e-300)
-    assert np.allclose(cho.cpu().numpy(), rc, rtol=1e-12, atol=1e-300)
+    gs_, gc_ = sig.cpu().numpy(), cho.cpu().numpy()
+    for l in range(2, lmax + 1):  # LAPACK's own inverse carries cond * eps: compare per l relative to the matrix scale
+        assert np.abs(gs_[l] - rs[l]).max() < 1e-11 * np.abs(rs[l]).max()
+        assert np.abs(gc_[l] - rc[l]).max() < 1e-11 * np.abs(rc[l]).max()
+        assert np.abs(gc_[l] @ gc_[l].T - gs_[l]).max() < 1e-14 * np.abs(gs_[l]).max()   # L L^T = Sigma
     assert np.all(sig.cpu().numpy()[:2] == 0)
     # matrix_product
     v = rng.standard_normal((n, 3))
     o = torch.empty(n, 3, dtype=torch.float64, device="cuda")
-    _lib.check(L.gs_matvec_3x3(ptr(sig), ptr(dev(v)), None, lmax, ptr(o), stream()))
-    assert np.allclose(o.cpu().numpy(), R.matrix_product(rs, v), rtol=1e-12, atol=1e-300)
+    v_d = dev(v)
+    _lib.check(L.gs_matvec_3x3(ptr(sig), ptr(v_d), None, lmax, ptr(o), stream()))
+    assert np.abs(o.cpu().numpy() - R.matrix_product(rs, v)).max() < 1e-10 * np.abs(rs).max() * np.abs(v).max()
 
 
 def test_cross_spectrum_and_inverse_wishart_injected_draws_vs_oracle():
@@ -100,8 +107,9 @@ def test_inverse_wishart_device_draws_have_the_right_moments():
     tt, te, ee = np.full(lmax + 1, 2.0), np.full(lmax + 1, 0.7), np.full(lmax + 1, 1.0)
     o = [torch.empty(lmax + 1, dtype=torch.float64, device="cuda") for _ in range(3)]
     acc = np.zeros((3, lmax + 1))
+    tt_d, te_d, ee_d = dev(tt), dev(te), dev(ee)
     for k in range(ndraw):
-        _lib.check(L.gs_cls_invwishart(ptr(dev(tt)), ptr(dev(te)), ptr(dev(ee)), lmax, None, 1234, k + 1, ptr(o[0]), ptr(o[1]), ptr(o[2]),
+        _lib.check(L.gs_cls_invwishart(ptr(tt_d), ptr(te_d), ptr(ee_d), lmax, None, 1234, k + 1, ptr(o[0]), ptr(o[1]), ptr(o[2]),
                                        stream()))
         acc += np.stack([x.cpu().numpy() for x in o])
     acc /= ndraw
