@@ -20,9 +20,17 @@ class ASIS(GibbsSampler):
         """Mirror of ASIS.__init__ (ASIS.py:18-65)."""
         super().__init__(pix_map, noise, beam, nside, lmax, polarization=polarization, bins=bins, n_iter=n_iter, gibbs_cr=gibbs_cr,
                          rj_step=rj_step, verbose=verbose)
-        if not polarization:
-            raise NotImplementedError("temperature-only samplers are not provided (reference TT path is dead at HEAD)")
         shared = _dev.Rng(rng, seed)
+        if not polarization:  # ASIS.py:46-54
+            from .CenteredGibbs import CenteredClsSampler
+            from .Temperature import CenteredConstrainedRealization, NonCenteredClsSampler
+            self.constrained_sampler = CenteredConstrainedRealization(pix_map, noise, self.bl_map, beam, lmax, Npix, mask_path=mask_path,
+                                                                      mask=mask, rng=shared)
+            self.non_centered_cls_sampler = NonCenteredClsSampler(pix_map, lmax, nside, self.bins, self.bl_map, noise, metropolis_blocks,
+                                                                  proposal_variances, n_iter=n_iter_metropolis, mask_path=mask_path,
+                                                                  mask=mask, rng=shared)
+            self.centered_cls_sampler = CenteredClsSampler(pix_map, lmax, nside, self.bins, self.bl_map, noise, rng=shared)
+            return
         self.non_centered_cls_sampler = PolarizationNonCenteredClsSampler(pix_map, lmax, nside, self.bins, self.bl_map, noise, noise_Q,
                                                                           metropolis_blocks, proposal_variances, n_iter=n_iter_metropolis,
                                                                           mask_path=mask_path, all_sph=all_sph, mask=mask, rng=shared)
@@ -40,6 +48,34 @@ class ASIS(GibbsSampler):
             check(_lib.lib().gs_mul(ptr(skymap[pol]), ptr(f), ptr(o), o.numel(), stream()))
             out[pol] = o
         return out
+
+    def run_temperature(self, dls_init):
+        """Mirror of ASIS.run_temperature (ASIS.py:68-132): CR, centred C_l draw, non-centred MwG, re-centring.
+        Returns (h_dls, h_accept, h_accept_cr, h_time_seconds)."""
+        h_accept_cr, h_accept, h_dls, h_time_seconds = [], [], [], []
+        binned_dls = f64(dls_init)
+        cls, var_cls_full = self._tt_state(binned_dls)
+        h_dls.append(_dev.to_host(binned_dls))
+        skymap, _ = self.constrained_sampler.sample(cls, var_cls_full, None, metropolis_step=False)
+        for i in range(self.n_iter):
+            if self.verbose:
+                print("Interweaving, iteration:", i)
+            t0 = time.perf_counter()
+            skymap, accept_cr = self.constrained_sampler.sample(cls, var_cls_full, skymap, use_gibbs=self.gibbs_cr)
+            h_accept_cr.append(accept_cr)
+            binned_dls_temp = self.centered_cls_sampler.sample(skymap)
+            dls_temp = utils.unfold_bins(binned_dls_temp, self.bins)
+            s_nonCentered = f64(skymap) * utils.expand_per_l(dls_temp, 4)          # sqrt(1/C) s (ASIS.py:104-106)
+            binned_dls, var_cls_full, accept = self.non_centered_cls_sampler.sample(s_nonCentered, binned_dls_temp,
+                                                                                    utils.generate_var_cl(dls_temp))
+            dls = utils.unfold_bins(binned_dls, self.bins)
+            cls = dls * f64(self.dls_to_cls_array)
+            skymap = torch.sqrt(f64(var_cls_full)) * s_nonCentered                   # re-centre (ASIS.py:116)
+            torch.cuda.synchronize()
+            h_time_seconds.append(time.perf_counter() - t0)
+            h_accept.append(accept)
+            h_dls.append(_dev.to_host(binned_dls))
+        return np.array(h_dls), np.array(h_accept), np.array(h_accept_cr), np.array(h_time_seconds)
 
     def run_polarization(self, dls_init):
         """Mirror of ASIS.run_polarization (ASIS.py:134-226); same 7-tuple.  Deviation: the re-centring at

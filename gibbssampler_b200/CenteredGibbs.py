@@ -210,8 +210,12 @@ class CenteredGibbs(GibbsSampler):
         cr_rng = shared
         if plan is not None and plan.world > 1 and shared.mode == "philox":
             cr_rng = _dev.Rng(rng, shared.seed + 7919 * (plan.rank + 1))
-        if not polarization:
-            raise NotImplementedError("temperature-only samplers are not provided (reference TT path is dead at HEAD)")
+        if not polarization:  # CenteredGibbs.py:867-870
+            from .Temperature import CenteredConstrainedRealization
+            self.constrained_sampler = CenteredConstrainedRealization(pix_map, noise_temp, self.bl_map, beam, lmax, Npix, mask_path,
+                                                                      isotropic=True, mask=mask, rng=cr_rng, plan=plan)
+            self.cls_sampler = CenteredClsSampler(pix_map, lmax, nside, self.bins, self.bl_map, noise_temp, rng=shared, plan=plan)
+            return
         self.cls_sampler = PolarizedCenteredClsSampler(pix_map, lmax, nside, self.bins, self.bl_map, noise_temp,
                                                        mask_path=mask_path, mask=mask, rng=shared, plan=plan)
         self.constrained_sampler = PolarizedCenteredConstrainedRealization(

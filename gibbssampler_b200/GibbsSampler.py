@@ -88,9 +88,31 @@ class GibbsSampler():
         h_dls["BB"] = np.array(h_dls["BB"])
         return h_dls, np.array(h_accept_cr), np.array(h_duration_cr), np.array(h_duration_cls_sampling)
 
+    def _tt_state(self, binned_dls):
+        """binned D_l -> (C_l, expanded variances) as GibbsSampler.py:88-90."""
+        dls = utils.unfold_bins(f64(binned_dls), self.bins)
+        return dls * f64(self.dls_to_cls_array), utils.generate_var_cl(dls)
+
     def run_temperature(self, dls_init):
-        raise NotImplementedError("temperature-only Gibbs loop: the reference's TT classes do not run at HEAD "
-                                  "(SURVEY.md 0); only the polarised EE/BB path is provided")
+        """Mirror of GibbsSampler.run_temperature (GibbsSampler.py:76-116); same return tuple."""
+        h_accept_cr, h_dls, h_time_seconds = [], [], []
+        binned_dls = f64(dls_init)
+        cls, var_cls_full = self._tt_state(binned_dls)
+        skymap, accept = self.constrained_sampler.sample(cls, var_cls_full, None, metropolis_step=False)
+        h_dls.append(_dev.to_host(binned_dls))
+        for i in range(self.n_iter):
+            if self.verbose:
+                print("Default Gibbs")
+                print(i)
+            start_time = time.perf_counter()
+            skymap, accept = self.constrained_sampler.sample(cls, var_cls_full, skymap, metropolis_step=False, use_gibbs=False)
+            binned_dls = self.cls_sampler.sample(skymap)
+            cls, var_cls_full = self._tt_state(binned_dls)
+            torch.cuda.synchronize()
+            h_accept_cr.append(accept)
+            h_dls.append(_dev.to_host(binned_dls))
+            h_time_seconds.append(time.perf_counter() - start_time)
+        return np.array(h_dls), np.array(h_accept_cr), h_time_seconds
 
     def run(self, dls_init):
         if not self.polarization:

@@ -172,14 +172,39 @@ class NonCenteredGibbs(GibbsSampler):
                  mask=None, rng="philox", seed=None, verbose=False):
         """Mirror of NonCenteredGibbs.__init__ (NonCenteredGibbs.py:450-486)."""
         super().__init__(pix_map, noise_I, beam, nside, lmax, polarization=polarization, bins=bins, n_iter=n_iter, verbose=verbose)
-        if not polarization:
-            raise NotImplementedError("temperature-only samplers are not provided (reference TT path is dead at HEAD)")
         shared = _dev.Rng(rng, seed)
+        if not polarization:  # NonCenteredGibbs.py:471-477
+            from .Temperature import NonCenteredClsSampler, NonCenteredConstrainedRealization
+            self.constrained_sampler = NonCenteredConstrainedRealization(pix_map, noise_I, self.bl_map, beam, lmax, Npix, isotropic=True,
+                                                                         mask_path=mask_path, mask=mask, rng=shared)
+            self.cls_sampler = NonCenteredClsSampler(pix_map, lmax, nside, self.bins, self.bl_map, noise_I, metropolis_blocks,
+                                                     proposal_variances, n_iter=n_iter_metropolis, mask_path=mask_path, mask=mask,
+                                                     rng=shared)
+            return
         self.constrained_sampler = PolarizedNonCenteredConstrainedRealization(pix_map, noise_I, noise_Q, self.bl_map, lmax, Npix, beam,
                                                                               mask_path=mask_path, all_sph=all_sph, mask=mask, rng=shared)
         self.cls_sampler = PolarizationNonCenteredClsSampler(pix_map, lmax, nside, self.bins, self.bl_map, noise_I, noise_Q,
                                                              metropolis_blocks, proposal_variances, n_iter=n_iter_metropolis,
                                                              mask_path=mask_path, all_sph=all_sph, mask=mask, rng=shared)
+
+    def run_temperature(self, dl_init):
+        """Mirror of NonCenteredGibbs.run_temperature (NonCenteredGibbs.py:488-527); same return tuple."""
+        import time
+        h_time_seconds, total_accept, h_dl = [], [], []
+        binned_dls = f64(dl_init)
+        cls, var_cls = self._tt_state(binned_dls)
+        for i in range(self.n_iter):
+            if self.verbose and i % 100 == 0:
+                print("Non centered gibbs")
+                print(i)
+            start_time = time.perf_counter()
+            s_nonCentered, _ = self.constrained_sampler.sample(cls, var_cls, None, False)
+            binned_dls, var_cls, accept = self.cls_sampler.sample(s_nonCentered, binned_dls, var_cls)
+            cls = utils.unfold_bins(binned_dls, self.bins) * f64(self.dls_to_cls_array)
+            total_accept.append(accept)
+            h_dl.append(_dev.to_host(binned_dls))
+            h_time_seconds.append(time.perf_counter() - start_time)
+        return np.array(h_dl), np.array(total_accept), np.array(h_time_seconds)
 
     def run_polarization(self, dls_init):
         """Mirror of NonCenteredGibbs.run_polarization (NonCenteredGibbs.py:529-571); same return tuple."""

@@ -90,8 +90,15 @@ class PNCPGibbs(GibbsSampler):
                  polarization=False, bins=None, n_iter=10000, n_iter_metropolis=1, *, noise_Q=None, mask_path=None, mask=None,
                  rng="philox", seed=None, verbose=False):
         super().__init__(pix_map, noise, beam, nside, lmax, polarization=polarization, bins=bins, n_iter=n_iter, verbose=verbose)
-        if not polarization:
-            raise NotImplementedError("the TT full-sky PNCP of the reference bytecode is not provided; polarization=True only")
+        self.l_cut = int(l_cut)
+        if not polarization:  # the recovered TT class: full sky, isotropic noise
+            from .Temperature import PNCPClsSamplerTT, PNCPConstrainedRealizationTT
+            shared = _dev.Rng(rng, seed)
+            self.constrained_sampler = PNCPConstrainedRealizationTT(pix_map, noise, self.bl_map, beam, lmax, Npix, isotropic=True,
+                                                                    rng=shared, l_cut=l_cut)
+            self.cls_sampler = PNCPClsSamplerTT(pix_map, lmax, nside, self.bins, self.bl_map, noise, metropolis_blocks,
+                                                proposal_variances, l_cut, n_iter=n_iter_metropolis, rng=shared)
+            return
         if noise_Q is None:
             raise ValueError("noise_Q (polarisation noise variance per pixel) is required")
         self.l_cut = int(l_cut)
@@ -100,6 +107,22 @@ class PNCPGibbs(GibbsSampler):
                                                               mask=mask, rng=shared, ula=False, l_cut=l_cut)
         self.cls_sampler = PNCPClsSampler(pix_map, lmax, nside, self.bins, self.bl_map, noise, noise_Q, metropolis_blocks,
                                           proposal_variances, l_cut, n_iter=n_iter_metropolis, mask_path=mask_path, mask=mask, rng=shared)
+
+    def run_temperature(self, dls_init):
+        """Recovered PNCPGibbs.run loop for TT: CR -> low-l centred draw -> high-l non-centred MwG.
+        Returns (h_dls, h_accept, h_time_cr)."""
+        h_dls, h_accept, h_time = [], [], []
+        binned = f64(dls_init)
+        h_dls.append(_dev.to_host(binned))
+        for i in range(self.n_iter):
+            _, var_cls = self._tt_state(binned)
+            mixed, t_cr, _ = self.constrained_sampler.sample(var_cls)
+            binned = self.cls_sampler.sample_low_l(mixed, binned)
+            binned, acc = self.cls_sampler.sample_high_l(mixed, binned)
+            h_time.append(t_cr)
+            h_accept.append(acc)
+            h_dls.append(_dev.to_host(binned))
+        return np.array(h_dls), np.array(h_accept), np.array(h_time)
 
     def run_polarization(self, dls_init):
         """CR -> low-l centred draw -> high-l non-centred MwG (recovered PNCPGibbs.run loop).

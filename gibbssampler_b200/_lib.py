@@ -46,7 +46,11 @@ SIGNATURES = {
     "gs_cr_pcg_pol": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp, _i, _d, _i, _i,
                            C.POINTER(_i), C.POINTER(_d), _vp]),
     "gs_cr_apply_q_pol": (_i, [_vp] * 10),
+    "gs_cr_rhs_tt": (_i, [_vp] * 10 + [_i, _vp, _vp]),
+    "gs_cr_pcg_tt": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _vp, _i, _d, _i, _i, C.POINTER(_i), C.POINTER(_d), _vp]),
+    "gs_cr_apply_q_tt": (_i, [_vp] * 7),
     "gs_cr_direct": (_i, [_vp, _vp, _vp, _vp, _d, _i, _i, _vp, _vp]),
+    "gs_cr_direct_pix": (_i, [_vp, _vp, _vp, _vp, _d, _i, _i, _i, _vp, _vp]),
     "gs_cls_invgamma": (_i, [_vp, _vp, _i, _vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]),
     "gs_truncnorm_propose": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "gs_truncnorm_logpdf": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),

@@ -112,6 +112,33 @@ __global__ void cr_direct_kernel(const double* __restrict__ dl, const double* __
     }
 }
 
+// Diagonal TT draw with the data and the noise fluctuation given as pixel-space adjoints (full sky, isotropic noise):
+//   bsum = b_l (Npix/4pi) map2alm_iter3(N^-1 d) + b_l (Npix/4pi) map2alm_iter3(N^-1/2 xi_pix)   (real layout)
+//   l <  l_cut (centred,     CenteredGibbs.py:100-127):  Sigma = 1/(1/C + w b^2),  s    = Sigma (bsum + xi sqrt(1/C))
+//   l >= l_cut (non-centred, NonCenteredGibbs.py:22-41): Sigma = 1/(1 + C w b^2),  s_nc = Sigma (sqrt(C) bsum + xi)
+// l_cut = L+1: centred sampler; 0: non-centred sampler; in between: the recovered TT PNCPConstrainedRealization.sample
+// (SURVEY.md 2.3), which also zeroes the monopole / dipole entries (zero_low).
+__global__ void cr_direct_pix_kernel(const double* __restrict__ dl, const double* __restrict__ bl, const double* __restrict__ bsum,
+                                     const double* __restrict__ xi, double w, int L, int l_cut, int zero_low, double* __restrict__ out)
+{
+    const int64_t n = (int64_t)(L + 1) * (L + 1);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int l = l_of_real(i, L);
+        double c = dl[l];
+        if (l) c = c * 2.0 * 3.14159265358979323846 / ((double)l * (double)(l + 1));
+        const double b = bl[l];
+        double v;
+        if (l < l_cut) {
+            const double ic = c != 0.0 ? 1.0 / c : 0.0;
+            v = (bsum[i] + xi[i] * sqrt(ic)) / (ic + w * b * b);
+        } else {
+            v = (sqrt(c) * bsum[i] + xi[i]) / (1.0 + c * w * b * b);
+        }
+        if (zero_low && l < 2) v = 0.0;
+        out[i] = v;
+    }
+}
+
 // ------------------------------------------------------------------ inverse-gamma C_l draw
 // PolarizedCenteredClsSampler.sample_one_pol / CenteredClsSampler.sample (CenteredGibbs.py:24-79):
 //   beta_l = (2l+1) l (l+1) Chat_l / (4 pi); per bin: beta = sum beta_l, alpha = sum (2l+1)/2 - 1;
@@ -212,6 +239,16 @@ extern "C" int gs_cr_direct(const double* dl, const double* bl, const double* d_
 {
     GS_REQUIRE(dl && bl && d_alm && xi && out && lmax >= 0 && (mode == 0 || mode == 1), "bad arguments");
     cr_direct_kernel<<<nblk((int64_t)(lmax + 1) * (lmax + 1)), SM_NT, 0, STREAM(stream)>>>(dl, bl, d_alm, xi, npix_over_noise_4pi, lmax, mode, out);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+extern "C" int gs_cr_direct_pix(const double* dl, const double* bl, const double* bsum, const double* xi, double npix_over_noise_4pi,
+                                int lmax, int l_cut, int zero_low, double* out, void* stream)
+{
+    GS_REQUIRE(dl && bl && bsum && xi && out && lmax >= 0 && l_cut >= 0, "bad arguments");
+    cr_direct_pix_kernel<<<nblk((int64_t)(lmax + 1) * (lmax + 1)), SM_NT, 0, STREAM(stream)>>>(dl, bl, bsum, xi, npix_over_noise_4pi, lmax,
+                                                                                                l_cut, zero_low, out);
     GS_CHECK_LAUNCH();
     return GS_OK;
 }

@@ -131,10 +131,10 @@ __global__ void pcg_scalar_kernel(gs_pcg_ws W, int stage)
 
 // r = b - q (q = Q x0, or q absent for x0 = 0), p = M r, delta = <r, M r>, d0 = rr = <r, r>
 __global__ void __launch_bounds__(SV_NT)
-pcg_init_kernel(gs_pcg_ws W, const double* bE, const double* bB, int have_q, int64_t n)
+pcg_init_kernel(gs_pcg_ws W, const double* bE, const double* bB, int have_q, int64_t n, int nc)
 {
     double v[2] = {0.0, 0.0};
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 2 * n; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nc * n; i += (int64_t)gridDim.x * blockDim.x) {
         int c; int64_t j;
         pick(i, n, c, j);
         double r = (c ? bB : bE)[j];
@@ -153,11 +153,11 @@ pcg_init_kernel(gs_pcg_ws W, const double* bE, const double* bB, int have_q, int
 }
 
 // q += C^-1 p ; pq = <p, q> ; alpha = delta / pq
-__global__ void __launch_bounds__(SV_NT) pcg_apq_kernel(gs_pcg_ws W, int64_t n)
+__global__ void __launch_bounds__(SV_NT) pcg_apq_kernel(gs_pcg_ws W, int64_t n, int nc)
 {
     if (W.state->done) return;
     double v[1] = {0.0};
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 2 * n; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nc * n; i += (int64_t)gridDim.x * blockDim.x) {
         int c; int64_t j;
         pick(i, n, c, j);
         const double p = W.p[c][j];
@@ -173,12 +173,12 @@ __global__ void __launch_bounds__(SV_NT) pcg_apq_kernel(gs_pcg_ws W, int64_t n)
 }
 
 // x += alpha p ; r -= alpha q ; rr = <r,r> ; rz = <r, M r> ; beta = rz/delta ; convergence test
-__global__ void __launch_bounds__(SV_NT) pcg_update_kernel(gs_pcg_ws W, double* xE, double* xB, int64_t n)
+__global__ void __launch_bounds__(SV_NT) pcg_update_kernel(gs_pcg_ws W, double* xE, double* xB, int64_t n, int nc)
 {
     if (W.state->done) return;
     const double alpha = W.state->alpha;
     double v[2] = {0.0, 0.0};
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 2 * n; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nc * n; i += (int64_t)gridDim.x * blockDim.x) {
         int c; int64_t j;
         pick(i, n, c, j);
         double* x = c ? xB : xE;
@@ -196,11 +196,11 @@ __global__ void __launch_bounds__(SV_NT) pcg_update_kernel(gs_pcg_ws W, double* 
 }
 
 // p = M r + beta p
-__global__ void __launch_bounds__(SV_NT) pcg_dir_kernel(gs_pcg_ws W, int64_t n)
+__global__ void __launch_bounds__(SV_NT) pcg_dir_kernel(gs_pcg_ws W, int64_t n, int nc)
 {
     if (W.state->done) return;
     const double beta = W.state->beta;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < 2 * n; i += (int64_t)gridDim.x * blockDim.x) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nc * n; i += (int64_t)gridDim.x * blockDim.x) {
         int c; int64_t j;
         pick(i, n, c, j);
         W.p[c][j] = fma(beta, W.p[c][j], W.pre[c][j] * W.r[c][j]);
@@ -256,22 +256,22 @@ static gs_pcg_ws* get_ws(gs_plan* p)
 
 // q = B A^T N^-1 A B v   (C^-1 v is added by pcg_apq_kernel / the caller)
 static int apply_noise_op(gs_plan* p, const double* vE, const double* vB, const double* bl, const double* inv_noise,
-                          double* qE, double* qB, cudaStream_t st, const int* skip)
+                          double* qE, double* qB, cudaStream_t st, const int* skip, int spin = 2)
 {
     int rc;
-    if ((rc = gs_leg_synth(p, 2, vE, vB, GS_ALM_REAL, bl, st, skip))) return rc;
-    if ((rc = gs_ring_synth(p, 2, p->mapQ_tmp, p->mapU_tmp, st, skip))) return rc;
-    if ((rc = gs_ring_anal(p, 2, p->mapQ_tmp, p->mapU_tmp, inv_noise, st, skip))) return rc;
-    return gs_leg_anal(p, 2, qE, qB, GS_ALM_REAL, bl, 1.0, 0, st, skip);
+    if ((rc = gs_leg_synth(p, spin, vE, vB, GS_ALM_REAL, bl, st, skip))) return rc;
+    if ((rc = gs_ring_synth(p, spin, p->mapQ_tmp, p->mapU_tmp, st, skip))) return rc;
+    if ((rc = gs_ring_anal(p, spin, p->mapQ_tmp, p->mapU_tmp, inv_noise, st, skip))) return rc;
+    return gs_leg_anal(p, spin, qE, qB, GS_ALM_REAL, bl, 1.0, 0, st, skip);
 }
 
-extern "C" int gs_cr_pcg_pol(gs_plan* p, const double* dl_EE, const double* dl_BB, const double* bl,
-                             const double* inv_noise, double ninv_sum_over_4pi, const double* rhs_E,
-                             const double* rhs_B, double* x_E, double* x_B, int warm_start, double eps, int itermax,
-                             int check_every, int* n_iter_out, double* resid_out, void* stream)
+// spin 2: (E, B) system; spin 0: temperature (dl_BB, rhs_B, x_B unused)
+static int cr_pcg_impl(gs_plan* p, int spin, const double* dl_EE, const double* dl_BB, const double* bl,
+                       const double* inv_noise, double ninv_sum_over_4pi, const double* rhs_E,
+                       const double* rhs_B, double* x_E, double* x_B, int warm_start, double eps, int itermax,
+                       int check_every, int* n_iter_out, double* resid_out, void* stream)
 {
-    if (!p) { gs_set_error("null plan"); return GS_E_BADARG; }
-    GS_REQUIRE(dl_EE && dl_BB && bl && inv_noise && rhs_E && rhs_B && x_E && x_B, "null pointer argument");
+    const int nc = spin ? 2 : 1;
     GS_REQUIRE(eps > 0.0 && itermax >= 0, "eps must be > 0 and itermax >= 0");
     GS_CHECK_CUDA(cudaSetDevice(p->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -285,13 +285,13 @@ extern "C" int gs_cr_pcg_pol(gs_plan* p, const double* dl_EE, const double* dl_B
     double* tmp_l = w->partials + SV_GRID * 2;  // 4 (L+1) doubles of scratch
     const int lb = (L + 256) / 256;
     precond_kernel<<<lb, 256, 0, st>>>(dl_EE, bl, ninv_sum_over_4pi, L, tmp_l, tmp_l + (L + 1));
-    precond_kernel<<<lb, 256, 0, st>>>(dl_BB, bl, ninv_sum_over_4pi, L, tmp_l + 2 * (L + 1), tmp_l + 3 * (L + 1));
+    if (nc == 2) precond_kernel<<<lb, 256, 0, st>>>(dl_BB, bl, ninv_sum_over_4pi, L, tmp_l + 2 * (L + 1), tmp_l + 3 * (L + 1));
     GS_CHECK_LAUNCH();
     int rc;
     if ((rc = gs_plan_expand_per_l(p, tmp_l, 0, w->invc[0], st))) return rc;
     if ((rc = gs_plan_expand_per_l(p, tmp_l + (L + 1), 0, w->pre[0], st))) return rc;
-    if ((rc = gs_plan_expand_per_l(p, tmp_l + 2 * (L + 1), 0, w->invc[1], st))) return rc;
-    if ((rc = gs_plan_expand_per_l(p, tmp_l + 3 * (L + 1), 0, w->pre[1], st))) return rc;
+    if (nc == 2 && (rc = gs_plan_expand_per_l(p, tmp_l + 2 * (L + 1), 0, w->invc[1], st))) return rc;
+    if (nc == 2 && (rc = gs_plan_expand_per_l(p, tmp_l + 3 * (L + 1), 0, w->pre[1], st))) return rc;
     const bool dist = p->world > 1;
 
     PcgState h;
@@ -301,13 +301,13 @@ extern "C" int gs_cr_pcg_pol(gs_plan* p, const double* dl_EE, const double* dl_B
     *w->host_state = h;
     GS_CHECK_CUDA(cudaMemcpyAsync(w->state, w->host_state, sizeof(PcgState), cudaMemcpyHostToDevice, st));
     if (warm_start) {  // r0 = b - Q x0
-        if ((rc = apply_noise_op(p, x_E, x_B, bl, inv_noise, w->q[0], w->q[1], st, nullptr))) return rc;
+        if ((rc = apply_noise_op(p, x_E, x_B, bl, inv_noise, w->q[0], w->q[1], st, nullptr, spin))) return rc;
         axy_kernel<<<SV_GRID, SV_NT, 0, st>>>(w->q[0], w->invc[0], x_E, w->q[0], n);
-        axy_kernel<<<SV_GRID, SV_NT, 0, st>>>(w->q[1], w->invc[1], x_B, w->q[1], n);
+        if (nc == 2) axy_kernel<<<SV_GRID, SV_NT, 0, st>>>(w->q[1], w->invc[1], x_B, w->q[1], n);
     } else {
-        zero2_kernel<<<SV_GRID, SV_NT, 0, st>>>(x_E, x_B, n);
+        zero2_kernel<<<SV_GRID, SV_NT, 0, st>>>(x_E, nc == 2 ? x_B : x_E, n);
     }
-    pcg_init_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, rhs_E, rhs_B, warm_start ? 1 : 0, n);
+    pcg_init_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, rhs_E, rhs_B, warm_start ? 1 : 0, n, nc);
     GS_CHECK_LAUNCH();
     if (dist) {
         if ((rc = gs_shard_allreduce(p, w->red, 2, st))) return rc;
@@ -319,18 +319,18 @@ extern "C" int gs_cr_pcg_pol(gs_plan* p, const double* dl_EE, const double* dl_B
     bool finished = false;
     while (!finished) {
         for (int k = 0; k < check_every && launched < itermax; ++k, ++launched) {
-            if ((rc = apply_noise_op(p, w->p[0], w->p[1], bl, inv_noise, w->q[0], w->q[1], st, done))) return rc;
-            pcg_apq_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, n);
+            if ((rc = apply_noise_op(p, w->p[0], w->p[1], bl, inv_noise, w->q[0], w->q[1], st, done, spin))) return rc;
+            pcg_apq_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, n, nc);
             if (dist) {
                 if ((rc = gs_shard_allreduce(p, w->red, 1, st))) return rc;
                 pcg_scalar_kernel<<<1, 1, 0, st>>>(*w, 1);
             }
-            pcg_update_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, x_E, x_B, n);
+            pcg_update_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, x_E, x_B, n, nc);
             if (dist) {
                 if ((rc = gs_shard_allreduce(p, w->red, 2, st))) return rc;
                 pcg_scalar_kernel<<<1, 1, 0, st>>>(*w, 2);
             }
-            pcg_dir_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, n);
+            pcg_dir_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, n, nc);
             GS_CHECK_LAUNCH();
             g_gs_launches += 3;
         }
@@ -345,6 +345,75 @@ extern "C" int gs_cr_pcg_pol(gs_plan* p, const double* dl_EE, const double* dl_B
         gs_set_error("PCG stopped at iter_max = %d with |r|/|r0| = %.3e > eps = %.1e", itermax, sqrt(s.rr / s.d0), eps);
         return GS_E_NOTCONVERGED;
     }
+    return GS_OK;
+}
+
+extern "C" int gs_cr_pcg_pol(gs_plan* p, const double* dl_EE, const double* dl_BB, const double* bl,
+                             const double* inv_noise, double ninv_sum_over_4pi, const double* rhs_E,
+                             const double* rhs_B, double* x_E, double* x_B, int warm_start, double eps, int itermax,
+                             int check_every, int* n_iter_out, double* resid_out, void* stream)
+{
+    if (!p) { gs_set_error("null plan"); return GS_E_BADARG; }
+    GS_REQUIRE(dl_EE && dl_BB && bl && inv_noise && rhs_E && rhs_B && x_E && x_B, "null pointer argument");
+    return cr_pcg_impl(p, 2, dl_EE, dl_BB, bl, inv_noise, ninv_sum_over_4pi, rhs_E, rhs_B, x_E, x_B, warm_start, eps, itermax,
+                       check_every, n_iter_out, resid_out, stream);
+}
+
+// Temperature twin (qcinv opfilt_tt chain of ConstrainedRealization.py:40-41, run at CenteredGibbs.py:141-165 and
+// NonCenteredGibbs.py:57-72): Q = C^-1 + B A^T N^-1 A B on one spin-0 field.
+extern "C" int gs_cr_pcg_tt(gs_plan* p, const double* dl_TT, const double* bl, const double* inv_noise,
+                            double ninv_sum_over_4pi, const double* rhs, double* x, int warm_start, double eps, int itermax,
+                            int check_every, int* n_iter_out, double* resid_out, void* stream)
+{
+    if (!p) { gs_set_error("null plan"); return GS_E_BADARG; }
+    GS_REQUIRE(dl_TT && bl && inv_noise && rhs && x, "null pointer argument");
+    return cr_pcg_impl(p, 0, dl_TT, nullptr, bl, inv_noise, ninv_sum_over_4pi, rhs, nullptr, x, nullptr, warm_start, eps, itermax,
+                       check_every, n_iter_out, resid_out, stream);
+}
+
+extern "C" int gs_cr_apply_q_tt(gs_plan* p, const double* dl_TT, const double* bl, const double* inv_noise, const double* x,
+                                double* y, void* stream)
+{
+    if (!p) { gs_set_error("null plan"); return GS_E_BADARG; }
+    GS_REQUIRE(dl_TT && bl && inv_noise && x && y, "null pointer argument");
+    GS_CHECK_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    gs_pcg_ws* w = get_ws(p);
+    if (!w) return GS_E_NOMEM;
+    int rc;
+    if ((rc = gs_plan_expand_per_l(p, dl_TT, 2, w->invc[0], st))) return rc;
+    if ((rc = apply_noise_op(p, x, nullptr, bl, inv_noise, w->q[0], nullptr, st, nullptr, 0))) return rc;
+    axy_kernel<<<SV_GRID, SV_NT, 0, st>>>(w->q[0], w->invc[0], x, y, p->nreal_loc);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+// Right-hand side of the temperature system (CenteredGibbs.py:145-147, NonCenteredGibbs.py:61-63; RNG order xi_alm, xi_pix):
+//   b = bdata + C^-1/2 xi_alm + B (Npix/4pi) map2alm_{iter}(N^-1/2 xi_pix),  bdata = B A^T N^-1 d (what qcinv adds in
+//   chain.sample) passed precomputed or computed from d.
+extern "C" int gs_cr_rhs_tt(gs_plan* p, const double* dl_TT, const double* bl, const double* inv_noise,
+                            const double* sqrt_inv_noise, const double* bdata, const double* d, const double* xi_alm,
+                            const double* xi_pix, int fluct_iter, double* rhs, void* stream)
+{
+    if (!p) { gs_set_error("null plan"); return GS_E_BADARG; }
+    GS_REQUIRE(dl_TT && bl && inv_noise && sqrt_inv_noise && xi_alm && xi_pix && rhs, "null pointer argument");
+    GS_REQUIRE(bdata || d, "need either the precomputed data term or the data map");
+    GS_REQUIRE(fluct_iter >= 0, "fluct_iter must be >= 0");
+    GS_CHECK_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    gs_pcg_ws* w = get_ws(p);
+    if (!w) return GS_E_NOMEM;
+    int rc;
+    if ((rc = gs_map2alm_spin0(p, xi_pix, sqrt_inv_noise, fluct_iter, 0, bl, rhs, GS_ALM_REAL, stream))) return rc;
+    const double resc = (double)p->d.npix / (4.0 * 3.14159265358979323846);
+    if ((rc = gs_plan_expand_per_l(p, dl_TT, 4, w->r[0], st))) return rc;
+    const double* bd = bdata;
+    if (!bd) {
+        if ((rc = gs_map2alm_spin0(p, d, inv_noise, 0, 1, bl, w->p[0], GS_ALM_REAL, stream))) return rc;
+        bd = w->p[0];
+    }
+    rhs_combine_kernel<<<SV_GRID, SV_NT, 0, st>>>(rhs, w->r[0], xi_alm, bd, resc, p->nreal_loc);
+    GS_CHECK_LAUNCH();
     return GS_OK;
 }
 

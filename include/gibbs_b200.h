@@ -150,6 +150,19 @@ int gs_cr_apply_q_pol(gs_plan* plan, const double* dl_EE, const double* dl_BB, c
                       const double* inv_noise, const double* x_E, const double* x_B, double* y_E,
                       double* y_B, void* stream);
 
+/* Temperature twins of the three entry points above (one spin-0 field; qcinv.opfilt_tt chain of
+ * ConstrainedRealization.py:40-41, run at CenteredGibbs.py:141-165 and NonCenteredGibbs.py:57-72).  RNG order
+ * of the reference for the right-hand side: xi_alm[(L+1)^2] first, then xi_pix[Npix] (CenteredGibbs.py:145-147).
+ * bdata = B A^T N^-1 d is what qcinv adds inside chain.sample; pass it precomputed or pass d. */
+int gs_cr_rhs_tt(gs_plan* plan, const double* dl_TT, const double* bl, const double* inv_noise,
+                 const double* sqrt_inv_noise, const double* bdata, const double* d, const double* xi_alm,
+                 const double* xi_pix, int fluct_iter, double* rhs, void* stream);
+int gs_cr_pcg_tt(gs_plan* plan, const double* dl_TT, const double* bl, const double* inv_noise,
+                 double ninv_sum_over_4pi, const double* rhs, double* x, int warm_start, double eps, int itermax,
+                 int check_every, int* n_iter_out, double* resid_out, void* stream);
+int gs_cr_apply_q_tt(gs_plan* plan, const double* dl_TT, const double* bl, const double* inv_noise,
+                     const double* x, double* y, void* stream);
+
 /* Diagonal draw for full sky + isotropic noise, one field, real layout, w = Npix/(noise 4 pi):
  *   mode 0 centred     (CenteredGibbs.py:317-353): sigma = 1/(w b^2 + 1/C), s = sigma b w d + xi sqrt(sigma)
  *   mode 1 non-centred (NonCenteredGibbs.py:138-176, all_sph): sigma = 1/(1 + b^2 C w),
@@ -157,6 +170,14 @@ int gs_cr_apply_q_pol(gs_plan* plan, const double* dl_EE, const double* dl_BB, c
  * dl = unbinned D_l, d_alm = data in harmonic space (pix_map["EE"/"BB"]), xi = standard normals. */
 int gs_cr_direct(const double* dl, const double* bl, const double* d_alm, const double* xi,
                  double npix_over_noise_4pi, int lmax, int mode, double* out, void* stream);
+
+/* Diagonal TT draw, full sky + isotropic noise, with data and noise fluctuation entering as pixel-space adjoints
+ * (utils.adjoint_synthesis_hp, iter = 3): bsum = b_l A^T N^-1 d + b_l A^T N^-1/2 xi_pix in the real layout,
+ * w = Npix / (noise 4 pi).  l < l_cut centred (CenteredConstrainedRealization.sample_no_mask, CenteredGibbs.py:100-127),
+ * l >= l_cut non-centred (NonCenteredConstrainedRealization.sample_no_mask, NonCenteredGibbs.py:22-41); 0 < l_cut <= L
+ * is the recovered TT PNCPConstrainedRealization.sample (PNCP.cpython-38.pyc), which zeroes l < 2 (zero_low). */
+int gs_cr_direct_pix(const double* dl, const double* bl, const double* bsum, const double* xi,
+                     double npix_over_noise_4pi, int lmax, int l_cut, int zero_low, double* out, void* stream);
 
 /* ---- C_l conditional samplers ------------------------------------------------------------ */
 /* PolarizedCenteredClsSampler.sample_one_pol / CenteredClsSampler.sample (CenteredGibbs.py:24-79):

@@ -267,3 +267,92 @@ def invwishart_bartlett(cl_tt, cl_te, cl_ee, draws):
         h = g @ a
         out[l] = np.linalg.inv(h @ h.T)
     return out
+
+
+# ---------------------------------------------------------------- temperature-only twins (CenteredGibbs.py:95-235, NonCenteredGibbs.py:17-101)
+class TTProblem:
+    """Inputs of the TT constrained-realization step (ConstrainedRealization.py:8-49)."""
+
+    def __init__(self, nside, lmax, d, inv_noise, fwhm_deg, kind="ld"):
+        self.nside, self.lmax, self.kind = nside, lmax, kind
+        self.npix = 12 * nside * nside
+        self.d, self.inv_noise = d, inv_noise
+        self.bl_gauss = sht.gauss_beam(np.radians(fwhm_deg), lmax)
+        self.bl_map = expand_per_l(self.bl_gauss)
+        self.resc = self.npix / (4 * np.pi)
+        self.bdata = self.adjoint(d * inv_noise, 0) * self.bl_map   # what qcinv's calc_prep adds in chain.sample
+
+    def adjoint(self, m, iter):
+        """(Npix/4pi) complex_to_real(map2alm(iter)) -- utils.adjoint_synthesis_hp (utils.py:101-111, iter = 3)"""
+        return complex_to_real(sht.map2alm(m, self.nside, self.lmax, iter=iter, kind=self.kind)) * self.resc
+
+    def synth(self, a):
+        return sht.alm2map(real_to_complex(a), self.nside, self.lmax, self.kind)
+
+    def rhs(self, var_cls, xi_alm, xi_pix, fluct_iter=3):
+        """CenteredGibbs.py:145-147 (alm draw first) + the data term added by qcinv"""
+        iv = safe_inv(var_cls)
+        return xi_alm * np.sqrt(iv) + self.bl_map * self.adjoint(xi_pix * np.sqrt(self.inv_noise), fluct_iter) + self.bdata
+
+    def apply_Q(self, var_cls, x):
+        """qcinv opfilt_tt.fwd_op: C^-1 x + b A^T N^-1 A b x"""
+        return safe_inv(var_cls) * x + self.bl_map * self.adjoint(self.synth(self.bl_map * x) * self.inv_noise, 0)
+
+    def pcg(self, var_cls, b, eps=1e-6, itermax=4000, x0=None):
+        cl = var_cls[:self.lmax + 1]
+        M = expand_per_l(safe_inv(safe_inv(cl) + self.bl_gauss ** 2 * np.sum(self.inv_noise) / (4 * np.pi)))
+        x = np.zeros(len(b)) if x0 is None else x0.copy()
+        r = b - self.apply_Q(var_cls, x) if x0 is not None else b.copy()
+        d0 = r @ r
+        z = M * r
+        p = z.copy()
+        delta = r @ z
+        it = 0
+        while it < itermax and r @ r > eps ** 2 * d0:
+            q = self.apply_Q(var_cls, p)
+            alpha = delta / (p @ q)
+            x += alpha * p
+            r -= alpha * q
+            z = M * r
+            dn = r @ z
+            p = z + (dn / delta) * p
+            delta = dn
+            it += 1
+        return x, it
+
+    def sample_no_mask(self, var_cls, xi_alm, xi_pix):
+        """CenteredGibbs.py:100-127"""
+        iv = safe_inv(var_cls)
+        b_w = self.bl_map * self.adjoint(self.inv_noise * self.d, 3)
+        b_f = xi_alm * np.sqrt(iv) + self.bl_map * self.adjoint(xi_pix * np.sqrt(self.inv_noise), 3)
+        sigma = 1 / (iv + self.inv_noise[0] * self.resc * self.bl_map ** 2)
+        return sigma * b_w + sigma * b_f
+
+    def sample_no_mask_nc(self, var_cls, xi_alm, xi_pix):
+        """NonCenteredGibbs.py:22-41"""
+        b_w = np.sqrt(var_cls) * self.bl_map * self.adjoint(self.d * self.inv_noise, 3)
+        b_f = xi_alm + np.sqrt(var_cls) * self.bl_map * self.adjoint(xi_pix * np.sqrt(self.inv_noise), 3)
+        sigma = 1 / (1 + var_cls * self.inv_noise[0] * self.resc * self.bl_map ** 2)
+        return sigma * b_w + sigma * b_f
+
+    def sample_pncp(self, var_cls, xi_alm, xi_pix, l_cut):
+        """PNCPConstrainedRealization.sample recovered from PNCP.cpython-38.pyc"""
+        ell = l_of_real_layout(self.lmax)
+        nc = ell >= l_cut
+        var_low, var_high = var_cls.copy(), var_cls.copy()
+        var_low[nc] = 1
+        var_high[~nc] = 1
+        inv_low = np.zeros(len(var_cls))
+        ok = np.ones(len(var_cls), bool)
+        ok[[0, 1, self.lmax + 1, self.lmax + 2]] = False
+        inv_low[ok] = 1 / var_low[ok]
+        b_w = np.sqrt(var_high) * self.bl_map * self.adjoint(self.d * self.inv_noise, 3)
+        b_f = xi_alm * np.sqrt(inv_low) + np.sqrt(var_high) * self.bl_map * self.adjoint(xi_pix * np.sqrt(self.inv_noise), 3)
+        sigma = 1 / (inv_low + var_high * self.inv_noise[0] * self.resc * self.bl_map ** 2)
+        out = sigma * (b_w + b_f)
+        out[[0, 1, self.lmax + 1, self.lmax + 2]] = 0
+        return out
+
+    def loglik(self, var_cls, s_nc):
+        """ClsSampler.py:94-108"""
+        return -0.5 * np.sum((self.d - self.synth(self.bl_map * np.sqrt(var_cls) * s_nc)) ** 2 * self.inv_noise)
