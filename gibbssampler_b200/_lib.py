@@ -46,7 +46,7 @@ SIGNATURES = {
     "gs_cr_pcg_pol": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp, _i, _d, _i, _i,
                            C.POINTER(_i), C.POINTER(_d), _vp]),
     "gs_cr_apply_q_pol": (_i, [_vp] * 10),
-    "gs_cr_rhs_tt": (_i, [_vp] * 10 + [_i, _vp, _vp]),
+    "gs_cr_rhs_tt": (_i, [_vp] * 9 + [_i, _vp, _vp]),
     "gs_cr_pcg_tt": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _vp, _i, _d, _i, _i, C.POINTER(_i), C.POINTER(_d), _vp]),
     "gs_cr_apply_q_tt": (_i, [_vp] * 7),
     "gs_cr_direct": (_i, [_vp, _vp, _vp, _vp, _d, _i, _i, _vp, _vp]),
