@@ -62,8 +62,11 @@ class PolarizedNonCenteredConstrainedRealization(ConstrainedRealization):
 
 class PolarizationNonCenteredClsSampler(MHClsSampler):
     def __init__(self, pix_map, lmax, nside, bins, bl_map, noise_I, noise_Q, metropolis_blocks, proposal_variances, n_iter=1,
-                 mask_path=None, polarization=True, all_sph=False, *, mask=None, rng="philox", seed=None, l_cut=0):
-        """Mirror of NonCenteredGibbs.py:256-289.  l_cut > 0 keeps l < l_cut centred (PNCP)."""
+                 mask_path=None, polarization=True, all_sph=False, *, mask=None, rng="philox", seed=None, l_cut=0,
+                 batched_blocks=True, workspace_bytes=0):
+        """Mirror of NonCenteredGibbs.py:256-289.  l_cut > 0 keeps l < l_cut centred (PNCP).
+        batched_blocks: run the sweep through gs_mwg_sweep_blocks (one Legendre pass for all blocks; NSIDE <= 1024)
+        instead of one synthesis per block; both give the same chain."""
         super().__init__(pix_map, lmax, nside, bins, bl_map, noise_I, metropolis_blocks, proposal_variances, n_iter=n_iter,
                          polarization=polarization, mask=None, rng=rng, seed=seed)
         self.noise_temp = noise_I
@@ -95,6 +98,10 @@ class PolarizationNonCenteredClsSampler(MHClsSampler):
         self._flE = torch.empty(self.lmax + 1, dtype=torch.float64, device=self.dev)
         self._flB = torch.empty_like(self._flE)
         self._scratch = torch.empty(592, dtype=torch.float64, device=self.dev)
+        self.batched_blocks = bool(batched_blocks) and self.nside <= 1024
+        self.workspace_bytes = int(workspace_bytes)
+        self._bins_h = {p: np.ascontiguousarray(self.bins[p], dtype=np.int32) for p in ("EE", "BB")}
+        self._blocks_h = {p: np.ascontiguousarray(self.metropolis_blocks[p], dtype=np.int32) for p in ("EE", "BB")}
 
     # ---- reference-named helpers -----------------------------------------------------------------
     def propose_dl(self, dls_old):
@@ -138,9 +145,6 @@ class PolarizationNonCenteredClsSampler(MHClsSampler):
         num = self.compute_log_proposal(prop, cur)
         den = self.compute_log_proposal(cur, prop)
         logr = {p: (num[p] - den[p]).contiguous() for p in ("EE", "BB")}
-        old_lik = torch.empty(1, dtype=torch.float64, device=self.dev)
-        new_lik = torch.empty(1, dtype=torch.float64, device=self.dev)
-        self._loglik_device(cur, None, -1, 0, 0, s, old_lik)
         nblk = {p: len(self.metropolis_blocks[p]) - 1 for p in ("EE", "BB")}
         ntot = (nblk["EE"] + nblk["BB"]) * self.n_iter
         if self.rng.mode == "numpy":
@@ -148,16 +152,27 @@ class PolarizationNonCenteredClsSampler(MHClsSampler):
         else:
             u = self.rng.uniform(max(ntot, 2))
         acc = torch.zeros(max(ntot, 1), dtype=torch.int32, device=self.dev)
-        k = 0
-        for ip, pol in enumerate(("EE", "BB")):
-            blocks = self.metropolis_blocks[pol]
-            for i in range(nblk[pol]):
-                b0, b1 = int(blocks[i]), int(blocks[i + 1])
-                for _ in range(self.n_iter):
-                    self._loglik_device(cur, prop, ip, b0, b1, s, new_lik)
-                    check(L.gs_mwg_accept(ptr(cur[pol]), ptr(prop[pol]), ptr(logr[pol]), b0, b1, ptr(new_lik), ptr(old_lik),
-                                          ptr(u[k:]), ptr(acc[k:]), stream()))
-                    k += 1
+        if self.batched_blocks and ntot > 0:
+            bh, kh = self._bins_h, self._blocks_h
+            check(L.gs_mwg_sweep_blocks(self.plan._h, ptr(s["EE"]), ptr(s["BB"]), ptr(cur["EE"]), ptr(cur["BB"]), ptr(prop["EE"]),
+                                        ptr(prop["BB"]), ptr(logr["EE"]), ptr(logr["BB"]), bh["EE"].ctypes.data, self.nb["EE"],
+                                        bh["BB"].ctypes.data, self.nb["BB"], kh["EE"].ctypes.data, nblk["EE"], kh["BB"].ctypes.data,
+                                        nblk["BB"], self.n_iter, ptr(self.bl_gauss_d), self.l_cut, ptr(self.d_Q), ptr(self.d_U),
+                                        ptr(self.inv_noise_pol), ptr(u), ptr(acc), None, self.workspace_bytes, stream()))
+        else:
+            old_lik = torch.empty(1, dtype=torch.float64, device=self.dev)
+            new_lik = torch.empty(1, dtype=torch.float64, device=self.dev)
+            self._loglik_device(cur, None, -1, 0, 0, s, old_lik)
+            k = 0
+            for ip, pol in enumerate(("EE", "BB")):
+                blocks = self.metropolis_blocks[pol]
+                for i in range(nblk[pol]):
+                    b0, b1 = int(blocks[i]), int(blocks[i + 1])
+                    for _ in range(self.n_iter):
+                        self._loglik_device(cur, prop, ip, b0, b1, s, new_lik)
+                        check(L.gs_mwg_accept(ptr(cur[pol]), ptr(prop[pol]), ptr(logr[pol]), b0, b1, ptr(new_lik), ptr(old_lik),
+                                              ptr(u[k:]), ptr(acc[k:]), stream()))
+                        k += 1
         a = acc.cpu().numpy()
         ne = nblk["EE"] * self.n_iter
         accept = {"EE": [int(x) for x in a[:ne]], "BB": [int(x) for x in a[ne:ntot]]}

@@ -60,6 +60,7 @@ SIGNATURES = {
     "gs_sum": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "gs_mwg_filters": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "gs_mwg_accept": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp]),
+    "gs_mwg_sweep_blocks": (_i, [_vp] * 9 + [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "gs_mul": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "gs_aux_v_update": (_i, [_vp, _vp, _vp, _vp, _d, _d, _vp, _vp, _i64, _vp]),
     "gs_aux_s_update": (_i, [_vp, _vp, _vp, _vp, _d, _d, _i, _vp, _vp]),

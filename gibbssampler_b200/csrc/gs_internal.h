@@ -137,6 +137,13 @@ struct gs_plan {
     int nsjobs0;
     double2* ring_scratch;
     size_t split_smem;
+    // block-batched Metropolis sweep workspace (allocated on first use)
+    double2* mwg_F;      // [G][2][nring][L+1]
+    double* mwg_maps;    // [G][2][npix]  (Q maps of all blocks, then U maps)
+    int mwg_group;       // G
+    double* mwg_small;   // reduction partials, likelihood pair, per-l filters
+    int* mwg_meta;       // bins / block boundaries / per-block mmax / flags (re-uploaded when the blocking changes)
+    std::vector<int> mwg_meta_host;
     // workspace
     double2* Fm;        // [2][nring][lmax+1] ring spectra
     double* partial;    // analysis partial sums [nchunk][nalm][4]
@@ -165,6 +172,11 @@ int gs_ring_setup(gs_plan* p);
 int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st, const int* skip = nullptr);
 int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, const double* pixw, cudaStream_t st,
                  const int* skip = nullptr);
+int gs_ring_synth_batch(gs_plan* p, const double2* F, int64_t f_stride, const int* mmax, double* mapQ, double* mapU,
+                        int64_t map_stride, int nb, cudaStream_t st);
+// legendre.cu: block-batched spin-2 synthesis for the Metropolis-within-Gibbs sweep (see leg_synth_blocks_kernel)
+int gs_leg_synth_blocks(gs_plan* p, const double* almE, const double* almB, const double* dflE, const double* dflB,
+                        const int* lbE, int e0, int e1, const int* lbB, int b0, int b1, int lend, double2* Fblk, cudaStream_t st);
 // almops.cu
 int gs_launch_expand_per_l(const double* x, int lmax, int mode, double* out, cudaStream_t st);
 // expansion over the plan's (possibly sharded) real layout

@@ -17,6 +17,8 @@
 // Analysis is the exact transpose; its sum over rings is a register fold + warp shuffle
 // reduce-scatter (9 SHFL.64 per two l for 8 values), then a shared-memory sum over the warps of
 // the block and one deterministic partial per 256-ring-pair chunk, combined by leg_finish_kernel.
+#include <algorithm>
+
 #include "gs_internal.h"
 
 #define LEG_NT 128   // threads per block
@@ -354,6 +356,121 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
     }
 }
 
+// ------------------------------------------------------------------ block-batched synthesis (Metropolis-within-Gibbs sweep)
+// The non-centred likelihood is linear in the synthesised field, so the map change of Metropolis block k is
+//   dM_k = A (dfl_k (.) s),  dfl_k[l] = b_l (sqrt(C'_l) - sqrt(C_l)) on the multipoles of block k, 0 elsewhere
+// (NonCenteredGibbs.py:333-355, 421-442).  The blocks of one spectrum partition the l axis, so ONE
+// pass of the recurrence serves every block: E and B contributions are accumulated separately and flushed to the
+// block's own ring-spectra slot whenever l crosses a block boundary.  lbE / lbB hold the block boundaries in l
+// (block i = [lb[i], lb[i+1])); this launch covers E blocks [e0, e1) -> slots 0.., B blocks [b0, b1) -> slots (e1-e0)..;
+// a slot is [2][nring][L+1] double2 and receives m < lb[i+1] only (the ring stage is told mmax per slot).
+template <int R>
+__global__ void __launch_bounds__(LEG_NT)
+leg_synth_blocks_kernel(PlanDev P, const double* __restrict__ almE, const double* __restrict__ almB, const double* __restrict__ dflE,
+                        const double* __restrict__ dflB, const int* __restrict__ lbE, int e0, int e1, const int* __restrict__ lbB,
+                        int b0, int b1, int lend, double2* __restrict__ Fblk)
+{
+    __shared__ double2 sE[LEG_TL], sB[LEG_TL], sR[LEG_TL];
+    const int L = P.lmax, m = blockIdx.y, tid = threadIdx.x;
+    const int l0 = m > 2 ? m : 2;
+    if (l0 >= lend) return;
+    const int64_t base = (int64_t)m * (2 * L + 1 - m) / 2;
+    const int64_t roff = real_off<false>(P, m, m, base);
+    const int chunk = blockIdx.x * (LEG_NT * R);
+    const int64_t nm = L + 1, cs = (int64_t)P.nring * nm, slot = 2 * cs;
+
+    RingState<2> st[R];
+    double aE[R][8], aB[R][8];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const int p = chunk + j * LEG_NT + tid;
+        st[j].x = 0.0; st[j].pc = st[j].pp = st[j].mc = st[j].mp = 0.0; st[j].sc = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { aE[j][k] = 0.0; aB[j][k] = 0.0; }
+        if (p < P.npair && m <= P.mlim2[p]) {
+            st[j].x = P.cth[p];
+            seed_ring<2>(P, p, m, st[j].pc, st[j].mc, st[j].sc);
+        }
+    }
+    int iE = e0, iB = b0;
+    while (iE < e1 && lbE[iE + 1] <= l0) ++iE;
+    while (iB < b1 && lbB[iB + 1] <= l0) ++iB;
+
+    int l = l0, tile_lo = -(1 << 30);
+    while (l < lend) {
+        int le = lend;
+        if (iE < e1) le = min(le, lbE[iE + 1]);
+        if (iB < b1) le = min(le, lbB[iB + 1]);
+        for (; l < le; ++l) {
+            if (l >= tile_lo + LEG_TL) {  // stage the next l tile (uniform over the block)
+                __syncthreads();
+                tile_lo = l;
+                const int lt = l + tid;
+                double2 e = make_double2(0.0, 0.0), b = e, r = e;
+                if (lt <= L) {
+                    const int64_t id = base + lt;
+                    double pre = -0.5 * P.alpha2[id];
+                    if (m == 0) { e.x = almE[roff + lt]; b.x = almB[roff + lt]; }
+                    else {
+                        const int64_t off = roff + 2 * lt;
+                        pre *= 0.70710678118654752440;
+                        e = make_double2(almE[off], almE[off + 1]);
+                        b = make_double2(almB[off], almB[off + 1]);
+                    }
+                    const double pe = pre * dflE[lt], pb = pre * dflB[lt];
+                    e.x *= pe; e.y *= pe; b.x *= pb; b.y *= pb;
+                    r = P.rec2[id];
+                }
+                sE[tid] = e; sB[tid] = b; sR[tid] = r;
+                __syncthreads();
+            }
+            const int i = l - tile_lo;
+            const double2 r = sR[i], e = sE[i], b = sB[i];
+            const double sgn = ((l + m) & 1) ? -1.0 : 1.0;   // lam^+-(pi - theta) = (-1)^(l+m) lam^-+(theta)
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const double pc = st[j].sc ? 0.0 : st[j].pc, mc = st[j].sc ? 0.0 : st[j].mc;
+                const double sp = sgn * pc, sm = sgn * mc;
+                // E only: c1 = c2 = E'r, c3 = c4 = E'i
+                aE[j][0] = fma(pc, e.x, aE[j][0]); aE[j][1] = fma(mc, e.x, aE[j][1]);
+                aE[j][2] = fma(pc, e.y, aE[j][2]); aE[j][3] = fma(mc, e.y, aE[j][3]);
+                aE[j][4] = fma(sm, e.x, aE[j][4]); aE[j][5] = fma(sp, e.x, aE[j][5]);
+                aE[j][6] = fma(sm, e.y, aE[j][6]); aE[j][7] = fma(sp, e.y, aE[j][7]);
+                // B only: c1 = -B'i, c2 = B'i, c3 = B'r, c4 = -B'r
+                aB[j][0] = fma(-pc, b.y, aB[j][0]); aB[j][1] = fma(mc, b.y, aB[j][1]);
+                aB[j][2] = fma(pc, b.x, aB[j][2]); aB[j][3] = fma(-mc, b.x, aB[j][3]);
+                aB[j][4] = fma(-sm, b.y, aB[j][4]); aB[j][5] = fma(sp, b.y, aB[j][5]);
+                aB[j][6] = fma(sm, b.x, aB[j][6]); aB[j][7] = fma(-sp, b.x, aB[j][7]);
+                rec_step<2>(st[j], r.x, r.y);
+                rescale_check<2>(st[j]);
+            }
+        }
+        // flush the block(s) that end at l
+        for (int which = 0; which < 2; ++which) {
+            const bool isE = which == 0;
+            if (isE ? !(iE < e1 && lbE[iE + 1] == l) : !(iB < b1 && lbB[iB + 1] == l)) continue;
+            double2* F = Fblk + (int64_t)(isE ? iE - e0 : (e1 - e0) + (iB - b0)) * slot;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int p = chunk + j * LEG_NT + tid;
+                double* a = isE ? aE[j] : aB[j];
+                if (p < P.npair) {
+                    const int rn = p, rs = P.nring - 1 - p;
+                    F[(int64_t)rn * nm + m] = make_double2(a[0] + a[1], a[2] + a[3]);
+                    F[cs + (int64_t)rn * nm + m] = make_double2(a[2] - a[3], a[1] - a[0]);
+                    if (rs != rn) {
+                        F[(int64_t)rs * nm + m] = make_double2(a[4] + a[5], a[6] + a[7]);
+                        F[cs + (int64_t)rs * nm + m] = make_double2(a[6] - a[7], a[5] - a[4]);
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) a[k] = 0.0;
+            }
+            if (isE) ++iE; else ++iB;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ analysis
 template <int SPIN>
 struct AnalIn {
@@ -677,5 +794,17 @@ int gs_leg_anal(gs_plan* p, int spin, double* almE, double* almB, int layout, co
     }
     GS_CHECK_LAUNCH();
     g_gs_launches += 2;
+    return GS_OK;
+}
+
+int gs_leg_synth_blocks(gs_plan* p, const double* almE, const double* almB, const double* dflE, const double* dflB,
+                        const int* lbE, int e0, int e1, const int* lbB, int b0, int b1, int lend, double2* Fblk, cudaStream_t st)
+{
+    if (p->world > 1) { gs_set_error("block-batched synthesis needs an unsharded plan"); return GS_E_BADARG; }
+    constexpr int RB = 2;
+    dim3 grid((p->d.npair + LEG_NT * RB - 1) / (LEG_NT * RB), std::min(lend, p->d.lmax + 1));
+    leg_synth_blocks_kernel<RB><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, dflE, dflB, lbE, e0, e1, lbB, b0, b1, lend, Fblk);
+    GS_CHECK_LAUNCH();
+    g_gs_launches += 1;
     return GS_OK;
 }

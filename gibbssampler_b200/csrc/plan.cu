@@ -226,6 +226,11 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
     p->sjobs0 = p->sjobs2 = nullptr;
     p->nsjobs0 = p->nsjobs2 = 0;
     p->ring_scratch = nullptr;
+    p->mwg_F = nullptr;
+    p->mwg_maps = nullptr;
+    p->mwg_group = 0;
+    p->mwg_small = nullptr;
+    p->mwg_meta = nullptr;
     p->world = world;
     p->rank = rank;
     p->comm = nullptr;
@@ -290,6 +295,10 @@ extern "C" int gs_plan_destroy(gs_plan* p)
     if (!p) return GS_OK;
     gs_shard_free(p);
     for (void* d : p->owned) cudaFree(d);
+    cudaFree(p->mwg_F);
+    cudaFree(p->mwg_maps);
+    cudaFree(p->mwg_small);
+    cudaFree(p->mwg_meta);
     delete p;
     return GS_OK;
 }

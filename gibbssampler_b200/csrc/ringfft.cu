@@ -248,11 +248,16 @@ __device__ __forceinline__ int64_t ring_first_pixel(const PlanDev& P, int ring)
 template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
 ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __restrict__ Fm, double* __restrict__ mapQ,
-                  double* __restrict__ mapU, const int* __restrict__ skip)
+                  double* __restrict__ mapU, const int* __restrict__ skip, int64_t f_stride, int64_t map_stride,
+                  const int* __restrict__ mmax)
 {
     if (skip && *skip) return;
     extern __shared__ double2 smem[];
-    const int L = P.lmax, nm = L + 1;
+    // batched use (blockIdx.y = transform index): spectra at Fm + y f_stride hold m <= mmax[y] only, maps at + y map_stride
+    Fm += blockIdx.y * f_stride;
+    mapQ += blockIdx.y * map_stride;
+    mapU += blockIdx.y * map_stride;
+    const int L = P.lmax, nm = L + 1, mtop = mmax ? min(mmax[blockIdx.y], L) : L;
     const RingJob job = jobs[blockIdx.x];
     const int n = P.ring_nphi[job.ringA], bsi = P.ring_bs[job.ringA];
     double2* twq = smem;
@@ -279,7 +284,8 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __
             const double2 step = ring_phase(P, pr, RF_NT);
             for (int m = threadIdx.x; m <= L; m += RF_NT) {
                 const double w = m ? 1.0 : 0.5;  // (2 - delta_m0) / 2
-                const double2 f = SH ? Fm[fm_ring_index<true>(P, cc, ring, m)] : F[m];
+                double2 f = make_double2(0.0, 0.0);
+                if (m <= mtop) f = SH ? Fm[fm_ring_index<true>(P, cc, ring, m)] : F[m];
                 st[m] = cmul(f, make_double2(ph.x * w, ph.y * w));
                 ph = cmul(ph, step);
             }
@@ -691,8 +697,8 @@ int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t
         g_gs_launches += 2;
     }
     if (nj > 0) {
-        if (sh) ring_synth_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, F, mapQ, mu, skip);
-        else ring_synth_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, F, mapQ, mu, skip);
+        if (sh) ring_synth_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, F, mapQ, mu, skip, 0, 0, nullptr);
+        else ring_synth_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, F, mapQ, mu, skip, 0, 0, nullptr);
         GS_CHECK_LAUNCH();
     }
     g_gs_launches += 1;
@@ -724,6 +730,18 @@ int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, c
         else ring_anal_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, mapQ, mu, pixw, F, skip);
         GS_CHECK_LAUNCH();
     }
+    g_gs_launches += 1;
+    return GS_OK;
+}
+
+// nb spin-2 ring syntheses in one launch: spectra F + k f_stride (m <= mmax[k]) -> maps Q/U + k map_stride
+int gs_ring_synth_batch(gs_plan* p, const double2* F, int64_t f_stride, const int* mmax, double* mapQ, double* mapU,
+                        int64_t map_stride, int nb, cudaStream_t st)
+{
+    if (p->world > 1 || p->nsjobs2 > 0) { gs_set_error("batched ring synthesis needs an unsharded plan without split rings"); return GS_E_BADARG; }
+    if (nb <= 0 || p->njobs2 <= 0) return GS_OK;
+    ring_synth_kernel<false><<<dim3(p->njobs2, nb), RF_NT, p->ring_smem, st>>>(p->d, p->jobs2, F, mapQ, mapU, nullptr, f_stride, map_stride, mmax);
+    GS_CHECK_LAUNCH();
     g_gs_launches += 1;
     return GS_OK;
 }

@@ -360,6 +360,237 @@ extern "C" int gs_mul(const double* a, const double* b, double* out, int64_t n, 
     return GS_OK;
 }
 
+// ------------------------------------------------------------------ block-batched Metropolis-within-Gibbs sweep
+// SURVEY.md 8f row 1.  The likelihood is -1/2 sum_p N^-1_p |d_p - M_p|^2 with M = A (fl (.) s_nc) linear in the per-l
+// filter fl, and every Metropolis block touches its own multipoles only.  So with r = d - M(current state) and
+//   dM_k = A (dfl_k (.) s_nc),  dfl_k[l] = b_l (sqrt(C'_l) - sqrt(C_l)) on block k, 0 elsewhere,
+// the candidate likelihood of block k is -1/2 sum N^-1 (r - dM_k)^2 and an acceptance is r -= dM_k.  All dM_k of a
+// group of blocks come out of ONE Legendre pass (leg_synth_blocks_kernel) and one batched ring-FFT launch; each
+// Metropolis test is then three small launches (chi^2 partials, decide, conditional r update), nothing leaves the device.
+__global__ void mwg_dfl_kernel(const double* cur_E, const double* cur_B, const double* prop_E, const double* prop_B,
+                               const int* bins_E, int nb_E, const int* bins_B, int nb_B, int eb0, int eb1, int bb0, int bb1,
+                               const double* bl, int L, int l_cut, double* flE, double* flB, double* dflE, double* dflB)
+{
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l > L) return;
+    const double f = l ? 2.0 * 3.14159265358979323846 / ((double)l * (double)(l + 1)) : 1.0;
+    const double cE = binned_value(cur_E, prop_E, bins_E, nb_E, l, false, 0, 0);
+    const double cB = binned_value(cur_B, prop_B, bins_B, nb_B, l, false, 0, 0);
+    const double pE = binned_value(cur_E, prop_E, bins_E, nb_E, l, true, eb0, eb1);
+    const double pB = binned_value(cur_B, prop_B, bins_B, nb_B, l, true, bb0, bb1);
+    const bool nc = l >= l_cut;
+    flE[l] = bl[l] * (nc ? sqrt(cE * f) : 1.0);
+    flB[l] = bl[l] * (nc ? sqrt(cB * f) : 1.0);
+    dflE[l] = nc ? bl[l] * (sqrt(pE * f) - sqrt(cE * f)) : 0.0;
+    dflB[l] = nc ? bl[l] * (sqrt(pB * f) - sqrt(cB * f)) : 0.0;
+}
+
+// r = d - m (in place over m) and the chi^2 partials of the current state
+__global__ void __launch_bounds__(SM_NT)
+mwg_resid_kernel(const double* __restrict__ dQ, const double* __restrict__ dU, double* __restrict__ mQ, double* __restrict__ mU,
+                 const double* __restrict__ invn, int64_t n, double* __restrict__ partials)
+{
+    double v[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = dQ[i] - mQ[i], b = dU[i] - mU[i];
+        mQ[i] = a; mU[i] = b;
+        v[0] = fma(fma(b, b, a * a), invn[i], v[0]);
+    }
+    block_sum<1>(v, partials + blockIdx.x);
+}
+
+// chi^2 partials of the candidate r - dM_k (the block's change is already in r when *applied != 0)
+__global__ void __launch_bounds__(SM_NT)
+mwg_test_kernel(const double* __restrict__ rQ, const double* __restrict__ rU, const double* __restrict__ gQ,
+                const double* __restrict__ gU, const double* __restrict__ invn, int64_t n, const int* __restrict__ applied,
+                double* __restrict__ partials)
+{
+    const bool sub = *applied == 0;
+    double v[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double a = rQ[i], b = rU[i];
+        if (sub) { a -= gQ[i]; b -= gU[i]; }
+        v[0] = fma(fma(b, b, a * a), invn[i], v[0]);
+    }
+    block_sum<1>(v, partials + blockIdx.x);
+}
+
+// lik[0] = old, lik[1] = new; flags[0] = do_apply for the following mwg_apply_kernel
+__global__ void __launch_bounds__(SM_NT)
+mwg_decide_kernel(const double* __restrict__ partials, int np, double* cur, const double* prop, const double* logr, int b0,
+                  int b1, double* lik, const double* u, int* applied, int* do_apply, int* accept_out)
+{
+    double v[1] = {0.0};
+    for (int i = threadIdx.x; i < np; i += blockDim.x) v[0] += partials[i];
+    __shared__ double res[1];
+    block_sum<1>(v, res);
+    __syncthreads();
+    if (threadIdx.x) return;
+    const double new_lik = -0.5 * res[0];
+    double s = 0.0;
+    for (int b = b0; b < b1; ++b) s += logr[b];
+    const bool acc = log(u[0]) < s + (new_lik - lik[0]);
+    int apply = 0;
+    if (acc) {
+        lik[0] = new_lik;
+        if (*applied == 0) {
+            for (int b = b0; b < b1; ++b) cur[b] = prop[b];
+            *applied = 1;
+            apply = 1;
+        }
+    }
+    lik[1] = new_lik;
+    *do_apply = apply;
+    accept_out[0] = acc ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(SM_NT)
+mwg_apply_kernel(double* __restrict__ rQ, double* __restrict__ rU, const double* __restrict__ gQ, const double* __restrict__ gU,
+                 int64_t n, const int* __restrict__ do_apply)
+{
+    if (*do_apply == 0) return;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        rQ[i] -= gQ[i];
+        rU[i] -= gU[i];
+    }
+}
+
+__global__ void mwg_first_lik_kernel(const double* partials, int np, double* lik)
+{
+    double v[1] = {0.0};
+    for (int i = threadIdx.x; i < np; i += blockDim.x) v[0] += partials[i];
+    __shared__ double res[1];
+    block_sum<1>(v, res);
+    __syncthreads();
+    if (threadIdx.x == 0) lik[0] = lik[1] = -0.5 * res[0];
+}
+
+extern "C" int gs_mwg_sweep_blocks(gs_plan* p, const double* snc_E, const double* snc_B, double* cur_E, double* cur_B,
+                                   const double* prop_E, const double* prop_B, const double* logr_E, const double* logr_B,
+                                   const int* bins_E_host, int nbins_E, const int* bins_B_host, int nbins_B,
+                                   const int* blocks_E_host, int nblk_E, const int* blocks_B_host, int nblk_B, int n_iter,
+                                   const double* bl, int l_cut, const double* d_Q, const double* d_U, const double* inv_noise,
+                                   const double* u, int* accept_out, double* loglik_out, int64_t workspace_bytes, void* stream)
+{
+    if (!p) { gs_set_error("null plan"); return GS_E_BADARG; }
+    GS_CHECK_CUDA(cudaSetDevice(p->device));
+    GS_REQUIRE(snc_E && snc_B && cur_E && cur_B && prop_E && prop_B && logr_E && logr_B && bins_E_host && bins_B_host && bl && d_Q &&
+                   d_U && inv_noise && u && accept_out && nbins_E >= 1 && nbins_B >= 1 && nblk_E >= 0 && nblk_B >= 0 && n_iter >= 1 &&
+                   l_cut >= 0,
+               "bad arguments");
+    GS_REQUIRE((nblk_E == 0 || blocks_E_host) && (nblk_B == 0 || blocks_B_host), "null block list");
+    GS_REQUIRE(p->world == 1 && p->nsjobs2 == 0, "needs an unsharded plan without split rings (NSIDE <= 1024)");
+    const int L = p->d.lmax, nring = p->d.nring;
+    const int64_t npix = p->d.npix;
+    cudaStream_t st = STREAM(stream);
+    // ---- block boundaries in l; blocks index the binned arrays (NonCenteredGibbs.py:421-426)
+    std::vector<int> meta;  // [bins_E | bins_B | lbE | lbB | mmax per block (E blocks then B blocks)]
+    auto check_blocks = [&](const int* blocks, int nblk, const int* bins, int nbins) {
+        for (int i = 0; i <= nblk && nblk > 0; ++i)
+            if (blocks[i] < 0 || blocks[i] > nbins || (i && blocks[i] <= blocks[i - 1])) return false;
+        return true;
+    };
+    GS_REQUIRE(check_blocks(blocks_E_host, nblk_E, bins_E_host, nbins_E) && check_blocks(blocks_B_host, nblk_B, bins_B_host, nbins_B),
+               "block boundaries must be increasing bin indices");
+    meta.insert(meta.end(), bins_E_host, bins_E_host + nbins_E + 1);
+    meta.insert(meta.end(), bins_B_host, bins_B_host + nbins_B + 1);
+    const int off_lbE = (int)meta.size();
+    for (int i = 0; i <= nblk_E && nblk_E > 0; ++i) meta.push_back(std::min(bins_E_host[blocks_E_host[i]], L + 1));
+    if (nblk_E == 0) meta.push_back(0);
+    const int off_lbB = (int)meta.size();
+    for (int i = 0; i <= nblk_B && nblk_B > 0; ++i) meta.push_back(std::min(bins_B_host[blocks_B_host[i]], L + 1));
+    if (nblk_B == 0) meta.push_back(0);
+    const int off_mmax = (int)meta.size();
+    // a block that ends at l <= 2 has no spin-2 multipole: mmax = -1 makes its (never written) spectra slot read as zero
+    for (int i = 0; i < nblk_E; ++i) meta.push_back(meta[off_lbE + i + 1] <= 2 ? -1 : meta[off_lbE + i + 1] - 1);
+    for (int i = 0; i < nblk_B; ++i) meta.push_back(meta[off_lbB + i + 1] <= 2 ? -1 : meta[off_lbB + i + 1] - 1);
+    const int ntot = nblk_E + nblk_B;
+    // ---- workspace (plan-owned, grown on demand): group of G blocks
+    const int64_t slotF = 2LL * nring * (L + 1);  // double2 per block
+    const int64_t per_block = slotF * 16 + 2 * npix * 8;
+    if (workspace_bytes <= 0) workspace_bytes = 8LL << 30;
+    int G = (int)std::max<int64_t>(1, std::min<int64_t>(std::max(ntot, 1), workspace_bytes / per_block));
+    if (G > p->mwg_group) {
+        if (p->mwg_F) { cudaFree(p->mwg_F); cudaFree(p->mwg_maps); p->mwg_F = nullptr; p->mwg_maps = nullptr; p->mwg_group = 0; }
+        GS_CHECK_CUDA(cudaMalloc(&p->mwg_F, (size_t)G * slotF * 16));
+        GS_CHECK_CUDA(cudaMalloc(&p->mwg_maps, (size_t)G * 2 * npix * 8));
+        p->mwg_group = G;
+    }
+    G = p->mwg_group;
+    if (!p->mwg_small) {
+        GS_CHECK_CUDA(cudaMalloc(&p->mwg_small, (SM_GRID + 8 + 4 * (size_t)(L + 1)) * sizeof(double)));
+    }
+    if (meta != p->mwg_meta_host) {
+        GS_CHECK_CUDA(cudaStreamSynchronize(st));
+        if (p->mwg_meta) cudaFree(p->mwg_meta);
+        p->mwg_meta = nullptr;
+        GS_CHECK_CUDA(cudaMalloc(&p->mwg_meta, (meta.size() + ntot + 4) * sizeof(int)));
+        GS_CHECK_CUDA(cudaMemcpy(p->mwg_meta, meta.data(), meta.size() * sizeof(int), cudaMemcpyHostToDevice));
+        p->mwg_meta_host = meta;
+    }
+    const int* bins_E = p->mwg_meta;
+    const int* bins_B = p->mwg_meta + nbins_E + 1;
+    const int* lbE = p->mwg_meta + off_lbE;
+    const int* lbB = p->mwg_meta + off_lbB;
+    const int* mmax = p->mwg_meta + off_mmax;
+    int* flags = p->mwg_meta + meta.size();  // [ntot] applied, then do_apply
+    int* do_apply = flags + ntot;
+    double* partials = p->mwg_small;
+    double* lik = partials + SM_GRID;
+    double* flE = lik + 8;
+    double* flB = flE + (L + 1);
+    double* dflE = flB + (L + 1);
+    double* dflB = dflE + (L + 1);
+    double* rQ = p->mapQ_tmp;
+    double* rU = p->mapU_tmp;
+
+    GS_CHECK_CUDA(cudaMemsetAsync(flags, 0, (ntot + 1) * sizeof(int), st));
+    const int eb0 = nblk_E ? blocks_E_host[0] : 0, eb1 = nblk_E ? blocks_E_host[nblk_E] : 0;
+    const int bb0 = nblk_B ? blocks_B_host[0] : 0, bb1 = nblk_B ? blocks_B_host[nblk_B] : 0;
+    mwg_dfl_kernel<<<(L + 128) / 128, 128, 0, st>>>(cur_E, cur_B, prop_E, prop_B, bins_E, nbins_E, bins_B, nbins_B, eb0, eb1, bb0, bb1,
+                                                    bl, L, l_cut, flE, flB, dflE, dflB);
+    GS_CHECK_LAUNCH();
+    int rc;
+    if ((rc = gs_leg_synth(p, 2, snc_E, snc_B, GS_ALM_REAL, flE, st, nullptr, flB))) return rc;
+    if ((rc = gs_ring_synth(p, 2, rQ, rU, st))) return rc;
+    mwg_resid_kernel<<<SM_GRID, SM_NT, 0, st>>>(d_Q, d_U, rQ, rU, inv_noise, npix, partials);
+    mwg_first_lik_kernel<<<1, SM_NT, 0, st>>>(partials, SM_GRID, lik);
+    GS_CHECK_LAUNCH();
+    g_gs_launches += 4;
+
+    for (int g0 = 0; g0 < ntot; g0 += G) {
+        const int g1 = std::min(ntot, g0 + G), ng = g1 - g0;
+        const int e0 = std::min(g0, nblk_E), e1 = std::min(g1, nblk_E);
+        const int b0 = std::max(g0 - nblk_E, 0), b1 = std::max(g1 - nblk_E, 0);
+        int lend = 0;
+        if (e1 > e0) lend = std::max(lend, meta[off_lbE + e1]);
+        if (b1 > b0) lend = std::max(lend, meta[off_lbB + b1]);
+        lend = std::min(lend, L + 1);
+        if ((rc = gs_leg_synth_blocks(p, snc_E, snc_B, dflE, dflB, lbE, e0, e1, lbB, b0, b1, lend, p->mwg_F, st))) return rc;
+        if ((rc = gs_ring_synth_batch(p, p->mwg_F, slotF, mmax + g0, p->mwg_maps, p->mwg_maps + (int64_t)G * npix, npix, ng, st)))
+            return rc;
+        for (int k = g0; k < g1; ++k) {
+            const bool isE = k < nblk_E;
+            const int* blocks = isE ? blocks_E_host : blocks_B_host;
+            const int i = isE ? k : k - nblk_E;
+            const double* gQ = p->mwg_maps + (int64_t)(k - g0) * npix;
+            const double* gU = p->mwg_maps + (int64_t)(G + k - g0) * npix;
+            for (int it = 0; it < n_iter; ++it) {
+                const int64_t idx = (int64_t)k * n_iter + it;
+                mwg_test_kernel<<<SM_GRID, SM_NT, 0, st>>>(rQ, rU, gQ, gU, inv_noise, npix, flags + k, partials);
+                mwg_decide_kernel<<<1, SM_NT, 0, st>>>(partials, SM_GRID, isE ? cur_E : cur_B, isE ? prop_E : prop_B,
+                                                        isE ? logr_E : logr_B, blocks[i], blocks[i + 1], lik, u + idx, flags + k,
+                                                        do_apply, accept_out + idx);
+                mwg_apply_kernel<<<SM_GRID, SM_NT, 0, st>>>(rQ, rU, gQ, gU, npix, do_apply);
+                g_gs_launches += 3;
+            }
+        }
+        GS_CHECK_LAUNCH();
+    }
+    if (loglik_out) GS_CHECK_CUDA(cudaMemcpyAsync(loglik_out, lik, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    return GS_OK;
+}
+
 // ------------------------------------------------------------------ auxiliary-variable CR sampler (pixel / alm updates)
 // sample_gibbs_change_variable / overrelaxation_sampler (CenteredGibbs.py:676-825):
 //   v | s : v = mean_v + [alpha (v_old - mean_v)] + sqrt(1 - alpha^2) sqrt(gamma) xi,  gamma = mu - N^-1, mean_v = gamma (A B s)

@@ -219,6 +219,23 @@ int gs_mwg_filters(const double* cur_E, const double* cur_B, const double* prop_
  * overwritten with the proposal and old_lik[0] = new_lik[0]; accept_out[0] = 0/1. */
 int gs_mwg_accept(double* cur, const double* prop, const double* logr, int b_start, int b_end,
                   const double* new_lik, double* old_lik, const double* u, int* accept_out, void* stream);
+/* The whole blocked Metropolis sweep of PolarizationNonCenteredClsSampler.sample (NonCenteredGibbs.py:401-445)
+ * in one call, using the linearity of the likelihood's synthesis in the per-l filter (NonCenteredGibbs.py:333-355):
+ * r = d - A (b sqrt(C) s_nc) is synthesised once, the map changes dM_k of ALL blocks come from one pass of the
+ * Legendre recurrence + one batched ring-FFT launch, and each Metropolis test is a fused chi^2 reduction of
+ * r - dM_k followed by a device-side accept (cur <- prop on the block, r <- r - dM_k).  Same accept rule, same
+ * order (EE blocks then BB blocks, n_iter tests per block) and same consumption of u as the per-block path
+ * (gs_mwg_filters + gs_alm2map_spin2_fl2 + gs_loglik_pix + gs_mwg_accept).
+ * snc_*: real-layout alm; cur_* (in/out), prop_*, logr_*: binned arrays; bins_*_host[nbins+1], blocks_*_host[nblk+1]:
+ * HOST int arrays (blocks index the binned arrays); u / accept_out: (nblk_E + nblk_B) * n_iter entries;
+ * loglik_out (nullable, device): final log-likelihood; workspace_bytes: cap of the plan-owned block workspace
+ * (<= 0: 8 GiB).  Needs an unsharded plan with NSIDE <= 1024. */
+int gs_mwg_sweep_blocks(gs_plan* plan, const double* snc_E, const double* snc_B, double* cur_E, double* cur_B,
+                        const double* prop_E, const double* prop_B, const double* logr_E, const double* logr_B,
+                        const int* bins_E_host, int nbins_E, const int* bins_B_host, int nbins_B,
+                        const int* blocks_E_host, int nblk_E, const int* blocks_B_host, int nblk_B, int n_iter,
+                        const double* bl, int l_cut, const double* d_Q, const double* d_U, const double* inv_noise,
+                        const double* u, int* accept_out, double* loglik_out, int64_t workspace_bytes, void* stream);
 /* out = a * b elementwise (re-centring s = sqrt(C) s_nc, ASIS.py:181-203; NonCenteredGibbs.py:192-194). */
 int gs_mul(const double* a, const double* b, double* out, int64_t n, void* stream);
 
