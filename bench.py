@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 # PCG iterations to eps = 1e-5 of the benchmark system (fixed seed).  The count is a property of the
 # linear system and stopping rule, not of the implementation (tests/test_cr_gpu.py shows the oracle and
 # the GPU agree to +-1); the CPU reference arm uses it to extrapolate its bounded sample.
-PCG_ITERS = {512: None, 256: None, 128: None, 64: None}
+PCG_ITERS = {512: 345}
 RHS_SHT_EQUIV = 8  # data term is precomputed; fluctuation term = map2alm(iter=3) = 1 + 3 x 2 transforms, +1 spare
 
 
@@ -76,6 +76,33 @@ def bins_for(lmax):
     bb = np.concatenate([np.arange(0, cut + 1), tail])
     bb[-1] = lmax + 1
     return {"EE": ee, "BB": bb}
+
+
+def blocks_for(lmax, bins, l_cut):
+    """Metropolis blocks over the BINNED arrays: EE one block, BB one wide block then one bin per block (the shipped
+    scheme, config.py:51-52: [2, 279] + arange(280, n_bins), scaled to lmax); the first block starts at the first
+    non-centred bin (l >= l_cut)."""
+    first = {p: int(np.searchsorted(np.asarray(bins[p]), max(l_cut, 2), side="left")) for p in ("EE", "BB")}
+    nb_bb = len(bins["BB"])
+    wide = int(round(279 * lmax / 512))
+    return {"EE": np.array([first["EE"], len(bins["EE"]) - 1]),
+            "BB": np.concatenate([[first["BB"], wide], np.arange(wide + 1, nb_bb)])}
+
+
+def proposal_variances_for(lmax, bins, dlE, dlB, noise_var, npix, bl, fsky=0.8):
+    """Cosmic-variance-like proposal variances per bin, indexed from bin 2 (config.py:196-197)."""
+    ell = np.arange(lmax + 1, dtype=np.float64)
+    nl = noise_var * 4 * np.pi / npix * ell * (ell + 1) / (2 * np.pi) / np.maximum(bl, 1e-30) ** 2
+    out = {}
+    for pol, dl in (("EE", dlE), ("BB", dlB)):
+        var_l = 2.0 / ((2 * ell + 1) * fsky) * (dl + nl) ** 2
+        e = np.asarray(bins[pol])
+        v = np.array([var_l[e[i]:e[i + 1]].sum() / (e[i + 1] - e[i]) ** 2 for i in range(len(e) - 1)])
+        out[pol] = 0.3 * v[2:]
+    return out
+
+
+L_CUT = 5  # PNCP: multipoles below l_cut stay centred (recovered config: l_cut = 5)
 
 
 class ClockSampler(threading.Thread):
@@ -135,7 +162,8 @@ def run_reference(args):
         t, cores = cpu_pair_seconds(nside, lmax, 1)
         t_pairs.append(t)
     t_pair = float(np.median(t_pairs[args.warmup:]))
-    t_iter = t_pair * (n_pcg + RHS_SHT_EQUIV / 2.0)
+    n_pairs = cpu_pairs_per_iteration(args, n_pcg)
+    t_iter = t_pair * n_pairs
     val = 1.0 / t_iter
     line = {
         "impl": "reference", "metric": "gibbs_iters_per_s", "value": val, "unit": "it/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -145,7 +173,8 @@ def run_reference(args):
         "sht_pairs_per_s": 1.0 / t_pair,
         "cpu_baseline": {"value": val, "unit": "it/s", "cores": cores, "kind": "port",
                          "sample": "each step times 1 spin-2 SHT pair (alm2map_spin2 + A^T) of the oracle port at the full NSIDE/lmax on all host "
-                                   "cores; a Gibbs iteration is extrapolated as (n_pcg + %g) pairs with n_pcg = %d" % (RHS_SHT_EQUIV / 2.0, n_pcg)},
+                                   "cores; a Gibbs iteration is extrapolated as %g pairs (n_pcg = %d mat-vecs + RHS transforms%s)"
+                                   % (n_pairs, n_pcg, " + one synthesis per Metropolis block" if args.sampler == "pncp" else "")},
         "e2e": {"value": val, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -169,9 +198,29 @@ def whole_job_value(world, steps, ms):
     return world * steps / (ms * 1e-3)
 
 
+def pncp_block_count(lmax):
+    b = blocks_for(lmax, bins_for(lmax), L_CUT)
+    return len(b["EE"]) + len(b["BB"]) - 2
+
+
+def cpu_pairs_per_iteration(args, n_pcg):
+    """SHT-pair equivalents of one Gibbs iteration on the reference CPU path: n_pcg mat-vecs + the RHS transforms, plus for
+    PNCP one synthesis (= half a pair) per Metropolis block and one for the current likelihood (NonCenteredGibbs.py:401-445)."""
+    pairs = n_pcg + RHS_SHT_EQUIV / 2.0
+    if args.sampler == "pncp":
+        pairs += (pncp_block_count(args.lmax) + 1) / 2.0
+    return pairs
+
+
 def workload_config(args, n_pcg):
-    return {"workload": "CenteredGibbs polarised masked sky: PCG constrained realization (eps 1e-5, diag_cl precond) + inverse-gamma C_l draw; "
-                        "one independent chain per GPU",
+    if args.sampler == "pncp":
+        wl = ("PNCP polarised masked sky (BASELINE config #3): PCG constrained realization (eps 1e-5, diag_cl precond) + inverse-gamma "
+              "draw of l < %d + blocked Metropolis-within-Gibbs sweep of l >= %d (%d blocks); one independent chain per GPU"
+              % (L_CUT, L_CUT, pncp_block_count(args.lmax)))
+    else:
+        wl = ("CenteredGibbs polarised masked sky: PCG constrained realization (eps 1e-5, diag_cl precond) + inverse-gamma C_l draw; "
+              "one independent chain per GPU")
+    return {"workload": wl, "sampler": args.sampler,
             "nside": args.nside, "lmax": args.lmax, "fsky": 0.8, "beam_fwhm_deg": 0.5 * max(1, 512 // args.nside) if args.nside < 512 else 0.5,
             "pcg_iterations": n_pcg, "chains_per_gpu": 1,
             "l2_policy": "inputs larger than L2: each PCG iteration streams the 67 MB ring-spectra intermediate, 50 MB of maps and 100 MB of "
@@ -298,6 +347,10 @@ def main():
     ap.add_argument("--lmax", type=int, default=1024)
     ap.add_argument("--pcg-iters", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sampler", default="pncp", choices=["pncp", "centered"],
+                    help="pncp (default): BASELINE config #3, partially non-centred polarised masked-sky sampler = PCG constrained "
+                         "realization + low-l inverse-gamma draw + high-l blocked Metropolis sweep; centered: CenteredGibbs "
+                         "(PCG constrained realization + inverse-gamma draw)")
     ap.add_argument("--mode", default="chains", choices=["chains", "sharded"],
                     help="chains: one independent chain per GPU (weak scaling, the default and the driver's contract); "
                          "sharded: ONE chain whose SHTs are m-sharded over the GPUs (BASELINE config #4, strong scaling)")
@@ -341,9 +394,21 @@ def main():
     bins = bins_for(lmax)
     bl_map = utils.expand_per_l(_dev.f64(bl), 0)
     noise_pol = torch.full((npix,), noise_var, dtype=torch.float64, device=dev)
-    cr = PolarizedCenteredConstrainedRealization({"Q": dQ, "U": dU}, noise_pol * 1e4, noise_pol, bl_map, lmax, npix, fwhm,
-                                                 mask=mask, rng="philox", seed=chain_seed(rank))
-    cls = PolarizedCenteredClsSampler({"Q": dQ, "U": dU}, lmax, nside, bins, bl_map, noise_pol, mask=mask, rng=cr.rng)
+    pncp = args.sampler == "pncp"
+    n_blocks = 0
+    if pncp:
+        from gibbssampler_b200.PNCP import PNCPClsSampler, PNCPConstrainedRealization
+        blocks = blocks_for(lmax, bins, L_CUT)
+        n_blocks = len(blocks["EE"]) + len(blocks["BB"]) - 2
+        pv = proposal_variances_for(lmax, bins, dlE, dlB, noise_var, npix, bl)
+        cr = PNCPConstrainedRealization({"Q": dQ, "U": dU}, noise_pol * 1e4, noise_pol, bl_map, lmax, npix, fwhm, mask=mask,
+                                        rng="philox", seed=chain_seed(rank), ula=False, l_cut=L_CUT)
+        cls = PNCPClsSampler({"Q": dQ, "U": dU}, lmax, nside, bins, bl_map, noise_pol * 1e4, noise_pol, blocks, pv, L_CUT, n_iter=1,
+                             mask=mask, rng=cr.rng)
+    else:
+        cr = PolarizedCenteredConstrainedRealization({"Q": dQ, "U": dU}, noise_pol * 1e4, noise_pol, bl_map, lmax, npix, fwhm,
+                                                     mask=mask, rng="philox", seed=chain_seed(rank))
+        cls = PolarizedCenteredClsSampler({"Q": dQ, "U": dU}, lmax, nside, bins, bl_map, noise_pol, mask=mask, rng=cr.rng)
 
     def binned_init():
         out = {}
@@ -355,12 +420,23 @@ def main():
     state = {"binned": binned_init()}
     pcg_its = []
 
+    accepts = []
+
+    def unfold(b):
+        return {"EE": utils.unfold_bins(b["EE"], bins["EE"]), "BB": utils.unfold_bins(b["BB"], bins["BB"])}
+
     def step_device():
         b = state["binned"]
-        dls = {"EE": utils.unfold_bins(b["EE"], bins["EE"]), "BB": utils.unfold_bins(b["BB"], bins["BB"])}
-        sky, _ = cr.sample_mask(dls)
+        sky, _ = cr.sample_mask(unfold(b))
         pcg_its.append(cr.last_pcg_iterations)
-        state["binned"] = cls.sample(sky)
+        if not pncp:
+            state["binned"] = cls.sample(sky)
+            return
+        b = cls.sample_low_l(sky, b)                       # PNCPGibbs.run_polarization, one iteration
+        mixed = cr.to_mixed(sky, unfold(b))
+        b, acc = cls.sample_high_l(mixed, b)
+        accepts.append((sum(acc["EE"]) + sum(acc["BB"])) / max(1, len(acc["EE"]) + len(acc["BB"])))
+        state["binned"] = b
 
     h2d = d2h = 0
 
@@ -370,9 +446,20 @@ def main():
         b = state["binned_host"]
         dls = {"EE": np.repeat(b["EE"], np.diff(bins["EE"])), "BB": np.repeat(b["BB"], np.diff(bins["BB"]))}
         sky, _ = cr.sample_mask(dls)                  # H2D: D_l; D2H: alms (numpy out)
-        state["binned_host"] = cls.sample(sky)        # H2D: alms; D2H: binned D_l
-        h2d = 8 * (2 * (lmax + 1) + 2 * nre)
-        d2h = 8 * (2 * nre + len(b["EE"]) + len(b["BB"]))
+        nb = len(b["EE"]) + len(b["BB"])
+        if not pncp:
+            state["binned_host"] = cls.sample(sky)    # H2D: alms; D2H: binned D_l
+            h2d = 8 * (2 * (lmax + 1) + 2 * nre)
+            d2h = 8 * (2 * nre + nb)
+            return
+        sky_d = {k: _dev.f64(v) for k, v in sky.items()}                            # H2D: alms
+        b_d = cls.sample_low_l(sky_d, {k: _dev.f64(v) for k, v in b.items()})       # H2D: binned D_l
+        mixed = {k: v.cpu().numpy() for k, v in cr.to_mixed(sky_d, unfold(b_d)).items()}   # D2H: mixed alms
+        b_h = {k: v.cpu().numpy() for k, v in b_d.items()}                          # D2H: binned D_l
+        b, _ = cls.sample_high_l(mixed, b_h)          # H2D: mixed alms, binned; D2H: binned + accept flags
+        state["binned_host"] = b
+        h2d = 8 * (2 * (lmax + 1) + 2 * nre) + 8 * (2 * nre + nb) + 8 * (2 * nre + nb)
+        d2h = 8 * (2 * nre) + 8 * (2 * nre + nb) + 8 * nb + 4 * n_blocks
 
     def timed(fn, nwarm, nsteps):
         for _ in range(nwarm):
@@ -448,11 +535,13 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         reps = 2 if nside >= 512 else 3
         t_pair, cores = cpu_pair_seconds(nside, lmax, reps)
-        t_iter = t_pair * (n_pcg + RHS_SHT_EQUIV / 2.0)
+        n_pairs = cpu_pairs_per_iteration(args, n_pcg)
+        t_iter = t_pair * n_pairs
         cpu_baseline = {"value": 1.0 / t_iter, "unit": "it/s", "cores": cores, "kind": "port",
                         "pairs_per_s": 1.0 / t_pair,
                         "sample": "%d spin-2 SHT pairs of the oracle port (C + OpenMP, FP64) at the same NSIDE/lmax; one Gibbs iteration "
-                                  "extrapolated as (n_pcg + %g) pairs with the n_pcg = %d of this run" % (reps, RHS_SHT_EQUIV / 2.0, n_pcg)}
+                                  "extrapolated as %g pairs (the n_pcg = %d mat-vecs of this run + RHS transforms%s)"
+                                  % (reps, n_pairs, n_pcg, " + one synthesis per Metropolis block" if pncp else "")}
 
     if rank == 0:
         line = {
@@ -465,6 +554,9 @@ def main():
             "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline, "clocks": clocks.summary(),
             "pcg_iterations_per_step": its_timed,
         }
+        if pncp:
+            line["mwg"] = {"blocks": n_blocks, "mean_accept_rate": float(np.mean(accepts[args.warmup:])) if accepts[args.warmup:] else None,
+                           "path": "gs_mwg_sweep_blocks (one Legendre pass per block group + batched ring FFT)"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -396,11 +396,15 @@ leg_synth_blocks_kernel(PlanDev P, const double* __restrict__ almE, const double
     while (iE < e1 && lbE[iE + 1] <= l0) ++iE;
     while (iB < b1 && lbB[iB + 1] <= l0) ++iB;
 
+    // multipoles below the first block of this launch belong to blocks of another group: their sums are discarded
+    const int startE = e1 > e0 ? lbE[e0] : 0, startB = b1 > b0 ? lbB[b0] : 0;
     int l = l0, tile_lo = -(1 << 30);
     while (l < lend) {
         int le = lend;
         if (iE < e1) le = min(le, lbE[iE + 1]);
         if (iB < b1) le = min(le, lbB[iB + 1]);
+        if (l < startE) le = min(le, startE);
+        if (l < startB) le = min(le, startB);
         for (; l < le; ++l) {
             if (l >= tile_lo + LEG_TL) {  // stage the next l tile (uniform over the block)
                 __syncthreads();
@@ -444,6 +448,18 @@ leg_synth_blocks_kernel(PlanDev P, const double* __restrict__ almE, const double
                 rec_step<2>(st[j], r.x, r.y);
                 rescale_check<2>(st[j]);
             }
+        }
+        if (l == startE) {
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) aE[j][k] = 0.0;
+        }
+        if (l == startB) {
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+#pragma unroll
+                for (int k = 0; k < 8; ++k) aB[j][k] = 0.0;
         }
         // flush the block(s) that end at l
         for (int which = 0; which < 2; ++which) {

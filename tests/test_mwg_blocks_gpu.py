@@ -84,7 +84,8 @@ def test_batched_sweep_tracks_likelihood():
     np.random.seed(5)
     prop = nc.propose_dl(cur)
     logr = {p: torch.zeros_like(cur[p]) for p in cur}
-    ntot = 2 * lmax
+    nblk = lmax - 1
+    ntot = 2 * nblk
     u = f64(np.random.uniform(size=ntot))
     acc = torch.zeros(ntot, dtype=torch.int32, device="cuda")
     out = torch.zeros(1, dtype=torch.float64, device="cuda")
@@ -92,7 +93,7 @@ def test_batched_sweep_tracks_likelihood():
     kh = {p: np.ascontiguousarray(blocks[p], dtype=np.int32) for p in blocks}
     _lib.check(_lib.lib().gs_mwg_sweep_blocks(nc.plan._h, ptr(s["EE"]), ptr(s["BB"]), ptr(cur["EE"]), ptr(cur["BB"]), ptr(prop["EE"]),
                                               ptr(prop["BB"]), ptr(logr["EE"]), ptr(logr["BB"]), bh["EE"].ctypes.data, lmax + 1,
-                                              bh["BB"].ctypes.data, lmax + 1, kh["EE"].ctypes.data, lmax, kh["BB"].ctypes.data, lmax,
+                                              bh["BB"].ctypes.data, lmax + 1, kh["EE"].ctypes.data, nblk, kh["BB"].ctypes.data, nblk,
                                               1, ptr(nc.bl_gauss_d), 0, ptr(nc.d_Q), ptr(nc.d_U), ptr(nc.inv_noise_pol), ptr(u),
                                               ptr(acc), ptr(out), 0, stream()))
     fresh = nc.compute_log_likelihood(cur, s)
