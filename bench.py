@@ -514,9 +514,20 @@ def main():
     f2 = 26.0 * ((nring + 1) // 2) * n_lm2                 # flops of one spin-2 Legendre transform (unpruned)
     dom = max(("leg_synth", "leg_anal"), key=lambda k: stage_ms[k])
     ach = f2 / (stage_ms[dom] * 1e-3) * 1e-12
-    roofline = {"kernel": "leg_anal_kernel<2,2>" if dom == "leg_anal" else "leg_synth_kernel<2,2>", "bound": "fp64",
+    def ncu_traffic(prefix):
+        """DRAM bytes per launch (read + write) of the kernel from the committed ncu --set full capture, or None."""
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))["kernels"]
+            k = next(v for name, v in t.items() if name.startswith(prefix))
+            return k["dram_bytes_read"] + k["dram_bytes_write"]
+        except Exception:
+            return None
+
+    roofline = {"kernel": "leg_anal_kernel<2,4>" if dom == "leg_anal" else "leg_synth_kernel<2,2>", "bound": "fp64",
                 "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value if peak.value else None,
-                "traffic": None,
+                "traffic": ncu_traffic(dom + "_kernel"),
+                "traffic_source": "profiles/traffic_r01.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch; NSIDE 512)"
+                                  if nside == 512 and lmax == 1024 else None,
                 "peak_source": "DFMA microkernel measured in this run (MEASURED_PEAKS.json has no FP64 figure; nominal 37.2 TFLOP/s)",
                 "algorithmic_flops_per_launch": f2, "ms_per_launch": stage_ms[dom],
                 "both_legendre_kernels_tflops": 2 * f2 / ((stage_ms["leg_synth"] + stage_ms["leg_anal"]) * 1e-3) * 1e-12}
@@ -528,7 +539,8 @@ def main():
     ring_bytes = 2 * 16.0 * nring * (lmax + 1) + 2 * 8.0 * npix      # ring spectra (Q,U) + maps (Q,U), one direction
     ring_ms = max(stage_ms["ring_synth"], stage_ms["ring_anal"])
     roofline_hbm = {"kernel": "ring_synth_kernel/ring_anal_kernel", "bound": "hbm", "achieved": ring_bytes / (ring_ms * 1e-3) * 1e-9,
-                    "peak": hbm_peak, "unit": "GB/s", "frac": ring_bytes / (ring_ms * 1e-3) * 1e-9 / hbm_peak, "traffic": None,
+                    "peak": hbm_peak, "unit": "GB/s", "frac": ring_bytes / (ring_ms * 1e-3) * 1e-9 / hbm_peak,
+                    "traffic": ncu_traffic("ring_synth_kernel" if stage_ms["ring_synth"] >= stage_ms["ring_anal"] else "ring_anal_kernel"),
                     "peak_source": hbm_src, "algorithmic_bytes_per_launch": ring_bytes}
 
     cpu_baseline = None
