@@ -505,7 +505,11 @@ def main():
                                    _dev.ptr(y_e), _dev.ptr(y_b), 3, ms4, _dev.stream()))
     _lib.check(L.gs_profile_matvec(plan._h, _dev.ptr(x_e), _dev.ptr(x_b), _dev.ptr(cr.bl_gauss_d), _dev.ptr(cr.inv_noise_pol),
                                    _dev.ptr(y_e), _dev.ptr(y_b), 20, ms4, _dev.stream()))
-    stage_ms = {"leg_synth": ms4[0], "ring_synth": ms4[1], "ring_anal": ms4[2], "leg_anal": ms4[3]}
+    fused_ring = ms4[2] == 0.0   # the PCG's ring stage is one kernel (synthesis -> N^-1 -> analysis per ring)
+    if fused_ring:
+        stage_ms = {"leg_synth": ms4[0], "ring_apply_fused": ms4[1], "leg_anal": ms4[3]}
+    else:
+        stage_ms = {"leg_synth": ms4[0], "ring_synth": ms4[1], "ring_anal": ms4[2], "leg_anal": ms4[3]}
     pair_ms = sum(stage_ms.values())
     peak = C.c_double(0.0)
     _lib.check(L.gs_measure_fp64_peak(C.byref(peak), _dev.stream()))
@@ -514,6 +518,7 @@ def main():
     f2 = 26.0 * ((nring + 1) // 2) * n_lm2                 # flops of one spin-2 Legendre transform (unpruned)
     dom = max(("leg_synth", "leg_anal"), key=lambda k: stage_ms[k])
     ach = f2 / (stage_ms[dom] * 1e-3) * 1e-12
+
     def ncu_traffic(prefix):
         """DRAM bytes per launch (read + write) of the kernel from the committed ncu --set full capture, or None."""
         try:
@@ -523,11 +528,11 @@ def main():
         except Exception:
             return None
 
+    at_bench_size = nside == 512 and lmax == 1024
     roofline = {"kernel": "leg_anal_kernel<2,4>" if dom == "leg_anal" else "leg_synth_kernel<2,2>", "bound": "fp64",
                 "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value if peak.value else None,
-                "traffic": ncu_traffic(dom + "_kernel"),
-                "traffic_source": "profiles/traffic_r01.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch; NSIDE 512)"
-                                  if nside == 512 and lmax == 1024 else None,
+                "traffic": ncu_traffic(dom + "_kernel") if at_bench_size else None,
+                "traffic_source": "profiles/traffic_r01.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
                 "peak_source": "DFMA microkernel measured in this run (MEASURED_PEAKS.json has no FP64 figure; nominal 37.2 TFLOP/s)",
                 "algorithmic_flops_per_launch": f2, "ms_per_launch": stage_ms[dom],
                 "both_legendre_kernels_tflops": 2 * f2 / ((stage_ms["leg_synth"] + stage_ms["leg_anal"]) * 1e-3) * 1e-12}
@@ -536,11 +541,17 @@ def main():
         hbm_peak, hbm_src = peaks["hbm_gbs"], "MEASURED_PEAKS.json"
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback"
-    ring_bytes = 2 * 16.0 * nring * (lmax + 1) + 2 * 8.0 * npix      # ring spectra (Q,U) + maps (Q,U), one direction
-    ring_ms = max(stage_ms["ring_synth"], stage_ms["ring_anal"])
-    roofline_hbm = {"kernel": "ring_synth_kernel/ring_anal_kernel", "bound": "hbm", "achieved": ring_bytes / (ring_ms * 1e-3) * 1e-9,
+    if fused_ring:
+        # ring spectra (Q,U) read and written in place + the N^-1 map; the pixels never leave shared memory
+        ring_bytes = 2 * 2 * 16.0 * nring * (lmax + 1) + 8.0 * npix
+        ring_ms, ring_kernel = stage_ms["ring_apply_fused"], "ring_apply_kernel"
+    else:
+        ring_bytes = 2 * 16.0 * nring * (lmax + 1) + 2 * 8.0 * npix      # ring spectra (Q,U) + maps (Q,U), one direction
+        ring_ms = max(stage_ms["ring_synth"], stage_ms["ring_anal"])
+        ring_kernel = "ring_synth_kernel" if stage_ms["ring_synth"] >= stage_ms["ring_anal"] else "ring_anal_kernel"
+    roofline_hbm = {"kernel": ring_kernel, "bound": "hbm", "achieved": ring_bytes / (ring_ms * 1e-3) * 1e-9,
                     "peak": hbm_peak, "unit": "GB/s", "frac": ring_bytes / (ring_ms * 1e-3) * 1e-9 / hbm_peak,
-                    "traffic": ncu_traffic("ring_synth_kernel" if stage_ms["ring_synth"] >= stage_ms["ring_anal"] else "ring_anal_kernel"),
+                    "traffic": ncu_traffic(ring_kernel) if at_bench_size else None,
                     "peak_source": hbm_src, "algorithmic_bytes_per_launch": ring_bytes}
 
     cpu_baseline = None

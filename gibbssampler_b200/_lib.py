@@ -94,6 +94,7 @@ SIGNATURES = {
     "gs_launch_count": (C.c_longlong, []),
     "gs_profile_matvec": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(C.c_float), _vp]),
     "gs_measure_fp64_peak": (_i, [C.POINTER(_d), _vp]),
+    "gs_set_ring_fused": (_i, [_i]),
 }
 
 

@@ -158,6 +158,7 @@ struct gs_plan {
     double* almB_tmp2;
 };
 
+extern int g_gs_ring_fused;       // 1: the PCG mat-vec runs its ring stage as one fused kernel (ring_apply_kernel)
 extern long long g_gs_launches;  // kernels launched by this library (bench.py's gpu_launches)
 static inline int64_t gs_nalm(int lmax) { return (int64_t)(lmax + 1) * (lmax + 2) / 2; }
 
@@ -172,6 +173,7 @@ int gs_ring_setup(gs_plan* p);
 int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st, const int* skip = nullptr);
 int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, const double* pixw, cudaStream_t st,
                  const int* skip = nullptr);
+int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, const int* skip = nullptr);
 int gs_ring_synth_batch(gs_plan* p, const double2* F, int64_t f_stride, const int* mmax, double* mapQ, double* mapU,
                         int64_t map_stride, int nb, cudaStream_t st);
 // legendre.cu: block-batched spin-2 synthesis for the Metropolis-within-Gibbs sweep (see leg_synth_blocks_kernel)

@@ -245,33 +245,54 @@ __device__ __forceinline__ int64_t ring_first_pixel(const PlanDev& P, int ring)
     return SH ? P.sh.ring_start_loc[ring] : P.ring_start[ring];
 }
 
+// Z[k] = Xa[k] + i Xb[k], X[k] = G[k] + conj G[n-k], G[k] = sum_{m = k mod n} w_m F_m e^{i m phi0} (alias fold), for the two
+// real sequences of a job, written to buf ready for ring_idft: bit-reversed (power-of-two n) or chirp-multiplied and
+// zero-padded (Bluestein).  F_m is taken as zero for m > mtop.
+//  * n > lmax (every belt ring and the longer cap rings): each k aliases at most one m on either side, so the
+//    spectrum is read straight from global memory, both components in one sweep (e^{i (n-k) phi0} = e^{i n phi0}
+//    conj e^{i k phi0}, phases by recurrence over the thread's k).
+//  * shorter rings: the phased spectrum is staged in st[0..lmax] one component at a time and folded from there.
+// All threads of the CTA must call; the caller synchronises before the transform (ring_idft does).
 template <bool SH>
-__global__ void __launch_bounds__(RF_NT, 2)
-ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __restrict__ Fm, double* __restrict__ mapQ,
-                  double* __restrict__ mapU, const int* __restrict__ skip, int64_t f_stride, int64_t map_stride,
-                  const int* __restrict__ mmax)
+__device__ __forceinline__ void ring_build_Z(const PlanDev& P, const RingJob& job, const double2* __restrict__ Fm, int mtop,
+                                             double2* st, double2* buf, int n, int bsi, int M, const double2* __restrict__ chirp)
 {
-    if (skip && *skip) return;
-    extern __shared__ double2 smem[];
-    // batched use (blockIdx.y = transform index): spectra at Fm + y f_stride hold m <= mmax[y] only, maps at + y map_stride
-    Fm += blockIdx.y * f_stride;
-    mapQ += blockIdx.y * map_stride;
-    mapU += blockIdx.y * map_stride;
-    const int L = P.lmax, nm = L + 1, mtop = mmax ? min(mmax[blockIdx.y], L) : L;
-    const RingJob job = jobs[blockIdx.x];
-    const int n = P.ring_nphi[job.ringA], bsi = P.ring_bs[job.ringA];
-    double2* twq = smem;
-    double2* st = twq + (P.tw_n >> 2) + 1;   // one component of the phased ring spectrum at a time
-    double2* buf = st + nm;
-    load_twq(P, twq);
-    const int lg = 31 - __clz(n);
-    const double2* chirp = bsi >= 0 ? P.bs_tab + P.bs[bsi].chirp_off : nullptr;
-    const int M = bsi >= 0 ? P.bs[bsi].M : n;
-    const bool same_phase = job.ringB == job.ringA ||
-                            (job.ringB >= 0 && P.ring_phq[job.ringB] == P.ring_phq[job.ringA] && P.ring_phden[job.ringB] == P.ring_phden[job.ringA]);
-    // Z[k] = Xa[k] + i Xb[k], X[k] = G[k] + conj G[n-k], G[k] = sum_{m = k mod n} w_m F_m e^{i m phi0} (alias fold),
-    // built in two sweeps (A, then B) through one staging buffer; stored bit-reversed (power-of-two n) or
-    // chirp-multiplied and zero-padded (Bluestein)
+    const int L = P.lmax, nm = L + 1, lg = 31 - __clz(n);
+    const bool same_phase = job.ringB < 0 || job.ringB == job.ringA ||
+                            (P.ring_phq[job.ringB] == P.ring_phq[job.ringA] && P.ring_phden[job.ringB] == P.ring_phden[job.ringA]);
+    if (n > L) {
+        const double2* FA = Fm + ((int64_t)job.compA * P.nring + job.ringA) * nm;
+        const double2* FB = job.ringB >= 0 ? Fm + ((int64_t)job.compB * P.nring + job.ringB) * nm : nullptr;
+        double2 pa = ring_phase(P, job.ringA, threadIdx.x);
+        const double2 stepa = ring_phase(P, job.ringA, RF_NT), phna = ring_phase(P, job.ringA, n);
+        double2 pb = pa, stepb = stepa, phnb = phna;
+        if (!same_phase) { pb = ring_phase(P, job.ringB, threadIdx.x); stepb = ring_phase(P, job.ringB, RF_NT); phnb = ring_phase(P, job.ringB, n); }
+        for (int k = threadIdx.x; k < M; k += RF_NT) {
+            const int pos = PADI(bsi < 0 ? (int)(__brev((unsigned)k) >> (32 - lg)) : k);
+            if (k >= n) { buf[pos] = make_double2(0.0, 0.0); continue; }
+            const int kk = k ? n - k : 0;
+            const double wk = k ? 1.0 : 0.5;   // (2 - delta_m0) / 2; kk = 0 only when k = 0
+            double2 fa = make_double2(0.0, 0.0), fa2 = fa, fb = fa, fb2 = fa;
+            if (k <= mtop) {
+                fa = SH ? Fm[fm_ring_index<true>(P, job.compA, job.ringA, k)] : FA[k];
+                if (job.ringB >= 0) fb = SH ? Fm[fm_ring_index<true>(P, job.compB, job.ringB, k)] : FB[k];
+            }
+            if (kk <= mtop) {
+                fa2 = SH ? Fm[fm_ring_index<true>(P, job.compA, job.ringA, kk)] : FA[kk];
+                if (job.ringB >= 0) fb2 = SH ? Fm[fm_ring_index<true>(P, job.compB, job.ringB, kk)] : FB[kk];
+            }
+            const double2 pka = make_double2(pa.x * wk, pa.y * wk), pkb = make_double2(pb.x * wk, pb.y * wk);
+            const double2 qa = k ? cmulc(phna, pa) : make_double2(0.5, 0.0), qb = k ? cmulc(phnb, pb) : make_double2(0.5, 0.0);
+            const double2 ga = cmul(fa, pka), ha = cmul(fa2, qa), gb = cmul(fb, pkb), hb = cmul(fb2, qb);
+            const double2 xa = make_double2(ga.x + ha.x, ga.y - ha.y), xb = make_double2(gb.x + hb.x, gb.y - hb.y);
+            double2 z = make_double2(xa.x - xb.y, xa.y + xb.x);   // Xa + i Xb
+            if (bsi >= 0) z = cmul(z, __ldg(&chirp[k]));
+            buf[pos] = z;
+            pa = cmul(pa, stepa);
+            pb = cmul(pb, stepb);
+        }
+        return;
+    }
     for (int comp = 0; comp < 2; ++comp) {
         const int ring = comp ? job.ringB : job.ringA;
         if (comp) __syncthreads();
@@ -311,6 +332,70 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __
             }
         }
     }
+}
+
+// F_m of the two real sequences of a job from the length-n DFT held in buf, m = 0..lmax:
+//   Xa[k] = (Z[k] + conj Z[n-k]) / 2, Xb[k] = (Z[k] - conj Z[n-k]) / (2i), F_m = X[m mod n] e^{-i m phi0}.
+// BR = false: buf[PADI(k)] = conj Z[k] (transform done as conj(idft(conj z))); BR = true: buf holds Z[k] at the
+// bit-reversed position of k (forward DIF transform of a power-of-two ring).
+template <bool SH>
+__device__ __forceinline__ void ring_unpack_F(const PlanDev& P, const RingJob& job, const double2* buf, int n, bool br,
+                                              double2* __restrict__ Fm)
+{
+    const int L = P.lmax, nm = L + 1, lg = 31 - __clz(n);
+    double2* FA = Fm + ((int64_t)job.compA * P.nring + job.ringA) * nm;
+    double2* FB = job.ringB >= 0 ? Fm + ((int64_t)job.compB * P.nring + job.ringB) * nm : nullptr;
+    const bool same_phase = job.ringB < 0 || job.ringB == job.ringA ||
+                            (P.ring_phq[job.ringB] == P.ring_phq[job.ringA] && P.ring_phden[job.ringB] == P.ring_phden[job.ringA]);
+    double2 pa = ring_phase(P, job.ringA, threadIdx.x), pb = same_phase ? pa : ring_phase(P, job.ringB, threadIdx.x);
+    const double2 stepa = ring_phase(P, job.ringA, RF_NT), stepb = same_phase ? stepa : ring_phase(P, job.ringB, RF_NT);
+    for (int m = threadIdx.x; m <= L; m += RF_NT) {
+        const int k = m % n, kk = (n - k) % n;
+        double2 z1, z2c;
+        if (br) {
+            const double2 c1 = buf[PADI((int)(__brev((unsigned)k) >> (32 - lg)))], c2 = buf[PADI((int)(__brev((unsigned)kk) >> (32 - lg)))];
+            z1 = c1; z2c = make_double2(c2.x, -c2.y);
+        } else {
+            const double2 c1 = buf[PADI(k)], c2 = buf[PADI(kk)];
+            z1 = make_double2(c1.x, -c1.y); z2c = c2;
+        }
+        const double2 xa = make_double2(0.5 * (z1.x + z2c.x), 0.5 * (z1.y + z2c.y));
+        const double2 d = csub(z1, z2c);
+        const double2 xb = make_double2(0.5 * d.y, -0.5 * d.x);
+        if (SH) {
+            Fm[fm_ring_index<true>(P, job.compA, job.ringA, m)] = cmulc(xa, pa);
+            if (FB) Fm[fm_ring_index<true>(P, job.compB, job.ringB, m)] = cmulc(xb, pb);
+        } else {
+            FA[m] = cmulc(xa, pa);
+            if (FB) FB[m] = cmulc(xb, pb);
+        }
+        pa = cmul(pa, stepa);
+        pb = cmul(pb, stepb);
+    }
+}
+
+template <bool SH>
+__global__ void __launch_bounds__(RF_NT, 2)
+ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __restrict__ Fm, double* __restrict__ mapQ,
+                  double* __restrict__ mapU, const int* __restrict__ skip, int64_t f_stride, int64_t map_stride,
+                  const int* __restrict__ mmax)
+{
+    if (skip && *skip) return;
+    extern __shared__ double2 smem[];
+    // batched use (blockIdx.y = transform index): spectra at Fm + y f_stride hold m <= mmax[y] only, maps at + y map_stride
+    Fm += blockIdx.y * f_stride;
+    mapQ += blockIdx.y * map_stride;
+    mapU += blockIdx.y * map_stride;
+    const int L = P.lmax, nm = L + 1, mtop = mmax ? min(mmax[blockIdx.y], L) : L;
+    const RingJob job = jobs[blockIdx.x];
+    const int n = P.ring_nphi[job.ringA], bsi = P.ring_bs[job.ringA];
+    double2* twq = smem;
+    double2* st = twq + (P.tw_n >> 2) + 1;   // one component of the phased ring spectrum at a time (rings with n <= lmax)
+    double2* buf = st + nm;
+    load_twq(P, twq);
+    const double2* chirp = bsi >= 0 ? P.bs_tab + P.bs[bsi].chirp_off : nullptr;
+    const int M = bsi >= 0 ? P.bs[bsi].M : n;
+    ring_build_Z<SH>(P, job, Fm, mtop, st, buf, n, bsi, M, chirp);
     ring_idft(P, buf, twq, n, bsi);
     double* oa = (job.compA ? mapU : mapQ) + ring_first_pixel<SH>(P, job.ringA);
     double* ob = job.ringB >= 0 ? (job.compB ? mapU : mapQ) + ring_first_pixel<SH>(P, job.ringB) : nullptr;
@@ -329,7 +414,6 @@ ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double* __re
 {
     if (skip && *skip) return;
     extern __shared__ double2 smem[];
-    const int L = P.lmax, nm = L + 1;
     const RingJob job = jobs[blockIdx.x];
     const int n = P.ring_nphi[job.ringA], bsi = P.ring_bs[job.ringA];
     double2* twq = smem;
@@ -356,29 +440,53 @@ ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double* __re
         for (int k = threadIdx.x; k < n; k += RF_NT) buf[PADI(k)] = cmul(buf[PADI(k)], __ldg(&chirp[k]));
         __syncthreads();
     }
-    double2* FA = Fm + ((int64_t)job.compA * P.nring + job.ringA) * nm;
-    double2* FB = job.ringB >= 0 ? Fm + ((int64_t)job.compB * P.nring + job.ringB) * nm : nullptr;
-    const bool same_phase = job.ringB == job.ringA ||
-                            (job.ringB >= 0 && P.ring_phq[job.ringB] == P.ring_phq[job.ringA] && P.ring_phden[job.ringB] == P.ring_phden[job.ringA]);
-    double2 pa = ring_phase(P, job.ringA, threadIdx.x), pb = same_phase ? pa : ring_phase(P, job.ringB, threadIdx.x);
-    const double2 stepa = ring_phase(P, job.ringA, RF_NT), stepb = same_phase ? stepa : ring_phase(P, job.ringB, RF_NT);
-    for (int m = threadIdx.x; m <= L; m += RF_NT) {
-        const int k = m % n, kk = (n - k) % n;
-        const double2 c1 = buf[PADI(k)], c2 = buf[PADI(kk)];
-        const double2 z1 = make_double2(c1.x, -c1.y);  // Z[k]
-        const double2 z2c = c2;                         // conj Z[n-k]
-        const double2 xa = make_double2(0.5 * (z1.x + z2c.x), 0.5 * (z1.y + z2c.y));
-        const double2 d = csub(z1, z2c);
-        const double2 xb = make_double2(0.5 * d.y, -0.5 * d.x);
-        if (SH) {
-            Fm[fm_ring_index<true>(P, job.compA, job.ringA, m)] = cmulc(xa, pa);
-            if (FB) Fm[fm_ring_index<true>(P, job.compB, job.ringB, m)] = cmulc(xb, pb);
-        } else {
-            FA[m] = cmulc(xa, pa);
-            if (FB) FB[m] = cmulc(xb, pb);
+    ring_unpack_F<SH>(P, job, buf, n, false, Fm);
+}
+
+// Ring stage of the PCG mat-vec A^T N^-1 A in ONE kernel: F_m(ring) -> pixels of the ring (kept in shared memory) ->
+// times the pixel weights -> F'_m(ring), written over F_m.  Equivalent to ring_synth_kernel + ring_anal_kernel(pixw)
+// without the map round trip through global memory, the second table load and the second launch.
+template <bool SH>
+__global__ void __launch_bounds__(RF_NT, 2)
+ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, double2* __restrict__ Fm, const double* __restrict__ pixw,
+                  const int* __restrict__ skip)
+{
+    if (skip && *skip) return;
+    extern __shared__ double2 smem[];
+    const int L = P.lmax, nm = L + 1;
+    const RingJob job = jobs[blockIdx.x];
+    const int n = P.ring_nphi[job.ringA], bsi = P.ring_bs[job.ringA];
+    double2* twq = smem;
+    double2* st = twq + (P.tw_n >> 2) + 1;
+    double2* buf = st + nm;
+    load_twq(P, twq);
+    const double2* chirp = bsi >= 0 ? P.bs_tab + P.bs[bsi].chirp_off : nullptr;
+    const int M = bsi >= 0 ? P.bs[bsi].M : n;
+    const double* wa = pixw + ring_first_pixel<SH>(P, job.ringA);
+    const double* wb = job.ringB >= 0 ? pixw + ring_first_pixel<SH>(P, job.ringB) : wa;
+    ring_build_Z<SH>(P, job, Fm, L, st, buf, n, bsi, M, chirp);
+    ring_idft(P, buf, twq, n, bsi);
+    if (bsi < 0) {
+        // pixels z_j = a_j + i b_j in natural order -> weighted -> forward DIF transform (bit-reversed output)
+        for (int j = threadIdx.x; j < n; j += RF_NT) {
+            const double2 z = buf[PADI(j)];
+            buf[PADI(j)] = make_double2(z.x * wa[j], z.y * wb[j]);
         }
-        pa = cmul(pa, stepa);
-        pb = cmul(pb, stepb);
+        __syncthreads();
+        fft_dif<false>(buf, n, twq, P.tw_n, nullptr);
+        ring_unpack_F<SH>(P, job, buf, n, true, Fm);
+    } else {
+        // Bluestein both ways: Z = conj(idft(conj z)); the chirp of the synthesis output and of the analysis input fuse
+        for (int j = threadIdx.x; j < M; j += RF_NT) {
+            if (j >= n) { buf[PADI(j)] = make_double2(0.0, 0.0); continue; }
+            const double2 c = __ldg(&chirp[j]);
+            const double2 z = cmul(buf[PADI(j)], c);
+            buf[PADI(j)] = cmul(make_double2(z.x * wa[j], -z.y * wb[j]), c);
+        }
+        ring_idft(P, buf, twq, n, bsi);
+        for (int k = threadIdx.x; k < n; k += RF_NT) buf[PADI(k)] = cmul(buf[PADI(k)], __ldg(&chirp[k]));
+        __syncthreads();
+        ring_unpack_F<SH>(P, job, buf, n, false, Fm);
     }
 }
 
@@ -624,6 +732,8 @@ int gs_ring_setup(gs_plan* p)
     GS_CHECK_CUDA(cudaFuncSetAttribute(ring_anal_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GS_CHECK_CUDA(cudaFuncSetAttribute(ring_synth_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GS_CHECK_CUDA(cudaFuncSetAttribute(ring_anal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GS_CHECK_CUDA(cudaFuncSetAttribute(ring_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GS_CHECK_CUDA(cudaFuncSetAttribute(ring_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GS_CHECK_CUDA(cudaFuncSetAttribute(ring_synth_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GS_CHECK_CUDA(cudaFuncSetAttribute(ring_anal_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GS_CHECK_CUDA(cudaFuncSetAttribute(ring_synth_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -730,6 +840,25 @@ int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, c
         else ring_anal_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, mapQ, mu, pixw, F, skip);
         GS_CHECK_LAUNCH();
     }
+    g_gs_launches += 1;
+    return GS_OK;
+}
+
+// ring stage of A^T diag(pixw) A on the ring spectra in place; falls back to synthesis + weighted analysis through the
+// plan's scratch maps when some rings take the split path
+int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, const int* skip)
+{
+    const int nj = spin == 0 ? p->njobs0 : p->njobs2, ns = spin == 0 ? p->nsjobs0 : p->nsjobs2;
+    if (ns > 0 || !pixw) {
+        int rc = gs_ring_synth(p, spin, p->mapQ_tmp, p->mapU_tmp, st, skip);
+        if (rc) return rc;
+        return gs_ring_anal(p, spin, p->mapQ_tmp, p->mapU_tmp, pixw, st, skip);
+    }
+    if (nj <= 0) return GS_OK;
+    const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
+    if (p->world > 1) ring_apply_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, p->Fx, pixw, skip);
+    else ring_apply_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, p->Fm, pixw, skip);
+    GS_CHECK_LAUNCH();
     g_gs_launches += 1;
     return GS_OK;
 }

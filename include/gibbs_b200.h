@@ -350,12 +350,17 @@ int gs_shard_allreduce_sum(gs_plan* plan, double* buf, int n, void* stream);
 /* ---- measurement helpers used by bench.py ------------------------------------------------ */
 /* Number of kernels this library has launched so far in the SHT stages and PCG vector updates. */
 long long gs_launch_count(void);
-/* Average duration (ms, CUDA events on `stream`) of the four kernels of one PCG mat-vec
+/* Average duration (ms, CUDA events on `stream`) of the kernels of one PCG mat-vec
  * y = B A^T N^-1 A B x: ms_out[0] Legendre synthesis, [1] ring synthesis, [2] ring analysis,
- * [3] Legendre analysis + finish.  Synchronous. */
+ * [3] Legendre analysis + finish.  With the fused ring stage (the default, see gs_set_ring_fused)
+ * ms_out[1] is the single ring kernel (synthesis -> N^-1 -> analysis per ring) and ms_out[2] = 0.  Synchronous. */
 int gs_profile_matvec(gs_plan* plan, const double* x_E, const double* x_B, const double* bl,
                       const double* inv_noise, double* y_E, double* y_B, int nrep, float* ms_out,
                       void* stream);
+/* Ring stage of the PCG mat-vec (opfilt_pp.fwd_op's alm2map_spin -> N^-1 -> map2alm_spin, CenteredGibbs.py:629,653):
+ * fused != 0 (default): one kernel per mat-vec keeps each ring's pixels in shared memory; 0: ring synthesis to the
+ * plan's scratch maps, then weighted ring analysis.  Same result to rounding.  Returns the previous setting. */
+int gs_set_ring_fused(int fused);
 /* FP64 FMA throughput of the current device in TFLOP/s (DFMA microkernel; the roofline
  * denominator of the Legendre kernels).  Synchronous. */
 int gs_measure_fp64_peak(double* tflops_out, void* stream);
