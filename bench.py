@@ -155,6 +155,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is ONE process that owns the host, so give the
+    # OpenMP oracle every core (the library reads the variable when it is first loaded, below)
+    if "TORCHELASTIC_RUN_ID" in os.environ or os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     nside, lmax = args.nside, args.lmax
     n_pcg = args.pcg_iters or PCG_ITERS.get(nside) or 300
     t_pairs = []

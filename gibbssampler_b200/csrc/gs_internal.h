@@ -131,6 +131,10 @@ struct gs_plan {
     int njobs2;
     RingJob* jobs0;  // spin 0: (north, south) ring of each pair
     int njobs0;
+    int2* groups2;   // CTA work list: (first job, 1 | 2 | 4 jobs of equal transform length) over jobs2 / jobs0
+    int ngroups2;
+    int2* groups0;
+    int ngroups0;
     SplitJob* sjobs2;   // rings of the spin-2 / spin-0 lists that take the split path (empty below nside 2048)
     int nsjobs2;
     SplitJob* sjobs0;

@@ -223,6 +223,8 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
     p->d.nside = nside;
     p->d.lmax = lmax;
     p->jobs0 = p->jobs2 = nullptr;
+    p->groups0 = p->groups2 = nullptr;
+    p->ngroups0 = p->ngroups2 = 0;
     p->sjobs0 = p->sjobs2 = nullptr;
     p->nsjobs0 = p->nsjobs2 = 0;
     p->ring_scratch = nullptr;

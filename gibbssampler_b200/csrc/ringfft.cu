@@ -77,10 +77,11 @@ __device__ __forceinline__ double2 w8c(int a)
 // radix-16 pass over sub-transforms of size N (N >= 16).  INV = false: DIF (forward), true: DIT (inverse).
 // POST (DIF only): outputs are multiplied by post[position].
 template <bool INV, bool POST>
-__device__ __forceinline__ void pass16(double2* buf, int M, int N, const double2* twq, int twn, const double2* __restrict__ post)
+__device__ __forceinline__ void pass16(double2* buf, int M, int N, const double2* twq, int twn, const double2* __restrict__ post,
+                                       int tid, int nt)
 {
     const int s = N >> 4, ls = 31 - __clz(s), ts = twn / N, quarter = twn >> 2, ng = M >> 4;
-    for (int t = threadIdx.x; t < ng; t += RF_NT) {
+    for (int t = tid; t < ng; t += nt) {
         const int g = t >> ls, j = t & (s - 1), i0 = g * N + j;
         double2 x[16];
 #pragma unroll
@@ -115,10 +116,10 @@ __device__ __forceinline__ void pass16(double2* buf, int M, int N, const double2
 
 // radix-4 pass over sub-transforms of size N (N >= 4)
 template <bool INV>
-__device__ __forceinline__ void pass4(double2* buf, int M, int N, const double2* twq, int twn)
+__device__ __forceinline__ void pass4(double2* buf, int M, int N, const double2* twq, int twn, int tid, int nt)
 {
     const int q = N >> 2, lq = 31 - __clz(q), ts = twn / N, quarter = twn >> 2, nq = M >> 2;
-    for (int t = threadIdx.x; t < nq; t += RF_NT) {
+    for (int t = tid; t < nq; t += nt) {
         const int g = t >> lq, j = t & (q - 1), i0 = g * N + j;
         double2 a0 = buf[PADI(i0)], a1 = buf[PADI(i0 + q)], a2 = buf[PADI(i0 + 2 * q)], a3 = buf[PADI(i0 + 3 * q)];
         const double2 w1 = twq[j * ts], w2 = tw_get(twq, 2 * j * ts, quarter);
@@ -130,10 +131,10 @@ __device__ __forceinline__ void pass4(double2* buf, int M, int N, const double2*
 
 // radix-2 pass over sub-transforms of size N (N >= 2)
 template <bool INV>
-__device__ __forceinline__ void pass2(double2* buf, int M, int N, const double2* twq, int twn)
+__device__ __forceinline__ void pass2(double2* buf, int M, int N, const double2* twq, int twn, int tid, int nt)
 {
     const int h = N >> 1, lh = 31 - __clz(h), ts = twn / N;
-    for (int t = threadIdx.x; t < (M >> 1); t += RF_NT) {
+    for (int t = tid; t < (M >> 1); t += nt) {
         const int g = t >> lh, j = t & (h - 1), i0 = g * N + j;
         const double2 a = buf[PADI(i0)], b = buf[PADI(i0 + h)];
         const double2 w = tw_get(twq, j * ts, twn >> 2);
@@ -145,29 +146,32 @@ __device__ __forceinline__ void pass2(double2* buf, int M, int N, const double2*
 
 // In-place forward DIF FFT (kernel exp(-2 pi i jk/M)), natural order in, bit-reversed order out;
 // POST: the bit-reversed-order output is multiplied by post[] inside the last pass (needs M >= 16).
+// (tid, nt): index and number of the threads working on THIS transform (a CTA may run several transforms of
+// equal length side by side, see RingGroup); every barrier is CTA-wide.
 template <bool POST>
-__device__ void fft_dif(double2* buf, int M, const double2* twq, int twn, const double2* __restrict__ post)
+__device__ void fft_dif(double2* buf, int M, const double2* twq, int twn, const double2* __restrict__ post, int tid = threadIdx.x,
+                        int nt = RF_NT)
 {
     const int lg = 31 - __clz(M), r = lg & 3;
     int N = M;
-    if (r & 1) { pass2<false>(buf, M, N, twq, twn); N >>= 1; }
-    if (r & 2) { pass4<false>(buf, M, N, twq, twn); N >>= 2; }
+    if (r & 1) { pass2<false>(buf, M, N, twq, twn, tid, nt); N >>= 1; }
+    if (r & 2) { pass4<false>(buf, M, N, twq, twn, tid, nt); N >>= 2; }
     while (N >= 16) {
-        if (POST && N == 16) pass16<false, true>(buf, M, N, twq, twn, post);
-        else pass16<false, false>(buf, M, N, twq, twn, post);
+        if (POST && N == 16) pass16<false, true>(buf, M, N, twq, twn, post, tid, nt);
+        else pass16<false, false>(buf, M, N, twq, twn, post, tid, nt);
         N >>= 4;
     }
 }
 
 // In-place inverse DIT FFT (kernel exp(+2 pi i jk/M), unnormalised), bit-reversed in, natural out.
-__device__ void fft_dit_inv(double2* buf, int M, const double2* twq, int twn)
+__device__ void fft_dit_inv(double2* buf, int M, const double2* twq, int twn, int tid = threadIdx.x, int nt = RF_NT)
 {
     const int lg = 31 - __clz(M), r = lg & 3;
     const int Ntop = M >> r;  // largest radix-16 sub-transform size
-    for (int N = 16; N <= Ntop; N <<= 4) pass16<true, false>(buf, M, N, twq, twn, nullptr);
+    for (int N = 16; N <= Ntop; N <<= 4) pass16<true, false>(buf, M, N, twq, twn, nullptr, tid, nt);
     int N = Ntop;
-    if (r & 2) { N <<= 2; pass4<true>(buf, M, N, twq, twn); }
-    if (r & 1) { N <<= 1; pass2<true>(buf, M, N, twq, twn); }
+    if (r & 2) { N <<= 2; pass4<true>(buf, M, N, twq, twn, tid, nt); }
+    if (r & 1) { N <<= 1; pass2<true>(buf, M, N, twq, twn, tid, nt); }
 }
 
 __device__ __forceinline__ void load_twq(const PlanDev& P, double2* twq)
@@ -189,13 +193,13 @@ __device__ __forceinline__ double2 chirp_val(int t, int n)
 // Otherwise (Bluestein): the caller stored Z_k * chirp[k] at k < n and zeros at n <= k < M; the result
 // still has to be multiplied by chirp[j] by the caller (fused into its output pass).
 // All threads of the CTA must call; begins and ends with a barrier.
-__device__ void ring_idft(const PlanDev& P, double2* buf, const double2* twq, int n, int bsi)
+__device__ void ring_idft(const PlanDev& P, double2* buf, const double2* twq, int n, int bsi, int tid = threadIdx.x, int nt = RF_NT)
 {
     __syncthreads();
-    if (bsi < 0) { fft_dit_inv(buf, n, twq, P.tw_n); return; }
+    if (bsi < 0) { fft_dit_inv(buf, n, twq, P.tw_n, tid, nt); return; }
     const BluesteinDesc d = P.bs[bsi];
-    fft_dif<true>(buf, d.M, twq, P.tw_n, P.bs_tab + d.bhat_off);
-    fft_dit_inv(buf, d.M, twq, P.tw_n);
+    fft_dif<true>(buf, d.M, twq, P.tw_n, P.bs_tab + d.bhat_off, tid, nt);
+    fft_dit_inv(buf, d.M, twq, P.tw_n, tid, nt);
 }
 
 __global__ void __launch_bounds__(RF_NT) bluestein_setup_kernel(PlanDev P, double2* tab, int nbs)
@@ -245,111 +249,183 @@ __device__ __forceinline__ int64_t ring_first_pixel(const PlanDev& P, int ring)
     return SH ? P.sh.ring_start_loc[ring] : P.ring_start[ring];
 }
 
+// A CTA of the direct ring kernels works on a GROUP of 1, 2 or 4 jobs whose transforms have the same length M and
+// the same kind (power of two / Bluestein), RF_NT / nsub threads each, side by side in shared memory: the passes of a
+// short transform cannot keep 256 threads busy (M / 16 radix-16 butterflies per pass) and the ring stage is latency
+// bound, so running equal-length rings together is what fills the CTA.  Control flow (number of passes and barriers)
+// depends on (M, kind) only, so it is uniform over the CTA.
+struct RingSub {
+    RingJob job;
+    int n, bsi, M, tid, nt;
+    double2* buf;
+    double2* scratch;
+    const double2* chirp;
+};
+
+__device__ __forceinline__ RingSub ring_sub(const PlanDev& P, const RingJob* __restrict__ jobs, const int2* __restrict__ groups,
+                                            double2* bufs)
+{
+    const int2 g = groups[blockIdx.x];   // (first job, nsub)
+    RingSub S;
+    S.nt = RF_NT / g.y;
+    const int sub = threadIdx.x / S.nt;
+    S.tid = threadIdx.x - sub * S.nt;
+    S.job = jobs[g.x + sub];
+    S.n = P.ring_nphi[S.job.ringA];
+    S.bsi = P.ring_bs[S.job.ringA];
+    S.M = S.bsi >= 0 ? P.bs[S.bsi].M : S.n;
+    S.chirp = S.bsi >= 0 ? P.bs_tab + P.bs[S.bsi].chirp_off : nullptr;
+    S.buf = bufs + sub * (S.M + (S.M >> 4) + 2);
+    S.scratch = bufs + g.y * (S.M + (S.M >> 4) + 2) + sub * S.nt;   // used by rings shorter than nt only (M <= 2 nt)
+    return S;
+}
+
 // Z[k] = Xa[k] + i Xb[k], X[k] = G[k] + conj G[n-k], G[k] = sum_{m = k mod n} w_m F_m e^{i m phi0} (alias fold), for the two
 // real sequences of a job, written to buf ready for ring_idft: bit-reversed (power-of-two n) or chirp-multiplied and
-// zero-padded (Bluestein).  F_m is taken as zero for m > mtop.
-//  * n > lmax (every belt ring and the longer cap rings): each k aliases at most one m on either side, so the
-//    spectrum is read straight from global memory, both components in one sweep (e^{i (n-k) phi0} = e^{i n phi0}
-//    conj e^{i k phi0}, phases by recurrence over the thread's k).
-//  * shorter rings: the phased spectrum is staged in st[0..lmax] one component at a time and folded from there.
-// All threads of the CTA must call; the caller synchronises before the transform (ring_idft does).
-template <bool SH>
-__device__ __forceinline__ void ring_build_Z(const PlanDev& P, const RingJob& job, const double2* __restrict__ Fm, int mtop,
-                                             double2* st, double2* buf, int n, int bsi, int M, const double2* __restrict__ chirp)
+// zero-padded (Bluestein).  F_m is taken as zero for m > mtop.  The spectrum is read straight from global memory, both
+// components in one sweep; the phases follow from e^{i k phi0} (recurrence over the thread's k) and q = e^{i n phi0}:
+// e^{i (k + j n) phi0} = e^{i k phi0} q^j, e^{i (n - k + j n) phi0} = conj(e^{i k phi0}) q^(j+1).
+// Partial alias sums for UK values of k (k0 + u ks, u < UK) over the alias terms j = j0, j0 + js, ... < nterm:
+//   z[u] += sum_j w e^{i (k + j n) phi0} (Fa + i Fb)[k + j n] + w conj(e^{i (kk + j n) phi0}) (conj Fa + i conj Fb)[kk + j n],
+// kk = n - k (0 for k = 0).  4 UK UJ independent global loads are in flight per step.
+template <bool SH, int UK, int UJ>
+__device__ __forceinline__ void ring_fold(const PlanDev& P, const RingJob& job, const double2* __restrict__ Fm, const double2* __restrict__ FA,
+                                          const double2* __restrict__ FB, int n, int mtop, int nterm, int k0, int ks, int j0, int js,
+                                          double2 pk0, double2 step, double2 q, double2 (&z)[UK])
 {
-    const int L = P.lmax, nm = L + 1, lg = 31 - __clz(n);
-    const bool same_phase = job.ringB < 0 || job.ringB == job.ringA ||
-                            (P.ring_phq[job.ringB] == P.ring_phq[job.ringA] && P.ring_phden[job.ringB] == P.ring_phden[job.ringA]);
-    if (n > L) {
-        const double2* FA = Fm + ((int64_t)job.compA * P.nring + job.ringA) * nm;
-        const double2* FB = job.ringB >= 0 ? Fm + ((int64_t)job.compB * P.nring + job.ringB) * nm : nullptr;
-        double2 pa = ring_phase(P, job.ringA, threadIdx.x);
-        const double2 stepa = ring_phase(P, job.ringA, RF_NT), phna = ring_phase(P, job.ringA, n);
-        double2 pb = pa, stepb = stepa, phnb = phna;
-        if (!same_phase) { pb = ring_phase(P, job.ringB, threadIdx.x); stepb = ring_phase(P, job.ringB, RF_NT); phnb = ring_phase(P, job.ringB, n); }
-        for (int k = threadIdx.x; k < M; k += RF_NT) {
-            const int pos = PADI(bsi < 0 ? (int)(__brev((unsigned)k) >> (32 - lg)) : k);
-            if (k >= n) { buf[pos] = make_double2(0.0, 0.0); continue; }
-            const int kk = k ? n - k : 0;
-            const double wk = k ? 1.0 : 0.5;   // (2 - delta_m0) / 2; kk = 0 only when k = 0
-            double2 fa = make_double2(0.0, 0.0), fa2 = fa, fb = fa, fb2 = fa;
-            if (k <= mtop) {
-                fa = SH ? Fm[fm_ring_index<true>(P, job.compA, job.ringA, k)] : FA[k];
-                if (job.ringB >= 0) fb = SH ? Fm[fm_ring_index<true>(P, job.compB, job.ringB, k)] : FB[k];
+    // pk0 = e^{i k0 phi0}, step = e^{i ks phi0}, q = e^{i n phi0}: the phases of the first alias term follow by
+    // multiplication when j0 = 0 (e^{i (n - k) phi0} = q conj e^{i k phi0}); one sincospi pair per k otherwise.
+    const double2 zero = make_double2(0.0, 0.0);
+    const bool hasB = job.ringB >= 0;
+    const double2 qs = js == 1 ? q : ring_phase(P, job.ringA, js * n), qsc = make_double2(qs.x, -qs.y);
+    double2 e1[UK], e2[UK];
+#pragma unroll
+    for (int u = 0; u < UK; ++u) {
+        const int k = k0 + u * ks;
+        z[u] = zero;
+        if (j0 == 0) {
+            e1[u] = u ? cmul(e1[u - 1], step) : pk0;
+            e2[u] = k ? cmulc(e1[u], q) : make_double2(1.0, 0.0);     // conj(q conj e1)
+        } else {
+            e1[u] = e2[u] = zero;
+            if (k < n) {
+                e1[u] = ring_phase(P, job.ringA, k + j0 * n);
+                const double2 t = ring_phase(P, job.ringA, (k ? n - k : 0) + j0 * n);
+                e2[u] = make_double2(t.x, -t.y);
             }
-            if (kk <= mtop) {
-                fa2 = SH ? Fm[fm_ring_index<true>(P, job.compA, job.ringA, kk)] : FA[kk];
-                if (job.ringB >= 0) fb2 = SH ? Fm[fm_ring_index<true>(P, job.compB, job.ringB, kk)] : FB[kk];
-            }
-            const double2 pka = make_double2(pa.x * wk, pa.y * wk), pkb = make_double2(pb.x * wk, pb.y * wk);
-            const double2 qa = k ? cmulc(phna, pa) : make_double2(0.5, 0.0), qb = k ? cmulc(phnb, pb) : make_double2(0.5, 0.0);
-            const double2 ga = cmul(fa, pka), ha = cmul(fa2, qa), gb = cmul(fb, pkb), hb = cmul(fb2, qb);
-            const double2 xa = make_double2(ga.x + ha.x, ga.y - ha.y), xb = make_double2(gb.x + hb.x, gb.y - hb.y);
-            double2 z = make_double2(xa.x - xb.y, xa.y + xb.x);   // Xa + i Xb
-            if (bsi >= 0) z = cmul(z, __ldg(&chirp[k]));
-            buf[pos] = z;
-            pa = cmul(pa, stepa);
-            pb = cmul(pb, stepb);
         }
-        return;
     }
-    for (int comp = 0; comp < 2; ++comp) {
-        const int ring = comp ? job.ringB : job.ringA;
-        if (comp) __syncthreads();
-        if (ring >= 0) {
-            const int cc = comp ? job.compB : job.compA;
-            const double2* F = Fm + ((int64_t)cc * P.nring + ring) * nm;
-            // e^{i m phi0} for m = tid, tid + 256, ...: one sincospi, then multiply by e^{i 256 phi0}
-            const int pr = (comp && !same_phase) ? job.ringB : job.ringA;
-            double2 ph = ring_phase(P, pr, threadIdx.x);
-            const double2 step = ring_phase(P, pr, RF_NT);
-            for (int m = threadIdx.x; m <= L; m += RF_NT) {
-                const double w = m ? 1.0 : 0.5;  // (2 - delta_m0) / 2
-                double2 f = make_double2(0.0, 0.0);
-                if (m <= mtop) f = SH ? Fm[fm_ring_index<true>(P, cc, ring, m)] : F[m];
-                st[m] = cmul(f, make_double2(ph.x * w, ph.y * w));
-                ph = cmul(ph, step);
+    for (int jb = j0; jb < nterm; jb += UJ * js) {
+        double2 fa1[UK][UJ], fa2[UK][UJ], fb1[UK][UJ], fb2[UK][UJ];
+#pragma unroll
+        for (int u = 0; u < UK; ++u) {
+            const int k = k0 + u * ks;
+#pragma unroll
+            for (int v = 0; v < UJ; ++v) {
+                const int j = jb + v * js;
+                const int m1 = k + j * n, m2 = (k ? n - k : 0) + j * n;
+                const bool v1 = k < n && m1 <= mtop, v2 = k < n && m2 <= mtop;
+                fa1[u][v] = v1 ? (SH ? Fm[fm_ring_index<true>(P, job.compA, job.ringA, m1)] : FA[m1]) : zero;
+                fa2[u][v] = v2 ? (SH ? Fm[fm_ring_index<true>(P, job.compA, job.ringA, m2)] : FA[m2]) : zero;
+                fb1[u][v] = (hasB && v1) ? (SH ? Fm[fm_ring_index<true>(P, job.compB, job.ringB, m1)] : FB[m1]) : zero;
+                fb2[u][v] = (hasB && v2) ? (SH ? Fm[fm_ring_index<true>(P, job.compB, job.ringB, m2)] : FB[m2]) : zero;
             }
         }
-        __syncthreads();
-        for (int k = threadIdx.x; k < M; k += RF_NT) {
-            const int pos = PADI(bsi < 0 ? (int)(__brev((unsigned)k) >> (32 - lg)) : k);
-            if (k >= n) { if (!comp) buf[pos] = make_double2(0.0, 0.0); continue; }
-            double2 x = make_double2(0.0, 0.0);
-            if (ring >= 0) {
-                const int kk = (n - k) % n;
-                double2 g = make_double2(0.0, 0.0), h = g;
-                for (int m = k; m <= L; m += n) g = cadd(g, st[m]);
-                for (int m = kk; m <= L; m += n) h = cadd(h, st[m]);
-                x = make_double2(g.x + h.x, g.y - h.y);
+#pragma unroll
+        for (int u = 0; u < UK; ++u) {
+            const int k = k0 + u * ks;
+#pragma unroll
+            for (int v = 0; v < UJ; ++v) {
+                const double w = (k + jb + v * js) ? 1.0 : 0.5;   // (2 - delta_m0) / 2: m = 0 only for k = 0, j = 0 (both sums)
+                const double2 t1 = make_double2(fa1[u][v].x - fb1[u][v].y, fa1[u][v].y + fb1[u][v].x);    // Fa + i Fb
+                const double2 t2 = make_double2(fa2[u][v].x + fb2[u][v].y, fb2[u][v].x - fa2[u][v].y);    // conj Fa + i conj Fb
+                z[u] = cadd(z[u], cadd(cmul(t1, make_double2(e1[u].x * w, e1[u].y * w)), cmul(t2, make_double2(e2[u].x * w, e2[u].y * w))));
+                e1[u] = cmul(e1[u], qs);
+                e2[u] = cmul(e2[u], qsc);
             }
-            if (!comp) buf[pos] = x;
-            else {
-                double2 z = buf[pos];
-                z = make_double2(z.x - x.y, z.y + x.x);   // + i Xb
-                if (bsi >= 0) z = cmul(z, __ldg(&chirp[k]));
-                buf[pos] = z;
-            }
+        }
+    }
+}
+
+// Z[k] = Xa[k] + i Xb[k], X[k] = G[k] + conj G[n-k], G[k] = sum_{m = k mod n} w_m F_m e^{i m phi0} (alias fold), for the two
+// real sequences of a job, written to buf ready for ring_idft: bit-reversed (power-of-two n) or chirp-multiplied and
+// zero-padded (Bluestein).  F_m is taken as zero for m > mtop.  Both sequences of a job share phi0 (Q and U of one ring; a
+// ring and its southern mirror by construction, plan.cu).  The spectrum is read straight from global memory with many
+// independent loads in flight (the stage is latency bound): rings at least 4 nt long take 4 values of k per step, shorter
+// ones 4 alias terms per step, and rings shorter than the thread count split the alias terms of each k over nt / n threads
+// and combine the partial sums in a fixed order through `scratch` (nt entries of shared memory).
+// Contains one CTA-wide barrier; all threads of the CTA must call.
+template <bool SH>
+__device__ __forceinline__ void ring_build_Z(const PlanDev& P, const RingSub& S, const double2* __restrict__ Fm, int mtop, double2* scratch)
+{
+    const RingJob& job = S.job;
+    const int L = P.lmax, nm = L + 1, n = S.n, lg = 31 - __clz(n);
+    const double2* FA = Fm + ((int64_t)job.compA * P.nring + job.ringA) * nm;
+    const double2* FB = job.ringB >= 0 ? Fm + ((int64_t)job.compB * P.nring + job.ringB) * nm : nullptr;
+    const int nterm = (mtop + n) / n;   // alias terms m = k + j n <= mtop, j < nterm
+    const double2 zero = make_double2(0.0, 0.0);
+    auto put = [&](int k, double2 v) {
+        if (k >= S.M) return;
+        const int pos = PADI(S.bsi < 0 ? (int)(__brev((unsigned)k) >> (32 - lg)) : k);
+        if (k >= n) v = zero;
+        else if (S.bsi >= 0) v = cmul(v, __ldg(&S.chirp[k]));
+        S.buf[pos] = v;
+    };
+    const bool split = n <= S.nt;
+    const double2 q = ring_phase(P, job.ringA, n);
+    if (split) {
+        const int J = S.nt / n, kq = S.tid % n, jq = S.tid / n;
+        double2 z[1] = {zero};
+        if (jq < J) ring_fold<SH, 1, 4>(P, job, Fm, FA, FB, n, mtop, nterm, kq, 1, jq, J, ring_phase(P, job.ringA, kq), zero, q, z);
+        scratch[S.tid] = z[0];
+    } else if (n >= 4 * S.nt) {
+        double2 pk = ring_phase(P, job.ringA, S.tid);
+        const double2 step = ring_phase(P, job.ringA, S.nt), step4 = ring_phase(P, job.ringA, 4 * S.nt);
+        for (int k0 = S.tid; k0 < n; k0 += 4 * S.nt) {
+            double2 z[4];
+            ring_fold<SH, 4, 1>(P, job, Fm, FA, FB, n, mtop, nterm, k0, S.nt, 0, 1, pk, step, q, z);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) put(k0 + u * S.nt, z[u]);
+            pk = cmul(pk, step4);
+        }
+        for (int k = S.tid + ((n - S.tid + 4 * S.nt - 1) / (4 * S.nt)) * 4 * S.nt; k < S.M; k += S.nt) put(k, zero);   // zero padding
+    } else {
+        double2 pk = ring_phase(P, job.ringA, S.tid);
+        const double2 step = ring_phase(P, job.ringA, S.nt);
+        for (int k0 = S.tid; k0 < n; k0 += S.nt) {
+            double2 z[1];
+            ring_fold<SH, 1, 4>(P, job, Fm, FA, FB, n, mtop, nterm, k0, S.nt, 0, 1, pk, step, q, z);
+            put(k0, z[0]);
+            pk = cmul(pk, step);
+        }
+        for (int k = S.tid + ((n - S.tid + S.nt - 1) / S.nt) * S.nt; k < S.M; k += S.nt) put(k, zero);   // zero padding
+    }
+    __syncthreads();
+    if (split) {
+        const int J = S.nt / n;
+        for (int k = S.tid; k < S.M; k += S.nt) {
+            double2 v = zero;
+            if (k < n) for (int i = 0; i < J; ++i) v = cadd(v, scratch[i * n + k]);
+            put(k, v);
         }
     }
 }
 
 // F_m of the two real sequences of a job from the length-n DFT held in buf, m = 0..lmax:
 //   Xa[k] = (Z[k] + conj Z[n-k]) / 2, Xb[k] = (Z[k] - conj Z[n-k]) / (2i), F_m = X[m mod n] e^{-i m phi0}.
-// BR = false: buf[PADI(k)] = conj Z[k] (transform done as conj(idft(conj z))); BR = true: buf holds Z[k] at the
+// br = false: buf[PADI(k)] = conj Z[k] (transform done as conj(idft(conj z))); br = true: buf holds Z[k] at the
 // bit-reversed position of k (forward DIF transform of a power-of-two ring).
 template <bool SH>
-__device__ __forceinline__ void ring_unpack_F(const PlanDev& P, const RingJob& job, const double2* buf, int n, bool br,
-                                              double2* __restrict__ Fm)
+__device__ __forceinline__ void ring_unpack_F(const PlanDev& P, const RingSub& S, bool br, double2* __restrict__ Fm)
 {
-    const int L = P.lmax, nm = L + 1, lg = 31 - __clz(n);
+    const RingJob& job = S.job;
+    const int L = P.lmax, nm = L + 1, n = S.n, lg = 31 - __clz(n);
+    const double2* buf = S.buf;
     double2* FA = Fm + ((int64_t)job.compA * P.nring + job.ringA) * nm;
     double2* FB = job.ringB >= 0 ? Fm + ((int64_t)job.compB * P.nring + job.ringB) * nm : nullptr;
-    const bool same_phase = job.ringB < 0 || job.ringB == job.ringA ||
-                            (P.ring_phq[job.ringB] == P.ring_phq[job.ringA] && P.ring_phden[job.ringB] == P.ring_phden[job.ringA]);
-    double2 pa = ring_phase(P, job.ringA, threadIdx.x), pb = same_phase ? pa : ring_phase(P, job.ringB, threadIdx.x);
-    const double2 stepa = ring_phase(P, job.ringA, RF_NT), stepb = same_phase ? stepa : ring_phase(P, job.ringB, RF_NT);
-    for (int m = threadIdx.x; m <= L; m += RF_NT) {
+    double2 pa = ring_phase(P, job.ringA, S.tid);   // both sequences of a job share phi0 (plan.cu gives a ring and its mirror the same phase)
+    const double2 stepa = ring_phase(P, job.ringA, S.nt);
+    for (int m = S.tid; m <= L; m += S.nt) {
         const int k = m % n, kk = (n - k) % n;
         double2 z1, z2c;
         if (br) {
@@ -364,21 +440,20 @@ __device__ __forceinline__ void ring_unpack_F(const PlanDev& P, const RingJob& j
         const double2 xb = make_double2(0.5 * d.y, -0.5 * d.x);
         if (SH) {
             Fm[fm_ring_index<true>(P, job.compA, job.ringA, m)] = cmulc(xa, pa);
-            if (FB) Fm[fm_ring_index<true>(P, job.compB, job.ringB, m)] = cmulc(xb, pb);
+            if (FB) Fm[fm_ring_index<true>(P, job.compB, job.ringB, m)] = cmulc(xb, pa);
         } else {
             FA[m] = cmulc(xa, pa);
-            if (FB) FB[m] = cmulc(xb, pb);
+            if (FB) FB[m] = cmulc(xb, pa);
         }
         pa = cmul(pa, stepa);
-        pb = cmul(pb, stepb);
     }
 }
 
 template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
-ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __restrict__ Fm, double* __restrict__ mapQ,
-                  double* __restrict__ mapU, const int* __restrict__ skip, int64_t f_stride, int64_t map_stride,
-                  const int* __restrict__ mmax)
+ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __restrict__ groups, const double2* __restrict__ Fm,
+                  double* __restrict__ mapQ, double* __restrict__ mapU, const int* __restrict__ skip, int64_t f_stride,
+                  int64_t map_stride, const int* __restrict__ mmax)
 {
     if (skip && *skip) return;
     extern __shared__ double2 smem[];
@@ -386,22 +461,17 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __
     Fm += blockIdx.y * f_stride;
     mapQ += blockIdx.y * map_stride;
     mapU += blockIdx.y * map_stride;
-    const int L = P.lmax, nm = L + 1, mtop = mmax ? min(mmax[blockIdx.y], L) : L;
-    const RingJob job = jobs[blockIdx.x];
-    const int n = P.ring_nphi[job.ringA], bsi = P.ring_bs[job.ringA];
+    const int mtop = mmax ? min(mmax[blockIdx.y], P.lmax) : P.lmax;
     double2* twq = smem;
-    double2* st = twq + (P.tw_n >> 2) + 1;   // one component of the phased ring spectrum at a time (rings with n <= lmax)
-    double2* buf = st + nm;
     load_twq(P, twq);
-    const double2* chirp = bsi >= 0 ? P.bs_tab + P.bs[bsi].chirp_off : nullptr;
-    const int M = bsi >= 0 ? P.bs[bsi].M : n;
-    ring_build_Z<SH>(P, job, Fm, mtop, st, buf, n, bsi, M, chirp);
-    ring_idft(P, buf, twq, n, bsi);
-    double* oa = (job.compA ? mapU : mapQ) + ring_first_pixel<SH>(P, job.ringA);
-    double* ob = job.ringB >= 0 ? (job.compB ? mapU : mapQ) + ring_first_pixel<SH>(P, job.ringB) : nullptr;
-    for (int j = threadIdx.x; j < n; j += RF_NT) {
-        double2 z = buf[PADI(j)];
-        if (bsi >= 0) z = cmul(z, __ldg(&chirp[j]));
+    const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
+    ring_build_Z<SH>(P, S, Fm, mtop, S.scratch);
+    ring_idft(P, S.buf, twq, S.n, S.bsi, S.tid, S.nt);
+    double* oa = (S.job.compA ? mapU : mapQ) + ring_first_pixel<SH>(P, S.job.ringA);
+    double* ob = S.job.ringB >= 0 ? (S.job.compB ? mapU : mapQ) + ring_first_pixel<SH>(P, S.job.ringB) : nullptr;
+    for (int j = S.tid; j < S.n; j += S.nt) {
+        double2 z = S.buf[PADI(j)];
+        if (S.bsi >= 0) z = cmul(z, __ldg(&S.chirp[j]));
         oa[j] = z.x;
         if (ob) ob[j] = z.y;
     }
@@ -409,85 +479,93 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double2* __
 
 template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
-ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const double* __restrict__ mapQ, const double* __restrict__ mapU,
-                 const double* __restrict__ pixw, double2* __restrict__ Fm, const int* __restrict__ skip)
+ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __restrict__ groups, const double* __restrict__ mapQ,
+                 const double* __restrict__ mapU, const double* __restrict__ pixw, double2* __restrict__ Fm, const int* __restrict__ skip)
 {
     if (skip && *skip) return;
     extern __shared__ double2 smem[];
-    const RingJob job = jobs[blockIdx.x];
-    const int n = P.ring_nphi[job.ringA], bsi = P.ring_bs[job.ringA];
     double2* twq = smem;
-    double2* buf = twq + (P.tw_n >> 2) + 1;
     load_twq(P, twq);
+    const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
+    const RingJob& job = S.job;
+    const int n = S.n;
     const int64_t sa = ring_first_pixel<SH>(P, job.ringA), sb = job.ringB >= 0 ? ring_first_pixel<SH>(P, job.ringB) : 0;
     const double* ia = (job.compA ? mapU : mapQ) + sa;
     const double* ib = job.ringB >= 0 ? (job.compB ? mapU : mapQ) + sb : nullptr;
     const int lg = 31 - __clz(n);
-    const double2* chirp = bsi >= 0 ? P.bs_tab + P.bs[bsi].chirp_off : nullptr;
-    const int M = bsi >= 0 ? P.bs[bsi].M : n;
     // Z[k] = sum_j z_j exp(-2 pi i jk/n) = conj( idft( conj z ) )
-    for (int j = threadIdx.x; j < M; j += RF_NT) {
-        const int pos = PADI(bsi < 0 ? (int)(__brev((unsigned)j) >> (32 - lg)) : j);
-        if (j >= n) { buf[pos] = make_double2(0.0, 0.0); continue; }
+    for (int j = S.tid; j < S.M; j += S.nt) {
+        const int pos = PADI(S.bsi < 0 ? (int)(__brev((unsigned)j) >> (32 - lg)) : j);
+        if (j >= n) { S.buf[pos] = make_double2(0.0, 0.0); continue; }
         double a = ia[j], b = ib ? ib[j] : 0.0;
         if (pixw) { a *= pixw[sa + j]; if (ib) b *= pixw[sb + j]; }
         double2 z = make_double2(a, -b);
-        if (bsi >= 0) z = cmul(z, __ldg(&chirp[j]));
-        buf[pos] = z;
+        if (S.bsi >= 0) z = cmul(z, __ldg(&S.chirp[j]));
+        S.buf[pos] = z;
     }
-    ring_idft(P, buf, twq, n, bsi);
-    if (bsi >= 0) {  // finish Bluestein in place: every m below reads two entries
-        for (int k = threadIdx.x; k < n; k += RF_NT) buf[PADI(k)] = cmul(buf[PADI(k)], __ldg(&chirp[k]));
+    ring_idft(P, S.buf, twq, n, S.bsi, S.tid, S.nt);
+    if (S.bsi >= 0) {  // finish Bluestein in place: every m below reads two entries
+        for (int k = S.tid; k < n; k += S.nt) S.buf[PADI(k)] = cmul(S.buf[PADI(k)], __ldg(&S.chirp[k]));
         __syncthreads();
     }
-    ring_unpack_F<SH>(P, job, buf, n, false, Fm);
+    ring_unpack_F<SH>(P, S, false, Fm);
 }
 
 // Ring stage of the PCG mat-vec A^T N^-1 A in ONE kernel: F_m(ring) -> pixels of the ring (kept in shared memory) ->
 // times the pixel weights -> F'_m(ring), written over F_m.  Equivalent to ring_synth_kernel + ring_anal_kernel(pixw)
 // without the map round trip through global memory, the second table load and the second launch.
+#ifdef GS_RING_DEBUG
+__device__ unsigned long long g_ring_dbg[4 * 8192];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
+extern "C" int gs_ring_debug_dump(unsigned long long* host, int n) { return (int)cudaMemcpyFromSymbol(host, g_ring_dbg, sizeof(unsigned long long) * n); }
+#define RING_DBG(slot) do { if (threadIdx.x == 0 && blockIdx.x < 8192) g_ring_dbg[4 * blockIdx.x + (slot)] = (slot) == 3 ? ((unsigned long long)smid() << 32 | (unsigned)S.M << 1 | (S.bsi >= 0)) : gtimer(); } while (0)
+#else
+#define RING_DBG(slot) do { } while (0)
+#endif
+
 template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
-ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, double2* __restrict__ Fm, const double* __restrict__ pixw,
-                  const int* __restrict__ skip)
+ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __restrict__ groups, double2* __restrict__ Fm,
+                  const double* __restrict__ pixw, const int* __restrict__ skip)
 {
     if (skip && *skip) return;
     extern __shared__ double2 smem[];
-    const int L = P.lmax, nm = L + 1;
-    const RingJob job = jobs[blockIdx.x];
-    const int n = P.ring_nphi[job.ringA], bsi = P.ring_bs[job.ringA];
     double2* twq = smem;
-    double2* st = twq + (P.tw_n >> 2) + 1;
-    double2* buf = st + nm;
     load_twq(P, twq);
-    const double2* chirp = bsi >= 0 ? P.bs_tab + P.bs[bsi].chirp_off : nullptr;
-    const int M = bsi >= 0 ? P.bs[bsi].M : n;
-    const double* wa = pixw + ring_first_pixel<SH>(P, job.ringA);
-    const double* wb = job.ringB >= 0 ? pixw + ring_first_pixel<SH>(P, job.ringB) : wa;
-    ring_build_Z<SH>(P, job, Fm, L, st, buf, n, bsi, M, chirp);
-    ring_idft(P, buf, twq, n, bsi);
-    if (bsi < 0) {
+    const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
+    const int n = S.n;
+    const double* wa = pixw + ring_first_pixel<SH>(P, S.job.ringA);
+    const double* wb = S.job.ringB >= 0 ? pixw + ring_first_pixel<SH>(P, S.job.ringB) : wa;
+    RING_DBG(0); RING_DBG(3);
+    ring_build_Z<SH>(P, S, Fm, P.lmax, S.scratch);
+    __syncthreads();
+    RING_DBG(1);
+    ring_idft(P, S.buf, twq, n, S.bsi, S.tid, S.nt);
+    if (S.bsi < 0) {
         // pixels z_j = a_j + i b_j in natural order -> weighted -> forward DIF transform (bit-reversed output)
-        for (int j = threadIdx.x; j < n; j += RF_NT) {
-            const double2 z = buf[PADI(j)];
-            buf[PADI(j)] = make_double2(z.x * wa[j], z.y * wb[j]);
+        for (int j = S.tid; j < n; j += S.nt) {
+            const double2 z = S.buf[PADI(j)];
+            S.buf[PADI(j)] = make_double2(z.x * wa[j], z.y * wb[j]);
         }
         __syncthreads();
-        fft_dif<false>(buf, n, twq, P.tw_n, nullptr);
-        ring_unpack_F<SH>(P, job, buf, n, true, Fm);
+        fft_dif<false>(S.buf, n, twq, P.tw_n, nullptr, S.tid, S.nt);
+        ring_unpack_F<SH>(P, S, true, Fm);
     } else {
         // Bluestein both ways: Z = conj(idft(conj z)); the chirp of the synthesis output and of the analysis input fuse
-        for (int j = threadIdx.x; j < M; j += RF_NT) {
-            if (j >= n) { buf[PADI(j)] = make_double2(0.0, 0.0); continue; }
-            const double2 c = __ldg(&chirp[j]);
-            const double2 z = cmul(buf[PADI(j)], c);
-            buf[PADI(j)] = cmul(make_double2(z.x * wa[j], -z.y * wb[j]), c);
+        for (int j = S.tid; j < S.M; j += S.nt) {
+            if (j >= n) { S.buf[PADI(j)] = make_double2(0.0, 0.0); continue; }
+            const double2 c = __ldg(&S.chirp[j]);
+            const double2 z = cmul(S.buf[PADI(j)], c);
+            S.buf[PADI(j)] = cmul(make_double2(z.x * wa[j], -z.y * wb[j]), c);
         }
-        ring_idft(P, buf, twq, n, bsi);
-        for (int k = threadIdx.x; k < n; k += RF_NT) buf[PADI(k)] = cmul(buf[PADI(k)], __ldg(&chirp[k]));
+        ring_idft(P, S.buf, twq, n, S.bsi, S.tid, S.nt);
+        for (int k = S.tid; k < n; k += S.nt) S.buf[PADI(k)] = cmul(S.buf[PADI(k)], __ldg(&S.chirp[k]));
         __syncthreads();
-        ring_unpack_F<SH>(P, job, buf, n, false, Fm);
+        ring_unpack_F<SH>(P, S, false, Fm);
     }
+    __syncthreads();
+    RING_DBG(2);
 }
 
 // ------------------------------------------------------------------ split path (rings longer than one CTA can hold)
@@ -666,11 +744,13 @@ int gs_ring_setup(gs_plan* p)
     const size_t smem_max = 227 * 1024;
     std::vector<int> rn(nring);
     for (int r = 0; r < nring; ++r) { int i = std::min(r + 1, 4 * nside - (r + 1)); rn[r] = i < nside ? 4 * i : 4 * nside; }
-    // direct path: staging (L+1) + transform buffer + quarter twiddle table in one CTA; Mcap = largest
-    // power-of-two transform length for which that fits.  Longer rings take the split path (n/4 per CTA).
-    auto direct_smem = [&](int M, int twn) { return (size_t)((L + 1) + (M + M / 16 + 2) + twn / 4 + 1) * sizeof(double2); };
+    // direct path: transform buffer(s) + quarter twiddle table in one CTA; Mcap = largest power-of-two transform
+    // length taken directly (two CTAs per SM).  Longer rings take the split path (n/4 per CTA).
+    // (+ RF_NT entries: partial alias sums of rings shorter than their thread count, see ring_build_Z)
+    auto direct_smem = [&](int M, int twn) { return (size_t)((M + M / 16 + 8 + RF_NT) + twn / 4 + 1) * sizeof(double2); };
     int Mcap = 4;
-    while (direct_smem(2 * Mcap, 2 * Mcap) <= smem_max) Mcap *= 2;
+    while (2 * direct_smem(2 * Mcap, 2 * Mcap) <= smem_max) Mcap *= 2;
+    (void)L;
     if (const char* e = getenv("GS_RING_MCAP")) {  // test knob: exercise the split path at small nside
         const int v = atoi(e);
         if (v >= 4 && v < Mcap && (v & (v - 1)) == 0) Mcap = v;
@@ -703,7 +783,7 @@ int gs_ring_setup(gs_plan* p)
     for (int r = 0; r < nring; ++r) rbs[r] = (!is_split(r) && n2bs.count(rn[r])) ? n2bs[rn[r]] : -1;
     p->d.max_M = maxM;
     p->d.tw_n = maxM;
-    p->ring_smem = direct_smem(maxMd, maxM);
+    p->ring_smem = direct_smem(std::max(maxMd, std::min(4096, Mcap)), maxM);   // groups of short rings fill up to 4096 points
     p->split_smem = (size_t)((maxMs + maxMs / 16 + 2) + maxM / 4 + 1) * sizeof(double2);
     if (p->ring_smem > smem_max || p->split_smem > smem_max) {
         gs_set_error("ring FFT needs %zu bytes of shared memory (> 227 KB): nside/lmax too large for this build", p->ring_smem);
@@ -764,6 +844,28 @@ int gs_ring_setup(gs_plan* p)
     }
     std::stable_sort(j2.begin(), j2.end(), [&](const RingJob& a, const RingJob& b) { return cost(a.ringA) > cost(b.ringA); });
     std::stable_sort(j0.begin(), j0.end(), [&](const RingJob& a, const RingJob& b) { return cost(a.ringA) > cost(b.ringA); });
+    // groups of 1 / 2 / 4 consecutive jobs with the same transform length and kind share a CTA (see RingGroup in the
+    // kernels): a pass of an M-point transform has M / 16 radix-16 butterflies, RF_NT threads need M >= 4096 alone
+    const int group_points = std::min(4096, Mcap);
+    auto make_groups = [&](const std::vector<RingJob>& jobs) {
+        std::vector<int2> g;
+        size_t i = 0;
+        while (i < jobs.size()) {
+            const int key = cost(jobs[i].ringA);
+            const int M = ring_M(rn[jobs[i].ringA]);
+            size_t e = i;
+            while (e < jobs.size() && cost(jobs[e].ringA) == key) ++e;
+            const int want = std::max(1, std::min(4, group_points / M));
+            while (i < e) {
+                int cnt = (int)std::min<size_t>(want, e - i);
+                if (cnt == 3) cnt = 2;
+                g.push_back(make_int2((int)i, cnt));
+                i += cnt;
+            }
+        }
+        return g;
+    };
+    const std::vector<int2> g2 = make_groups(j2), g0 = make_groups(j0);
     auto put = [&](const void* h, size_t bytes, void** out) -> int {
         void* q = nullptr;
         GS_CHECK_CUDA(cudaMalloc(&q, std::max<size_t>(16, bytes)));
@@ -777,6 +879,9 @@ int gs_ring_setup(gs_plan* p)
     if ((rc = put(j0.data(), j0.size() * sizeof(RingJob), (void**)&p->jobs0))) return rc;
     if ((rc = put(s2.data(), s2.size() * sizeof(SplitJob), (void**)&p->sjobs2))) return rc;
     if ((rc = put(s0.data(), s0.size() * sizeof(SplitJob), (void**)&p->sjobs0))) return rc;
+    if ((rc = put(g2.data(), g2.size() * sizeof(int2), (void**)&p->groups2))) return rc;
+    if ((rc = put(g0.data(), g0.size() * sizeof(int2), (void**)&p->groups0))) return rc;
+    p->ngroups2 = (int)g2.size(); p->ngroups0 = (int)g0.size();
     p->njobs2 = (int)j2.size(); p->njobs0 = (int)j0.size();
     p->nsjobs2 = (int)s2.size(); p->nsjobs0 = (int)s0.size();
     if (so2 || so0) {
@@ -789,8 +894,9 @@ int gs_ring_setup(gs_plan* p)
 
 int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st, const int* skip)
 {
-    const int nj = spin == 0 ? p->njobs0 : p->njobs2, ns = spin == 0 ? p->nsjobs0 : p->nsjobs2;
+    const int nj = spin == 0 ? p->ngroups0 : p->ngroups2, ns = spin == 0 ? p->nsjobs0 : p->nsjobs2;
     const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
+    const int2* grp = spin == 0 ? p->groups0 : p->groups2;
     const SplitJob* sj = spin == 0 ? p->sjobs0 : p->sjobs2;
     double* mu = spin == 0 ? mapQ : mapU;
     const bool sh = p->world > 1;
@@ -807,8 +913,8 @@ int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t
         g_gs_launches += 2;
     }
     if (nj > 0) {
-        if (sh) ring_synth_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, F, mapQ, mu, skip, 0, 0, nullptr);
-        else ring_synth_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, F, mapQ, mu, skip, 0, 0, nullptr);
+        if (sh) ring_synth_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr);
+        else ring_synth_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr);
         GS_CHECK_LAUNCH();
     }
     g_gs_launches += 1;
@@ -818,8 +924,9 @@ int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t
 int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, const double* pixw, cudaStream_t st,
                  const int* skip)
 {
-    const int nj = spin == 0 ? p->njobs0 : p->njobs2, ns = spin == 0 ? p->nsjobs0 : p->nsjobs2;
+    const int nj = spin == 0 ? p->ngroups0 : p->ngroups2, ns = spin == 0 ? p->nsjobs0 : p->nsjobs2;
     const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
+    const int2* grp = spin == 0 ? p->groups0 : p->groups2;
     const SplitJob* sj = spin == 0 ? p->sjobs0 : p->sjobs2;
     const double* mu = spin == 0 ? mapQ : mapU;
     const bool sh = p->world > 1;
@@ -836,8 +943,8 @@ int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, c
         g_gs_launches += 2;
     }
     if (nj > 0) {
-        if (sh) ring_anal_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, mapQ, mu, pixw, F, skip);
-        else ring_anal_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, mapQ, mu, pixw, F, skip);
+        if (sh) ring_anal_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, mapQ, mu, pixw, F, skip);
+        else ring_anal_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, mapQ, mu, pixw, F, skip);
         GS_CHECK_LAUNCH();
     }
     g_gs_launches += 1;
@@ -848,7 +955,7 @@ int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, c
 // plan's scratch maps when some rings take the split path
 int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, const int* skip)
 {
-    const int nj = spin == 0 ? p->njobs0 : p->njobs2, ns = spin == 0 ? p->nsjobs0 : p->nsjobs2;
+    const int nj = spin == 0 ? p->ngroups0 : p->ngroups2, ns = spin == 0 ? p->nsjobs0 : p->nsjobs2;
     if (ns > 0 || !pixw) {
         int rc = gs_ring_synth(p, spin, p->mapQ_tmp, p->mapU_tmp, st, skip);
         if (rc) return rc;
@@ -856,8 +963,9 @@ int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, con
     }
     if (nj <= 0) return GS_OK;
     const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
-    if (p->world > 1) ring_apply_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, p->Fx, pixw, skip);
-    else ring_apply_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, p->Fm, pixw, skip);
+    const int2* grp = spin == 0 ? p->groups0 : p->groups2;
+    if (p->world > 1) ring_apply_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fx, pixw, skip);
+    else ring_apply_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fm, pixw, skip);
     GS_CHECK_LAUNCH();
     g_gs_launches += 1;
     return GS_OK;
@@ -868,8 +976,9 @@ int gs_ring_synth_batch(gs_plan* p, const double2* F, int64_t f_stride, const in
                         int64_t map_stride, int nb, cudaStream_t st)
 {
     if (p->world > 1 || p->nsjobs2 > 0) { gs_set_error("batched ring synthesis needs an unsharded plan without split rings"); return GS_E_BADARG; }
-    if (nb <= 0 || p->njobs2 <= 0) return GS_OK;
-    ring_synth_kernel<false><<<dim3(p->njobs2, nb), RF_NT, p->ring_smem, st>>>(p->d, p->jobs2, F, mapQ, mapU, nullptr, f_stride, map_stride, mmax);
+    if (nb <= 0 || p->ngroups2 <= 0) return GS_OK;
+    ring_synth_kernel<false><<<dim3(p->ngroups2, nb), RF_NT, p->ring_smem, st>>>(p->d, p->jobs2, p->groups2, F, mapQ, mapU, nullptr, f_stride,
+                                                                                 map_stride, mmax);
     GS_CHECK_LAUNCH();
     g_gs_launches += 1;
     return GS_OK;
