@@ -66,8 +66,10 @@ def gauss_beam(fwhm_rad, lmax):
 
 
 def load_mask(mask_path, nside, mask=None):
-    """The reference reads a FITS mask and ud_grades it (ConstrainedRealization.py:33-37).  Here a mask
-    array (RING order, already at `nside`) can be given directly, or a .npy path; FITS needs healpy."""
+    """The reference reads a FITS mask and ud_grades it (ConstrainedRealization.py:33-37, CenteredGibbs.py:266-268):
+    hp.ud_grade(hp.read_map(mask_path), nside).  Same here, with the package's own FITS reader and ud_grade
+    (healpix_io.py; healpy is not a dependency); a mask array (RING order, already at `nside`) or a .npy path is
+    accepted as well."""
     if mask is not None:
         m = to_host(mask).astype(np.float64)
     elif mask_path is None:
@@ -75,11 +77,8 @@ def load_mask(mask_path, nside, mask=None):
     elif str(mask_path).endswith(".npy"):
         m = np.load(mask_path).astype(np.float64)
     else:
-        try:
-            import healpy as hp  # not available in the build container; used when present
-        except ImportError as e:  # pragma: no cover
-            raise _lib.GibbsB200Error("reading a FITS mask needs healpy; pass mask=<array> or a .npy path") from e
-        m = hp.ud_grade(hp.read_map(mask_path), nside)
+        from . import healpix_io
+        m = healpix_io.ud_grade(healpix_io.read_map(mask_path), nside)
     if m.shape != (12 * nside * nside,):
         raise ValueError("mask must have 12 nside^2 = %d RING pixels, got %s" % (12 * nside * nside, m.shape))
     return m

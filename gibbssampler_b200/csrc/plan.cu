@@ -107,7 +107,9 @@ static int build_tables(gs_plan* p)
             omz = 1.0L - z;
             st = sqrtl(omz * (1.0L + z));
             nphi = 4 * nside;
-            q = 2 - ((i - nside + 1) & 1);
+            // HEALPix pix2ang_ring: phi_j = (j - fodd) pi / (2 nside), fodd = 1/2 when (ring + nside) is even, else 1:
+            // half-pixel shift on rings nside, nside + 2, ...; the other belt rings start at phi = 0
+            q = (i - nside + 1) & 1;
             den = 4 * nside;
             start = ncap + (int64_t)(i - nside) * 4 * ns;
         }

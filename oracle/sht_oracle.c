@@ -73,8 +73,11 @@ static void ring_geom(int nside, int i, ring_t *r)
     } else {
         z = 4.0L / 3.0L - 2.0L * north / (3.0L * ns);
         r->nphi = 4 * nside;
+        /* HEALPix pix2ang_ring: phi = (j - fodd) pi / (2 nside), j = 1.., fodd = 1/2 when (ring + nside) is even (the
+         * half-pixel-shifted rings, starting with ring nside) and 1 otherwise: unshifted belt rings START AT phi = 0
+         * (pixel 4 of nside 1 sits at (pi/2, 0)). */
         int s = (north - nside + 1) & 1;
-        r->phi0 = (2 - s) * PI_L / (4.0L * ns);
+        r->phi0 = s * PI_L / (4.0L * ns);
         r->start = ncap + (int64_t)(north - nside) * 4 * ns;
         r->sth = sqrtl((1.0L - z) * (1.0L + z));
     }

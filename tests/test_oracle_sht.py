@@ -160,3 +160,27 @@ def test_alm_helpers():
             assert x[i] == a[i] * fl[l]
     bl = sht.gauss_beam(np.radians(0.5), 512)
     assert bl[0] == 1.0 and abs(bl[512] - np.exp(-0.5 * 512 * 513 * (np.radians(0.5) / 2.3548200450309493) ** 2)) < 1e-15
+
+
+def test_pixel_centres_known_answers():
+    """Pixel positions pinned to healpy facts that do not depend on this repo: the 12 base pixels (hp.pix2ang(1, p)) and
+    the HEALPix rule that belt rings alternate between a half-pixel shift (rings nside, nside + 2, ...) and a start at
+    phi = 0 (pix2ang_ring: phi = (j - fodd) pi / (2 nside)).  tests/test_healpix_io.py adds the NESTED-hierarchy check."""
+    from oracle import sht as O
+    th, ph = O.pix_angles(1)
+    assert np.allclose(np.cos(th), [2 / 3] * 4 + [0] * 4 + [-2 / 3] * 4, atol=1e-15)
+    assert np.allclose(ph, [np.pi / 4 + k * np.pi / 2 for k in range(4)] + [k * np.pi / 2 for k in range(4)]
+                       + [np.pi / 4 + k * np.pi / 2 for k in range(4)], atol=1e-15)
+    th, ph = O.pix_angles(2)
+    # ring 1 (cap, 4 pixels), ring 2 = nside (belt, shifted), ring 3 (belt, starts at 0), ring 4 (equator, shifted)
+    assert np.isclose(ph[0], np.pi / 4) and np.isclose(np.cos(th[0]), 1 - 1 / 12)
+    assert np.isclose(ph[4], np.pi / 8) and np.isclose(np.cos(th[4]), 2 / 3)
+    assert np.isclose(ph[12], 0.0) and np.isclose(np.cos(th[12]), 1 / 3)
+    assert np.isclose(ph[20], np.pi / 8) and abs(np.cos(th[20])) < 1e-15
+    assert np.isclose(ph[28], 0.0) and np.isclose(np.cos(th[28]), -1 / 3)
+    for nside in (4, 8):
+        th, ph = O.pix_angles(nside)
+        ncap = 2 * nside * (nside - 1)
+        first = ph[ncap::4 * nside][:2 * nside + 1]           # first pixel of every belt ring
+        want = np.where(np.arange(2 * nside + 1) % 2 == 0, np.pi / (4 * nside), 0.0)
+        assert np.allclose(first, want, atol=1e-15)
