@@ -133,20 +133,21 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def cpu_pair_seconds(nside, lmax, reps, seed=0):
-    """Seconds per spin-2 SHT pair (alm2map_spin2 + adjoint) of the CPU oracle port on all host cores."""
+def cpu_pair_seconds(nside, lmax, reps, seed=0, min_seconds=0.0):
+    """Seconds per spin-2 SHT pair (alm2map_spin2 + adjoint) of the CPU oracle port on all host cores: median over at least
+    `reps` pairs, continued until `min_seconds` of CPU work have been sampled.  Returns (seconds, threads, pairs timed)."""
     from oracle import sht as O
     rng = np.random.default_rng(seed)
     n = O.nalm(lmax)
     e = rng.standard_normal(n) + 1j * rng.standard_normal(n)
     b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
     ts = []
-    for _ in range(reps):
+    while len(ts) < reps or (sum(ts) < min_seconds and len(ts) < 200):
         t0 = time.perf_counter()
         q, u = O.alm2map_spin2(e, b, nside, lmax, kind="f64")
         O.map2alm_spin2(q, u, nside, lmax, adjoint=True, kind="f64")
         ts.append(time.perf_counter() - t0)
-    return float(np.median(ts)), O._lib("f64").orc_num_threads()
+    return float(np.median(ts)), O._lib("f64").orc_num_threads(), len(ts)
 
 
 def run_reference(args):
@@ -163,7 +164,7 @@ def run_reference(args):
     n_pcg = args.pcg_iters or PCG_ITERS.get(nside) or 300
     t_pairs = []
     for _ in range(args.warmup + args.steps):
-        t, cores = cpu_pair_seconds(nside, lmax, 1)
+        t, cores, _ = cpu_pair_seconds(nside, lmax, 1)
         t_pairs.append(t)
     t_pair = float(np.median(t_pairs[args.warmup:]))
     n_pairs = cpu_pairs_per_iteration(args, n_pcg)
@@ -560,8 +561,7 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        reps = 2 if nside >= 512 else 3
-        t_pair, cores = cpu_pair_seconds(nside, lmax, reps)
+        t_pair, cores, reps = cpu_pair_seconds(nside, lmax, 3, min_seconds=10.0)   # ~10 s of host CPU work
         n_pairs = cpu_pairs_per_iteration(args, n_pcg)
         t_iter = t_pair * n_pairs
         cpu_baseline = {"value": 1.0 / t_iter, "unit": "it/s", "cores": cores, "kind": "port",
