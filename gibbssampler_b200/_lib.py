@@ -95,6 +95,8 @@ SIGNATURES = {
     "gs_profile_matvec": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(C.c_float), _vp]),
     "gs_measure_fp64_peak": (_i, [C.POINTER(_d), _vp]),
     "gs_set_ring_fused": (_i, [_i]),
+    "gs_set_ring_skip": (_i, [_i]),
+    "gs_active_ring_pairs": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
 }
 
 

@@ -148,6 +148,12 @@ struct gs_plan {
     double* mwg_small;   // reduction partials, likelihood pair, per-l filters
     int* mwg_meta;       // bins / block boundaries / per-block mmax / flags (re-uploaded when the blocking changes)
     std::vector<int> mwg_meta_host;
+    // rings / ring pairs that carry a non-zero pixel weight (gs_active_rings_build); use_act = the Legendre and fused
+    // ring kernels launched through gs_leg_synth / gs_leg_anal / gs_ring_apply walk these lists (PCG mat-vec only)
+    unsigned char* act_ring;  // [nring] 1 = some pixel weight of the ring is non-zero
+    int* act_pairs;           // [npair] ascending list of pairs with an active north or south ring
+    int* act_count;           // device int: entries of act_pairs
+    bool use_act;
     // workspace
     double2* Fm;        // [2][nring][lmax+1] ring spectra
     double* partial;    // analysis partial sums [nchunk][nalm][4]
@@ -172,6 +178,7 @@ int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, i
                  cudaStream_t st, const int* skip = nullptr, const double* flB = nullptr);
 int gs_leg_anal(gs_plan* p, int spin, double* almE, double* almB, int layout, const double* fl, double scale,
                 int accumulate, cudaStream_t st, const int* skip = nullptr);
+int gs_active_rings_build(gs_plan* p, const double* pixw, cudaStream_t st);
 // ringfft.cu
 int gs_ring_setup(gs_plan* p);
 int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st, const int* skip = nullptr);

@@ -31,7 +31,15 @@
 #define LEG_RA 4     // ring pairs per thread (analysis); LEG_NT * LEG_RA ring pairs per partial chunk
 #endif
 #ifndef LEG_UA
-#define LEG_UA 1     // unroll of the analysis fast loop
+#define LEG_UA 2     // unroll of the analysis fast loop (two reduce-scatters in flight)
+#endif
+#ifdef LEG_MINB_S     // minimum resident blocks per SM asked of the synthesis kernel (tuning; default: none)
+#define LEG_SYNTH_BOUNDS __launch_bounds__(LEG_NT, LEG_MINB_S)
+#else
+#define LEG_SYNTH_BOUNDS __launch_bounds__(LEG_NT)
+#endif
+#ifndef LEG_FOLD2
+#define LEG_FOLD2 1  // spin-2 analysis: lane-permuted inputs so that the warp reduce-scatter needs one select stage instead of three
 #endif
 #define FULL 0xffffffffu
 constexpr int kUnrollA = LEG_UA;
@@ -229,13 +237,17 @@ __device__ __forceinline__ void synth_acc(SynthAcc<SPIN>& A, double pc, double m
 }
 
 template <int SPIN, int R, bool SH>
-__global__ void __launch_bounds__(LEG_NT)
+__global__ void LEG_SYNTH_BOUNDS
 leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __restrict__ almB, int layout,
                  const double* __restrict__ fl, const double* __restrict__ flB, double2* __restrict__ Fm,
-                 const int* __restrict__ skip)
+                 const int* __restrict__ skip, const int* __restrict__ plist, const int* __restrict__ pcount)
 {
     if (skip && *skip) return;
     static_assert(LEG_TL == LEG_NT, "one staged l per thread");
+    // plist / pcount: compacted list of the ring pairs that carry a non-zero pixel weight (gs_active_rings_build);
+    // the k-th slot of the grid works on pair plist[k], slots beyond the count have nothing to do
+    const int npa = plist ? *pcount : P.npair;
+    if ((int)blockIdx.x * (LEG_NT * R) >= npa) return;
     __shared__ double2 sEb[2][LEG_TL], sBb[2][SPIN ? LEG_TL : 1], sRb[2][LEG_TL];
     const int L = P.lmax, mk = blockIdx.y, m = SH ? P.sh.mlist[mk] : mk, tid = threadIdx.x;
     const int l0 = m > SPIN ? m : SPIN;
@@ -245,14 +257,17 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
 
     RingState<SPIN> st[R];
     SynthAcc<SPIN> acc[R];
+    int pj[R];
     bool any_act = false;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
-        const int p = chunk + j * LEG_NT + tid;
+        const int k = chunk + ((tid >> 5) * R + j) * 32 + (tid & 31);   // warp-major: a warp owns 32 R consecutive pairs, so idle slots fill whole warps
+        const int p = k < npa ? (plist ? plist[k] : k) : -1;
+        pj[j] = p;
         st[j].x = 0.0; st[j].pc = st[j].pp = st[j].mc = st[j].mp = 0.0; st[j].sc = 0;
         acc[j].sqr = acc[j].sqi = acc[j].aqr = acc[j].aqi = 0.0;
         acc[j].sur = acc[j].sui = acc[j].aur = acc[j].aui = 0.0;
-        if (p < P.npair && m <= (SPIN ? P.mlim2[p] : P.mlim0[p])) {
+        if (p >= 0 && m <= (SPIN ? P.mlim2[p] : P.mlim0[p])) {
             st[j].x = P.cth[p];
             seed_ring<SPIN>(P, p, m, st[j].pc, st[j].mc, st[j].sc);
             any_act = true;
@@ -336,8 +351,8 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
     const double sg = ((l0 + m) & 1) ? -1.0 : 1.0;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
-        const int p = chunk + j * LEG_NT + tid;
-        if (p >= P.npair) continue;
+        const int p = pj[j];
+        if (p < 0) continue;
         const int rn = p, rs = P.nring - 1 - p;
         const SynthAcc<SPIN>& a = acc[j];
         const int64_t in = fm_index<SH>(P, 0, rn, m, mk), is = fm_index<SH>(P, 0, rs, m, mk);
@@ -518,6 +533,39 @@ __device__ __forceinline__ void anal_acc(double* o, const AnalIn<SPIN>& G, doubl
     }
 }
 
+#if LEG_FOLD2
+// Spin 2, lane-permuted form.  With X = (k1n, k2s, k3n, k4s) (multiplied by lam^+) and Y = (k1s, k2n, k3s, k4n) (by lam^-),
+//   first-parity l:  Y_c = lam^+ X_c + lam^- Y_c,   other parity:  Y_c = s_c (lam^+ X_c - lam^- Y_c),  s = (+,-,+,-),
+// every slot has the same instruction pattern, so a lane may hold value c = slot ^ pi in slot `slot` for any lane constant pi
+// by permuting its X, Y once.  pi = (lane bit 4, lane bit 3) makes the first two exchange stages of the reduce-scatter
+// (which move half and a quarter of the values) select-free: every lane keeps the low slots and sends the high ones.
+// The sign s_c is applied by the lane that ends up owning the value (anal_sign).
+template <bool FIRST, bool INIT>
+__device__ __forceinline__ void anal_acc2(double* o, const AnalIn<2>& G, double pc, double mc)
+{
+    if (INIT) { o[0] = pc * G.q1r; o[1] = pc * G.q1i; o[2] = pc * G.q2r; o[3] = pc * G.q2i; }
+    else { o[0] = fma(pc, G.q1r, o[0]); o[1] = fma(pc, G.q1i, o[1]); o[2] = fma(pc, G.q2r, o[2]); o[3] = fma(pc, G.q2i, o[3]); }
+    if (FIRST) { o[0] = fma(mc, G.u1r, o[0]); o[1] = fma(mc, G.u1i, o[1]); o[2] = fma(mc, G.u2r, o[2]); o[3] = fma(mc, G.u2i, o[3]); }
+    else { o[0] = fma(-mc, G.u1r, o[0]); o[1] = fma(-mc, G.u1i, o[1]); o[2] = fma(-mc, G.u2r, o[2]); o[3] = fma(-mc, G.u2i, o[3]); }
+}
+
+// v[0..3]: slots of the first l, v[4..7]: of the second.  Returns the full sum of value (h, c) = (lane bit 2, pi) in every
+// lane: 9 SHFL.64, 9 DADD, one select pair.
+__device__ __forceinline__ double warp_fold2(double* v, int lane)
+{
+    v[0] += __shfl_xor_sync(FULL, v[2], 16); v[1] += __shfl_xor_sync(FULL, v[3], 16);
+    v[4] += __shfl_xor_sync(FULL, v[6], 16); v[5] += __shfl_xor_sync(FULL, v[7], 16);
+    v[0] += __shfl_xor_sync(FULL, v[1], 8);
+    v[4] += __shfl_xor_sync(FULL, v[5], 8);
+    const bool h = lane & 4;
+    const double keep = h ? v[4] : v[0], send = h ? v[0] : v[4];
+    double r = keep + __shfl_xor_sync(FULL, send, 4);
+    r += __shfl_xor_sync(FULL, r, 2);
+    r += __shfl_xor_sync(FULL, r, 1);
+    return r;
+}
+#endif
+
 // reduce-scatter of NVAL values over the warp: afterwards lane holds the full sum of value
 // index lane >> (5 - log2(NVAL)); all lanes sharing that index hold the same number.
 template <int NVAL>
@@ -559,14 +607,36 @@ __device__ __forceinline__ double warp_fold(double* v, int lane)
     }
 }
 
+template <int SPIN, bool FIRST, bool INIT>
+__device__ __forceinline__ void anal_acc_sel(double* o, const AnalIn<SPIN>& G, double pc, double mc)
+{
+#if LEG_FOLD2
+    if constexpr (SPIN == 2) { anal_acc2<FIRST, INIT>(o, G, pc, mc); return; }
+#endif
+    anal_acc<SPIN, FIRST, INIT>(o, G, pc, mc);
+}
+template <int SPIN, int NVAL>
+__device__ __forceinline__ double anal_fold_sel(double* v, int lane)
+{
+#if LEG_FOLD2
+    if constexpr (SPIN == 2) return warp_fold2(v, lane);
+#endif
+    return warp_fold<NVAL>(v, lane);
+}
+#define ANAL_ACC(FIRST, INIT, o, G, pc, mc) anal_acc_sel<SPIN, FIRST, INIT>(o, G, pc, mc)
+#define ANAL_FOLD(v, lane) anal_fold_sel<SPIN, NVAL>(v, lane)
+
 #ifndef LEG_MINB_A
-#define LEG_MINB_A 1
+#define LEG_MINB_A 3   // 3 CTAs per SM: caps the unrolled fast loop at 168 registers
 #endif
 template <int SPIN, int R, bool SH>
 __global__ void __launch_bounds__(LEG_NT, LEG_MINB_A)
-leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ partial, const int* __restrict__ skip)
+leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ partial, const int* __restrict__ skip,
+                const int* __restrict__ plist, const int* __restrict__ pcount)
 {
     if (skip && *skip) return;
+    const int npa = plist ? *pcount : P.npair;   // see leg_synth_kernel; leg_finish_kernel sums the chunks below the count only
+    if ((int)blockIdx.x * (LEG_NT * R) >= npa) return;
     constexpr int NV = SPIN ? 4 : 2;   // doubles per (l,m)
     constexpr int NVAL = 2 * NV;       // values reduced per pair of l
     __shared__ double2 sR[LEG_TL];
@@ -585,11 +655,12 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
     bool any_act = false;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
-        const int p = chunk + j * LEG_NT + tid;
+        const int k = chunk + ((tid >> 5) * R + j) * 32 + (tid & 31);   // warp-major: a warp owns 32 R consecutive pairs, so idle slots fill whole warps
+        const int p = k < npa ? (plist ? plist[k] : k) : -1;
         st[j].x = 0.0; st[j].pc = st[j].pp = st[j].mc = st[j].mp = 0.0; st[j].sc = 0;
         G[j].q1r = G[j].q1i = G[j].q2r = G[j].q2i = 0.0;
         G[j].u1r = G[j].u1i = G[j].u2r = G[j].u2i = 0.0;
-        if (p < P.npair && m <= (SPIN ? P.mlim2[p] : P.mlim0[p])) {
+        if (p >= 0 && m <= (SPIN ? P.mlim2[p] : P.mlim0[p])) {
             st[j].x = P.cth[p];
             seed_ring<SPIN>(P, p, m, st[j].pc, st[j].mc, st[j].sc);
             any_act = true;
@@ -607,11 +678,32 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
                 G[j].q1r = qn.x - un.y; G[j].q1i = qn.x + un.y; G[j].q2r = qn.y + un.x; G[j].q2i = qn.y - un.x;
                 G[j].u1r = sg * (qs.x - us.y); G[j].u1i = sg * (qs.x + us.y);
                 G[j].u2r = sg * (qs.y + us.x); G[j].u2i = sg * (qs.y - us.x);
+#if LEG_FOLD2
+                {   // (q1r,q1i,q2r,q2i) <- X = (k1n, k2s, k3n, k4s), (u1r,u1i,u2r,u2i) <- Y = (k1s, k2n, k3s, k4n), then slot = c ^ pi
+                    double t = G[j].q1i; G[j].q1i = G[j].u1i; G[j].u1i = t;
+                    t = G[j].q2i; G[j].q2i = G[j].u2i; G[j].u2i = t;
+                    if (lane & 16) {
+                        t = G[j].q1r; G[j].q1r = G[j].q2r; G[j].q2r = t;  t = G[j].q1i; G[j].q1i = G[j].q2i; G[j].q2i = t;
+                        t = G[j].u1r; G[j].u1r = G[j].u2r; G[j].u2r = t;  t = G[j].u1i; G[j].u1i = G[j].u2i; G[j].u2i = t;
+                    }
+                    if (lane & 8) {
+                        t = G[j].q1r; G[j].q1r = G[j].q1i; G[j].q1i = t;  t = G[j].q2r; G[j].q2r = G[j].q2i; G[j].q2i = t;
+                        t = G[j].u1r; G[j].u1r = G[j].u1i; G[j].u1i = t;  t = G[j].u2r; G[j].u2r = G[j].u2i; G[j].u2i = t;
+                    }
+                }
+#endif
             }
         }
     }
     const bool warp_act = __any_sync(FULL, any_act);
+#if LEG_FOLD2
+    // spin 2: the lane ends up owning (h, c) = (bit 2, (bit 4, bit 3)); odd c of the second l carries a minus sign
+    const int vidx = SPIN ? ((lane & 4) | ((lane >> 3) & 3)) : lane >> 3;
+    const bool flip = SPIN && (lane & 4) && (lane & 8);
+#else
     const int vidx = lane >> (SPIN ? 2 : 3);           // value index this lane ends up owning
+    const bool flip = false;
+#endif
     const bool writer = (lane & (SPIN ? 3 : 7)) == 0;
 
     for (int lt = l0; lt <= L; lt += LEG_TL) {
@@ -657,14 +749,14 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
                     const double pc = st[j].sc ? 0.0 : st[j].pc, mc = st[j].sc ? 0.0 : st[j].mc;
-                    if (h == 0) { if (j == 0) anal_acc<SPIN, true, true>(v, G[j], pc, mc); else anal_acc<SPIN, true, false>(v, G[j], pc, mc); }
-                    else { if (j == 0) anal_acc<SPIN, false, true>(v + NV, G[j], pc, mc); else anal_acc<SPIN, false, false>(v + NV, G[j], pc, mc); }
+                    if (h == 0) { if (j == 0) ANAL_ACC(true, true, v, G[j], pc, mc); else ANAL_ACC(true, false, v, G[j], pc, mc); }
+                    else { if (j == 0) ANAL_ACC(false, true, v + NV, G[j], pc, mc); else ANAL_ACC(false, false, v + NV, G[j], pc, mc); }
                     rec_step<SPIN>(st[j], r.x, r.y);
                     rescale_check<SPIN>(st[j]);
                 }
             }
-            const double s = warp_fold<NVAL>(v, lane);
-            if (writer) myPart[ip * NVAL + vidx] = s;
+            const double s = ANAL_FOLD(v, lane);
+            if (writer) myPart[ip * NVAL + vidx] = flip ? -s : s;
             ++ip;
         }
 #pragma unroll kUnrollA
@@ -673,15 +765,15 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
             const double2 r0 = sR[2 * ip], r1 = sR[2 * ip + 1];
 #pragma unroll
             for (int j = 0; j < R; ++j) {
-                if (j == 0) anal_acc<SPIN, true, true>(v, G[j], st[j].pc, st[j].mc);
-                else anal_acc<SPIN, true, false>(v, G[j], st[j].pc, st[j].mc);
+                if (j == 0) ANAL_ACC(true, true, v, G[j], st[j].pc, st[j].mc);
+                else ANAL_ACC(true, false, v, G[j], st[j].pc, st[j].mc);
                 rec_step<SPIN>(st[j], r0.x, r0.y);
-                if (j == 0) anal_acc<SPIN, false, true>(v + NV, G[j], st[j].pc, st[j].mc);
-                else anal_acc<SPIN, false, false>(v + NV, G[j], st[j].pc, st[j].mc);
+                if (j == 0) ANAL_ACC(false, true, v + NV, G[j], st[j].pc, st[j].mc);
+                else ANAL_ACC(false, false, v + NV, G[j], st[j].pc, st[j].mc);
                 rec_step<SPIN>(st[j], r1.x, r1.y);
             }
-            const double s = warp_fold<NVAL>(v, lane);
-            if (writer) myPart[ip * NVAL + vidx] = s;
+            const double s = ANAL_FOLD(v, lane);
+            if (writer) myPart[ip * NVAL + vidx] = flip ? -s : s;
         }
         __syncthreads();
         // sum over the warps of the block, one deterministic partial per chunk
@@ -698,9 +790,10 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
 template <int SPIN, bool SH>
 __global__ void leg_finish_kernel(PlanDev P, const double* __restrict__ partial, int nchunk, double* __restrict__ almE,
                                   double* __restrict__ almB, int layout, const double* __restrict__ fl, double scale,
-                                  int accumulate, const int* __restrict__ skip)
+                                  int accumulate, const int* __restrict__ skip, const int* __restrict__ pcount, int chunk_pairs)
 {
     if (skip && *skip) return;
+    if (pcount) nchunk = (*pcount + chunk_pairs - 1) / chunk_pairs;   // chunks beyond the active pairs were not written
     constexpr int NV = SPIN ? 4 : 2;
     const int L = P.lmax, mk = blockIdx.y, m = SH ? P.sh.mlist[mk] : mk;
     const int l = m + blockIdx.x * blockDim.x + threadIdx.x;
@@ -752,6 +845,57 @@ __global__ void leg_finish_kernel(PlanDev P, const double* __restrict__ partial,
     }
 }
 
+// ------------------------------------------------------------------ active rings of a pixel-weight map
+// In the PCG mat-vec A^T N^-1 A the rings whose N^-1 vanishes identically (inside a galactic mask) contribute exactly
+// nothing: their synthesis is multiplied by zero and their analysis input is zero.  gs_active_rings_build marks the rings
+// that carry weight and compacts the ring PAIRS with at least one such ring into an ascending list, all on the device
+// (no host round trip); the Legendre kernels then walk that list and the fused ring stage drops the CTAs of idle rings.
+__global__ void __launch_bounds__(256) ring_active_kernel(PlanDev P, const double* __restrict__ pixw, unsigned char* __restrict__ act)
+{
+    const int ring = blockIdx.x, n = P.ring_nphi[ring];
+    const double* w = pixw + P.ring_start[ring];
+    int any = 0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) any |= (w[j] != 0.0);
+    any = __syncthreads_or(any);
+    if (threadIdx.x == 0) act[ring] = any ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(1024) pair_compact_kernel(PlanDev P, unsigned char* act, int* __restrict__ list,
+                                                            int* __restrict__ count)
+{
+    __shared__ int wsum[32];
+    __shared__ int base;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) base = 0;
+    __syncthreads();
+    for (int p0 = 0; p0 < P.npair; p0 += 1024) {
+        const int p = p0 + tid;
+        const bool on = p < P.npair && (act[p] || act[P.nring - 1 - p]);
+        const unsigned b = __ballot_sync(FULL, on);
+        if (lane == 0) wsum[w] = __popc(b);
+        __syncthreads();
+        int off = base;
+        for (int i = 0; i < w; ++i) off += wsum[i];
+        if (on) list[off + __popc(b & ((1u << lane) - 1u))] = p;
+        // the ring stage must still process (to zero) an idle ring whose mirror ring carries weight: mark pairs, not rings
+        if (p < P.npair) { act[p] = on; act[P.nring - 1 - p] = on; }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int i = 0; i < 32; ++i) t += wsum[i]; base += t; }
+        __syncthreads();
+    }
+    if (tid == 0) *count = base;
+}
+
+int gs_active_rings_build(gs_plan* p, const double* pixw, cudaStream_t st)
+{
+    if (p->world > 1) { gs_set_error("active-ring lists need an unsharded plan"); return GS_E_BADARG; }
+    ring_active_kernel<<<p->d.nring, 256, 0, st>>>(p->d, pixw, p->act_ring);
+    pair_compact_kernel<<<1, 1024, 0, st>>>(p->d, p->act_ring, p->act_pairs, p->act_count);
+    GS_CHECK_LAUNCH();
+    g_gs_launches += 2;
+    return GS_OK;
+}
+
 // ------------------------------------------------------------------ host launchers
 int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, int layout, const double* fl,
                  cudaStream_t st, const int* skip, const double* flB)
@@ -759,12 +903,14 @@ int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, i
     const bool sh = p->world > 1;
     if (sh && layout != GS_ALM_REAL) { gs_set_error("sharded plans take the (local) real alm layout only"); return GS_E_BADARG; }
     dim3 grid((p->d.npair + LEG_NT * LEG_R - 1) / (LEG_NT * LEG_R), sh ? p->d.sh.nm_loc : p->d.lmax + 1);
+    const int* plist = (p->use_act && !sh) ? p->act_pairs : nullptr;
+    const int* pcount = plist ? p->act_count : nullptr;
     if (!sh) {
-        if (spin == 0) leg_synth_kernel<0, LEG_R, false><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip);
-        else leg_synth_kernel<2, LEG_R, false><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip);
+        if (spin == 0) leg_synth_kernel<0, LEG_R, false><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount);
+        else leg_synth_kernel<2, LEG_R, false><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount);
     } else {
-        if (spin == 0) leg_synth_kernel<0, LEG_R, true><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip);
-        else leg_synth_kernel<2, LEG_R, true><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip);
+        if (spin == 0) leg_synth_kernel<0, LEG_R, true><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount);
+        else leg_synth_kernel<2, LEG_R, true><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount);
     }
     GS_CHECK_LAUNCH();
     g_gs_launches += 1;
@@ -783,29 +929,31 @@ int gs_leg_anal(gs_plan* p, int spin, double* almE, double* almB, int layout, co
     const int nmy = sh ? p->d.sh.nm_loc : p->d.lmax + 1;
     dim3 grid(nchunk, nmy);
     dim3 fgrid((p->d.lmax + 256) / 256, nmy);
+    const int* plist = (p->use_act && !sh) ? p->act_pairs : nullptr;
+    const int* pcount = plist ? p->act_count : nullptr;
     if (sh) {  // ring-sharded (p->Fx, written by the ring analysis) -> m-sharded
         int rc = gs_shard_exchange(p, p->Fx, p->Fm, st);
         if (rc) return rc;
     }
     if (!sh) {
         if (spin == 0) {
-            leg_anal_kernel<0, LEG_RA, false><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip);
+            leg_anal_kernel<0, LEG_RA, false><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount);
             GS_CHECK_LAUNCH();
-            leg_finish_kernel<0, false><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip);
+            leg_finish_kernel<0, false><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, LEG_NT * LEG_RA);
         } else {
-            leg_anal_kernel<2, LEG_RA, false><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip);
+            leg_anal_kernel<2, LEG_RA, false><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount);
             GS_CHECK_LAUNCH();
-            leg_finish_kernel<2, false><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip);
+            leg_finish_kernel<2, false><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, LEG_NT * LEG_RA);
         }
     } else {
         if (spin == 0) {
-            leg_anal_kernel<0, LEG_RA, true><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip);
+            leg_anal_kernel<0, LEG_RA, true><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount);
             GS_CHECK_LAUNCH();
-            leg_finish_kernel<0, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip);
+            leg_finish_kernel<0, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, LEG_NT * LEG_RA);
         } else {
-            leg_anal_kernel<2, LEG_RA, true><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip);
+            leg_anal_kernel<2, LEG_RA, true><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount);
             GS_CHECK_LAUNCH();
-            leg_finish_kernel<2, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip);
+            leg_finish_kernel<2, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, LEG_NT * LEG_RA);
         }
     }
     GS_CHECK_LAUNCH();

@@ -230,6 +230,10 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
     p->sjobs0 = p->sjobs2 = nullptr;
     p->nsjobs0 = p->nsjobs2 = 0;
     p->ring_scratch = nullptr;
+    p->act_ring = nullptr;
+    p->act_pairs = nullptr;
+    p->act_count = nullptr;
+    p->use_act = false;
     p->mwg_F = nullptr;
     p->mwg_maps = nullptr;
     p->mwg_group = 0;
@@ -259,6 +263,9 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
         p->anal_chunks = (p->d.npair + 127) / 128;
         const size_t nalm_part = world > 1 ? (size_t)p->d.sh.nalm_loc : (size_t)p->d.nalm;
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->anal_chunks * nalm_part * 4, &p->partial);
+        if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->d.nring, &p->act_ring);
+        if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->d.npair, &p->act_pairs);
+        if (rc == GS_OK) rc = dev_alloc(p, (size_t)1, &p->act_count);
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->npix_loc, &p->mapQ_tmp);
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->npix_loc, &p->mapU_tmp);
         const size_t nre = (size_t)p->nreal_loc;  // big enough for either layout

@@ -527,9 +527,18 @@ extern "C" int gs_ring_debug_dump(unsigned long long* host, int n) { return (int
 template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
 ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __restrict__ groups, double2* __restrict__ Fm,
-                  const double* __restrict__ pixw, const int* __restrict__ skip)
+                  const double* __restrict__ pixw, const int* __restrict__ skip, const unsigned char* __restrict__ ract)
 {
     if (skip && *skip) return;
+    if (ract) {   // a group whose rings all have zero weight maps to zero: nobody reads its spectra (gs_active_rings_build)
+        const int2 g = groups[blockIdx.x];
+        bool any = false;
+        for (int s = 0; s < g.y; ++s) {
+            const RingJob jb = jobs[g.x + s];
+            any = any || ract[jb.ringA] || (jb.ringB >= 0 && ract[jb.ringB]);
+        }
+        if (!any) return;
+    }
     extern __shared__ double2 smem[];
     double2* twq = smem;
     load_twq(P, twq);
@@ -964,8 +973,8 @@ int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, con
     if (nj <= 0) return GS_OK;
     const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
     const int2* grp = spin == 0 ? p->groups0 : p->groups2;
-    if (p->world > 1) ring_apply_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fx, pixw, skip);
-    else ring_apply_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fm, pixw, skip);
+    if (p->world > 1) ring_apply_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fx, pixw, skip, nullptr);
+    else ring_apply_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fm, pixw, skip, p->use_act ? p->act_ring : nullptr);
     GS_CHECK_LAUNCH();
     g_gs_launches += 1;
     return GS_OK;

@@ -257,6 +257,25 @@ static gs_pcg_ws* get_ws(gs_plan* p)
 int g_gs_ring_fused = 1;
 extern "C" int gs_set_ring_fused(int fused) { const int old = g_gs_ring_fused; g_gs_ring_fused = fused ? 1 : 0; return old; }
 
+// Rings whose N^-1 is identically zero (inside the mask) add nothing to A^T N^-1 A: the mat-vec walks the rings that carry
+// weight only (gs_active_rings_build; lists rebuilt from the weight map of each solve, on the device).
+int g_gs_ring_skip = 1;
+extern "C" int gs_set_ring_skip(int on) { const int old = g_gs_ring_skip; g_gs_ring_skip = on ? 1 : 0; return old; }
+
+struct ActiveRings {   // scope guard: the plan's launchers use the active lists while one of these lives
+    gs_plan* p;
+    bool on;
+    ActiveRings(gs_plan* p_) : p(p_), on(false) {}
+    int begin(const double* pixw, cudaStream_t st)
+    {
+        if (!g_gs_ring_skip || p->world > 1 || !pixw) return GS_OK;
+        int rc = gs_active_rings_build(p, pixw, st);
+        if (rc == GS_OK) { p->use_act = true; on = true; }
+        return rc;
+    }
+    ~ActiveRings() { if (on) p->use_act = false; }
+};
+
 // q = B A^T N^-1 A B v   (C^-1 v is added by pcg_apq_kernel / the caller)
 static int apply_noise_op(gs_plan* p, const double* vE, const double* vB, const double* bl, const double* inv_noise,
                           double* qE, double* qB, cudaStream_t st, const int* skip, int spin = 2)
@@ -300,6 +319,8 @@ static int cr_pcg_impl(gs_plan* p, int spin, const double* dl_EE, const double* 
     if (nc == 2 && (rc = gs_plan_expand_per_l(p, tmp_l + 2 * (L + 1), 0, w->invc[1], st))) return rc;
     if (nc == 2 && (rc = gs_plan_expand_per_l(p, tmp_l + 3 * (L + 1), 0, w->pre[1], st))) return rc;
     const bool dist = p->world > 1;
+    ActiveRings act(p);
+    if ((rc = act.begin(inv_noise, st))) return rc;
 
     PcgState h;
     memset(&h, 0, sizeof(h));
@@ -388,6 +409,8 @@ extern "C" int gs_cr_apply_q_tt(gs_plan* p, const double* dl_TT, const double* b
     gs_pcg_ws* w = get_ws(p);
     if (!w) return GS_E_NOMEM;
     int rc;
+    ActiveRings act(p);
+    if ((rc = act.begin(inv_noise, st))) return rc;
     if ((rc = gs_plan_expand_per_l(p, dl_TT, 2, w->invc[0], st))) return rc;
     if ((rc = apply_noise_op(p, x, nullptr, bl, inv_noise, w->q[0], nullptr, st, nullptr, 0))) return rc;
     axy_kernel<<<SV_GRID, SV_NT, 0, st>>>(w->q[0], w->invc[0], x, y, p->nreal_loc);
@@ -438,6 +461,8 @@ extern "C" int gs_cr_apply_q_pol(gs_plan* p, const double* dl_EE, const double* 
     const int L = p->d.lmax;
     const int64_t n = p->nreal_loc;
     int rc;
+    ActiveRings act(p);
+    if ((rc = act.begin(inv_noise, st))) return rc;
     if ((rc = gs_plan_expand_per_l(p, dl_EE, 2, w->invc[0], st))) return rc;
     if ((rc = gs_plan_expand_per_l(p, dl_BB, 2, w->invc[1], st))) return rc;
     if ((rc = apply_noise_op(p, x_E, x_B, bl, inv_noise, w->q[0], w->q[1], st, nullptr))) return rc;
@@ -509,6 +534,8 @@ extern "C" int gs_profile_matvec(gs_plan* p, const double* x_E, const double* x_
     for (int i = 0; i < 5; ++i) GS_CHECK_CUDA(cudaEventCreate(&ev[i]));
     double acc[4] = {0, 0, 0, 0};
     int rc = GS_OK;
+    ActiveRings act(p);   // as in the PCG: rings without weight are skipped unless gs_set_ring_skip(0)
+    if ((rc = act.begin(inv_noise, st))) return rc;
     for (int r = 0; r < nrep && rc == GS_OK; ++r) {
         cudaEventRecord(ev[0], st);
         rc = gs_leg_synth(p, 2, x_E, x_B, GS_ALM_REAL, bl, st);
@@ -569,5 +596,15 @@ extern "C" int gs_measure_fp64_peak(double* tflops_out, void* stream)
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     *tflops_out = best;
+    return GS_OK;
+}
+
+extern "C" int gs_active_ring_pairs(gs_plan* p, int* active_out, int* total_out)
+{
+    if (!p) { gs_set_error("null plan"); return GS_E_BADARG; }
+    GS_REQUIRE(active_out && total_out, "null output");
+    GS_CHECK_CUDA(cudaSetDevice(p->device));
+    GS_CHECK_CUDA(cudaMemcpy(active_out, p->act_count, sizeof(int), cudaMemcpyDeviceToHost));
+    *total_out = p->d.npair;
     return GS_OK;
 }

@@ -361,6 +361,14 @@ int gs_profile_matvec(gs_plan* plan, const double* x_E, const double* x_B, const
  * fused != 0 (default): one kernel per mat-vec keeps each ring's pixels in shared memory; 0: ring synthesis to the
  * plan's scratch maps, then weighted ring analysis.  Same result to rounding.  Returns the previous setting. */
 int gs_set_ring_fused(int fused);
+/* Rings whose pixel weights N^-1 vanish identically (inside a mask) contribute exactly nothing to A^T N^-1 A.  on != 0
+ * (default): gs_cr_pcg_* / gs_cr_apply_q_* / gs_profile_matvec mark those rings from the weight map they are given (two
+ * small kernels per call, no host round trip) and the Legendre and ring kernels of the mat-vec leave them out; 0: every
+ * ring is processed.  Same result up to the rounding of a re-associated sum.  Unsharded plans only (sharded plans always
+ * process every ring).  Returns the previous setting. */
+int gs_set_ring_skip(int on);
+/* Number of ring pairs (north/south) with a non-zero weight found by the last such call on this plan, and the total. */
+int gs_active_ring_pairs(gs_plan* plan, int* active_out, int* total_out);
 /* FP64 FMA throughput of the current device in TFLOP/s (DFMA microkernel; the roofline
  * denominator of the Legendre kernels).  Synchronous. */
 int gs_measure_fp64_peak(double* tflops_out, void* stream);
