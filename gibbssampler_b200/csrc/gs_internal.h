@@ -92,9 +92,12 @@ struct PlanDev {
     const double* s2;    // sin^2(theta/2)
     const int* mlim0;    // last m with a non-negligible lambda_lm on this ring pair (spin 0)
     const int* mlim2;    // same for spin 2
+    const int* pmin0;    // [lmax+1] first pair p with mlim0[p] >= m (npair when none)
+    const int* pmin2;    // same for spin 2
     // per-m seed factors
     const ScaledSeed* seed0;  // (-1)^m prod sqrt((2k-1)/2k) sqrt((2m+1)/4pi)
     const ScaledSeed* seed2;  // ... * sqrt(m(m-1)/((m+1)(m+2)))  (m >= 2)
+    const ScaledSeed* sinpow; // [lmax+1][npair] sin(theta_pair)^m as mant 2^ex (built on the device at plan creation)
     // recurrence tables indexed like healpy alm: idx(l,m) = m(2L+1-m)/2 + l
     const double* rec0;   // a_l (spin 0)
     const double* alpha0; // alpha_l (spin 0)
@@ -153,6 +156,7 @@ struct gs_plan {
     unsigned char* act_ring;  // [nring] 1 = some pixel weight of the ring is non-zero
     int* act_pairs;           // [npair] ascending list of pairs with an active north or south ring
     int* act_count;           // device int: entries of act_pairs
+    int* act_slot0;           // [2][lmax+1] (spin 0, spin 2): first entry of act_pairs whose pair reaches m
     bool use_act;
     // workspace
     double2* Fm;        // [2][nring][lmax+1] ring spectra
@@ -179,6 +183,7 @@ int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, i
 int gs_leg_anal(gs_plan* p, int spin, double* almE, double* almB, int layout, const double* fl, double scale,
                 int accumulate, cudaStream_t st, const int* skip = nullptr);
 int gs_active_rings_build(gs_plan* p, const double* pixw, cudaStream_t st);
+int gs_leg_build_sinpow(gs_plan* p);
 // ringfft.cu
 int gs_ring_setup(gs_plan* p);
 int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st, const int* skip = nullptr);

@@ -21,9 +21,11 @@
 
 #include "gs_internal.h"
 
+#ifndef LEG_NT
 #define LEG_NT 128   // threads per block
+#endif
 #define LEG_NW (LEG_NT / 32)
-#define LEG_TL 128   // l-tile (even)
+#define LEG_TL LEG_NT   // l-tile (even): one staged l per thread
 #ifndef LEG_R
 #define LEG_R 2      // ring pairs per thread (synthesis)
 #endif
@@ -68,6 +70,36 @@ __device__ __forceinline__ void pow_scaled(double x, int n, double& mant, int& e
     mant = r; ex = er;
 }
 
+// sin(theta_p)^m = mant 2^ex from the plan's table (built once by sinpow_build_kernel with pow_scaled: the binary
+// exponentiation is a serial chain of ~2 log2(m) dependent multiplications that used to open every (pair, m) thread)
+__device__ __forceinline__ void load_sinpow(const PlanDev& P, int p, int m, double& mant, int& ex)
+{
+    const double2 raw = __ldg(reinterpret_cast<const double2*>(P.sinpow) + (int64_t)m * P.npair + p);
+    mant = raw.x;
+    ex = __double2loint(raw.y);
+}
+
+__global__ void __launch_bounds__(256) sinpow_build_kernel(PlanDev P, ScaledSeed* __restrict__ tab)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x, m = blockIdx.y;
+    if (p >= P.npair) return;
+    ScaledSeed s;
+    pow_scaled(P.sth[p], m, s.mant, s.ex);
+    s.pad = 0;
+    tab[(int64_t)m * P.npair + p] = s;
+}
+
+int gs_leg_build_sinpow(gs_plan* p)
+{
+    void* d = nullptr;
+    GS_CHECK_CUDA(cudaMalloc(&d, (size_t)(p->d.lmax + 1) * p->d.npair * sizeof(ScaledSeed)));
+    p->owned.push_back(d);
+    sinpow_build_kernel<<<dim3((p->d.npair + 255) / 256, p->d.lmax + 1), 256>>>(p->d, (ScaledSeed*)d);
+    GS_CHECK_LAUNCH();
+    p->d.sinpow = (const ScaledSeed*)d;
+    return GS_OK;
+}
+
 // Seeds of the recurrence at l0 = max(m, SPIN) for one ring: vp = mu^+ (m' = -2, or the spin-0
 // chain), vm = mu^- (m' = +2), common scale sc.
 template <int SPIN>
@@ -77,13 +109,13 @@ __device__ __forceinline__ void seed_ring(const PlanDev& P, int p, int m, double
     double mant; int ex;
     double fp, fm;  // plain factors multiplying mant * 2^ex
     if (SPIN == 0) {
-        pow_scaled(sth, m, mant, ex);
+        load_sinpow(P, p, m, mant, ex);
         ScaledSeed s = P.seed0[m];
         mant *= s.mant; ex += s.ex; fp = 1.0; fm = 0.0;
     } else {
         const double c2 = P.c2[p], s2 = P.s2[p];
         if (m >= 2) {
-            pow_scaled(sth, m, mant, ex);
+            load_sinpow(P, p, m, mant, ex);
             ScaledSeed s = P.seed2[m];
             mant *= s.mant; ex += s.ex;
             fp = s2 / c2; fm = c2 / s2;
@@ -240,16 +272,19 @@ template <int SPIN, int R, bool SH>
 __global__ void LEG_SYNTH_BOUNDS
 leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __restrict__ almB, int layout,
                  const double* __restrict__ fl, const double* __restrict__ flB, double2* __restrict__ Fm,
-                 const int* __restrict__ skip, const int* __restrict__ plist, const int* __restrict__ pcount)
+                 const int* __restrict__ skip, const int* __restrict__ plist, const int* __restrict__ pcount,
+                 const int* __restrict__ slot0)
 {
     if (skip && *skip) return;
     static_assert(LEG_TL == LEG_NT, "one staged l per thread");
-    // plist / pcount: compacted list of the ring pairs that carry a non-zero pixel weight (gs_active_rings_build);
-    // the k-th slot of the grid works on pair plist[k], slots beyond the count have nothing to do
-    const int npa = plist ? *pcount : P.npair;
-    if ((int)blockIdx.x * (LEG_NT * R) >= npa) return;
-    __shared__ double2 sEb[2][LEG_TL], sBb[2][SPIN ? LEG_TL : 1], sRb[2][LEG_TL];
     const int L = P.lmax, mk = blockIdx.y, m = SH ? P.sh.mlist[mk] : mk, tid = threadIdx.x;
+    // Ring pairs run from the pole to the equator and lambda_lm is negligible on the pairs before slot0[m] (m > m_lim), so
+    // for this m the grid packs the pairs from slot0[m] on: the k-th slot works on pair slot0[m] + k, or on
+    // plist[slot0[m] + k] when a compacted list of the pairs with non-zero pixel weight is given (gs_active_rings_build);
+    // the blocks beyond the last slot have nothing to do.
+    const int s0 = slot0[m], nact = (plist ? *pcount : P.npair) - s0;
+    if ((int)blockIdx.x * (LEG_NT * R) >= nact) return;
+    __shared__ double2 sEb[2][LEG_TL], sBb[2][SPIN ? LEG_TL : 1], sRb[2][LEG_TL];
     const int l0 = m > SPIN ? m : SPIN;
     const int64_t base = (int64_t)m * (2 * L + 1 - m) / 2;
     const int64_t roff = real_off<SH>(P, m, mk, base);
@@ -262,7 +297,7 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
 #pragma unroll
     for (int j = 0; j < R; ++j) {
         const int k = chunk + ((tid >> 5) * R + j) * 32 + (tid & 31);   // warp-major: a warp owns 32 R consecutive pairs, so idle slots fill whole warps
-        const int p = k < npa ? (plist ? plist[k] : k) : -1;
+        const int p = k < nact ? (plist ? plist[s0 + k] : s0 + k) : -1;
         pj[j] = p;
         st[j].x = 0.0; st[j].pc = st[j].pp = st[j].mc = st[j].mp = 0.0; st[j].sc = 0;
         acc[j].sqr = acc[j].sqi = acc[j].aqr = acc[j].aqi = 0.0;
@@ -632,16 +667,17 @@ __device__ __forceinline__ double anal_fold_sel(double* v, int lane)
 template <int SPIN, int R, bool SH>
 __global__ void __launch_bounds__(LEG_NT, LEG_MINB_A)
 leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ partial, const int* __restrict__ skip,
-                const int* __restrict__ plist, const int* __restrict__ pcount)
+                const int* __restrict__ plist, const int* __restrict__ pcount, const int* __restrict__ slot0)
 {
     if (skip && *skip) return;
-    const int npa = plist ? *pcount : P.npair;   // see leg_synth_kernel; leg_finish_kernel sums the chunks below the count only
-    if ((int)blockIdx.x * (LEG_NT * R) >= npa) return;
+    const int L = P.lmax, mk = blockIdx.y, m = SH ? P.sh.mlist[mk] : mk, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    // slots of this m: see leg_synth_kernel; leg_finish_kernel sums the chunks that hold slots only
+    const int s0 = slot0[m], nact = (plist ? *pcount : P.npair) - s0;
+    if ((int)blockIdx.x * (LEG_NT * R) >= nact) return;
     constexpr int NV = SPIN ? 4 : 2;   // doubles per (l,m)
     constexpr int NVAL = 2 * NV;       // values reduced per pair of l
     __shared__ double2 sR[LEG_TL];
     __shared__ double sPart[LEG_NW][LEG_TL * NV];
-    const int L = P.lmax, mk = blockIdx.y, m = SH ? P.sh.mlist[mk] : mk, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int l0 = m > SPIN ? m : SPIN;
     const int64_t base = (int64_t)m * (2 * L + 1 - m) / 2;
     // first entry (l = lt) of this block's partial sums is pbase + lt
@@ -656,7 +692,7 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
 #pragma unroll
     for (int j = 0; j < R; ++j) {
         const int k = chunk + ((tid >> 5) * R + j) * 32 + (tid & 31);   // warp-major: a warp owns 32 R consecutive pairs, so idle slots fill whole warps
-        const int p = k < npa ? (plist ? plist[k] : k) : -1;
+        const int p = k < nact ? (plist ? plist[s0 + k] : s0 + k) : -1;
         st[j].x = 0.0; st[j].pc = st[j].pp = st[j].mc = st[j].mp = 0.0; st[j].sc = 0;
         G[j].q1r = G[j].q1i = G[j].q2r = G[j].q2i = 0.0;
         G[j].u1r = G[j].u1i = G[j].u2r = G[j].u2i = 0.0;
@@ -699,10 +735,10 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
 #if LEG_FOLD2
     // spin 2: the lane ends up owning (h, c) = (bit 2, (bit 4, bit 3)); odd c of the second l carries a minus sign
     const int vidx = SPIN ? ((lane & 4) | ((lane >> 3) & 3)) : lane >> 3;
-    const bool flip = SPIN && (lane & 4) && (lane & 8);
+    const int flipmask = (SPIN && (lane & 4) && (lane & 8)) ? (int)0x80000000 : 0;   // sign flip as an integer XOR (no FP64 op)
 #else
     const int vidx = lane >> (SPIN ? 2 : 3);           // value index this lane ends up owning
-    const bool flip = false;
+    const int flipmask = 0;
 #endif
     const bool writer = (lane & (SPIN ? 3 : 7)) == 0;
 
@@ -756,7 +792,7 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
                 }
             }
             const double s = ANAL_FOLD(v, lane);
-            if (writer) myPart[ip * NVAL + vidx] = flip ? -s : s;
+            if (writer) myPart[ip * NVAL + vidx] = __hiloint2double(__double2hiint(s) ^ flipmask, __double2loint(s));
             ++ip;
         }
 #pragma unroll kUnrollA
@@ -773,7 +809,7 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
                 rec_step<SPIN>(st[j], r1.x, r1.y);
             }
             const double s = ANAL_FOLD(v, lane);
-            if (writer) myPart[ip * NVAL + vidx] = flip ? -s : s;
+            if (writer) myPart[ip * NVAL + vidx] = __hiloint2double(__double2hiint(s) ^ flipmask, __double2loint(s));
         }
         __syncthreads();
         // sum over the warps of the block, one deterministic partial per chunk
@@ -790,12 +826,16 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
 template <int SPIN, bool SH>
 __global__ void leg_finish_kernel(PlanDev P, const double* __restrict__ partial, int nchunk, double* __restrict__ almE,
                                   double* __restrict__ almB, int layout, const double* __restrict__ fl, double scale,
-                                  int accumulate, const int* __restrict__ skip, const int* __restrict__ pcount, int chunk_pairs)
+                                  int accumulate, const int* __restrict__ skip, const int* __restrict__ pcount,
+                                  const int* __restrict__ slot0, int chunk_pairs)
 {
     if (skip && *skip) return;
-    if (pcount) nchunk = (*pcount + chunk_pairs - 1) / chunk_pairs;   // chunks beyond the active pairs were not written
     constexpr int NV = SPIN ? 4 : 2;
     const int L = P.lmax, mk = blockIdx.y, m = SH ? P.sh.mlist[mk] : mk;
+    {   // chunks of this m that hold slots (the others were not written)
+        const int nact = (pcount ? *pcount : P.npair) - slot0[m];
+        nchunk = nact > 0 ? (nact + chunk_pairs - 1) / chunk_pairs : 0;
+    }
     const int l = m + blockIdx.x * blockDim.x + threadIdx.x;
     if (l > L) return;
     const int64_t base = (int64_t)m * (2 * L + 1 - m) / 2, id = base + l;
@@ -886,13 +926,31 @@ __global__ void __launch_bounds__(1024) pair_compact_kernel(PlanDev P, unsigned 
     if (tid == 0) *count = base;
 }
 
+// slot0[spin][m] = first entry k of the list with m_lim(list[k]) >= m (count when none): one warp per (spin, m)
+__global__ void __launch_bounds__(256) list_slot0_kernel(PlanDev P, const int* __restrict__ list, const int* __restrict__ count,
+                                                         int* __restrict__ slot0)
+{
+    const int L = P.lmax, wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= 2 * (L + 1)) return;
+    const int spin2 = wid > L, m = spin2 ? wid - (L + 1) : wid, n = *count;
+    const int* mlim = spin2 ? P.mlim2 : P.mlim0;
+    int first = n;
+    for (int k0 = 0; k0 < n && first == n; k0 += 32) {
+        const int k = k0 + lane;
+        const unsigned b = __ballot_sync(FULL, k < n && mlim[list[k]] >= m);
+        if (b) first = k0 + __ffs(b) - 1;
+    }
+    if (lane == 0) slot0[wid] = first;
+}
+
 int gs_active_rings_build(gs_plan* p, const double* pixw, cudaStream_t st)
 {
     if (p->world > 1) { gs_set_error("active-ring lists need an unsharded plan"); return GS_E_BADARG; }
     ring_active_kernel<<<p->d.nring, 256, 0, st>>>(p->d, pixw, p->act_ring);
     pair_compact_kernel<<<1, 1024, 0, st>>>(p->d, p->act_ring, p->act_pairs, p->act_count);
+    list_slot0_kernel<<<(2 * (p->d.lmax + 1) * 32 + 255) / 256, 256, 0, st>>>(p->d, p->act_pairs, p->act_count, p->act_slot0);
     GS_CHECK_LAUNCH();
-    g_gs_launches += 2;
+    g_gs_launches += 3;
     return GS_OK;
 }
 
@@ -905,12 +963,13 @@ int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, i
     dim3 grid((p->d.npair + LEG_NT * LEG_R - 1) / (LEG_NT * LEG_R), sh ? p->d.sh.nm_loc : p->d.lmax + 1);
     const int* plist = (p->use_act && !sh) ? p->act_pairs : nullptr;
     const int* pcount = plist ? p->act_count : nullptr;
+    const int* slot0 = plist ? p->act_slot0 + (spin ? p->d.lmax + 1 : 0) : (spin ? p->d.pmin2 : p->d.pmin0);
     if (!sh) {
-        if (spin == 0) leg_synth_kernel<0, LEG_R, false><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount);
-        else leg_synth_kernel<2, LEG_R, false><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount);
+        if (spin == 0) leg_synth_kernel<0, LEG_R, false><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0);
+        else leg_synth_kernel<2, LEG_R, false><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0);
     } else {
-        if (spin == 0) leg_synth_kernel<0, LEG_R, true><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount);
-        else leg_synth_kernel<2, LEG_R, true><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount);
+        if (spin == 0) leg_synth_kernel<0, LEG_R, true><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0);
+        else leg_synth_kernel<2, LEG_R, true><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0);
     }
     GS_CHECK_LAUNCH();
     g_gs_launches += 1;
@@ -931,29 +990,30 @@ int gs_leg_anal(gs_plan* p, int spin, double* almE, double* almB, int layout, co
     dim3 fgrid((p->d.lmax + 256) / 256, nmy);
     const int* plist = (p->use_act && !sh) ? p->act_pairs : nullptr;
     const int* pcount = plist ? p->act_count : nullptr;
+    const int* slot0 = plist ? p->act_slot0 + (spin ? p->d.lmax + 1 : 0) : (spin ? p->d.pmin2 : p->d.pmin0);
     if (sh) {  // ring-sharded (p->Fx, written by the ring analysis) -> m-sharded
         int rc = gs_shard_exchange(p, p->Fx, p->Fm, st);
         if (rc) return rc;
     }
     if (!sh) {
         if (spin == 0) {
-            leg_anal_kernel<0, LEG_RA, false><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount);
+            leg_anal_kernel<0, LEG_RA, false><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount, slot0);
             GS_CHECK_LAUNCH();
-            leg_finish_kernel<0, false><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, LEG_NT * LEG_RA);
+            leg_finish_kernel<0, false><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, LEG_NT * LEG_RA);
         } else {
-            leg_anal_kernel<2, LEG_RA, false><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount);
+            leg_anal_kernel<2, LEG_RA, false><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount, slot0);
             GS_CHECK_LAUNCH();
-            leg_finish_kernel<2, false><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, LEG_NT * LEG_RA);
+            leg_finish_kernel<2, false><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, LEG_NT * LEG_RA);
         }
     } else {
         if (spin == 0) {
-            leg_anal_kernel<0, LEG_RA, true><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount);
+            leg_anal_kernel<0, LEG_RA, true><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount, slot0);
             GS_CHECK_LAUNCH();
-            leg_finish_kernel<0, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, LEG_NT * LEG_RA);
+            leg_finish_kernel<0, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, LEG_NT * LEG_RA);
         } else {
-            leg_anal_kernel<2, LEG_RA, true><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount);
+            leg_anal_kernel<2, LEG_RA, true><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount, slot0);
             GS_CHECK_LAUNCH();
-            leg_finish_kernel<2, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, LEG_NT * LEG_RA);
+            leg_finish_kernel<2, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, LEG_NT * LEG_RA);
         }
     }
     GS_CHECK_LAUNCH();

@@ -133,6 +133,15 @@ static int build_tables(gs_plan* p)
     if ((rc = upload(p, s2, &p->d.s2))) return rc;
     if ((rc = upload(p, mlim0, &p->d.mlim0))) return rc;
     if ((rc = upload(p, mlim2, &p->d.mlim2))) return rc;
+    {   // first ring pair (pole -> equator) that reaches a given m: the Legendre kernels pack the pairs from there on
+        std::vector<int> pmin0(L + 1, npair), pmin2(L + 1, npair);
+        for (int m = 0; m <= L; ++m) {
+            for (int q = 0; q < npair; ++q) if (mlim0[q] >= m) { pmin0[m] = q; break; }
+            for (int q = 0; q < npair; ++q) if (mlim2[q] >= m) { pmin2[m] = q; break; }
+        }
+        if ((rc = upload(p, pmin0, &p->d.pmin0))) return rc;
+        if ((rc = upload(p, pmin2, &p->d.pmin2))) return rc;
+    }
     if ((rc = upload(p, rn, &p->d.ring_nphi))) return rc;
     if ((rc = upload(p, rq, &p->d.ring_phq))) return rc;
     if ((rc = upload(p, rden, &p->d.ring_phden))) return rc;
@@ -233,6 +242,7 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
     p->act_ring = nullptr;
     p->act_pairs = nullptr;
     p->act_count = nullptr;
+    p->act_slot0 = nullptr;
     p->use_act = false;
     p->mwg_F = nullptr;
     p->mwg_maps = nullptr;
@@ -247,6 +257,7 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
     p->red_loc = nullptr;
     p->d.sh.world = 1;
     int rc = build_tables(p);
+    if (rc == GS_OK) rc = gs_leg_build_sinpow(p);
     const int64_t nm = lmax + 1;
     p->nreal_loc = nm * nm;
     p->npix_loc = p->d.npix;
@@ -266,6 +277,7 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->d.nring, &p->act_ring);
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->d.npair, &p->act_pairs);
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)1, &p->act_count);
+        if (rc == GS_OK) rc = dev_alloc(p, (size_t)2 * (lmax + 1), &p->act_slot0);
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->npix_loc, &p->mapQ_tmp);
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->npix_loc, &p->mapU_tmp);
         const size_t nre = (size_t)p->nreal_loc;  // big enough for either layout

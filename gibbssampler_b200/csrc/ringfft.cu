@@ -249,6 +249,14 @@ __device__ __forceinline__ int64_t ring_first_pixel(const PlanDev& P, int ring)
     return SH ? P.sh.ring_start_loc[ring] : P.ring_start[ring];
 }
 
+// Highest m that carries signal on a ring: the Legendre kernels neither write (synthesis) nor read (analysis) the spectrum
+// of a ring above the m_lim of its ring pair, so the ring stage must treat those entries as zero / may skip them.
+__device__ __forceinline__ int ring_mtop(const PlanDev& P, int ring, int spin2)
+{
+    const int p = ring < P.npair ? ring : P.nring - 1 - ring;
+    return spin2 ? P.mlim2[p] : P.mlim0[p];
+}
+
 // A CTA of the direct ring kernels works on a GROUP of 1, 2 or 4 jobs whose transforms have the same length M and
 // the same kind (power of two / Bluestein), RF_NT / nsub threads each, side by side in shared memory: the passes of a
 // short transform cannot keep 256 threads busy (M / 16 radix-16 butterflies per pass) and the ring stage is latency
@@ -416,7 +424,7 @@ __device__ __forceinline__ void ring_build_Z(const PlanDev& P, const RingSub& S,
 // br = false: buf[PADI(k)] = conj Z[k] (transform done as conj(idft(conj z))); br = true: buf holds Z[k] at the
 // bit-reversed position of k (forward DIF transform of a power-of-two ring).
 template <bool SH>
-__device__ __forceinline__ void ring_unpack_F(const PlanDev& P, const RingSub& S, bool br, double2* __restrict__ Fm)
+__device__ __forceinline__ void ring_unpack_F(const PlanDev& P, const RingSub& S, bool br, double2* __restrict__ Fm, int mtop)
 {
     const RingJob& job = S.job;
     const int L = P.lmax, nm = L + 1, n = S.n, lg = 31 - __clz(n);
@@ -425,7 +433,7 @@ __device__ __forceinline__ void ring_unpack_F(const PlanDev& P, const RingSub& S
     double2* FB = job.ringB >= 0 ? Fm + ((int64_t)job.compB * P.nring + job.ringB) * nm : nullptr;
     double2 pa = ring_phase(P, job.ringA, S.tid);   // both sequences of a job share phi0 (plan.cu gives a ring and its mirror the same phase)
     const double2 stepa = ring_phase(P, job.ringA, S.nt);
-    for (int m = S.tid; m <= L; m += S.nt) {
+    for (int m = S.tid; m <= mtop; m += S.nt) {
         const int k = m % n, kk = (n - k) % n;
         double2 z1, z2c;
         if (br) {
@@ -453,7 +461,7 @@ template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
 ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __restrict__ groups, const double2* __restrict__ Fm,
                   double* __restrict__ mapQ, double* __restrict__ mapU, const int* __restrict__ skip, int64_t f_stride,
-                  int64_t map_stride, const int* __restrict__ mmax)
+                  int64_t map_stride, const int* __restrict__ mmax, int spin2)
 {
     if (skip && *skip) return;
     extern __shared__ double2 smem[];
@@ -461,11 +469,11 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
     Fm += blockIdx.y * f_stride;
     mapQ += blockIdx.y * map_stride;
     mapU += blockIdx.y * map_stride;
-    const int mtop = mmax ? min(mmax[blockIdx.y], P.lmax) : P.lmax;
+    const int mcap = mmax ? min(mmax[blockIdx.y], P.lmax) : P.lmax;
     double2* twq = smem;
     load_twq(P, twq);
     const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
-    ring_build_Z<SH>(P, S, Fm, mtop, S.scratch);
+    ring_build_Z<SH>(P, S, Fm, min(mcap, ring_mtop(P, S.job.ringA, spin2)), S.scratch);
     ring_idft(P, S.buf, twq, S.n, S.bsi, S.tid, S.nt);
     double* oa = (S.job.compA ? mapU : mapQ) + ring_first_pixel<SH>(P, S.job.ringA);
     double* ob = S.job.ringB >= 0 ? (S.job.compB ? mapU : mapQ) + ring_first_pixel<SH>(P, S.job.ringB) : nullptr;
@@ -480,7 +488,8 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
 template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
 ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __restrict__ groups, const double* __restrict__ mapQ,
-                 const double* __restrict__ mapU, const double* __restrict__ pixw, double2* __restrict__ Fm, const int* __restrict__ skip)
+                 const double* __restrict__ mapU, const double* __restrict__ pixw, double2* __restrict__ Fm, const int* __restrict__ skip,
+                 int spin2)
 {
     if (skip && *skip) return;
     extern __shared__ double2 smem[];
@@ -508,7 +517,7 @@ ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __rest
         for (int k = S.tid; k < n; k += S.nt) S.buf[PADI(k)] = cmul(S.buf[PADI(k)], __ldg(&S.chirp[k]));
         __syncthreads();
     }
-    ring_unpack_F<SH>(P, S, false, Fm);
+    ring_unpack_F<SH>(P, S, false, Fm, ring_mtop(P, job.ringA, spin2));
 }
 
 // Ring stage of the PCG mat-vec A^T N^-1 A in ONE kernel: F_m(ring) -> pixels of the ring (kept in shared memory) ->
@@ -527,7 +536,7 @@ extern "C" int gs_ring_debug_dump(unsigned long long* host, int n) { return (int
 template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
 ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __restrict__ groups, double2* __restrict__ Fm,
-                  const double* __restrict__ pixw, const int* __restrict__ skip, const unsigned char* __restrict__ ract)
+                  const double* __restrict__ pixw, const int* __restrict__ skip, const unsigned char* __restrict__ ract, int spin2)
 {
     if (skip && *skip) return;
     if (ract) {   // a group whose rings all have zero weight maps to zero: nobody reads its spectra (gs_active_rings_build)
@@ -547,7 +556,8 @@ ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
     const double* wa = pixw + ring_first_pixel<SH>(P, S.job.ringA);
     const double* wb = S.job.ringB >= 0 ? pixw + ring_first_pixel<SH>(P, S.job.ringB) : wa;
     RING_DBG(0); RING_DBG(3);
-    ring_build_Z<SH>(P, S, Fm, P.lmax, S.scratch);
+    const int mtop = ring_mtop(P, S.job.ringA, spin2);
+    ring_build_Z<SH>(P, S, Fm, mtop, S.scratch);
     __syncthreads();
     RING_DBG(1);
     ring_idft(P, S.buf, twq, n, S.bsi, S.tid, S.nt);
@@ -559,7 +569,7 @@ ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
         }
         __syncthreads();
         fft_dif<false>(S.buf, n, twq, P.tw_n, nullptr, S.tid, S.nt);
-        ring_unpack_F<SH>(P, S, true, Fm);
+        ring_unpack_F<SH>(P, S, true, Fm, mtop);
     } else {
         // Bluestein both ways: Z = conj(idft(conj z)); the chirp of the synthesis output and of the analysis input fuse
         for (int j = S.tid; j < S.M; j += S.nt) {
@@ -571,7 +581,7 @@ ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
         ring_idft(P, S.buf, twq, n, S.bsi, S.tid, S.nt);
         for (int k = S.tid; k < n; k += S.nt) S.buf[PADI(k)] = cmul(S.buf[PADI(k)], __ldg(&S.chirp[k]));
         __syncthreads();
-        ring_unpack_F<SH>(P, S, false, Fm);
+        ring_unpack_F<SH>(P, S, false, Fm, mtop);
     }
     __syncthreads();
     RING_DBG(2);
@@ -585,9 +595,9 @@ ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
 // Analysis is the transpose: CTA (job, b) loads v_b[j2] = e^{2 pi i j2 b/n} sum_q i^{qb} c_{j2 + n2 q}, transforms
 // it to C_{4a+b}, and ring_anal_finish_kernel unpacks the two real sequences into F_m.
 template <bool SH>
-__device__ __forceinline__ double2 fold_spectrum(const PlanDev& P, const double2* __restrict__ Fm, int comp, int ring, int k, int n)
-{  // X_k = G_k + conj G_{n-k},  G_k = sum_{m = k mod n} w_m F_m e^{i m phi0}
-    const int L = P.lmax, kk = (n - k) % n;
+__device__ __forceinline__ double2 fold_spectrum(const PlanDev& P, const double2* __restrict__ Fm, int comp, int ring, int k, int n, int L)
+{  // X_k = G_k + conj G_{n-k},  G_k = sum_{m = k mod n, m <= L} w_m F_m e^{i m phi0}
+    const int kk = (n - k) % n;
     double2 g = make_double2(0.0, 0.0), h = g;
     for (int m = k; m <= L; m += n) {
         const double w = m ? 1.0 : 0.5;
@@ -619,11 +629,12 @@ __device__ __forceinline__ double2 unit_root(int num, int n)
 template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
 ring_synth_split_kernel(PlanDev P, const SplitJob* __restrict__ jobs, const double2* __restrict__ Fm, double2* __restrict__ scratch,
-                        const int* __restrict__ skip)
+                        const int* __restrict__ skip, int spin2)
 {
     if (skip && *skip) return;
     extern __shared__ double2 smem[];
     const SplitJob job = jobs[blockIdx.x >> 2];
+    const int mtop = ring_mtop(P, job.ringA, spin2);
     const int b = blockIdx.x & 3;
     const int n = P.ring_nphi[job.ringA], n2 = n >> 2, bsi = job.bs2;
     double2* twq = smem;
@@ -636,10 +647,10 @@ ring_synth_split_kernel(PlanDev P, const SplitJob* __restrict__ jobs, const doub
         const int pos = PADI(bsi < 0 ? (int)(__brev((unsigned)a) >> (32 - lg)) : a);
         if (a >= n2) { buf[pos] = make_double2(0.0, 0.0); continue; }
         const int k = 4 * a + b;
-        const double2 xa = fold_spectrum<SH>(P, Fm, job.compA, job.ringA, k, n);
+        const double2 xa = fold_spectrum<SH>(P, Fm, job.compA, job.ringA, k, n, mtop);
         double2 z = xa;
         if (job.ringB >= 0) {
-            const double2 xb = fold_spectrum<SH>(P, Fm, job.compB, job.ringB, k, n);
+            const double2 xb = fold_spectrum<SH>(P, Fm, job.compB, job.ringB, k, n, mtop);
             z = make_double2(xa.x - xb.y, xa.y + xb.x);  // + i Xb
         }
         if (bsi >= 0) z = cmul(z, __ldg(&chirp[a]));
@@ -912,18 +923,18 @@ int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t
     const double2* F = sh ? p->Fx : p->Fm;
     if (ns > 0) {  // long rings first: they are the heavy ones
         if (sh) {
-            ring_synth_split_kernel<true><<<4 * ns, RF_NT, p->split_smem, st>>>(p->d, sj, F, p->ring_scratch, skip);
+            ring_synth_split_kernel<true><<<4 * ns, RF_NT, p->split_smem, st>>>(p->d, sj, F, p->ring_scratch, skip, spin ? 1 : 0);
             ring_synth_combine_kernel<true><<<ns, RF_NT, 0, st>>>(p->d, sj, p->ring_scratch, mapQ, mu, skip);
         } else {
-            ring_synth_split_kernel<false><<<4 * ns, RF_NT, p->split_smem, st>>>(p->d, sj, F, p->ring_scratch, skip);
+            ring_synth_split_kernel<false><<<4 * ns, RF_NT, p->split_smem, st>>>(p->d, sj, F, p->ring_scratch, skip, spin ? 1 : 0);
             ring_synth_combine_kernel<false><<<ns, RF_NT, 0, st>>>(p->d, sj, p->ring_scratch, mapQ, mu, skip);
         }
         GS_CHECK_LAUNCH();
         g_gs_launches += 2;
     }
     if (nj > 0) {
-        if (sh) ring_synth_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr);
-        else ring_synth_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr);
+        if (sh) ring_synth_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr, spin ? 1 : 0);
+        else ring_synth_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr, spin ? 1 : 0);
         GS_CHECK_LAUNCH();
     }
     g_gs_launches += 1;
@@ -952,8 +963,8 @@ int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, c
         g_gs_launches += 2;
     }
     if (nj > 0) {
-        if (sh) ring_anal_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, mapQ, mu, pixw, F, skip);
-        else ring_anal_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, mapQ, mu, pixw, F, skip);
+        if (sh) ring_anal_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, mapQ, mu, pixw, F, skip, spin ? 1 : 0);
+        else ring_anal_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, mapQ, mu, pixw, F, skip, spin ? 1 : 0);
         GS_CHECK_LAUNCH();
     }
     g_gs_launches += 1;
@@ -973,8 +984,8 @@ int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, con
     if (nj <= 0) return GS_OK;
     const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
     const int2* grp = spin == 0 ? p->groups0 : p->groups2;
-    if (p->world > 1) ring_apply_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fx, pixw, skip, nullptr);
-    else ring_apply_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fm, pixw, skip, p->use_act ? p->act_ring : nullptr);
+    if (p->world > 1) ring_apply_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fx, pixw, skip, nullptr, spin ? 1 : 0);
+    else ring_apply_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fm, pixw, skip, p->use_act ? p->act_ring : nullptr, spin ? 1 : 0);
     GS_CHECK_LAUNCH();
     g_gs_launches += 1;
     return GS_OK;
@@ -987,7 +998,7 @@ int gs_ring_synth_batch(gs_plan* p, const double2* F, int64_t f_stride, const in
     if (p->world > 1 || p->nsjobs2 > 0) { gs_set_error("batched ring synthesis needs an unsharded plan without split rings"); return GS_E_BADARG; }
     if (nb <= 0 || p->ngroups2 <= 0) return GS_OK;
     ring_synth_kernel<false><<<dim3(p->ngroups2, nb), RF_NT, p->ring_smem, st>>>(p->d, p->jobs2, p->groups2, F, mapQ, mapU, nullptr, f_stride,
-                                                                                 map_stride, mmax);
+                                                                                 map_stride, mmax, 1);
     GS_CHECK_LAUNCH();
     g_gs_launches += 1;
     return GS_OK;

@@ -556,20 +556,25 @@ extern "C" int gs_profile_matvec(gs_plan* p, const double* x_E, const double* x_
     return rc;
 }
 
-// FP64 FMA throughput of the device (MEASURED_PEAKS.json holds no FP64 figure): 8 independent DFMA
-// chains per thread, 148 x 8 CTAs of 256 threads; returns TFLOP/s (2 flops per FMA), best of 5.
-__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b)
+// FP64 FMA throughput of the device (MEASURED_PEAKS.json holds no FP64 figure).  16 independent sums per thread in the
+// operand pattern of the Legendre kernels, sum += x_k * y_j with register operands that change during the loop (three
+// distinct register pairs per DFMA; scripts/ubench/dfma_operands.cu compares patterns: this one is the highest the pipe
+// delivers, 36.9 TFLOP/s on B200 = 99 % of 148 x 64 x 2 x 1.965 GHz); 148 x 8 CTAs of 128 threads; TFLOP/s, best of 5.
+__global__ void __launch_bounds__(128) dfma_peak_kernel(double* out, int iters, double a, double b)
 {
-    double v[8];
+    double v[16], w[4], u[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = threadIdx.x * 1e-3 + k;
+    for (int k = 0; k < 16; ++k) v[k] = threadIdx.x * 1e-3 + k;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { w[k] = a + 1e-9 * k; u[k] = b * (k + 1); }
     for (int i = 0; i < iters; ++i) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = fma(v[k], a, b);
+        for (int k = 0; k < 16; ++k) v[k] = fma(w[k & 3], u[k >> 2], v[k]);
+        w[i & 3] = fma(w[i & 3], a, b * 1e-30);   // keeps the multiplicands live (1 of 17 DFMAs, counted)
     }
     double s = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += v[k];
+    for (int k = 0; k < 16; ++k) s += v[k];
     if (s == 123.456) out[0] = s;
 }
 
@@ -582,16 +587,16 @@ extern "C" int gs_measure_fp64_peak(double* tflops_out, void* stream)
     cudaEvent_t e0, e1;
     GS_CHECK_CUDA(cudaEventCreate(&e0));
     GS_CHECK_CUDA(cudaEventCreate(&e1));
-    const int iters = 1 << 15, grid = 148 * 8;
+    const int iters = 1 << 14, grid = 148 * 8;
     double best = 0.0;
     for (int r = 0; r < 6; ++r) {
         cudaEventRecord(e0, st);
-        dfma_peak_kernel<<<grid, 256, 0, st>>>(d, iters, 0.999999, 1e-9);
+        dfma_peak_kernel<<<grid, 128, 0, st>>>(d, iters, 0.999999, 1e-9);
         cudaEventRecord(e1, st);
         GS_CHECK_CUDA(cudaEventSynchronize(e1));
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
-        const double tf = 2.0 * 8.0 * iters * (double)grid * 256.0 / (ms * 1e-3) * 1e-12;
+        const double tf = 2.0 * 17.0 * iters * (double)grid * 128.0 / (ms * 1e-3) * 1e-12;
         if (r > 0 && tf > best) best = tf;
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);

@@ -1,0 +1,64 @@
+// FP64 pipe ceiling as a function of operand pattern and resident warps (sm_100a).
+//   mode 0: v = fma(v, a, b)        one changing register pair, two loop constants (register reuse cache friendly)
+//   mode 1: v = fma(v, w_k, u_k)    three distinct register pairs per FMA, w_k / u_k differ per chain
+//   mode 2: v = fma(x_k, y_j, v)    accumulate pattern of the Legendre kernels: lambda (per ring) x coefficient (shared) into 8 sums
+// build: nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o dfma_operands dfma_operands.cu
+#include <cstdio>
+#include <cuda_runtime.h>
+
+template <int MODE, int NCH>
+__global__ void __launch_bounds__(128) k(double* out, int iters, double a, double b)
+{
+    double v[NCH], w[NCH], u[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) { v[i] = threadIdx.x * 1e-3 + i; w[i] = a + 1e-9 * i; u[i] = b * (i + 1); }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+            if (MODE == 0) v[i] = fma(v[i], a, b);
+            else if (MODE == 1) v[i] = fma(v[i], w[i], u[i]);
+            else v[i] = fma(w[i & 3], u[(i >> 2) & 3], v[i]);
+        }
+        if (MODE == 2) {   // keep the multiplicands changing (cheap: 2 of 18 FMAs) so that nothing is hoisted
+            w[it & 3] = fma(w[it & 3], a, b * 1e-30);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) s += v[i] + w[i] * 1e-300;
+    if (s == 123.456) out[0] = s;
+}
+
+template <int MODE, int NCH>
+double run(int ctas_per_sm)
+{
+    double* d; cudaMalloc(&d, 8);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int iters = 1 << 14, grid = 148 * ctas_per_sm;
+    double best = 0;
+    for (int r = 0; r < 4; ++r) {
+        cudaEventRecord(e0);
+        k<MODE, NCH><<<grid, 128>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        const double fm = (double)NCH + (MODE == 2 ? 1.0 : 0.0);
+        const double tf = 2.0 * fm * iters * (double)grid * 128.0 / (ms * 1e-3) * 1e-12;
+        if (r && tf > best) best = tf;
+    }
+    cudaFree(d);
+    return best;
+}
+
+int main()
+{
+    printf("TFLOP/s (2 flop per DFMA), 128-thread CTAs; columns = CTAs per SM (warps per scheduler = CTAs)\n");
+    printf("%-34s %7s %7s %7s %7s %7s\n", "pattern", "1", "2", "3", "4", "8");
+    const int cs[5] = {1, 2, 3, 4, 8};
+#define ROW(MODE, NCH, name) { printf("%-34s", name); for (int c : cs) printf(" %7.2f", run<MODE, NCH>(c)); printf("\n"); }
+    ROW(0, 8, "fma(v,a,b) 8 chains");
+    ROW(0, 16, "fma(v,a,b) 16 chains");
+    ROW(1, 8, "fma(v,w_k,u_k) 8 chains");
+    ROW(1, 16, "fma(v,w_k,u_k) 16 chains");
+    ROW(2, 16, "fma(x_k,y_j,v) 16 sums");
+    return 0;
+}
