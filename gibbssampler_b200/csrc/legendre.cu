@@ -413,126 +413,178 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
 // pass of the recurrence serves every block: E and B contributions are accumulated separately and flushed to the
 // block's own ring-spectra slot whenever l crosses a block boundary.  lbE / lbB hold the block boundaries in l
 // (block i = [lb[i], lb[i+1])); this launch covers E blocks [e0, e1) -> slots 0.., B blocks [b0, b1) -> slots (e1-e0)..;
-// a slot is [2][nring][L+1] double2 and receives m < lb[i+1] only (the ring stage is told mmax per slot).
-template <int R>
+// a slot is [nring][L+1][2] double2 (Q and U of one (ring, m) adjacent: every store completes a 32-byte sector, the
+// [comp][ring][m] layout cost a DRAM fill read per half-written sector) and receives m < lb[i+1] only (the ring stage is
+// told mmax per slot).
+template <int R, bool DO_E, bool DO_B>
 __global__ void __launch_bounds__(LEG_NT)
 leg_synth_blocks_kernel(PlanDev P, const double* __restrict__ almE, const double* __restrict__ almB, const double* __restrict__ dflE,
                         const double* __restrict__ dflB, const int* __restrict__ lbE, int e0, int e1, const int* __restrict__ lbB,
                         int b0, int b1, int lend, double2* __restrict__ Fblk)
 {
-    __shared__ double2 sE[LEG_TL], sB[LEG_TL], sR[LEG_TL];
+    // per-l staging of one tile: e = (E'r, E'i), b = (B'r, B'i), their copies times (-1)^(l+m) for the southern ring
+    // (lam^+-(pi - theta) = (-1)^(l+m) lam^-+(theta)), and the recurrence coefficients
+    __shared__ double2 sE[LEG_TL], sB[LEG_TL], sSE[LEG_TL], sSB[LEG_TL], sR[LEG_TL];
+    extern __shared__ unsigned char sflag[];   // [2][L+2]: an E / a B block of this launch ends after multipole l
     const int L = P.lmax, m = blockIdx.y, tid = threadIdx.x;
     const int l0 = m > 2 ? m : 2;
     if (l0 >= lend) return;
+    // ring pairs that reach this m, packed (see leg_synth_kernel); the ring stage reads a ring up to its m_lim only
+    const int s0 = P.pmin2[m], nact = P.npair - s0;
+    const int chunk = blockIdx.x * (LEG_NT * R);
+    if (chunk >= nact) return;
+    unsigned char* sfE = sflag;
+    unsigned char* sfB = sflag + (L + 2);
+    for (int i = tid; i < 2 * (L + 2); i += LEG_NT) sflag[i] = 0;
+    __syncthreads();
+    if (DO_E) for (int i = e0 + tid; i < e1; i += LEG_NT) { const int end = lbE[i + 1]; if (end >= 1 && end <= L + 1) sfE[end - 1] = 1; }
+    if (DO_B) for (int i = b0 + tid; i < b1; i += LEG_NT) { const int end = lbB[i + 1]; if (end >= 1 && end <= L + 1) sfB[end - 1] = 1; }
     const int64_t base = (int64_t)m * (2 * L + 1 - m) / 2;
     const int64_t roff = real_off<false>(P, m, m, base);
-    const int chunk = blockIdx.x * (LEG_NT * R);
     const int64_t nm = L + 1, cs = (int64_t)P.nring * nm, slot = 2 * cs;
 
     RingState<2> st[R];
-    double aE[R][8], aB[R][8];
+    double aE[R][DO_E ? 8 : 1], aB[R][DO_B ? 8 : 1];
+    int pj[R];
+    bool any_act = false, all_plain = true;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
-        const int p = chunk + j * LEG_NT + tid;
+        const int k = chunk + ((tid >> 5) * R + j) * 32 + (tid & 31);
+        const int p = k < nact ? s0 + k : -1;
+        pj[j] = p;
         st[j].x = 0.0; st[j].pc = st[j].pp = st[j].mc = st[j].mp = 0.0; st[j].sc = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { aE[j][k] = 0.0; aB[j][k] = 0.0; }
-        if (p < P.npair && m <= P.mlim2[p]) {
+        for (int q = 0; q < (DO_E ? 8 : 1); ++q) aE[j][q] = 0.0;
+#pragma unroll
+        for (int q = 0; q < (DO_B ? 8 : 1); ++q) aB[j][q] = 0.0;
+        if (p >= 0 && m <= P.mlim2[p]) {
             st[j].x = P.cth[p];
             seed_ring<2>(P, p, m, st[j].pc, st[j].mc, st[j].sc);
+            any_act = true;
+            all_plain = all_plain && st[j].sc == 0;
         }
     }
+    const bool warp_act = __any_sync(FULL, any_act);
+    bool fast = __all_sync(FULL, all_plain);   // no ring of the warp carries a range-extension scale (any more)
+    // blocks that end at or below the first multipole of this m receive nothing from it
     int iE = e0, iB = b0;
-    while (iE < e1 && lbE[iE + 1] <= l0) ++iE;
-    while (iB < b1 && lbB[iB + 1] <= l0) ++iB;
-
+    if (DO_E) while (iE < e1 && lbE[iE + 1] <= l0) ++iE;
+    if (DO_B) while (iB < b1 && lbB[iB + 1] <= l0) ++iB;
     // multipoles below the first block of this launch belong to blocks of another group: their sums are discarded
-    const int startE = e1 > e0 ? lbE[e0] : 0, startB = b1 > b0 ? lbB[b0] : 0;
-    int l = l0, tile_lo = -(1 << 30);
-    while (l < lend) {
-        int le = lend;
-        if (iE < e1) le = min(le, lbE[iE + 1]);
-        if (iB < b1) le = min(le, lbB[iB + 1]);
-        if (l < startE) le = min(le, startE);
-        if (l < startB) le = min(le, startB);
-        for (; l < le; ++l) {
-            if (l >= tile_lo + LEG_TL) {  // stage the next l tile (uniform over the block)
-                __syncthreads();
-                tile_lo = l;
-                const int lt = l + tid;
-                double2 e = make_double2(0.0, 0.0), b = e, r = e;
-                if (lt <= L) {
-                    const int64_t id = base + lt;
-                    double pre = -0.5 * P.alpha2[id];
-                    if (m == 0) { e.x = almE[roff + lt]; b.x = almB[roff + lt]; }
-                    else {
-                        const int64_t off = roff + 2 * lt;
-                        pre *= 0.70710678118654752440;
-                        e = make_double2(almE[off], almE[off + 1]);
-                        b = make_double2(almB[off], almB[off + 1]);
-                    }
-                    const double pe = pre * dflE[lt], pb = pre * dflB[lt];
-                    e.x *= pe; e.y *= pe; b.x *= pb; b.y *= pb;
-                    r = P.rec2[id];
+    const int startE = (DO_E && e1 > e0) ? lbE[e0] : -1, startB = (DO_B && b1 > b0) ? lbB[b0] : -1;
+
+    for (int lt = l0; lt < lend; lt += LEG_TL) {
+        __syncthreads();
+        {
+            const int l = lt + tid;
+            double2 e = make_double2(0.0, 0.0), b = e, r = e;
+            double sg = 1.0;
+            if (l <= L) {
+                const int64_t id = base + l;
+                double pre = -0.5 * P.alpha2[id];
+                if (m == 0) { e.x = almE[roff + l]; b.x = almB[roff + l]; }
+                else {
+                    const int64_t off = roff + 2 * l;
+                    pre *= 0.70710678118654752440;
+                    e = make_double2(almE[off], almE[off + 1]);
+                    b = make_double2(almB[off], almB[off + 1]);
                 }
-                sE[tid] = e; sB[tid] = b; sR[tid] = r;
-                __syncthreads();
+                const double pe = pre * dflE[l], pb = pre * dflB[l];
+                e.x *= pe; e.y *= pe; b.x *= pb; b.y *= pb;
+                r = P.rec2[id];
+                sg = ((l + m) & 1) ? -1.0 : 1.0;
             }
-            const int i = l - tile_lo;
-            const double2 r = sR[i], e = sE[i], b = sB[i];
-            const double sgn = ((l + m) & 1) ? -1.0 : 1.0;   // lam^+-(pi - theta) = (-1)^(l+m) lam^-+(theta)
+            sE[tid] = e; sB[tid] = b; sR[tid] = r;
+            sSE[tid] = make_double2(sg * e.x, sg * e.y);
+            sSB[tid] = make_double2(sg * b.x, sg * b.y);
+        }
+        __syncthreads();
+        if (!warp_act) continue;
+        const int ni = min(LEG_TL, lend - lt);
+        for (int i = 0; i < ni; ++i) {
+            const int l = lt + i;
+            if (DO_E && l == startE) {
+#pragma unroll
+                for (int j = 0; j < R; ++j)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) aE[j][q] = 0.0;
+            }
+            if (DO_B && l == startB) {
+#pragma unroll
+                for (int j = 0; j < R; ++j)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) aB[j][q] = 0.0;
+            }
+            const double2 r = sR[i], e = sE[i], b = sB[i], se = sSE[i], sb = sSB[i];
 #pragma unroll
             for (int j = 0; j < R; ++j) {
-                const double pc = st[j].sc ? 0.0 : st[j].pc, mc = st[j].sc ? 0.0 : st[j].mc;
-                const double sp = sgn * pc, sm = sgn * mc;
-                // E only: c1 = c2 = E'r, c3 = c4 = E'i
-                aE[j][0] = fma(pc, e.x, aE[j][0]); aE[j][1] = fma(mc, e.x, aE[j][1]);
-                aE[j][2] = fma(pc, e.y, aE[j][2]); aE[j][3] = fma(mc, e.y, aE[j][3]);
-                aE[j][4] = fma(sm, e.x, aE[j][4]); aE[j][5] = fma(sp, e.x, aE[j][5]);
-                aE[j][6] = fma(sm, e.y, aE[j][6]); aE[j][7] = fma(sp, e.y, aE[j][7]);
-                // B only: c1 = -B'i, c2 = B'i, c3 = B'r, c4 = -B'r
-                aB[j][0] = fma(-pc, b.y, aB[j][0]); aB[j][1] = fma(mc, b.y, aB[j][1]);
-                aB[j][2] = fma(pc, b.x, aB[j][2]); aB[j][3] = fma(-mc, b.x, aB[j][3]);
-                aB[j][4] = fma(-sm, b.y, aB[j][4]); aB[j][5] = fma(sp, b.y, aB[j][5]);
-                aB[j][6] = fma(sm, b.x, aB[j][6]); aB[j][7] = fma(-sp, b.x, aB[j][7]);
+                const double pc = (fast || st[j].sc == 0) ? st[j].pc : 0.0, mc = (fast || st[j].sc == 0) ? st[j].mc : 0.0;
+                if (DO_E) {   // E only: c1 = c2 = E'r, c3 = c4 = E'i
+                    aE[j][0] = fma(pc, e.x, aE[j][0]); aE[j][1] = fma(mc, e.x, aE[j][1]);
+                    aE[j][2] = fma(pc, e.y, aE[j][2]); aE[j][3] = fma(mc, e.y, aE[j][3]);
+                    aE[j][4] = fma(mc, se.x, aE[j][4]); aE[j][5] = fma(pc, se.x, aE[j][5]);
+                    aE[j][6] = fma(mc, se.y, aE[j][6]); aE[j][7] = fma(pc, se.y, aE[j][7]);
+                }
+                if (DO_B) {   // B only: c1 = -B'i, c2 = B'i, c3 = B'r, c4 = -B'r
+                    aB[j][0] = fma(-pc, b.y, aB[j][0]); aB[j][1] = fma(mc, b.y, aB[j][1]);
+                    aB[j][2] = fma(pc, b.x, aB[j][2]); aB[j][3] = fma(-mc, b.x, aB[j][3]);
+                    aB[j][4] = fma(-mc, sb.y, aB[j][4]); aB[j][5] = fma(pc, sb.y, aB[j][5]);
+                    aB[j][6] = fma(mc, sb.x, aB[j][6]); aB[j][7] = fma(-pc, sb.x, aB[j][7]);
+                }
                 rec_step<2>(st[j], r.x, r.y);
-                rescale_check<2>(st[j]);
+                if (!fast) rescale_check<2>(st[j]);
             }
-        }
-        if (l == startE) {
+            if (!fast) {
+                bool plain = true;
 #pragma unroll
-            for (int j = 0; j < R; ++j)
+                for (int j = 0; j < R; ++j) plain = plain && st[j].sc == 0;
+                fast = __all_sync(FULL, plain);
+            }
+            // flush the block(s) that end after l
+            if (DO_E && sfE[l]) {
+                double2* F = Fblk + (int64_t)(iE - e0) * slot;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) aE[j][k] = 0.0;
-        }
-        if (l == startB) {
-#pragma unroll
-            for (int j = 0; j < R; ++j)
-#pragma unroll
-                for (int k = 0; k < 8; ++k) aB[j][k] = 0.0;
-        }
-        // flush the block(s) that end at l
-        for (int which = 0; which < 2; ++which) {
-            const bool isE = which == 0;
-            if (isE ? !(iE < e1 && lbE[iE + 1] == l) : !(iB < b1 && lbB[iB + 1] == l)) continue;
-            double2* F = Fblk + (int64_t)(isE ? iE - e0 : (e1 - e0) + (iB - b0)) * slot;
-#pragma unroll
-            for (int j = 0; j < R; ++j) {
-                const int p = chunk + j * LEG_NT + tid;
-                double* a = isE ? aE[j] : aB[j];
-                if (p < P.npair) {
-                    const int rn = p, rs = P.nring - 1 - p;
-                    F[(int64_t)rn * nm + m] = make_double2(a[0] + a[1], a[2] + a[3]);
-                    F[cs + (int64_t)rn * nm + m] = make_double2(a[2] - a[3], a[1] - a[0]);
-                    if (rs != rn) {
-                        F[(int64_t)rs * nm + m] = make_double2(a[4] + a[5], a[6] + a[7]);
-                        F[cs + (int64_t)rs * nm + m] = make_double2(a[6] - a[7], a[5] - a[4]);
+                for (int j = 0; j < R; ++j) {
+                    const int p = pj[j];
+                    double* a = aE[j];
+                    if (p >= 0) {
+                        const int rn = p, rs = P.nring - 1 - p;
+                        double2* fn = F + ((int64_t)rn * nm + m) * 2;   // [ring][m][comp]: Q and U fill one 32-byte sector
+                        fn[0] = make_double2(a[0] + a[1], a[2] + a[3]);
+                        fn[1] = make_double2(a[2] - a[3], a[1] - a[0]);
+                        if (rs != rn) {
+                            double2* fsn = F + ((int64_t)rs * nm + m) * 2;
+                            fsn[0] = make_double2(a[4] + a[5], a[6] + a[7]);
+                            fsn[1] = make_double2(a[6] - a[7], a[5] - a[4]);
+                        }
                     }
-                }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) a[k] = 0.0;
+                    for (int q = 0; q < 8; ++q) a[q] = 0.0;
+                }
+                ++iE;
             }
-            if (isE) ++iE; else ++iB;
+            if (DO_B && sfB[l]) {
+                double2* F = Fblk + (int64_t)((e1 - e0) + (iB - b0)) * slot;
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    const int p = pj[j];
+                    double* a = aB[j];
+                    if (p >= 0) {
+                        const int rn = p, rs = P.nring - 1 - p;
+                        double2* fn = F + ((int64_t)rn * nm + m) * 2;   // [ring][m][comp]: Q and U fill one 32-byte sector
+                        fn[0] = make_double2(a[0] + a[1], a[2] + a[3]);
+                        fn[1] = make_double2(a[2] - a[3], a[1] - a[0]);
+                        if (rs != rn) {
+                            double2* fsn = F + ((int64_t)rs * nm + m) * 2;
+                            fsn[0] = make_double2(a[4] + a[5], a[6] + a[7]);
+                            fsn[1] = make_double2(a[6] - a[7], a[5] - a[4]);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) a[q] = 0.0;
+                }
+                ++iB;
+            }
         }
     }
 }
@@ -1027,7 +1079,12 @@ int gs_leg_synth_blocks(gs_plan* p, const double* almE, const double* almB, cons
     if (p->world > 1) { gs_set_error("block-batched synthesis needs an unsharded plan"); return GS_E_BADARG; }
     constexpr int RB = 2;
     dim3 grid((p->d.npair + LEG_NT * RB - 1) / (LEG_NT * RB), std::min(lend, p->d.lmax + 1));
-    leg_synth_blocks_kernel<RB><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, dflE, dflB, lbE, e0, e1, lbB, b0, b1, lend, Fblk);
+    const size_t sm = 2 * (size_t)(p->d.lmax + 2);
+    const bool doE = e1 > e0, doB = b1 > b0;
+    if (!doE && !doB) return GS_OK;
+    if (doE && doB) leg_synth_blocks_kernel<RB, true, true><<<grid, LEG_NT, sm, st>>>(p->d, almE, almB, dflE, dflB, lbE, e0, e1, lbB, b0, b1, lend, Fblk);
+    else if (doE) leg_synth_blocks_kernel<RB, true, false><<<grid, LEG_NT, sm, st>>>(p->d, almE, almB, dflE, dflB, lbE, e0, e1, lbB, b0, b1, lend, Fblk);
+    else leg_synth_blocks_kernel<RB, false, true><<<grid, LEG_NT, sm, st>>>(p->d, almE, almB, dflE, dflB, lbE, e0, e1, lbB, b0, b1, lend, Fblk);
     GS_CHECK_LAUNCH();
     g_gs_launches += 1;
     return GS_OK;

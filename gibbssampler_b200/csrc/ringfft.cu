@@ -298,9 +298,9 @@ __device__ __forceinline__ RingSub ring_sub(const PlanDev& P, const RingJob* __r
 // kk = n - k (0 for k = 0).  4 UK UJ independent global loads are in flight per step.
 template <bool SH, int UK, int UJ>
 __device__ __forceinline__ void ring_fold(const PlanDev& P, const RingJob& job, const double2* __restrict__ Fm, const double2* __restrict__ FA,
-                                          const double2* __restrict__ FB, int n, int mtop, int nterm, int k0, int ks, int j0, int js,
+                                          const double2* __restrict__ FB, int fs, int n, int mtop, int nterm, int k0, int ks, int j0, int js,
                                           double2 pk0, double2 step, double2 q, double2 (&z)[UK])
-{
+{   // fs: stride of m in FA / FB (1: [comp][ring][m]; 2: components interleaved, [ring][m][comp])
     // pk0 = e^{i k0 phi0}, step = e^{i ks phi0}, q = e^{i n phi0}: the phases of the first alias term follow by
     // multiplication when j0 = 0 (e^{i (n - k) phi0} = q conj e^{i k phi0}); one sincospi pair per k otherwise.
     const double2 zero = make_double2(0.0, 0.0);
@@ -333,10 +333,10 @@ __device__ __forceinline__ void ring_fold(const PlanDev& P, const RingJob& job, 
                 const int j = jb + v * js;
                 const int m1 = k + j * n, m2 = (k ? n - k : 0) + j * n;
                 const bool v1 = k < n && m1 <= mtop, v2 = k < n && m2 <= mtop;
-                fa1[u][v] = v1 ? (SH ? Fm[fm_ring_index<true>(P, job.compA, job.ringA, m1)] : FA[m1]) : zero;
-                fa2[u][v] = v2 ? (SH ? Fm[fm_ring_index<true>(P, job.compA, job.ringA, m2)] : FA[m2]) : zero;
-                fb1[u][v] = (hasB && v1) ? (SH ? Fm[fm_ring_index<true>(P, job.compB, job.ringB, m1)] : FB[m1]) : zero;
-                fb2[u][v] = (hasB && v2) ? (SH ? Fm[fm_ring_index<true>(P, job.compB, job.ringB, m2)] : FB[m2]) : zero;
+                fa1[u][v] = v1 ? (SH ? Fm[fm_ring_index<true>(P, job.compA, job.ringA, m1)] : FA[m1 * fs]) : zero;
+                fa2[u][v] = v2 ? (SH ? Fm[fm_ring_index<true>(P, job.compA, job.ringA, m2)] : FA[m2 * fs]) : zero;
+                fb1[u][v] = (hasB && v1) ? (SH ? Fm[fm_ring_index<true>(P, job.compB, job.ringB, m1)] : FB[m1 * fs]) : zero;
+                fb2[u][v] = (hasB && v2) ? (SH ? Fm[fm_ring_index<true>(P, job.compB, job.ringB, m2)] : FB[m2 * fs]) : zero;
             }
         }
 #pragma unroll
@@ -364,12 +364,16 @@ __device__ __forceinline__ void ring_fold(const PlanDev& P, const RingJob& job, 
 // and combine the partial sums in a fixed order through `scratch` (nt entries of shared memory).
 // Contains one CTA-wide barrier; all threads of the CTA must call.
 template <bool SH>
-__device__ __forceinline__ void ring_build_Z(const PlanDev& P, const RingSub& S, const double2* __restrict__ Fm, int mtop, double2* scratch)
+__device__ __forceinline__ void ring_build_Z(const PlanDev& P, const RingSub& S, const double2* __restrict__ Fm, int mtop, double2* scratch,
+                                             bool interleaved = false)
 {
     const RingJob& job = S.job;
     const int L = P.lmax, nm = L + 1, n = S.n, lg = 31 - __clz(n);
-    const double2* FA = Fm + ((int64_t)job.compA * P.nring + job.ringA) * nm;
-    const double2* FB = job.ringB >= 0 ? Fm + ((int64_t)job.compB * P.nring + job.ringB) * nm : nullptr;
+    // spectra layout [comp][ring][m], or (block-batched Metropolis sweep) [ring][m][comp] with Q and U of one (ring, m) adjacent
+    const int fs = interleaved ? 2 : 1;
+    const double2* FA = interleaved ? Fm + (int64_t)job.ringA * nm * 2 + job.compA : Fm + ((int64_t)job.compA * P.nring + job.ringA) * nm;
+    const double2* FB = job.ringB < 0 ? nullptr
+                        : interleaved ? Fm + (int64_t)job.ringB * nm * 2 + job.compB : Fm + ((int64_t)job.compB * P.nring + job.ringB) * nm;
     const int nterm = (mtop + n) / n;   // alias terms m = k + j n <= mtop, j < nterm
     const double2 zero = make_double2(0.0, 0.0);
     auto put = [&](int k, double2 v) {
@@ -384,14 +388,14 @@ __device__ __forceinline__ void ring_build_Z(const PlanDev& P, const RingSub& S,
     if (split) {
         const int J = S.nt / n, kq = S.tid % n, jq = S.tid / n;
         double2 z[1] = {zero};
-        if (jq < J) ring_fold<SH, 1, 4>(P, job, Fm, FA, FB, n, mtop, nterm, kq, 1, jq, J, ring_phase(P, job.ringA, kq), zero, q, z);
+        if (jq < J) ring_fold<SH, 1, 4>(P, job, Fm, FA, FB, fs, n, mtop, nterm, kq, 1, jq, J, ring_phase(P, job.ringA, kq), zero, q, z);
         scratch[S.tid] = z[0];
     } else if (n >= 4 * S.nt) {
         double2 pk = ring_phase(P, job.ringA, S.tid);
         const double2 step = ring_phase(P, job.ringA, S.nt), step4 = ring_phase(P, job.ringA, 4 * S.nt);
         for (int k0 = S.tid; k0 < n; k0 += 4 * S.nt) {
             double2 z[4];
-            ring_fold<SH, 4, 1>(P, job, Fm, FA, FB, n, mtop, nterm, k0, S.nt, 0, 1, pk, step, q, z);
+            ring_fold<SH, 4, 1>(P, job, Fm, FA, FB, fs, n, mtop, nterm, k0, S.nt, 0, 1, pk, step, q, z);
 #pragma unroll
             for (int u = 0; u < 4; ++u) put(k0 + u * S.nt, z[u]);
             pk = cmul(pk, step4);
@@ -402,7 +406,7 @@ __device__ __forceinline__ void ring_build_Z(const PlanDev& P, const RingSub& S,
         const double2 step = ring_phase(P, job.ringA, S.nt);
         for (int k0 = S.tid; k0 < n; k0 += S.nt) {
             double2 z[1];
-            ring_fold<SH, 1, 4>(P, job, Fm, FA, FB, n, mtop, nterm, k0, S.nt, 0, 1, pk, step, q, z);
+            ring_fold<SH, 1, 4>(P, job, Fm, FA, FB, fs, n, mtop, nterm, k0, S.nt, 0, 1, pk, step, q, z);
             put(k0, z[0]);
             pk = cmul(pk, step);
         }
@@ -473,7 +477,7 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
     double2* twq = smem;
     load_twq(P, twq);
     const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
-    ring_build_Z<SH>(P, S, Fm, min(mcap, ring_mtop(P, S.job.ringA, spin2)), S.scratch);
+    ring_build_Z<SH>(P, S, Fm, min(mcap, ring_mtop(P, S.job.ringA, spin2)), S.scratch, mmax != nullptr);
     ring_idft(P, S.buf, twq, S.n, S.bsi, S.tid, S.nt);
     double* oa = (S.job.compA ? mapU : mapQ) + ring_first_pixel<SH>(P, S.job.ringA);
     double* ob = S.job.ringB >= 0 ? (S.job.compB ? mapU : mapQ) + ring_first_pixel<SH>(P, S.job.ringB) : nullptr;

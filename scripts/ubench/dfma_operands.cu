@@ -55,6 +55,9 @@ int main()
     printf("%-34s %7s %7s %7s %7s %7s\n", "pattern", "1", "2", "3", "4", "8");
     const int cs[5] = {1, 2, 3, 4, 8};
 #define ROW(MODE, NCH, name) { printf("%-34s", name); for (int c : cs) printf(" %7.2f", run<MODE, NCH>(c)); printf("\n"); }
+    ROW(0, 1, "fma(v,a,b) 1 chain (latency)");
+    ROW(0, 2, "fma(v,a,b) 2 chains");
+    ROW(0, 4, "fma(v,a,b) 4 chains");
     ROW(0, 8, "fma(v,a,b) 8 chains");
     ROW(0, 16, "fma(v,a,b) 16 chains");
     ROW(1, 8, "fma(v,w_k,u_k) 8 chains");
