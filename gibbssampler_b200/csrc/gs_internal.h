@@ -172,6 +172,7 @@ struct gs_plan {
     double* almB_tmp2;
 };
 
+extern int g_gs_ring_skip;        // 1: rings whose pixel weights vanish identically are left out (PCG mat-vec, Metropolis sweep)
 extern int g_gs_ring_fused;       // 1: the PCG mat-vec runs its ring stage as one fused kernel (ring_apply_kernel)
 extern long long g_gs_launches;  // kernels launched by this library (bench.py's gpu_launches)
 static inline int64_t gs_nalm(int lmax) { return (int64_t)(lmax + 1) * (lmax + 2) / 2; }
@@ -191,7 +192,7 @@ int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, c
                  const int* skip = nullptr);
 int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, const int* skip = nullptr);
 int gs_ring_synth_batch(gs_plan* p, const double2* F, int64_t f_stride, const int* mmax, double* mapQ, double* mapU,
-                        int64_t map_stride, int nb, cudaStream_t st);
+                        int64_t map_stride, int nb, cudaStream_t st, const unsigned char* ract = nullptr);
 // legendre.cu: block-batched spin-2 synthesis for the Metropolis-within-Gibbs sweep (see leg_synth_blocks_kernel)
 int gs_leg_synth_blocks(gs_plan* p, const double* almE, const double* almB, const double* dflE, const double* dflB,
                         const int* lbE, int e0, int e1, const int* lbB, int b0, int b1, int lend, double2* Fblk, cudaStream_t st);

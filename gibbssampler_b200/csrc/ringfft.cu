@@ -465,9 +465,18 @@ template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
 ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __restrict__ groups, const double2* __restrict__ Fm,
                   double* __restrict__ mapQ, double* __restrict__ mapU, const int* __restrict__ skip, int64_t f_stride,
-                  int64_t map_stride, const int* __restrict__ mmax, int spin2)
+                  int64_t map_stride, const int* __restrict__ mmax, int spin2, const unsigned char* __restrict__ ract)
 {
     if (skip && *skip) return;
+    if (ract) {   // rings without pixel weight: their pixels are never looked at (Metropolis sweep, gs_active_rings_build)
+        const int2 g = groups[blockIdx.x];
+        bool any = false;
+        for (int s = 0; s < g.y; ++s) {
+            const RingJob jb = jobs[g.x + s];
+            any = any || ract[jb.ringA] || (jb.ringB >= 0 && ract[jb.ringB]);
+        }
+        if (!any) return;
+    }
     extern __shared__ double2 smem[];
     // batched use (blockIdx.y = transform index): spectra at Fm + y f_stride hold m <= mmax[y] only, maps at + y map_stride
     Fm += blockIdx.y * f_stride;
@@ -937,8 +946,8 @@ int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t
         g_gs_launches += 2;
     }
     if (nj > 0) {
-        if (sh) ring_synth_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr, spin ? 1 : 0);
-        else ring_synth_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr, spin ? 1 : 0);
+        if (sh) ring_synth_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr, spin ? 1 : 0, nullptr);
+        else ring_synth_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr, spin ? 1 : 0, nullptr);
         GS_CHECK_LAUNCH();
     }
     g_gs_launches += 1;
@@ -997,12 +1006,12 @@ int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, con
 
 // nb spin-2 ring syntheses in one launch: spectra F + k f_stride (m <= mmax[k]) -> maps Q/U + k map_stride
 int gs_ring_synth_batch(gs_plan* p, const double2* F, int64_t f_stride, const int* mmax, double* mapQ, double* mapU,
-                        int64_t map_stride, int nb, cudaStream_t st)
+                        int64_t map_stride, int nb, cudaStream_t st, const unsigned char* ract)
 {
     if (p->world > 1 || p->nsjobs2 > 0) { gs_set_error("batched ring synthesis needs an unsharded plan without split rings"); return GS_E_BADARG; }
     if (nb <= 0 || p->ngroups2 <= 0) return GS_OK;
     ring_synth_kernel<false><<<dim3(p->ngroups2, nb), RF_NT, p->ring_smem, st>>>(p->d, p->jobs2, p->groups2, F, mapQ, mapU, nullptr, f_stride,
-                                                                                 map_stride, mmax, 1);
+                                                                                 map_stride, mmax, 1, ract);
     GS_CHECK_LAUNCH();
     g_gs_launches += 1;
     return GS_OK;

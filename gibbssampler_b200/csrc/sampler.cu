@@ -514,6 +514,8 @@ extern "C" int gs_mwg_sweep_blocks(gs_plan* p, const double* snc_E, const double
         if (p->mwg_F) { cudaFree(p->mwg_F); cudaFree(p->mwg_maps); p->mwg_F = nullptr; p->mwg_maps = nullptr; p->mwg_group = 0; }
         GS_CHECK_CUDA(cudaMalloc(&p->mwg_F, (size_t)G * slotF * 16));
         GS_CHECK_CUDA(cudaMalloc(&p->mwg_maps, (size_t)G * 2 * npix * 8));
+        // rings without pixel weight are not synthesised below: their (never written) pixels meet N^-1 = 0 and must be finite
+        GS_CHECK_CUDA(cudaMemsetAsync(p->mwg_maps, 0, (size_t)G * 2 * npix * 8, st));
         p->mwg_group = G;
     }
     G = p->mwg_group;
@@ -545,6 +547,13 @@ extern "C" int gs_mwg_sweep_blocks(gs_plan* p, const double* snc_E, const double
     double* rU = p->mapU_tmp;
 
     GS_CHECK_CUDA(cudaMemsetAsync(flags, 0, (ntot + 1) * sizeof(int), st));
+    // block maps are only ever weighted by N^-1: the rings on which it vanishes identically need no ring FFT
+    const unsigned char* ract = nullptr;
+    if (g_gs_ring_skip) {
+        int rc0 = gs_active_rings_build(p, inv_noise, st);
+        if (rc0) return rc0;
+        ract = p->act_ring;
+    }
     const int eb0 = nblk_E ? blocks_E_host[0] : 0, eb1 = nblk_E ? blocks_E_host[nblk_E] : 0;
     const int bb0 = nblk_B ? blocks_B_host[0] : 0, bb1 = nblk_B ? blocks_B_host[nblk_B] : 0;
     mwg_dfl_kernel<<<(L + 128) / 128, 128, 0, st>>>(cur_E, cur_B, prop_E, prop_B, bins_E, nbins_E, bins_B, nbins_B, eb0, eb1, bb0, bb1,
@@ -567,7 +576,7 @@ extern "C" int gs_mwg_sweep_blocks(gs_plan* p, const double* snc_E, const double
         if (b1 > b0) lend = std::max(lend, meta[off_lbB + b1]);
         lend = std::min(lend, L + 1);
         if ((rc = gs_leg_synth_blocks(p, snc_E, snc_B, dflE, dflB, lbE, e0, e1, lbB, b0, b1, lend, p->mwg_F, st))) return rc;
-        if ((rc = gs_ring_synth_batch(p, p->mwg_F, slotF, mmax + g0, p->mwg_maps, p->mwg_maps + (int64_t)G * npix, npix, ng, st)))
+        if ((rc = gs_ring_synth_batch(p, p->mwg_F, slotF, mmax + g0, p->mwg_maps, p->mwg_maps + (int64_t)G * npix, npix, ng, st, ract)))
             return rc;
         for (int k = g0; k < g1; ++k) {
             const bool isE = k < nblk_E;
