@@ -156,6 +156,7 @@ struct gs_plan {
     unsigned char* act_ring;  // [nring] 1 = some pixel weight of the ring is non-zero
     int* act_pairs;           // [npair] ascending list of pairs with an active north or south ring
     int* act_count;           // device int: entries of act_pairs
+    double* act_red;          // [nring] sharded plans: ring flags as doubles for the sum over ranks
     int* act_slot0;           // [2][lmax+1] (spin 0, spin 2): first entry of act_pairs whose pair reaches m
     bool use_act;
     // workspace

@@ -942,14 +942,25 @@ __global__ void leg_finish_kernel(PlanDev P, const double* __restrict__ partial,
 // nothing: their synthesis is multiplied by zero and their analysis input is zero.  gs_active_rings_build marks the rings
 // that carry weight and compacts the ring PAIRS with at least one such ring into an ascending list, all on the device
 // (no host round trip); the Legendre kernels then walk that list and the fused ring stage drops the CTAs of idle rings.
-__global__ void __launch_bounds__(256) ring_active_kernel(PlanDev P, const double* __restrict__ pixw, unsigned char* __restrict__ act)
+// SH: the weight map is this rank's ring-sharded local map; every rank marks its own rings in `actd` (doubles, summed over
+// the ranks by the caller), the others stay zero
+template <bool SH>
+__global__ void __launch_bounds__(256) ring_active_kernel(PlanDev P, const double* __restrict__ pixw, unsigned char* __restrict__ act,
+                                                          double* __restrict__ actd)
 {
     const int ring = blockIdx.x, n = P.ring_nphi[ring];
-    const double* w = pixw + P.ring_start[ring];
+    if (SH && P.sh.ring_owner[ring] != P.sh.rank) { if (threadIdx.x == 0) actd[ring] = 0.0; return; }
+    const double* w = pixw + (SH ? P.sh.ring_start_loc[ring] : P.ring_start[ring]);
     int any = 0;
     for (int j = threadIdx.x; j < n; j += blockDim.x) any |= (w[j] != 0.0);
     any = __syncthreads_or(any);
-    if (threadIdx.x == 0) act[ring] = any ? 1 : 0;
+    if (threadIdx.x == 0) { if (SH) actd[ring] = any ? 1.0 : 0.0; else act[ring] = any ? 1 : 0; }
+}
+
+__global__ void ring_flags_kernel(const double* __restrict__ actd, unsigned char* __restrict__ act, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) act[i] = actd[i] > 0.0 ? 1 : 0;
 }
 
 __global__ void __launch_bounds__(1024) pair_compact_kernel(PlanDev P, unsigned char* act, int* __restrict__ list,
@@ -997,8 +1008,15 @@ __global__ void __launch_bounds__(256) list_slot0_kernel(PlanDev P, const int* _
 
 int gs_active_rings_build(gs_plan* p, const double* pixw, cudaStream_t st)
 {
-    if (p->world > 1) { gs_set_error("active-ring lists need an unsharded plan"); return GS_E_BADARG; }
-    ring_active_kernel<<<p->d.nring, 256, 0, st>>>(p->d, pixw, p->act_ring);
+    if (p->world > 1) {   // ring-sharded weights: local flags, summed over the ranks (every rank builds the same lists)
+        ring_active_kernel<true><<<p->d.nring, 256, 0, st>>>(p->d, pixw, p->act_ring, p->act_red);
+        GS_CHECK_LAUNCH();
+        int rc = gs_shard_allreduce(p, p->act_red, p->d.nring, st);
+        if (rc) return rc;
+        ring_flags_kernel<<<(p->d.nring + 255) / 256, 256, 0, st>>>(p->act_red, p->act_ring, p->d.nring);
+    } else {
+        ring_active_kernel<false><<<p->d.nring, 256, 0, st>>>(p->d, pixw, p->act_ring, nullptr);
+    }
     pair_compact_kernel<<<1, 1024, 0, st>>>(p->d, p->act_ring, p->act_pairs, p->act_count);
     list_slot0_kernel<<<(2 * (p->d.lmax + 1) * 32 + 255) / 256, 256, 0, st>>>(p->d, p->act_pairs, p->act_count, p->act_slot0);
     GS_CHECK_LAUNCH();
@@ -1013,7 +1031,7 @@ int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, i
     const bool sh = p->world > 1;
     if (sh && layout != GS_ALM_REAL) { gs_set_error("sharded plans take the (local) real alm layout only"); return GS_E_BADARG; }
     dim3 grid((p->d.npair + LEG_NT * LEG_R - 1) / (LEG_NT * LEG_R), sh ? p->d.sh.nm_loc : p->d.lmax + 1);
-    const int* plist = (p->use_act && !sh) ? p->act_pairs : nullptr;
+    const int* plist = p->use_act ? p->act_pairs : nullptr;
     const int* pcount = plist ? p->act_count : nullptr;
     const int* slot0 = plist ? p->act_slot0 + (spin ? p->d.lmax + 1 : 0) : (spin ? p->d.pmin2 : p->d.pmin0);
     if (!sh) {
@@ -1040,7 +1058,7 @@ int gs_leg_anal(gs_plan* p, int spin, double* almE, double* almB, int layout, co
     const int nmy = sh ? p->d.sh.nm_loc : p->d.lmax + 1;
     dim3 grid(nchunk, nmy);
     dim3 fgrid((p->d.lmax + 256) / 256, nmy);
-    const int* plist = (p->use_act && !sh) ? p->act_pairs : nullptr;
+    const int* plist = p->use_act ? p->act_pairs : nullptr;
     const int* pcount = plist ? p->act_count : nullptr;
     const int* slot0 = plist ? p->act_slot0 + (spin ? p->d.lmax + 1 : 0) : (spin ? p->d.pmin2 : p->d.pmin0);
     if (sh) {  // ring-sharded (p->Fx, written by the ring analysis) -> m-sharded

@@ -243,6 +243,7 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
     p->act_pairs = nullptr;
     p->act_count = nullptr;
     p->act_slot0 = nullptr;
+    p->act_red = nullptr;
     p->use_act = false;
     p->mwg_F = nullptr;
     p->mwg_maps = nullptr;
@@ -278,6 +279,7 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->d.npair, &p->act_pairs);
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)1, &p->act_count);
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)2 * (lmax + 1), &p->act_slot0);
+        if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->d.nring, &p->act_red);
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->npix_loc, &p->mapQ_tmp);
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->npix_loc, &p->mapU_tmp);
         const size_t nre = (size_t)p->nreal_loc;  // big enough for either layout

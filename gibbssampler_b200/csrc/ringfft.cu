@@ -257,6 +257,24 @@ __device__ __forceinline__ int ring_mtop(const PlanDev& P, int ring, int spin2)
     return spin2 ? P.mlim2[p] : P.mlim0[p];
 }
 
+// Rings without pixel weight (gs_active_rings_build; flags are per ring PAIR): nobody reads what the ring stage would
+// produce for them.  ract == nullptr: every ring is processed.
+__device__ __forceinline__ bool group_idle(const unsigned char* __restrict__ ract, const RingJob* __restrict__ jobs, const int2* __restrict__ groups)
+{
+    if (!ract) return false;
+    const int2 g = groups[blockIdx.x];
+    bool any = false;
+    for (int s = 0; s < g.y; ++s) {
+        const RingJob jb = jobs[g.x + s];
+        any = any || ract[jb.ringA] || (jb.ringB >= 0 && ract[jb.ringB]);
+    }
+    return !any;
+}
+__device__ __forceinline__ bool split_idle(const unsigned char* __restrict__ ract, const SplitJob& jb)
+{
+    return ract && !(ract[jb.ringA] || (jb.ringB >= 0 && ract[jb.ringB]));
+}
+
 // A CTA of the direct ring kernels works on a GROUP of 1, 2 or 4 jobs whose transforms have the same length M and
 // the same kind (power of two / Bluestein), RF_NT / nsub threads each, side by side in shared memory: the passes of a
 // short transform cannot keep 256 threads busy (M / 16 radix-16 butterflies per pass) and the ring stage is latency
@@ -468,15 +486,7 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
                   int64_t map_stride, const int* __restrict__ mmax, int spin2, const unsigned char* __restrict__ ract)
 {
     if (skip && *skip) return;
-    if (ract) {   // rings without pixel weight: their pixels are never looked at (Metropolis sweep, gs_active_rings_build)
-        const int2 g = groups[blockIdx.x];
-        bool any = false;
-        for (int s = 0; s < g.y; ++s) {
-            const RingJob jb = jobs[g.x + s];
-            any = any || ract[jb.ringA] || (jb.ringB >= 0 && ract[jb.ringB]);
-        }
-        if (!any) return;
-    }
+    if (group_idle(ract, jobs, groups)) return;
     extern __shared__ double2 smem[];
     // batched use (blockIdx.y = transform index): spectra at Fm + y f_stride hold m <= mmax[y] only, maps at + y map_stride
     Fm += blockIdx.y * f_stride;
@@ -502,9 +512,10 @@ template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
 ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __restrict__ groups, const double* __restrict__ mapQ,
                  const double* __restrict__ mapU, const double* __restrict__ pixw, double2* __restrict__ Fm, const int* __restrict__ skip,
-                 int spin2)
+                 int spin2, const unsigned char* __restrict__ ract)
 {
     if (skip && *skip) return;
+    if (group_idle(ract, jobs, groups)) return;
     extern __shared__ double2 smem[];
     double2* twq = smem;
     load_twq(P, twq);
@@ -552,15 +563,7 @@ ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
                   const double* __restrict__ pixw, const int* __restrict__ skip, const unsigned char* __restrict__ ract, int spin2)
 {
     if (skip && *skip) return;
-    if (ract) {   // a group whose rings all have zero weight maps to zero: nobody reads its spectra (gs_active_rings_build)
-        const int2 g = groups[blockIdx.x];
-        bool any = false;
-        for (int s = 0; s < g.y; ++s) {
-            const RingJob jb = jobs[g.x + s];
-            any = any || ract[jb.ringA] || (jb.ringB >= 0 && ract[jb.ringB]);
-        }
-        if (!any) return;
-    }
+    if (group_idle(ract, jobs, groups)) return;
     extern __shared__ double2 smem[];
     double2* twq = smem;
     load_twq(P, twq);
@@ -642,11 +645,12 @@ __device__ __forceinline__ double2 unit_root(int num, int n)
 template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
 ring_synth_split_kernel(PlanDev P, const SplitJob* __restrict__ jobs, const double2* __restrict__ Fm, double2* __restrict__ scratch,
-                        const int* __restrict__ skip, int spin2)
+                        const int* __restrict__ skip, int spin2, const unsigned char* __restrict__ ract)
 {
     if (skip && *skip) return;
     extern __shared__ double2 smem[];
     const SplitJob job = jobs[blockIdx.x >> 2];
+    if (split_idle(ract, job)) return;
     const int mtop = ring_mtop(P, job.ringA, spin2);
     const int b = blockIdx.x & 3;
     const int n = P.ring_nphi[job.ringA], n2 = n >> 2, bsi = job.bs2;
@@ -681,10 +685,11 @@ ring_synth_split_kernel(PlanDev P, const SplitJob* __restrict__ jobs, const doub
 template <bool SH>
 __global__ void __launch_bounds__(RF_NT)
 ring_synth_combine_kernel(PlanDev P, const SplitJob* __restrict__ jobs, const double2* __restrict__ scratch, double* __restrict__ mapQ,
-                          double* __restrict__ mapU, const int* __restrict__ skip)
+                          double* __restrict__ mapU, const int* __restrict__ skip, const unsigned char* __restrict__ ract)
 {
     if (skip && *skip) return;
     const SplitJob job = jobs[blockIdx.x];
+    if (split_idle(ract, job)) return;
     const int n = P.ring_nphi[job.ringA], n2 = n >> 2;
     const double2* Y = scratch + job.off;
     double* oa = (job.compA ? mapU : mapQ) + ring_first_pixel<SH>(P, job.ringA);
@@ -704,11 +709,12 @@ ring_synth_combine_kernel(PlanDev P, const SplitJob* __restrict__ jobs, const do
 template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
 ring_anal_split_kernel(PlanDev P, const SplitJob* __restrict__ jobs, const double* __restrict__ mapQ, const double* __restrict__ mapU,
-                       const double* __restrict__ pixw, double2* __restrict__ scratch, const int* __restrict__ skip)
+                       const double* __restrict__ pixw, double2* __restrict__ scratch, const int* __restrict__ skip, const unsigned char* __restrict__ ract)
 {
     if (skip && *skip) return;
     extern __shared__ double2 smem[];
     const SplitJob job = jobs[blockIdx.x >> 2];
+    if (split_idle(ract, job)) return;
     const int b = blockIdx.x & 3;
     const int n = P.ring_nphi[job.ringA], n2 = n >> 2, bsi = job.bs2;
     double2* twq = smem;
@@ -747,10 +753,11 @@ ring_anal_split_kernel(PlanDev P, const SplitJob* __restrict__ jobs, const doubl
 template <bool SH>
 __global__ void __launch_bounds__(RF_NT)
 ring_anal_finish_kernel(PlanDev P, const SplitJob* __restrict__ jobs, const double2* __restrict__ scratch, double2* __restrict__ Fm,
-                        const int* __restrict__ skip)
+                        const int* __restrict__ skip, const unsigned char* __restrict__ ract)
 {
     if (skip && *skip) return;
     const SplitJob job = jobs[blockIdx.x];
+    if (split_idle(ract, job)) return;
     const int L = P.lmax, n = P.ring_nphi[job.ringA], n2 = n >> 2;
     const double2* Cs = scratch + job.off;
     for (int m = threadIdx.x; m <= L; m += RF_NT) {
@@ -931,23 +938,24 @@ int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t
     const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
     const int2* grp = spin == 0 ? p->groups0 : p->groups2;
     const SplitJob* sj = spin == 0 ? p->sjobs0 : p->sjobs2;
+    const unsigned char* ract = p->use_act ? p->act_ring : nullptr;   // PCG mat-vec: rings without pixel weight are left out
     double* mu = spin == 0 ? mapQ : mapU;
     const bool sh = p->world > 1;
     const double2* F = sh ? p->Fx : p->Fm;
     if (ns > 0) {  // long rings first: they are the heavy ones
         if (sh) {
-            ring_synth_split_kernel<true><<<4 * ns, RF_NT, p->split_smem, st>>>(p->d, sj, F, p->ring_scratch, skip, spin ? 1 : 0);
-            ring_synth_combine_kernel<true><<<ns, RF_NT, 0, st>>>(p->d, sj, p->ring_scratch, mapQ, mu, skip);
+            ring_synth_split_kernel<true><<<4 * ns, RF_NT, p->split_smem, st>>>(p->d, sj, F, p->ring_scratch, skip, spin ? 1 : 0, ract);
+            ring_synth_combine_kernel<true><<<ns, RF_NT, 0, st>>>(p->d, sj, p->ring_scratch, mapQ, mu, skip, ract);
         } else {
-            ring_synth_split_kernel<false><<<4 * ns, RF_NT, p->split_smem, st>>>(p->d, sj, F, p->ring_scratch, skip, spin ? 1 : 0);
-            ring_synth_combine_kernel<false><<<ns, RF_NT, 0, st>>>(p->d, sj, p->ring_scratch, mapQ, mu, skip);
+            ring_synth_split_kernel<false><<<4 * ns, RF_NT, p->split_smem, st>>>(p->d, sj, F, p->ring_scratch, skip, spin ? 1 : 0, ract);
+            ring_synth_combine_kernel<false><<<ns, RF_NT, 0, st>>>(p->d, sj, p->ring_scratch, mapQ, mu, skip, ract);
         }
         GS_CHECK_LAUNCH();
         g_gs_launches += 2;
     }
     if (nj > 0) {
-        if (sh) ring_synth_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr, spin ? 1 : 0, nullptr);
-        else ring_synth_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr, spin ? 1 : 0, nullptr);
+        if (sh) ring_synth_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr, spin ? 1 : 0, ract);
+        else ring_synth_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr, spin ? 1 : 0, ract);
         GS_CHECK_LAUNCH();
     }
     g_gs_launches += 1;
@@ -961,23 +969,24 @@ int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, c
     const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
     const int2* grp = spin == 0 ? p->groups0 : p->groups2;
     const SplitJob* sj = spin == 0 ? p->sjobs0 : p->sjobs2;
+    const unsigned char* ract = p->use_act ? p->act_ring : nullptr;
     const double* mu = spin == 0 ? mapQ : mapU;
     const bool sh = p->world > 1;
     double2* F = sh ? p->Fx : p->Fm;
     if (ns > 0) {
         if (sh) {
-            ring_anal_split_kernel<true><<<4 * ns, RF_NT, p->split_smem, st>>>(p->d, sj, mapQ, mu, pixw, p->ring_scratch, skip);
-            ring_anal_finish_kernel<true><<<ns, RF_NT, 0, st>>>(p->d, sj, p->ring_scratch, F, skip);
+            ring_anal_split_kernel<true><<<4 * ns, RF_NT, p->split_smem, st>>>(p->d, sj, mapQ, mu, pixw, p->ring_scratch, skip, ract);
+            ring_anal_finish_kernel<true><<<ns, RF_NT, 0, st>>>(p->d, sj, p->ring_scratch, F, skip, ract);
         } else {
-            ring_anal_split_kernel<false><<<4 * ns, RF_NT, p->split_smem, st>>>(p->d, sj, mapQ, mu, pixw, p->ring_scratch, skip);
-            ring_anal_finish_kernel<false><<<ns, RF_NT, 0, st>>>(p->d, sj, p->ring_scratch, F, skip);
+            ring_anal_split_kernel<false><<<4 * ns, RF_NT, p->split_smem, st>>>(p->d, sj, mapQ, mu, pixw, p->ring_scratch, skip, ract);
+            ring_anal_finish_kernel<false><<<ns, RF_NT, 0, st>>>(p->d, sj, p->ring_scratch, F, skip, ract);
         }
         GS_CHECK_LAUNCH();
         g_gs_launches += 2;
     }
     if (nj > 0) {
-        if (sh) ring_anal_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, mapQ, mu, pixw, F, skip, spin ? 1 : 0);
-        else ring_anal_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, mapQ, mu, pixw, F, skip, spin ? 1 : 0);
+        if (sh) ring_anal_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, mapQ, mu, pixw, F, skip, spin ? 1 : 0, ract);
+        else ring_anal_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, mapQ, mu, pixw, F, skip, spin ? 1 : 0, ract);
         GS_CHECK_LAUNCH();
     }
     g_gs_launches += 1;
@@ -997,7 +1006,7 @@ int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, con
     if (nj <= 0) return GS_OK;
     const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
     const int2* grp = spin == 0 ? p->groups0 : p->groups2;
-    if (p->world > 1) ring_apply_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fx, pixw, skip, nullptr, spin ? 1 : 0);
+    if (p->world > 1) ring_apply_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fx, pixw, skip, p->use_act ? p->act_ring : nullptr, spin ? 1 : 0);
     else ring_apply_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fm, pixw, skip, p->use_act ? p->act_ring : nullptr, spin ? 1 : 0);
     GS_CHECK_LAUNCH();
     g_gs_launches += 1;

@@ -268,7 +268,7 @@ struct ActiveRings {   // scope guard: the plan's launchers use the active lists
     ActiveRings(gs_plan* p_) : p(p_), on(false) {}
     int begin(const double* pixw, cudaStream_t st)
     {
-        if (!g_gs_ring_skip || p->world > 1 || !pixw) return GS_OK;
+        if (!g_gs_ring_skip || !pixw) return GS_OK;
         int rc = gs_active_rings_build(p, pixw, st);
         if (rc == GS_OK) { p->use_act = true; on = true; }
         return rc;

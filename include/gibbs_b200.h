@@ -364,8 +364,9 @@ int gs_set_ring_fused(int fused);
 /* Rings whose pixel weights N^-1 vanish identically (inside a mask) contribute exactly nothing to A^T N^-1 A.  on != 0
  * (default): gs_cr_pcg_* / gs_cr_apply_q_* / gs_profile_matvec mark those rings from the weight map they are given (two
  * small kernels per call, no host round trip) and the Legendre and ring kernels of the mat-vec leave them out; 0: every
- * ring is processed.  Same result up to the rounding of a re-associated sum.  Unsharded plans only (sharded plans always
- * process every ring).  Returns the previous setting. */
+ * ring is processed.  Same result up to the rounding of a re-associated sum.  On sharded plans the ranks mark their own
+ * rings and sum the flags (one small all-reduce per call).  gs_mwg_sweep_blocks skips the ring FFTs of those rings too.
+ * Returns the previous setting. */
 int gs_set_ring_skip(int on);
 /* Number of ring pairs (north/south) with a non-zero weight found by the last such call on this plan, and the total. */
 int gs_active_ring_pairs(gs_plan* plan, int* active_out, int* total_out);

@@ -108,7 +108,7 @@ def _cr_problem(nside, lmax, seed=3):
 
 @pytest.mark.parametrize("nside,lmax,world", [(16, 32, 2), (32, 64, 4)])
 def test_local_group_cr_solve_matches_single_gpu(nside, lmax, world):
-    from gibbssampler_b200 import _dev, utils
+    from gibbssampler_b200 import _dev, _lib, utils
     from gibbssampler_b200.CenteredGibbs import PolarizedCenteredConstrainedRealization as CR
     from gibbssampler_b200.sharded import ShardedPlan, run_local_group
     dlE, dlB, bl, noise_var, mask, dQ, dU, xi = _cr_problem(nside, lmax)
@@ -127,8 +127,10 @@ def test_local_group_cr_solve_matches_single_gpu(nside, lmax, world):
         cr = CR({"Q": dQ, "U": dU}, 1.0, noise_var, bl_map, lmax, npix, fwhm, mask=mask, rng="philox", seed=1, plan=p)
         cr.pcg_accuracy = 1e-9
         s, _ = cr.sample_mask(dls, xi=xid)
+        act, tot = C.c_int(-1), C.c_int(-1)
+        _lib.check(_lib.lib().gs_active_ring_pairs(p._h, C.byref(act), C.byref(tot)))
         return dict(e=s["EE"], b=s["BB"], re=cr.last_rhs[0], rb=cr.last_rhs[1], it=cr.last_pcg_iterations,
-                    ninv=cr.ninv_sum_over_4pi)
+                    ninv=cr.ninv_sum_over_4pi, act=(act.value, tot.value))
 
     res = run_local_group(plans, work)
 
@@ -139,6 +141,8 @@ def test_local_group_cr_solve_matches_single_gpu(nside, lmax, world):
         return out
 
     assert abs(res[0]["ninv"] - ref.ninv_sum_over_4pi) < 1e-12 * ref.ninv_sum_over_4pi
+    # the ring pairs wholly inside the mask are left out of the sharded mat-vec too: every rank holds the same global list
+    assert len({r["act"] for r in res}) == 1 and 0 < res[0]["act"][0] < res[0]["act"][1] == 2 * nside, [r["act"] for r in res]
     assert relerr(join("re"), rhs_ref[0]) < RTOL and relerr(join("rb"), rhs_ref[1]) < RTOL
     its = [r["it"] for r in res]
     assert len(set(its)) == 1, its                                     # every rank stops at the same iteration
