@@ -80,13 +80,21 @@ class PolarizationNonCenteredClsSampler(MHClsSampler):
             self.inv_noise_pol = self.inv_noise_pol * f64(m)
         self.sigma = 0.8
         self.Npix = 12 * nside ** 2
-        self.all_sph = all_sph
+        self.all_sph = bool(all_sph)
         self.l_cut = int(l_cut)
-        if all_sph:
-            raise NotImplementedError("all_sph likelihood (NonCenteredGibbs.py:357-377) is not provided; use all_sph=False")
         from .sht import Plan
         self.plan = Plan.get(self.nside, self.lmax)
-        self.d_Q, self.d_U = f64(pix_map["Q"]), f64(pix_map["U"])
+        if self.all_sph:
+            # full sky, isotropic noise, data in harmonic space (NonCenteredGibbs.py:273-274, 357-377): the likelihood is a sum
+            # over the real alm layout weighted by N^-1[0] Npix / 4 pi
+            if m is not None:
+                raise ValueError("all_sph=True needs a full sky (no mask), NonCenteredGibbs.py:273-274")
+            self.d_E, self.d_B = f64(pix_map["EE"]), f64(pix_map["BB"])
+            self.allsph_weight = float(self.inv_noise_pol[0].item()) * self.Npix / (4.0 * np.pi)
+        if "Q" in pix_map and "U" in pix_map:
+            self.d_Q, self.d_U = f64(pix_map["Q"]), f64(pix_map["U"])
+        elif not self.all_sph:
+            raise KeyError("pix_map needs the pixel maps 'Q' and 'U'")
         fw = getattr(self, "bl_gauss", None)
         # b_l from the expanded bl_map: entries 0..lmax are the m = 0 column
         self.bl_gauss_d = f64(bl_map)[: self.lmax + 1].contiguous()
@@ -98,7 +106,7 @@ class PolarizationNonCenteredClsSampler(MHClsSampler):
         self._flE = torch.empty(self.lmax + 1, dtype=torch.float64, device=self.dev)
         self._flB = torch.empty_like(self._flE)
         self._scratch = torch.empty(592, dtype=torch.float64, device=self.dev)
-        self.batched_blocks = bool(batched_blocks) and self.nside <= 1024
+        self.batched_blocks = bool(batched_blocks) and self.nside <= 1024 and not self.all_sph
         self.workspace_bytes = int(workspace_bytes)
         self._bins_h = {p: np.ascontiguousarray(self.bins[p], dtype=np.int32) for p in ("EE", "BB")}
         self._blocks_h = {p: np.ascontiguousarray(self.metropolis_blocks[p], dtype=np.int32) for p in ("EE", "BB")}
@@ -122,18 +130,28 @@ class PolarizationNonCenteredClsSampler(MHClsSampler):
         check(L.gs_mwg_filters(ptr(cur["EE"]), ptr(cur["BB"]), ptr(pe), ptr(pb), ptr(self.bins_d["EE"]), self.nb["EE"],
                                ptr(self.bins_d["BB"]), self.nb["BB"], pol, b0, b1, ptr(self.bl_gauss_d), self.lmax, self.l_cut,
                                ptr(self._flE), ptr(self._flB), stream()))
+        if self.all_sph:   # compute_log_MH_ratio's all_sph branch (NonCenteredGibbs.py:385-393)
+            check(L.gs_loglik_alm(ptr(self.d_E), ptr(self.d_B), ptr(s_nc["EE"]), ptr(s_nc["BB"]), ptr(self._flE), ptr(self._flB),
+                                  self.lmax, self.allsph_weight, ptr(self._scratch), ptr(out), stream()))
+            return
         check(L.gs_alm2map_spin2_fl2(self.plan._h, ptr(s_nc["EE"]), ptr(s_nc["BB"]), GS_ALM_REAL, ptr(self._flE), ptr(self._flB),
                                      ptr(self._mq), ptr(self._mu), stream()))
         check(L.gs_loglik_pix(ptr(self.d_Q), ptr(self.d_U), ptr(self._mq), ptr(self._mu), ptr(self.inv_noise_pol), self.Npix,
                               ptr(self._scratch), ptr(out), stream()))
 
     def compute_log_likelihood(self, dls, s_nonCentered):
-        """NonCenteredGibbs.py:333-355 -> python float."""
+        """NonCenteredGibbs.py:333-355 (pixel domain; with all_sph=True the harmonic form of :357-377) -> python float."""
         cur = {p: f64(dls[p]) for p in ("EE", "BB")}
         s = {p: f64(s_nonCentered[p]) for p in ("EE", "BB")}
         out = torch.empty(1, dtype=torch.float64, device=self.dev)
         self._loglik_device(cur, None, -1, 0, 0, s, out)
         return float(out.item())
+
+    def compute_log_likelihood_all_sph(self, dls, s_nonCentered):
+        """NonCenteredGibbs.py:357-377 -> python float (needs all_sph=True at construction: harmonic data, no mask)."""
+        if not self.all_sph:
+            raise ValueError("compute_log_likelihood_all_sph needs a sampler built with all_sph=True")
+        return self.compute_log_likelihood(dls, s_nonCentered)
 
     def sample(self, s_nonCentered, binned_dls_old):
         """Blocked Metropolis-within-Gibbs sweep (NonCenteredGibbs.py:401-445); same return values."""

@@ -55,6 +55,7 @@ SIGNATURES = {
     "gs_truncnorm_propose": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "gs_truncnorm_logpdf": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),
     "gs_loglik_pix": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "gs_loglik_alm": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _d, _vp, _vp, _vp]),
     "gs_randn": (_i, [_vp, _i64, C.c_uint64, C.c_uint64, _vp]),
     "gs_randu": (_i, [_vp, _i64, C.c_uint64, C.c_uint64, _vp]),
     "gs_sum": (_i, [_vp, _i64, _vp, _vp, _vp]),

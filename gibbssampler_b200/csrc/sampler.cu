@@ -234,6 +234,46 @@ extern "C" int gs_loglik_pix(const double* d_Q, const double* d_U, const double*
     return GS_OK;
 }
 
+// compute_log_likelihood_all_sph (NonCenteredGibbs.py:357-377): full sky, isotropic noise, everything in harmonic space:
+//   -1/2 w sum_i [(dE_i - flE_l(i) sE_i)^2 + (dB_i - flB_l(i) sB_i)^2],  i over the real alm layout, fl = b_l sqrt(C_l),
+//   w = N^-1 Npix / 4 pi.  One block per (m, l-chunk): entry (l, m) sits at l (m = 0) or 2 (base_m + l) - (L+1) + {0,1}.
+__global__ void __launch_bounds__(SM_NT)
+loglik_alm_partial_kernel(const double* __restrict__ dE, const double* __restrict__ dB, const double* __restrict__ sE,
+                          const double* __restrict__ sB, const double* __restrict__ flE, const double* __restrict__ flB, int L,
+                          double* __restrict__ partials)
+{
+    double v[1] = {0.0};
+    const int64_t nm = L + 1, total = nm * (nm + 1) / 2;   // complex coefficients, m-major
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < total; c += (int64_t)gridDim.x * blockDim.x) {
+        // c -> (m, l): base_m = m (2L + 1 - m) / 2 <= c
+        int m = (int)(((2.0 * L + 1.0) - sqrt((2.0 * L + 1.0) * (2.0 * L + 1.0) - 8.0 * (double)c)) * 0.5);
+        while (m > 0 && (int64_t)m * (2 * L + 1 - m) / 2 > c) --m;
+        while ((int64_t)(m + 1) * (2 * L + 1 - (m + 1)) / 2 <= c) ++m;
+        const int l = (int)(c - (int64_t)m * (2 * L + 1 - m) / 2) + m;
+        const double fe = flE[l], fb = flB[l];
+        if (m == 0) {
+            const double a = dE[l] - fe * sE[l], b = dB[l] - fb * sB[l];
+            v[0] += a * a + b * b;
+        } else {
+            const int64_t off = 2 * c - nm;
+            const double a0 = dE[off] - fe * sE[off], a1 = dE[off + 1] - fe * sE[off + 1];
+            const double b0 = dB[off] - fb * sB[off], b1 = dB[off + 1] - fb * sB[off + 1];
+            v[0] += a0 * a0 + a1 * a1 + b0 * b0 + b1 * b1;
+        }
+    }
+    block_sum<1>(v, partials + blockIdx.x);
+}
+
+extern "C" int gs_loglik_alm(const double* d_E, const double* d_B, const double* s_E, const double* s_B, const double* fl_E,
+                             const double* fl_B, int lmax, double weight, double* scratch, double* out, void* stream)
+{
+    GS_REQUIRE(d_E && d_B && s_E && s_B && fl_E && fl_B && scratch && out && lmax >= 0, "bad arguments (scratch needs 592 doubles)");
+    loglik_alm_partial_kernel<<<SM_GRID, SM_NT, 0, STREAM(stream)>>>(d_E, d_B, s_E, s_B, fl_E, fl_B, lmax, scratch);
+    final_sum_kernel<<<1, SM_NT, 0, STREAM(stream)>>>(scratch, SM_GRID, -0.5 * weight, out);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
 extern "C" int gs_cr_direct(const double* dl, const double* bl, const double* d_alm, const double* xi, double npix_over_noise_4pi,
                             int lmax, int mode, double* out, void* stream)
 {

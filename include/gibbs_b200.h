@@ -203,6 +203,12 @@ int gs_truncnorm_logpdf(const double* x, const double* from, const double* prop_
  * for temperature (NonCenteredGibbs.py:353-355; ClsSampler.py:107-108).  scratch: 592 doubles. */
 int gs_loglik_pix(const double* d_Q, const double* d_U, const double* m_Q, const double* m_U,
                   const double* inv_noise, int64_t npix, double* scratch, double* out, void* stream);
+/* compute_log_likelihood_all_sph (NonCenteredGibbs.py:357-377; full sky, isotropic noise, data given in harmonic space):
+ * -1/2 weight sum_i [(d_E_i - fl_E[l(i)] s_E_i)^2 + (d_B_i - fl_B[l(i)] s_B_i)^2] -> out[0] (device), i over the real alm
+ * layout ((lmax+1)^2 doubles per array), fl_* = b_l sqrt(C_l) per multipole (gs_mwg_filters), weight = N^-1 Npix / 4 pi
+ * (NonCenteredGibbs.py:375-377).  scratch: 592 doubles. */
+int gs_loglik_alm(const double* d_E, const double* d_B, const double* s_E, const double* s_B, const double* fl_E,
+                  const double* fl_B, int lmax, double weight, double* scratch, double* out, void* stream);
 
 /* ---- Metropolis-within-Gibbs on the binned D_l, device resident ---------------------------- */
 /* Per-l synthesis filters fl_X[l] = b_l sqrt(C^X_l) of the candidate state = current binned D_l

@@ -200,6 +200,14 @@ def nc_loglik(binned, bins, s_nc, prob):
     return -0.5 * (np.sum((prob.d_Q - q) ** 2 * prob.inv_noise) + np.sum((prob.d_U - u) ** 2 * prob.inv_noise))
 
 
+def nc_loglik_all_sph(binned, bins, s_nc, d_E, d_B, bl_map, inv_noise0, npix):
+    """compute_log_likelihood_all_sph (NonCenteredGibbs.py:357-377): full sky, isotropic noise, harmonic-space data."""
+    dlE, dlB = unfold_bins(binned["EE"], bins["EE"]), unfold_bins(binned["BB"], bins["BB"])
+    vE, vB = generate_var_cl(dlE), generate_var_cl(dlB)
+    w = inv_noise0 * npix / (4 * np.pi)
+    return -0.5 * (np.sum((d_E - bl_map * np.sqrt(vE) * s_nc["EE"]) ** 2 * w) + np.sum((d_B - bl_map * np.sqrt(vB) * s_nc["BB"]) ** 2 * w))
+
+
 # ---------------------------------------------------------------- per-l 3x3 TT/TE/EE/BB machinery (SURVEY.md 8a A9, 8f 4)
 def expand_var_cl_3x3(dls):
     """variance_expension.pyx:36-61 with the :51 index bug fixed (cls_[l], not cls_[idx]): (L+1,3,3) D_l ->

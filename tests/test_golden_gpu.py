@@ -160,3 +160,28 @@ def test_alternative_cr_kernels_match_reference():
     np.random.seed(int(G["overrelax_seed"]))
     sol, _ = cr.sample(dls, s_old)
     assert close(sol["EE"], G["overrelax_E"], 1e-8)
+
+
+def test_all_sph_sampler_matches_reference():
+    """all_sph branch (full sky, isotropic noise, harmonic data: NonCenteredGibbs.py:357-377, 385-393, 414-419) against the
+    reference's own module (tests/golden/make_golden_allsph.py): likelihood values and the whole blocked sweep."""
+    from gibbssampler_b200.NonCenteredGibbs import PolarizationNonCenteredClsSampler
+    A = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_allsph_nside4.npz"))
+    bins = {"EE": A["bins_EE"], "BB": A["bins_BB"]}
+    blocks = {"EE": list(A["blocks_EE"]), "BB": list(A["blocks_BB"])}
+    pv = {"EE": A["prop_var_EE"], "BB": A["prop_var_BB"]}
+    pix_map = {"EE": A["dE"], "BB": A["dB"]}
+    nc = PolarizationNonCenteredClsSampler(pix_map, LMAX, NSIDE, bins, A["bl_map"], np.full(NPIX, 1600.0), A["noise_pol"], blocks, pv,
+                                           n_iter=2, all_sph=True, rng="numpy")
+    old = {"EE": A["binned_old_EE"], "BB": A["binned_old_BB"]}
+    s_nc = {"EE": A["s_nc_E"], "BB": A["s_nc_B"]}
+    assert abs(nc.compute_log_likelihood_all_sph(old, s_nc) - float(A["loglik_old"])) < 1e-12 * abs(float(A["loglik_old"]))
+    prop = {"EE": A["propose_EE"], "BB": A["propose_BB"]}
+    assert abs(nc.compute_log_likelihood_all_sph(prop, s_nc) - float(A["loglik_prop"])) < 1e-12 * abs(float(A["loglik_prop"]))
+    np.random.seed(int(A["mwg_seed"]))
+    new, accept = nc.sample(s_nc, old)
+    assert accept["EE"] == list(A["mwg_accept_EE"]) and accept["BB"] == list(A["mwg_accept_BB"])
+    assert close(new["EE"], A["mwg_EE"], 1e-12) and close(new["BB"], A["mwg_BB"], 1e-12)
+    with pytest.raises(ValueError):
+        PolarizationNonCenteredClsSampler(pix_map, LMAX, NSIDE, bins, A["bl_map"], np.full(NPIX, 1600.0), A["noise_pol"], blocks, pv,
+                                          all_sph=True, mask=np.ones(NPIX), rng="numpy")

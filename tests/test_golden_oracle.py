@@ -111,3 +111,15 @@ def test_3x3_restatements_self_consistent_and_reference_expansion_is_broken():
     if ref is not None:
         with pytest.raises(IndexError):  # variance_expension.pyx:51 indexes cls_[idx] with idx up to (L+1)(L+2)/2 - 1
             ref.generate_polarization_var_cl_cython(np.asfortranarray(cls))
+
+
+def test_all_sph_likelihood_matches_reference():
+    """compute_log_likelihood_all_sph (NonCenteredGibbs.py:357-377) from the reference's own module
+    (tests/golden/make_golden_allsph.py) against the oracle restatement."""
+    A = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_allsph_nside4.npz"))
+    bins = {"EE": A["bins_EE"], "BB": A["bins_BB"]}
+    s_nc = {"EE": A["s_nc_E"], "BB": A["s_nc_B"]}
+    for key, st in (("loglik_old", {"EE": A["binned_old_EE"], "BB": A["binned_old_BB"]}),
+                    ("loglik_prop", {"EE": A["propose_EE"], "BB": A["propose_BB"]})):
+        got = R.nc_loglik_all_sph(st, bins, s_nc, A["dE"], A["dB"], A["bl_map"], 1.0 / A["noise_pol"][0], 12 * NSIDE ** 2)
+        assert abs(got - float(A[key])) < 1e-12 * abs(float(A[key]))
