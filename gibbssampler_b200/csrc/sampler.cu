@@ -236,7 +236,7 @@ extern "C" int gs_loglik_pix(const double* d_Q, const double* d_U, const double*
 
 // compute_log_likelihood_all_sph (NonCenteredGibbs.py:357-377): full sky, isotropic noise, everything in harmonic space:
 //   -1/2 w sum_i [(dE_i - flE_l(i) sE_i)^2 + (dB_i - flB_l(i) sB_i)^2],  i over the real alm layout, fl = b_l sqrt(C_l),
-//   w = N^-1 Npix / 4 pi.  One block per (m, l-chunk): entry (l, m) sits at l (m = 0) or 2 (base_m + l) - (L+1) + {0,1}.
+//   w = N^-1 Npix / 4 pi.  Thread per complex coefficient c = idx(l, m): real-layout entry l (m = 0) or 2 c - (L+1) + {0,1}.
 __global__ void __launch_bounds__(SM_NT)
 loglik_alm_partial_kernel(const double* __restrict__ dE, const double* __restrict__ dB, const double* __restrict__ sE,
                           const double* __restrict__ sB, const double* __restrict__ flE, const double* __restrict__ flB, int L,
@@ -245,11 +245,13 @@ loglik_alm_partial_kernel(const double* __restrict__ dE, const double* __restric
     double v[1] = {0.0};
     const int64_t nm = L + 1, total = nm * (nm + 1) / 2;   // complex coefficients, m-major
     for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < total; c += (int64_t)gridDim.x * blockDim.x) {
-        // c -> (m, l): base_m = m (2L + 1 - m) / 2 <= c
-        int m = (int)(((2.0 * L + 1.0) - sqrt((2.0 * L + 1.0) * (2.0 * L + 1.0) - 8.0 * (double)c)) * 0.5);
-        while (m > 0 && (int64_t)m * (2 * L + 1 - m) / 2 > c) --m;
-        while ((int64_t)(m + 1) * (2 * L + 1 - (m + 1)) / 2 <= c) ++m;
-        const int l = (int)(c - (int64_t)m * (2 * L + 1 - m) / 2) + m;
+        // c = idx(l, m) = m (2L + 1 - m) / 2 + l, l = m..L: column m starts at s_m = m (2L + 3 - m) / 2 <= c
+        const double t = 2.0 * L + 3.0;
+        int m = (int)((t - sqrt(fmax(t * t - 8.0 * (double)c, 0.0))) * 0.5);
+        m = max(0, min(m, L));
+        while (m > 0 && (int64_t)m * (2 * L + 3 - m) / 2 > c) --m;
+        while (m < L && (int64_t)(m + 1) * (2 * L + 3 - (m + 1)) / 2 <= c) ++m;
+        const int l = (int)(c - (int64_t)m * (2 * L + 1 - m) / 2);
         const double fe = flE[l], fb = flB[l];
         if (m == 0) {
             const double a = dE[l] - fe * sE[l], b = dB[l] - fb * sB[l];

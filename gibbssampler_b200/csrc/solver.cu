@@ -138,10 +138,10 @@ pcg_init_kernel(gs_pcg_ws W, const double* bE, const double* bB, int have_q, int
         int c; int64_t j;
         pick(i, n, c, j);
         double r = (c ? bB : bE)[j];
-        if (have_q) r -= W.q[c][j];
-        const double z = W.pre[c][j] * r;
-        W.r[c][j] = r;
-        W.p[c][j] = z;
+        if (have_q) r -= (c ? W.q[1] : W.q[0])[j];
+        const double z = (c ? W.pre[1] : W.pre[0])[j] * r;
+        (c ? W.r[1] : W.r[0])[j] = r;
+        (c ? W.p[1] : W.p[0])[j] = z;
         v[0] += r * r;
         v[1] += r * z;
     }
@@ -152,18 +152,36 @@ pcg_init_kernel(gs_pcg_ws W, const double* bE, const double* bB, int have_q, int
     }
 }
 
+// The vector kernels walk the E and B arrays with a grid stride, SV_U elements per thread and step with all loads issued
+// before the first store (the arrays may alias as far as the compiler knows): enough bytes in flight to approach HBM speed.
+#define SV_U 4
+
 // q += C^-1 p ; pq = <p, q> ; alpha = delta / pq
 __global__ void __launch_bounds__(SV_NT) pcg_apq_kernel(gs_pcg_ws W, int64_t n, int nc)
 {
     if (W.state->done) return;
     double v[1] = {0.0};
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nc * n; i += (int64_t)gridDim.x * blockDim.x) {
-        int c; int64_t j;
-        pick(i, n, c, j);
-        const double p = W.p[c][j];
-        const double q = fma(W.invc[c][j], p, W.q[c][j]);
-        W.q[c][j] = q;
-        v[0] += p * q;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, total = nc * n;
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total; i0 += SV_U * stride) {
+        double p[SV_U], q[SV_U], ic[SV_U];
+#pragma unroll
+        for (int k = 0; k < SV_U; ++k) {
+            const int64_t i = i0 + k * stride;
+            int c; int64_t j;
+            pick(i, n, c, j);
+            const bool ok = i < total;
+            p[k] = ok ? (c ? W.p[1] : W.p[0])[j] : 0.0; q[k] = ok ? (c ? W.q[1] : W.q[0])[j] : 0.0; ic[k] = ok ? (c ? W.invc[1] : W.invc[0])[j] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < SV_U; ++k) {
+            const int64_t i = i0 + k * stride;
+            if (i >= total) break;
+            int c; int64_t j;
+            pick(i, n, c, j);
+            const double qq = fma(ic[k], p[k], q[k]);
+            (c ? W.q[1] : W.q[0])[j] = qq;
+            v[0] += p[k] * qq;
+        }
     }
     double tot[1];
     if (grid_reduce<1>(v, W.partials, &W.state->counter, tot) && threadIdx.x == 0) {
@@ -178,15 +196,30 @@ __global__ void __launch_bounds__(SV_NT) pcg_update_kernel(gs_pcg_ws W, double* 
     if (W.state->done) return;
     const double alpha = W.state->alpha;
     double v[2] = {0.0, 0.0};
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nc * n; i += (int64_t)gridDim.x * blockDim.x) {
-        int c; int64_t j;
-        pick(i, n, c, j);
-        double* x = c ? xB : xE;
-        x[j] = fma(alpha, W.p[c][j], x[j]);
-        const double r = fma(-alpha, W.q[c][j], W.r[c][j]);
-        W.r[c][j] = r;
-        v[0] += r * r;
-        v[1] += r * r * W.pre[c][j];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, total = nc * n;
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total; i0 += SV_U * stride) {
+        double x[SV_U], p[SV_U], q[SV_U], r[SV_U], pre[SV_U];
+#pragma unroll
+        for (int k = 0; k < SV_U; ++k) {
+            const int64_t i = i0 + k * stride;
+            int c; int64_t j;
+            pick(i, n, c, j);
+            const bool ok = i < total;
+            x[k] = ok ? (c ? xB : xE)[j] : 0.0; p[k] = ok ? (c ? W.p[1] : W.p[0])[j] : 0.0; q[k] = ok ? (c ? W.q[1] : W.q[0])[j] : 0.0;
+            r[k] = ok ? (c ? W.r[1] : W.r[0])[j] : 0.0; pre[k] = ok ? (c ? W.pre[1] : W.pre[0])[j] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < SV_U; ++k) {
+            const int64_t i = i0 + k * stride;
+            if (i >= total) break;
+            int c; int64_t j;
+            pick(i, n, c, j);
+            (c ? xB : xE)[j] = fma(alpha, p[k], x[k]);
+            const double rr = fma(-alpha, q[k], r[k]);
+            (c ? W.r[1] : W.r[0])[j] = rr;
+            v[0] += rr * rr;
+            v[1] += rr * rr * pre[k];
+        }
     }
     double tot[2];
     if (grid_reduce<2>(v, W.partials, &W.state->counter, tot) && threadIdx.x == 0) {
@@ -200,10 +233,25 @@ __global__ void __launch_bounds__(SV_NT) pcg_dir_kernel(gs_pcg_ws W, int64_t n, 
 {
     if (W.state->done) return;
     const double beta = W.state->beta;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nc * n; i += (int64_t)gridDim.x * blockDim.x) {
-        int c; int64_t j;
-        pick(i, n, c, j);
-        W.p[c][j] = fma(beta, W.p[c][j], W.pre[c][j] * W.r[c][j]);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, total = nc * n;
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total; i0 += SV_U * stride) {
+        double p[SV_U], r[SV_U], pre[SV_U];
+#pragma unroll
+        for (int k = 0; k < SV_U; ++k) {
+            const int64_t i = i0 + k * stride;
+            int c; int64_t j;
+            pick(i, n, c, j);
+            const bool ok = i < total;
+            p[k] = ok ? (c ? W.p[1] : W.p[0])[j] : 0.0; r[k] = ok ? (c ? W.r[1] : W.r[0])[j] : 0.0; pre[k] = ok ? (c ? W.pre[1] : W.pre[0])[j] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < SV_U; ++k) {
+            const int64_t i = i0 + k * stride;
+            if (i >= total) break;
+            int c; int64_t j;
+            pick(i, n, c, j);
+            (c ? W.p[1] : W.p[0])[j] = fma(beta, p[k], pre[k] * r[k]);
+        }
     }
 }
 
