@@ -43,6 +43,10 @@
 #ifndef LEG_FOLD2
 #define LEG_FOLD2 1  // spin-2 analysis: lane-permuted inputs so that the warp reduce-scatter needs one select stage instead of three
 #endif
+#ifndef LEG_FOLD3
+#define LEG_FOLD3 1  // spin-2 analysis fast loop: the last three stages of the reduce-scatter are deferred, FOLD3_NB pairs of l
+#endif               // at a time, to a sum through shared memory (needs LEG_FOLD2)
+#define FOLD3_NB 8
 #define FULL 0xffffffffu
 constexpr int kUnrollA = LEG_UA;
 
@@ -730,6 +734,14 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
     constexpr int NVAL = 2 * NV;       // values reduced per pair of l
     __shared__ double2 sR[LEG_TL];
     __shared__ double sPart[LEG_NW][LEG_TL * NV];
+#if LEG_FOLD2 && LEG_FOLD3
+    // After the two select-free exchange stages a lane holds, for each of the two l of a pair, the sum over 4 lanes of the
+    // value c = (lane bit 4, lane bit 3); what remains is a sum over the 8 lanes that differ in bits 2..0.  Instead of three
+    // more dependent shuffle stages per pair of l, the fast loop parks those two numbers in shared memory and sums FOLD3_NB
+    // pairs of l at a time (8 independent loads per output, no selects).  Slot of lane L for local pair q:
+    // L ^ c(L) ^ ((q & 1) << 2): stores are conflict free and the 32 outputs read in one step hit 16 distinct 8-byte banks.
+    __shared__ double2 sFold[SPIN ? LEG_NW : 1][SPIN ? FOLD3_NB * 32 : 1];
+#endif
     const int l0 = m > SPIN ? m : SPIN;
     const int64_t base = (int64_t)m * (2 * L + 1 - m) / 2;
     // first entry (l = lt) of this block's partial sums is pbase + lt
@@ -847,6 +859,55 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
             if (writer) myPart[ip * NVAL + vidx] = __hiloint2double(__double2hiint(s) ^ flipmask, __double2loint(s));
             ++ip;
         }
+#if LEG_FOLD2 && LEG_FOLD3
+        if (SPIN == 2) {
+            double2* fbuf = sFold[SPIN ? w : 0];
+            const int cperm = ((lane >> 4) & 1) << 1 | ((lane >> 3) & 1);
+            int ipb = ip;   // first pair of l of the batch parked in fbuf
+            // sums the parked pairs [ipb, ipb + n) over the 8 lanes of each value and writes them to myPart
+            auto flush = [&](int n) {
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < FOLD3_NB / 4; ++t) {
+                    const int o = lane + 32 * t, q = o >> 3, h = (o >> 2) & 1, c = o & 3;
+                    if (q < n) {
+                        const double* e = reinterpret_cast<const double*>(fbuf + q * 32) + h;
+                        const int s0 = (((c >> 1) << 4) | ((c & 1) << 3)) ^ c ^ ((q & 1) << 2);   // slot of source lane (c, s = 0)
+                        double a[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) a[k] = e[2 * (s0 ^ k)];   // s ^ (low bits of the swizzle) runs over the same 8 slots
+                        double sum = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+                        if (h && (c & 1)) sum = -sum;
+                        myPart[(ipb + q) * NVAL + h * 4 + c] = sum;
+                    }
+                }
+                __syncwarp();
+            };
+#pragma unroll kUnrollA
+            for (; ip < npr; ++ip) {  // (C)
+                double v[NVAL];
+                const double2 r0 = sR[2 * ip], r1 = sR[2 * ip + 1];
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+                    if (j == 0) ANAL_ACC(true, true, v, G[j], st[j].pc, st[j].mc);
+                    else ANAL_ACC(true, false, v, G[j], st[j].pc, st[j].mc);
+                    rec_step<SPIN>(st[j], r0.x, r0.y);
+                    if (j == 0) ANAL_ACC(false, true, v + NV, G[j], st[j].pc, st[j].mc);
+                    else ANAL_ACC(false, false, v + NV, G[j], st[j].pc, st[j].mc);
+                    rec_step<SPIN>(st[j], r1.x, r1.y);
+                }
+                v[0] += __shfl_xor_sync(FULL, v[2], 16); v[1] += __shfl_xor_sync(FULL, v[3], 16);
+                v[4] += __shfl_xor_sync(FULL, v[6], 16); v[5] += __shfl_xor_sync(FULL, v[7], 16);
+                v[0] += __shfl_xor_sync(FULL, v[1], 8);
+                v[4] += __shfl_xor_sync(FULL, v[5], 8);
+                const int q = ip - ipb;
+                fbuf[q * 32 + (lane ^ cperm ^ ((q & 1) << 2))] = make_double2(v[0], v[4]);
+                if (q == FOLD3_NB - 1) { flush(FOLD3_NB); ipb = ip + 1; }
+            }
+            if (ip > ipb) flush(ip - ipb);
+        } else
+#endif
+        {
 #pragma unroll kUnrollA
         for (; ip < npr; ++ip) {  // (C)
             double v[NVAL];
@@ -862,6 +923,7 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
             }
             const double s = ANAL_FOLD(v, lane);
             if (writer) myPart[ip * NVAL + vidx] = __hiloint2double(__double2hiint(s) ^ flipmask, __double2loint(s));
+        }
         }
         __syncthreads();
         // sum over the warps of the block, one deterministic partial per chunk
