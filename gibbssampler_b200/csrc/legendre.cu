@@ -26,6 +26,10 @@
 #endif
 #define LEG_NW (LEG_NT / 32)
 #define LEG_TL LEG_NT   // l-tile (even): one staged l per thread
+#ifndef LEG_SU
+#define LEG_SU 1        // synthesis kernel: multipoles staged per thread and tile (tile = LEG_SU * LEG_NT, one barrier per tile)
+#endif
+#define LEG_TLS (LEG_SU * LEG_NT)
 #ifndef LEG_R
 #define LEG_R 2      // ring pairs per thread (synthesis)
 #endif
@@ -280,7 +284,6 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
                  const int* __restrict__ slot0)
 {
     if (skip && *skip) return;
-    static_assert(LEG_TL == LEG_NT, "one staged l per thread");
     const int L = P.lmax, mk = blockIdx.y, m = SH ? P.sh.mlist[mk] : mk, tid = threadIdx.x;
     // Ring pairs run from the pole to the equator and lambda_lm is negligible on the pairs before slot0[m] (m > m_lim), so
     // for this m the grid packs the pairs from slot0[m] on: the k-th slot works on pair slot0[m] + k, or on
@@ -288,7 +291,7 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
     // the blocks beyond the last slot have nothing to do.
     const int s0 = slot0[m], nact = (plist ? *pcount : P.npair) - s0;
     if ((int)blockIdx.x * (LEG_NT * R) >= nact) return;
-    __shared__ double2 sEb[2][LEG_TL], sBb[2][SPIN ? LEG_TL : 1], sRb[2][LEG_TL];
+    __shared__ double2 sEb[2][LEG_TLS], sBb[2][SPIN ? LEG_TLS : 1], sRb[2][LEG_TLS];
     const int l0 = m > SPIN ? m : SPIN;
     const int64_t base = (int64_t)m * (2 * L + 1 - m) / 2;
     const int64_t roff = real_off<SH>(P, m, mk, base);
@@ -314,21 +317,26 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
     }
     const bool warp_act = __any_sync(FULL, any_act);
 
-    {
+#pragma unroll
+    for (int u = 0; u < LEG_SU; ++u) {
         double2 e, b, r;
-        fetch_alm<SPIN>(P, m, l0 + tid, base, roff, almE, almB, layout, fl, flB, e, b, r);
-        sEb[0][tid] = e; if (SPIN) sBb[0][tid] = b; sRb[0][tid] = r;
+        fetch_alm<SPIN>(P, m, l0 + u * LEG_NT + tid, base, roff, almE, almB, layout, fl, flB, e, b, r);
+        sEb[0][u * LEG_NT + tid] = e; if (SPIN) sBb[0][u * LEG_NT + tid] = b; sRb[0][u * LEG_NT + tid] = r;
     }
     __syncthreads();
     int cur = 0;
-    for (int lt = l0; lt <= L; lt += LEG_TL, cur ^= 1) {
-        const bool has_next = lt + LEG_TL <= L;
-        double2 ne, nb, nr;
-        if (has_next) fetch_alm<SPIN>(P, m, lt + LEG_TL + tid, base, roff, almE, almB, layout, fl, flB, ne, nb, nr);
+    for (int lt = l0; lt <= L; lt += LEG_TLS, cur ^= 1) {
+        const bool has_next = lt + LEG_TLS <= L;
+        double2 ne[LEG_SU], nb[LEG_SU], nr[LEG_SU];
+        if (has_next) {
+#pragma unroll
+            for (int u = 0; u < LEG_SU; ++u)
+                fetch_alm<SPIN>(P, m, lt + LEG_TLS + u * LEG_NT + tid, base, roff, almE, almB, layout, fl, flB, ne[u], nb[u], nr[u]);
+        }
         const double2* sE = sEb[cur];
         const double2* sB = sBb[cur];
         const double2* sR = sRb[cur];
-        const int ni = warp_act ? min(LEG_TL, L - lt + 1) : 0;
+        const int ni = warp_act ? min(LEG_TLS, L - lt + 1) : 0;
         const int npr = (ni + 1) >> 1;
         int ip = 0;
         // (A) every lane still below range: recurrence only
@@ -381,7 +389,12 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
                 rec_step<SPIN>(st[j], r1.x, r1.y);
             }
         }
-        if (has_next) { sEb[cur ^ 1][tid] = ne; if (SPIN) sBb[cur ^ 1][tid] = nb; sRb[cur ^ 1][tid] = nr; }
+        if (has_next) {
+#pragma unroll
+            for (int u = 0; u < LEG_SU; ++u) {
+                sEb[cur ^ 1][u * LEG_NT + tid] = ne[u]; if (SPIN) sBb[cur ^ 1][u * LEG_NT + tid] = nb[u]; sRb[cur ^ 1][u * LEG_NT + tid] = nr[u];
+            }
+        }
         __syncthreads();
     }
 
