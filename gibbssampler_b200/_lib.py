@@ -97,6 +97,7 @@ SIGNATURES = {
     "gs_measure_fp64_peak": (_i, [C.POINTER(_d), _vp]),
     "gs_set_ring_fused": (_i, [_i]),
     "gs_set_ring_skip": (_i, [_i]),
+    "gs_set_fuse_apq": (_i, [_i]),
     "gs_active_ring_pairs": (_i, [_vp, C.POINTER(_i), C.POINTER(_i)]),
 }
 

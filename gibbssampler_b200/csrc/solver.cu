@@ -29,6 +29,8 @@ struct PcgState {
 struct gs_pcg_ws {
     double *r[2], *p[2], *q[2], *invc[2], *pre[2];
     double* partials;  // SV_GRID * 2
+    double* fuse_partials;  // per-block partials of the fused analysis-finish + <p, q> kernel (unsharded plans)
+    double* fuse_out;       // its result
     double* red;       // sharded plans: local sums in, all-reduced sums out (NULL on one GPU)
     PcgState* state;
     PcgState* host_state;  // pinned
@@ -119,6 +121,12 @@ __device__ __forceinline__ void fin_update(PcgState* s, double rr, double rz)
     s->iter += 1;
     // qcinv cd_monitors.monitor_basic: stop when <r,r> <= eps^2 <r0,r0> or iter >= iter_max
     if (rr <= s->eps2 * s->d0 || s->iter >= s->itermax) s->done = 1;
+}
+// after the fused analysis-finish kernel: alpha = delta / <p, q>
+__global__ void pcg_apq_scalar_kernel(gs_pcg_ws W)
+{
+    if (W.state->done) return;
+    fin_apq(W.state, W.fuse_out[0]);
 }
 __global__ void pcg_scalar_kernel(gs_pcg_ws W, int stage)
 {
@@ -293,6 +301,8 @@ static gs_pcg_ws* get_ws(gs_plan* p)
     bool ok = true;
     for (int c = 0; c < 2 && ok; ++c) ok = alloc(&w->r[c], n) && alloc(&w->p[c], n) && alloc(&w->q[c], n) && alloc(&w->invc[c], n) && alloc(&w->pre[c], n);
     ok = ok && alloc(&w->partials, SV_GRID * 2 + 4 * (size_t)(p->d.lmax + 1));
+    ok = ok && alloc(&w->fuse_partials, (size_t)((p->d.lmax + 256) / 256) * (p->d.lmax + 1));
+    ok = ok && alloc(&w->fuse_out, 4);
     void* d = nullptr;
     ok = ok && cudaMalloc(&d, sizeof(PcgState)) == cudaSuccess;
     if (ok) { p->owned.push_back(d); w->state = (PcgState*)d; }
@@ -302,6 +312,9 @@ static gs_pcg_ws* get_ws(gs_plan* p)
     return w;
 }
 
+int g_gs_fuse_apq = 0;   // 1: fused analysis-finish + (q += C^-1 p, <p, q>) kernel in the unsharded PCG (measured 0.4 % SLOWER
+                         // than the separate pass at NSIDE 512: 5125 block partials + a scalar kernel; kept as an option)
+extern "C" int gs_set_fuse_apq(int on) { const int old = g_gs_fuse_apq; g_gs_fuse_apq = on ? 1 : 0; return old; }
 int g_gs_ring_fused = 1;
 extern "C" int gs_set_ring_fused(int fused) { const int old = g_gs_ring_fused; g_gs_ring_fused = fused ? 1 : 0; return old; }
 
@@ -326,7 +339,7 @@ struct ActiveRings {   // scope guard: the plan's launchers use the active lists
 
 // q = B A^T N^-1 A B v   (C^-1 v is added by pcg_apq_kernel / the caller)
 static int apply_noise_op(gs_plan* p, const double* vE, const double* vB, const double* bl, const double* inv_noise,
-                          double* qE, double* qB, cudaStream_t st, const int* skip, int spin = 2)
+                          double* qE, double* qB, cudaStream_t st, const int* skip, int spin = 2, const FinishFuse* fuse = nullptr)
 {
     int rc;
     if ((rc = gs_leg_synth(p, spin, vE, vB, GS_ALM_REAL, bl, st, skip))) return rc;
@@ -336,7 +349,7 @@ static int apply_noise_op(gs_plan* p, const double* vE, const double* vB, const 
         if ((rc = gs_ring_synth(p, spin, p->mapQ_tmp, p->mapU_tmp, st, skip))) return rc;
         if ((rc = gs_ring_anal(p, spin, p->mapQ_tmp, p->mapU_tmp, inv_noise, st, skip))) return rc;
     }
-    return gs_leg_anal(p, spin, qE, qB, GS_ALM_REAL, bl, 1.0, 0, st, skip);
+    return gs_leg_anal(p, spin, qE, qB, GS_ALM_REAL, bl, 1.0, 0, st, skip, fuse);
 }
 
 // spin 2: (E, B) system; spin 0: temperature (dl_BB, rhs_B, x_B unused)
@@ -391,12 +404,18 @@ static int cr_pcg_impl(gs_plan* p, int spin, const double* dl_EE, const double* 
     }
 
     const int* done = &w->state->done;
+    // optional (gs_set_fuse_apq): q += C^-1 p and <p, q> ride on the last kernel of the analysis
+    FinishFuse ff;
+    ff.pE = w->p[0]; ff.pB = w->p[1]; ff.icE = tmp_l; ff.icB = tmp_l + 2 * (L + 1);
+    ff.partials = w->fuse_partials; ff.counter = &w->state->counter; ff.out = w->fuse_out;
+    const bool fused_apq = !dist && g_gs_fuse_apq;
     int launched = 0;
     bool finished = false;
     while (!finished) {
         for (int k = 0; k < check_every && launched < itermax; ++k, ++launched) {
-            if ((rc = apply_noise_op(p, w->p[0], w->p[1], bl, inv_noise, w->q[0], w->q[1], st, done, spin))) return rc;
-            pcg_apq_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, n, nc);
+            if ((rc = apply_noise_op(p, w->p[0], w->p[1], bl, inv_noise, w->q[0], w->q[1], st, done, spin, fused_apq ? &ff : nullptr))) return rc;
+            if (fused_apq) pcg_apq_scalar_kernel<<<1, 1, 0, st>>>(*w);
+            else pcg_apq_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, n, nc);
             if (dist) {
                 if ((rc = gs_shard_allreduce(p, w->red, 1, st))) return rc;
                 pcg_scalar_kernel<<<1, 1, 0, st>>>(*w, 1);

@@ -374,6 +374,10 @@ int gs_set_ring_fused(int fused);
  * rings and sum the flags (one small all-reduce per call).  gs_mwg_sweep_blocks skips the ring FFTs of those rings too.
  * Returns the previous setting. */
 int gs_set_ring_skip(int on);
+/* on != 0: in gs_cr_pcg_* on unsharded plans the step  q += C^-1 p ; <p, q>  rides on the last kernel of the Legendre
+ * analysis instead of a separate pass; 0 (default; the fused form measured 0.4 % slower at NSIDE 512): separate kernel.
+ * Same numbers up to the summation order of the dot product.  Returns the previous setting. */
+int gs_set_fuse_apq(int on);
 /* Number of ring pairs (north/south) with a non-zero weight found by the last such call on this plan, and the total. */
 int gs_active_ring_pairs(gs_plan* plan, int* active_out, int* total_out);
 /* FP64 FMA throughput of the current device in TFLOP/s (DFMA microkernel; the roofline

@@ -110,8 +110,10 @@ def test_skipping_operator_vs_oracle():
     assert np.abs(yb - rb).max() <= 1e-10 * np.abs(rb).max()
 
 
-@pytest.mark.parametrize("kind", ["band", "south"])
-def test_pcg_solution_with_and_without_skipping(kind):
+@pytest.mark.parametrize("kind,setter", [("band", "gs_set_ring_skip"), ("south", "gs_set_ring_skip"), ("band", "gs_set_fuse_apq"),
+                                         ("holes", "gs_set_fuse_apq")])
+def test_pcg_solution_with_and_without_skipping(kind, setter):
+    """Same solve with the optimisation on and off: idle-ring skipping, and the fused analysis-finish + <p, q> kernel."""
     from gibbssampler_b200 import _lib, utils
     from gibbssampler_b200.CenteredGibbs import PolarizedCenteredConstrainedRealization
     from oracle import sht as O
@@ -129,13 +131,13 @@ def test_pcg_solution_with_and_without_skipping(kind):
     xi = (rng.standard_normal(npix), rng.standard_normal(npix), rng.standard_normal(nre), rng.standard_normal(nre))
     out = []
     for skip in (1, 0):
-        old = L.gs_set_ring_skip(skip)
+        old = getattr(L, setter)(skip)
         try:
             cr = PolarizedCenteredConstrainedRealization({"Q": dQ, "U": dU}, noise * 1e4, noise, bl_map, lmax, npix, fwhm, mask=mask)
             sol, _ = cr.sample_mask(dls, xi)
             out.append((np.concatenate([np.asarray(sol["EE"]), np.asarray(sol["BB"])]), cr.last_pcg_iterations))
         finally:
-            L.gs_set_ring_skip(old)
+            getattr(L, setter)(old)
     (xa, ia), (xb_, ib) = out
     assert abs(ia - ib) <= 1
     assert np.abs(xa - xb_).max() <= 1e-6 * np.abs(xb_).max()
