@@ -569,6 +569,19 @@ def main():
                     "traffic": ncu_traffic(ring_kernel) if at_bench_size else None,
                     "peak_source": hbm_src, "algorithmic_bytes_per_launch": ring_bytes}
 
+    # the HBM-bound vector kernels of one PCG iteration (algorithmic bytes: 4 + 7 + 4 arrays of 8 N_re bytes per field)
+    ms3 = (C.c_float * 3)()
+    _lib.check(L.gs_profile_pcg_vectors(plan._h, 2, 20, ms3, _dev.stream()))
+    vec_bytes = [4 * 2 * 8.0 * nre, 7 * 2 * 8.0 * nre, 4 * 2 * 8.0 * nre]
+    roofline_pcg = {"kernel": "pcg_apq + pcg_update + pcg_dir", "bound": "hbm",
+                    "achieved": sum(vec_bytes) / (sum(ms3) * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": sum(vec_bytes) / (sum(ms3) * 1e-3) * 1e-9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                    "algorithmic_bytes_per_iteration": sum(vec_bytes),
+                    "ms": {"pcg_apq": ms3[0], "pcg_update": ms3[1], "pcg_dir": ms3[2]},
+                    "gb_per_s": {"pcg_apq": vec_bytes[0] / ms3[0] * 1e-6, "pcg_update": vec_bytes[1] / ms3[1] * 1e-6,
+                                 "pcg_dir": vec_bytes[2] / ms3[2] * 1e-6},
+                    "note": "each launch timed alone after a write of the 134 MB analysis workspace (L2 flushed), as inside a PCG iteration"}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t_pair, cores, reps = cpu_pair_seconds(nside, lmax, 3, min_seconds=10.0)   # ~10 s of host CPU work
@@ -590,7 +603,7 @@ def main():
             "sht_pairs_per_s": world * 1e3 / pair_ms, "sht_pair_ms": pair_ms, "stage_ms": stage_ms,
             "pcg_matvec": {"ms": sum(matvec_ms.values()), "stage_ms": matvec_ms, "active_ring_pairs": act.value, "ring_pairs": tot.value,
                            "note": "mat-vec of the PCG: ring pairs wholly inside the mask (N^-1 = 0) are skipped, exact"},
-            "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu_baseline, "clocks": clocks.summary(),
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_pcg": roofline_pcg, "cpu_baseline": cpu_baseline, "clocks": clocks.summary(),
             "pcg_iterations_per_step": its_timed,
         }
         if pncp:

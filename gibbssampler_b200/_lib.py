@@ -95,6 +95,7 @@ SIGNATURES = {
     "gs_launch_count": (C.c_longlong, []),
     "gs_profile_matvec": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(C.c_float), _vp]),
     "gs_measure_fp64_peak": (_i, [C.POINTER(_d), _vp]),
+    "gs_profile_pcg_vectors": (_i, [_vp, _i, _i, C.POINTER(C.c_float), _vp]),
     "gs_set_ring_fused": (_i, [_i]),
     "gs_set_ring_skip": (_i, [_i]),
     "gs_set_fuse_apq": (_i, [_i]),

@@ -623,6 +623,55 @@ extern "C" int gs_profile_matvec(gs_plan* p, const double* x_E, const double* x_
     return rc;
 }
 
+// Times the three vector kernels of one PCG iteration (q += C^-1 p with <p,q>; x, r update with <r,r>, <r,Mr>; p = M r + beta p)
+// on the plan's own workspace, zero-filled, with CUDA events on `stream`: ms_out[0..2] = average of nrep launches each.  The
+// reductions run as in the solver but their results go to a scratch slot, so no solver state changes.
+extern "C" int gs_profile_pcg_vectors(gs_plan* p, int spin, int nrep, float* ms_out, void* stream)
+{
+    if (!p) { gs_set_error("null plan"); return GS_E_BADARG; }
+    GS_REQUIRE(ms_out && nrep >= 1 && (spin == 0 || spin == 2), "bad arguments");
+    GS_CHECK_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    gs_pcg_ws* w = get_ws(p);
+    if (!w) return GS_E_NOMEM;
+    const int nc = spin ? 2 : 1;
+    const int64_t n = p->nreal_loc;
+    for (int c = 0; c < 2; ++c) {
+        double* arrs[5] = {w->r[c], w->p[c], w->q[c], w->invc[c], w->pre[c]};
+        for (double* a : arrs) GS_CHECK_CUDA(cudaMemsetAsync(a, 0, (size_t)n * sizeof(double), st));
+    }
+    GS_CHECK_CUDA(cudaMemsetAsync(p->almE_tmp, 0, (size_t)n * sizeof(double), st));
+    GS_CHECK_CUDA(cudaMemsetAsync(p->almB_tmp, 0, (size_t)n * sizeof(double), st));
+    GS_CHECK_CUDA(cudaMemsetAsync(w->state, 0, sizeof(PcgState), st));
+    gs_pcg_ws v = *w;
+    v.red = w->fuse_out;   // reductions land here: the solver state (done flag, alpha, beta = 0) stays untouched
+    cudaEvent_t e0, e1;
+    GS_CHECK_CUDA(cudaEventCreate(&e0));
+    GS_CHECK_CUDA(cudaEventCreate(&e1));
+    // between launches the analysis partials (> L2 at the bench size) are overwritten, as the Legendre / ring kernels do
+    // between the vector kernels of a real iteration: the arrays come from HBM, not from the 126 MB L2
+    const size_t flush_bytes = (size_t)p->anal_chunks * (size_t)(p->world > 1 ? p->d.sh.nalm_loc : p->d.nalm) * 4 * sizeof(double);
+    for (int k = 0; k < 3; ++k) {
+        double acc = 0.0;
+        for (int rep = -2; rep < nrep; ++rep) {   // two warm-up launches
+            GS_CHECK_CUDA(cudaMemsetAsync(p->partial, 0, flush_bytes, st));
+            cudaEventRecord(e0, st);
+            if (k == 0) pcg_apq_kernel<<<SV_GRID, SV_NT, 0, st>>>(v, n, nc);
+            else if (k == 1) pcg_update_kernel<<<SV_GRID, SV_NT, 0, st>>>(v, p->almE_tmp, p->almB_tmp, n, nc);
+            else pcg_dir_kernel<<<SV_GRID, SV_NT, 0, st>>>(v, n, nc);
+            cudaEventRecord(e1, st);
+            GS_CHECK_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (rep >= 0) acc += ms;
+        }
+        ms_out[k] = (float)(acc / nrep);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
 // FP64 FMA throughput of the device (MEASURED_PEAKS.json holds no FP64 figure).  16 independent sums per thread in the
 // operand pattern of the Legendre kernels, sum += x_k * y_j with register operands that change during the loop (three
 // distinct register pairs per DFMA; scripts/ubench/dfma_operands.cu compares patterns: this one is the highest the pipe

@@ -363,6 +363,12 @@ long long gs_launch_count(void);
 int gs_profile_matvec(gs_plan* plan, const double* x_E, const double* x_B, const double* bl,
                       const double* inv_noise, double* y_E, double* y_B, int nrep, float* ms_out,
                       void* stream);
+/* Average duration (ms, CUDA events on `stream`) of the three vector kernels of one PCG iteration of gs_cr_pcg_pol
+ * (spin = 2) / gs_cr_pcg_tt (spin = 0) on the plan's own zero-filled workspace: ms_out[0]  q += C^-1 p with <p, q>
+ * (4 arrays of 8 n bytes per field), [1]  x += alpha p, r -= alpha q with <r, r>, <r, M r>  (7 arrays), [2]  p = M r +
+ * beta p  (4 arrays); n = (lmax+1)^2, 2 fields for spin 2.  Every launch is timed alone after the plan's analysis workspace
+ * (larger than L2 at NSIDE >= 512) has been overwritten.  No solver state is changed.  Synchronous. */
+int gs_profile_pcg_vectors(gs_plan* plan, int spin, int nrep, float* ms_out, void* stream);
 /* Ring stage of the PCG mat-vec (opfilt_pp.fwd_op's alm2map_spin -> N^-1 -> map2alm_spin, CenteredGibbs.py:629,653):
  * fused != 0 (default): one kernel per mat-vec keeps each ring's pixels in shared memory; 0: ring synthesis to the
  * plan's scratch maps, then weighted ring analysis.  Same result to rounding.  Returns the previous setting. */
