@@ -58,6 +58,30 @@ def unfold_bins(binned, bins):
     return np.repeat(binned, bins[1:] - bins[:-1])
 
 
+_ELL = {}
+
+
+def ell_index(lmax):
+    """multipole of every entry of the real layout, cached (vectorised twin of the loops above)."""
+    if lmax not in _ELL:
+        _ELL[lmax] = l_of_real_layout(lmax)
+    return _ELL[lmax]
+
+
+def generate_var_cl_vec(dls):
+    """Same values as generate_var_cl (utils.py:114-147), without the Python double loop: what the compiled Cython twin
+    (variance_expension.pyx:8-33) costs.  tests/test_golden_oracle.py checks the two agree bit for bit."""
+    lmax = len(dls) - 1
+    ell = np.arange(lmax + 1, dtype=np.float64)
+    cl = np.asarray(dls, dtype=np.float64).copy()
+    cl[1:] = cl[1:] * 2 * np.pi / (ell[1:] * (ell[1:] + 1))
+    return cl[ell_index(lmax)]
+
+
+def expand_per_l_vec(x):
+    return np.asarray(x)[ell_index(len(x) - 1)]
+
+
 def safe_inv(v):
     out = np.zeros(len(v))
     out[v != 0] = 1 / v[v != 0]
@@ -79,29 +103,34 @@ def adjoint_pol(q, u, nside, lmax, iter=0, kind="ld"):
 class PolProblem:
     """Inputs of the polarised masked-sky CR step (CenteredGibbs.py:243-314)."""
 
-    def __init__(self, nside, lmax, d_Q, d_U, inv_noise_pol, fwhm_deg, kind="ld"):
+    def __init__(self, nside, lmax, d_Q, d_U, inv_noise_pol, fwhm_deg, kind="ld", vectorised=False):
+        """vectorised=True swaps the reference's pure-Python O(L^2) loops (generate_var_cl, the bl_map expansion) for their
+        numpy twins -- identical values; used where the restatement is TIMED (bench.py reference arm), so that the CPU
+        baseline is not charged for interpreter loops the reference's compiled Cython twin avoids."""
         self.nside, self.lmax, self.kind = nside, lmax, kind
+        self.var_cl = generate_var_cl_vec if vectorised else generate_var_cl
+        self.expand = expand_per_l_vec if vectorised else expand_per_l
         self.npix = 12 * nside * nside
         self.d_Q, self.d_U = d_Q, d_U
         self.inv_noise = inv_noise_pol
         self.bl_gauss = sht.gauss_beam(np.radians(fwhm_deg), lmax)
-        self.bl_map = expand_per_l(self.bl_gauss)
+        self.bl_map = self.expand(self.bl_gauss)
         # second_part_grad (CenteredGibbs.py:298-308)
         e, b = adjoint_pol(d_Q * inv_noise_pol, d_U * inv_noise_pol, nside, lmax, 0, kind)
         self.bdata_E, self.bdata_B = e * self.bl_map, b * self.bl_map
 
     def rhs(self, dl_EE, dl_BB, xi_Q, xi_U, xi_E, xi_B, fluct_iter=3):
         """CenteredGibbs.py:469-483 + the data term qcinv's calc_prep adds in chain.sample"""
-        ivE, ivB = safe_inv(generate_var_cl(dl_EE)), safe_inv(generate_var_cl(dl_BB))
+        ivE, ivB = safe_inv(self.var_cl(dl_EE)), safe_inv(self.var_cl(dl_BB))
         fe, fb = adjoint_pol(xi_Q * np.sqrt(self.inv_noise), xi_U * np.sqrt(self.inv_noise), self.nside, self.lmax,
                              fluct_iter, self.kind)
         bE = fe * self.bl_map + np.sqrt(ivE) * xi_E + self.bdata_E
         bB = fb * self.bl_map + np.sqrt(ivB) * xi_B + self.bdata_B
         return bE, bB
 
-    def apply_Q(self, dl_EE, dl_BB, xE, xB):
+    def apply_Q(self, dl_EE, dl_BB, xE, xB, inv_var=None):
         """qcinv opfilt_pp.fwd_op: C^-1 x + b (Npix/4pi) map2alm0(N^-1 alm2map(b x))"""
-        ivE, ivB = safe_inv(generate_var_cl(dl_EE)), safe_inv(generate_var_cl(dl_BB))
+        ivE, ivB = inv_var if inv_var is not None else (safe_inv(self.var_cl(dl_EE)), safe_inv(self.var_cl(dl_BB)))
         q, u = synth_pol(xE * self.bl_map, xB * self.bl_map, self.nside, self.lmax, self.kind)
         e, b = adjoint_pol(q * self.inv_noise, u * self.inv_noise, self.nside, self.lmax, 0, self.kind)
         return ivE * xE + e * self.bl_map, ivB * xB + b * self.bl_map
@@ -114,7 +143,7 @@ class PolProblem:
             cl = dl * np.array([2 * np.pi / (l * (l + 1)) if l else 0 for l in range(self.lmax + 1)])
             cl[0] = dl[0]
             d = safe_inv(cl) + self.bl_gauss ** 2 * ninv
-            out.append(expand_per_l(safe_inv(d)))
+            out.append(self.expand(safe_inv(d)))
         return out
 
     def pcg(self, dl_EE, dl_BB, bE, bB, eps=1e-5, itermax=4000, x0=None):
@@ -123,7 +152,8 @@ class PolProblem:
         b = np.concatenate([bE, bB])
         M = np.concatenate([ME, MB])
         n = len(bE)
-        A = lambda v: np.concatenate(self.apply_Q(dl_EE, dl_BB, v[:n], v[n:]))
+        inv_var = (safe_inv(self.var_cl(dl_EE)), safe_inv(self.var_cl(dl_BB)))   # s_cls of the chain, built once per solve
+        A = lambda v: np.concatenate(self.apply_Q(dl_EE, dl_BB, v[:n], v[n:], inv_var))
         x = np.zeros(2 * n) if x0 is None else np.concatenate(x0)
         r = b - A(x) if x0 is not None else b.copy()
         d0 = r @ r
@@ -192,12 +222,112 @@ def cls_sample(alms_real, bins, lmax, gamma_draws):
 
 
 # ---------------------------------------------------------------- non-centred likelihood (NonCenteredGibbs.py:333-355)
-def nc_loglik(binned, bins, s_nc, prob):
+def nc_loglik(binned, bins, s_nc, prob, l_cut=0):
+    """NonCenteredGibbs.py:333-355.  l_cut > 0 (partially non-centred parametrisation, see PNCPPol below): the
+    multipoles l < l_cut of `s_nc` are the centred coefficients and are synthesised without the sqrt(C_l) factor."""
     dlE, dlB = unfold_bins(binned["EE"], bins["EE"]), unfold_bins(binned["BB"], bins["BB"])
-    vE, vB = generate_var_cl(dlE), generate_var_cl(dlB)
-    q, u = synth_pol(prob.bl_map * np.sqrt(vE) * s_nc["EE"], prob.bl_map * np.sqrt(vB) * s_nc["BB"], prob.nside, prob.lmax,
-                     prob.kind)
+    vE, vB = prob.var_cl(dlE), prob.var_cl(dlB)
+    fE, fB = np.sqrt(vE), np.sqrt(vB)
+    if l_cut > 0:
+        low = ell_index(prob.lmax) < l_cut
+        fE, fB = np.where(low, 1.0, fE), np.where(low, 1.0, fB)
+    q, u = synth_pol(prob.bl_map * fE * s_nc["EE"], prob.bl_map * fB * s_nc["BB"], prob.nside, prob.lmax, prob.kind)
     return -0.5 * (np.sum((prob.d_Q - q) ** 2 * prob.inv_noise) + np.sum((prob.d_U - u) ** 2 * prob.inv_noise))
+
+
+# ---------------------------------------------------------------- blocked Metropolis-within-Gibbs (NonCenteredGibbs.py:292-330, 401-445)
+def mwg_propose(old, proposal_variances):
+    """propose_dl for one spectrum (NonCenteredGibbs.py:292-309 / ClsSampler.py:79-92): truncated normal on [0, inf) centred on
+    the current value, bins 0 and 1 pinned to 0; scipy draws from numpy's global stream."""
+    from scipy.stats import truncnorm
+    sc = np.sqrt(proposal_variances)
+    return np.concatenate([np.zeros(2), truncnorm.rvs(a=-old[2:] / sc, b=np.inf, loc=old[2:], scale=sc)])
+
+
+def mwg_log_proposal(x, frm, proposal_variances):
+    """compute_log_proposal for one spectrum (NonCenteredGibbs.py:313-330): log q(frm -> x) per bin."""
+    from scipy.stats import truncnorm
+    sc = np.sqrt(proposal_variances)
+    return np.concatenate([np.zeros(2), truncnorm.logpdf(x[2:], a=-frm[2:] / sc, b=np.inf, loc=frm[2:], scale=sc)])
+
+
+def mwg_sweep(prob, bins, blocks, proposal_variances, s_nc, binned_old, l_cut=0, n_iter=1):
+    """PolarizationNonCenteredClsSampler.sample (NonCenteredGibbs.py:401-445): propose every bin of EE then BB, then accept
+    / reject block by block (EE blocks first) with  log r = sum_block [log q(new -> old) - log q(old -> new)] + lik(new) -
+    lik(old);  one uniform per test from numpy's global stream.  Returns (binned, accept lists)."""
+    cur = {p: np.array(binned_old[p], dtype=np.float64) for p in ("EE", "BB")}
+    prop = {p: mwg_propose(cur[p], proposal_variances[p]) for p in ("EE", "BB")}
+    logr = {p: mwg_log_proposal(cur[p], prop[p], proposal_variances[p]) - mwg_log_proposal(prop[p], cur[p], proposal_variances[p])
+            for p in ("EE", "BB")}
+    old_lik = nc_loglik(cur, bins, s_nc, prob, l_cut)
+    accept = {"EE": [], "BB": []}
+    for pol in ("EE", "BB"):
+        bl = blocks[pol]
+        for i in range(len(bl) - 1):
+            b0, b1 = int(bl[i]), int(bl[i + 1])
+            for _ in range(n_iter):
+                cand = {p: cur[p].copy() for p in cur}
+                cand[pol][b0:b1] = prop[pol][b0:b1]
+                new_lik = nc_loglik(cand, bins, s_nc, prob, l_cut)
+                log_r = np.sum(logr[pol][b0:b1]) + new_lik - old_lik
+                if np.log(np.random.uniform()) < log_r:
+                    cur, old_lik = cand, new_lik
+                    accept[pol].append(1)
+                else:
+                    accept[pol].append(0)
+    return cur, accept
+
+
+class PNCPPol:
+    """Polarised, masked-sky partially non-centred Gibbs iteration (BASELINE config #3).
+
+    The reference ships PNCP only as TT / full-sky bytecode (__pycache__/PNCP.cpython-38.pyc), so there is no reference
+    implementation of this sampler: it is DEFINED as the composition of reference pieces below, and this class is the
+    deterministic CPU statement of that definition which gibbssampler_b200/PNCP.py must reproduce draw for draw:
+      1. CR: the centred PCG draw of CenteredGibbs.py:448-491 (PolProblem.rhs + .pcg, eps 1e-5);
+      2. low l: inverse-gamma draw of CenteredGibbs.py:54-79, kept only for the bins below l_cut
+         (recovered PNCPClsSampler.sample_low_l);
+      3. s -> mixed variable: s_l for l < l_cut, C_l^-1/2 s_l for l >= l_cut (generalises NonCenteredGibbs.py:192-194 and
+         the recovered compute_var_high_low / PNCPConstrainedRealization.sample);
+      4. high l: the blocked Metropolis-within-Gibbs sweep of NonCenteredGibbs.py:401-445 on the bins >= l_cut with the
+         pixel-space likelihood of :333-355 (recovered PNCPClsSampler.sample_high_l).
+    Random numbers come from numpy's legacy global stream in exactly this order: xi_Q, xi_U, xi_E, xi_B (normal), the
+    EE then BB inverse-gamma draws (scipy), the EE then BB truncated-normal proposals (scipy), one uniform per test."""
+
+    def __init__(self, prob, bins, blocks, proposal_variances, l_cut, n_iter=1, eps=1e-5):
+        self.prob, self.bins, self.blocks, self.pv = prob, bins, blocks, proposal_variances
+        self.l_cut, self.n_iter, self.eps = int(l_cut), n_iter, eps
+        self.low_bins = {p: int(np.searchsorted(np.asarray(bins[p]), l_cut, side="left")) for p in ("EE", "BB")}
+        self.last_pcg_iterations = 0
+
+    def factor(self, dl, inverse):
+        """per-coefficient factor of step 3 (inverse=True: C^-1/2, else C^1/2) on l >= l_cut, 1 below"""
+        v = self.prob.var_cl(dl)
+        f = np.sqrt(safe_inv(v)) if inverse else np.sqrt(v)
+        return np.where(ell_index(self.prob.lmax) < self.l_cut, 1.0, f)
+
+    def iteration(self, binned):
+        from scipy.stats import invgamma
+        p, lmax = self.prob, self.prob.lmax
+        npix, nre = p.npix, (lmax + 1) ** 2
+        dls = {k: unfold_bins(binned[k], self.bins[k]) for k in ("EE", "BB")}
+        xi = [np.random.normal(loc=0, scale=1, size=n) for n in (npix, npix, nre, nre)]
+        bE, bB = p.rhs(dls["EE"], dls["BB"], *xi)
+        sE, sB, it, _ = p.pcg(dls["EE"], dls["BB"], bE, bB, eps=self.eps)
+        self.last_pcg_iterations = it
+        sky = {"EE": sE, "BB": sB}
+        new = {}
+        for pol in ("EE", "BB"):                                    # step 2
+            al, be = cls_alpha_beta(sky[pol], self.bins[pol], lmax)
+            draw = be * invgamma.rvs(a=al)
+            draw[:2] = 0
+            o = np.array(binned[pol], dtype=np.float64)
+            o[:self.low_bins[pol]] = draw[:self.low_bins[pol]]
+            new[pol] = o
+        dls = {k: unfold_bins(new[k], self.bins[k]) for k in ("EE", "BB")}
+        mixed = {k: sky[k] * self.factor(dls[k], True) for k in ("EE", "BB")}    # step 3
+        out, accept = mwg_sweep(p, self.bins, self.blocks, self.pv, mixed, new, self.l_cut, self.n_iter)   # step 4
+        return out, accept, sky
 
 
 def nc_loglik_all_sph(binned, bins, s_nc, d_E, d_B, bl_map, inv_noise0, npix):

@@ -33,6 +33,25 @@ def _lib(kind="ld"):
     return _LIBS[kind]
 
 
+def _fast():
+    """oracle/sht_fast.c: the vectorised spin-2 pair (libsharp-style stand-in for healpy on the host cores)."""
+    if "fast" not in _LIBS:
+        path = os.path.join(_HERE, "_build", "liboracle_fast.so")
+        if not os.path.exists(path):
+            build()
+        lib = C.CDLL(path)
+        dp = C.POINTER(C.c_double)
+        lib.orf_alm2map_spin2.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp]
+        lib.orf_map2alm_spin2.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.c_double]
+        lib.orf_test_fft.argtypes = [C.c_int, dp, dp, dp, dp]
+        _LIBS["fast"] = lib
+    return _LIBS["fast"]
+
+
+def num_threads(kind="f64"):
+    return _fast().orf_num_threads() if kind == "fast" else _lib(kind).orc_num_threads()
+
+
 def _p(a):
     return a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None else None
 
@@ -88,6 +107,10 @@ def alm2map_spin2(almE, almB, nside, lmax, kind="ld"):
     e = np.ascontiguousarray(almE, dtype=np.complex128)
     b = np.ascontiguousarray(almB, dtype=np.complex128)
     q, u = np.empty(12 * nside * nside), np.empty(12 * nside * nside)
+    if kind == "fast":
+        rc = _fast().orf_alm2map_spin2(nside, lmax, _p(e.view(np.float64)), _p(b.view(np.float64)), _p(q), _p(u))
+        assert rc == 0
+        return q, u
     rc = _lib(kind).orc_alm2map(nside, lmax, 2, _p(e.view(np.float64)), _p(b.view(np.float64)), _p(q), _p(u))
     assert rc == 0
     return q, u
@@ -106,6 +129,10 @@ def _map2alm2(q, u, nside, lmax, weight, kind):
     u = np.ascontiguousarray(u, dtype=np.float64)
     e = np.zeros(nalm(lmax), dtype=np.complex128)
     b = np.zeros(nalm(lmax), dtype=np.complex128)
+    if kind == "fast":
+        rc = _fast().orf_map2alm_spin2(nside, lmax, _p(q), _p(u), _p(e.view(np.float64)), _p(b.view(np.float64)), weight)
+        assert rc == 0
+        return e, b
     rc = _lib(kind).orc_map2alm(nside, lmax, 2, _p(q), _p(u), _p(e.view(np.float64)), _p(b.view(np.float64)), weight)
     assert rc == 0
     return e, b
