@@ -27,11 +27,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# PCG iterations to eps = 1e-5 of the benchmark system (fixed seed).  The count is a property of the
-# linear system and stopping rule, not of the implementation (tests/test_cr_gpu.py shows the oracle and
-# the GPU agree to +-1); the CPU reference arm uses it to extrapolate its bounded sample.
-PCG_ITERS = {512: 345}
-RHS_SHT_EQUIV = 8  # data term is precomputed; fluctuation term = map2alm(iter=3) = 1 + 3 x 2 transforms, +1 spare
+REF_BUDGET_S = 1500.0   # wall-clock budget of the reference arm (the driver's limit per arm is 1800 s)
 
 
 def pixel_z(nside):
@@ -133,55 +129,217 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
-def cpu_pair_seconds(nside, lmax, reps, seed=0, min_seconds=0.0):
-    """Seconds per spin-2 SHT pair (alm2map_spin2 + adjoint) of the CPU oracle port on all host cores: median over at least
-    `reps` pairs, continued until `min_seconds` of CPU work have been sampled.  Returns (seconds, threads, pairs timed)."""
+def cpu_problem(args):
+    """The benchmark workload restated for the CPU arm: same spectra, beam, noise level, mask, bins, Metropolis blocks and
+    proposal variances as the GPU arm (its own realisation of sky and noise, numpy seed 1234), as the oracle's PolProblem /
+    PNCPPol on the vectorised SHT (oracle/sht_fast.c) with the numpy twins of the reference's O(L^2) Python loops."""
+    from oracle import reference_logic as R
+    from oracle import sht as O
+    import scipy.stats  # noqa: F401  (imported here so that no timed step pays for it)
+    nside, lmax = args.nside, args.lmax
+    npix, nre = 12 * nside * nside, (lmax + 1) ** 2
+    dlE, dlB = fiducial(lmax)
+    fwhm = 0.5 * (512 // nside) if nside < 512 else 0.5
+    bl = O.gauss_beam(np.radians(fwhm), lmax)
+    noise_var = 0.04 * npix / 786432.0
+    mask = make_mask(nside)
+    rng = np.random.default_rng(1234)
+    bl_map = R.expand_per_l_vec(bl)
+    sE = rng.standard_normal(nre) * np.sqrt(R.generate_var_cl_vec(dlE))
+    sB = rng.standard_normal(nre) * np.sqrt(R.generate_var_cl_vec(dlB))
+    q, u = R.synth_pol(sE * bl_map, sB * bl_map, nside, lmax, "fast")
+    dQ = (q + rng.standard_normal(npix) * np.sqrt(noise_var)) * mask
+    dU = (u + rng.standard_normal(npix) * np.sqrt(noise_var)) * mask
+    prob = R.PolProblem(nside, lmax, dQ, dU, mask / noise_var, fwhm, kind="fast", vectorised=True)
+    bins = bins_for(lmax)
+    blocks = blocks_for(lmax, bins, L_CUT)
+    pv = proposal_variances_for(lmax, bins, dlE, dlB, noise_var, npix, bl)
+    binned = {pol: np.array([dl[bins[pol][i]:bins[pol][i + 1]].mean() for i in range(len(bins[pol]) - 1)])
+              for pol, dl in (("EE", dlE), ("BB", dlB))}
+    return prob, bins, blocks, pv, binned
+
+
+def cpu_centered_iteration(prob, bins, binned):
+    """One CenteredGibbs iteration on the CPU restatement: sample_mask (CenteredGibbs.py:448-491) + the inverse-gamma draw
+    (CenteredGibbs.py:54-93).  Returns (binned, PCG iterations)."""
+    from oracle import reference_logic as R
+    from scipy.stats import invgamma
+    lmax = prob.lmax
+    dls = {k: R.unfold_bins(binned[k], bins[k]) for k in ("EE", "BB")}
+    xi = [np.random.normal(size=n) for n in (prob.npix, prob.npix, (lmax + 1) ** 2, (lmax + 1) ** 2)]
+    bE, bB = prob.rhs(dls["EE"], dls["BB"], *xi)
+    sE, sB, it, _ = prob.pcg(dls["EE"], dls["BB"], bE, bB, eps=1e-5)
+    out = {}
+    for pol, s in (("EE", sE), ("BB", sB)):
+        al, be = R.cls_alpha_beta(s, bins[pol], lmax)
+        d = be * invgamma.rvs(a=al)
+        d[:2] = 0
+        out[pol] = d
+    return out, it
+
+
+def host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; a CPU arm is ONE process that owns the host, so give the OpenMP
+    oracle every core (the library reads the variable when it is first loaded)."""
+    if "TORCHELASTIC_RUN_ID" in os.environ or os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    # numpy's BLAS pool (the PCG dot products) would spin on the same cores as the OpenMP SHT threads: keep BLAS serial
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=1, user_api="blas")
+    except Exception:
+        pass
+
+
+def cpu_host_info():
+    """Threads, vector ISA and measured DFMA peak of the host cores (all cores busy), for the GFLOP/s-per-core figure."""
+    import ctypes as C
+    from oracle import sht as O
+    lib = O._fast()
+    lib.orf_fma_peak_gflops_per_core.restype = C.c_double
+    lib.orf_fma_peak_gflops_per_core.argtypes = [C.c_double]
+    return {"threads": int(lib.orf_num_threads()), "simd_bits": int(lib.orf_simd_bits()),
+            "dfma_peak_gflops_per_core": float(lib.orf_fma_peak_gflops_per_core(1.0))}
+
+
+def cpu_pair_seconds(nside, lmax, reps, seed=0):
+    """Seconds per spin-2 SHT pair (alm2map_spin2 + A^T) of the vectorised CPU port on all host cores, best of reps."""
     from oracle import sht as O
     rng = np.random.default_rng(seed)
     n = O.nalm(lmax)
     e = rng.standard_normal(n) + 1j * rng.standard_normal(n)
     b = rng.standard_normal(n) + 1j * rng.standard_normal(n)
     ts = []
-    while len(ts) < reps or (sum(ts) < min_seconds and len(ts) < 200):
+    for _ in range(reps + 1):
         t0 = time.perf_counter()
-        q, u = O.alm2map_spin2(e, b, nside, lmax, kind="f64")
-        O.map2alm_spin2(q, u, nside, lmax, adjoint=True, kind="f64")
+        q, u = O.alm2map_spin2(e, b, nside, lmax, kind="fast")
+        O.map2alm_spin2(q, u, nside, lmax, adjoint=True, kind="fast")
         ts.append(time.perf_counter() - t0)
-    return float(np.median(ts)), O._lib("f64").orc_num_threads(), len(ts)
+    return float(np.min(ts[1:]))
+
+
+def legendre_flops(nside, lmax):
+    """algorithmic flops of one spin-2 Legendre transform (unpruned): 26 per (ring pair, l, m)."""
+    nring = 4 * nside - 1
+    n_lm2 = sum(lmax - max(m, 2) + 1 for m in range(lmax + 1))
+    return 26.0 * ((nring + 1) // 2) * n_lm2
+
+
+def python_overhead_term(args, n_blocks):
+    """The live reference calls the PURE-PYTHON utils.generate_var_cl (utils.py:114-147; the Cython import is commented out,
+    utils.py:5) twice per constrained realization and twice per likelihood evaluation: its cost per Gibbs iteration, timed on
+    the restatement of that loop (oracle.reference_logic.generate_var_cl), stated separately and NOT part of `value`."""
+    from oracle import reference_logic as R
+    dl = fiducial(args.lmax)[0]
+    t0 = time.perf_counter()
+    R.generate_var_cl(dl)
+    t = time.perf_counter() - t0
+    calls = 2 + (2 * (n_blocks + 1) if args.sampler == "pncp" else 0)
+    return {"generate_var_cl_s_per_call": t, "calls_per_iteration": calls, "s_per_iteration": t * calls,
+            "note": "pure-Python O(lmax^2) loop of the live reference (utils.py:114-147), excluded from value: the CPU arm uses "
+                    "its vectorised twin, i.e. what the reference's compiled Cython version (variance_expension.pyx:8-33) would cost"}
+
+
+def cpu_baseline_sample(args, n_pcg, n_blocks):
+    """cpu_baseline leg of the GPU arm (rank 0, N = 1): a BOUNDED sample of the same workload on the host cores, about
+    10-30 s of CPU work: the RHS, a PCG solve cut after `n_cap` iterations and `n_lik` likelihood evaluations of the
+    Metropolis sweep are timed on the CPU restatement and scaled to the iteration counts the GPU run measured.
+    (`bench.py --impl reference` runs whole iterations instead.)"""
+    host_threads()
+    from oracle import reference_logic as R
+    prob, bins, blocks, pv, binned = cpu_problem(args)
+    host = cpu_host_info()
+    pair_s = cpu_pair_seconds(args.nside, args.lmax, 2)
+    lmax = args.lmax
+    dls = {k: R.unfold_bins(binned[k], bins[k]) for k in ("EE", "BB")}
+    np.random.seed(99)
+    xi = [np.random.normal(size=n) for n in (prob.npix, prob.npix, (lmax + 1) ** 2, (lmax + 1) ** 2)]
+    t0 = time.perf_counter()
+    bE, bB = prob.rhs(dls["EE"], dls["BB"], *xi)
+    t_rhs = time.perf_counter() - t0
+    n_cap = max(4, min(n_pcg, int(8.0 / max(pair_s, 1e-3))))
+    t0 = time.perf_counter()
+    sE, sB, it, _ = prob.pcg(dls["EE"], dls["BB"], bE, bB, eps=1e-5, itermax=n_cap)
+    t_pcg_it = (time.perf_counter() - t0) / max(it, 1)
+    t_lik, n_lik = 0.0, 0
+    if args.sampler == "pncp":
+        n_lik = 8
+        s = {"EE": sE, "BB": sB}
+        t0 = time.perf_counter()
+        for _ in range(n_lik):
+            R.nc_loglik(binned, bins, s, prob, L_CUT)
+        t_lik = (time.perf_counter() - t0) / n_lik
+    t_iter = t_rhs + n_pcg * t_pcg_it + (n_blocks + 1) * t_lik if args.sampler == "pncp" else t_rhs + n_pcg * t_pcg_it
+    gf_core = 2 * legendre_flops(args.nside, args.lmax) / pair_s * 1e-9 / host["threads"]
+    return {"value": 1.0 / t_iter, "unit": "it/s", "cores": host["threads"], "kind": "port",
+            "sample": "bounded: RHS (%.2f s) + %d PCG iterations (%.3f s each) + %d likelihood evaluations (%.3f s each) of the CPU "
+                      "restatement (oracle/reference_logic.py on oracle/sht_fast.c) at the full NSIDE/lmax, scaled to the %d PCG "
+                      "iterations and %d Metropolis tests + 1 of the GPU run" % (t_rhs, it, t_pcg_it, n_lik, t_lik, n_pcg, n_blocks),
+            "sht_pair_s": pair_s, "pairs_per_s": 1.0 / pair_s, "sht_gflops_per_core": gf_core, "simd_bits": host["simd_bits"],
+            "dfma_peak_gflops_per_core": host["dfma_peak_gflops_per_core"],
+            "sht_fraction_of_host_dfma_peak": gf_core / host["dfma_peak_gflops_per_core"] if host["dfma_peak_gflops_per_core"] else None,
+            "reference_python_overhead": python_overhead_term(args, n_blocks)}
 
 
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path.  healpy/qcinv cannot be installed
-    here, so this is the oracle port (C + OpenMP, FP64) of the same algorithm on the box's host cores."""
+    """Reference arm: the reference's own CPU algorithm for the path, on the box's host cores.  healpy / qcinv cannot be
+    installed here, so it is the oracle restatement (PolProblem.rhs + .pcg to eps 1e-5, inverse-gamma draw, blocked
+    Metropolis sweep with one full spin-2 synthesis per block: oracle/reference_logic.py) on the vectorised SHT port
+    (oracle/sht_fast.c).  A timed step is ONE REAL Gibbs iteration at the full NSIDE / lmax; the warm-up steps page the
+    tables in and spin the thread pool up with one SHT pair each (a CPU arm has nothing else to warm)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm is ONE process that owns the host, so give the
-    # OpenMP oracle every core (the library reads the variable when it is first loaded, below)
-    if "TORCHELASTIC_RUN_ID" in os.environ or os.environ.get("OMP_NUM_THREADS") == "1":
-        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
-    nside, lmax = args.nside, args.lmax
-    n_pcg = args.pcg_iters or PCG_ITERS.get(nside) or 300
-    t_pairs = []
-    for _ in range(args.warmup + args.steps):
-        t, cores, _ = cpu_pair_seconds(nside, lmax, 1)
-        t_pairs.append(t)
-    t_pair = float(np.median(t_pairs[args.warmup:]))
-    n_pairs = cpu_pairs_per_iteration(args, n_pcg)
-    t_iter = t_pair * n_pairs
+    host_threads()
+    from oracle import reference_logic as R
+    t_start = time.perf_counter()
+    prob, bins, blocks, pv, binned = cpu_problem(args)
+    pncp = args.sampler == "pncp"
+    n_blocks = len(blocks["EE"]) + len(blocks["BB"]) - 2 if pncp else 0
+    host = cpu_host_info()
+    pair_s = None
+    for _ in range(max(args.warmup, 1)):
+        pair_s = cpu_pair_seconds(args.nside, args.lmax, 1)
+    np.random.seed(4321)
+    pn = R.PNCPPol(prob, bins, blocks, pv, L_CUT) if pncp else None
+    t_steps, its, acc = [], [], []
+    budget = float(os.environ.get("GS_REF_BUDGET_S", REF_BUDGET_S))
+    for k in range(args.steps):
+        if t_steps and (time.perf_counter() - t_start) + 1.15 * max(t_steps) > budget:
+            break    # out of wall-clock budget: report the iterations that were really run (steps < requested)
+        t0 = time.perf_counter()
+        if pncp:
+            binned, a, _ = pn.iteration(binned)
+            its.append(pn.last_pcg_iterations)
+            acc.append((sum(a["EE"]) + sum(a["BB"])) / max(1, len(a["EE"]) + len(a["BB"])))
+        else:
+            binned, it = cpu_centered_iteration(prob, bins, binned)
+            its.append(it)
+        t_steps.append(time.perf_counter() - t0)
+    done = len(t_steps)
+    t_iter = float(np.sum(t_steps)) / done
     val = 1.0 / t_iter
+    f2 = legendre_flops(args.nside, args.lmax)
+    gf_core = 2 * f2 / pair_s * 1e-9 / host["threads"]
     line = {
-        "impl": "reference", "metric": "gibbs_iters_per_s", "value": val, "unit": "it/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": "gibbs_iters_per_s", "value": val, "unit": "it/s", "n_gpus": args.gpus, "steps": done,
         "warmup": args.warmup, "ms_per_step": 1e3 * t_iter, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, n_pcg),
-        "sht_pairs_per_s": 1.0 / t_pair,
-        "cpu_baseline": {"value": val, "unit": "it/s", "cores": cores, "kind": "port",
-                         "sample": "each step times 1 spin-2 SHT pair (alm2map_spin2 + A^T) of the oracle port at the full NSIDE/lmax on all host "
-                                   "cores; a Gibbs iteration is extrapolated as %g pairs (n_pcg = %d mat-vecs + RHS transforms%s)"
-                                   % (n_pairs, n_pcg, " + one synthesis per Metropolis block" if args.sampler == "pncp" else "")},
+        "config": workload_config(args),
+        "steps_requested": args.steps, "seconds_per_step": t_steps, "pcg_iterations_per_step": its,
+        "sht_pairs_per_s": 1.0 / pair_s,
+        "cpu_baseline": {"value": val, "unit": "it/s", "cores": host["threads"], "kind": "port",
+                         "sample": "%d full Gibbs iterations of the CPU restatement at the full NSIDE/lmax (none extrapolated): RHS with "
+                                   "map2alm(iter=3), PCG to eps 1e-5 (%s iterations), inverse-gamma draw%s; SHT = oracle/sht_fast.c on all host cores"
+                                   % (done, its, ", %d-block Metropolis sweep with one spin-2 synthesis per block" % n_blocks if pncp else ""),
+                         "sht_pair_s": pair_s, "sht_gflops_per_core": gf_core, "simd_bits": host["simd_bits"],
+                         "dfma_peak_gflops_per_core": host["dfma_peak_gflops_per_core"],
+                         "sht_fraction_of_host_dfma_peak": gf_core / host["dfma_peak_gflops_per_core"] if host["dfma_peak_gflops_per_core"] else None,
+                         "reference_python_overhead": python_overhead_term(args, n_blocks)},
         "e2e": {"value": val, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
+    if pncp:
+        line["mwg"] = {"blocks": n_blocks, "mean_accept_rate": float(np.mean(acc)) if acc else None}
     print(json.dumps(line), flush=True)
 
 
@@ -208,16 +366,7 @@ def pncp_block_count(lmax):
     return len(b["EE"]) + len(b["BB"]) - 2
 
 
-def cpu_pairs_per_iteration(args, n_pcg):
-    """SHT-pair equivalents of one Gibbs iteration on the reference CPU path: n_pcg mat-vecs + the RHS transforms, plus for
-    PNCP one synthesis (= half a pair) per Metropolis block and one for the current likelihood (NonCenteredGibbs.py:401-445)."""
-    pairs = n_pcg + RHS_SHT_EQUIV / 2.0
-    if args.sampler == "pncp":
-        pairs += (pncp_block_count(args.lmax) + 1) / 2.0
-    return pairs
-
-
-def workload_config(args, n_pcg):
+def workload_config(args):
     if args.sampler == "pncp":
         wl = ("PNCP polarised masked sky (BASELINE config #3): PCG constrained realization (eps 1e-5, diag_cl precond) + inverse-gamma "
               "draw of l < %d + blocked Metropolis-within-Gibbs sweep of l >= %d (%d blocks); one independent chain per GPU"
@@ -227,7 +376,7 @@ def workload_config(args, n_pcg):
               "one independent chain per GPU")
     return {"workload": wl, "sampler": args.sampler,
             "nside": args.nside, "lmax": args.lmax, "fsky": 0.8, "beam_fwhm_deg": 0.5 * max(1, 512 // args.nside) if args.nside < 512 else 0.5,
-            "pcg_iterations": n_pcg, "chains_per_gpu": 1,
+            "pcg": "eps 1e-5, diag_cl preconditioner, cold start", "chains_per_gpu": 1,
             "l2_policy": "inputs larger than L2: each PCG iteration streams the 67 MB ring-spectra intermediate, 50 MB of maps and 100 MB of "
                          "recurrence/alm vectors (126 MB L2)"}
 
@@ -329,9 +478,9 @@ def run_sharded(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "CenteredGibbs polarised masked sky, ONE chain, m-sharded SHT with NCCL all-to-all ring<->m transpose "
                                    "(PCG eps 1e-5, diag_cl precond) + inverse-gamma C_l draw", "nside": nside, "lmax": lmax, "fsky": 0.8,
-                       "beam_fwhm_deg": fwhm, "pcg_iterations": n_pcg, "parallelism": "m-shard x%d" % world,
+                       "beam_fwhm_deg": fwhm, "parallelism": "m-shard x%d" % world,
                        "l2_policy": "inputs larger than L2"},
-            "gpu_launches": launches, "sht_pair_ms": sum(st), "sht_pairs_per_s": 1e3 / sum(st),
+            "pcg_iterations_mean": n_pcg, "gpu_launches": launches, "sht_pair_ms": sum(st), "sht_pairs_per_s": 1e3 / sum(st),
             "stage_ms": {"leg_synth+a2a": st[0], "ring_synth": st[1], "ring_anal": st[2], "a2a+leg_anal": st[3]},
             "legendre_tflops_all_gpus": 2 * f2 / ((st[0] + st[3]) * 1e-3) * 1e-12,
             "a2a_bytes_sent_per_gpu_per_transform": exch_bytes,
@@ -466,6 +615,8 @@ def main():
         h2d = 8 * (2 * (lmax + 1) + 2 * nre) + 8 * (2 * nre + nb) + 8 * (2 * nre + nb)
         d2h = 8 * (2 * nre) + 8 * (2 * nre + nb) + 8 * nb + 4 * n_blocks
 
+    counted = {}
+
     def timed(fn, nwarm, nsteps):
         for _ in range(nwarm):
             fn()
@@ -474,11 +625,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = L.gs_launch_count()
         e0.record()
         for _ in range(nsteps):
             fn()
         e1.record()
         torch.cuda.synchronize()
+        counted["launches"] = int(L.gs_launch_count() - n0)     # kernels of this library launched inside the timed region
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.barrier()
@@ -486,12 +639,10 @@ def main():
 
     clocks = ClockSampler(local)
     clocks.start()
-    launches0 = L.gs_launch_count()
     pcg_its.clear()
     ms_total = timed(step_device, args.warmup, args.steps)
-    launches = L.gs_launch_count() - launches0
+    launches = counted["launches"]
     its_timed = pcg_its[args.warmup:]
-    launches = int(launches * args.steps / (args.warmup + args.steps))
     clocks.stop_flag = True
     clocks.join(timeout=2)
 
@@ -582,25 +733,22 @@ def main():
                                  "pcg_dir": vec_bytes[2] / ms3[2] * 1e-6},
                     "note": "each launch timed alone after a write of the 134 MB analysis workspace (L2 flushed), as inside a PCG iteration"}
 
+    # the SHT pair is timed on EVERY rank; the whole-job pairs/s uses the slowest rank's time
+    pair_t = torch.tensor([pair_ms], device=dev, dtype=torch.float64)
+    pair_ms_max = reduce_max_ms(pair_t, world)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        t_pair, cores, reps = cpu_pair_seconds(nside, lmax, 3, min_seconds=10.0)   # ~10 s of host CPU work
-        n_pairs = cpu_pairs_per_iteration(args, n_pcg)
-        t_iter = t_pair * n_pairs
-        cpu_baseline = {"value": 1.0 / t_iter, "unit": "it/s", "cores": cores, "kind": "port",
-                        "pairs_per_s": 1.0 / t_pair,
-                        "sample": "%d spin-2 SHT pairs of the oracle port (C + OpenMP, FP64) at the same NSIDE/lmax; one Gibbs iteration "
-                                  "extrapolated as %g pairs (the n_pcg = %d mat-vecs of this run + RHS transforms%s)"
-                                  % (reps, n_pairs, n_pcg, " + one synthesis per Metropolis block" if pncp else "")}
+        cpu_baseline = cpu_baseline_sample(args, n_pcg, n_blocks)
 
     if rank == 0:
         line = {
             "metric": "gibbs_iters_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(args, n_pcg),
+            "data": "synthetic", "config": workload_config(args), "pcg_iterations_mean": n_pcg,
             "e2e": {"value": e2e_val, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
-            "sht_pairs_per_s": world * 1e3 / pair_ms, "sht_pair_ms": pair_ms, "stage_ms": stage_ms,
+            "sht_pairs_per_s": world * 1e3 / pair_ms_max, "sht_pair_ms": pair_ms_max, "stage_ms": stage_ms,
             "pcg_matvec": {"ms": sum(matvec_ms.values()), "stage_ms": matvec_ms, "active_ring_pairs": act.value, "ring_pairs": tot.value,
                            "note": "mat-vec of the PCG: ring pairs wholly inside the mask (N^-1 = 0) are skipped, exact"},
             "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_pcg": roofline_pcg, "cpu_baseline": cpu_baseline, "clocks": clocks.summary(),

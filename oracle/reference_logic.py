@@ -131,6 +131,12 @@ class PolProblem:
     def apply_Q(self, dl_EE, dl_BB, xE, xB, inv_var=None):
         """qcinv opfilt_pp.fwd_op: C^-1 x + b (Npix/4pi) map2alm0(N^-1 alm2map(b x))"""
         ivE, ivB = inv_var if inv_var is not None else (safe_inv(self.var_cl(dl_EE)), safe_inv(self.var_cl(dl_BB)))
+        if self.kind == "fast":   # same operator; the beam, N^-1 and the layout conversions ride inside the two SHT calls
+            q, u = sht.synth_real_fast(xE, xB, self.bl_gauss, self.bl_gauss, self.nside, self.lmax)
+            e, b = sht.adjoint_real_fast(q, u, self.inv_noise, self.bl_gauss, self.bl_gauss, self.nside, self.lmax)
+            e += ivE * xE
+            b += ivB * xB
+            return e, b
         q, u = synth_pol(xE * self.bl_map, xB * self.bl_map, self.nside, self.lmax, self.kind)
         e, b = adjoint_pol(q * self.inv_noise, u * self.inv_noise, self.nside, self.lmax, 0, self.kind)
         return ivE * xE + e * self.bl_map, ivB * xB + b * self.bl_map
@@ -153,25 +159,30 @@ class PolProblem:
         M = np.concatenate([ME, MB])
         n = len(bE)
         inv_var = (safe_inv(self.var_cl(dl_EE)), safe_inv(self.var_cl(dl_BB)))   # s_cls of the chain, built once per solve
-        A = lambda v: np.concatenate(self.apply_Q(dl_EE, dl_BB, v[:n], v[n:], inv_var))
+        q, tmp = np.empty(2 * n), np.empty(2 * n)
+
+        def A(v):
+            q[:n], q[n:] = self.apply_Q(dl_EE, dl_BB, v[:n], v[n:], inv_var)
+            return q
         x = np.zeros(2 * n) if x0 is None else np.concatenate(x0)
         r = b - A(x) if x0 is not None else b.copy()
         d0 = r @ r
         z = M * r
         p = z.copy()
         delta = r @ z
-        it = 0
-        while it < itermax and r @ r > eps ** 2 * d0:
-            q = A(p)
+        it, rr = 0, d0
+        while it < itermax and rr > eps ** 2 * d0:
+            A(p)
             alpha = delta / (p @ q)
-            x += alpha * p
-            r -= alpha * q
-            z = M * r
+            np.multiply(p, alpha, out=tmp); x += tmp          # x += alpha p
+            np.multiply(q, alpha, out=tmp); r -= tmp          # r -= alpha q
+            np.multiply(M, r, out=z)
             dn = r @ z
-            p = z + (dn / delta) * p
+            p *= dn / delta; p += z                            # p = z + beta p
             delta = dn
+            rr = r @ r
             it += 1
-        return x[:n], x[n:], it, np.sqrt((r @ r) / d0) if d0 > 0 else 0.0
+        return x[:n], x[n:], it, np.sqrt(rr / d0) if d0 > 0 else 0.0
 
     def dense_Q(self, dl_EE, dl_BB):
         n = (self.lmax + 1) ** 2
@@ -227,6 +238,12 @@ def nc_loglik(binned, bins, s_nc, prob, l_cut=0):
     multipoles l < l_cut of `s_nc` are the centred coefficients and are synthesised without the sqrt(C_l) factor."""
     dlE, dlB = unfold_bins(binned["EE"], bins["EE"]), unfold_bins(binned["BB"], bins["BB"])
     vE, vB = prob.var_cl(dlE), prob.var_cl(dlB)
+    if prob.kind == "fast":   # the filter b_l sqrt(C_l) is a per-l factor: hand it to the fused synthesis
+        lm = prob.lmax
+        fE, fB = np.sqrt(vE[:lm + 1]), np.sqrt(vB[:lm + 1])      # entries 0..lmax of the real layout are the m = 0 column
+        fE[:l_cut], fB[:l_cut] = 1.0, 1.0
+        q, u = sht.synth_real_fast(s_nc["EE"], s_nc["BB"], prob.bl_gauss * fE, prob.bl_gauss * fB, prob.nside, lm)
+        return -0.5 * sht.chi2_fast(prob.d_Q, prob.d_U, q, u, prob.inv_noise)
     fE, fB = np.sqrt(vE), np.sqrt(vB)
     if l_cut > 0:
         low = ell_index(prob.lmax) < l_cut

@@ -44,6 +44,10 @@ def _fast():
         lib.orf_alm2map_spin2.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp]
         lib.orf_map2alm_spin2.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, C.c_double]
         lib.orf_test_fft.argtypes = [C.c_int, dp, dp, dp, dp]
+        lib.orf_chi2.argtypes = [dp, dp, dp, dp, dp, C.c_int64]
+        lib.orf_chi2.restype = C.c_double
+        lib.orf_synth_real.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, dp]
+        lib.orf_adjoint_real.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp, C.c_double, dp, dp]
         _LIBS["fast"] = lib
     return _LIBS["fast"]
 
@@ -156,6 +160,35 @@ def map2alm_spin2(q, u, nside, lmax, iter=0, adjoint=False, kind="ld"):
         de, db = _map2alm2(np.asarray(q) - q2, np.asarray(u) - u2, nside, lmax, w, kind)
         e, b = e + de, b + db
     return e, b
+
+
+def synth_real_fast(sE, sB, flE, flB, nside, lmax):
+    """alm2map_spin2(almxfl(real_to_complex(s), fl)) in one call of the vectorised port (real layout in, per-l factors)."""
+    sE, sB = np.ascontiguousarray(sE, dtype=np.float64), np.ascontiguousarray(sB, dtype=np.float64)
+    flE = None if flE is None else np.ascontiguousarray(flE, dtype=np.float64)
+    flB = None if flB is None else np.ascontiguousarray(flB, dtype=np.float64)
+    q, u = np.empty(12 * nside * nside), np.empty(12 * nside * nside)
+    rc = _fast().orf_synth_real(nside, lmax, _p(sE), _p(sB), _p(flE), _p(flB), _p(q), _p(u))
+    assert rc == 0
+    return q, u
+
+
+def adjoint_real_fast(q, u, pixw, flE, flB, nside, lmax, weight=1.0):
+    """complex_to_real(almxfl(A^T (map * pixw), fl)) * weight in one call of the vectorised port (real layout out)."""
+    q, u = np.ascontiguousarray(q, dtype=np.float64), np.ascontiguousarray(u, dtype=np.float64)
+    pixw = None if pixw is None else np.ascontiguousarray(pixw, dtype=np.float64)
+    flE = None if flE is None else np.ascontiguousarray(flE, dtype=np.float64)
+    flB = None if flB is None else np.ascontiguousarray(flB, dtype=np.float64)
+    e, b = np.empty((lmax + 1) ** 2), np.empty((lmax + 1) ** 2)
+    rc = _fast().orf_adjoint_real(nside, lmax, _p(q), _p(u), _p(pixw), _p(flE), _p(flB), weight, _p(e), _p(b))
+    assert rc == 0
+    return e, b
+
+
+def chi2_fast(dQ, dU, q, u, w):
+    """sum_p w_p [(dQ - q)^2 + (dU - u)^2] in one pass (the two np.sum of NonCenteredGibbs.py:353-355)."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (dQ, dU, q, u, w)]
+    return float(_fast().orf_chi2(*[_p(a) for a in arrs], arrs[0].size))
 
 
 def alm2cl(alm, lmax):

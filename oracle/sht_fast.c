@@ -114,7 +114,7 @@ typedef struct { double a, b, c[8]; } coef_t;   /* per l: recurrence (a, b) + 8 
 typedef void (*fft_fn)(int, v4d *, v4d *, v4d *, v4d *, const double *, const double *, int, v4d **, v4d **);
 typedef void (*rfft_fn)(const fplan *, const blue_t *, v4d *, v4d *, v4d *, v4d *, v4d **, v4d **);
 typedef void (*rsyn_fn)(const fplan *, int, const double *, const double *, v4d *, size_t, double *, double *);
-typedef void (*rana_fn)(const fplan *, int, const double *, const double *, v4d *, size_t, const double *, const double *, double);
+typedef void (*rana_fn)(const fplan *, int, const double *, const double *, v4d *, size_t, const double *, const double *, const double *, double);
 typedef void (*synth_fn)(const fplan *, int, const coef_t *);
 typedef void (*anal_fn)(const fplan *, int, const double *, v8d *, v8d *, int *);
 static fft_fn fft_pow2 = NULL;
@@ -376,8 +376,11 @@ static void ring_phases(const fplan *p, int q, double *cr, double *ci)
 /* ------------------------------------------------------------------ transforms */
 static inline __attribute__((always_inline)) double hsum(v8d v) { double s = 0; for (int i = 0; i < VL; ++i) s += v[i]; return s; }
 
-/* (E, B) healpy complex alms (interleaved re/im) -> RING maps (Q, U): hp.alm2map([0, E, B], pol=True) */
-int orf_alm2map_spin2(int nside, int lmax, const double *almE, const double *almB, double *mapQ, double *mapU)
+/* (E, B) -> RING maps (Q, U): hp.alm2map([0, E, B], pol=True).  real_layout = 0: healpy complex alms (interleaved
+ * re/im); 1: the reference's real layout (utils.py:49-76), i.e. real_to_complex is done while the coefficients are
+ * staged.  flE / flB (nullable): per-l factors applied to the input (hp.almxfl). */
+static int synth_impl(int nside, int lmax, const double *almE, const double *almB, int real_layout, const double *flE,
+                      const double *flB, double *mapQ, double *mapU)
 {
     if (nside < 1 || lmax < 2) return -1;
     fplan *p = plan_get(nside, lmax);
@@ -395,8 +398,18 @@ int orf_alm2map_spin2(int nside, int lmax, const double *almE, const double *alm
             for (int l = l0; l <= L; ++l) {
                 coef_t *c = &cf[l - l0];
                 const double k = -0.5 * p->alpha[base + l], s = ((l + m) & 1) ? -1.0 : 1.0;
-                const double er = almE[2 * (base + l)], ei = almE[2 * (base + l) + 1];
-                const double br = almB[2 * (base + l)], bi = almB[2 * (base + l) + 1];
+                double er, ei, br, bi;
+                if (!real_layout) {
+                    er = almE[2 * (base + l)]; ei = almE[2 * (base + l) + 1];
+                    br = almB[2 * (base + l)]; bi = almB[2 * (base + l) + 1];
+                } else if (m == 0) {
+                    er = almE[l]; ei = 0.0; br = almB[l]; bi = 0.0;
+                } else {
+                    const int64_t o = 2 * (base + l) - (L + 1);
+                    er = almE[o] * M_SQRT1_2; ei = almE[o + 1] * M_SQRT1_2; br = almB[o] * M_SQRT1_2; bi = almB[o + 1] * M_SQRT1_2;
+                }
+                if (flE) { er *= flE[l]; ei *= flE[l]; }
+                if (flB) { br *= flB[l]; bi *= flB[l]; }
                 c->a = p->ra[base + l]; c->b = p->rb[base + l];
                 const double cpr = k * (er - bi), cpi = k * (ei + br);   /* c+ = E + iB */
                 const double cmr = k * (er + bi), cmi = k * (ei - br);   /* c- = E - iB */
@@ -426,17 +439,31 @@ int orf_alm2map_spin2(int nside, int lmax, const double *almE, const double *alm
     return 0;
 }
 
+int orf_alm2map_spin2(int nside, int lmax, const double *almE, const double *almB, double *mapQ, double *mapU)
+{
+    return synth_impl(nside, lmax, almE, almB, 0, NULL, NULL, mapQ, mapU);
+}
+
+/* real-layout coefficients times per-l factors -> maps: alm2map(almxfl(real_to_complex(s), fl)) in one call */
+int orf_synth_real(int nside, int lmax, const double *sE, const double *sB, const double *flE, const double *flB,
+                   double *mapQ, double *mapU)
+{
+    return synth_impl(nside, lmax, sE, sB, 1, flE, flB, mapQ, mapU);
+}
+
 /* RING maps (Q, U) -> (E, B) = weight * sum_p conj(Y)(p) f(p): weight = 4 pi / Npix is hp.map2alm(iter=0,
  * use_weights=False); weight = 1 is the plain transpose A^T of the synthesis (utils.py:79-111 / config.py:72) */
-int orf_map2alm_spin2(int nside, int lmax, const double *mapQ, const double *mapU, double *almE, double *almB, double weight)
+static int anal_impl(int nside, int lmax, const double *mapQ, const double *mapU, const double *pixw, int real_layout,
+                     const double *flE, const double *flB, double *almE, double *almB, double weight)
 {
     if (nside < 1 || lmax < 2) return -1;
     fplan *p = plan_get(nside, lmax);
     if (!p) return -2;
     const int L = lmax, npad = p->npad;
     const int64_t nalm = (int64_t)(L + 1) * (L + 2) / 2;
-    memset(almE, 0, sizeof(double) * 2 * nalm);
-    memset(almB, 0, sizeof(double) * 2 * nalm);
+    const size_t nout = real_layout ? (size_t)(L + 1) * (L + 1) : 2 * (size_t)nalm;
+    memset(almE, 0, sizeof(double) * nout);
+    memset(almB, 0, sizeof(double) * nout);
     const double t_begin = now();
 #pragma omp parallel
     {
@@ -452,7 +479,7 @@ int orf_map2alm_spin2(int nside, int lmax, const double *mapQ, const double *map
                     continue;
                 }
                 ring_phases(p, q, cr, ci);
-                ring_anal_pair(p, q, cr, ci, w, wlen, mapQ, mapU, weight);
+                ring_anal_pair(p, q, cr, ci, w, wlen, mapQ, mapU, pixw, weight);
             }
         }
         free(w); free(cr);
@@ -475,14 +502,49 @@ int orf_map2alm_spin2(int nside, int lmax, const double *mapQ, const double *map
                 const double xr = hsum(a[0]), xi = hsum(a[1]), yr = hsum(a[2]), yi = hsum(a[3]);
                 const double k = -0.5 * p->alpha[base + l];
                 /* E = k (X + Y), B = -i k (X - Y) */
-                almE[2 * (base + l)] = k * (xr + yr); almE[2 * (base + l) + 1] = k * (xi + yi);
-                almB[2 * (base + l)] = k * (xi - yi); almB[2 * (base + l) + 1] = -k * (xr - yr);
+                double er = k * (xr + yr), ei = k * (xi + yi), br = k * (xi - yi), bi = -k * (xr - yr);
+                if (flE) { er *= flE[l]; ei *= flE[l]; }
+                if (flB) { br *= flB[l]; bi *= flB[l]; }
+                if (!real_layout) {
+                    almE[2 * (base + l)] = er; almE[2 * (base + l) + 1] = ei;
+                    almB[2 * (base + l)] = br; almB[2 * (base + l) + 1] = bi;
+                } else if (m == 0) {
+                    almE[l] = er; almB[l] = br;
+                } else {
+                    const int64_t o = 2 * (base + l) - (L + 1);
+                    almE[o] = er * M_SQRT2; almE[o + 1] = ei * M_SQRT2; almB[o] = br * M_SQRT2; almB[o + 1] = bi * M_SQRT2;
+                }
             }
         }
         free(acc); free(rab); free(st); free(lst);
     }
     g_t[2] = now() - t_begin - g_t[3];
     return 0;
+}
+
+int orf_map2alm_spin2(int nside, int lmax, const double *mapQ, const double *mapU, double *almE, double *almB, double weight)
+{
+    return anal_impl(nside, lmax, mapQ, mapU, NULL, 0, NULL, NULL, almE, almB, weight);
+}
+
+/* maps (times the per-pixel weights pixw, nullable) -> real-layout coefficients times per-l factors and `weight`:
+ * complex_to_real(almxfl(map2alm(map * pixw), fl)) * weight / (4 pi / Npix) in one call (weight = 1: A^T) */
+int orf_adjoint_real(int nside, int lmax, const double *mapQ, const double *mapU, const double *pixw, const double *flE,
+                     const double *flB, double weight, double *outE, double *outB)
+{
+    return anal_impl(nside, lmax, mapQ, mapU, pixw, 1, flE, flB, outE, outB, weight);
+}
+
+/* sum_p w_p [(dQ_p - q_p)^2 + (dU_p - u_p)^2]: the pixel-space chi^2 of NonCenteredGibbs.py:353-355 in one pass */
+double orf_chi2(const double *dQ, const double *dU, const double *q, const double *u, const double *w, int64_t npix)
+{
+    double s = 0.0;
+#pragma omp parallel for reduction(+ : s) schedule(static)
+    for (int64_t i = 0; i < npix; ++i) {
+        const double a = dQ[i] - q[i], b = dU[i] - u[i];
+        s += w[i] * (a * a + b * b);
+    }
+    return s;
 }
 
 void orf_last_times(double *t4) { for (int i = 0; i < 4; ++i) t4[i] = g_t[i]; }
@@ -544,7 +606,7 @@ double orf_fma_peak_gflops_per_core(double seconds)
     volatile double sink = 0;
     long iters = 1000000;
     double best = 0;
-    for (int rep = 0; rep < 3; ++rep) {
+    for (int rep = 0; rep < 6; ++rep) {
         double t0 = now();
 #pragma omp parallel
         {
@@ -555,7 +617,7 @@ double orf_fma_peak_gflops_per_core(double seconds)
         double dt = now() - t0;
         double g = (double)iters * 16 * VL * 2 / dt * 1e-9;
         if (g > best) best = g;
-        if (dt < seconds / 3 && rep < 2) iters = (long)(iters * (seconds / 3) / (dt > 1e-6 ? dt : 1e-6));
+        if (dt < seconds / 6 && rep < 2) iters = (long)(iters * (seconds / 6) / (dt > 1e-6 ? dt : 1e-6));
     }
     return best;
 }

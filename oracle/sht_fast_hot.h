@@ -132,7 +132,7 @@ static void FN(ring_synth_pair)(const fplan *p, int q, const double *cr, const d
 
 /* ring stage of one pair, analysis: DFT of the 4 pixel sequences, phase-shifted bins to the records of the pair */
 static void FN(ring_anal_pair)(const fplan *p, int q, const double *cr, const double *ci, v4d *w, size_t wlen,
-                               const double *mapQ, const double *mapU, double weight)
+                               const double *mapQ, const double *mapU, const double *pixw, double weight)
 {
     const int L = p->lmax;
     const int n = p->nphi[q];
@@ -140,9 +140,17 @@ static void FN(ring_anal_pair)(const fplan *p, int q, const double *cr, const do
     const double *qn = mapQ + p->startN[q], *un = mapU + p->startN[q];
     const double *qs = mapQ + p->startS[q], *us = mapU + p->startS[q];
     const int eq = (q == p->npair - 1);
-    for (int j = 0; j < n; ++j) {
-        xr[j] = (v4d){qn[j], un[j], eq ? 0.0 : qs[j], eq ? 0.0 : us[j]};
-        xi[j] = (v4d){0, 0, 0, 0};
+    if (pixw) {   /* per-pixel weight (N^-1) applied while the ring is read */
+        const double *wn = pixw + p->startN[q], *ws = pixw + p->startS[q];
+        for (int j = 0; j < n; ++j) {
+            xr[j] = (v4d){qn[j] * wn[j], un[j] * wn[j], eq ? 0.0 : qs[j] * ws[j], eq ? 0.0 : us[j] * ws[j]};
+            xi[j] = (v4d){0, 0, 0, 0};
+        }
+    } else {
+        for (int j = 0; j < n; ++j) {
+            xr[j] = (v4d){qn[j], un[j], eq ? 0.0 : qs[j], eq ? 0.0 : us[j]};
+            xi[j] = (v4d){0, 0, 0, 0};
+        }
     }
     v4d *orr, *oii;
     FN(ring_fft)(p, &p->blue[q], xr, xi, yr, yi, &orr, &oii);
