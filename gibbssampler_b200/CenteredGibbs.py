@@ -159,8 +159,69 @@ class PolarizedCenteredConstrainedRealization(ConstrainedRealization):
         xe, xb = self.solve(all_dls, rhs_e, rhs_b)
         return self._ret({"EE": xe, "BB": xb}, all_dls["EE"]), 1
 
+    def _single_gpu_only(self, what):
+        """The Metropolis-adjusted / auxiliary-variable CR kernels reduce over whole vectors and draw full-size fields; on an
+        m-sharded plan every rank would see partial sums and its own random numbers and the ranks' accept decisions would
+        diverge.  They are not shard-aware: refuse instead of corrupting the chain."""
+        if self.plan.world > 1:
+            raise _lib.GibbsB200Error("%s is not available on an m-sharded plan (world = %d): use the PCG sampler "
+                                      "(sample_mask) for sharded chains" % (what, self.plan.world))
+
+    # ---- the alternative CR kernels of the reference class (CenteredGibbs.py:494-825) live in cr_extra; bound here as
+    # ---- methods so that cr.sample_mala(...) etc. work as on the reference object
+    def compute_gradient_mala(self, all_dls, s_old):
+        """CenteredGibbs.py:494-520 -> (grad_E, grad_B, s_Q_pix, s_U_pix)."""
+        from . import cr_extra
+        return cr_extra.compute_gradient_mala(self, all_dls, s_old)
+
+    def compute_log_density(self, all_dls, s, s_E_pix=None, s_B_pix=None):
+        """CenteredGibbs.py:534-558 (the pixel-space maps are recomputed when not supplied)."""
+        from . import cr_extra
+        return cr_extra.compute_log_density(self, all_dls, s, s_E_pix, s_B_pix)
+
+    def sample_mala(self, all_dls, s_old, grad_E_old=None, grad_B_old=None):
+        """CenteredGibbs.py:560-603."""
+        from . import cr_extra
+        return cr_extra.sample_mala(self, all_dls, s_old)
+
+    def sample_gibbs_change_variable(self, all_dls, old_s):
+        """CenteredGibbs.py:676-729."""
+        from . import cr_extra
+        return cr_extra.sample_gibbs_change_variable(self, all_dls, old_s)
+
+    def overrelaxation_sampler(self, all_dls, old_s):
+        """CenteredGibbs.py:733-825."""
+        from . import cr_extra
+        return cr_extra.overrelaxation_sampler(self, all_dls, old_s)
+
+    def ULA_no_mask(self, all_dls, s_old):
+        """Preconditioned MALA step for full sky + isotropic noise, all in harmonic space (CenteredGibbs.py:417-446 with
+        :355-414); RNG order: EE normals, BB normals, one uniform.  Returns (s, accept)."""
+        self._single_gpu_only("ULA_no_mask")
+        if self.d_E is None:
+            raise _lib.GibbsB200Error("ULA_no_mask needs pix_map['EE'] and pix_map['BB'] (CenteredGibbs.py:364-365)")
+        dle, dlb = self._dls(all_dls)
+        w = self.Npix / (self.noise_pol0 * 4 * np.pi)
+        L = _lib.lib()
+        scratch = torch.empty(592, dtype=torch.float64, device=self.dev)
+        lr = torch.empty(2, dtype=torch.float64, device=self.dev)
+        new = {}
+        for k, (pol, dl, d) in enumerate((("EE", dle, self.d_E), ("BB", dlb, self.d_B))):
+            so = f64(s_old[pol])
+            xi = self.rng.normal(self.dimension_alm)
+            out = torch.empty_like(so)
+            check(L.gs_ula_nomask(ptr(dl), ptr(self.bl_gauss_d), ptr(d), ptr(so), ptr(xi), w, self.tau, self.lmax, ptr(out),
+                                  ptr(scratch), ptr(lr[k:]), stream()))
+            new[pol] = out
+        log_ratio = float(lr.sum().item())
+        u = float(self.rng.uniform(2)[0].item()) if self.rng.mode == "philox" else np.random.uniform()
+        if np.log(u) < log_ratio:
+            return self._ret(new, s_old["EE"]), 1
+        return s_old, 0
+
     def sample_mask_rj(self, all_dls, s_old, xi=None, u=None):
         """RJPO (CenteredGibbs.py:606-674): PCG started at -s_old, accept with min(1, exp(-r^T (s_old - s)))."""
+        self._single_gpu_only("sample_mask_rj")
         rhs_e, rhs_b = self.build_rhs(all_dls, xi)
         so = {"EE": f64(s_old["EE"]), "BB": f64(s_old["BB"])}
         xe, xb = self.solve(all_dls, rhs_e, rhs_b, x0={"EE": -so["EE"], "BB": -so["BB"]})

@@ -29,19 +29,34 @@ class PolarizedNonCenteredConstrainedRealization(ConstrainedRealization):
             pix_map, noise_temp, noise_pol, bl_map, lmax, Npix, bl_fwhm, mask_path=mask_path, mask=mask, rng=self.rng)
         self.noise_pol0 = self.pol_centered_constraint_realizer.noise_pol0
 
-    def sample_no_mask(self, all_dls):
-        """Full sky, isotropic noise, everything in harmonic space (NonCenteredGibbs.py:138-176, all_sph branch)."""
+    def _data_alm(self):
+        """Harmonic-space data term of the no-mask draw, as d with  r = sqrt(C) b (Npix N^-1[0] / 4 pi) d :
+        all_sph (NonCenteredGibbs.py:162-168): d = pix_map["EE"/"BB"];
+        otherwise (NonCenteredGibbs.py:155-160): (Npix/4pi) map2alm([0, Q N^-1, U N^-1]) with healpy's default iter = 3, i.e.
+        d = map2alm_iter3(Q N^-1, U N^-1) / N^-1[0] in the real layout (computed once, the data do not change)."""
         c = self.pol_centered_constraint_realizer
-        if c.d_E is None:
-            raise _lib.GibbsB200Error("sample_no_mask needs pix_map['EE'] and pix_map['BB']")
+        if self.all_sph or c.d_Q is None:
+            if c.d_E is None:
+                raise _lib.GibbsB200Error("sample_no_mask needs pix_map['EE'] / ['BB'] (all_sph) or the pixel maps 'Q' / 'U'")
+            return c.d_E, c.d_B
+        if getattr(self, "_d_pix_alm", None) is None:
+            inv0 = float(c.inv_noise_pol[0].item())
+            e, b = self.plan.map2alm_spin2(c.d_Q * c.inv_noise_pol, c.d_U * c.inv_noise_pol, iter=3, real_layout=True)
+            self._d_pix_alm = (e / inv0, b / inv0)
+        return self._d_pix_alm
+
+    def sample_no_mask(self, all_dls):
+        """Full sky, isotropic noise (NonCenteredGibbs.py:138-176): harmonic-space data when all_sph, else the pixel maps."""
+        c = self.pol_centered_constraint_realizer
+        d_E, d_B = self._data_alm()
         dle, dlb = c._dls(all_dls)
         w = self.Npix / (self.noise_pol0 * 4 * np.pi)
         n = self.dimension_alm
         xe, xb = self.rng.normal(n), self.rng.normal(n)
         oe, ob = torch.empty_like(xe), torch.empty_like(xb)
         L = _lib.lib()
-        check(L.gs_cr_direct(ptr(dle), ptr(self.bl_gauss_d), ptr(c.d_E), ptr(xe), w, self.lmax, 1, ptr(oe), stream()))
-        check(L.gs_cr_direct(ptr(dlb), ptr(self.bl_gauss_d), ptr(c.d_B), ptr(xb), w, self.lmax, 1, ptr(ob), stream()))
+        check(L.gs_cr_direct(ptr(dle), ptr(self.bl_gauss_d), ptr(d_E), ptr(xe), w, self.lmax, 1, ptr(oe), stream()))
+        check(L.gs_cr_direct(ptr(dlb), ptr(self.bl_gauss_d), ptr(d_B), ptr(xb), w, self.lmax, 1, ptr(ob), stream()))
         return c._ret({"EE": oe, "BB": ob}, all_dls["EE"]), 0
 
     def sample_mask(self, all_dls):

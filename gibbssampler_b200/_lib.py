@@ -71,6 +71,8 @@ SIGNATURES = {
     "gs_mala_propose": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _i64, _vp]),
     "gs_mala_logq": (_i, [_vp, _vp, _vp, _vp, _d, _i64, _vp, _vp, _vp]),
     "gs_dot3": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "gs_ula_nomask": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _d, _i, _vp, _vp, _vp, _vp]),
+    "gs_remove_monopole_dipole": (_i, [_vp, _i, _vp]),
     "gs_expand_var_cl_3x3": (_i, [_vp, _i, _vp, _vp]),
     "gs_inv_chol_3x3": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "gs_matvec_3x3": (_i, [_vp, _vp, _vp, _i, _vp, _vp]),

@@ -43,6 +43,7 @@ def _s_step(cr, dle, dlb, maps, s, alpha):
 
 def sample_gibbs_change_variable(cr, all_dls, old_s):
     """Auxiliary-variable CR step (CenteredGibbs.py:676-729)."""
+    cr._single_gpu_only("sample_gibbs_change_variable")
     dle, dlb = cr._dls(all_dls)
     s = {"EE": f64(old_s["EE"]).clone(), "BB": f64(old_s["BB"]).clone()}
     v = {"Q": torch.zeros(cr.Npix, dtype=torch.float64, device=cr.dev), "U": torch.zeros(cr.Npix, dtype=torch.float64, device=cr.dev)}
@@ -54,6 +55,7 @@ def sample_gibbs_change_variable(cr, all_dls, old_s):
 
 def overrelaxation_sampler(cr, all_dls, old_s):
     """Over-relaxed auxiliary-variable step (CenteredGibbs.py:733-825): v|s plain, then n_gibbs x (s|v, v|s, s|v)."""
+    cr._single_gpu_only("overrelaxation_sampler")
     dle, dlb = cr._dls(all_dls)
     s = {"EE": f64(old_s["EE"]).clone(), "BB": f64(old_s["BB"]).clone()}
     v = {"Q": torch.zeros(cr.Npix, dtype=torch.float64, device=cr.dev), "U": torch.zeros(cr.Npix, dtype=torch.float64, device=cr.dev)}
@@ -77,6 +79,27 @@ def _grad_and_pix(cr, dle, dlb, s):
         check(L.gs_mala_grad(ptr(bd), ptr(invc), ptr(s[pol]), ptr(y), ptr(out), y.numel(), stream()))
         g[pol] = out
     return g, (mq, mu_)
+
+
+def compute_gradient_mala(cr, all_dls, s_old):
+    """compute_gradient_mala (CenteredGibbs.py:494-520) with the reference's return tuple (grad_E, grad_B, Q map, U map)."""
+    dle, dlb = cr._dls(all_dls)
+    s = {"EE": f64(s_old["EE"]), "BB": f64(s_old["BB"])}
+    g, (mq, mu_) = _grad_and_pix(cr, dle, dlb, s)
+    host = not isinstance(s_old["EE"], torch.Tensor)
+    outs = (g["EE"], g["BB"], mq, mu_)
+    return tuple(o.cpu().numpy() for o in outs) if host else outs
+
+
+def compute_log_density(cr, all_dls, s, s_Q_pix=None, s_U_pix=None):
+    """compute_log_density (CenteredGibbs.py:534-558) -> python float."""
+    dle, dlb = cr._dls(all_dls)
+    sd = {"EE": f64(s["EE"]), "BB": f64(s["BB"])}
+    if s_Q_pix is None or s_U_pix is None:
+        pix = cr.plan.alm2map_spin2(sd["EE"], sd["BB"], fl=cr.bl_gauss_d)
+    else:
+        pix = (f64(s_Q_pix), f64(s_U_pix))
+    return _log_density(cr, dle, dlb, sd, pix)
 
 
 def _dot3(a, b, c):
@@ -108,6 +131,7 @@ def _log_q(cr, to, frm, g_from, sigma):
 
 def sample_mala(cr, all_dls, s_old):
     """Preconditioned MALA step (CenteredGibbs.py:560-603)."""
+    cr._single_gpu_only("sample_mala")
     L = _lib.lib()
     dle, dlb = cr._dls(all_dls)
     so = {"EE": f64(s_old["EE"]), "BB": f64(s_old["BB"])}

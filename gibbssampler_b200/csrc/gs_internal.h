@@ -171,6 +171,7 @@ struct gs_plan {
     double* almB_tmp;
     double* almE_tmp2;
     double* almB_tmp2;
+    void* pcg_ws;       // gs_pcg_ws* (solver.cu): PCG vectors / state of this plan, allocated on the first solve
 };
 
 extern int g_gs_ring_skip;        // 1: rings whose pixel weights vanish identically are left out (PCG mat-vec, Metropolis sweep)
@@ -214,6 +215,8 @@ int gs_leg_synth_blocks(gs_plan* p, const double* almE, const double* almB, cons
 int gs_launch_expand_per_l(const double* x, int lmax, int mode, double* out, cudaStream_t st);
 // expansion over the plan's (possibly sharded) real layout
 int gs_plan_expand_per_l(gs_plan* p, const double* x, int mode, double* out, cudaStream_t st);
+// solver.cu
+void gs_pcg_ws_free(gs_plan* p);
 // shard.cu
 int gs_shard_build(gs_plan* p, int rank, int world, const char* nccl_id);
 void gs_shard_free(gs_plan* p);

@@ -254,6 +254,7 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
     p->rank = rank;
     p->comm = nullptr;
     p->lgroup = lgroup;
+    p->pcg_ws = nullptr;
     p->Fx = nullptr;
     p->red_loc = nullptr;
     p->d.sh.world = 1;
@@ -318,6 +319,7 @@ extern "C" int gs_plan_create_sharded_local(gs_plan** out, int nside, int lmax, 
 extern "C" int gs_plan_destroy(gs_plan* p)
 {
     if (!p) return GS_OK;
+    gs_pcg_ws_free(p);
     gs_shard_free(p);
     for (void* d : p->owned) cudaFree(d);
     cudaFree(p->mwg_F);

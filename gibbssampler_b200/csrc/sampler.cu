@@ -809,6 +809,68 @@ extern "C" int gs_mala_logq(const double* to, const double* from, const double* 
     return GS_OK;
 }
 
+// ULA_no_mask (CenteredGibbs.py:355-446) for one spectrum, full sky + isotropic noise, everything diagonal in the real layout:
+//   sigma = 1/(w b^2 + 1/C), mean = sigma b w d, grad(s) = -(s - mean)/sigma,
+//   s_new = s_old + tau sigma grad(s_old) + sqrt(2 tau sigma) xi,
+//   log density(s) = -1/2 (s - mean)^2 / sigma,  log q(to | from) = -1/2 (to - from - tau sigma grad(from))^2 / (2 tau sigma);
+// partial sums of  [log dens(new) + log q(old | new)] - [log dens(old) + log q(new | old)].
+__global__ void __launch_bounds__(SM_NT)
+ula_nomask_kernel(const double* __restrict__ dl, const double* __restrict__ bl, const double* __restrict__ d_alm,
+                  const double* __restrict__ s_old, const double* __restrict__ xi, double w, double tau, int L,
+                  double* __restrict__ s_new, double* __restrict__ partials)
+{
+    double v[1] = {0.0};
+    const int64_t n = (int64_t)(L + 1) * (L + 1);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int l = l_of_real(i, L);
+        double c = dl[l];
+        if (l) c = c * 2.0 * 3.14159265358979323846 / ((double)l * (double)(l + 1));
+        const double b = bl[l];
+        const double ic = c != 0.0 ? 1.0 / c : 0.0;
+        const double sigma = 1.0 / (w * b * b + ic);
+        const double mean = sigma * (b * (w * d_alm[i]));
+        const double so = s_old[i];
+        const double g_old = -(1.0 / sigma) * (so - mean);
+        const double sn = so + tau * sigma * g_old + sqrt(2.0 * tau * sigma) * xi[i];
+        const double g_new = -(1.0 / sigma) * (sn - mean);
+        s_new[i] = sn;
+        const double den = 2.0 * tau * sigma;
+        const double a_new = sn - mean, a_old = so - mean;
+        const double q_on = so - sn - tau * sigma * g_new;   // old | new
+        const double q_no = sn - so - tau * sigma * g_old;   // new | old
+        v[0] += -0.5 * (a_new * a_new / sigma) - 0.5 * (q_on * q_on / den) + 0.5 * (a_old * a_old / sigma) + 0.5 * (q_no * q_no / den);
+    }
+    block_sum<1>(v, partials + blockIdx.x);
+}
+
+extern "C" int gs_ula_nomask(const double* dl, const double* bl, const double* d_alm, const double* s_old, const double* xi,
+                             double npix_over_noise_4pi, double tau, int lmax, double* s_new, double* scratch, double* log_ratio_out,
+                             void* stream)
+{
+    GS_REQUIRE(dl && bl && d_alm && s_old && xi && s_new && scratch && log_ratio_out && lmax >= 0 && tau > 0.0, "bad arguments");
+    ula_nomask_kernel<<<SM_GRID, SM_NT, 0, STREAM(stream)>>>(dl, bl, d_alm, s_old, xi, npix_over_noise_4pi, tau, lmax, s_new, scratch);
+    final_sum_kernel<<<1, SM_NT, 0, STREAM(stream)>>>(scratch, SM_GRID, 1.0, log_ratio_out);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+// remove_monopole_dipole_contributions (variance_expension.pyx:103-111): entries 0, 1, L+1, L+2 of the real layout := 0
+__global__ void zero_mono_dipole_kernel(double* a, int L)
+{
+    if (blockIdx.x == 0 && threadIdx.x < 4) {
+        const int idx[4] = {0, 1, L + 1, L + 2};
+        a[idx[threadIdx.x]] = 0.0;
+    }
+}
+
+extern "C" int gs_remove_monopole_dipole(double* alm_real, int lmax, void* stream)
+{
+    GS_REQUIRE(alm_real && lmax >= 1, "bad arguments");
+    zero_mono_dipole_kernel<<<1, 32, 0, STREAM(stream)>>>(alm_real, lmax);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
 extern "C" int gs_dot3(const double* a, const double* b, const double* c, int64_t n, double* scratch, double* out, void* stream)
 {
     GS_REQUIRE(a && b && scratch && out && n > 0, "bad arguments");

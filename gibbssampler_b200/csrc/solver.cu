@@ -290,10 +290,11 @@ __global__ void rhs_combine_kernel(double* rhs, const double* sic, const double*
 }
 
 // ------------------------------------------------------------------ workspace
+// The workspace belongs to the plan (gs_plan::pcg_ws): created on the first solve, released by gs_plan_destroy through
+// gs_pcg_ws_free.  A plan is used by one host thread at a time (include/gibbs_b200.h), so no lock is taken.
 static gs_pcg_ws* get_ws(gs_plan* p)
 {
-    static thread_local std::vector<std::pair<gs_plan*, gs_pcg_ws*>> cache;
-    for (auto& kv : cache) if (kv.first == p) return kv.second;
+    if (p->pcg_ws) return (gs_pcg_ws*)p->pcg_ws;
     gs_pcg_ws* w = new gs_pcg_ws();
     const size_t n = (size_t)p->nreal_loc;
     w->red = p->world > 1 ? p->red_loc : nullptr;
@@ -308,8 +309,17 @@ static gs_pcg_ws* get_ws(gs_plan* p)
     if (ok) { p->owned.push_back(d); w->state = (PcgState*)d; }
     ok = ok && cudaMallocHost((void**)&w->host_state, sizeof(PcgState)) == cudaSuccess;
     if (!ok) { gs_set_error("PCG workspace allocation failed: %s", cudaGetErrorString(cudaGetLastError())); delete w; return nullptr; }
-    cache.push_back({p, w});
+    p->pcg_ws = w;
     return w;
+}
+
+void gs_pcg_ws_free(gs_plan* p)
+{
+    gs_pcg_ws* w = (gs_pcg_ws*)p->pcg_ws;
+    if (!w) return;
+    if (w->host_state) cudaFreeHost(w->host_state);   // the device buffers are in p->owned
+    delete w;
+    p->pcg_ws = nullptr;
 }
 
 int g_gs_fuse_apq = 0;   // 1: fused analysis-finish + (q += C^-1 p, <p, q>) kernel in the unsharded PCG (measured 0.4 % SLOWER

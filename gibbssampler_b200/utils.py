@@ -60,6 +60,20 @@ def unfold_bins(binned_cls_, bins):
     return _ret(out, binned_cls_)
 
 
+def remove_monopole_dipole_contributions(alms):
+    """variance_expension.remove_monopole_dipole_contributions (variance_expension.pyx:103-111): zeroes the real-layout
+    entries 0, 1, L+1, L+2 IN PLACE and returns the array, like the Cython function does with its memoryview."""
+    if isinstance(alms, torch.Tensor) and alms.is_cuda:
+        lmax = _dev.lmax_from_real(alms.numel())
+        assert alms.dtype == torch.float64 and alms.is_contiguous()
+        check(_lib.lib().gs_remove_monopole_dipole(ptr(alms), lmax, stream()))
+        return alms
+    a = np.asarray(alms)
+    lmax = _dev.lmax_from_real(a.size)
+    a[[0, 1, lmax + 1, lmax + 2]] = 0.0
+    return alms
+
+
 def synthesis_hp(alms, nside):
     """variance_expension.synthesis_hp (variance_expension.pyx:114-123): real-layout alm -> map."""
     a = f64(alms)

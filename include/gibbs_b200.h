@@ -274,6 +274,15 @@ int gs_mala_propose(const double* s, const double* g, const double* sigma, const
 /* out[0] = -1/2 sum (to - from - tau sigma g_from)^2 / (2 tau sigma) (compute_log_proposal, :530-532). */
 int gs_mala_logq(const double* to, const double* from, const double* g_from, const double* sigma,
                  double tau, int64_t n, double* scratch, double* out, void* stream);
+/* ULA_no_mask for one spectrum (CenteredGibbs.py:355-446: compute_gradient_no_mask :355-377, compute_log_proposal_no_mask
+ * :379-392, compute_log_density_no_mask :394-414, proposal and ratio :417-446), full sky + isotropic noise, diagonal in the
+ * real layout: s_new = s_old + tau sigma grad + sqrt(2 tau sigma) xi and log_ratio_out[0] = this spectrum's share of the
+ * Metropolis log-ratio; d_alm = harmonic-space data (pix_map["EE"/"BB"]); scratch: 592 doubles. */
+int gs_ula_nomask(const double* dl, const double* bl, const double* d_alm, const double* s_old, const double* xi,
+                  double npix_over_noise_4pi, double tau, int lmax, double* s_new, double* scratch,
+                  double* log_ratio_out, void* stream);
+/* remove_monopole_dipole_contributions (variance_expension.pyx:103-111): real-layout entries 0, 1, L+1, L+2 := 0, in place. */
+int gs_remove_monopole_dipole(double* alm_real, int lmax, void* stream);
 /* out[0] = sum a b c (c nullable), fixed summation order; scratch: 592 doubles. */
 int gs_dot3(const double* a, const double* b, const double* c, int64_t n, double* scratch, double* out,
             void* stream);

@@ -211,6 +211,36 @@ def sample_no_mask_nc(dl, bl_map, d_alm, xi, npix, noise0):
     return sigma * r + xi * np.sqrt(sigma)
 
 
+def sample_no_mask_nc_pix(dl_EE, dl_BB, bl_map, d_Q, d_U, inv_noise_pol, xi_E, xi_B, nside, lmax, kind="ld"):
+    """PolarizedNonCenteredConstrainedRealization.sample_no_mask, pixel-domain branch (NonCenteredGibbs.py:141-176 with
+    all_sph False, :155-160): r = sqrt(C) b (Npix/4pi) complex_to_real(map2alm([0, Q N^-1, U N^-1], iter=3 (healpy default)))."""
+    npix = 12 * nside * nside
+    out = []
+    rE, rB = adjoint_pol(d_Q * inv_noise_pol, d_U * inv_noise_pol, nside, lmax, 3, kind)
+    for dl, r, xi in ((dl_EE, rE, xi_E), (dl_BB, rB, xi_B)):
+        var = generate_var_cl(dl)
+        sigma = 1 / (1 + inv_noise_pol[0] * bl_map ** 2 * var * npix / (4 * np.pi))
+        out.append(sigma * (np.sqrt(var) * bl_map * r) + xi * np.sqrt(sigma))
+    return out
+
+
+def ula_no_mask(dl_EE, dl_BB, bl_map, d_E, d_B, s_old, npix, noise0, tau, xi_E, xi_B):
+    """ULA_no_mask (CenteredGibbs.py:417-446) with compute_gradient_no_mask (:355-377), compute_log_proposal_no_mask
+    (:379-392) and compute_log_density_no_mask (:394-414): returns (s_new dict, log_ratio)."""
+    sig, mean = {}, {}
+    for pol, dl, d in (("EE", dl_EE, d_E), ("BB", dl_BB, d_B)):
+        iv = safe_inv(generate_var_cl(dl))
+        sig[pol] = 1 / ((npix / (noise0 * 4 * np.pi)) * bl_map ** 2 + iv)
+        mean[pol] = sig[pol] * (bl_map * ((npix * (1 / noise0) / (4 * np.pi)) * d))
+    grad = lambda s: {p: -(1 / sig[p]) * (s[p] - mean[p]) for p in ("EE", "BB")}
+    logq = lambda to, frm: sum(-0.5 * np.sum((to[p] - frm[p] - tau * sig[p] * grad(frm)[p]) ** 2 / (2 * tau * sig[p])) for p in ("EE", "BB"))
+    logd = lambda s: sum(-0.5 * np.sum((s[p] - mean[p]) ** 2 / sig[p]) for p in ("EE", "BB"))
+    g = grad(s_old)
+    s_new = {"EE": s_old["EE"] + tau * sig["EE"] * g["EE"] + np.sqrt(2 * tau * sig["EE"]) * xi_E,
+             "BB": s_old["BB"] + tau * sig["BB"] * g["BB"] + np.sqrt(2 * tau * sig["BB"]) * xi_B}
+    return s_new, logd(s_new) + logq(s_old, s_new) - (logd(s_old) + logq(s_new, s_old))
+
+
 # ---------------------------------------------------------------- C_l conditional (CenteredGibbs.py:54-79)
 def cls_alpha_beta(alms_real, bins, lmax):
     observed = sht.alm2cl(real_to_complex(alms_real), lmax)
