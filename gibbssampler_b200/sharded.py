@@ -219,8 +219,16 @@ def run_local_group(plans, fn):
         except BaseException as e:  # noqa: BLE001 -- reported below; a dead rank would deadlock the others' barriers
             err[i] = e
             import os
+            import sys
             import traceback
-            traceback.print_exc()
+            msg = "run_local_group: rank %d failed\n%s" % (i, traceback.format_exc())
+            try:   # pytest captures fd 2 and os._exit drops the capture: keep a copy where it survives
+                with open(os.environ.get("GS_CRASH_LOG", "/tmp/gs_local_group_crash.log"), "a") as f:
+                    f.write(msg)
+            except OSError:
+                pass
+            sys.stderr.write(msg)
+            sys.stderr.flush()
             os._exit(86)
     torch.cuda.synchronize()
     ts = [threading.Thread(target=work, args=(i,)) for i in range(len(plans))]

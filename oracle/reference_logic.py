@@ -267,7 +267,8 @@ def nc_loglik(binned, bins, s_nc, prob, l_cut=0):
     """NonCenteredGibbs.py:333-355.  l_cut > 0 (partially non-centred parametrisation, see PNCPPol below): the
     multipoles l < l_cut of `s_nc` are the centred coefficients and are synthesised without the sqrt(C_l) factor."""
     dlE, dlB = unfold_bins(binned["EE"], bins["EE"]), unfold_bins(binned["BB"], bins["BB"])
-    vE, vB = prob.var_cl(dlE), prob.var_cl(dlB)
+    var_cl = getattr(prob, "var_cl", generate_var_cl)
+    vE, vB = var_cl(dlE), var_cl(dlB)
     if prob.kind == "fast":   # the filter b_l sqrt(C_l) is a per-l factor: hand it to the fused synthesis
         lm = prob.lmax
         fE, fB = np.sqrt(vE[:lm + 1]), np.sqrt(vB[:lm + 1])      # entries 0..lmax of the real layout are the m = 0 column

@@ -28,6 +28,7 @@ def _lib(kind="ld"):
         lib.orc_alm2map.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp]
         lib.orc_map2alm.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, C.c_double]
         lib.orc_lambda.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, dp]
+        lib.orc_lambda_zs.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, dp]
         lib.orc_ring_info.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.POINTER(C.c_int), C.POINTER(C.c_int64)]
         _LIBS[kind] = lib
     return _LIBS[kind]
@@ -92,6 +93,14 @@ def pix_angles(nside):
 def lam(lmax, m, mp, z):
     out = np.zeros(lmax + 1)
     if _lib().orc_lambda(lmax, m, mp, float(z), _p(out)):
+        raise ValueError("bad args")
+    return out
+
+
+def lam_zs(lmax, m, mp, z, sth):
+    """lambda^{mp}_{lm} from cos(theta) AND sin(theta) as doubles (libsharp's inputs; see orc_lambda_zs)."""
+    out = np.zeros(lmax + 1)
+    if _lib().orc_lambda_zs(lmax, m, mp, float(z), float(sth), _p(out)):
         raise ValueError("bad args")
     return out
 

@@ -209,6 +209,30 @@ int orc_lambda(int lmax, int m, int mp, double z_in, double *out)
     return 0;
 }
 
+/* Same with cos(theta) and sin(theta) both given as doubles -- what libsharp's Legendre loop sees (cth, sth of a double
+ * theta).  Next to the poles of a large map the rounding of cos(theta) to a double alone moves lambda_lm by
+ * ~ l ulp(1) / sin(theta) (5e-10 at ring 1 of nside 2048, l = 4096): a check of an FP64 transform at such rings has to feed
+ * the same rounded cos(theta), with sin(theta) from 1 - |z| (not from the rounded z). */
+int orc_lambda_zs(int lmax, int m, int mp, double z_in, double sth_in, double *out)
+{
+    if (m < 0 || m > lmax || (mp != 0 && mp != 2 && mp != -2)) return -1;
+    long double z = z_in, sth = sth_in;
+    int amp = mp < 0 ? -mp : mp, l0 = m > amp ? m : amp;
+    for (int l = 0; l <= lmax; ++l) out[l] = 0.0;
+    if (l0 > lmax) return 0;
+    rec_t *rc = (rec_t *)malloc(sizeof(rec_t) * (size_t)(lmax - l0 + 1));
+    rec_coef(lmax, m, mp, rc);
+    int mfe; long double mf = mfac_scaled(m, &mfe);
+    real mant; int ex; lam_seed(m, mp, z, sth, mf, mfe, &mant, &ex);
+    lam_state s; lam_init(&s, mant, ex);
+    for (int l = l0; l <= lmax; ++l) {
+        out[l] = (s.scale == 0) ? (double)s.cur : 0.0;
+        if (l < lmax) lam_step(&s, &rc[l - l0], (real)z);
+    }
+    free(rc);
+    return 0;
+}
+
 /* ---------------------------------------------------- mixed-radix complex FFT */
 /* out[k] = sum_j in[j*stride] exp(sign*2*pi*i*j*k/n); recursive decimation in time on the
  * smallest prime factor, direct DFT for prime lengths. tw = exp(sign*2*pi*i*t/N0), t<N0. */

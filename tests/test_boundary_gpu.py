@@ -15,7 +15,7 @@ from oracle import reference_logic as R
 from oracle import sht as O
 
 pytestmark = pytest.mark.gpu
-G = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_nside4.npz"))
+G = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_nside4.npz")))   # materialised: NpzFile is lazy and not thread-safe
 NSIDE, LMAX = 4, 8
 NPIX, NRE = 12 * NSIDE ** 2, (LMAX + 1) ** 2
 

@@ -184,3 +184,24 @@ def test_pixel_centres_known_answers():
         first = ph[ncap::4 * nside][:2 * nside + 1]           # first pixel of every belt ring
         want = np.where(np.arange(2 * nside + 1) % 2 == 0, np.pi / (4 * nside), 0.0)
         assert np.allclose(first, want, atol=1e-15)
+
+
+@pytest.mark.parametrize("nside,lmax", [(8, 16), (16, 40)])
+def test_sampled_direct_sum_helper_matches_full_transforms(nside, lmax):
+    """tests/sampled_sht.py (the reference of the nside 1024 / 2048 GPU checks) against the oracle's own full transforms."""
+    from tests import sampled_sht as S
+    rng = np.random.default_rng(77 + nside)
+    ms = S.sampled_m(lmax)
+    e, b, t, coef = S.sampled_alm(lmax, ms, rng)
+    q, u = sht.alm2map_spin2(e, b, nside, lmax)
+    tm = sht.alm2map(t, nside, lmax)
+    rings = list(range(1, 4 * nside))
+    assert S.synthesis_error(nside, lmax, ms, coef, rings, q, u, tm, rng) < 1e-13
+    # a deliberately wrong map must be seen
+    assert S.synthesis_error(nside, lmax, ms, coef, rings, q, -u, tm, rng) > 1e-3
+    trings = [1, 2, nside - 1, nside, 2 * nside, 3 * nside + 1, 4 * nside - 1]
+    fq, fu, geo = S.ring_supported_maps(nside, trings, rng)
+    ge, gb = sht.map2alm_spin2(fq, fu, nside, lmax, adjoint=True)
+    gt = sht.map2alm(fq, nside, lmax, adjoint=True)
+    assert S.analysis_error(nside, lmax, ms, trings, fq, fu, geo, ge, gb, gt) < 1e-13
+    assert S.analysis_error(nside, lmax, ms, trings, fq, fu, geo, gb, ge, gt) > 1e-3

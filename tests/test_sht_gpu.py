@@ -159,6 +159,63 @@ def test_large_size_vs_double_oracle():
     assert relerr(ge.cpu().numpy(), re_) < RTOL and relerr(gb.cpu().numpy(), rb_) < RTOL
 
 
+def test_bench_size_vs_double_oracle():
+    """BASELINE config #3 size (nside 512 / lmax 1024): spin-0 and spin-2 synthesis and analysis against the FP64 OpenMP build of
+    the oracle on the same seeded inputs (adjointness alone is blind to errors shared by A and A^T)."""
+    from gibbssampler_b200.sht import Plan
+    nside, lmax = 512, 1024
+    plan = Plan.get(nside, lmax)
+    rng = np.random.default_rng(512)
+    e, b = rand_alm(lmax, rng, 2), rand_alm(lmax, rng, 2)
+    rq, ru = O.alm2map_spin2(e, b, nside, lmax, kind="f64")
+    q, u = plan.alm2map_spin2(dev(e), dev(b))
+    assert relerr(q.cpu().numpy(), rq) < RTOL and relerr(u.cpu().numpy(), ru) < RTOL
+    q2, u2 = plan.alm2map_spin2(dev(to_real(e, lmax)), dev(to_real(b, lmax)))
+    assert relerr(q2.cpu().numpy(), rq) < RTOL and relerr(u2.cpu().numpy(), ru) < RTOL
+    fq, fu = rng.standard_normal(12 * nside ** 2), rng.standard_normal(12 * nside ** 2)
+    re_, rb_ = O.map2alm_spin2(fq, fu, nside, lmax, kind="f64")
+    ge, gb = plan.map2alm_spin2(dev(fq), dev(fu))
+    assert relerr(ge.cpu().numpy(), re_) < RTOL and relerr(gb.cpu().numpy(), rb_) < RTOL
+    ae, ab = O.map2alm_spin2(fq, fu, nside, lmax, adjoint=True, kind="f64")
+    ge, gb = plan.map2alm_spin2(dev(fq), dev(fu), adjoint=True, real_layout=True)
+    assert relerr(ge.cpu().numpy(), to_real(ae, lmax)) < RTOL and relerr(gb.cpu().numpy(), to_real(ab, lmax)) < RTOL
+    a = rand_alm(lmax, rng)
+    ref = O.alm2map(a, nside, lmax, kind="f64")
+    assert relerr(plan.alm2map(dev(a)).cpu().numpy(), ref) < RTOL
+    ra = O.map2alm(fq, nside, lmax, kind="f64")
+    assert relerr(plan.map2alm(dev(fq)).cpu().numpy(), ra) < RTOL
+
+
+@pytest.mark.parametrize("nside,lmax", [(1024, 2048), (2048, 4096)])
+def test_sampled_legendre_sums_at_large_sizes(nside, lmax):
+    """nside 1024 / 2048 (BASELINE config #4), where a full CPU transform is too slow for the suite: alm that live on a sampled
+    set of m (0, 1, 2, 3, 17, ~lmax/4, lmax/2, 3 lmax/4, lmax - 96, lmax - 1, lmax) are synthesised by the GPU, and pixels of
+    ~2400 rings (the first and last 400 rings one by one, the cap/belt boundaries, the equator, every 5th ring in between) are
+    compared with direct sums over the oracle's long-double lambda_lm (tests/sampled_sht.py; the helper itself is pinned to the
+    oracle's full transforms on the CPU, tests/test_oracle_sht.py).  The rings around every sampled m's pruning boundary
+    m = m_lim(theta) are in the set and the deepest range-extension ladder (m = lmax next to the poles) is exercised.
+    Analysis (A^T): maps supported on a few rings, every l of the sampled m."""
+    from gibbssampler_b200.sht import Plan
+    from tests import sampled_sht as S
+    plan = Plan(nside, lmax)
+    rng = np.random.default_rng(4096 + nside)
+    ms = S.sampled_m(lmax)
+    nring = 4 * nside - 1
+    rings = sorted(set(range(1, 401)) | set(range(nring - 399, nring + 1)) | set(range(1, nring + 1, 5))
+                   | set(range(nside - 3, nside + 4)) | set(range(2 * nside - 2, 2 * nside + 3)) | set(range(3 * nside - 3, 3 * nside + 4)))
+    e, b, t, coef = S.sampled_alm(lmax, ms, rng)
+    q, u = (x.cpu().numpy() for x in plan.alm2map_spin2(dev(e), dev(b)))
+    tm = plan.alm2map(dev(t)).cpu().numpy()
+    worst = S.synthesis_error(nside, lmax, ms, coef, rings, q, u, tm, rng)
+    assert worst < RTOL, worst
+    trings = [1, 2, 37, nside - 1, nside, 2 * nside, 3 * nside + 1, nring - 5, nring]
+    fq, fu, geo = S.ring_supported_maps(nside, trings, rng)
+    ge, gb = (x.cpu().numpy() for x in plan.map2alm_spin2(dev(fq), dev(fu), adjoint=True))
+    gt = plan.map2alm(dev(fq), adjoint=True).cpu().numpy()
+    worst = S.analysis_error(nside, lmax, ms, trings, fq, fu, geo, ge, gb, gt)
+    assert worst < RTOL, worst
+
+
 @pytest.mark.parametrize("nside,lmax,mcap", [(16, 32, 32), (32, 64, 64), (64, 160, 128), (128, 256, 256)])
 def test_split_ring_path_matches_direct_path(nside, lmax, mcap, monkeypatch):
     """Rings too long for one CTA (nside >= 2048 in production) are transformed as 4 sub-transforms of length
