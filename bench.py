@@ -501,6 +501,7 @@ def main():
     ap.add_argument("--lmax", type=int, default=1024)
     ap.add_argument("--pcg-iters", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-chain-batch", action="store_true", help="skip the secondary measurement with two chains per GPU")
     ap.add_argument("--sampler", default="pncp", choices=["pncp", "centered"],
                     help="pncp (default): BASELINE config #3, partially non-centred polarised masked-sky sampler = PCG constrained "
                          "realization + low-l inverse-gamma draw + high-l blocked Metropolis sweep; centered: CenteredGibbs "
@@ -653,6 +654,51 @@ def main():
     value = whole_job_value(world, args.steps, ms_total)
     n_pcg = int(round(float(np.mean(its_timed)))) if its_timed else 0
 
+    # ---- secondary measurement: TWO chains per GPU whose PCG mat-vecs run as chain batches (one Legendre recurrence for both
+    # right-hand sides: gs_cr_pcg_pol_batch; BASELINE config #5 / north_star (a) "batched over chains").  `value` above stays the
+    # one-chain-per-GPU configuration of BASELINE config #3; this is reported next to it.
+    chain_batch = None
+    if not args.no_chain_batch:
+        from gibbssampler_b200.CenteredGibbs import sample_mask_batch
+        if pncp:
+            cr2 = PNCPConstrainedRealization({"Q": dQ, "U": dU}, noise_pol * 1e4, noise_pol, bl_map, lmax, npix, fwhm, mask=mask,
+                                             rng="philox", seed=chain_seed(rank) + 500, ula=False, l_cut=L_CUT)
+            cls2 = PNCPClsSampler({"Q": dQ, "U": dU}, lmax, nside, bins, bl_map, noise_pol * 1e4, noise_pol, blocks, pv, L_CUT, n_iter=1,
+                                  mask=mask, rng=cr2.rng)
+        else:
+            cr2 = PolarizedCenteredConstrainedRealization({"Q": dQ, "U": dU}, noise_pol * 1e4, noise_pol, bl_map, lmax, npix, fwhm,
+                                                          mask=mask, rng="philox", seed=chain_seed(rank) + 500)
+            cls2 = PolarizedCenteredClsSampler({"Q": dQ, "U": dU}, lmax, nside, bins, bl_map, noise_pol, mask=mask, rng=cr2.rng)
+        cr2.inv_noise_pol = cr.inv_noise_pol
+        pair = [(cr, cls), (cr2, cls2)]
+        pstate = [state["binned"], binned_init()]
+        pair_its = []
+
+        def step_pair():
+            outs = sample_mask_batch([c for c, _ in pair], [unfold(b) for b in pstate])
+            pair_its.append([c.last_pcg_iterations for c, _ in pair])
+            for k, ((c, s), (sky, _)) in enumerate(zip(pair, outs)):
+                if not pncp:
+                    pstate[k] = s.sample(sky)
+                    continue
+                b = s.sample_low_l(sky, pstate[k])
+                mixed = c.to_mixed(sky, unfold(b))
+                pstate[k], _ = s.sample_high_l(mixed, b)
+
+        ms_pair = timed(step_pair, max(1, args.warmup - 1), args.steps)
+        xx = data_rng.normal(4 * nre).reshape(2, 2, nre)
+        yy = torch.empty_like(xx)
+        ms3 = (C.c_float * 3)()
+        for nrep in (3, 20):
+            _lib.check(L.gs_profile_matvec_batch(plan._h, 2, _dev.ptr(xx[0, 0]), _dev.ptr(xx[0, 1]), 2 * nre, _dev.ptr(cr.bl_gauss_d),
+                                                 _dev.ptr(cr.inv_noise_pol), _dev.ptr(yy[0, 0]), _dev.ptr(yy[0, 1]), nrep, ms3, _dev.stream()))
+        chain_batch = {"chains_per_gpu": 2, "value": whole_job_value(world, 2 * args.steps, ms_pair), "unit": "it/s",
+                       "ms_per_step_of_two_chains": ms_pair / args.steps, "gpu_launches": counted["launches"],
+                       "pcg_iterations_per_step": pair_its[max(1, args.warmup - 1):],
+                       "pcg_matvec_two_chains_ms": {"leg_synth": ms3[0], "ring_apply_fused": ms3[1], "leg_anal": ms3[2], "total": sum(ms3)},
+                       "note": "two independent chains per GPU; their PCG solves share the Legendre recurrences (two right-hand sides per "
+                               "launch, 4 + 8 K DFMA per ring pair and multipole instead of 12 K); C_l sampling per chain"}
+
     # ---- per-kernel timing of one PCG mat-vec (CUDA events on the launching stream) + roofline
     x_e, x_b = data_rng.normal(nre), data_rng.normal(nre)
     y_e, y_b = torch.empty_like(x_e), torch.empty_like(x_b)
@@ -747,7 +793,7 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args), "pcg_iterations_mean": n_pcg,
             "e2e": {"value": e2e_val, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "chain_batch": chain_batch,
             "sht_pairs_per_s": world * 1e3 / pair_ms_max, "sht_pair_ms": pair_ms_max, "stage_ms": stage_ms,
             "pcg_matvec": {"ms": sum(matvec_ms.values()), "stage_ms": matvec_ms, "active_ring_pairs": act.value, "ring_pairs": tot.value,
                            "note": "mat-vec of the PCG: ring pairs wholly inside the mask (N^-1 = 0) are skipped, exact"},

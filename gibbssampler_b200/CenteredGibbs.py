@@ -282,3 +282,43 @@ class CenteredGibbs(GibbsSampler):
         self.constrained_sampler = PolarizedCenteredConstrainedRealization(
             pix_map, noise_temp, noise_pol, self.bl_map, lmax, Npix, beam, mask_path=mask_path, gibbs_cr=gibbs_cr,
             overrelaxation=overrelaxation, ula=ula, mask=mask, rng=cr_rng, plan=plan)
+
+
+def sample_mask_batch(crs, dls_list, xis=None):
+    """sample_mask (CenteredGibbs.py:448-491) of TWO independent chains on the same data in one batched solve: every chain
+    draws its own right-hand side from its own random stream (as two processes of the reference would), the two PCG solves run
+    side by side with chain-batched mat-vecs that share the Legendre recurrences (gs_cr_pcg_pol_batch).  `crs`: the chains'
+    PolarizedCenteredConstrainedRealization objects (same plan, data, mask and noise); returns [(alms dict, 1), ...]."""
+    assert len(crs) == len(dls_list) and len(crs) in (1, 2)
+    if len(crs) == 1:
+        return [crs[0].sample_mask(dls_list[0], None if xis is None else xis[0])]
+    a, b = crs
+    if a.plan is not b.plan or a.plan.world > 1:
+        raise _lib.GibbsB200Error("sample_mask_batch needs two chains on the same unsharded plan")
+    if a.inv_noise_pol.data_ptr() != b.inv_noise_pol.data_ptr():
+        if not torch.equal(a.inv_noise_pol, b.inv_noise_pol):
+            raise _lib.GibbsB200Error("sample_mask_batch: the chains of a batch share the noise / mask (N^-1)")
+        b.inv_noise_pol = a.inv_noise_pol   # checked once: later calls compare pointers only
+    n, lmax = a.dimension_alm, a.lmax
+    rhs = torch.empty((2, 2, n), dtype=torch.float64, device=a.dev)      # [chain][E, B][n]
+    dl = torch.empty((2, 2, lmax + 1), dtype=torch.float64, device=a.dev)  # [E, B][chain][L + 1]
+    for k, (cr, dls) in enumerate(zip(crs, dls_list)):
+        re_, rb_ = cr.build_rhs(dls, None if xis is None else xis[k])
+        cr.last_rhs = (re_, rb_)
+        rhs[k, 0].copy_(re_)
+        rhs[k, 1].copy_(rb_)
+        dle, dlb = cr._dls(dls)
+        dl[0, k].copy_(dle)
+        dl[1, k].copy_(dlb)
+    x = torch.empty_like(rhs)
+    nit, res = (C.c_int * 2)(), (C.c_double * 2)()
+    rc = _lib.lib().gs_cr_pcg_pol_batch(a.plan._h, 2, ptr(dl[0]), ptr(dl[1]), ptr(a.bl_gauss_d), ptr(a.inv_noise_pol),
+                                        a.ninv_sum_over_4pi, ptr(rhs[0, 0]), ptr(rhs[0, 1]), ptr(x[0, 0]), ptr(x[0, 1]), 2 * n,
+                                        a.pcg_accuracy, a.pcg_itermax, a.pcg_check_every, nit, res, stream())
+    if rc not in (0, -3):
+        check(rc)
+    out = []
+    for k, (cr, dls) in enumerate(zip(crs, dls_list)):
+        cr.last_pcg_iterations, cr.last_pcg_residual = nit[k], res[k]
+        out.append((cr._ret({"EE": x[k, 0], "BB": x[k, 1]}, dls["EE"]), 1))
+    return out

@@ -26,6 +26,7 @@ SIGNATURES = {
     "gs_version": (_i, []),
     "gs_plan_create": (_i, [C.POINTER(_vp), _i, _i, _i]),
     "gs_plan_destroy": (_i, [_vp]),
+    "gs_plan_reserve_chains": (_i, [_vp, _i]),
     "gs_plan_nside": (_i, [_vp]),
     "gs_plan_lmax": (_i, [_vp]),
     "gs_plan_npix": (_i64, [_vp]),
@@ -35,6 +36,8 @@ SIGNATURES = {
     "gs_alm2map_spin2": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "gs_map2alm_spin0": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     "gs_map2alm_spin2": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp]),
+    "gs_alm2map_batch": (_i, [_vp, _i, _i, _vp, _vp, _i64, _i, _vp, _vp, _vp, _i64, _vp]),
+    "gs_map2alm_batch": (_i, [_vp, _i, _i, _vp, _vp, _i64, _vp, _i, _vp, _vp, _vp, _i64, _i, _vp]),
     "gs_real_to_complex": (_i, [_vp, _vp, _i, _vp]),
     "gs_complex_to_real": (_i, [_vp, _vp, _i, _vp]),
     "gs_expand_per_l": (_i, [_vp, _i, _i, _vp, _vp]),
@@ -45,6 +48,8 @@ SIGNATURES = {
     "gs_cr_rhs_pol": (_i, [_vp] * 14 + [_i, _vp, _vp, _vp]),
     "gs_cr_pcg_pol": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp, _i, _d, _i, _i,
                            C.POINTER(_i), C.POINTER(_d), _vp]),
+    "gs_cr_pcg_pol_batch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp, _i64, _d, _i, _i,
+                                 C.POINTER(_i), C.POINTER(_d), _vp]),
     "gs_cr_apply_q_pol": (_i, [_vp] * 10),
     "gs_cr_rhs_tt": (_i, [_vp] * 9 + [_i, _vp, _vp]),
     "gs_cr_pcg_tt": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _vp, _i, _d, _i, _i, C.POINTER(_i), C.POINTER(_d), _vp]),
@@ -96,6 +101,7 @@ SIGNATURES = {
     "gs_shard_allreduce_sum": (_i, [_vp, _vp, _i, _vp]),
     "gs_launch_count": (C.c_longlong, []),
     "gs_profile_matvec": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(C.c_float), _vp]),
+    "gs_profile_matvec_batch": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, C.POINTER(C.c_float), _vp]),
     "gs_measure_fp64_peak": (_i, [C.POINTER(_d), _vp]),
     "gs_profile_pcg_vectors": (_i, [_vp, _i, _i, C.POINTER(C.c_float), _vp]),
     "gs_set_ring_fused": (_i, [_i]),

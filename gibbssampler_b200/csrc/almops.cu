@@ -280,3 +280,52 @@ extern "C" int gs_map2alm_spin2(gs_plan* p, const double* mapQ, const double* ma
     GS_REQUIRE(mapQ && mapU && almE && almB && iter >= 0 && (layout == GS_ALM_COMPLEX || layout == GS_ALM_REAL), "bad arguments");
     return map2alm_impl(p, 2, mapQ, mapU, pixw, iter, adjoint, fl, almE, almB, layout, STREAM(stream));
 }
+
+// ---- chain-batched SHTs (BASELINE config #5: "alm2map + map2alm ... batched over chains"; north_star (a))
+// n_chain right-hand sides, chain c at alm + c alm_stride / map + c map_stride (strides in doubles), are transformed two per
+// launch: the two chains of a pair share ONE Legendre recurrence per (ring pair, m) thread (4 + 8 K DFMA per ring pair and l
+// instead of 12 K, K = 2); an odd last chain takes the single-chain kernels.  Same results as n_chain separate calls.
+extern "C" int gs_alm2map_batch(gs_plan* p, int spin, int n_chain, const double* almE, const double* almB, int64_t alm_stride,
+                                int layout, const double* fl, double* mapQ, double* mapU, int64_t map_stride, void* stream)
+{
+    int rc = check_plan(p);
+    if (rc) return rc;
+    GS_REQUIRE((spin == 0 || spin == 2) && n_chain >= 1 && almE && mapQ && (spin == 0 || (almB && mapU)) &&
+               (layout == GS_ALM_COMPLEX || layout == GS_ALM_REAL), "bad arguments");
+    if (n_chain > 1 && (rc = gs_plan_reserve_chains(p, 2))) return rc;
+    cudaStream_t st = STREAM(stream);
+    for (int c = 0; c < n_chain; c += 2) {
+        const int nc = n_chain - c >= 2 ? 2 : 1;
+        const double* e = almE + c * alm_stride;
+        const double* b = spin ? almB + c * alm_stride : nullptr;
+        double* q = mapQ + c * map_stride;
+        double* u = spin ? mapU + c * map_stride : nullptr;
+        if ((rc = gs_leg_synth(p, spin, e, b, layout, fl, st, nullptr, nullptr, nc, alm_stride))) return rc;
+        if ((rc = gs_ring_synth(p, spin, q, u, st, nullptr, nc, map_stride))) return rc;
+    }
+    return GS_OK;
+}
+
+// map2alm(iter = 0) (adjoint = 0: weight 4 pi / Npix, adjoint = 1: A^T) of n_chain map sets; pixw (optional) multiplies the pixels
+extern "C" int gs_map2alm_batch(gs_plan* p, int spin, int n_chain, const double* mapQ, const double* mapU, int64_t map_stride,
+                                const double* pixw, int adjoint, const double* fl, double* almE, double* almB, int64_t alm_stride,
+                                int layout, void* stream)
+{
+    int rc = check_plan(p);
+    if (rc) return rc;
+    GS_REQUIRE((spin == 0 || spin == 2) && n_chain >= 1 && almE && mapQ && (spin == 0 || (almB && mapU)) &&
+               (layout == GS_ALM_COMPLEX || layout == GS_ALM_REAL), "bad arguments");
+    if (n_chain > 1 && (rc = gs_plan_reserve_chains(p, 2))) return rc;
+    cudaStream_t st = STREAM(stream);
+    const double scale = adjoint ? 1.0 : 4.0 * 3.14159265358979323846 / (double)p->d.npix;
+    for (int c = 0; c < n_chain; c += 2) {
+        const int nc = n_chain - c >= 2 ? 2 : 1;
+        const double* q = mapQ + c * map_stride;
+        const double* u = spin ? mapU + c * map_stride : nullptr;
+        double* e = almE + c * alm_stride;
+        double* b = spin ? almB + c * alm_stride : nullptr;
+        if ((rc = gs_ring_anal(p, spin, q, u, pixw, st, nullptr, nc, map_stride))) return rc;
+        if ((rc = gs_leg_anal(p, spin, e, b, layout, fl, scale, 0, st, nullptr, nullptr, nc, alm_stride))) return rc;
+    }
+    return GS_OK;
+}

@@ -163,6 +163,7 @@ struct gs_plan {
     double2* Fm;        // [2][nring][lmax+1] ring spectra
     double* partial;    // analysis partial sums [nchunk][nalm][4]
     int anal_chunks;
+    int chain_cap;      // right-hand sides the spectra / partial-sum buffers hold (1; gs_plan_reserve_chains raises it)
     size_t ring_smem;   // dynamic shared memory of the ring-FFT kernels
     // scratch maps / alms for iter>0 analysis and solvers
     double* mapQ_tmp;
@@ -172,6 +173,8 @@ struct gs_plan {
     double* almE_tmp2;
     double* almB_tmp2;
     void* pcg_ws;       // gs_pcg_ws* (solver.cu): PCG vectors / state of this plan, allocated on the first solve
+    void* pcg_ws_batch; // gs_pcg_ws[2]: workspaces of a two-chain batch (gs_cr_pcg_pol_batch), allocated on first use
+    int* pcg_alldone;   // device flag: both chains of the batch have converged
 };
 
 extern int g_gs_ring_skip;        // 1: rings whose pixel weights vanish identically are left out (PCG mat-vec, Metropolis sweep)
@@ -194,18 +197,25 @@ struct FinishFuse {
 
 // legendre.cu
 // `skip` (nullable device int): when *skip != 0 the kernels return immediately (device-side early exit)
+// nc = 2: chain batch (two right-hand sides share one recurrence; chain c at alm + c alm_stride, spectra at p->Fm + c gs_fm_stride(p));
+// needs gs_plan_reserve_chains(p, 2) and an unsharded plan
 int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, int layout, const double* fl,
-                 cudaStream_t st, const int* skip = nullptr, const double* flB = nullptr);
+                 cudaStream_t st, const int* skip = nullptr, const double* flB = nullptr, int nc = 1, int64_t alm_stride = 0);
 int gs_leg_anal(gs_plan* p, int spin, double* almE, double* almB, int layout, const double* fl, double scale,
-                int accumulate, cudaStream_t st, const int* skip = nullptr, const FinishFuse* fuse = nullptr);
+                int accumulate, cudaStream_t st, const int* skip = nullptr, const FinishFuse* fuse = nullptr, int nc = 1,
+                int64_t alm_stride = 0);
+int64_t gs_fm_stride(const gs_plan* p);            // double2 entries of one chain's ring spectra
+int64_t gs_part_stride(const gs_plan* p, int nc);  // doubles of one chain's analysis partial sums
 int gs_active_rings_build(gs_plan* p, const double* pixw, cudaStream_t st);
 int gs_leg_build_sinpow(gs_plan* p);
 // ringfft.cu
 int gs_ring_setup(gs_plan* p);
-int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st, const int* skip = nullptr);
+// nc > 1 (chain batch): chain c uses the spectra p->Fm + c gs_fm_stride(p) and the maps + c map_stride
+int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st, const int* skip = nullptr, int nc = 1,
+                  int64_t map_stride = 0);
 int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, const double* pixw, cudaStream_t st,
-                 const int* skip = nullptr);
-int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, const int* skip = nullptr);
+                 const int* skip = nullptr, int nc = 1, int64_t map_stride = 0);
+int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, const int* skip = nullptr, int nc = 1);
 int gs_ring_synth_batch(gs_plan* p, const double2* F, int64_t f_stride, const int* mmax, double* mapQ, double* mapU,
                         int64_t map_stride, int nb, cudaStream_t st, const unsigned char* ract = nullptr);
 // legendre.cu: block-batched spin-2 synthesis for the Metropolis-within-Gibbs sweep (see leg_synth_blocks_kernel)

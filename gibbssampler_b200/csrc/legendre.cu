@@ -52,6 +52,11 @@
 #endif               // at a time, to a sum through shared memory (needs LEG_FOLD2)
 #define FOLD3_NB 8
 #define FULL 0xffffffffu
+#ifdef LEG_XNOBAR      // EXPERIMENT ONLY (wrong results): tile-loop barriers of the synthesis / analysis kernels become warp barriers,
+#define TILE_SYNC() __syncwarp()   // to measure what the CTA-wide barriers cost
+#else
+#define TILE_SYNC() __syncthreads()
+#endif
 constexpr int kUnrollA = LEG_UA;
 
 __device__ __forceinline__ double pow2i(int e) { return __hiloint2double((e + 1023) << 20, 0); }
@@ -192,12 +197,12 @@ __device__ __forceinline__ void rescale_check(RingState<SPIN>& s)
 // Each thread fetches the (pre-scaled) a_lm pair and the recurrence coefficients of ONE l of the tile into
 // registers (LEG_TL == LEG_NT); the values are stored to the other half of a double-buffered shared-memory
 // tile after the current tile has been consumed, so the global-memory latency hides behind the recurrence.
-template <int SPIN>
+template <int SPIN, bool WITH_R = true>
 __device__ __forceinline__ void fetch_alm(const PlanDev& P, int m, int l, int64_t base, int64_t roff, const double* almE, const double* almB,
                                           int layout, const double* fl, const double* flB, double2& e, double2& b, double2& r)
 {
     const int L = P.lmax;
-    e = make_double2(0.0, 0.0); b = e; r = e;
+    e = make_double2(0.0, 0.0); b = e; if (WITH_R) r = e;
     if (l <= L) {
         const int64_t id = base + l;
         double pre = SPIN ? -0.5 * P.alpha2[id] : P.alpha0[id];
@@ -223,8 +228,21 @@ __device__ __forceinline__ void fetch_alm(const PlanDev& P, int m, int l, int64_
             // -> c1 = E'r - B'i, c2 = E'r + B'i, c3 = E'i + B'r, c4 = E'i - B'r
             const double2 c12 = make_double2(e.x - b.y, e.x + b.y), c34 = make_double2(e.y + b.x, e.y - b.x);
             e = c12; b = c34;
-            r = P.rec2[id];
-        } else r.x = P.rec0[id];
+            if (WITH_R) r = P.rec2[id];
+        } else if (WITH_R) r.x = P.rec0[id];
+    }
+}
+// the same for the NC right-hand sides of a chain batch (chain c at almE/almB + c alm_stride): one set of recurrence coefficients
+template <int SPIN, int NC>
+__device__ __forceinline__ void fetch_alm_nc(const PlanDev& P, int m, int l, int64_t base, int64_t roff, const double* almE, const double* almB,
+                                             int64_t alm_stride, int layout, const double* fl, const double* flB, double2 (&e)[NC], double2 (&b)[NC],
+                                             double2& r)
+{
+    fetch_alm<SPIN, true>(P, m, l, base, roff, almE, almB, layout, fl, flB, e[0], b[0], r);
+#pragma unroll
+    for (int c = 1; c < NC; ++c) {
+        double2 dummy;
+        fetch_alm<SPIN, false>(P, m, l, base, roff, almE + c * alm_stride, SPIN ? almB + c * alm_stride : almB, layout, fl, flB, e[c], b[c], dummy);
     }
 }
 
@@ -276,12 +294,14 @@ __device__ __forceinline__ void synth_acc(SynthAcc<SPIN>& A, double pc, double m
     }
 }
 
-template <int SPIN, int R, bool SH>
+// NC > 1: chain batch.  NC right-hand sides (chain c: alm at + c alm_stride, spectra at + c fm_stride) share ONE recurrence per
+// (ring pair, m) thread: 4 + 8 NC DFMA per ring pair and l instead of 12 NC (BASELINE config #5, north_star (a)).
+template <int SPIN, int R, bool SH, int NC>
 __global__ void LEG_SYNTH_BOUNDS
 leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __restrict__ almB, int layout,
                  const double* __restrict__ fl, const double* __restrict__ flB, double2* __restrict__ Fm,
                  const int* __restrict__ skip, const int* __restrict__ plist, const int* __restrict__ pcount,
-                 const int* __restrict__ slot0)
+                 const int* __restrict__ slot0, int64_t alm_stride, int64_t fm_stride)
 {
     if (skip && *skip) return;
     const int L = P.lmax, mk = blockIdx.y, m = SH ? P.sh.mlist[mk] : mk, tid = threadIdx.x;
@@ -291,14 +311,14 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
     // the blocks beyond the last slot have nothing to do.
     const int s0 = slot0[m], nact = (plist ? *pcount : P.npair) - s0;
     if ((int)blockIdx.x * (LEG_NT * R) >= nact) return;
-    __shared__ double2 sEb[2][LEG_TLS], sBb[2][SPIN ? LEG_TLS : 1], sRb[2][LEG_TLS];
+    __shared__ double2 sEb[2][NC][LEG_TLS], sBb[2][SPIN ? NC : 1][SPIN ? LEG_TLS : 1], sRb[2][LEG_TLS];
     const int l0 = m > SPIN ? m : SPIN;
     const int64_t base = (int64_t)m * (2 * L + 1 - m) / 2;
     const int64_t roff = real_off<SH>(P, m, mk, base);
     const int chunk = blockIdx.x * (LEG_NT * R);
 
     RingState<SPIN> st[R];
-    SynthAcc<SPIN> acc[R];
+    SynthAcc<SPIN> acc[R][NC];
     int pj[R];
     bool any_act = false;
 #pragma unroll
@@ -307,8 +327,11 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
         const int p = k < nact ? (plist ? plist[s0 + k] : s0 + k) : -1;
         pj[j] = p;
         st[j].x = 0.0; st[j].pc = st[j].pp = st[j].mc = st[j].mp = 0.0; st[j].sc = 0;
-        acc[j].sqr = acc[j].sqi = acc[j].aqr = acc[j].aqi = 0.0;
-        acc[j].sur = acc[j].sui = acc[j].aur = acc[j].aui = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            acc[j][c].sqr = acc[j][c].sqi = acc[j][c].aqr = acc[j][c].aqi = 0.0;
+            acc[j][c].sur = acc[j][c].sui = acc[j][c].aur = acc[j][c].aui = 0.0;
+        }
         if (p >= 0 && m <= (SPIN ? P.mlim2[p] : P.mlim0[p])) {
             st[j].x = P.cth[p];
             seed_ring<SPIN>(P, p, m, st[j].pc, st[j].mc, st[j].sc);
@@ -319,22 +342,24 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
 
 #pragma unroll
     for (int u = 0; u < LEG_SU; ++u) {
-        double2 e, b, r;
-        fetch_alm<SPIN>(P, m, l0 + u * LEG_NT + tid, base, roff, almE, almB, layout, fl, flB, e, b, r);
-        sEb[0][u * LEG_NT + tid] = e; if (SPIN) sBb[0][u * LEG_NT + tid] = b; sRb[0][u * LEG_NT + tid] = r;
+        double2 e[NC], b[NC], r;
+        fetch_alm_nc<SPIN, NC>(P, m, l0 + u * LEG_NT + tid, base, roff, almE, almB, alm_stride, layout, fl, flB, e, b, r);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { sEb[0][c][u * LEG_NT + tid] = e[c]; if (SPIN) sBb[0][c][u * LEG_NT + tid] = b[c]; }
+        sRb[0][u * LEG_NT + tid] = r;
     }
     __syncthreads();
     int cur = 0;
     for (int lt = l0; lt <= L; lt += LEG_TLS, cur ^= 1) {
         const bool has_next = lt + LEG_TLS <= L;
-        double2 ne[LEG_SU], nb[LEG_SU], nr[LEG_SU];
+        double2 ne[LEG_SU][NC], nb[LEG_SU][NC], nr[LEG_SU];
         if (has_next) {
 #pragma unroll
             for (int u = 0; u < LEG_SU; ++u)
-                fetch_alm<SPIN>(P, m, lt + LEG_TLS + u * LEG_NT + tid, base, roff, almE, almB, layout, fl, flB, ne[u], nb[u], nr[u]);
+                fetch_alm_nc<SPIN, NC>(P, m, lt + LEG_TLS + u * LEG_NT + tid, base, roff, almE, almB, alm_stride, layout, fl, flB, ne[u], nb[u], nr[u]);
         }
-        const double2* sE = sEb[cur];
-        const double2* sB = sBb[cur];
+        const double2 (*sE)[LEG_TLS] = sEb[cur];
+        const double2 (*sB)[SPIN ? LEG_TLS : 1] = sBb[cur];
         const double2* sR = sRb[cur];
         const int ni = warp_act ? min(LEG_TLS, L - lt + 1) : 0;
         const int npr = (ni + 1) >> 1;
@@ -362,13 +387,18 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int i = 2 * ip + h;
-                const double2 r = sR[i], e = sE[i];
-                const double2 b = SPIN ? sB[i] : e;
+                const double2 r = sR[i];
+                double2 e[NC], b[NC];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) { e[c] = sE[c][i]; b[c] = SPIN ? sB[c][i] : e[c]; }
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
                     const double pc = st[j].sc ? 0.0 : st[j].pc, mc = st[j].sc ? 0.0 : st[j].mc;
-                    if (h == 0) synth_acc<SPIN, true>(acc[j], pc, mc, e, b);
-                    else synth_acc<SPIN, false>(acc[j], pc, mc, e, b);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        if (h == 0) synth_acc<SPIN, true>(acc[j][c], pc, mc, e[c], b[c]);
+                        else synth_acc<SPIN, false>(acc[j][c], pc, mc, e[c], b[c]);
+                    }
                     rec_step<SPIN>(st[j], r.x, r.y);
                     rescale_check<SPIN>(st[j]);
                 }
@@ -379,23 +409,32 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
 #pragma unroll 2
         for (; ip < npr; ++ip) {
             const int i = 2 * ip;
-            const double2 r0 = sR[i], e0 = sE[i], r1 = sR[i + 1], e1 = sE[i + 1];
-            const double2 b0 = SPIN ? sB[i] : e0, b1 = SPIN ? sB[i + 1] : e1;
+            const double2 r0 = sR[i], r1 = sR[i + 1];
+            double2 e0[NC], b0[NC], e1[NC], b1[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                e0[c] = sE[c][i]; e1[c] = sE[c][i + 1];
+                b0[c] = SPIN ? sB[c][i] : e0[c]; b1[c] = SPIN ? sB[c][i + 1] : e1[c];
+            }
 #pragma unroll
             for (int j = 0; j < R; ++j) {
-                synth_acc<SPIN, true>(acc[j], st[j].pc, st[j].mc, e0, b0);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) synth_acc<SPIN, true>(acc[j][c], st[j].pc, st[j].mc, e0[c], b0[c]);
                 rec_step<SPIN>(st[j], r0.x, r0.y);
-                synth_acc<SPIN, false>(acc[j], st[j].pc, st[j].mc, e1, b1);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) synth_acc<SPIN, false>(acc[j][c], st[j].pc, st[j].mc, e1[c], b1[c]);
                 rec_step<SPIN>(st[j], r1.x, r1.y);
             }
         }
         if (has_next) {
 #pragma unroll
             for (int u = 0; u < LEG_SU; ++u) {
-                sEb[cur ^ 1][u * LEG_NT + tid] = ne[u]; if (SPIN) sBb[cur ^ 1][u * LEG_NT + tid] = nb[u]; sRb[cur ^ 1][u * LEG_NT + tid] = nr[u];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) { sEb[cur ^ 1][c][u * LEG_NT + tid] = ne[u][c]; if (SPIN) sBb[cur ^ 1][c][u * LEG_NT + tid] = nb[u][c]; }
+                sRb[cur ^ 1][u * LEG_NT + tid] = nr[u];
             }
         }
-        __syncthreads();
+        TILE_SYNC();
     }
 
     // spin 0: north = S + A, south = +-(S - A); spin 2: combine the lambda^+- sums; the south sign follows the
@@ -406,18 +445,22 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
         const int p = pj[j];
         if (p < 0) continue;
         const int rn = p, rs = P.nring - 1 - p;
-        const SynthAcc<SPIN>& a = acc[j];
         const int64_t in = fm_index<SH>(P, 0, rn, m, mk), is = fm_index<SH>(P, 0, rs, m, mk);
-        if (SPIN == 0) {
-            Fm[in] = make_double2(a.sqr + a.aqr, a.sqi + a.aqi);
-            if (rs != rn) Fm[is] = make_double2(sg * (a.sqr - a.aqr), sg * (a.sqi - a.aqi));
-        } else {
-            const int64_t cs = SH ? (int64_t)P.sh.RL * P.sh.ML : (int64_t)P.nring * (L + 1);  // component stride
-            Fm[in] = make_double2(a.sqr + a.sqi, a.sur + a.sui);
-            Fm[in + cs] = make_double2(a.sur - a.sui, a.sqi - a.sqr);
-            if (rs != rn) {
-                Fm[is] = make_double2(sg * (a.aqr + a.aqi), sg * (a.aur + a.aui));
-                Fm[is + cs] = make_double2(sg * (a.aur - a.aui), sg * (a.aqi - a.aqr));
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const SynthAcc<SPIN>& a = acc[j][c];
+            double2* F = Fm + c * fm_stride;
+            if (SPIN == 0) {
+                F[in] = make_double2(a.sqr + a.aqr, a.sqi + a.aqi);
+                if (rs != rn) F[is] = make_double2(sg * (a.sqr - a.aqr), sg * (a.sqi - a.aqi));
+            } else {
+                const int64_t cs = SH ? (int64_t)P.sh.RL * P.sh.ML : (int64_t)P.nring * (L + 1);  // component stride
+                F[in] = make_double2(a.sqr + a.sqi, a.sur + a.sui);
+                F[in + cs] = make_double2(a.sur - a.sui, a.sqi - a.sqr);
+                if (rs != rn) {
+                    F[is] = make_double2(sg * (a.aqr + a.aqi), sg * (a.aur + a.aui));
+                    F[is + cs] = make_double2(sg * (a.aur - a.aui), sg * (a.aqi - a.aqr));
+                }
             }
         }
     }
@@ -733,10 +776,23 @@ __device__ __forceinline__ double anal_fold_sel(double* v, int lane)
 #ifndef LEG_MINB_A
 #define LEG_MINB_A 3   // 3 CTAs per SM: caps the unrolled fast loop at 168 registers
 #endif
-template <int SPIN, int R, bool SH>
+#ifndef LEG_RA2
+#define LEG_RA2 2      // ring pairs per thread of the chain-batched analysis (NC = 2): R NC = 4 keeps the register budget
+#endif
+// dynamic shared memory of leg_anal_kernel<SPIN, R, SH, NC>: recurrence tile, per-warp partial sums, parked exchange values
+template <int SPIN, int NC>
+constexpr size_t leg_anal_smem()
+{
+    return sizeof(double2) * LEG_TL + sizeof(double) * LEG_NW * NC * LEG_TL * (SPIN ? 4 : 2)
+           + ((SPIN && LEG_FOLD2 && LEG_FOLD3) ? sizeof(double2) * LEG_NW * NC * FOLD3_NB * 32 : 0);
+}
+// NC > 1: chain batch (see leg_synth_kernel): spectra of chain c at Fm + c fm_stride, partial sums at partial + c part_stride;
+// the recurrence of a (ring pair, m) thread is shared, the reduce-scatter runs once per chain.
+template <int SPIN, int R, bool SH, int NC>
 __global__ void __launch_bounds__(LEG_NT, LEG_MINB_A)
 leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ partial, const int* __restrict__ skip,
-                const int* __restrict__ plist, const int* __restrict__ pcount, const int* __restrict__ slot0)
+                const int* __restrict__ plist, const int* __restrict__ pcount, const int* __restrict__ slot0, int64_t fm_stride,
+                int64_t part_stride)
 {
     if (skip && *skip) return;
     const int L = P.lmax, mk = blockIdx.y, m = SH ? P.sh.mlist[mk] : mk, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -745,15 +801,17 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
     if ((int)blockIdx.x * (LEG_NT * R) >= nact) return;
     constexpr int NV = SPIN ? 4 : 2;   // doubles per (l,m)
     constexpr int NVAL = 2 * NV;       // values reduced per pair of l
-    __shared__ double2 sR[LEG_TL];
-    __shared__ double sPart[LEG_NW][LEG_TL * NV];
+    extern __shared__ double2 leg_dyn[];
+    double2* sR = leg_dyn;                                                  // [LEG_TL]
+    double* sPartAll = reinterpret_cast<double*>(leg_dyn + LEG_TL);         // [LEG_NW][NC][LEG_TL * NV]
+    auto sPart = [&](int ww, int c) { return sPartAll + ((size_t)(ww * NC + c)) * (LEG_TL * NV); };
 #if LEG_FOLD2 && LEG_FOLD3
     // After the two select-free exchange stages a lane holds, for each of the two l of a pair, the sum over 4 lanes of the
     // value c = (lane bit 4, lane bit 3); what remains is a sum over the 8 lanes that differ in bits 2..0.  Instead of three
     // more dependent shuffle stages per pair of l, the fast loop parks those two numbers in shared memory and sums FOLD3_NB
     // pairs of l at a time (8 independent loads per output, no selects).  Slot of lane L for local pair q:
     // L ^ c(L) ^ ((q & 1) << 2): stores are conflict free and the 32 outputs read in one step hit 16 distinct 8-byte banks.
-    __shared__ double2 sFold[SPIN ? LEG_NW : 1][SPIN ? FOLD3_NB * 32 : 1];
+    double2* sFoldAll = reinterpret_cast<double2*>(sPartAll + (size_t)LEG_NW * NC * LEG_TL * NV);   // [LEG_NW][NC][FOLD3_NB * 32] (spin 2)
 #endif
     const int l0 = m > SPIN ? m : SPIN;
     const int64_t base = (int64_t)m * (2 * L + 1 - m) / 2;
@@ -764,15 +822,18 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
     const int64_t cs = SH ? (int64_t)P.sh.RL * P.sh.ML : (int64_t)P.nring * (L + 1);  // component stride
 
     RingState<SPIN> st[R];
-    AnalIn<SPIN> G[R];
+    AnalIn<SPIN> G[R][NC];
     bool any_act = false;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
         const int k = chunk + ((tid >> 5) * R + j) * 32 + (tid & 31);   // warp-major: a warp owns 32 R consecutive pairs, so idle slots fill whole warps
         const int p = k < nact ? (plist ? plist[s0 + k] : s0 + k) : -1;
         st[j].x = 0.0; st[j].pc = st[j].pp = st[j].mc = st[j].mp = 0.0; st[j].sc = 0;
-        G[j].q1r = G[j].q1i = G[j].q2r = G[j].q2i = 0.0;
-        G[j].u1r = G[j].u1i = G[j].u2r = G[j].u2i = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            G[j][c].q1r = G[j][c].q1i = G[j][c].q2r = G[j][c].q2i = 0.0;
+            G[j][c].u1r = G[j][c].u1i = G[j][c].u2r = G[j][c].u2i = 0.0;
+        }
         if (p >= 0 && m <= (SPIN ? P.mlim2[p] : P.mlim0[p])) {
             st[j].x = P.cth[p];
             seed_ring<SPIN>(P, p, m, st[j].pc, st[j].mc, st[j].sc);
@@ -780,31 +841,36 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
             const int rn = p, rs = P.nring - 1 - p;
             const double2 z = make_double2(0.0, 0.0);
             const int64_t in = fm_index<SH>(P, 0, rn, m, mk), is = fm_index<SH>(P, 0, rs, m, mk);
-            const double2 qn = Fm[in], qs = (rs != rn) ? Fm[is] : z;
-            if (SPIN == 0) {
-                const double2 sy = make_double2(qn.x + qs.x, qn.y + qs.y), an = make_double2(qn.x - qs.x, qn.y - qs.y);
-                G[j].q1r = odd0 ? an.x : sy.x; G[j].q1i = odd0 ? an.y : sy.y;
-                G[j].q2r = odd0 ? sy.x : an.x; G[j].q2i = odd0 ? sy.y : an.y;
-            } else {
-                const double2 un = Fm[in + cs], us = (rs != rn) ? Fm[is + cs] : z;
-                const double sg = odd0 ? -1.0 : 1.0;
-                G[j].q1r = qn.x - un.y; G[j].q1i = qn.x + un.y; G[j].q2r = qn.y + un.x; G[j].q2i = qn.y - un.x;
-                G[j].u1r = sg * (qs.x - us.y); G[j].u1i = sg * (qs.x + us.y);
-                G[j].u2r = sg * (qs.y + us.x); G[j].u2i = sg * (qs.y - us.x);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const double2* F = Fm + c * fm_stride;
+                AnalIn<SPIN>& g = G[j][c];
+                const double2 qn = F[in], qs = (rs != rn) ? F[is] : z;
+                if (SPIN == 0) {
+                    const double2 sy = make_double2(qn.x + qs.x, qn.y + qs.y), an = make_double2(qn.x - qs.x, qn.y - qs.y);
+                    g.q1r = odd0 ? an.x : sy.x; g.q1i = odd0 ? an.y : sy.y;
+                    g.q2r = odd0 ? sy.x : an.x; g.q2i = odd0 ? sy.y : an.y;
+                } else {
+                    const double2 un = F[in + cs], us = (rs != rn) ? F[is + cs] : z;
+                    const double sg = odd0 ? -1.0 : 1.0;
+                    g.q1r = qn.x - un.y; g.q1i = qn.x + un.y; g.q2r = qn.y + un.x; g.q2i = qn.y - un.x;
+                    g.u1r = sg * (qs.x - us.y); g.u1i = sg * (qs.x + us.y);
+                    g.u2r = sg * (qs.y + us.x); g.u2i = sg * (qs.y - us.x);
 #if LEG_FOLD2
-                {   // (q1r,q1i,q2r,q2i) <- X = (k1n, k2s, k3n, k4s), (u1r,u1i,u2r,u2i) <- Y = (k1s, k2n, k3s, k4n), then slot = c ^ pi
-                    double t = G[j].q1i; G[j].q1i = G[j].u1i; G[j].u1i = t;
-                    t = G[j].q2i; G[j].q2i = G[j].u2i; G[j].u2i = t;
-                    if (lane & 16) {
-                        t = G[j].q1r; G[j].q1r = G[j].q2r; G[j].q2r = t;  t = G[j].q1i; G[j].q1i = G[j].q2i; G[j].q2i = t;
-                        t = G[j].u1r; G[j].u1r = G[j].u2r; G[j].u2r = t;  t = G[j].u1i; G[j].u1i = G[j].u2i; G[j].u2i = t;
+                    {   // (q1r,q1i,q2r,q2i) <- X = (k1n, k2s, k3n, k4s), (u1r,u1i,u2r,u2i) <- Y = (k1s, k2n, k3s, k4n), then slot = c ^ pi
+                        double t = g.q1i; g.q1i = g.u1i; g.u1i = t;
+                        t = g.q2i; g.q2i = g.u2i; g.u2i = t;
+                        if (lane & 16) {
+                            t = g.q1r; g.q1r = g.q2r; g.q2r = t;  t = g.q1i; g.q1i = g.q2i; g.q2i = t;
+                            t = g.u1r; g.u1r = g.u2r; g.u2r = t;  t = g.u1i; g.u1i = g.u2i; g.u2i = t;
+                        }
+                        if (lane & 8) {
+                            t = g.q1r; g.q1r = g.q1i; g.q1i = t;  t = g.q2r; g.q2r = g.q2i; g.q2i = t;
+                            t = g.u1r; g.u1r = g.u1i; g.u1i = t;  t = g.u2r; g.u2r = g.u2i; g.u2i = t;
+                        }
                     }
-                    if (lane & 8) {
-                        t = G[j].q1r; G[j].q1r = G[j].q1i; G[j].q1i = t;  t = G[j].q2r; G[j].q2r = G[j].q2i; G[j].q2i = t;
-                        t = G[j].u1r; G[j].u1r = G[j].u1i; G[j].u1i = t;  t = G[j].u2r; G[j].u2r = G[j].u2i; G[j].u2i = t;
-                    }
-                }
 #endif
+                }
             }
         }
     }
@@ -820,20 +886,23 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
     const bool writer = (lane & (SPIN ? 3 : 7)) == 0;
 
     for (int lt = l0; lt <= L; lt += LEG_TL) {
-        __syncthreads();
+        TILE_SYNC();
         for (int i = tid; i < LEG_TL; i += LEG_NT) {
             const int l = lt + i;
             double2 r = make_double2(0.0, 0.0);
             if (l <= L) { if (SPIN) r = P.rec2[base + l]; else r.x = P.rec0[base + l]; }
             sR[i] = r;
         }
-        __syncthreads();
+        TILE_SYNC();
         const int ni = min(LEG_TL, L - lt + 1);
         const int npr = (ni + 1) >> 1;
         int ip = 0;
-        double* myPart = sPart[w];
         if (!warp_act) {
-            for (int i = lane; i < LEG_TL * NV; i += 32) myPart[i] = 0.0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                double* mp = sPart(w, c);
+                for (int i = lane; i < LEG_TL * NV; i += 32) mp[i] = 0.0;
+            }
             ip = npr;
         }
         while (ip < npr) {  // (A)
@@ -847,7 +916,10 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
 #pragma unroll
                 for (int j = 0; j < R; ++j) { rec_step<SPIN>(st[j], r.x, r.y); rescale_check<SPIN>(st[j]); }
             }
-            if (lane < NVAL) myPart[ip * NVAL + lane] = 0.0;
+            if (lane < NVAL) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c) sPart(w, c)[ip * NVAL + lane] = 0.0;
+            }
             ++ip;
         }
         while (ip < npr) {  // (B)
@@ -855,66 +927,91 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
 #pragma unroll
             for (int j = 0; j < R; ++j) anys = anys || st[j].sc > 0;
             if (!__any_sync(FULL, anys)) break;
-            double v[NVAL];
+            double v[NC][NVAL];
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const double2 r = sR[2 * ip + h];
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
                     const double pc = st[j].sc ? 0.0 : st[j].pc, mc = st[j].sc ? 0.0 : st[j].mc;
-                    if (h == 0) { if (j == 0) ANAL_ACC(true, true, v, G[j], pc, mc); else ANAL_ACC(true, false, v, G[j], pc, mc); }
-                    else { if (j == 0) ANAL_ACC(false, true, v + NV, G[j], pc, mc); else ANAL_ACC(false, false, v + NV, G[j], pc, mc); }
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        if (h == 0) { if (j == 0) ANAL_ACC(true, true, v[c], G[j][c], pc, mc); else ANAL_ACC(true, false, v[c], G[j][c], pc, mc); }
+                        else { if (j == 0) ANAL_ACC(false, true, v[c] + NV, G[j][c], pc, mc); else ANAL_ACC(false, false, v[c] + NV, G[j][c], pc, mc); }
+                    }
                     rec_step<SPIN>(st[j], r.x, r.y);
                     rescale_check<SPIN>(st[j]);
                 }
             }
-            const double s = ANAL_FOLD(v, lane);
-            if (writer) myPart[ip * NVAL + vidx] = __hiloint2double(__double2hiint(s) ^ flipmask, __double2loint(s));
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const double s = ANAL_FOLD(v[c], lane);
+                if (writer) sPart(w, c)[ip * NVAL + vidx] = __hiloint2double(__double2hiint(s) ^ flipmask, __double2loint(s));
+            }
             ++ip;
         }
 #if LEG_FOLD2 && LEG_FOLD3
         if (SPIN == 2) {
-            double2* fbuf = sFold[SPIN ? w : 0];
             const int cperm = ((lane >> 4) & 1) << 1 | ((lane >> 3) & 1);
-            int ipb = ip;   // first pair of l of the batch parked in fbuf
-            // sums the parked pairs [ipb, ipb + n) over the 8 lanes of each value and writes them to myPart
+            int ipb = ip;   // first pair of l of the batch parked in the fold buffers
+            // sums the parked pairs [ipb, ipb + n) over the 8 lanes of each value and writes them to the warp's partial sums
             auto flush = [&](int n) {
                 __syncwarp();
 #pragma unroll
-                for (int t = 0; t < FOLD3_NB / 4; ++t) {
-                    const int o = lane + 32 * t, q = o >> 3, h = (o >> 2) & 1, c = o & 3;
-                    if (q < n) {
-                        const double* e = reinterpret_cast<const double*>(fbuf + q * 32) + h;
-                        const int s0 = (((c >> 1) << 4) | ((c & 1) << 3)) ^ c ^ ((q & 1) << 2);   // slot of source lane (c, s = 0)
-                        double a[8];
+                for (int c = 0; c < NC; ++c) {
+                    const double2* fbuf = sFoldAll + ((size_t)(w * NC + c)) * (FOLD3_NB * 32);
+                    double* myPart = sPart(w, c);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) a[k] = e[2 * (s0 ^ k)];   // s ^ (low bits of the swizzle) runs over the same 8 slots
-                        double sum = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-                        if (h && (c & 1)) sum = -sum;
-                        myPart[(ipb + q) * NVAL + h * 4 + c] = sum;
+                    for (int t = 0; t < FOLD3_NB / 4; ++t) {
+                        const int o = lane + 32 * t, q = o >> 3, h = (o >> 2) & 1, cc = o & 3;
+                        if (q < n) {
+                            const double* e = reinterpret_cast<const double*>(fbuf + q * 32) + h;
+                            const int sl0 = (((cc >> 1) << 4) | ((cc & 1) << 3)) ^ cc ^ ((q & 1) << 2);   // slot of source lane (cc, s = 0)
+                            double a[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) a[k] = e[2 * (sl0 ^ k)];   // s ^ (low bits of the swizzle) runs over the same 8 slots
+                            double sum = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+                            if (h && (cc & 1)) sum = -sum;
+                            myPart[(ipb + q) * NVAL + h * 4 + cc] = sum;
+                        }
                     }
                 }
                 __syncwarp();
             };
 #pragma unroll kUnrollA
             for (; ip < npr; ++ip) {  // (C)
-                double v[NVAL];
+                double v[NC][NVAL];
                 const double2 r0 = sR[2 * ip], r1 = sR[2 * ip + 1];
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
-                    if (j == 0) ANAL_ACC(true, true, v, G[j], st[j].pc, st[j].mc);
-                    else ANAL_ACC(true, false, v, G[j], st[j].pc, st[j].mc);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        if (j == 0) ANAL_ACC(true, true, v[c], G[j][c], st[j].pc, st[j].mc);
+                        else ANAL_ACC(true, false, v[c], G[j][c], st[j].pc, st[j].mc);
+                    }
                     rec_step<SPIN>(st[j], r0.x, r0.y);
-                    if (j == 0) ANAL_ACC(false, true, v + NV, G[j], st[j].pc, st[j].mc);
-                    else ANAL_ACC(false, false, v + NV, G[j], st[j].pc, st[j].mc);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        if (j == 0) ANAL_ACC(false, true, v[c] + NV, G[j][c], st[j].pc, st[j].mc);
+                        else ANAL_ACC(false, false, v[c] + NV, G[j][c], st[j].pc, st[j].mc);
+                    }
                     rec_step<SPIN>(st[j], r1.x, r1.y);
                 }
-                v[0] += __shfl_xor_sync(FULL, v[2], 16); v[1] += __shfl_xor_sync(FULL, v[3], 16);
-                v[4] += __shfl_xor_sync(FULL, v[6], 16); v[5] += __shfl_xor_sync(FULL, v[7], 16);
-                v[0] += __shfl_xor_sync(FULL, v[1], 8);
-                v[4] += __shfl_xor_sync(FULL, v[5], 8);
                 const int q = ip - ipb;
-                fbuf[q * 32 + (lane ^ cperm ^ ((q & 1) << 2))] = make_double2(v[0], v[4]);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    double* vv = v[c];
+#ifdef LEG_XNORED   // EXPERIMENT ONLY (wrong results): no cross-lane exchange, to measure what the in-loop reduce-scatter costs
+                    vv[0] += vv[2]; vv[1] += vv[3]; vv[4] += vv[6]; vv[5] += vv[7]; vv[0] += vv[1]; vv[4] += vv[5];
+#else
+                    vv[0] += __shfl_xor_sync(FULL, vv[2], 16); vv[1] += __shfl_xor_sync(FULL, vv[3], 16);
+                    vv[4] += __shfl_xor_sync(FULL, vv[6], 16); vv[5] += __shfl_xor_sync(FULL, vv[7], 16);
+                    vv[0] += __shfl_xor_sync(FULL, vv[1], 8);
+                    vv[4] += __shfl_xor_sync(FULL, vv[5], 8);
+#endif
+                    double2* fbuf = sFoldAll + ((size_t)(w * NC + c)) * (FOLD3_NB * 32);
+                    fbuf[q * 32 + (lane ^ cperm ^ ((q & 1) << 2))] = make_double2(vv[0], vv[4]);
+                }
                 if (q == FOLD3_NB - 1) { flush(FOLD3_NB); ipb = ip + 1; }
             }
             if (ip > ipb) flush(ip - ipb);
@@ -923,28 +1020,41 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
         {
 #pragma unroll kUnrollA
         for (; ip < npr; ++ip) {  // (C)
-            double v[NVAL];
+            double v[NC][NVAL];
             const double2 r0 = sR[2 * ip], r1 = sR[2 * ip + 1];
 #pragma unroll
             for (int j = 0; j < R; ++j) {
-                if (j == 0) ANAL_ACC(true, true, v, G[j], st[j].pc, st[j].mc);
-                else ANAL_ACC(true, false, v, G[j], st[j].pc, st[j].mc);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    if (j == 0) ANAL_ACC(true, true, v[c], G[j][c], st[j].pc, st[j].mc);
+                    else ANAL_ACC(true, false, v[c], G[j][c], st[j].pc, st[j].mc);
+                }
                 rec_step<SPIN>(st[j], r0.x, r0.y);
-                if (j == 0) ANAL_ACC(false, true, v + NV, G[j], st[j].pc, st[j].mc);
-                else ANAL_ACC(false, false, v + NV, G[j], st[j].pc, st[j].mc);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    if (j == 0) ANAL_ACC(false, true, v[c] + NV, G[j][c], st[j].pc, st[j].mc);
+                    else ANAL_ACC(false, false, v[c] + NV, G[j][c], st[j].pc, st[j].mc);
+                }
                 rec_step<SPIN>(st[j], r1.x, r1.y);
             }
-            const double s = ANAL_FOLD(v, lane);
-            if (writer) myPart[ip * NVAL + vidx] = __hiloint2double(__double2hiint(s) ^ flipmask, __double2loint(s));
-        }
-        }
-        __syncthreads();
-        // sum over the warps of the block, one deterministic partial per chunk
-        for (int i = tid; i < ni * NV; i += LEG_NT) {
-            double s = 0.0;
 #pragma unroll
-            for (int ww = 0; ww < LEG_NW; ++ww) s += sPart[ww][i];
-            partial[(pbase + lt) * NV + i] = s;
+            for (int c = 0; c < NC; ++c) {
+                const double s = ANAL_FOLD(v[c], lane);
+                if (writer) sPart(w, c)[ip * NVAL + vidx] = __hiloint2double(__double2hiint(s) ^ flipmask, __double2loint(s));
+            }
+        }
+        }
+        TILE_SYNC();
+        // sum over the warps of the block, one deterministic partial per chunk
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            double* out = partial + c * part_stride + (pbase + lt) * NV;
+            for (int i = tid; i < ni * NV; i += LEG_NT) {
+                double s = 0.0;
+#pragma unroll
+                for (int ww = 0; ww < LEG_NW; ++ww) s += sPart(ww, c)[i];
+                out[i] = s;
+            }
         }
     }
 }
@@ -954,11 +1064,15 @@ template <int SPIN, bool SH>
 __global__ void leg_finish_kernel(PlanDev P, const double* __restrict__ partial, int nchunk, double* __restrict__ almE,
                                   double* __restrict__ almB, int layout, const double* __restrict__ fl, double scale,
                                   int accumulate, const int* __restrict__ skip, const int* __restrict__ pcount,
-                                  const int* __restrict__ slot0, int chunk_pairs)
+                                  const int* __restrict__ slot0, int chunk_pairs, int64_t part_stride, int64_t alm_stride)
 {
     if (skip && *skip) return;
     constexpr int NV = SPIN ? 4 : 2;
     const int L = P.lmax, mk = blockIdx.y, m = SH ? P.sh.mlist[mk] : mk;
+    // chain batch: blockIdx.z = chain
+    partial += blockIdx.z * part_stride;
+    almE += blockIdx.z * alm_stride;
+    if (SPIN) almB += blockIdx.z * alm_stride;
     {   // chunks of this m that hold slots (the others were not written)
         const int nact = (pcount ? *pcount : P.npair) - slot0[m];
         nchunk = nact > 0 ? (nact + chunk_pairs - 1) / chunk_pairs : 0;
@@ -1186,21 +1300,43 @@ int gs_active_rings_build(gs_plan* p, const double* pixw, cudaStream_t st)
 }
 
 // ------------------------------------------------------------------ host launchers
+// nc = 1: one right-hand side (spectra in p->Fm).  nc = 2: chain batch, unsharded plans whose buffers were sized by
+// gs_plan_reserve_chains: chain c reads almE/almB + c alm_stride and fills the spectra p->Fm + c gs_fm_stride(p).
+int64_t gs_fm_stride(const gs_plan* p) { return (int64_t)2 * p->d.nring * (p->d.lmax + 1); }
+static int anal_chunks_of(const gs_plan* p, int nc) { const int per = LEG_NT * (nc > 1 ? LEG_RA2 : LEG_RA); return (p->d.npair + per - 1) / per; }
+int64_t gs_part_stride(const gs_plan* p, int nc) { return (int64_t)anal_chunks_of(p, nc) * p->d.nalm * 4; }
+
+static int check_batch(const gs_plan* p, int nc, int layout, const char* who)
+{
+    if (nc == 1) return GS_OK;
+    if (nc != 2) { gs_set_error("%s: chain batches run 2 right-hand sides per launch (got %d)", who, nc); return GS_E_BADARG; }
+    if (p->world > 1) { gs_set_error("%s: chain batches need an unsharded plan", who); return GS_E_BADARG; }
+    if (p->chain_cap < nc) { gs_set_error("%s: call gs_plan_reserve_chains(plan, %d) first", who, nc); return GS_E_BADARG; }
+    (void)layout;
+    return GS_OK;
+}
+
 int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, int layout, const double* fl,
-                 cudaStream_t st, const int* skip, const double* flB)
+                 cudaStream_t st, const int* skip, const double* flB, int nc, int64_t alm_stride)
 {
     const bool sh = p->world > 1;
     if (sh && layout != GS_ALM_REAL) { gs_set_error("sharded plans take the (local) real alm layout only"); return GS_E_BADARG; }
+    int rc = check_batch(p, nc, layout, "gs_leg_synth");
+    if (rc) return rc;
     dim3 grid((p->d.npair + LEG_NT * LEG_R - 1) / (LEG_NT * LEG_R), sh ? p->d.sh.nm_loc : p->d.lmax + 1);
     const int* plist = p->use_act ? p->act_pairs : nullptr;
     const int* pcount = plist ? p->act_count : nullptr;
     const int* slot0 = plist ? p->act_slot0 + (spin ? p->d.lmax + 1 : 0) : (spin ? p->d.pmin2 : p->d.pmin0);
-    if (!sh) {
-        if (spin == 0) leg_synth_kernel<0, LEG_R, false><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0);
-        else leg_synth_kernel<2, LEG_R, false><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0);
+    const int64_t fs = gs_fm_stride(p);
+    if (nc == 2) {
+        if (spin == 0) leg_synth_kernel<0, LEG_R, false, 2><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, alm_stride, fs);
+        else leg_synth_kernel<2, LEG_R, false, 2><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, alm_stride, fs);
+    } else if (!sh) {
+        if (spin == 0) leg_synth_kernel<0, LEG_R, false, 1><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, 0, 0);
+        else leg_synth_kernel<2, LEG_R, false, 1><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, 0, 0);
     } else {
-        if (spin == 0) leg_synth_kernel<0, LEG_R, true><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0);
-        else leg_synth_kernel<2, LEG_R, true><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0);
+        if (spin == 0) leg_synth_kernel<0, LEG_R, true, 1><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, 0, 0);
+        else leg_synth_kernel<2, LEG_R, true, 1><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, 0, 0);
     }
     GS_CHECK_LAUNCH();
     g_gs_launches += 1;
@@ -1209,53 +1345,76 @@ int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, i
     return GS_OK;
 }
 
+template <int SPIN, int R, bool SH, int NC>
+static int launch_anal(gs_plan* p, dim3 grid, cudaStream_t st, const int* skip, const int* plist, const int* pcount, const int* slot0,
+                       int64_t fs, int64_t ps)
+{
+    static bool attr_set[64] = {false};   // per device: the 48 KB default limit of dynamic shared memory is exceeded by the chain batch
+    constexpr size_t sm = leg_anal_smem<SPIN, NC>();
+    const int dev = p->device & 63;
+    if (!attr_set[dev]) {
+        GS_CHECK_CUDA(cudaFuncSetAttribute(leg_anal_kernel<SPIN, R, SH, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        attr_set[dev] = true;
+    }
+    leg_anal_kernel<SPIN, R, SH, NC><<<grid, LEG_NT, sm, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount, slot0, fs, ps);
+    GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
 int gs_leg_anal(gs_plan* p, int spin, double* almE, double* almB, int layout, const double* fl, double scale,
-                int accumulate, cudaStream_t st, const int* skip, const FinishFuse* fuse)
+                int accumulate, cudaStream_t st, const int* skip, const FinishFuse* fuse, int nc, int64_t alm_stride)
 {
     const bool sh = p->world > 1;
     if (sh && layout != GS_ALM_REAL) { gs_set_error("sharded plans take the (local) real alm layout only"); return GS_E_BADARG; }
-    const int nchunk = (p->d.npair + LEG_NT * LEG_RA - 1) / (LEG_NT * LEG_RA);
-    if (nchunk > p->anal_chunks) { gs_set_error("gs_leg_anal: workspace too small"); return GS_E_BADARG; }
+    int rc = check_batch(p, nc, layout, "gs_leg_anal");
+    if (rc) return rc;
+    const int nchunk = anal_chunks_of(p, nc);
+    if (nchunk * nc > p->anal_chunks) { gs_set_error("gs_leg_anal: workspace too small"); return GS_E_BADARG; }
     const int nmy = sh ? p->d.sh.nm_loc : p->d.lmax + 1;
     dim3 grid(nchunk, nmy);
-    dim3 fgrid((p->d.lmax + 256) / 256, nmy);
+    dim3 fgrid((p->d.lmax + 256) / 256, nmy, nc);
     const int* plist = p->use_act ? p->act_pairs : nullptr;
     const int* pcount = plist ? p->act_count : nullptr;
     const int* slot0 = plist ? p->act_slot0 + (spin ? p->d.lmax + 1 : 0) : (spin ? p->d.pmin2 : p->d.pmin0);
+    const int64_t fs = gs_fm_stride(p), ps = gs_part_stride(p, nc);
+    const int cp = LEG_NT * (nc > 1 ? LEG_RA2 : LEG_RA);   // ring pairs per chunk
     if (sh) {  // ring-sharded (p->Fx, written by the ring analysis) -> m-sharded
-        int rc = gs_shard_exchange(p, p->Fx, p->Fm, st);
+        rc = gs_shard_exchange(p, p->Fx, p->Fm, st);
         if (rc) return rc;
     }
-    if (fuse) {
+    if (nc == 2) {
+        if (fuse) { gs_set_error("gs_leg_anal: the fused finish takes one right-hand side"); return GS_E_BADARG; }
+        if (spin == 0) {
+            if ((rc = launch_anal<0, LEG_RA2, false, 2>(p, grid, st, skip, plist, pcount, slot0, fs, ps))) return rc;
+            leg_finish_kernel<0, false><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, cp, ps, alm_stride);
+        } else {
+            if ((rc = launch_anal<2, LEG_RA2, false, 2>(p, grid, st, skip, plist, pcount, slot0, fs, ps))) return rc;
+            leg_finish_kernel<2, false><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, cp, ps, alm_stride);
+        }
+    } else if (fuse) {
         if (sh || layout != GS_ALM_REAL || accumulate || scale != 1.0) { gs_set_error("gs_leg_anal: fused finish needs an unsharded real-layout plain analysis"); return GS_E_BADARG; }
         if (spin == 0) {
-            leg_anal_kernel<0, LEG_RA, false><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount, slot0);
-            GS_CHECK_LAUNCH();
-            leg_finish_apq_kernel<0><<<fgrid, 256, 0, st>>>(p->d, p->partial, almE, almB, fl, skip, pcount, slot0, LEG_NT * LEG_RA, *fuse);
+            if ((rc = launch_anal<0, LEG_RA, false, 1>(p, grid, st, skip, plist, pcount, slot0, 0, 0))) return rc;
+            leg_finish_apq_kernel<0><<<dim3(fgrid.x, fgrid.y), 256, 0, st>>>(p->d, p->partial, almE, almB, fl, skip, pcount, slot0, cp, *fuse);
         } else {
-            leg_anal_kernel<2, LEG_RA, false><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount, slot0);
-            GS_CHECK_LAUNCH();
-            leg_finish_apq_kernel<2><<<fgrid, 256, 0, st>>>(p->d, p->partial, almE, almB, fl, skip, pcount, slot0, LEG_NT * LEG_RA, *fuse);
+            if ((rc = launch_anal<2, LEG_RA, false, 1>(p, grid, st, skip, plist, pcount, slot0, 0, 0))) return rc;
+            leg_finish_apq_kernel<2><<<dim3(fgrid.x, fgrid.y), 256, 0, st>>>(p->d, p->partial, almE, almB, fl, skip, pcount, slot0, cp, *fuse);
         }
     } else if (!sh) {
         if (spin == 0) {
-            leg_anal_kernel<0, LEG_RA, false><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount, slot0);
-            GS_CHECK_LAUNCH();
-            leg_finish_kernel<0, false><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, LEG_NT * LEG_RA);
+            if ((rc = launch_anal<0, LEG_RA, false, 1>(p, grid, st, skip, plist, pcount, slot0, 0, 0))) return rc;
+            leg_finish_kernel<0, false><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, cp, 0, 0);
         } else {
-            leg_anal_kernel<2, LEG_RA, false><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount, slot0);
-            GS_CHECK_LAUNCH();
-            leg_finish_kernel<2, false><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, LEG_NT * LEG_RA);
+            if ((rc = launch_anal<2, LEG_RA, false, 1>(p, grid, st, skip, plist, pcount, slot0, 0, 0))) return rc;
+            leg_finish_kernel<2, false><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, cp, 0, 0);
         }
     } else {
         if (spin == 0) {
-            leg_anal_kernel<0, LEG_RA, true><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount, slot0);
-            GS_CHECK_LAUNCH();
-            leg_finish_kernel<0, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, LEG_NT * LEG_RA);
+            if ((rc = launch_anal<0, LEG_RA, true, 1>(p, grid, st, skip, plist, pcount, slot0, 0, 0))) return rc;
+            leg_finish_kernel<0, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, cp, 0, 0);
         } else {
-            leg_anal_kernel<2, LEG_RA, true><<<grid, LEG_NT, 0, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount, slot0);
-            GS_CHECK_LAUNCH();
-            leg_finish_kernel<2, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, LEG_NT * LEG_RA);
+            if ((rc = launch_anal<2, LEG_RA, true, 1>(p, grid, st, skip, plist, pcount, slot0, 0, 0))) return rc;
+            leg_finish_kernel<2, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, cp, 0, 0);
         }
     }
     GS_CHECK_LAUNCH();

@@ -255,6 +255,9 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
     p->comm = nullptr;
     p->lgroup = lgroup;
     p->pcg_ws = nullptr;
+    p->pcg_ws_batch = nullptr;
+    p->pcg_alldone = nullptr;
+    p->chain_cap = 1;
     p->Fx = nullptr;
     p->red_loc = nullptr;
     p->d.sh.world = 1;
@@ -314,6 +317,36 @@ extern "C" int gs_plan_create_sharded_local(gs_plan** out, int nside, int lmax, 
 {
     if (!local_group) { gs_set_error("null local group"); return GS_E_BADARG; }
     return plan_create_impl(out, nside, lmax, device, rank, world, nullptr, local_group);
+}
+
+// Chain batches (BASELINE config #5 "batched over chains", north_star (a)): size the ring-spectra and analysis partial-sum
+// buffers for n_chain right-hand sides that share one Legendre recurrence per launch.  Unsharded plans, n_chain <= 2 per launch.
+extern "C" int gs_plan_reserve_chains(gs_plan* p, int n_chain)
+{
+    if (!p) { gs_set_error("null plan"); return GS_E_BADARG; }
+    GS_REQUIRE(n_chain >= 1 && n_chain <= 2, "n_chain must be 1 or 2");
+    GS_REQUIRE(p->world == 1, "chain batches need an unsharded plan");
+    if (n_chain <= p->chain_cap) return GS_OK;
+    GS_CHECK_CUDA(cudaSetDevice(p->device));
+    const int64_t nm = p->d.lmax + 1;
+    const size_t nfm = (size_t)n_chain * 2 * p->d.nring * nm;
+    double2* F = nullptr;
+    int rc = dev_alloc(p, nfm, &F);
+    if (rc) return rc;
+    GS_CHECK_CUDA(cudaMemset(F, 0, nfm * sizeof(double2)));
+    // every chain of a batch takes ceil(npair / 256) chunks of partial sums (legendre.cu: LEG_NT * LEG_RA2 ring pairs per chunk)
+    const int chunks = std::max(p->anal_chunks, n_chain * ((p->d.npair + 255) / 256));
+    double* part = nullptr;
+    if (chunks > p->anal_chunks) {
+        rc = dev_alloc(p, (size_t)chunks * p->d.nalm * 4, &part);
+        if (rc) return rc;
+        p->partial = part;
+        p->anal_chunks = chunks;
+    }
+    GS_CHECK_CUDA(cudaDeviceSynchronize());
+    p->Fm = F;   // the single-chain buffer stays in p->owned until the plan is destroyed
+    p->chain_cap = n_chain;
+    return GS_OK;
 }
 
 extern "C" int gs_plan_destroy(gs_plan* p)

@@ -512,11 +512,15 @@ template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
 ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __restrict__ groups, const double* __restrict__ mapQ,
                  const double* __restrict__ mapU, const double* __restrict__ pixw, double2* __restrict__ Fm, const int* __restrict__ skip,
-                 int spin2, const unsigned char* __restrict__ ract)
+                 int spin2, const unsigned char* __restrict__ ract, int64_t f_stride, int64_t map_stride)
 {
     if (skip && *skip) return;
     if (group_idle(ract, jobs, groups)) return;
     extern __shared__ double2 smem[];
+    // chain batch (blockIdx.y = chain): maps at + y map_stride -> spectra at + y f_stride; the pixel weights are shared
+    Fm += blockIdx.y * f_stride;
+    mapQ += blockIdx.y * map_stride;
+    mapU += blockIdx.y * map_stride;
     double2* twq = smem;
     load_twq(P, twq);
     const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
@@ -560,11 +564,13 @@ extern "C" int gs_ring_debug_dump(unsigned long long* host, int n) { return (int
 template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
 ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __restrict__ groups, double2* __restrict__ Fm,
-                  const double* __restrict__ pixw, const int* __restrict__ skip, const unsigned char* __restrict__ ract, int spin2)
+                  const double* __restrict__ pixw, const int* __restrict__ skip, const unsigned char* __restrict__ ract, int spin2,
+                  int64_t f_stride)
 {
     if (skip && *skip) return;
     if (group_idle(ract, jobs, groups)) return;
     extern __shared__ double2 smem[];
+    Fm += blockIdx.y * f_stride;   // chain batch: blockIdx.y = chain, same pixel weights
     double2* twq = smem;
     load_twq(P, twq);
     const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
@@ -932,8 +938,9 @@ int gs_ring_setup(gs_plan* p)
     return GS_OK;
 }
 
-int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st, const int* skip)
+int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st, const int* skip, int nc, int64_t map_stride)
 {
+    if (nc > 1 && (p->world > 1 || (spin == 0 ? p->nsjobs0 : p->nsjobs2) > 0)) { gs_set_error("chain batches need an unsharded plan without split rings (nside < 2048)"); return GS_E_BADARG; }
     const int nj = spin == 0 ? p->ngroups0 : p->ngroups2, ns = spin == 0 ? p->nsjobs0 : p->nsjobs2;
     const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
     const int2* grp = spin == 0 ? p->groups0 : p->groups2;
@@ -955,7 +962,7 @@ int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t
     }
     if (nj > 0) {
         if (sh) ring_synth_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr, spin ? 1 : 0, ract);
-        else ring_synth_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr, spin ? 1 : 0, ract);
+        else ring_synth_kernel<false><<<dim3(nj, nc), RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, nc > 1 ? gs_fm_stride(p) : 0, nc > 1 ? map_stride : 0, nullptr, spin ? 1 : 0, ract);
         GS_CHECK_LAUNCH();
     }
     g_gs_launches += 1;
@@ -963,8 +970,9 @@ int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t
 }
 
 int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, const double* pixw, cudaStream_t st,
-                 const int* skip)
+                 const int* skip, int nc, int64_t map_stride)
 {
+    if (nc > 1 && (p->world > 1 || (spin == 0 ? p->nsjobs0 : p->nsjobs2) > 0)) { gs_set_error("chain batches need an unsharded plan without split rings (nside < 2048)"); return GS_E_BADARG; }
     const int nj = spin == 0 ? p->ngroups0 : p->ngroups2, ns = spin == 0 ? p->nsjobs0 : p->nsjobs2;
     const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
     const int2* grp = spin == 0 ? p->groups0 : p->groups2;
@@ -985,8 +993,8 @@ int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, c
         g_gs_launches += 2;
     }
     if (nj > 0) {
-        if (sh) ring_anal_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, mapQ, mu, pixw, F, skip, spin ? 1 : 0, ract);
-        else ring_anal_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, mapQ, mu, pixw, F, skip, spin ? 1 : 0, ract);
+        if (sh) ring_anal_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, mapQ, mu, pixw, F, skip, spin ? 1 : 0, ract, 0, 0);
+        else ring_anal_kernel<false><<<dim3(nj, nc), RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, mapQ, mu, pixw, F, skip, spin ? 1 : 0, ract, nc > 1 ? gs_fm_stride(p) : 0, nc > 1 ? map_stride : 0);
         GS_CHECK_LAUNCH();
     }
     g_gs_launches += 1;
@@ -995,9 +1003,10 @@ int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, c
 
 // ring stage of A^T diag(pixw) A on the ring spectra in place; falls back to synthesis + weighted analysis through the
 // plan's scratch maps when some rings take the split path
-int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, const int* skip)
+int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, const int* skip, int nc)
 {
     const int nj = spin == 0 ? p->ngroups0 : p->ngroups2, ns = spin == 0 ? p->nsjobs0 : p->nsjobs2;
+    if (nc > 1 && (p->world > 1 || ns > 0 || !pixw)) { gs_set_error("chain batches need an unsharded plan without split rings (nside < 2048) and pixel weights"); return GS_E_BADARG; }
     if (ns > 0 || !pixw) {
         int rc = gs_ring_synth(p, spin, p->mapQ_tmp, p->mapU_tmp, st, skip);
         if (rc) return rc;
@@ -1006,8 +1015,8 @@ int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, con
     if (nj <= 0) return GS_OK;
     const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
     const int2* grp = spin == 0 ? p->groups0 : p->groups2;
-    if (p->world > 1) ring_apply_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fx, pixw, skip, p->use_act ? p->act_ring : nullptr, spin ? 1 : 0);
-    else ring_apply_kernel<false><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fm, pixw, skip, p->use_act ? p->act_ring : nullptr, spin ? 1 : 0);
+    if (p->world > 1) ring_apply_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fx, pixw, skip, p->use_act ? p->act_ring : nullptr, spin ? 1 : 0, 0);
+    else ring_apply_kernel<false><<<dim3(nj, nc), RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fm, pixw, skip, p->use_act ? p->act_ring : nullptr, spin ? 1 : 0, nc > 1 ? gs_fm_stride(p) : 0);
     GS_CHECK_LAUNCH();
     g_gs_launches += 1;
     return GS_OK;

@@ -313,13 +313,53 @@ static gs_pcg_ws* get_ws(gs_plan* p)
     return w;
 }
 
+// Chain batch (gs_cr_pcg_pol_batch): two workspaces whose p and q vectors lie one batch stride (2 n doubles: E then B of a chain)
+// apart, so that the chain-batched mat-vec reads / writes them as one strided array.  Allocated on the first batched solve.
+static gs_pcg_ws* get_ws_batch(gs_plan* p)
+{
+    if (p->pcg_ws_batch) return (gs_pcg_ws*)p->pcg_ws_batch;
+    gs_pcg_ws* w = new gs_pcg_ws[2]();
+    const size_t n = (size_t)p->nreal_loc;
+    auto alloc = [&](double** q, size_t cnt) { void* d = nullptr; if (cudaMalloc(&d, cnt * sizeof(double)) != cudaSuccess) return false; p->owned.push_back(d); *q = (double*)d; return true; };
+    double *P = nullptr, *Q = nullptr;
+    bool ok = alloc(&P, 4 * n) && alloc(&Q, 4 * n);
+    for (int k = 0; k < 2 && ok; ++k) {
+        w[k].red = nullptr;
+        for (int c = 0; c < 2 && ok; ++c) {
+            w[k].p[c] = P + (2 * k + c) * n;
+            w[k].q[c] = Q + (2 * k + c) * n;
+            ok = alloc(&w[k].r[c], n) && alloc(&w[k].invc[c], n) && alloc(&w[k].pre[c], n);
+        }
+        ok = ok && alloc(&w[k].partials, SV_GRID * 2 + 4 * (size_t)(p->d.lmax + 1));
+        w[k].fuse_partials = nullptr;
+        ok = ok && alloc(&w[k].fuse_out, 4);
+        void* d = nullptr;
+        ok = ok && cudaMalloc(&d, sizeof(PcgState)) == cudaSuccess;
+        if (ok) { p->owned.push_back(d); w[k].state = (PcgState*)d; }
+        ok = ok && cudaMallocHost((void**)&w[k].host_state, sizeof(PcgState)) == cudaSuccess;
+    }
+    void* d = nullptr;
+    ok = ok && cudaMalloc(&d, sizeof(int)) == cudaSuccess;
+    if (ok) { p->owned.push_back(d); p->pcg_alldone = (int*)d; }
+    if (!ok) { gs_set_error("batched PCG workspace allocation failed: %s", cudaGetErrorString(cudaGetLastError())); delete[] w; return nullptr; }
+    p->pcg_ws_batch = w;
+    return w;
+}
+
 void gs_pcg_ws_free(gs_plan* p)
 {
     gs_pcg_ws* w = (gs_pcg_ws*)p->pcg_ws;
-    if (!w) return;
-    if (w->host_state) cudaFreeHost(w->host_state);   // the device buffers are in p->owned
-    delete w;
-    p->pcg_ws = nullptr;
+    if (w) {
+        if (w->host_state) cudaFreeHost(w->host_state);   // the device buffers are in p->owned
+        delete w;
+        p->pcg_ws = nullptr;
+    }
+    gs_pcg_ws* b = (gs_pcg_ws*)p->pcg_ws_batch;
+    if (b) {
+        for (int k = 0; k < 2; ++k) if (b[k].host_state) cudaFreeHost(b[k].host_state);
+        delete[] b;
+        p->pcg_ws_batch = nullptr;
+    }
 }
 
 int g_gs_fuse_apq = 0;   // 1: fused analysis-finish + (q += C^-1 p, <p, q>) kernel in the unsharded PCG (measured 0.4 % SLOWER
@@ -348,18 +388,20 @@ struct ActiveRings {   // scope guard: the plan's launchers use the active lists
 };
 
 // q = B A^T N^-1 A B v   (C^-1 v is added by pcg_apq_kernel / the caller)
+// nc = 2 (chain batch): chain c reads vE/vB + c stride and writes qE/qB + c stride; one recurrence serves both chains
 static int apply_noise_op(gs_plan* p, const double* vE, const double* vB, const double* bl, const double* inv_noise,
-                          double* qE, double* qB, cudaStream_t st, const int* skip, int spin = 2, const FinishFuse* fuse = nullptr)
+                          double* qE, double* qB, cudaStream_t st, const int* skip, int spin = 2, const FinishFuse* fuse = nullptr,
+                          int nc = 1, int64_t stride = 0)
 {
     int rc;
-    if ((rc = gs_leg_synth(p, spin, vE, vB, GS_ALM_REAL, bl, st, skip))) return rc;
-    if (g_gs_ring_fused) {
-        if ((rc = gs_ring_apply(p, spin, inv_noise, st, skip))) return rc;
+    if ((rc = gs_leg_synth(p, spin, vE, vB, GS_ALM_REAL, bl, st, skip, nullptr, nc, stride))) return rc;
+    if (g_gs_ring_fused || nc > 1) {
+        if ((rc = gs_ring_apply(p, spin, inv_noise, st, skip, nc))) return rc;
     } else {
         if ((rc = gs_ring_synth(p, spin, p->mapQ_tmp, p->mapU_tmp, st, skip))) return rc;
         if ((rc = gs_ring_anal(p, spin, p->mapQ_tmp, p->mapU_tmp, inv_noise, st, skip))) return rc;
     }
-    return gs_leg_anal(p, spin, qE, qB, GS_ALM_REAL, bl, 1.0, 0, st, skip, fuse);
+    return gs_leg_anal(p, spin, qE, qB, GS_ALM_REAL, bl, 1.0, 0, st, skip, fuse, nc, stride);
 }
 
 // spin 2: (E, B) system; spin 0: temperature (dl_BB, rhs_B, x_B unused)
@@ -462,6 +504,97 @@ extern "C" int gs_cr_pcg_pol(gs_plan* p, const double* dl_EE, const double* dl_B
     GS_REQUIRE(dl_EE && dl_BB && bl && inv_noise && rhs_E && rhs_B && x_E && x_B, "null pointer argument");
     return cr_pcg_impl(p, 2, dl_EE, dl_BB, bl, inv_noise, ninv_sum_over_4pi, rhs_E, rhs_B, x_E, x_B, warm_start, eps, itermax,
                        check_every, n_iter_out, resid_out, stream);
+}
+
+__global__ void pcg_alldone_kernel(const PcgState* a, const PcgState* b, int* out) { *out = (a->done && b->done) ? 1 : 0; }
+
+// Two independent chains (same data, beam and N^-1; their own D_l, right-hand sides and solutions, chain c at + c stride
+// doubles, dl at + c (L+1)) solved side by side: while both are iterating, every mat-vec is ONE chain-batched launch per stage
+// (leg_synth / ring_apply / leg_anal with two right-hand sides sharing the Legendre recurrence); the vector kernels, alpha,
+// beta and the stopping rule stay per chain, so each chain performs exactly the iterations of its own gs_cr_pcg_pol call.
+// When one chain has converged (seen at the next poll) the other continues on the single-chain kernels.
+extern "C" int gs_cr_pcg_pol_batch(gs_plan* p, int n_chain, const double* dl_EE, const double* dl_BB, const double* bl,
+                                   const double* inv_noise, double ninv_sum_over_4pi, const double* rhs_E,
+                                   const double* rhs_B, double* x_E, double* x_B, int64_t stride, double eps, int itermax,
+                                   int check_every, int* n_iter_out, double* resid_out, void* stream)
+{
+    if (!p) { gs_set_error("null plan"); return GS_E_BADARG; }
+    GS_REQUIRE(dl_EE && dl_BB && bl && inv_noise && rhs_E && rhs_B && x_E && x_B, "null pointer argument");
+    GS_REQUIRE(n_chain == 1 || n_chain == 2, "n_chain must be 1 or 2");
+    const int L = p->d.lmax;
+    if (n_chain == 1)
+        return cr_pcg_impl(p, 2, dl_EE, dl_BB, bl, inv_noise, ninv_sum_over_4pi, rhs_E, rhs_B, x_E, x_B, 0, eps, itermax, check_every,
+                           n_iter_out, resid_out, stream);
+    GS_REQUIRE(p->world == 1, "chain batches need an unsharded plan");
+    GS_REQUIRE(eps > 0.0 && itermax >= 0, "eps must be > 0 and itermax >= 0");
+    GS_CHECK_CUDA(cudaSetDevice(p->device));
+    int rc;
+    if ((rc = gs_plan_reserve_chains(p, 2))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    gs_pcg_ws* W = get_ws_batch(p);
+    if (!W) return GS_E_NOMEM;
+    const int64_t n = p->nreal_loc;
+    if (check_every < 1) check_every = 8;
+    const int lb = (L + 256) / 256;
+    ActiveRings act(p);
+    if ((rc = act.begin(inv_noise, st))) return rc;
+    for (int k = 0; k < 2; ++k) {
+        gs_pcg_ws* w = &W[k];
+        double* tmp_l = w->partials + SV_GRID * 2;
+        precond_kernel<<<lb, 256, 0, st>>>(dl_EE + k * (L + 1), bl, ninv_sum_over_4pi, L, tmp_l, tmp_l + (L + 1));
+        precond_kernel<<<lb, 256, 0, st>>>(dl_BB + k * (L + 1), bl, ninv_sum_over_4pi, L, tmp_l + 2 * (L + 1), tmp_l + 3 * (L + 1));
+        GS_CHECK_LAUNCH();
+        if ((rc = gs_plan_expand_per_l(p, tmp_l, 0, w->invc[0], st))) return rc;
+        if ((rc = gs_plan_expand_per_l(p, tmp_l + (L + 1), 0, w->pre[0], st))) return rc;
+        if ((rc = gs_plan_expand_per_l(p, tmp_l + 2 * (L + 1), 0, w->invc[1], st))) return rc;
+        if ((rc = gs_plan_expand_per_l(p, tmp_l + 3 * (L + 1), 0, w->pre[1], st))) return rc;
+        PcgState h;
+        memset(&h, 0, sizeof(h));
+        h.eps2 = eps * eps;
+        h.itermax = itermax;
+        *w->host_state = h;
+        GS_CHECK_CUDA(cudaMemcpyAsync(w->state, w->host_state, sizeof(PcgState), cudaMemcpyHostToDevice, st));
+        zero2_kernel<<<SV_GRID, SV_NT, 0, st>>>(x_E + k * stride, x_B + k * stride, n);
+        pcg_init_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, rhs_E + k * stride, rhs_B + k * stride, 0, n, 2);
+        GS_CHECK_LAUNCH();
+    }
+    pcg_alldone_kernel<<<1, 1, 0, st>>>(W[0].state, W[1].state, p->pcg_alldone);
+    const int64_t bstride = 2 * n;   // W[1].p[c] = W[0].p[c] + 2 n (get_ws_batch)
+    bool done[2] = {false, false};
+    int launched = 0;
+    while (!(done[0] && done[1]) && launched < itermax) {
+        for (int it = 0; it < check_every && launched < itermax; ++it, ++launched) {
+            if (!done[0] && !done[1]) {
+                if ((rc = apply_noise_op(p, W[0].p[0], W[0].p[1], bl, inv_noise, W[0].q[0], W[0].q[1], st, p->pcg_alldone, 2, nullptr, 2, bstride))) return rc;
+            } else {
+                gs_pcg_ws* w = &W[done[0] ? 1 : 0];
+                if ((rc = apply_noise_op(p, w->p[0], w->p[1], bl, inv_noise, w->q[0], w->q[1], st, &w->state->done, 2))) return rc;
+            }
+            for (int k = 0; k < 2; ++k) {
+                if (done[k]) continue;
+                pcg_apq_kernel<<<SV_GRID, SV_NT, 0, st>>>(W[k], n, 2);
+                pcg_update_kernel<<<SV_GRID, SV_NT, 0, st>>>(W[k], x_E + k * stride, x_B + k * stride, n, 2);
+                pcg_dir_kernel<<<SV_GRID, SV_NT, 0, st>>>(W[k], n, 2);
+                g_gs_launches += 3;
+            }
+            if (!done[0] && !done[1]) { pcg_alldone_kernel<<<1, 1, 0, st>>>(W[0].state, W[1].state, p->pcg_alldone); g_gs_launches += 1; }
+            GS_CHECK_LAUNCH();
+        }
+        for (int k = 0; k < 2; ++k) GS_CHECK_CUDA(cudaMemcpyAsync(W[k].host_state, W[k].state, sizeof(PcgState), cudaMemcpyDeviceToHost, st));
+        GS_CHECK_CUDA(cudaStreamSynchronize(st));
+        for (int k = 0; k < 2; ++k) done[k] = W[k].host_state->done != 0;
+    }
+    int ret = GS_OK;
+    for (int k = 0; k < 2; ++k) {
+        const PcgState& sdone = *W[k].host_state;
+        if (n_iter_out) n_iter_out[k] = sdone.iter;
+        if (resid_out) resid_out[k] = sdone.d0 > 0.0 ? sqrt(sdone.rr / sdone.d0) : 0.0;
+        if (sdone.d0 > 0.0 && sdone.rr > sdone.eps2 * sdone.d0) {
+            gs_set_error("PCG (chain %d of the batch) stopped at iter_max = %d with |r|/|r0| = %.3e > eps = %.1e", k, itermax, sqrt(sdone.rr / sdone.d0), eps);
+            ret = GS_E_NOTCONVERGED;
+        }
+    }
+    return ret;
 }
 
 // Temperature twin (qcinv opfilt_tt chain of ConstrainedRealization.py:40-41, run at CenteredGibbs.py:141-165 and
@@ -630,6 +763,42 @@ extern "C" int gs_profile_matvec(gs_plan* p, const double* x_E, const double* x_
     for (int i = 0; i < 4; ++i) ms_out[i] = (float)(acc[i] / nrep);
     if (g_gs_ring_fused) ms_out[2] = 0.0f;
     for (int i = 0; i < 5; ++i) cudaEventDestroy(ev[i]);
+    return rc;
+}
+
+// gs_profile_matvec for a chain batch: n_chain (1 or 2) right-hand sides at x / y + c stride (doubles) per launch; the fused ring
+// stage only.  ms_out[0] Legendre synthesis, [1] fused ring stage, [2] Legendre analysis + finish, each for the WHOLE batch.
+extern "C" int gs_profile_matvec_batch(gs_plan* p, int n_chain, const double* x_E, const double* x_B, int64_t stride,
+                                       const double* bl, const double* inv_noise, double* y_E, double* y_B, int nrep,
+                                       float* ms_out, void* stream)
+{
+    if (!p) { gs_set_error("null plan"); return GS_E_BADARG; }
+    GS_REQUIRE(x_E && x_B && bl && inv_noise && y_E && y_B && ms_out && nrep >= 1 && (n_chain == 1 || n_chain == 2), "bad arguments");
+    GS_CHECK_CUDA(cudaSetDevice(p->device));
+    int rc;
+    if (n_chain > 1 && (rc = gs_plan_reserve_chains(p, n_chain))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t ev[4];
+    for (int i = 0; i < 4; ++i) GS_CHECK_CUDA(cudaEventCreate(&ev[i]));
+    double acc[3] = {0, 0, 0};
+    rc = GS_OK;
+    {
+        ActiveRings act(p);
+        rc = act.begin(inv_noise, st);
+        for (int r = 0; r < nrep && rc == GS_OK; ++r) {
+            cudaEventRecord(ev[0], st);
+            rc = gs_leg_synth(p, 2, x_E, x_B, GS_ALM_REAL, bl, st, nullptr, nullptr, n_chain, stride);
+            cudaEventRecord(ev[1], st);
+            if (!rc) rc = gs_ring_apply(p, 2, inv_noise, st, nullptr, n_chain);
+            cudaEventRecord(ev[2], st);
+            if (!rc) rc = gs_leg_anal(p, 2, y_E, y_B, GS_ALM_REAL, bl, 1.0, 0, st, nullptr, nullptr, n_chain, stride);
+            cudaEventRecord(ev[3], st);
+            if (cudaEventSynchronize(ev[3]) != cudaSuccess) { gs_set_error("gs_profile_matvec_batch: %s", cudaGetErrorString(cudaGetLastError())); rc = GS_E_CUDA; break; }
+            for (int i = 0; i < 3; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); acc[i] += ms; }
+        }
+    }
+    for (int i = 0; i < 3; ++i) ms_out[i] = (float)(acc[i] / nrep);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
     return rc;
 }
 

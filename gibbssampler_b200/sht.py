@@ -145,3 +145,58 @@ class Plan:
         check(_lib.lib().gs_map2alm_spin2(self._h, _ptr(q), _ptr(u), _ptr(pixw), int(iter), int(bool(adjoint)),
                                           _ptr(fl), _ptr(e), _ptr(b), lay, _stream()))
         return e, b
+
+    # ------------------------------------------------------------------ chain batches (BASELINE config #5)
+    def alm2map_spin2_batch(self, almE, almB, fl=None):
+        """(Q, U) of n_chain right-hand sides at once: almE / almB are (n_chain, n) stacks (real layout, float64, or complex
+        healpy layout); two chains per launch share one Legendre recurrence (gs_alm2map_batch).  Returns (n_chain, npix) maps."""
+        e, b = almE.contiguous(), almB.contiguous()
+        assert e.dim() == 2 and e.shape == b.shape and e.dtype == b.dtype
+        k = e.shape[0]
+        lay = GS_ALM_REAL if e.dtype == torch.float64 else GS_ALM_COMPLEX
+        stride = e.shape[1] * (1 if lay == GS_ALM_REAL else 2)   # in doubles
+        q = torch.empty((k, self.npix), dtype=torch.float64, device=self.device)
+        u = torch.empty((k, self.npix), dtype=torch.float64, device=self.device)
+        check(_lib.lib().gs_alm2map_batch(self._h, 2, k, _ptr(e), _ptr(b), stride, lay, _ptr(self._fl(fl)), _ptr(q), _ptr(u),
+                                          self.npix, _stream()))
+        return q, u
+
+    def alm2map_batch(self, alm, fl=None):
+        """spin-0 twin of alm2map_spin2_batch."""
+        a = alm.contiguous()
+        assert a.dim() == 2
+        k = a.shape[0]
+        lay = GS_ALM_REAL if a.dtype == torch.float64 else GS_ALM_COMPLEX
+        stride = a.shape[1] * (1 if lay == GS_ALM_REAL else 2)
+        m = torch.empty((k, self.npix), dtype=torch.float64, device=self.device)
+        check(_lib.lib().gs_alm2map_batch(self._h, 0, k, _ptr(a), None, stride, lay, _ptr(self._fl(fl)), _ptr(m), None,
+                                          self.npix, _stream()))
+        return m
+
+    def map2alm_spin2_batch(self, q, u, adjoint=False, pixw=None, fl=None, real_layout=False):
+        """(E, B) of map2alm(iter=0) (adjoint=True: A^T) of (n_chain, npix) map stacks; (n_chain, n) alm stacks out."""
+        q, u = q.contiguous(), u.contiguous()
+        assert q.dim() == 2 and q.shape == u.shape and q.shape[1] == self.npix and q.dtype == torch.float64
+        k = q.shape[0]
+        lay = GS_ALM_REAL if real_layout else GS_ALM_COMPLEX
+        n = self.nreal if real_layout else self.nalm
+        dt = torch.float64 if real_layout else torch.complex128
+        e = torch.empty((k, n), dtype=dt, device=self.device)
+        b = torch.empty((k, n), dtype=dt, device=self.device)
+        stride = n * (1 if real_layout else 2)
+        check(_lib.lib().gs_map2alm_batch(self._h, 2, k, _ptr(q), _ptr(u), self.npix, _ptr(pixw), int(bool(adjoint)),
+                                          _ptr(self._fl(fl)), _ptr(e), _ptr(b), stride, lay, _stream()))
+        return e, b
+
+    def map2alm_batch(self, m, adjoint=False, pixw=None, fl=None, real_layout=False):
+        """spin-0 twin of map2alm_spin2_batch."""
+        m = m.contiguous()
+        assert m.dim() == 2 and m.shape[1] == self.npix and m.dtype == torch.float64
+        k = m.shape[0]
+        lay = GS_ALM_REAL if real_layout else GS_ALM_COMPLEX
+        n = self.nreal if real_layout else self.nalm
+        a = torch.empty((k, n), dtype=torch.float64 if real_layout else torch.complex128, device=self.device)
+        stride = n * (1 if real_layout else 2)
+        check(_lib.lib().gs_map2alm_batch(self._h, 0, k, _ptr(m), None, self.npix, _ptr(pixw), int(bool(adjoint)),
+                                          _ptr(self._fl(fl)), _ptr(a), None, stride, lay, _stream()))
+        return a

@@ -54,6 +54,11 @@ int gs_version(void);
  * hp.alm2map / hp.map2alm rebuild on every call.  Synchronous. */
 int gs_plan_create(gs_plan** plan, int nside, int lmax, int device);
 int gs_plan_destroy(gs_plan* plan);
+/* Chain batches (gs_plan_create(nside, lmax, n_chain, ...); BASELINE config #5 "batched over chains"): sizes the
+ * plan's ring-spectra and partial-sum workspaces for n_chain (1 or 2) right-hand sides per launch.  The reference runs one
+ * chain per process (SLURM array, job-script.sh:6), every chain repeating the Legendre recurrences of hp.alm2map / hp.map2alm;
+ * a batch shares them.  Unsharded plans only; called implicitly by the *_batch entry points. */
+int gs_plan_reserve_chains(gs_plan* plan, int n_chain);
 int gs_plan_nside(const gs_plan* plan);
 int gs_plan_lmax(const gs_plan* plan);
 int64_t gs_plan_npix(const gs_plan* plan);
@@ -86,6 +91,18 @@ int gs_map2alm_spin0(gs_plan* plan, const double* map, const double* pixw, int i
 int gs_map2alm_spin2(gs_plan* plan, const double* mapQ, const double* mapU, const double* pixw,
                      int iter, int adjoint, const double* fl, double* almE, double* almB,
                      int layout, void* stream);
+
+/* n_chain independent right-hand sides per call (hp.alm2map / hp.map2alm of n_chain chains that the reference runs as
+ * separate processes): chain c reads / writes alm + c alm_stride and map + c map_stride (strides in doubles; spin 0 ignores
+ * almB / mapU).  Chains are transformed two per launch and the two share ONE Legendre recurrence per (ring pair, m)
+ * (4 + 8 K DFMA per ring pair and multipole for K = 2 chains instead of 12 K).  Results equal n_chain single calls.
+ * gs_map2alm_batch is map2alm(iter = 0) (adjoint != 0: A^T, weight 1); pixw (nullable) multiplies the pixels of every chain. */
+int gs_alm2map_batch(gs_plan* plan, int spin, int n_chain, const double* almE, const double* almB,
+                     int64_t alm_stride, int layout, const double* fl, double* mapQ, double* mapU,
+                     int64_t map_stride, void* stream);
+int gs_map2alm_batch(gs_plan* plan, int spin, int n_chain, const double* mapQ, const double* mapU,
+                     int64_t map_stride, const double* pixw, int adjoint, const double* fl, double* almE,
+                     double* almB, int64_t alm_stride, int layout, void* stream);
 
 /* ---- harmonic-space array utilities (all device pointers) ------------------------------ */
 /* utils.real_to_complex (utils.py:49-60) / variance_expension.real_to_complex (.pyx:84-100) */
@@ -144,6 +161,15 @@ int gs_cr_pcg_pol(gs_plan* plan, const double* dl_EE, const double* dl_BB, const
                   const double* inv_noise, double ninv_sum_over_4pi, const double* rhs_E,
                   const double* rhs_B, double* x_E, double* x_B, int warm_start, double eps,
                   int itermax, int check_every, int* n_iter_out, double* resid_out, void* stream);
+
+/* gs_cr_pcg_pol (cold start) for n_chain = 1 or 2 independent chains on the same data (what n_chain processes of the
+ * reference each do at CenteredGibbs.py:486-488): chain c uses dl_* + c (L+1) and rhs / x + c stride (doubles).  While both
+ * chains iterate, every mat-vec is one chain-batched launch per stage (shared Legendre recurrence); alpha, beta and the
+ * stopping rule stay per chain, so each chain runs the iterations of its own single solve (n_iter_out[c], resid_out[c]). */
+int gs_cr_pcg_pol_batch(gs_plan* plan, int n_chain, const double* dl_EE, const double* dl_BB, const double* bl,
+                        const double* inv_noise, double ninv_sum_over_4pi, const double* rhs_E,
+                        const double* rhs_B, double* x_E, double* x_B, int64_t stride, double eps, int itermax,
+                        int check_every, int* n_iter_out, double* resid_out, void* stream);
 
 /* y = Q x (qcinv opfilt_pp.fwd_op; CenteredGibbs.py:629, 653). */
 int gs_cr_apply_q_pol(gs_plan* plan, const double* dl_EE, const double* dl_BB, const double* bl,
@@ -372,6 +398,11 @@ long long gs_launch_count(void);
 int gs_profile_matvec(gs_plan* plan, const double* x_E, const double* x_B, const double* bl,
                       const double* inv_noise, double* y_E, double* y_B, int nrep, float* ms_out,
                       void* stream);
+/* gs_profile_matvec for a chain batch (n_chain = 1 or 2 right-hand sides at x / y + c stride doubles, one launch per stage, fused
+ * ring stage): ms_out[0] Legendre synthesis, [1] ring stage, [2] Legendre analysis + finish, each for the whole batch. */
+int gs_profile_matvec_batch(gs_plan* plan, int n_chain, const double* x_E, const double* x_B, int64_t stride,
+                            const double* bl, const double* inv_noise, double* y_E, double* y_B, int nrep,
+                            float* ms_out, void* stream);
 /* Average duration (ms, CUDA events on `stream`) of the three vector kernels of one PCG iteration of gs_cr_pcg_pol
  * (spin = 2) / gs_cr_pcg_tt (spin = 0) on the plan's own zero-filled workspace: ms_out[0]  q += C^-1 p with <p, q>
  * (4 arrays of 8 n bytes per field), [1]  x += alpha p, r -= alpha q with <r, r>, <r, M r>  (7 arrays), [2]  p = M r +
