@@ -382,8 +382,25 @@ def workload_config(args):
 
 
 def run_sharded(args):
+    """BASELINE config #4 as its own run (--mode sharded): see sharded_measure."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = sharded_measure(args.nside, args.lmax, args.steps, args.warmup)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def sharded_measure(nside, lmax, steps, warmup):
     """BASELINE config #4: a single CenteredGibbs chain with the m-sharded SHT (NCCL all-to-all ring<->m transpose)
-    over all ranks; strong scaling, value = iterations/s of that one chain."""
+    over all ranks of the (already initialised) process group; strong scaling, value = iterations/s of that one chain.
+    Returns the JSON object on rank 0, None elsewhere."""
     import torch
     import torch.distributed as dist
     from gibbssampler_b200 import _dev, _lib, utils
@@ -391,14 +408,14 @@ def run_sharded(args):
     from gibbssampler_b200.sharded import ShardedPlan
     from gibbssampler_b200.sht import Plan
 
+    class A:
+        pass
+    args = A()
+    args.nside, args.lmax, args.steps, args.warmup = nside, lmax, steps, warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    nside, lmax = args.nside, args.lmax
     npix, nre = 12 * nside * nside, (lmax + 1) ** 2
     L = _lib.lib()
     plan = ShardedPlan(nside, lmax) if world > 1 else Plan.get(nside, lmax)
@@ -465,6 +482,13 @@ def run_sharded(args):
     if world > 1:
         dist.all_reduce(st, op=dist.ReduceOp.MAX)
     st = [float(x) for x in st.tolist()]
+    a2a_ms = C.c_float(0.0)
+    if world > 1:
+        _lib.check(L.gs_profile_exchange(plan._h, 10, C.byref(a2a_ms), _dev.stream()))
+    a2a = torch.tensor([a2a_ms.value], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(a2a, op=dist.ReduceOp.MAX)
+    a2a_ms = float(a2a.item())
     its = pcg_its[args.warmup:]
     n_pcg = int(round(float(np.mean(its)))) if its else 0
     nring = 4 * nside - 1
@@ -482,13 +506,14 @@ def run_sharded(args):
                        "l2_policy": "inputs larger than L2"},
             "pcg_iterations_mean": n_pcg, "gpu_launches": launches, "sht_pair_ms": sum(st), "sht_pairs_per_s": 1e3 / sum(st),
             "stage_ms": {"leg_synth+a2a": st[0], "ring_synth": st[1], "ring_anal": st[2], "a2a+leg_anal": st[3]},
-            "legendre_tflops_all_gpus": 2 * f2 / ((st[0] + st[3]) * 1e-3) * 1e-12,
+            "a2a_ms_alone": a2a_ms, "legendre_ms_without_a2a": {"leg_synth": st[0] - a2a_ms, "leg_anal": st[3] - a2a_ms},
+            "exposed_communication_fraction_of_pair": 2 * a2a_ms / sum(st) if sum(st) > 0 else None,
+            "legendre_tflops_all_gpus": 2 * f2 / (max(st[0] + st[3] - 2 * a2a_ms, 1e-9) * 1e-3) * 1e-12,
             "a2a_bytes_sent_per_gpu_per_transform": exch_bytes,
             "clocks": clocks.summary(), "pcg_iterations_per_step": its,
         }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        return line
+    return None
 
 
 def main():
@@ -502,6 +527,8 @@ def main():
     ap.add_argument("--pcg-iters", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-chain-batch", action="store_true", help="skip the secondary measurement with two chains per GPU")
+    ap.add_argument("--no-config4", action="store_true", help="N >= 2: skip the m-sharded single-chain measurement (BASELINE config #4)")
+    ap.add_argument("--config4-nside", type=int, default=2048)
     ap.add_argument("--sampler", default="pncp", choices=["pncp", "centered"],
                     help="pncp (default): BASELINE config #3, partially non-centred polarised masked-sky sampler = PCG constrained "
                          "realization + low-l inverse-gamma draw + high-l blocked Metropolis sweep; centered: CenteredGibbs "
@@ -787,13 +814,23 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_baseline_sample(args, n_pcg, n_blocks)
 
+    # ---- BASELINE config #4 on the same ranks (N >= 2): ONE chain at NSIDE 2048 / lmax 4096 whose SHTs are m-sharded over
+    # the GPUs with an NCCL all-to-all ring <-> m transpose (strong scaling); reported next to the chains-per-GPU value
+    config4 = None
+    if world > 1 and not args.no_config4:
+        try:
+            torch.cuda.empty_cache()
+            config4 = sharded_measure(args.config4_nside, 2 * args.config4_nside, 2, 1)
+        except Exception as e:   # the headline measurement above stands on its own
+            config4 = {"error": "%s: %s" % (type(e).__name__, e)} if rank == 0 else None
+
     if rank == 0:
         line = {
             "metric": "gibbs_iters_per_s", "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args), "pcg_iterations_mean": n_pcg,
             "e2e": {"value": e2e_val, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "chain_batch": chain_batch,
+            "gpu_launches": launches, "chain_batch": chain_batch, "config4_m_sharded": config4,
             "sht_pairs_per_s": world * 1e3 / pair_ms_max, "sht_pair_ms": pair_ms_max, "stage_ms": stage_ms,
             "pcg_matvec": {"ms": sum(matvec_ms.values()), "stage_ms": matvec_ms, "active_ring_pairs": act.value, "ring_pairs": tot.value,
                            "note": "mat-vec of the PCG: ring pairs wholly inside the mask (N^-1 = 0) are skipped, exact"},

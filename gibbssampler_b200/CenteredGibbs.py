@@ -283,6 +283,30 @@ class CenteredGibbs(GibbsSampler):
             pix_map, noise_temp, noise_pol, self.bl_map, lmax, Npix, beam, mask_path=mask_path, gibbs_cr=gibbs_cr,
             overrelaxation=overrelaxation, ula=ula, mask=mask, rng=cr_rng, plan=plan)
 
+    def run_fused(self, dls_init, use_graph=True):
+        """run() for the full-sky isotropic-noise polarised chain (BASELINE config #1) in ONE C call: the whole loop of
+        GibbsSampler.run_polarization (GibbsSampler.py:118-180) stays on the device (gs_gibbs_run_centered_fullsky: three kernels
+        per iteration, captured once in a CUDA graph and replayed).  Same return tuple as run(); the per-iteration timing lists
+        hold the mean.  Philox draws only (numpy-stream parity is what run() is for)."""
+        import time
+        cr = self.constrained_sampler
+        if not self.polarization or cr.masked or cr.d_E is None or cr.plan.world > 1 or cr.rng.mode != "philox":
+            raise _lib.GibbsB200Error("run_fused: polarised full-sky chain with harmonic data (pix_map['EE'/'BB']) and Philox draws only")
+        bins = {k: torch.as_tensor(np.asarray(self.bins[k]), dtype=torch.int32, device=cr.dev) for k in ("EE", "BB")}
+        nb = {k: bins[k].numel() - 1 for k in bins}
+        init = {k: f64(dls_init[k]).contiguous() for k in ("EE", "BB")}
+        hist = {k: torch.empty((self.n_iter + 1, nb[k]), dtype=torch.float64, device=cr.dev) for k in bins}
+        cr.rng.counter += 1
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        check(_lib.lib().gs_gibbs_run_centered_fullsky(self.lmax, cr.Npix, cr.noise_pol0, ptr(cr.bl_gauss_d), ptr(cr.d_E), ptr(cr.d_B),
+                                                       ptr(bins["EE"]), nb["EE"], ptr(bins["BB"]), nb["BB"], ptr(init["EE"]), ptr(init["BB"]),
+                                                       int(self.n_iter), ((cr.rng.seed << 8) + cr.rng.counter) & 0xFFFFFFFFFFFFFFFF, ptr(hist["EE"]), ptr(hist["BB"]),
+                                                       None, None, 1 if use_graph else 0, stream()))
+        dt = (time.perf_counter() - t0) / max(1, self.n_iter)
+        h = {k: hist[k].cpu().numpy() for k in hist}
+        return h, np.ones(self.n_iter), np.full(self.n_iter, 0.5 * dt), np.full(self.n_iter, 0.5 * dt)
+
 
 def sample_mask_batch(crs, dls_list, xis=None):
     """sample_mask (CenteredGibbs.py:448-491) of TWO independent chains on the same data in one batched solve: every chain

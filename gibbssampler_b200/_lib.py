@@ -54,6 +54,8 @@ SIGNATURES = {
     "gs_cr_rhs_tt": (_i, [_vp] * 9 + [_i, _vp, _vp]),
     "gs_cr_pcg_tt": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _vp, _i, _d, _i, _i, C.POINTER(_i), C.POINTER(_d), _vp]),
     "gs_cr_apply_q_tt": (_i, [_vp] * 7),
+    "gs_gibbs_run_centered_fullsky": (_i, [_i, _i64, _d, _vp, _vp, _vp, _vp, _i, _vp, _i, _vp, _vp, _i, C.c_uint64, _vp, _vp, _vp, _vp,
+                                           _i, _vp]),
     "gs_cr_direct": (_i, [_vp, _vp, _vp, _vp, _d, _i, _i, _vp, _vp]),
     "gs_cr_direct_pix": (_i, [_vp, _vp, _vp, _vp, _d, _i, _i, _i, _vp, _vp]),
     "gs_cls_invgamma": (_i, [_vp, _vp, _i, _vp, C.c_uint64, C.c_uint64, _vp, _vp, _vp, _vp]),
@@ -101,6 +103,7 @@ SIGNATURES = {
     "gs_shard_allreduce_sum": (_i, [_vp, _vp, _i, _vp]),
     "gs_launch_count": (C.c_longlong, []),
     "gs_profile_matvec": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, C.POINTER(C.c_float), _vp]),
+    "gs_profile_exchange": (_i, [_vp, _i, C.POINTER(C.c_float), _vp]),
     "gs_profile_matvec_batch": (_i, [_vp, _i, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, C.POINTER(C.c_float), _vp]),
     "gs_measure_fp64_peak": (_i, [C.POINTER(_d), _vp]),
     "gs_profile_pcg_vectors": (_i, [_vp, _i, _i, C.POINTER(C.c_float), _vp]),

@@ -313,6 +313,30 @@ int gs_shard_exchange(gs_plan* p, const double2* send, double2* recv, cudaStream
     return GS_OK;
 }
 
+// Average duration (ms, CUDA events on `stream`) of ONE ring <-> m all-to-all of the plan's spectra buffers, timed alone
+// (collective: every rank calls it with the same nrep).  bench.py reports it next to the Legendre stages of config #4.
+extern "C" int gs_profile_exchange(gs_plan* p, int nrep, float* ms_out, void* stream)
+{
+    if (!p) { gs_set_error("null plan"); return GS_E_BADARG; }
+    GS_REQUIRE(ms_out && nrep >= 1, "bad arguments");
+    if (p->world <= 1) { *ms_out = 0.0f; return GS_OK; }
+    GS_CHECK_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    GS_CHECK_CUDA(cudaEventCreate(&e0));
+    GS_CHECK_CUDA(cudaEventCreate(&e1));
+    int rc = gs_shard_exchange(p, p->Fm, p->Fx, st);   // warm-up
+    cudaEventRecord(e0, st);
+    for (int r = 0; r < nrep && rc == GS_OK; ++r) rc = gs_shard_exchange(p, p->Fm, p->Fx, st);
+    cudaEventRecord(e1, st);
+    if (rc == GS_OK && cudaEventSynchronize(e1) != cudaSuccess) { gs_set_error("gs_profile_exchange: %s", cudaGetErrorString(cudaGetLastError())); rc = GS_E_CUDA; }
+    float ms = 0.0f;
+    if (rc == GS_OK) cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out = ms / nrep;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
+}
+
 int gs_shard_allreduce(gs_plan* p, double* buf, int n, cudaStream_t st)
 {
     if (p->lgroup) return local_allreduce(p, buf, n, st);

@@ -348,6 +348,19 @@ int gs_cls_invwishart(const double* cl_tt, const double* cl_te, const double* cl
                       const double* inject, uint64_t seed, uint64_t call, double* out_tt, double* out_te,
                       double* out_ee, void* stream);
 
+/* ---- whole chain in one call (SURVEY.md 8b gs_gibbs_step_centered; BASELINE config #1) -----------------------------------
+ * GibbsSampler.run_polarization (GibbsSampler.py:118-180) for the full-sky isotropic-noise centred sampler: every iteration is
+ * PolarizedCenteredConstrainedRealization.sample_no_mask (CenteredGibbs.py:317-353) + PolarizedCenteredClsSampler.sample
+ * (CenteredGibbs.py:54-93) + utils.unfold_bins, run as three kernels that take the iteration number from device memory; the
+ * iteration is captured once in a CUDA graph (use_graph != 0) and replayed n_iter times.  d_E / d_B = pix_map["EE"/"BB"] (real
+ * layout), bins_* = nbins_* + 1 int32 edges, init_* = binned D_l of the start.  hist_* receive [n_iter + 1][nbins_*] binned D_l
+ * (row 0 = init), last_E / last_B (nullable) the last sky map.  Philox draws (seed); synchronous on return. */
+int gs_gibbs_run_centered_fullsky(int lmax, int64_t npix, double noise_pol, const double* bl, const double* d_E,
+                                  const double* d_B, const int* bins_EE, int nbins_EE, const int* bins_BB, int nbins_BB,
+                                  const double* init_EE, const double* init_BB, int n_iter, uint64_t seed,
+                                  double* hist_EE, double* hist_BB, double* last_E, double* last_B, int use_graph,
+                                  void* stream);
+
 /* ---- m-sharded transforms over the GPUs of one node (BASELINE config #4) --------------
  * The reference has no multi-GPU transform (one chain per SLURM task, job-script.sh:6); this is the
  * single-chain strategy for NSIDE >= 1024.  Rank r of `world` owns the m pairs {j, L-j} with j mod world = r
@@ -387,6 +400,10 @@ int gs_shard_expand_per_l(gs_plan* plan, const double* x, int mode, double* out,
 int gs_shard_alm2cl(gs_plan* plan, const double* alm_local, double* cl, void* stream);
 /* In-place sum over the ranks of the plan of n device doubles. */
 int gs_shard_allreduce_sum(gs_plan* plan, double* buf, int n, void* stream);
+
+/* Average duration (ms) of one ring <-> m all-to-all of a sharded plan's spectra buffers, timed alone with CUDA events on
+ * `stream` (collective: every rank calls it; 0 on unsharded plans).  bench.py reports it for BASELINE config #4. */
+int gs_profile_exchange(gs_plan* plan, int nrep, float* ms_out, void* stream);
 
 /* ---- measurement helpers used by bench.py ------------------------------------------------ */
 /* Number of kernels this library has launched so far in the SHT stages and PCG vector updates. */

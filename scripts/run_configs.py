@@ -65,6 +65,18 @@ def main():
     print(json.dumps({"config": 1, "workload": "CenteredGibbs full-sky isotropic noise (direct solve + inverse-gamma draw)", "nside": nside,
                       "lmax": lmax, "iterations": n_iter, "seconds": dt, "it_per_s": n_iter / dt,
                       "posterior_mean_DEE_l50": float(h["EE"][200:, 50].mean()), "input_DEE_l50": float(dlE[50])}), flush=True)
+    # the same chain in ONE C call (gs_gibbs_run_centered_fullsky: the iteration as a replayed CUDA graph)
+    g.run_fused(binned(bins, dlE, dlB))   # warm-up
+    for use_graph in (True, False):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h = g.run_fused(binned(bins, dlE, dlB), use_graph=use_graph)[0]
+        dt = time.perf_counter() - t0
+        print(json.dumps({"config": 1, "workload": "same chain through CenteredGibbs.run_fused (one C call, %s)" % ("CUDA graph replayed per iteration" if use_graph else "plain launches"),
+                          "nside": nside, "lmax": lmax, "iterations": n_iter, "seconds": dt, "it_per_s": n_iter / dt, "us_per_iteration": 1e6 * dt / n_iter,
+                          "posterior_mean_DEE_l50": float(h["EE"][200:, 50].mean()), "input_DEE_l50": float(dlE[50])}), flush=True)
+    if len(sys.argv) > 2 and sys.argv[2] == "config1":
+        return
     # ---- config #2
     nside, lmax, fwhm = 256, 512, 1.0
     pix_map, mask, nv, dlE, dlB, bl = sky(nside, lmax, True, fwhm)
