@@ -156,18 +156,21 @@ def test_masked_chains_agree_centered_asis_pncp():
 
 
 def test_masked_chains_agree_centered_pncp_nside16():
-    """The same check at NSIDE 16 / lmax 32 (3072 pixels, 1089 coefficients per field, fractional mask edge): the polarised
-    masked PNCP sampler (l_cut = 4, fifteen two-bin Metropolis blocks per spectrum) and CenteredGibbs target the same posterior; means of
-    log D_l over the chains agree within 5 sigma of the ESS-corrected Monte-Carlo error for low, mid and high multipoles."""
+    """The same check at NSIDE 16 / lmax 32 (3072 pixels, 1089 coefficients per field, fractional mask edge) with the noise level
+    chosen so that the signal-to-noise ratio per multipole falls from ~20 at l = 4 through ~1 at l = 16 to 0.1 at l = 32 -- the regime
+    the partially non-centred parametrisation is made for: l < l_cut = 12 centred (inverse-gamma draw), l >= 12 non-centred
+    (Metropolis blocks of three bins).  PNCP and CenteredGibbs target the same posterior: means of log D_l agree within 5 sigma of
+    the ESS-corrected Monte-Carlo error at low, mid and high multipoles."""
     from gibbssampler_b200.CenteredGibbs import CenteredGibbs
     from gibbssampler_b200.PNCP import PNCPGibbs
-    nside, lmax = 16, 32
+    nside, lmax, l_cut = 16, 32, 12
     npix, n = 12 * nside ** 2, (lmax + 1) ** 2
     rng = np.random.default_rng(16)
     ell = np.arange(lmax + 1)
     dl_true = np.where(ell >= 2, 1.0, 0.0)
-    fwhm, noise0 = 4.0, 0.05
-    bl_map = R.expand_per_l(O.gauss_beam(np.radians(fwhm), lmax))
+    fwhm, noise0 = 4.0, 5.0
+    bl = O.gauss_beam(np.radians(fwhm), lmax)
+    bl_map = R.expand_per_l(bl)
     th, ph = O.pix_angles(nside)
     mask = np.clip((np.abs(np.cos(th)) - 0.2) / 0.1, 0.0, 1.0)      # band mask with a fractional edge (ud_grade-like values)
     sE = rng.standard_normal(n) * np.sqrt(R.generate_var_cl(dl_true))
@@ -175,24 +178,25 @@ def test_masked_chains_agree_centered_pncp_nside16():
     q, u = R.synth_pol(sE * bl_map, sB * bl_map, nside, lmax)
     pix_map = {"Q": (q + rng.standard_normal(npix) * np.sqrt(noise0)) * mask, "U": (u + rng.standard_normal(npix) * np.sqrt(noise0)) * mask}
     bins = {"EE": np.arange(0, lmax + 2), "BB": np.arange(0, lmax + 2)}
-    var_l = 2.0 / ((2 * ell + 1) * 0.75)
-    pv = {"EE": 0.25 * var_l[2:], "BB": 0.25 * var_l[2:]}
+    nl = noise0 * 4 * np.pi / npix * ell * (ell + 1) / (2 * np.pi) / bl ** 2          # noise power in D_l units
+    var_l = 2.0 / ((2 * ell + 1) * 0.75) * (1.0 + nl) ** 2
+    pv = {"EE": 0.3 * var_l[2:], "BB": 0.3 * var_l[2:]}
     nt, npol = np.full(npix, 1.0), np.full(npix, noise0)
     init = {"EE": dl_true.copy(), "BB": dl_true.copy()}
-    n_iter, burn = 1500, 200
+    n_iter, burn = 2000, 300
     cg = CenteredGibbs(pix_map, nt, npol, fwhm, nside, lmax, npix, mask=mask, polarization=True, bins=bins, n_iter=n_iter, seed=31)
     cg.constrained_sampler.pcg_accuracy = 1e-7
     hc = cg.run(init)[0]
-    edges = list(range(4, lmax + 1, 2)) + [lmax + 1]     # two bins per Metropolis block
+    edges = list(range(l_cut, lmax + 1, 3)) + [lmax + 1]
     blocks_p = {"EE": edges, "BB": list(edges)}
-    pn = PNCPGibbs(pix_map, nt, fwhm, nside, lmax, npix, pv, 4, metropolis_blocks=blocks_p, polarization=True, bins=bins, n_iter=n_iter,
+    pn = PNCPGibbs(pix_map, nt, fwhm, nside, lmax, npix, pv, l_cut, metropolis_blocks=blocks_p, polarization=True, bins=bins, n_iter=n_iter,
                    noise_Q=npol, mask=mask, seed=32)
     pn.constrained_sampler.pcg_accuracy = 1e-7
     hp_, acc = pn.run(init)[:2]
     rate = np.mean([np.mean(np.asarray(acc[p], dtype=float)) for p in ("EE", "BB")])
-    assert 0.05 < rate < 0.95, rate       # the Metropolis blocks move
+    assert 0.1 < rate < 0.95, rate       # the Metropolis blocks move
     for pol in ("EE", "BB"):
-        for l in (2, 3, 6, 12, 20, 32):
+        for l in (2, 3, 6, 11, 12, 16, 20, 26, 32):
             a, b = np.log(hc[pol][burn:, l]), np.log(hp_[pol][burn:, l])
             se = np.sqrt(a.var() / ess(a) + b.var() / ess(b))
-            assert abs(a.mean() - b.mean()) < 5 * se, (pol, l, a.mean(), b.mean(), se)
+            assert abs(a.mean() - b.mean()) < 5 * se, (pol, l, a.mean(), b.mean(), se, rate)
