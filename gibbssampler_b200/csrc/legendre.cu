@@ -18,6 +18,7 @@
 // reduce-scatter (9 SHFL.64 per two l for 8 values), then a shared-memory sum over the warps of
 // the block and one deterministic partial per 256-ring-pair chunk, combined by leg_finish_kernel.
 #include <algorithm>
+#include <type_traits>
 
 #include "gs_internal.h"
 
@@ -52,6 +53,9 @@
 #endif               // at a time, to a sum through shared memory (needs LEG_FOLD2)
 #define FOLD3_NB 8
 #define FULL 0xffffffffu
+#ifndef LEG_CHK
+#define LEG_CHK 4     // pairs of l between two looks at which ring groups of a warp have come alive (transition phase)
+#endif
 #ifdef LEG_XNOBAR      // EXPERIMENT ONLY (wrong results): tile-loop barriers of the synthesis / analysis kernels become warp barriers,
 #define TILE_SYNC() __syncwarp()   // to measure what the CTA-wide barriers cost
 #else
@@ -193,6 +197,27 @@ __device__ __forceinline__ void rescale_check(RingState<SPIN>& s)
     }
 }
 
+// lambda still negligible on this ring: range-extension scale pending, or both chains below 2^LEG_SMALL_EXP.  libsharp starts to
+// accumulate a ring once |lambda| passes sharp_ftol = 2^-60 (sharp_core_inc.c, iter_to_ieee): on the evanescent side of
+// l ~ m / sin(theta) lambda_lm grows by orders of magnitude per few multipoles, and a term below 2^-60 of the largest one cannot
+// reach the last bit of the sum.  The chains here are mu = lambda / alpha_l with alpha_l = O(1..1e-2), and the threshold is kept
+// 2^90 below libsharp's; the test is an integer compare of the exponent field (no FP64 instruction).
+// Between two looks (LEG_CHK pairs of l = 8 multipoles) a chain grows by at most ~2^35 (the ratio mu_{l+1} / mu_l is about
+// a_l cos(theta) <= sqrt(2 m / (l - m)) right after l = m and falls to ~2 quickly), so a ring that was below 2^-150 at the last
+// look has not passed 2^-115 before the next one.  Measured effect at NSIDE 512: 1-3 % of a single-chain transform, 4 % of a
+// chain batch (the skipped accumulations are the larger share there).
+#ifndef LEG_SMALL_EXP
+#define LEG_SMALL_EXP (-150)
+#endif
+template <int SPIN>
+__device__ __forceinline__ bool ring_dead(const RingState<SPIN>& s)
+{
+    constexpr int thr = (1023 + LEG_SMALL_EXP) << 20;
+    bool small = (__double2hiint(s.pc) & 0x7fffffff) < thr;
+    if (SPIN) small = small && (__double2hiint(s.mc) & 0x7fffffff) < thr;
+    return s.sc > 0 || small;
+}
+
 // ------------------------------------------------------------------ staging of one l-tile
 // Each thread fetches the (pre-scaled) a_lm pair and the recurrence coefficients of ONE l of the tile into
 // registers (LEG_TL == LEG_NT); the values are stored to the other half of a double-buffered shared-memory
@@ -321,6 +346,7 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
     SynthAcc<SPIN> acc[R][NC];
     int pj[R];
     bool any_act = false;
+    unsigned myact = 0;   // bit j: ring pair j of this thread reaches m
 #pragma unroll
     for (int j = 0; j < R; ++j) {
         const int k = chunk + ((tid >> 5) * R + j) * 32 + (tid & 31);   // warp-major: a warp owns 32 R consecutive pairs, so idle slots fill whole warps
@@ -336,9 +362,14 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
             st[j].x = P.cth[p];
             seed_ring<SPIN>(P, p, m, st[j].pc, st[j].mc, st[j].sc);
             any_act = true;
+            myact |= 1u << j;
         }
     }
     const bool warp_act = __any_sync(FULL, any_act);
+    unsigned gact = 0;          // 32-ring groups of this warp that hold at least one ring reaching this m
+#pragma unroll
+    for (int j = 0; j < R; ++j) if (__any_sync(FULL, (myact >> j) & 1u)) gact |= 1u << j;
+    bool all_live = false;      // set once every group accumulates and no range-extension scale is pending: fast loop from then on
 
 #pragma unroll
     for (int u = 0; u < LEG_SU; ++u) {
@@ -364,46 +395,75 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
         const int ni = warp_act ? min(LEG_TLS, L - lt + 1) : 0;
         const int npr = (ni + 1) >> 1;
         int ip = 0;
-        // (A) every lane still below range: recurrence only
-        while (ip < npr) {
-            bool alls = true;
-#pragma unroll
-            for (int j = 0; j < R; ++j) alls = alls && (st[j].sc > 0 || st[j].pc == 0.0);
-            if (!__all_sync(FULL, alls)) break;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const double2 r = sR[2 * ip + h];
-#pragma unroll
-                for (int j = 0; j < R; ++j) { rec_step<SPIN>(st[j], r.x, r.y); rescale_check<SPIN>(st[j]); }
-            }
-            ++ip;
-        }
-        // (B) mixed: predicated accumulation + range checks
-        while (ip < npr) {
+        // (A/B) until every 32-ring group of the warp accumulates.  Groups come alive one after the other, equator side (high j)
+        // first.  Every LEG_CHK pairs of l the warp finds the lowest group with a ring that is no longer negligible (ring_dead)
+        // and runs the next pairs with the groups below it on the recurrence only (4 instead of 12 DFMA per ring pair and l;
+        // no checks inside).  Lanes with a pending range-extension scale (seeds below 2^-644) take the checked path pair by pair.
+        while (ip < npr && !all_live) {
             bool anys = false;
 #pragma unroll
             for (int j = 0; j < R; ++j) anys = anys || st[j].sc > 0;
-            if (!__any_sync(FULL, anys)) break;
+            if (__any_sync(FULL, anys)) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int i = 2 * ip + h;
-                const double2 r = sR[i];
-                double2 e[NC], b[NC];
+                for (int h = 0; h < 2; ++h) {
+                    const int i = 2 * ip + h;
+                    const double2 r = sR[i];
+                    double2 e[NC], b[NC];
 #pragma unroll
-                for (int c = 0; c < NC; ++c) { e[c] = sE[c][i]; b[c] = SPIN ? sB[c][i] : e[c]; }
+                    for (int c = 0; c < NC; ++c) { e[c] = sE[c][i]; b[c] = SPIN ? sB[c][i] : e[c]; }
 #pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const double pc = st[j].sc ? 0.0 : st[j].pc, mc = st[j].sc ? 0.0 : st[j].mc;
+                    for (int j = 0; j < R; ++j) {
+                        const double pc = st[j].sc ? 0.0 : st[j].pc, mc = st[j].sc ? 0.0 : st[j].mc;
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) {
-                        if (h == 0) synth_acc<SPIN, true>(acc[j][c], pc, mc, e[c], b[c]);
-                        else synth_acc<SPIN, false>(acc[j][c], pc, mc, e[c], b[c]);
+                        for (int c = 0; c < NC; ++c) {
+                            if (h == 0) synth_acc<SPIN, true>(acc[j][c], pc, mc, e[c], b[c]);
+                            else synth_acc<SPIN, false>(acc[j][c], pc, mc, e[c], b[c]);
+                        }
+                        rec_step<SPIN>(st[j], r.x, r.y);
+                        rescale_check<SPIN>(st[j]);
                     }
-                    rec_step<SPIN>(st[j], r.x, r.y);
-                    rescale_check<SPIN>(st[j]);
                 }
+                ++ip;
+                continue;
             }
-            ++ip;
+            int jlo = R;
+#pragma unroll
+            for (int j = R - 1; j >= 0; --j)
+                if (((gact >> j) & 1u) && __any_sync(FULL, !ring_dead<SPIN>(st[j]))) jlo = j;
+            if (jlo == 0) { all_live = true; break; }
+            const int ipe = min(npr, ip + LEG_CHK);
+            auto run = [&](auto JLO) {
+                constexpr int J0 = decltype(JLO)::value;
+                for (; ip < ipe; ++ip) {
+                    const int i = 2 * ip;
+                    const double2 r0 = sR[i], r1 = sR[i + 1];
+                    double2 e0[NC], b0[NC], e1[NC], b1[NC];
+                    if (J0 < R) {
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            e0[c] = sE[c][i]; e1[c] = sE[c][i + 1];
+                            b0[c] = SPIN ? sB[c][i] : e0[c]; b1[c] = SPIN ? sB[c][i + 1] : e1[c];
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        if (j >= J0) {
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) synth_acc<SPIN, true>(acc[j][c], st[j].pc, st[j].mc, e0[c], b0[c]);
+                        }
+                        rec_step<SPIN>(st[j], r0.x, r0.y);
+                        if (j >= J0) {
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) synth_acc<SPIN, false>(acc[j][c], st[j].pc, st[j].mc, e1[c], b1[c]);
+                        }
+                        rec_step<SPIN>(st[j], r1.x, r1.y);
+                    }
+                }
+            };
+            if (R >= 4 && jlo == 3) run(std::integral_constant<int, (R >= 4 ? 3 : R)>());
+            else if (R >= 3 && jlo == 2) run(std::integral_constant<int, (R >= 3 ? 2 : R)>());
+            else if (R >= 2 && jlo == 1) run(std::integral_constant<int, (R >= 2 ? 1 : R)>());
+            else run(std::integral_constant<int, R>());
         }
         // (C) fast path
 #pragma unroll 2
@@ -824,6 +884,7 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
     RingState<SPIN> st[R];
     AnalIn<SPIN> G[R][NC];
     bool any_act = false;
+    unsigned myact = 0;   // bit j: ring pair j of this thread reaches m
 #pragma unroll
     for (int j = 0; j < R; ++j) {
         const int k = chunk + ((tid >> 5) * R + j) * 32 + (tid & 31);   // warp-major: a warp owns 32 R consecutive pairs, so idle slots fill whole warps
@@ -838,6 +899,7 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
             st[j].x = P.cth[p];
             seed_ring<SPIN>(P, p, m, st[j].pc, st[j].mc, st[j].sc);
             any_act = true;
+            myact |= 1u << j;
             const int rn = p, rs = P.nring - 1 - p;
             const double2 z = make_double2(0.0, 0.0);
             const int64_t in = fm_index<SH>(P, 0, rn, m, mk), is = fm_index<SH>(P, 0, rs, m, mk);
@@ -875,6 +937,10 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
         }
     }
     const bool warp_act = __any_sync(FULL, any_act);
+    unsigned gact = 0;          // 32-ring groups of this warp that hold at least one ring reaching this m
+#pragma unroll
+    for (int j = 0; j < R; ++j) if (__any_sync(FULL, (myact >> j) & 1u)) gact |= 1u << j;
+    bool all_live = false;      // see leg_synth_kernel
 #if LEG_FOLD2
     // spin 2: the lane ends up owning (h, c) = (bit 2, (bit 4, bit 3)); odd c of the second l carries a minus sign
     const int vidx = SPIN ? ((lane & 4) | ((lane >> 3) & 3)) : lane >> 3;
@@ -905,50 +971,85 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
             }
             ip = npr;
         }
-        while (ip < npr) {  // (A)
-            bool alls = true;
-#pragma unroll
-            for (int j = 0; j < R; ++j) alls = alls && (st[j].sc > 0 || st[j].pc == 0.0);
-            if (!__all_sync(FULL, alls)) break;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const double2 r = sR[2 * ip + h];
-#pragma unroll
-                for (int j = 0; j < R; ++j) { rec_step<SPIN>(st[j], r.x, r.y); rescale_check<SPIN>(st[j]); }
-            }
-            if (lane < NVAL) {
-#pragma unroll
-                for (int c = 0; c < NC; ++c) sPart(w, c)[ip * NVAL + lane] = 0.0;
-            }
-            ++ip;
-        }
-        while (ip < npr) {  // (B)
+        // (A/B) until every 32-ring group of the warp accumulates: see leg_synth_kernel.  Groups below the lowest live one run the
+        // recurrence only; checked every LEG_CHK pairs of l; lanes with a pending range-extension scale go pair by pair.
+        while (ip < npr && !all_live) {
             bool anys = false;
 #pragma unroll
             for (int j = 0; j < R; ++j) anys = anys || st[j].sc > 0;
-            if (!__any_sync(FULL, anys)) break;
-            double v[NC][NVAL];
+            if (__any_sync(FULL, anys)) {
+                double v[NC][NVAL];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const double2 r = sR[2 * ip + h];
+                for (int h = 0; h < 2; ++h) {
+                    const double2 r = sR[2 * ip + h];
 #pragma unroll
-                for (int j = 0; j < R; ++j) {
-                    const double pc = st[j].sc ? 0.0 : st[j].pc, mc = st[j].sc ? 0.0 : st[j].mc;
+                    for (int j = 0; j < R; ++j) {
+                        const double pc = st[j].sc ? 0.0 : st[j].pc, mc = st[j].sc ? 0.0 : st[j].mc;
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) {
-                        if (h == 0) { if (j == 0) ANAL_ACC(true, true, v[c], G[j][c], pc, mc); else ANAL_ACC(true, false, v[c], G[j][c], pc, mc); }
-                        else { if (j == 0) ANAL_ACC(false, true, v[c] + NV, G[j][c], pc, mc); else ANAL_ACC(false, false, v[c] + NV, G[j][c], pc, mc); }
+                        for (int c = 0; c < NC; ++c) {
+                            if (h == 0) { if (j == 0) ANAL_ACC(true, true, v[c], G[j][c], pc, mc); else ANAL_ACC(true, false, v[c], G[j][c], pc, mc); }
+                            else { if (j == 0) ANAL_ACC(false, true, v[c] + NV, G[j][c], pc, mc); else ANAL_ACC(false, false, v[c] + NV, G[j][c], pc, mc); }
+                        }
+                        rec_step<SPIN>(st[j], r.x, r.y);
+                        rescale_check<SPIN>(st[j]);
                     }
-                    rec_step<SPIN>(st[j], r.x, r.y);
-                    rescale_check<SPIN>(st[j]);
                 }
-            }
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                const double s = ANAL_FOLD(v[c], lane);
-                if (writer) sPart(w, c)[ip * NVAL + vidx] = __hiloint2double(__double2hiint(s) ^ flipmask, __double2loint(s));
+                for (int c = 0; c < NC; ++c) {
+                    const double s = ANAL_FOLD(v[c], lane);
+                    if (writer) sPart(w, c)[ip * NVAL + vidx] = __hiloint2double(__double2hiint(s) ^ flipmask, __double2loint(s));
+                }
+                ++ip;
+                continue;
             }
-            ++ip;
+            int jlo = R;
+#pragma unroll
+            for (int j = R - 1; j >= 0; --j)
+                if (((gact >> j) & 1u) && __any_sync(FULL, !ring_dead<SPIN>(st[j]))) jlo = j;
+            if (jlo == 0) { all_live = true; break; }
+            const int ipe = min(npr, ip + LEG_CHK);
+            auto run = [&](auto JLO) {
+                constexpr int J0 = decltype(JLO)::value;
+                for (; ip < ipe; ++ip) {
+                    const double2 r0 = sR[2 * ip], r1 = sR[2 * ip + 1];
+                    double v[NC][NVAL];
+#pragma unroll
+                    for (int j = 0; j < R; ++j) {
+                        if (j >= J0) {
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) {
+                                if (j == J0) ANAL_ACC(true, true, v[c], G[j][c], st[j].pc, st[j].mc);
+                                else ANAL_ACC(true, false, v[c], G[j][c], st[j].pc, st[j].mc);
+                            }
+                        }
+                        rec_step<SPIN>(st[j], r0.x, r0.y);
+                        if (j >= J0) {
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) {
+                                if (j == J0) ANAL_ACC(false, true, v[c] + NV, G[j][c], st[j].pc, st[j].mc);
+                                else ANAL_ACC(false, false, v[c] + NV, G[j][c], st[j].pc, st[j].mc);
+                            }
+                        }
+                        rec_step<SPIN>(st[j], r1.x, r1.y);
+                    }
+                    if (J0 >= R) {   // nothing accumulates yet
+                        if (lane < NVAL) {
+#pragma unroll
+                            for (int c = 0; c < NC; ++c) sPart(w, c)[ip * NVAL + lane] = 0.0;
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) {
+                            const double s = ANAL_FOLD(v[c], lane);
+                            if (writer) sPart(w, c)[ip * NVAL + vidx] = __hiloint2double(__double2hiint(s) ^ flipmask, __double2loint(s));
+                        }
+                    }
+                }
+            };
+            if (R >= 4 && jlo == 3) run(std::integral_constant<int, (R >= 4 ? 3 : R)>());
+            else if (R >= 3 && jlo == 2) run(std::integral_constant<int, (R >= 3 ? 2 : R)>());
+            else if (R >= 2 && jlo == 1) run(std::integral_constant<int, (R >= 2 ? 1 : R)>());
+            else run(std::integral_constant<int, R>());
         }
 #if LEG_FOLD2 && LEG_FOLD3
         if (SPIN == 2) {
