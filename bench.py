@@ -760,18 +760,20 @@ def main():
 
     def ncu_traffic(prefix):
         """DRAM bytes per launch (read + write) of the kernel from the committed ncu --set full capture, or None."""
-        try:
-            t = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json")))["kernels"]
-            k = next(v for name, v in t.items() if name.startswith(prefix))
-            return k["dram_bytes_read"] + k["dram_bytes_write"]
-        except Exception:
-            return None
+        for fn in ("traffic_r02.json", "traffic_r01.json"):   # this round's capture first (the ring kernel was last captured in r01)
+            try:
+                t = json.load(open(os.path.join(ROOT, "profiles", fn)))["kernels"]
+                k = next(v for name, v in t.items() if name.startswith(prefix))
+                return k["dram_bytes_read"] + k["dram_bytes_write"]
+            except Exception:
+                continue
+        return None
 
     at_bench_size = nside == 512 and lmax == 1024
-    roofline = {"kernel": "leg_anal_kernel<2,4>" if dom == "leg_anal" else "leg_synth_kernel<2,2>", "bound": "fp64",
+    roofline = {"kernel": "leg_anal_kernel<2,4,0,1>" if dom == "leg_anal" else "leg_synth_kernel<2,2,0,1>", "bound": "fp64",
                 "achieved": ach, "peak": peak.value, "unit": "TFLOP/s", "frac": ach / peak.value if peak.value else None,
                 "traffic": ncu_traffic(dom + "_kernel") if at_bench_size else None,
-                "traffic_source": "profiles/traffic_r01.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                "traffic_source": "profiles/traffic_r02.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)",
                 "peak_source": "DFMA microkernel measured in this run (MEASURED_PEAKS.json has no FP64 figure; nominal 37.2 TFLOP/s)",
                 "algorithmic_flops_per_launch": f2, "ms_per_launch": stage_ms[dom],
                 "both_legendre_kernels_tflops": 2 * f2 / ((stage_ms["leg_synth"] + stage_ms["leg_anal"]) * 1e-3) * 1e-12}

@@ -52,6 +52,9 @@
 #define LEG_FOLD3 1  // spin-2 analysis fast loop: the last three stages of the reduce-scatter are deferred, FOLD3_NB pairs of l
 #endif               // at a time, to a sum through shared memory (needs LEG_FOLD2)
 #define FOLD3_NB 8
+#ifndef LEG_SPLITACC
+#define LEG_SPLITACC 0   // spin-2 analysis fast loop: two half-length accumulation chains per value (experiment, see the loop)
+#endif
 #define FULL 0xffffffffu
 #ifndef LEG_CHK
 #define LEG_CHK 4     // pairs of l between two looks at which ring groups of a warp have come alive (transition phase)
@@ -1083,6 +1086,34 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
             for (; ip < npr; ++ip) {  // (C)
                 double v[NC][NVAL];
                 const double2 r0 = sR[2 * ip], r1 = sR[2 * ip + 1];
+#if LEG_SPLITACC
+                // two half-length accumulation chains per value (rings j < R/2 and j >= R/2), joined by one add: the sums over
+                // the R rings of a thread are dependent DFMA chains of depth 2 R, the longest ones in the loop
+                double v2[NC][NVAL];
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        double* t = (R >= 4 && j >= R / 2) ? v2[c] : v[c];
+                        if (j == 0 || (R >= 4 && j == R / 2)) ANAL_ACC(true, true, t, G[j][c], st[j].pc, st[j].mc);
+                        else ANAL_ACC(true, false, t, G[j][c], st[j].pc, st[j].mc);
+                    }
+                    rec_step<SPIN>(st[j], r0.x, r0.y);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        double* t = (R >= 4 && j >= R / 2) ? v2[c] : v[c];
+                        if (j == 0 || (R >= 4 && j == R / 2)) ANAL_ACC(false, true, t + NV, G[j][c], st[j].pc, st[j].mc);
+                        else ANAL_ACC(false, false, t + NV, G[j][c], st[j].pc, st[j].mc);
+                    }
+                    rec_step<SPIN>(st[j], r1.x, r1.y);
+                }
+                if (R >= 4) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+#pragma unroll
+                        for (int qq = 0; qq < NVAL; ++qq) v[c][qq] += v2[c][qq];
+                }
+#else
 #pragma unroll
                 for (int j = 0; j < R; ++j) {
 #pragma unroll
@@ -1098,6 +1129,7 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
                     }
                     rec_step<SPIN>(st[j], r1.x, r1.y);
                 }
+#endif
                 const int q = ip - ipb;
 #pragma unroll
                 for (int c = 0; c < NC; ++c) {

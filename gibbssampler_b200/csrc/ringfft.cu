@@ -940,8 +940,18 @@ int gs_ring_setup(gs_plan* p)
 
 int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st, const int* skip, int nc, int64_t map_stride)
 {
-    if (nc > 1 && (p->world > 1 || (spin == 0 ? p->nsjobs0 : p->nsjobs2) > 0)) { gs_set_error("chain batches need an unsharded plan without split rings (nside < 2048)"); return GS_E_BADARG; }
+    if (nc > 1 && p->world > 1) { gs_set_error("chain batches need an unsharded plan"); return GS_E_BADARG; }
     const int nj = spin == 0 ? p->ngroups0 : p->ngroups2, ns = spin == 0 ? p->nsjobs0 : p->nsjobs2;
+    if (nc > 1 && ns > 0) {   // rings on the split path (nside >= 1024) share one scratch buffer: the chains of a batch take turns
+        double2* F0 = p->Fm;
+        int rc = GS_OK;
+        for (int c = 0; c < nc && rc == GS_OK; ++c) {
+            p->Fm = F0 + c * gs_fm_stride(p);
+            rc = gs_ring_synth(p, spin, mapQ + c * map_stride, spin ? mapU + c * map_stride : mapU, st, skip, 1, 0);
+        }
+        p->Fm = F0;
+        return rc;
+    }
     const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
     const int2* grp = spin == 0 ? p->groups0 : p->groups2;
     const SplitJob* sj = spin == 0 ? p->sjobs0 : p->sjobs2;
@@ -972,8 +982,18 @@ int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t
 int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, const double* pixw, cudaStream_t st,
                  const int* skip, int nc, int64_t map_stride)
 {
-    if (nc > 1 && (p->world > 1 || (spin == 0 ? p->nsjobs0 : p->nsjobs2) > 0)) { gs_set_error("chain batches need an unsharded plan without split rings (nside < 2048)"); return GS_E_BADARG; }
+    if (nc > 1 && p->world > 1) { gs_set_error("chain batches need an unsharded plan"); return GS_E_BADARG; }
     const int nj = spin == 0 ? p->ngroups0 : p->ngroups2, ns = spin == 0 ? p->nsjobs0 : p->nsjobs2;
+    if (nc > 1 && ns > 0) {   // split path: one chain after the other (see gs_ring_synth)
+        double2* F0 = p->Fm;
+        int rc = GS_OK;
+        for (int c = 0; c < nc && rc == GS_OK; ++c) {
+            p->Fm = F0 + c * gs_fm_stride(p);
+            rc = gs_ring_anal(p, spin, mapQ + c * map_stride, spin ? mapU + c * map_stride : mapU, pixw, st, skip, 1, 0);
+        }
+        p->Fm = F0;
+        return rc;
+    }
     const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
     const int2* grp = spin == 0 ? p->groups0 : p->groups2;
     const SplitJob* sj = spin == 0 ? p->sjobs0 : p->sjobs2;
@@ -1006,7 +1026,17 @@ int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, c
 int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, const int* skip, int nc)
 {
     const int nj = spin == 0 ? p->ngroups0 : p->ngroups2, ns = spin == 0 ? p->nsjobs0 : p->nsjobs2;
-    if (nc > 1 && (p->world > 1 || ns > 0 || !pixw)) { gs_set_error("chain batches need an unsharded plan without split rings (nside < 2048) and pixel weights"); return GS_E_BADARG; }
+    if (nc > 1 && (p->world > 1 || !pixw)) { gs_set_error("chain batches need an unsharded plan and pixel weights"); return GS_E_BADARG; }
+    if (nc > 1 && ns > 0) {   // split path: the chains take turns through the plan's scratch maps
+        double2* F0 = p->Fm;
+        int rc = GS_OK;
+        for (int c = 0; c < nc && rc == GS_OK; ++c) {
+            p->Fm = F0 + c * gs_fm_stride(p);
+            rc = gs_ring_apply(p, spin, pixw, st, skip, 1);
+        }
+        p->Fm = F0;
+        return rc;
+    }
     if (ns > 0 || !pixw) {
         int rc = gs_ring_synth(p, spin, p->mapQ_tmp, p->mapU_tmp, st, skip);
         if (rc) return rc;

@@ -154,3 +154,25 @@ def test_batched_pcg_first_iterations_match_single_chain_exactly_in_count():
     for k in range(2):
         assert relerr(x[k, 0].cpu().numpy(), single[k][0]) < 1e-9 and relerr(x[k, 1].cpu().numpy(), single[k][1]) < 1e-9
         assert abs(res2[k] - single[k][2]) < 1e-8 * single[k][2]
+
+
+def test_batched_transforms_on_split_ring_path(monkeypatch):
+    """Rings too long for one CTA (nside >= 1024 in production) go through a shared scratch buffer: a chain batch shares the
+    Legendre recurrence and runs that ring stage one chain after the other.  GS_RING_MCAP forces the path at nside 32."""
+    from gibbssampler_b200.sht import Plan
+    nside, lmax, k = 32, 64, 3
+    monkeypatch.setenv("GS_RING_MCAP", "64")
+    plan = Plan(nside, lmax)
+    monkeypatch.delenv("GS_RING_MCAP")
+    rng = np.random.default_rng(8)
+    es = [rand_alm(lmax, rng, 2) for _ in range(k)]
+    bs = [rand_alm(lmax, rng, 2) for _ in range(k)]
+    q, u = plan.alm2map_spin2_batch(dev(np.stack(es)), dev(np.stack(bs)))
+    npix = 12 * nside ** 2
+    fq, fu = rng.standard_normal((k, npix)), rng.standard_normal((k, npix))
+    ge, gb = plan.map2alm_spin2_batch(dev(fq), dev(fu))
+    for c in range(k):
+        rq, ru = O.alm2map_spin2(es[c], bs[c], nside, lmax)
+        assert relerr(q[c].cpu().numpy(), rq) < 1e-10 and relerr(u[c].cpu().numpy(), ru) < 1e-10
+        re_, rb_ = O.map2alm_spin2(fq[c], fu[c], nside, lmax)
+        assert relerr(ge[c].cpu().numpy(), re_) < 1e-10 and relerr(gb[c].cpu().numpy(), rb_) < 1e-10
