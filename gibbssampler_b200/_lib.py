@@ -50,6 +50,7 @@ SIGNATURES = {
                            C.POINTER(_i), C.POINTER(_d), _vp]),
     "gs_cr_pcg_pol_batch": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _d, _vp, _vp, _vp, _vp, _i64, _d, _i, _i,
                                  C.POINTER(_i), C.POINTER(_d), _vp]),
+    "gs_set_pcg_graph": (_i, [_i]),
     "gs_cr_apply_q_pol": (_i, [_vp] * 10),
     "gs_cr_rhs_tt": (_i, [_vp] * 9 + [_i, _vp, _vp]),
     "gs_cr_pcg_tt": (_i, [_vp, _vp, _vp, _vp, _d, _vp, _vp, _i, _d, _i, _i, C.POINTER(_i), C.POINTER(_d), _vp]),

@@ -175,6 +175,8 @@ struct gs_plan {
     void* pcg_ws;       // gs_pcg_ws* (solver.cu): PCG vectors / state of this plan, allocated on the first solve
     void* pcg_ws_batch; // gs_pcg_ws[2]: workspaces of a two-chain batch (gs_cr_pcg_pol_batch), allocated on first use
     int* pcg_alldone;   // device flag: both chains of the batch have converged
+    void* work_stream;  // cudaStream_t of the plan for graph-captured solves (NULL until first used)
+    void* work_event;   // cudaEvent_t ordering work_stream after the caller's stream
 };
 
 extern int g_gs_ring_skip;        // 1: rings whose pixel weights vanish identically are left out (PCG mat-vec, Metropolis sweep)
@@ -208,6 +210,7 @@ int64_t gs_fm_stride(const gs_plan* p);            // double2 entries of one cha
 int64_t gs_part_stride(const gs_plan* p, int nc);  // doubles of one chain's analysis partial sums
 int gs_active_rings_build(gs_plan* p, const double* pixw, cudaStream_t st);
 int gs_leg_build_sinpow(gs_plan* p);
+int gs_leg_prepare(gs_plan* p);   // per-device kernel attributes (dynamic shared memory opt-in)
 // ringfft.cu
 int gs_ring_setup(gs_plan* p);
 // nc > 1 (chain batch): chain c uses the spectra p->Fm + c gs_fm_stride(p) and the maps + c map_stride

@@ -34,6 +34,9 @@
 #ifndef LEG_R
 #define LEG_R 2      // ring pairs per thread (synthesis)
 #endif
+#ifndef LEG_R2
+#define LEG_R2 2     // ring pairs per thread of the chain-batched synthesis (NC = 2)
+#endif
 #ifndef LEG_RA
 #define LEG_RA 4     // ring pairs per thread (analysis); LEG_NT * LEG_RA ring pairs per partial chunk
 #endif
@@ -1456,14 +1459,15 @@ int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, i
     if (sh && layout != GS_ALM_REAL) { gs_set_error("sharded plans take the (local) real alm layout only"); return GS_E_BADARG; }
     int rc = check_batch(p, nc, layout, "gs_leg_synth");
     if (rc) return rc;
-    dim3 grid((p->d.npair + LEG_NT * LEG_R - 1) / (LEG_NT * LEG_R), sh ? p->d.sh.nm_loc : p->d.lmax + 1);
+    const int rr = nc == 2 ? LEG_R2 : LEG_R;
+    dim3 grid((p->d.npair + LEG_NT * rr - 1) / (LEG_NT * rr), sh ? p->d.sh.nm_loc : p->d.lmax + 1);
     const int* plist = p->use_act ? p->act_pairs : nullptr;
     const int* pcount = plist ? p->act_count : nullptr;
     const int* slot0 = plist ? p->act_slot0 + (spin ? p->d.lmax + 1 : 0) : (spin ? p->d.pmin2 : p->d.pmin0);
     const int64_t fs = gs_fm_stride(p);
     if (nc == 2) {
-        if (spin == 0) leg_synth_kernel<0, LEG_R, false, 2><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, alm_stride, fs);
-        else leg_synth_kernel<2, LEG_R, false, 2><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, alm_stride, fs);
+        if (spin == 0) leg_synth_kernel<0, LEG_R2, false, 2><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, alm_stride, fs);
+        else leg_synth_kernel<2, LEG_R2, false, 2><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, alm_stride, fs);
     } else if (!sh) {
         if (spin == 0) leg_synth_kernel<0, LEG_R, false, 1><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, 0, 0);
         else leg_synth_kernel<2, LEG_R, false, 1><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, 0, 0);
@@ -1482,15 +1486,23 @@ template <int SPIN, int R, bool SH, int NC>
 static int launch_anal(gs_plan* p, dim3 grid, cudaStream_t st, const int* skip, const int* plist, const int* pcount, const int* slot0,
                        int64_t fs, int64_t ps)
 {
-    static bool attr_set[64] = {false};   // per device: the 48 KB default limit of dynamic shared memory is exceeded by the chain batch
-    constexpr size_t sm = leg_anal_smem<SPIN, NC>();
-    const int dev = p->device & 63;
-    if (!attr_set[dev]) {
-        GS_CHECK_CUDA(cudaFuncSetAttribute(leg_anal_kernel<SPIN, R, SH, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        attr_set[dev] = true;
-    }
+    constexpr size_t sm = leg_anal_smem<SPIN, NC>();   // opt-in size set by gs_leg_prepare at plan creation
     leg_anal_kernel<SPIN, R, SH, NC><<<grid, LEG_NT, sm, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount, slot0, fs, ps);
     GS_CHECK_LAUNCH();
+    return GS_OK;
+}
+
+// The analysis kernels take their tiles from dynamic shared memory (the chain batch exceeds the 48 KB default): opt in once per
+// device, at plan creation, so that no attribute call happens inside a stream capture (graph-replayed PCG).
+int gs_leg_prepare(gs_plan* p)
+{
+    (void)p;
+#define GS_ANAL_ATTR(SPIN, R, SH, NC) \
+    GS_CHECK_CUDA(cudaFuncSetAttribute(leg_anal_kernel<SPIN, R, SH, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)leg_anal_smem<SPIN, NC>()))
+    GS_ANAL_ATTR(0, LEG_RA, false, 1); GS_ANAL_ATTR(2, LEG_RA, false, 1);
+    GS_ANAL_ATTR(0, LEG_RA, true, 1);  GS_ANAL_ATTR(2, LEG_RA, true, 1);
+    GS_ANAL_ATTR(0, LEG_RA2, false, 2); GS_ANAL_ATTR(2, LEG_RA2, false, 2);
+#undef GS_ANAL_ATTR
     return GS_OK;
 }
 

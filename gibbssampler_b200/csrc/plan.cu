@@ -257,12 +257,15 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
     p->pcg_ws = nullptr;
     p->pcg_ws_batch = nullptr;
     p->pcg_alldone = nullptr;
+    p->work_stream = nullptr;
+    p->work_event = nullptr;
     p->chain_cap = 1;
     p->Fx = nullptr;
     p->red_loc = nullptr;
     p->d.sh.world = 1;
     int rc = build_tables(p);
     if (rc == GS_OK) rc = gs_leg_build_sinpow(p);
+    if (rc == GS_OK) rc = gs_leg_prepare(p);
     const int64_t nm = lmax + 1;
     p->nreal_loc = nm * nm;
     p->npix_loc = p->d.npix;
@@ -354,6 +357,8 @@ extern "C" int gs_plan_destroy(gs_plan* p)
     if (!p) return GS_OK;
     gs_pcg_ws_free(p);
     gs_shard_free(p);
+    if (p->work_event) cudaEventDestroy((cudaEvent_t)p->work_event);
+    if (p->work_stream) cudaStreamDestroy((cudaStream_t)p->work_stream);
     for (void* d : p->owned) cudaFree(d);
     cudaFree(p->mwg_F);
     cudaFree(p->mwg_maps);

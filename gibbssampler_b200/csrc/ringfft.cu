@@ -20,6 +20,12 @@
 #include "gs_internal.h"
 
 #define RF_NT 256
+#ifndef RING_UNPACK_CHIRP
+#define RING_UNPACK_CHIRP 1   // Bluestein rings: last chirp product taken while the spectrum is unpacked (no pass of its own)
+#endif
+#ifndef RING_FUSE_MID
+#define RING_FUSE_MID 0   // Bluestein rings of ring_apply_kernel: pointwise chirp / weight product inside the next transform's first pass
+#endif
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ double2 cmulc(double2 a, double2 b) { return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a conj(b)
@@ -27,15 +33,18 @@ __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_doub
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
 
 // ---- shared-memory FFT core -------------------------------------------------------------------
-// Layout: element i of the transform lives at buf[PADI(i)], PADI(i) = i + (i >> 4): one 16-byte pad per
+// Layout: element i of the transform lives at buf[PADI(i)], PADI(i) = i + (i >> 4) + (i >> 8): one 16-byte pad per
 // 16 elements makes the stride-16 accesses of the final radix-16 pass bank-conflict free and leaves the
-// unit-stride passes (consecutive lanes -> consecutive elements) conflict free as well.
+// unit-stride passes (consecutive lanes -> consecutive elements) conflict free as well; the pad per 256 elements (r02)
+// does the same for the BIT-REVERSED accesses of the power-of-two rings (alias fold stores and spectrum unpack loads of
+// consecutive k touch elements n/8 apart: 8-way conflicts on every belt ring with the first pad alone).
 // Passes: a radix-16 butterfly (= two radix-4 levels) is done entirely in registers, so a 4096-point
 // transform makes 3 trips through shared memory (6 with radix-4); leftover stages (log2 M mod 4) are a
 // radix-2 and/or radix-4 pass at the top (DIF) / bottom (DIT).
 // Twiddles: quarter table twq[k] = exp(-2 pi i k / twn), k <= twn/4, in shared memory;
 // W^(k + twn/4) = -i W^k covers the second quadrant (indices stay below twn/2).
-#define PADI(i) ((i) + ((i) >> 4))
+#define PADI(i) ((i) + ((i) >> 4) + ((i) >> 8))
+#define PADLEN(M) ((M) + ((M) >> 4) + ((M) >> 8) + 2)   // shared-memory slots of a padded M-point buffer
 
 __device__ __forceinline__ double2 tw_get(const double2* twq, int idx, int quarter)
 {
@@ -74,18 +83,20 @@ __device__ __forceinline__ double2 w8c(int a)
     return a == 0 ? make_double2(1.0, 0.0) : a == 1 ? make_double2(h, -h) : a == 2 ? make_double2(0.0, -1.0) : make_double2(-h, -h);
 }
 
+struct NoPre { __device__ __forceinline__ double2 operator()(int, double2 v) const { return v; } };   // identity load hook of the passes
+
 // radix-16 pass over sub-transforms of size N (N >= 16).  INV = false: DIF (forward), true: DIT (inverse).
 // POST (DIF only): outputs are multiplied by post[position].
-template <bool INV, bool POST>
+template <bool INV, bool POST, class PRE = NoPre>
 __device__ __forceinline__ void pass16(double2* buf, int M, int N, const double2* twq, int twn, const double2* __restrict__ post,
-                                       int tid, int nt)
+                                       int tid, int nt, PRE pre = PRE())
 {
     const int s = N >> 4, ls = 31 - __clz(s), ts = twn / N, quarter = twn >> 2, ng = M >> 4;
     for (int t = tid; t < ng; t += nt) {
         const int g = t >> ls, j = t & (s - 1), i0 = g * N + j;
         double2 x[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) x[k] = buf[PADI(i0 + k * s)];
+        for (int k = 0; k < 16; ++k) x[k] = pre(i0 + k * s, buf[PADI(i0 + k * s)]);
         double2 wj = make_double2(1.0, 0.0), w2j = wj, w4j = wj, w8j = wj;
         if (s > 1) {
             wj = twq[j * ts];
@@ -115,13 +126,14 @@ __device__ __forceinline__ void pass16(double2* buf, int M, int N, const double2
 }
 
 // radix-4 pass over sub-transforms of size N (N >= 4)
-template <bool INV>
-__device__ __forceinline__ void pass4(double2* buf, int M, int N, const double2* twq, int twn, int tid, int nt)
+template <bool INV, class PRE = NoPre>
+__device__ __forceinline__ void pass4(double2* buf, int M, int N, const double2* twq, int twn, int tid, int nt, PRE pre = PRE())
 {
     const int q = N >> 2, lq = 31 - __clz(q), ts = twn / N, quarter = twn >> 2, nq = M >> 2;
     for (int t = tid; t < nq; t += nt) {
         const int g = t >> lq, j = t & (q - 1), i0 = g * N + j;
-        double2 a0 = buf[PADI(i0)], a1 = buf[PADI(i0 + q)], a2 = buf[PADI(i0 + 2 * q)], a3 = buf[PADI(i0 + 3 * q)];
+        double2 a0 = pre(i0, buf[PADI(i0)]), a1 = pre(i0 + q, buf[PADI(i0 + q)]), a2 = pre(i0 + 2 * q, buf[PADI(i0 + 2 * q)]),
+                a3 = pre(i0 + 3 * q, buf[PADI(i0 + 3 * q)]);
         const double2 w1 = twq[j * ts], w2 = tw_get(twq, 2 * j * ts, quarter);
         if (!INV) bf4_dif(a0, a1, a2, a3, w1, w2); else bf4_dit(a0, a1, a2, a3, w1, w2);
         buf[PADI(i0)] = a0; buf[PADI(i0 + q)] = a1; buf[PADI(i0 + 2 * q)] = a2; buf[PADI(i0 + 3 * q)] = a3;
@@ -129,14 +141,57 @@ __device__ __forceinline__ void pass4(double2* buf, int M, int N, const double2*
     __syncthreads();
 }
 
+// radix-8 pass over sub-transforms of size N (N >= 8) = one radix-2 level + one radix-4 level in registers.  Transform lengths
+// 2^(4k+3) (2048: the belt rings of nside 512 and the Bluestein length of the cap rings with 516..1024 pixels) used to take a
+// radix-2 AND a radix-4 trip through shared memory at the top (DIF) / bottom (DIT) of the transform; this is one trip.
+// PRE (DIF only): the loaded element idx is replaced by pre(idx, value) (fused pointwise products, see ring_apply_kernel).
+template <bool INV, class PRE = NoPre>
+__device__ __forceinline__ void pass8(double2* buf, int M, int N, const double2* twq, int twn, int tid, int nt, PRE pre = PRE())
+{
+    const int s = N >> 3, ls = 31 - __clz(s), ts = twn / N, quarter = twn >> 2, ng = M >> 3;
+    for (int t = tid; t < ng; t += nt) {
+        const int g = t >> ls, j = t & (s - 1), i0 = g * N + j;
+        double2 x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) x[k] = pre(i0 + k * s, buf[PADI(i0 + k * s)]);
+        double2 wj = make_double2(1.0, 0.0), w2j = wj, w4j = wj;
+        if (s > 1) {
+            wj = twq[j * ts];
+            w2j = tw_get(twq, 2 * j * ts, quarter);
+            w4j = tw_get(twq, 4 * j * ts, quarter);
+        }
+        if (!INV) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 u = cadd(x[k], x[k + 4]), v = cmul(csub(x[k], x[k + 4]), cmul(wj, w8c(k)));
+                x[k] = u; x[k + 4] = v;
+            }
+            bf4_dif(x[0], x[1], x[2], x[3], w2j, w4j);
+            bf4_dif(x[4], x[5], x[6], x[7], w2j, w4j);
+        } else {
+            bf4_dit(x[0], x[1], x[2], x[3], w2j, w4j);
+            bf4_dit(x[4], x[5], x[6], x[7], w2j, w4j);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double2 tb = cmulc(x[k + 4], cmul(wj, w8c(k)));
+                const double2 a = x[k];
+                x[k] = cadd(a, tb); x[k + 4] = csub(a, tb);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) buf[PADI(i0 + k * s)] = x[k];
+    }
+    __syncthreads();
+}
+
 // radix-2 pass over sub-transforms of size N (N >= 2)
-template <bool INV>
-__device__ __forceinline__ void pass2(double2* buf, int M, int N, const double2* twq, int twn, int tid, int nt)
+template <bool INV, class PRE = NoPre>
+__device__ __forceinline__ void pass2(double2* buf, int M, int N, const double2* twq, int twn, int tid, int nt, PRE pre = PRE())
 {
     const int h = N >> 1, lh = 31 - __clz(h), ts = twn / N;
     for (int t = tid; t < (M >> 1); t += nt) {
         const int g = t >> lh, j = t & (h - 1), i0 = g * N + j;
-        const double2 a = buf[PADI(i0)], b = buf[PADI(i0 + h)];
+        const double2 a = pre(i0, buf[PADI(i0)]), b = pre(i0 + h, buf[PADI(i0 + h)]);
         const double2 w = tw_get(twq, j * ts, twn >> 2);
         if (!INV) { buf[PADI(i0)] = cadd(a, b); buf[PADI(i0 + h)] = cmul(csub(a, b), w); }
         else { const double2 tb = cmulc(b, w); buf[PADI(i0)] = cadd(a, tb); buf[PADI(i0 + h)] = csub(a, tb); }
@@ -148,17 +203,30 @@ __device__ __forceinline__ void pass2(double2* buf, int M, int N, const double2*
 // POST: the bit-reversed-order output is multiplied by post[] inside the last pass (needs M >= 16).
 // (tid, nt): index and number of the threads working on THIS transform (a CTA may run several transforms of
 // equal length side by side, see RingGroup); every barrier is CTA-wide.
-template <bool POST>
+// PRE: pre(idx, value) replaces every element as the FIRST pass loads it (M >= 2): pointwise products in front of a transform
+// (pixel weights, Bluestein chirps, zero padding) cost no trip through shared memory of their own.
+template <bool POST, class PRE = NoPre>
 __device__ void fft_dif(double2* buf, int M, const double2* twq, int twn, const double2* __restrict__ post, int tid = threadIdx.x,
-                        int nt = RF_NT)
+                        int nt = RF_NT, PRE pre = PRE())
 {
     const int lg = 31 - __clz(M), r = lg & 3;
     int N = M;
-    if (r & 1) { pass2<false>(buf, M, N, twq, twn, tid, nt); N >>= 1; }
-    if (r & 2) { pass4<false>(buf, M, N, twq, twn, tid, nt); N >>= 2; }
+    bool first = true;
+    if (r == 3) { pass8<false, PRE>(buf, M, N, twq, twn, tid, nt, pre); N >>= 3; first = false; }
+    else {
+        if (r & 1) { pass2<false, PRE>(buf, M, N, twq, twn, tid, nt, pre); N >>= 1; first = false; }
+        if (r & 2) {
+            if (first) pass4<false, PRE>(buf, M, N, twq, twn, tid, nt, pre); else pass4<false>(buf, M, N, twq, twn, tid, nt);
+            N >>= 2; first = false;
+        }
+    }
     while (N >= 16) {
-        if (POST && N == 16) pass16<false, true>(buf, M, N, twq, twn, post, tid, nt);
+        if (first) {
+            if (POST && N == 16) pass16<false, true, PRE>(buf, M, N, twq, twn, post, tid, nt, pre);
+            else pass16<false, false, PRE>(buf, M, N, twq, twn, post, tid, nt, pre);
+        } else if (POST && N == 16) pass16<false, true>(buf, M, N, twq, twn, post, tid, nt);
         else pass16<false, false>(buf, M, N, twq, twn, post, tid, nt);
+        first = false;
         N >>= 4;
     }
 }
@@ -170,6 +238,7 @@ __device__ void fft_dit_inv(double2* buf, int M, const double2* twq, int twn, in
     const int Ntop = M >> r;  // largest radix-16 sub-transform size
     for (int N = 16; N <= Ntop; N <<= 4) pass16<true, false>(buf, M, N, twq, twn, nullptr, tid, nt);
     int N = Ntop;
+    if (r == 3) { N <<= 3; pass8<true>(buf, M, N, twq, twn, tid, nt); return; }
     if (r & 2) { N <<= 2; pass4<true>(buf, M, N, twq, twn, tid, nt); }
     if (r & 1) { N <<= 1; pass2<true>(buf, M, N, twq, twn, tid, nt); }
 }
@@ -199,6 +268,14 @@ __device__ void ring_idft(const PlanDev& P, double2* buf, const double2* twq, in
     if (bsi < 0) { fft_dit_inv(buf, n, twq, P.tw_n, tid, nt); return; }
     const BluesteinDesc d = P.bs[bsi];
     fft_dif<true>(buf, d.M, twq, P.tw_n, P.bs_tab + d.bhat_off, tid, nt);
+    fft_dit_inv(buf, d.M, twq, P.tw_n, tid, nt);
+}
+// Bluestein only: the input of the convolution is pre(k, buf[k]) (chirp products / zero padding applied as the first pass loads)
+template <class PRE>
+__device__ void ring_idft_bs_pre(const PlanDev& P, double2* buf, const double2* twq, int bsi, int tid, int nt, PRE pre)
+{
+    const BluesteinDesc d = P.bs[bsi];
+    fft_dif<true, PRE>(buf, d.M, twq, P.tw_n, P.bs_tab + d.bhat_off, tid, nt, pre);
     fft_dit_inv(buf, d.M, twq, P.tw_n, tid, nt);
 }
 
@@ -301,8 +378,8 @@ __device__ __forceinline__ RingSub ring_sub(const PlanDev& P, const RingJob* __r
     S.bsi = P.ring_bs[S.job.ringA];
     S.M = S.bsi >= 0 ? P.bs[S.bsi].M : S.n;
     S.chirp = S.bsi >= 0 ? P.bs_tab + P.bs[S.bsi].chirp_off : nullptr;
-    S.buf = bufs + sub * (S.M + (S.M >> 4) + 2);
-    S.scratch = bufs + g.y * (S.M + (S.M >> 4) + 2) + sub * S.nt;   // used by rings shorter than nt only (M <= 2 nt)
+    S.buf = bufs + sub * PADLEN(S.M);
+    S.scratch = bufs + g.y * PADLEN(S.M) + sub * S.nt;   // used by rings shorter than nt only (M <= 2 nt)
     return S;
 }
 
@@ -445,8 +522,10 @@ __device__ __forceinline__ void ring_build_Z(const PlanDev& P, const RingSub& S,
 //   Xa[k] = (Z[k] + conj Z[n-k]) / 2, Xb[k] = (Z[k] - conj Z[n-k]) / (2i), F_m = X[m mod n] e^{-i m phi0}.
 // br = false: buf[PADI(k)] = conj Z[k] (transform done as conj(idft(conj z))); br = true: buf holds Z[k] at the
 // bit-reversed position of k (forward DIF transform of a power-of-two ring).
+// chirp (br = false only, nullable): buf still lacks the final Bluestein product, buf[k] chirp[k] is taken on the fly
 template <bool SH>
-__device__ __forceinline__ void ring_unpack_F(const PlanDev& P, const RingSub& S, bool br, double2* __restrict__ Fm, int mtop)
+__device__ __forceinline__ void ring_unpack_F(const PlanDev& P, const RingSub& S, bool br, double2* __restrict__ Fm, int mtop,
+                                              const double2* __restrict__ chirp = nullptr)
 {
     const RingJob& job = S.job;
     const int L = P.lmax, nm = L + 1, n = S.n, lg = 31 - __clz(n);
@@ -462,7 +541,8 @@ __device__ __forceinline__ void ring_unpack_F(const PlanDev& P, const RingSub& S
             const double2 c1 = buf[PADI((int)(__brev((unsigned)k) >> (32 - lg)))], c2 = buf[PADI((int)(__brev((unsigned)kk) >> (32 - lg)))];
             z1 = c1; z2c = make_double2(c2.x, -c2.y);
         } else {
-            const double2 c1 = buf[PADI(k)], c2 = buf[PADI(kk)];
+            double2 c1 = buf[PADI(k)], c2 = buf[PADI(kk)];
+            if (chirp) { c1 = cmul(c1, __ldg(&chirp[k])); c2 = cmul(c2, __ldg(&chirp[kk])); }
             z1 = make_double2(c1.x, -c1.y); z2c = c2;
         }
         const double2 xa = make_double2(0.5 * (z1.x + z2c.x), 0.5 * (z1.y + z2c.y));
@@ -541,11 +621,8 @@ ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __rest
         S.buf[pos] = z;
     }
     ring_idft(P, S.buf, twq, n, S.bsi, S.tid, S.nt);
-    if (S.bsi >= 0) {  // finish Bluestein in place: every m below reads two entries
-        for (int k = S.tid; k < n; k += S.nt) S.buf[PADI(k)] = cmul(S.buf[PADI(k)], __ldg(&S.chirp[k]));
-        __syncthreads();
-    }
-    ring_unpack_F<SH>(P, S, false, Fm, ring_mtop(P, job.ringA, spin2));
+    // Bluestein: the last chirp product is taken as the spectrum is unpacked
+    ring_unpack_F<SH>(P, S, false, Fm, ring_mtop(P, job.ringA, spin2), S.bsi >= 0 ? S.chirp : nullptr);
 }
 
 // Ring stage of the PCG mat-vec A^T N^-1 A in ONE kernel: F_m(ring) -> pixels of the ring (kept in shared memory) ->
@@ -584,26 +661,42 @@ ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
     RING_DBG(1);
     ring_idft(P, S.buf, twq, n, S.bsi, S.tid, S.nt);
     if (S.bsi < 0) {
-        // pixels z_j = a_j + i b_j in natural order -> weighted -> forward DIF transform (bit-reversed output)
-        for (int j = S.tid; j < n; j += S.nt) {
-            const double2 z = S.buf[PADI(j)];
-            S.buf[PADI(j)] = make_double2(z.x * wa[j], z.y * wb[j]);
-        }
-        __syncthreads();
-        fft_dif<false>(S.buf, n, twq, P.tw_n, nullptr, S.tid, S.nt);
+        // pixels z_j = a_j + i b_j in natural order -> weighted (as the first pass of the transform loads them) -> forward DIF
+        // transform (bit-reversed output)
+        auto weigh = [wa, wb](int j, double2 z) { return make_double2(z.x * wa[j], z.y * wb[j]); };
+        fft_dif<false>(S.buf, n, twq, P.tw_n, nullptr, S.tid, S.nt, weigh);
         ring_unpack_F<SH>(P, S, true, Fm, mtop);
     } else {
-        // Bluestein both ways: Z = conj(idft(conj z)); the chirp of the synthesis output and of the analysis input fuse
+        // Bluestein both ways: Z = conj(idft(conj z)); the chirp of the synthesis output, the pixel weights, the chirp of the
+        // analysis input and the zero padding are applied as the first pass of the second convolution loads its input, the last
+        // chirp as the spectrum is unpacked: no pointwise trip through shared memory is left
+        const double2* chirp = S.chirp;
+#if RING_FUSE_MID
+        auto mid = [wa, wb, chirp, n](int j, double2 v) {
+            if (j >= n) return make_double2(0.0, 0.0);
+            const double2 c = __ldg(&chirp[j]);
+            const double2 z = cmul(v, c);
+            return cmul(make_double2(z.x * wa[j], -z.y * wb[j]), c);
+        };
+        ring_idft_bs_pre(P, S.buf, twq, S.bsi, S.tid, S.nt, mid);
+#else
+        // (fusing this product into the first radix-16 pass of the next transform was measured SLOWER: 49 vs 43 us per 4096-point
+        // ring; 48 more global loads inside a pass that already holds 16 complex values in registers, and spills)
         for (int j = S.tid; j < S.M; j += S.nt) {
             if (j >= n) { S.buf[PADI(j)] = make_double2(0.0, 0.0); continue; }
-            const double2 c = __ldg(&S.chirp[j]);
+            const double2 c = __ldg(&chirp[j]);
             const double2 z = cmul(S.buf[PADI(j)], c);
             S.buf[PADI(j)] = cmul(make_double2(z.x * wa[j], -z.y * wb[j]), c);
         }
         ring_idft(P, S.buf, twq, n, S.bsi, S.tid, S.nt);
-        for (int k = S.tid; k < n; k += S.nt) S.buf[PADI(k)] = cmul(S.buf[PADI(k)], __ldg(&S.chirp[k]));
+#endif
+#if RING_UNPACK_CHIRP
+        ring_unpack_F<SH>(P, S, false, Fm, mtop, chirp);
+#else
+        for (int k = S.tid; k < n; k += S.nt) S.buf[PADI(k)] = cmul(S.buf[PADI(k)], __ldg(&chirp[k]));
         __syncthreads();
         ring_unpack_F<SH>(P, S, false, Fm, mtop);
+#endif
     }
     __syncthreads();
     RING_DBG(2);
@@ -793,7 +886,7 @@ int gs_ring_setup(gs_plan* p)
     // direct path: transform buffer(s) + quarter twiddle table in one CTA; Mcap = largest power-of-two transform
     // length taken directly (two CTAs per SM).  Longer rings take the split path (n/4 per CTA).
     // (+ RF_NT entries: partial alias sums of rings shorter than their thread count, see ring_build_Z)
-    auto direct_smem = [&](int M, int twn) { return (size_t)((M + M / 16 + 8 + RF_NT) + twn / 4 + 1) * sizeof(double2); };
+    auto direct_smem = [&](int M, int twn) { return (size_t)((M + M / 16 + M / 256 + 16 + RF_NT) + twn / 4 + 1) * sizeof(double2); };
     int Mcap = 4;
     while (2 * direct_smem(2 * Mcap, 2 * Mcap) <= smem_max) Mcap *= 2;
     (void)L;
@@ -830,7 +923,7 @@ int gs_ring_setup(gs_plan* p)
     p->d.max_M = maxM;
     p->d.tw_n = maxM;
     p->ring_smem = direct_smem(std::max(maxMd, std::min(4096, Mcap)), maxM);   // groups of short rings fill up to 4096 points
-    p->split_smem = (size_t)((maxMs + maxMs / 16 + 2) + maxM / 4 + 1) * sizeof(double2);
+    p->split_smem = (size_t)(PADLEN(maxMs) + maxM / 4 + 1) * sizeof(double2);
     if (p->ring_smem > smem_max || p->split_smem > smem_max) {
         gs_set_error("ring FFT needs %zu bytes of shared memory (> 227 KB): nside/lmax too large for this build", p->ring_smem);
         return GS_E_BADARG;
@@ -865,7 +958,7 @@ int gs_ring_setup(gs_plan* p)
     GS_CHECK_CUDA(cudaFuncSetAttribute(ring_synth_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GS_CHECK_CUDA(cudaFuncSetAttribute(ring_anal_split_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (!descs.empty()) {
-        const size_t bsm = (size_t)((maxM + maxM / 16 + 2) + maxM / 4 + 1) * sizeof(double2);
+        const size_t bsm = (size_t)(PADLEN(maxM) + maxM / 4 + 1) * sizeof(double2);
         bluestein_setup_kernel<<<(int)descs.size(), RF_NT, bsm>>>(p->d, (double2*)d, (int)descs.size());
         GS_CHECK_LAUNCH();
     }

@@ -365,6 +365,8 @@ void gs_pcg_ws_free(gs_plan* p)
 int g_gs_fuse_apq = 0;   // 1: fused analysis-finish + (q += C^-1 p, <p, q>) kernel in the unsharded PCG (measured 0.4 % SLOWER
                          // than the separate pass at NSIDE 512: 5125 block partials + a scalar kernel; kept as an option)
 extern "C" int gs_set_fuse_apq(int on) { const int old = g_gs_fuse_apq; g_gs_fuse_apq = on ? 1 : 0; return old; }
+int g_gs_pcg_graph = 1;   // 1: the iterations between two convergence polls of an unsharded PCG solve are replayed from a CUDA graph
+extern "C" int gs_set_pcg_graph(int on) { const int old = g_gs_pcg_graph; g_gs_pcg_graph = on ? 1 : 0; return old; }
 int g_gs_ring_fused = 1;
 extern "C" int gs_set_ring_fused(int fused) { const int old = g_gs_ring_fused; g_gs_ring_fused = fused ? 1 : 0; return old; }
 
@@ -463,28 +465,75 @@ static int cr_pcg_impl(gs_plan* p, int spin, const double* dl_EE, const double* 
     const bool fused_apq = !dist && g_gs_fuse_apq;
     int launched = 0;
     bool finished = false;
-    while (!finished) {
-        for (int k = 0; k < check_every && launched < itermax; ++k, ++launched) {
-            if ((rc = apply_noise_op(p, w->p[0], w->p[1], bl, inv_noise, w->q[0], w->q[1], st, done, spin, fused_apq ? &ff : nullptr))) return rc;
-            if (fused_apq) pcg_apq_scalar_kernel<<<1, 1, 0, st>>>(*w);
-            else pcg_apq_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, n, nc);
-            if (dist) {
-                if ((rc = gs_shard_allreduce(p, w->red, 1, st))) return rc;
-                pcg_scalar_kernel<<<1, 1, 0, st>>>(*w, 1);
-            }
-            pcg_update_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, x_E, x_B, n, nc);
-            if (dist) {
-                if ((rc = gs_shard_allreduce(p, w->red, 2, st))) return rc;
-                pcg_scalar_kernel<<<1, 1, 0, st>>>(*w, 2);
-            }
-            pcg_dir_kernel<<<SV_GRID, SV_NT, 0, st>>>(*w, n, nc);
-            GS_CHECK_LAUNCH();
-            g_gs_launches += 3;
+    // one PCG iteration: 7 launches whose arguments do not change during the solve (alpha, beta and the done flag live on the device)
+    auto iteration = [&](cudaStream_t s) -> int {
+        int r;
+        if ((r = apply_noise_op(p, w->p[0], w->p[1], bl, inv_noise, w->q[0], w->q[1], s, done, spin, fused_apq ? &ff : nullptr))) return r;
+        if (fused_apq) pcg_apq_scalar_kernel<<<1, 1, 0, s>>>(*w);
+        else pcg_apq_kernel<<<SV_GRID, SV_NT, 0, s>>>(*w, n, nc);
+        if (dist) {
+            if ((r = gs_shard_allreduce(p, w->red, 1, s))) return r;
+            pcg_scalar_kernel<<<1, 1, 0, s>>>(*w, 1);
         }
-        GS_CHECK_CUDA(cudaMemcpyAsync(w->host_state, w->state, sizeof(PcgState), cudaMemcpyDeviceToHost, st));
-        GS_CHECK_CUDA(cudaStreamSynchronize(st));
+        pcg_update_kernel<<<SV_GRID, SV_NT, 0, s>>>(*w, x_E, x_B, n, nc);
+        if (dist) {
+            if ((r = gs_shard_allreduce(p, w->red, 2, s))) return r;
+            pcg_scalar_kernel<<<1, 1, 0, s>>>(*w, 2);
+        }
+        pcg_dir_kernel<<<SV_GRID, SV_NT, 0, s>>>(*w, n, nc);
+        GS_CHECK_LAUNCH();
+        g_gs_launches += 3;
+        return GS_OK;
+    };
+    // Unsharded plans: the `check_every` iterations between two polls of the convergence flag are captured ONCE per solve in a
+    // CUDA graph on a stream of the plan (capture is not allowed on the legacy default stream) and replayed: one graph launch
+    // instead of 7 check_every kernel launches per poll (the host side of a solve was ~2300 launches; SCALE_r01 lost 1.8 % at 8
+    // GPUs to 8 processes doing that on shared cores).  gs_set_pcg_graph(0) restores plain launches.
+    cudaGraphExec_t gexec = nullptr;
+    long long launches_per_graph = 0;
+    if (g_gs_pcg_graph && !dist && itermax >= check_every) {
+        if (!p->work_stream) {
+            cudaStream_t ws = nullptr;
+            GS_CHECK_CUDA(cudaStreamCreateWithFlags(&ws, cudaStreamNonBlocking));
+            p->work_stream = ws;
+            cudaEvent_t ev = nullptr;
+            GS_CHECK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            p->work_event = ev;
+        }
+        cudaStream_t ws = (cudaStream_t)p->work_stream;
+        GS_CHECK_CUDA(cudaEventRecord((cudaEvent_t)p->work_event, st));
+        GS_CHECK_CUDA(cudaStreamWaitEvent(ws, (cudaEvent_t)p->work_event, 0));
+        st = ws;   // the rest of the solve runs here; every poll (and the return) synchronises it with the host
+        cudaGraph_t graph = nullptr;
+        const long long l0 = g_gs_launches;
+        GS_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        rc = GS_OK;
+        for (int k = 0; k < check_every && rc == GS_OK; ++k) rc = iteration(st);
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        launches_per_graph = g_gs_launches - l0;
+        g_gs_launches = l0;   // nothing ran yet: counted per replay below
+        if (rc != GS_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) { gs_set_error("PCG graph capture: %s", cudaGetErrorString(ce)); return GS_E_CUDA; }
+        ce = cudaGraphInstantiate(&gexec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { gs_set_error("PCG graph instantiate: %s", cudaGetErrorString(ce)); return GS_E_CUDA; }
+    }
+    while (!finished) {
+        if (gexec && launched + check_every <= itermax) {
+            cudaError_t ce = cudaGraphLaunch(gexec, st);
+            if (ce != cudaSuccess) { cudaGraphExecDestroy(gexec); gs_set_error("PCG graph launch: %s", cudaGetErrorString(ce)); return GS_E_CUDA; }
+            launched += check_every;
+            g_gs_launches += launches_per_graph;
+        } else {
+            for (int k = 0; k < check_every && launched < itermax; ++k, ++launched)
+                if ((rc = iteration(st))) { if (gexec) cudaGraphExecDestroy(gexec); return rc; }
+        }
+        cudaError_t ce = cudaMemcpyAsync(w->host_state, w->state, sizeof(PcgState), cudaMemcpyDeviceToHost, st);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) { if (gexec) cudaGraphExecDestroy(gexec); gs_set_error("PCG poll: %s", cudaGetErrorString(ce)); return GS_E_CUDA; }
         finished = w->host_state->done || launched >= itermax;
     }
+    if (gexec) cudaGraphExecDestroy(gexec);
     const PcgState& s = *w->host_state;
     if (n_iter_out) *n_iter_out = s.iter;
     if (resid_out) *resid_out = s.d0 > 0.0 ? sqrt(s.rr / s.d0) : 0.0;

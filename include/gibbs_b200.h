@@ -171,6 +171,11 @@ int gs_cr_pcg_pol_batch(gs_plan* plan, int n_chain, const double* dl_EE, const d
                         const double* rhs_B, double* x_E, double* x_B, int64_t stride, double eps, int itermax,
                         int check_every, int* n_iter_out, double* resid_out, void* stream);
 
+/* 1 (default): unsharded gs_cr_pcg_* solves capture the `check_every` iterations between two polls of the convergence flag in a
+ * CUDA graph (once per solve, on a stream owned by the plan and ordered after `stream`) and replay it; 0: plain launches.
+ * Returns the previous setting.  Same arithmetic either way. */
+int gs_set_pcg_graph(int on);
+
 /* y = Q x (qcinv opfilt_pp.fwd_op; CenteredGibbs.py:629, 653). */
 int gs_cr_apply_q_pol(gs_plan* plan, const double* dl_EE, const double* dl_BB, const double* bl,
                       const double* inv_noise, const double* x_E, const double* x_B, double* y_E,
