@@ -506,7 +506,10 @@ def sharded_measure(nside, lmax, steps, warmup):
                        "l2_policy": "inputs larger than L2"},
             "pcg_iterations_mean": n_pcg, "gpu_launches": launches, "sht_pair_ms": sum(st), "sht_pairs_per_s": 1e3 / sum(st),
             "stage_ms": {"leg_synth+a2a": st[0], "ring_synth": st[1], "ring_anal": st[2], "a2a+leg_anal": st[3]},
-            "a2a_ms_alone": a2a_ms, "legendre_ms_without_a2a": {"leg_synth": st[0] - a2a_ms, "leg_anal": st[3] - a2a_ms},
+            "a2a_ms_alone": a2a_ms, "a2a_blocks": int(os.environ.get("GS_SHARD_NB", "1")),
+            "a2a_note": "GS_SHARD_NB=k > 1 runs the ring <-> m all-to-all block of m by block of m on a communication stream, overlapped "
+                        "with the Legendre kernels of the neighbouring blocks (default 1: one exchange per transform; 4 blocks "
+                        "measured slower on 2 GPUs at NSIDE 1024, profiles/shard_overlap_r02.txt)", "legendre_ms_without_a2a": {"leg_synth": st[0] - a2a_ms, "leg_anal": st[3] - a2a_ms},
             "exposed_communication_fraction_of_pair": 2 * a2a_ms / sum(st) if sum(st) > 0 else None,
             "legendre_tflops_all_gpus": 2 * f2 / (max(st[0] + st[3] - 2 * a2a_ms, 1e-9) * 1e-3) * 1e-12,
             "a2a_bytes_sent_per_gpu_per_transform": exch_bytes,

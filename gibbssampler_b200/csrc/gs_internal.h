@@ -59,7 +59,13 @@ struct RingJob {  // one complex DFT = two real ring sequences of equal length
 struct ShardDev {
     int world, rank;
     int nm_loc;       // m owned by this rank
-    int ML, RL;       // per-rank m / ring counts, padded to the maximum over ranks
+    int ML, RL;       // per-rank m / ring counts, padded to the maximum over ranks (ML = NB * MLb)
+    // r02: the local m are cut in NB blocks of MLb so that the all-to-all can run block by block, overlapped with the Legendre
+    // stage of the neighbouring block: element (ring, m) lives at
+    //   ((((blk * world + peer) * 2 + comp) * RL + ring_loc[ring]) * MLb + (mloc % MLb),  blk = mloc / MLb
+    // with mloc = index of m in its owner's list; peer as above.  NB = 1 is the single-exchange layout.
+    int NB, MLb;
+    const int64_t* m_base;   // [L+1] ring-sharded side: ((blk * world + m_owner[m]) * 2 * RL) * MLb + (m_loc[m] % MLb)
     int64_t nalm_loc; // complex coefficients owned: sum over owned m of (L - m + 1)
     const int* mlist;        // [nm_loc] owned m, ascending
     const int64_t* cbase;    // [nm_loc] index of (l = m) in the local complex numbering
@@ -175,6 +181,8 @@ struct gs_plan {
     void* pcg_ws;       // gs_pcg_ws* (solver.cu): PCG vectors / state of this plan, allocated on the first solve
     void* pcg_ws_batch; // gs_pcg_ws[2]: workspaces of a two-chain batch (gs_cr_pcg_pol_batch), allocated on first use
     int* pcg_alldone;   // device flag: both chains of the batch have converged
+    void* comm_stream;  // cudaStream_t the block-wise all-to-all of a sharded plan runs on (NULL until first used)
+    std::vector<void*> comm_events;   // cudaEvent_t: NB + 1 of them
     void* work_stream;  // cudaStream_t of the plan for graph-captured solves (NULL until first used)
     void* work_event;   // cudaEvent_t ordering work_stream after the caller's stream
 };
@@ -233,7 +241,11 @@ void gs_pcg_ws_free(gs_plan* p);
 // shard.cu
 int gs_shard_build(gs_plan* p, int rank, int world, const char* nccl_id);
 void gs_shard_free(gs_plan* p);
-// all-to-all of the spectra buffers (ring <-> m transpose): send -> recv, chunk = 2 RL ML double2 per peer
+// all-to-all of the spectra buffers (ring <-> m transpose): send -> recv, all NB blocks (chunk = 2 RL MLb double2 per peer and block)
 int gs_shard_exchange(gs_plan* p, const double2* send, double2* recv, cudaStream_t st);
+// one block of it (collective; blocks must be exchanged in the same order on every rank)
+int gs_shard_exchange_block(gs_plan* p, const double2* send, double2* recv, int blk, cudaStream_t st);
+// streams / events of the pipelined exchange (NCCL plans): comm stream and NB + 1 events, created on first use
+int gs_shard_pipeline(gs_plan* p, cudaStream_t* comm, cudaEvent_t** events);
 // in-place sum over ranks of n doubles (device)
 int gs_shard_allreduce(gs_plan* p, double* buf, int n, cudaStream_t st);

@@ -278,11 +278,14 @@ __device__ __forceinline__ void fetch_alm_nc(const PlanDev& P, int m, int l, int
 }
 
 // Position of F_m(ring) of component comp in the ring-spectra buffer.  Unsharded: [comp][ring][m].
-// Sharded (SH): [peer = owner of the ring][comp][ring_loc][mk], mk = index of m in this rank's m list.
+// Sharded (SH): [block of mk][peer = owner of the ring][comp][ring_loc][mk within the block], mk = index of m in this rank's m list.
 template <bool SH>
 __device__ __forceinline__ int64_t fm_index(const PlanDev& P, int comp, int ring, int m, int mk)
 {
-    if (SH) return (((int64_t)P.sh.ring_owner[ring] * 2 + comp) * P.sh.RL + P.sh.ring_loc[ring]) * P.sh.ML + mk;
+    if (SH) {
+        const int blk = mk / P.sh.MLb, w = mk - blk * P.sh.MLb;
+        return ((((int64_t)blk * P.sh.world + P.sh.ring_owner[ring]) * 2 + comp) * P.sh.RL + P.sh.ring_loc[ring]) * P.sh.MLb + w;
+    }
     return ((int64_t)comp * P.nring + ring) * (P.lmax + 1) + m;
 }
 // offset such that entry (l, m) of the real layout sits at roff + (m ? 2 : 1) * l
@@ -332,10 +335,10 @@ __global__ void LEG_SYNTH_BOUNDS
 leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __restrict__ almB, int layout,
                  const double* __restrict__ fl, const double* __restrict__ flB, double2* __restrict__ Fm,
                  const int* __restrict__ skip, const int* __restrict__ plist, const int* __restrict__ pcount,
-                 const int* __restrict__ slot0, int64_t alm_stride, int64_t fm_stride)
+                 const int* __restrict__ slot0, int64_t alm_stride, int64_t fm_stride, int mk0)
 {
     if (skip && *skip) return;
-    const int L = P.lmax, mk = blockIdx.y, m = SH ? P.sh.mlist[mk] : mk, tid = threadIdx.x;
+    const int L = P.lmax, mk = blockIdx.y + mk0, m = SH ? P.sh.mlist[mk] : mk, tid = threadIdx.x;   // mk0: first m of this launch (block-wise sharded pipeline)
     // Ring pairs run from the pole to the equator and lambda_lm is negligible on the pairs before slot0[m] (m > m_lim), so
     // for this m the grid packs the pairs from slot0[m] on: the k-th slot works on pair slot0[m] + k, or on
     // plist[slot0[m] + k] when a compacted list of the pairs with non-zero pixel weight is given (gs_active_rings_build);
@@ -520,7 +523,7 @@ leg_synth_kernel(PlanDev P, const double* __restrict__ almE, const double* __res
                 F[in] = make_double2(a.sqr + a.aqr, a.sqi + a.aqi);
                 if (rs != rn) F[is] = make_double2(sg * (a.sqr - a.aqr), sg * (a.sqi - a.aqi));
             } else {
-                const int64_t cs = SH ? (int64_t)P.sh.RL * P.sh.ML : (int64_t)P.nring * (L + 1);  // component stride
+                const int64_t cs = SH ? (int64_t)P.sh.RL * P.sh.MLb : (int64_t)P.nring * (L + 1);  // component stride
                 F[in] = make_double2(a.sqr + a.sqi, a.sur + a.sui);
                 F[in + cs] = make_double2(a.sur - a.sui, a.sqi - a.sqr);
                 if (rs != rn) {
@@ -858,10 +861,10 @@ template <int SPIN, int R, bool SH, int NC>
 __global__ void __launch_bounds__(LEG_NT, LEG_MINB_A)
 leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ partial, const int* __restrict__ skip,
                 const int* __restrict__ plist, const int* __restrict__ pcount, const int* __restrict__ slot0, int64_t fm_stride,
-                int64_t part_stride)
+                int64_t part_stride, int mk0)
 {
     if (skip && *skip) return;
-    const int L = P.lmax, mk = blockIdx.y, m = SH ? P.sh.mlist[mk] : mk, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int L = P.lmax, mk = blockIdx.y + mk0, m = SH ? P.sh.mlist[mk] : mk, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     // slots of this m: see leg_synth_kernel; leg_finish_kernel sums the chunks that hold slots only
     const int s0 = slot0[m], nact = (plist ? *pcount : P.npair) - s0;
     if ((int)blockIdx.x * (LEG_NT * R) >= nact) return;
@@ -885,7 +888,7 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
     const int64_t pbase = SH ? (int64_t)blockIdx.x * P.sh.nalm_loc + P.sh.cbase[mk] - m : (int64_t)blockIdx.x * P.nalm + base;
     const int chunk = blockIdx.x * (LEG_NT * R);
     const bool odd0 = (l0 + m) & 1;
-    const int64_t cs = SH ? (int64_t)P.sh.RL * P.sh.ML : (int64_t)P.nring * (L + 1);  // component stride
+    const int64_t cs = SH ? (int64_t)P.sh.RL * P.sh.MLb : (int64_t)P.nring * (L + 1);  // component stride
 
     RingState<SPIN> st[R];
     AnalIn<SPIN> G[R][NC];
@@ -1466,28 +1469,52 @@ int gs_leg_synth(gs_plan* p, int spin, const double* almE, const double* almB, i
     const int* slot0 = plist ? p->act_slot0 + (spin ? p->d.lmax + 1 : 0) : (spin ? p->d.pmin2 : p->d.pmin0);
     const int64_t fs = gs_fm_stride(p);
     if (nc == 2) {
-        if (spin == 0) leg_synth_kernel<0, LEG_R2, false, 2><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, alm_stride, fs);
-        else leg_synth_kernel<2, LEG_R2, false, 2><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, alm_stride, fs);
+        if (spin == 0) leg_synth_kernel<0, LEG_R2, false, 2><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, alm_stride, fs, 0);
+        else leg_synth_kernel<2, LEG_R2, false, 2><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, alm_stride, fs, 0);
     } else if (!sh) {
-        if (spin == 0) leg_synth_kernel<0, LEG_R, false, 1><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, 0, 0);
-        else leg_synth_kernel<2, LEG_R, false, 1><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, 0, 0);
+        if (spin == 0) leg_synth_kernel<0, LEG_R, false, 1><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, 0, 0, 0);
+        else leg_synth_kernel<2, LEG_R, false, 1><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, 0, 0, 0);
     } else {
-        if (spin == 0) leg_synth_kernel<0, LEG_R, true, 1><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, 0, 0);
-        else leg_synth_kernel<2, LEG_R, true, 1><<<grid, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, 0, 0);
+        // m-sharded -> ring-sharded (the ring stage reads p->Fx), block of m by block of m: while the all-to-all of block b runs on
+        // the plan's communication stream, the Legendre kernel of block b + 1 runs on `st`.  In-process test groups
+        // exchange on `st` itself (host barriers).
+        const ShardDev& S = p->d.sh;
+        cudaStream_t comm = st;
+        cudaEvent_t* ev = nullptr;
+        const bool pipelined = !p->lgroup && S.NB > 1;
+        if (pipelined && (rc = gs_shard_pipeline(p, &comm, &ev))) return rc;
+        for (int b = 0; b < S.NB; ++b) {
+            const int mk0 = b * S.MLb, cnt = std::min(S.MLb, S.nm_loc - mk0);
+            if (cnt > 0) {
+                dim3 g(grid.x, cnt);
+                if (spin == 0) leg_synth_kernel<0, LEG_R, true, 1><<<g, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, 0, 0, mk0);
+                else leg_synth_kernel<2, LEG_R, true, 1><<<g, LEG_NT, 0, st>>>(p->d, almE, almB, layout, fl, flB, p->Fm, skip, plist, pcount, slot0, 0, 0, mk0);
+                GS_CHECK_LAUNCH();
+                g_gs_launches += 1;
+            }
+            if (pipelined) {
+                GS_CHECK_CUDA(cudaEventRecord(ev[b], st));
+                GS_CHECK_CUDA(cudaStreamWaitEvent(comm, ev[b], 0));
+            }
+            if ((rc = gs_shard_exchange_block(p, p->Fm, p->Fx, b, comm))) return rc;
+        }
+        if (pipelined) {
+            GS_CHECK_CUDA(cudaEventRecord(ev[S.NB], comm));
+            GS_CHECK_CUDA(cudaStreamWaitEvent(st, ev[S.NB], 0));
+        }
+        return GS_OK;
     }
     GS_CHECK_LAUNCH();
     g_gs_launches += 1;
-    // m-sharded -> ring-sharded: the ring stage reads p->Fx
-    if (sh) return gs_shard_exchange(p, p->Fm, p->Fx, st);
     return GS_OK;
 }
 
 template <int SPIN, int R, bool SH, int NC>
 static int launch_anal(gs_plan* p, dim3 grid, cudaStream_t st, const int* skip, const int* plist, const int* pcount, const int* slot0,
-                       int64_t fs, int64_t ps)
+                       int64_t fs, int64_t ps, int mk0 = 0)
 {
     constexpr size_t sm = leg_anal_smem<SPIN, NC>();   // opt-in size set by gs_leg_prepare at plan creation
-    leg_anal_kernel<SPIN, R, SH, NC><<<grid, LEG_NT, sm, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount, slot0, fs, ps);
+    leg_anal_kernel<SPIN, R, SH, NC><<<grid, LEG_NT, sm, st>>>(p->d, p->Fm, p->partial, skip, plist, pcount, slot0, fs, ps, mk0);
     GS_CHECK_LAUNCH();
     return GS_OK;
 }
@@ -1523,10 +1550,7 @@ int gs_leg_anal(gs_plan* p, int spin, double* almE, double* almB, int layout, co
     const int* slot0 = plist ? p->act_slot0 + (spin ? p->d.lmax + 1 : 0) : (spin ? p->d.pmin2 : p->d.pmin0);
     const int64_t fs = gs_fm_stride(p), ps = gs_part_stride(p, nc);
     const int cp = LEG_NT * (nc > 1 ? LEG_RA2 : LEG_RA);   // ring pairs per chunk
-    if (sh) {  // ring-sharded (p->Fx, written by the ring analysis) -> m-sharded
-        rc = gs_shard_exchange(p, p->Fx, p->Fm, st);
-        if (rc) return rc;
-    }
+
     if (nc == 2) {
         if (fuse) { gs_set_error("gs_leg_anal: the fused finish takes one right-hand side"); return GS_E_BADARG; }
         if (spin == 0) {
@@ -1554,13 +1578,32 @@ int gs_leg_anal(gs_plan* p, int spin, double* almE, double* almB, int layout, co
             leg_finish_kernel<2, false><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, cp, 0, 0);
         }
     } else {
-        if (spin == 0) {
-            if ((rc = launch_anal<0, LEG_RA, true, 1>(p, grid, st, skip, plist, pcount, slot0, 0, 0))) return rc;
-            leg_finish_kernel<0, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, cp, 0, 0);
-        } else {
-            if ((rc = launch_anal<2, LEG_RA, true, 1>(p, grid, st, skip, plist, pcount, slot0, 0, 0))) return rc;
-            leg_finish_kernel<2, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, cp, 0, 0);
+        // ring-sharded (p->Fx, written by the ring analysis) -> m-sharded, block by block: the all-to-all of block b + 1 runs on the
+        // communication stream while the Legendre kernel of block b runs on `st`
+        const ShardDev& S = p->d.sh;
+        cudaStream_t comm = st;
+        cudaEvent_t* ev = nullptr;
+        const bool pipelined = !p->lgroup && S.NB > 1;
+        if (pipelined) {
+            if ((rc = gs_shard_pipeline(p, &comm, &ev))) return rc;
+            GS_CHECK_CUDA(cudaEventRecord(ev[S.NB], st));
+            GS_CHECK_CUDA(cudaStreamWaitEvent(comm, ev[S.NB], 0));
         }
+        for (int b = 0; b < S.NB; ++b) {
+            if ((rc = gs_shard_exchange_block(p, p->Fx, p->Fm, b, comm))) return rc;
+            if (pipelined) {
+                GS_CHECK_CUDA(cudaEventRecord(ev[b], comm));
+                GS_CHECK_CUDA(cudaStreamWaitEvent(st, ev[b], 0));
+            }
+            const int mk0 = b * S.MLb, cnt = std::min(S.MLb, S.nm_loc - mk0);
+            if (cnt <= 0) continue;
+            dim3 g(grid.x, cnt);
+            if (spin == 0) rc = launch_anal<0, LEG_RA, true, 1>(p, g, st, skip, plist, pcount, slot0, 0, 0, mk0);
+            else rc = launch_anal<2, LEG_RA, true, 1>(p, g, st, skip, plist, pcount, slot0, 0, 0, mk0);
+            if (rc) return rc;
+        }
+        if (spin == 0) leg_finish_kernel<0, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, cp, 0, 0);
+        else leg_finish_kernel<2, true><<<fgrid, 256, 0, st>>>(p->d, p->partial, nchunk, almE, almB, layout, fl, scale, accumulate, skip, pcount, slot0, cp, 0, 0);
     }
     GS_CHECK_LAUNCH();
     g_gs_launches += 2;

@@ -259,6 +259,7 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
     p->pcg_alldone = nullptr;
     p->work_stream = nullptr;
     p->work_event = nullptr;
+    p->comm_stream = nullptr;
     p->chain_cap = 1;
     p->Fx = nullptr;
     p->red_loc = nullptr;
@@ -272,7 +273,7 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
     if (rc == GS_OK && world > 1) rc = gs_shard_build(p, rank, world, nccl_id);
     if (rc == GS_OK) rc = gs_ring_setup(p);
     if (rc == GS_OK) {
-        const size_t nfm = world > 1 ? (size_t)world * 2 * p->d.sh.RL * p->d.sh.ML : (size_t)2 * p->d.nring * nm;
+        const size_t nfm = world > 1 ? (size_t)world * 2 * p->d.sh.RL * p->d.sh.ML : (size_t)2 * p->d.nring * nm;   // ML = NB MLb
         rc = dev_alloc(p, nfm, &p->Fm);
         if (rc == GS_OK && world > 1) rc = dev_alloc(p, nfm, &p->Fx);
         // the padding entries of the spectra buffers are exchanged but never read; keep them finite
@@ -357,6 +358,8 @@ extern "C" int gs_plan_destroy(gs_plan* p)
     if (!p) return GS_OK;
     gs_pcg_ws_free(p);
     gs_shard_free(p);
+    for (void* e : p->comm_events) cudaEventDestroy((cudaEvent_t)e);
+    if (p->comm_stream) cudaStreamDestroy((cudaStream_t)p->comm_stream);
     if (p->work_event) cudaEventDestroy((cudaEvent_t)p->work_event);
     if (p->work_stream) cudaStreamDestroy((cudaStream_t)p->work_stream);
     for (void* d : p->owned) cudaFree(d);

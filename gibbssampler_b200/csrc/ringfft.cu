@@ -317,7 +317,7 @@ __device__ __forceinline__ double2 ring_phase(const PlanDev& P, int ring, int m)
 template <bool SH>
 __device__ __forceinline__ int64_t fm_ring_index(const PlanDev& P, int comp, int ring, int m)
 {
-    if (SH) return (((int64_t)P.sh.m_owner[m] * 2 + comp) * P.sh.RL + P.sh.ring_loc[ring]) * P.sh.ML + P.sh.m_loc[m];
+    if (SH) return P.sh.m_base[m] + ((int64_t)comp * P.sh.RL + P.sh.ring_loc[ring]) * P.sh.MLb;   // see ShardDev
     return ((int64_t)comp * P.nring + ring) * (P.lmax + 1) + m;
 }
 template <bool SH>

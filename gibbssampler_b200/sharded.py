@@ -66,16 +66,20 @@ def pixel_index(nside, world, rank):
     return out
 
 
-def pack_spectra(values, ring_lists, m_list, RL, ML):
-    """Host model of the all-to-all send buffer [peer][comp][RL][ML] of an m-owner: values[comp][ring][k]
-    for k over m_list.  Used by the CPU (gloo) test of the exchange layout; the CUDA kernels write the
-    same positions (ShardDev in csrc/gs_internal.h)."""
+def pack_spectra(values, ring_lists, m_list, RL, ML, nb=1):
+    """Host model of the all-to-all send buffer [block][peer][comp][RL][MLb] of an m-owner: values[comp][ring][k]
+    for k over m_list, the local m cut in `nb` blocks of MLb = ceil(ML / nb) so that the exchange can run block by block
+    (one all-to-all of [peer][comp][RL][MLb] chunks per block).  nb = 1 is the single-exchange layout [peer][comp][RL][ML].
+    Used by the CPU (gloo) test of the exchange layout; the CUDA kernels write the same positions (ShardDev in
+    csrc/gs_internal.h)."""
     world = len(ring_lists)
     ncomp = values.shape[0]
-    buf = np.zeros((world, ncomp, RL, ML), dtype=values.dtype)
+    mlb = (ML + nb - 1) // nb
+    buf = np.zeros((nb, world, ncomp, RL, mlb), dtype=values.dtype)
     for peer, rings in enumerate(ring_lists):
-        buf[peer, :, :len(rings), :len(m_list)] = values[:, rings, :]
-    return buf
+        for k in range(len(m_list)):
+            buf[k // mlb, peer, :, :len(rings), k % mlb] = values[:, rings, k]
+    return buf if nb > 1 else buf[0]
 
 
 # ---------------------------------------------------------------------------- the plan

@@ -99,6 +99,19 @@ def _worker(rank, world, port, nside, lmax, out):
     back = torch.empty_like(send)
     dist.all_to_all_single(back, recv)
     ok &= torch.equal(back, send)
+    # blocked layout (pipelined exchange: one all-to-all per block of local m): element (ring, m) must sit at
+    # [m_loc // MLb][m_owner][comp][ring_loc][m_loc % MLb]
+    for nb in (2, 3):
+        mlb = (ML + nb - 1) // nb
+        sendb = torch.from_numpy(S.pack_spectra(vals, ring_lists, mine, RL, ML, nb=nb))
+        recvb = torch.empty_like(sendb)
+        for b in range(nb):
+            dist.all_to_all_single(recvb[b], sendb[b])
+        for src in range(world):
+            for k, m in enumerate(m_lists[src]):
+                for j, r in enumerate(ring_lists[rank]):
+                    for c in range(2):
+                        ok &= recvb[k // mlb, src, c, j, k % mlb].item() == _f(c, r, m)
     res = torch.tensor([1 if ok else 0])
     dist.all_reduce(res, op=dist.ReduceOp.MIN)
     if rank == 0:

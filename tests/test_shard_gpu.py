@@ -40,10 +40,12 @@ def full_inputs(nside, lmax, seed):
     return e, b, q, u, w, fl
 
 
-@pytest.mark.parametrize("nside,lmax,world", [(8, 16, 2), (16, 47, 3), (32, 64, 4), (64, 128, 8), (128, 256, 2)])
-def test_local_group_transforms_match_single_gpu(nside, lmax, world):
+@pytest.mark.parametrize("nside,lmax,world,nb", [(8, 16, 2, 1), (16, 47, 3, 3), (32, 64, 4, 2), (64, 128, 8, 4), (128, 256, 2, 4)])
+def test_local_group_transforms_match_single_gpu(nside, lmax, world, nb, monkeypatch):
+    """nb: blocks of local m of the spectra layout (GS_SHARD_NB; production: 4 from 128 local m on), one all-to-all per block."""
     from gibbssampler_b200.sharded import ShardedPlan, run_local_group
     from gibbssampler_b200.sht import Plan
+    monkeypatch.setenv("GS_SHARD_NB", str(nb))
     ref = Plan.get(nside, lmax)
     e, b, q, u, w, fl = full_inputs(nside, lmax, 5 + nside)
     rq, ru = ref.alm2map_spin2(e, b, fl=fl)
@@ -150,13 +152,14 @@ def test_local_group_cr_solve_matches_single_gpu(nside, lmax, world):
     assert relerr(join("e"), sol["EE"]) < 1e-7 and relerr(join("b"), sol["BB"]) < 1e-7
 
 
-@pytest.mark.parametrize("world", [2])
-def test_nccl_sharded_sht_and_gibbs(world):
-    """Production path: one process per GPU, NCCL all-to-all; needs >= `world` GPUs on the box."""
+@pytest.mark.parametrize("world,nb", [(2, 1), (2, 4)])
+def test_nccl_sharded_sht_and_gibbs(world, nb):
+    """Production path: one process per GPU, NCCL all-to-all; needs >= `world` GPUs on the box.  nb = 4: the exchange runs block by
+    block on the plan's communication stream, overlapped with the Legendre kernels of the neighbouring blocks."""
     if torch.cuda.device_count() < world:
         pytest.skip("needs %d GPUs" % world)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
-           "127.0.0.1", "--master-port", "29631", os.path.join(ROOT, "tests", "shard_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+           "127.0.0.1", "--master-port", str(29631 + nb), os.path.join(ROOT, "tests", "shard_worker.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, GS_SHARD_NB=str(nb)))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "SHARD_WORKER_OK" in out.stdout
