@@ -48,6 +48,13 @@
 #else
 #define LEG_SYNTH_BOUNDS __launch_bounds__(LEG_NT)
 #endif
+#ifndef LEG_SMEMRED
+#define LEG_SMEMRED 0   // spin-2 analysis fast loop: the WHOLE sum over the 32 lanes goes through shared memory (no shuffles in the loop)
+#endif
+#if LEG_SMEMRED
+#define LEG_FOLD2 0
+#define LEG_FOLD3 0
+#endif
 #ifndef LEG_FOLD2
 #define LEG_FOLD2 1  // spin-2 analysis: lane-permuted inputs so that the warp reduce-scatter needs one select stage instead of three
 #endif
@@ -853,7 +860,8 @@ template <int SPIN, int NC>
 constexpr size_t leg_anal_smem()
 {
     return sizeof(double2) * LEG_TL + sizeof(double) * LEG_NW * NC * LEG_TL * (SPIN ? 4 : 2)
-           + ((SPIN && LEG_FOLD2 && LEG_FOLD3) ? sizeof(double2) * LEG_NW * NC * FOLD3_NB * 32 : 0);
+           + ((SPIN && LEG_FOLD2 && LEG_FOLD3) ? sizeof(double2) * LEG_NW * NC * FOLD3_NB * 32 : 0)
+           + ((SPIN && LEG_SMEMRED) ? sizeof(double2) * LEG_NW * NC * (NC == 1 ? 4 : 2) * 4 * 32 : 0);
 }
 // NC > 1: chain batch (see leg_synth_kernel): spectra of chain c at Fm + c fm_stride, partial sums at partial + c part_stride;
 // the recurrence of a (ring pair, m) thread is shared, the reduce-scatter runs once per chain.
@@ -881,6 +889,13 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
     // pairs of l at a time (8 independent loads per output, no selects).  Slot of lane L for local pair q:
     // L ^ c(L) ^ ((q & 1) << 2): stores are conflict free and the 32 outputs read in one step hit 16 distinct 8-byte banks.
     double2* sFoldAll = reinterpret_cast<double2*>(sPartAll + (size_t)LEG_NW * NC * LEG_TL * NV);   // [LEG_NW][NC][FOLD3_NB * 32] (spin 2)
+#endif
+#if LEG_SMEMRED
+    // Every lane parks its 8 values of a pair of l as 4 double2 rows [pair][value pair][lane]; NBQ pairs at a time a lane sums half
+    // a row (16 lanes, rotated start: conflict free) with LDS.128, the two halves meet in one shuffle.  No shuffle, select or
+    // lane-dependent slot in the accumulation loop; fixed summation order.
+    constexpr int NBQ = NC == 1 ? 4 : 2;
+    double2* sRedAll = reinterpret_cast<double2*>(sPartAll + (size_t)LEG_NW * NC * LEG_TL * NV);   // [LEG_NW][NC][NBQ * 4 * 32] (spin 2)
 #endif
     const int l0 = m > SPIN ? m : SPIN;
     const int64_t base = (int64_t)m * (2 * L + 1 - m) / 2;
@@ -1152,6 +1167,66 @@ leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ 
                     fbuf[q * 32 + (lane ^ cperm ^ ((q & 1) << 2))] = make_double2(vv[0], vv[4]);
                 }
                 if (q == FOLD3_NB - 1) { flush(FOLD3_NB); ipb = ip + 1; }
+            }
+            if (ip > ipb) flush(ip - ipb);
+        } else
+#endif
+#if LEG_SMEMRED
+        if (SPIN == 2) {
+            int ipb = ip;
+            auto flush = [&](int n) {
+                __syncwarp();
+                const int row = lane & 15, half = lane >> 4;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    const double2* rb = sRedAll + ((size_t)(w * NC + c)) * (NBQ * 4 * 32) + row * 32;
+                    double sx = 0.0, sy = 0.0;
+                    if (row < 4 * n) {
+                        double2 a[16];
+#pragma unroll
+                        for (int k = 0; k < 16; ++k) a[k] = rb[(half * 16 + k + row) & 31];
+#pragma unroll
+                        for (int st2 = 8; st2 >= 1; st2 >>= 1)
+#pragma unroll
+                            for (int k = 0; k < st2; ++k) { a[k].x += a[k + st2].x; a[k].y += a[k + st2].y; }
+                        sx = a[0].x; sy = a[0].y;
+                    }
+                    sx += __shfl_xor_sync(FULL, sx, 16);
+                    sy += __shfl_xor_sync(FULL, sy, 16);
+                    if (half == 0 && row < 4 * n) {
+                        double* o = sPart(w, c) + (ipb + (row >> 2)) * NVAL + 2 * (row & 3);
+                        o[0] = sx; o[1] = sy;
+                    }
+                }
+                __syncwarp();
+            };
+#pragma unroll kUnrollA
+            for (; ip < npr; ++ip) {  // (C)
+                double v[NC][NVAL];
+                const double2 r0 = sR[2 * ip], r1 = sR[2 * ip + 1];
+#pragma unroll
+                for (int j = 0; j < R; ++j) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        if (j == 0) ANAL_ACC(true, true, v[c], G[j][c], st[j].pc, st[j].mc);
+                        else ANAL_ACC(true, false, v[c], G[j][c], st[j].pc, st[j].mc);
+                    }
+                    rec_step<SPIN>(st[j], r0.x, r0.y);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        if (j == 0) ANAL_ACC(false, true, v[c] + NV, G[j][c], st[j].pc, st[j].mc);
+                        else ANAL_ACC(false, false, v[c] + NV, G[j][c], st[j].pc, st[j].mc);
+                    }
+                    rec_step<SPIN>(st[j], r1.x, r1.y);
+                }
+                const int q = ip - ipb;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) {
+                    double2* rb = sRedAll + ((size_t)(w * NC + c)) * (NBQ * 4 * 32) + q * 4 * 32 + lane;
+#pragma unroll
+                    for (int cp = 0; cp < 4; ++cp) rb[cp * 32] = make_double2(v[c][2 * cp], v[c][2 * cp + 1]);
+                }
+                if (q == NBQ - 1) { flush(NBQ); ipb = ip + 1; }
             }
             if (ip > ipb) flush(ip - ipb);
         } else
