@@ -54,7 +54,10 @@ class ClsSampler():
             alphas = np.array([np.sum(exponent[edges[i]:edges[i + 1]]) - 1 for i in range(nb)])
             alphas[0] = 1
             inject = f64(1.0 / invgamma.rvs(a=alphas))
-        self._call += 1
+        # the call index comes from the SHARED generator's counter: samplers that share an Rng (EE / BB, several chains built with
+        # one seed) never repeat a gamma stream, and the gamma domain (tag in the top byte, sampler.cu) is disjoint from the normals
+        self.rng.counter += 1
+        self._call = self.rng.counter
         check(_lib.lib().gs_cls_invgamma(ptr(cl), ptr(_dev.i32(edges)), nb, ptr(inject), self.rng.seed,
                                          self._call, ptr(out), None, None, stream()))
         return out

@@ -82,7 +82,8 @@ class JointClsSampler():
         (L+1) Gamma variates for parity runs; default Philox."""
         L = _lib.lib()
         ch = self.empirical(alms)
-        self._call += 1
+        self.rng.counter += 2          # shared generator counter (see ClsSampler._invgamma_draw): one index per draw kernel
+        self._call = self.rng.counter - 1
         tt, te, ee = (torch.empty(self.lmax + 1, dtype=torch.float64, device=self.dev) for _ in range(3))
         inj = f64(inject).contiguous() if inject is not None else None
         check(L.gs_cls_invwishart(ptr(ch["TT"]), ptr(ch["TE"]), ptr(ch["EE"]), self.lmax, ptr(inj), self.rng.seed, self._call,
@@ -91,7 +92,7 @@ class JointClsSampler():
         c2d = ell * (ell + 1) / (2 * np.pi)
         bb = torch.empty(self.lmax + 1, dtype=torch.float64, device=self.dev)
         gi = f64(gamma_inject).contiguous() if gamma_inject is not None else None
-        check(L.gs_cls_invgamma(ptr(ch["BB"]), ptr(self.bins1), self.lmax + 1, ptr(gi), self.rng.seed, (1 << 30) + self._call,
+        check(L.gs_cls_invgamma(ptr(ch["BB"]), ptr(self.bins1), self.lmax + 1, ptr(gi), self.rng.seed, self._call + 1,
                                 ptr(bb), None, None, stream()))
         return {"TT": tt * c2d, "TE": te * c2d, "EE": ee * c2d, "BB": bb}
 

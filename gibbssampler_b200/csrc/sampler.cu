@@ -161,7 +161,10 @@ __global__ void cls_invgamma_kernel(const double* __restrict__ cl_hat, const int
     if (beta_out) beta_out[b] = beta;
     double g;
     if (gamma_inject) g = gamma_inject[b];
-    else g = alpha > 0.0 ? gamma_mt(alpha, Philox(seed), (call << 20) + (uint64_t)b) : 1.0;
+    // Philox stream ids carry the consumer in the top byte: the running counters of gs_randn / gs_randu stay below 2^56, "G"amma
+    // draws sit at 0x47 << 56, the inverse-Wishart draws of teb.cu at 0x57 << 56, the fused chain of gibbs_step.cu at 0x43 / 0x47 with
+    // its own seed word: no consumer can walk into another one's streams however long the chain runs
+    else g = alpha > 0.0 ? gamma_mt(alpha, Philox(seed), (0x47ull << 56) | (((call << 20) + (uint64_t)b) & 0x00ffffffffffffffull)) : 1.0;
     out[b] = (b < 2) ? 0.0 : beta / g;
 }
 

@@ -794,7 +794,7 @@ extern "C" int gs_profile_matvec(gs_plan* p, const double* x_E, const double* x_
     double acc[4] = {0, 0, 0, 0};
     int rc = GS_OK;
     ActiveRings act(p);   // as in the PCG: rings without weight are skipped unless gs_set_ring_skip(0)
-    if ((rc = act.begin(inv_noise, st))) return rc;
+    if ((rc = act.begin(inv_noise, st))) { for (int i = 0; i < 5; ++i) cudaEventDestroy(ev[i]); return rc; }
     for (int r = 0; r < nrep && rc == GS_OK; ++r) {
         cudaEventRecord(ev[0], st);
         rc = gs_leg_synth(p, 2, x_E, x_B, GS_ALM_REAL, bl, st);
@@ -806,7 +806,7 @@ extern "C" int gs_profile_matvec(gs_plan* p, const double* x_E, const double* x_
         cudaEventRecord(ev[3], st);
         if (!rc) rc = gs_leg_anal(p, 2, y_E, y_B, GS_ALM_REAL, bl, 1.0, 0, st);
         cudaEventRecord(ev[4], st);
-        GS_CHECK_CUDA(cudaEventSynchronize(ev[4]));
+        if (cudaEventSynchronize(ev[4]) != cudaSuccess) { gs_set_error("gs_profile_matvec: %s", cudaGetErrorString(cudaGetLastError())); rc = GS_E_CUDA; break; }
         for (int i = 0; i < 4; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]); acc[i] += ms; }
     }
     for (int i = 0; i < 4; ++i) ms_out[i] = (float)(acc[i] / nrep);
@@ -882,13 +882,21 @@ extern "C" int gs_profile_pcg_vectors(gs_plan* p, int spin, int nrep, float* ms_
     for (int k = 0; k < 3; ++k) {
         double acc = 0.0;
         for (int rep = -2; rep < nrep; ++rep) {   // two warm-up launches
-            GS_CHECK_CUDA(cudaMemsetAsync(p->partial, 0, flush_bytes, st));
+            if (cudaMemsetAsync(p->partial, 0, flush_bytes, st) != cudaSuccess) {
+                gs_set_error("gs_profile_pcg_vectors: %s", cudaGetErrorString(cudaGetLastError()));
+                cudaEventDestroy(e0); cudaEventDestroy(e1);
+                return GS_E_CUDA;
+            }
             cudaEventRecord(e0, st);
             if (k == 0) pcg_apq_kernel<<<SV_GRID, SV_NT, 0, st>>>(v, n, nc);
             else if (k == 1) pcg_update_kernel<<<SV_GRID, SV_NT, 0, st>>>(v, p->almE_tmp, p->almB_tmp, n, nc);
             else pcg_dir_kernel<<<SV_GRID, SV_NT, 0, st>>>(v, n, nc);
             cudaEventRecord(e1, st);
-            GS_CHECK_CUDA(cudaEventSynchronize(e1));
+            if (cudaEventSynchronize(e1) != cudaSuccess) {
+                gs_set_error("gs_profile_pcg_vectors: %s", cudaGetErrorString(cudaGetLastError()));
+                cudaEventDestroy(e0); cudaEventDestroy(e1);
+                return GS_E_CUDA;
+            }
             float ms = 0;
             cudaEventElapsedTime(&ms, e0, e1);
             if (rep >= 0) acc += ms;

@@ -124,7 +124,7 @@ __global__ void invwishart_2x2_kernel(const double* __restrict__ tt, const doubl
     if (inject) { c1 = inject[3 * l]; c2 = inject[3 * l + 1]; z = inject[3 * l + 2]; }
     else {
         const Philox ph(seed);
-        const uint64_t base = (call << 22) + 4ull * (uint64_t)l;
+        const uint64_t base = (0x57ull << 56) | (((call << 22) + 4ull * (uint64_t)l) & 0x00ffffffffffffffull);   // "W"ishart domain (see sampler.cu)
         c1 = 2.0 * gamma_mt(0.5 * nu, ph, base);
         c2 = 2.0 * gamma_mt(0.5 * (nu - 1.0), ph, base + 1);
         double z2;
