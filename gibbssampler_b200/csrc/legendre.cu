@@ -865,8 +865,11 @@ constexpr size_t leg_anal_smem()
 }
 // NC > 1: chain batch (see leg_synth_kernel): spectra of chain c at Fm + c fm_stride, partial sums at partial + c part_stride;
 // the recurrence of a (ring pair, m) thread is shared, the reduce-scatter runs once per chain.
+#ifndef LEG_MINB_A2
+#define LEG_MINB_A2 LEG_MINB_A   // same for the chain batch (NC = 2)
+#endif
 template <int SPIN, int R, bool SH, int NC>
-__global__ void __launch_bounds__(LEG_NT, LEG_MINB_A)
+__global__ void __launch_bounds__(LEG_NT, (NC > 1 ? LEG_MINB_A2 : LEG_MINB_A))
 leg_anal_kernel(PlanDev P, const double2* __restrict__ Fm, double* __restrict__ partial, const int* __restrict__ skip,
                 const int* __restrict__ plist, const int* __restrict__ pcount, const int* __restrict__ slot0, int64_t fm_stride,
                 int64_t part_stride, int mk0)
