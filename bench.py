@@ -801,11 +801,14 @@ def main():
     # the HBM-bound vector kernels of one PCG iteration (algorithmic bytes: 4 + 7 + 4 arrays of 8 N_re bytes per field)
     ms3 = (C.c_float * 3)()
     _lib.check(L.gs_profile_pcg_vectors(plan._h, 2, 20, ms3, _dev.stream()))
-    vec_bytes = [4 * 2 * 8.0 * nre, 7 * 2 * 8.0 * nre, 4 * 2 * 8.0 * nre]
+    # r02: C^-1_l and M_l come from per-l tables through a 2-byte multipole index per coefficient: 3 + 6 + 3 passes over 8 N_re bytes
+    # per field (+ the index) instead of 4 + 7 + 4
+    vec_bytes = [(3 * 8.0 + 2.0) * 2 * nre, (6 * 8.0 + 2.0) * 2 * nre, (3 * 8.0 + 2.0) * 2 * nre]
     roofline_pcg = {"kernel": "pcg_apq + pcg_update + pcg_dir", "bound": "hbm",
                     "achieved": sum(vec_bytes) / (sum(ms3) * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": sum(vec_bytes) / (sum(ms3) * 1e-3) * 1e-9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
-                    "algorithmic_bytes_per_iteration": sum(vec_bytes),
+                    "algorithmic_bytes_per_iteration": sum(vec_bytes), "survey_minimum_bytes_per_iteration": 10 * 2 * 8.0 * nre,
+                    "frac_of_peak_on_survey_minimum": 10 * 2 * 8.0 * nre / (sum(ms3) * 1e-3) * 1e-9 / hbm_peak,
                     "ms": {"pcg_apq": ms3[0], "pcg_update": ms3[1], "pcg_dir": ms3[2]},
                     "gb_per_s": {"pcg_apq": vec_bytes[0] / ms3[0] * 1e-6, "pcg_update": vec_bytes[1] / ms3[1] * 1e-6,
                                  "pcg_dir": vec_bytes[2] / ms3[2] * 1e-6},

@@ -16,6 +16,7 @@
 #include <algorithm>
 
 #include "gs_internal.h"
+#include "rng.cuh"
 
 #define SV_NT 256
 #define SV_GRID (148 * 4)
@@ -28,6 +29,11 @@ struct PcgState {
 
 struct gs_pcg_ws {
     double *r[2], *p[2], *q[2], *invc[2], *pre[2];
+    // r02: the solver regenerates C^-1_l and the preconditioner M_l per coefficient from per-l tables (L1-resident) and a 2-byte
+    // multipole index per coefficient instead of streaming two expanded 8-byte arrays: 12 instead of 15 array passes per iteration
+    const unsigned short* lof;   // [n] multipole of every coefficient of the (local) real layout
+    const double* ic_l[2];       // [L+1] 1 / C_l (E, B)
+    const double* pre_l[2];      // [L+1] M_l
     double* partials;  // SV_GRID * 2
     double* fuse_partials;  // per-block partials of the fused analysis-finish + <p, q> kernel (unsharded plans)
     double* fuse_out;       // its result
@@ -147,7 +153,7 @@ pcg_init_kernel(gs_pcg_ws W, const double* bE, const double* bB, int have_q, int
         pick(i, n, c, j);
         double r = (c ? bB : bE)[j];
         if (have_q) r -= (c ? W.q[1] : W.q[0])[j];
-        const double z = (c ? W.pre[1] : W.pre[0])[j] * r;
+        const double z = (c ? W.pre_l[1] : W.pre_l[0])[W.lof[j]] * r;
         (c ? W.r[1] : W.r[0])[j] = r;
         (c ? W.p[1] : W.p[0])[j] = z;
         v[0] += r * r;
@@ -178,7 +184,8 @@ __global__ void __launch_bounds__(SV_NT) pcg_apq_kernel(gs_pcg_ws W, int64_t n, 
             int c; int64_t j;
             pick(i, n, c, j);
             const bool ok = i < total;
-            p[k] = ok ? (c ? W.p[1] : W.p[0])[j] : 0.0; q[k] = ok ? (c ? W.q[1] : W.q[0])[j] : 0.0; ic[k] = ok ? (c ? W.invc[1] : W.invc[0])[j] : 0.0;
+            p[k] = ok ? (c ? W.p[1] : W.p[0])[j] : 0.0; q[k] = ok ? (c ? W.q[1] : W.q[0])[j] : 0.0;
+            ic[k] = ok ? __ldg((c ? W.ic_l[1] : W.ic_l[0]) + W.lof[j]) : 0.0;
         }
 #pragma unroll
         for (int k = 0; k < SV_U; ++k) {
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(SV_NT) pcg_update_kernel(gs_pcg_ws W, double* 
             pick(i, n, c, j);
             const bool ok = i < total;
             x[k] = ok ? (c ? xB : xE)[j] : 0.0; p[k] = ok ? (c ? W.p[1] : W.p[0])[j] : 0.0; q[k] = ok ? (c ? W.q[1] : W.q[0])[j] : 0.0;
-            r[k] = ok ? (c ? W.r[1] : W.r[0])[j] : 0.0; pre[k] = ok ? (c ? W.pre[1] : W.pre[0])[j] : 0.0;
+            r[k] = ok ? (c ? W.r[1] : W.r[0])[j] : 0.0; pre[k] = ok ? __ldg((c ? W.pre_l[1] : W.pre_l[0]) + W.lof[j]) : 0.0;
         }
 #pragma unroll
         for (int k = 0; k < SV_U; ++k) {
@@ -250,7 +257,8 @@ __global__ void __launch_bounds__(SV_NT) pcg_dir_kernel(gs_pcg_ws W, int64_t n, 
             int c; int64_t j;
             pick(i, n, c, j);
             const bool ok = i < total;
-            p[k] = ok ? (c ? W.p[1] : W.p[0])[j] : 0.0; r[k] = ok ? (c ? W.r[1] : W.r[0])[j] : 0.0; pre[k] = ok ? (c ? W.pre[1] : W.pre[0])[j] : 0.0;
+            p[k] = ok ? (c ? W.p[1] : W.p[0])[j] : 0.0; r[k] = ok ? (c ? W.r[1] : W.r[0])[j] : 0.0;
+            pre[k] = ok ? __ldg((c ? W.pre_l[1] : W.pre_l[0]) + W.lof[j]) : 0.0;
         }
 #pragma unroll
         for (int k = 0; k < SV_U; ++k) {
@@ -289,6 +297,24 @@ __global__ void rhs_combine_kernel(double* rhs, const double* sic, const double*
         rhs[i] = fma(resc, rhs[i], fma(sic[i], xi[i], bdata[i]));
 }
 
+// multipole of every coefficient of the real layout (unsharded: index algebra of utils.py:49-76; sharded: the plan's l_of_loc)
+__global__ void lof_build_kernel(unsigned short* __restrict__ lof, const int* __restrict__ l_of_loc, int L, int64_t n)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        lof[i] = (unsigned short)(l_of_loc ? l_of_loc[i] : l_of_real(i, L));
+}
+static bool build_lof(gs_plan* p, const unsigned short** out)
+{
+    void* d = nullptr;
+    const int64_t n = p->nreal_loc;
+    if (cudaMalloc(&d, (size_t)n * sizeof(unsigned short)) != cudaSuccess) return false;
+    p->owned.push_back(d);
+    lof_build_kernel<<<SV_GRID, SV_NT>>>((unsigned short*)d, p->world > 1 ? p->d.sh.l_of_loc : nullptr, p->d.lmax, n);
+    if (cudaDeviceSynchronize() != cudaSuccess) return false;
+    *out = (const unsigned short*)d;
+    return true;
+}
+
 // ------------------------------------------------------------------ workspace
 // The workspace belongs to the plan (gs_plan::pcg_ws): created on the first solve, released by gs_plan_destroy through
 // gs_pcg_ws_free.  A plan is used by one host thread at a time (include/gibbs_b200.h), so no lock is taken.
@@ -302,6 +328,12 @@ static gs_pcg_ws* get_ws(gs_plan* p)
     bool ok = true;
     for (int c = 0; c < 2 && ok; ++c) ok = alloc(&w->r[c], n) && alloc(&w->p[c], n) && alloc(&w->q[c], n) && alloc(&w->invc[c], n) && alloc(&w->pre[c], n);
     ok = ok && alloc(&w->partials, SV_GRID * 2 + 4 * (size_t)(p->d.lmax + 1));
+    ok = ok && build_lof(p, &w->lof);
+    if (ok) {
+        double* tl = w->partials + SV_GRID * 2;   // [icE | preE | icB | preB], filled by precond_kernel at the start of a solve
+        const int L1 = p->d.lmax + 1;
+        w->ic_l[0] = tl; w->pre_l[0] = tl + L1; w->ic_l[1] = tl + 2 * L1; w->pre_l[1] = tl + 3 * L1;
+    }
     ok = ok && alloc(&w->fuse_partials, (size_t)((p->d.lmax + 256) / 256) * (p->d.lmax + 1));
     ok = ok && alloc(&w->fuse_out, 4);
     void* d = nullptr;
@@ -331,6 +363,12 @@ static gs_pcg_ws* get_ws_batch(gs_plan* p)
             ok = alloc(&w[k].r[c], n) && alloc(&w[k].invc[c], n) && alloc(&w[k].pre[c], n);
         }
         ok = ok && alloc(&w[k].partials, SV_GRID * 2 + 4 * (size_t)(p->d.lmax + 1));
+        if (ok) {
+            if (k == 0) ok = build_lof(p, &w[0].lof); else w[1].lof = w[0].lof;
+            double* tl = w[k].partials + SV_GRID * 2;
+            const int L1 = p->d.lmax + 1;
+            w[k].ic_l[0] = tl; w[k].pre_l[0] = tl + L1; w[k].ic_l[1] = tl + 2 * L1; w[k].pre_l[1] = tl + 3 * L1;
+        }
         w[k].fuse_partials = nullptr;
         ok = ok && alloc(&w[k].fuse_out, 4);
         void* d = nullptr;
@@ -429,10 +467,7 @@ static int cr_pcg_impl(gs_plan* p, int spin, const double* dl_EE, const double* 
     if (nc == 2) precond_kernel<<<lb, 256, 0, st>>>(dl_BB, bl, ninv_sum_over_4pi, L, tmp_l + 2 * (L + 1), tmp_l + 3 * (L + 1));
     GS_CHECK_LAUNCH();
     int rc;
-    if ((rc = gs_plan_expand_per_l(p, tmp_l, 0, w->invc[0], st))) return rc;
-    if ((rc = gs_plan_expand_per_l(p, tmp_l + (L + 1), 0, w->pre[0], st))) return rc;
-    if (nc == 2 && (rc = gs_plan_expand_per_l(p, tmp_l + 2 * (L + 1), 0, w->invc[1], st))) return rc;
-    if (nc == 2 && (rc = gs_plan_expand_per_l(p, tmp_l + 3 * (L + 1), 0, w->pre[1], st))) return rc;
+    // (the per-l tables are used as they are: the vector kernels index them with the multipole of each coefficient, w->lof)
     const bool dist = p->world > 1;
     ActiveRings act(p);
     if ((rc = act.begin(inv_noise, st))) return rc;
@@ -444,6 +479,8 @@ static int cr_pcg_impl(gs_plan* p, int spin, const double* dl_EE, const double* 
     *w->host_state = h;
     GS_CHECK_CUDA(cudaMemcpyAsync(w->state, w->host_state, sizeof(PcgState), cudaMemcpyHostToDevice, st));
     if (warm_start) {  // r0 = b - Q x0
+        if ((rc = gs_plan_expand_per_l(p, tmp_l, 0, w->invc[0], st))) return rc;
+        if (nc == 2 && (rc = gs_plan_expand_per_l(p, tmp_l + 2 * (L + 1), 0, w->invc[1], st))) return rc;
         if ((rc = apply_noise_op(p, x_E, x_B, bl, inv_noise, w->q[0], w->q[1], st, nullptr, spin))) return rc;
         axy_kernel<<<SV_GRID, SV_NT, 0, st>>>(w->q[0], w->invc[0], x_E, w->q[0], n);
         if (nc == 2) axy_kernel<<<SV_GRID, SV_NT, 0, st>>>(w->q[1], w->invc[1], x_B, w->q[1], n);
@@ -593,10 +630,6 @@ extern "C" int gs_cr_pcg_pol_batch(gs_plan* p, int n_chain, const double* dl_EE,
         precond_kernel<<<lb, 256, 0, st>>>(dl_EE + k * (L + 1), bl, ninv_sum_over_4pi, L, tmp_l, tmp_l + (L + 1));
         precond_kernel<<<lb, 256, 0, st>>>(dl_BB + k * (L + 1), bl, ninv_sum_over_4pi, L, tmp_l + 2 * (L + 1), tmp_l + 3 * (L + 1));
         GS_CHECK_LAUNCH();
-        if ((rc = gs_plan_expand_per_l(p, tmp_l, 0, w->invc[0], st))) return rc;
-        if ((rc = gs_plan_expand_per_l(p, tmp_l + (L + 1), 0, w->pre[0], st))) return rc;
-        if ((rc = gs_plan_expand_per_l(p, tmp_l + 2 * (L + 1), 0, w->invc[1], st))) return rc;
-        if ((rc = gs_plan_expand_per_l(p, tmp_l + 3 * (L + 1), 0, w->pre[1], st))) return rc;
         PcgState h;
         memset(&h, 0, sizeof(h));
         h.eps2 = eps * eps;
@@ -871,6 +904,7 @@ extern "C" int gs_profile_pcg_vectors(gs_plan* p, int spin, int nrep, float* ms_
     GS_CHECK_CUDA(cudaMemsetAsync(p->almE_tmp, 0, (size_t)n * sizeof(double), st));
     GS_CHECK_CUDA(cudaMemsetAsync(p->almB_tmp, 0, (size_t)n * sizeof(double), st));
     GS_CHECK_CUDA(cudaMemsetAsync(w->state, 0, sizeof(PcgState), st));
+    GS_CHECK_CUDA(cudaMemsetAsync(w->partials + SV_GRID * 2, 0, (size_t)4 * (p->d.lmax + 1) * sizeof(double), st));   // per-l tables
     gs_pcg_ws v = *w;
     v.red = w->fuse_out;   // reductions land here: the solver state (done flag, alpha, beta = 0) stays untouched
     cudaEvent_t e0, e1;
