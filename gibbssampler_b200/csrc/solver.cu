@@ -11,6 +11,7 @@
 // so alpha/beta and the convergence flag never travel to the host inside the loop; once the flag
 // is set every later kernel (SHT stages included) returns immediately.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -528,7 +529,8 @@ static int cr_pcg_impl(gs_plan* p, int spin, const double* dl_EE, const double* 
     // GPUs to 8 processes doing that on shared cores).  gs_set_pcg_graph(0) restores plain launches.
     cudaGraphExec_t gexec = nullptr;
     long long launches_per_graph = 0;
-    if (g_gs_pcg_graph && !dist && itermax >= check_every) {
+    static const bool env_graph_off = [] { const char* e = getenv("GS_PCG_GRAPH"); return e && e[0] == '0'; }();   // GS_PCG_GRAPH=0: plain launches
+    if (g_gs_pcg_graph && !env_graph_off && !dist && itermax >= check_every) {
         if (!p->work_stream) {
             cudaStream_t ws = nullptr;
             GS_CHECK_CUDA(cudaStreamCreateWithFlags(&ws, cudaStreamNonBlocking));

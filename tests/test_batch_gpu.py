@@ -176,3 +176,35 @@ def test_batched_transforms_on_split_ring_path(monkeypatch):
         assert relerr(q[c].cpu().numpy(), rq) < 1e-10 and relerr(u[c].cpu().numpy(), ru) < 1e-10
         re_, rb_ = O.map2alm_spin2(fq[c], fu[c], nside, lmax)
         assert relerr(ge[c].cpu().numpy(), re_) < 1e-10 and relerr(gb[c].cpu().numpy(), rb_) < 1e-10
+
+
+def test_run_chains_reproduces_each_chain_own_run():
+    """multichain.run_chains (two chains per GPU, batched constrained realizations) against the chains' own run(): same Philox
+    seeds -> the same right-hand sides; the batched PCG stops at the same tolerance, so the D_l histories agree to the solver
+    tolerance (and exactly in the accept flags of the Metropolis sweep)."""
+    from gibbssampler_b200.multichain import run_chains
+    from gibbssampler_b200.PNCP import PNCPGibbs
+    nside, lmax, l_cut, n_iter = 8, 16, 4, 4
+    rng = np.random.default_rng(21)
+    npix, mask, dls, fwhm, bl_map, dQ, dU = _problem(nside, lmax, rng)
+    ell = np.arange(lmax + 1)
+    bins = {"EE": np.arange(0, lmax + 2), "BB": np.arange(0, lmax + 2)}
+    blocks = {"EE": [4, 8, 12, lmax + 1], "BB": [4, 8, 12, lmax + 1]}
+    pv = {"EE": np.full(lmax - 1, 0.05), "BB": np.full(lmax - 1, 0.05)}
+    nt, npol = np.full(npix, 1.0), np.full(npix, 0.05)
+    init = [{"EE": np.where(ell >= 2, 1.0, 0.0), "BB": np.where(ell >= 2, 0.5, 0.0)},
+            {"EE": np.where(ell >= 2, 0.7, 0.0), "BB": np.where(ell >= 2, 0.3, 0.0)}]
+
+    def make(seed):
+        g = PNCPGibbs({"Q": dQ, "U": dU}, nt, fwhm, nside, lmax, npix, pv, l_cut, metropolis_blocks=blocks, polarization=True, bins=bins,
+                      n_iter=n_iter, noise_Q=npol, mask=mask, seed=seed)
+        g.constrained_sampler.pcg_accuracy = 1e-12
+        return g
+    ref = [make(41 + k).run(init[k]) for k in range(2)]
+    got = run_chains([make(41 + k) for k in range(2)], init)
+    for k in range(2):
+        for pol in ("EE", "BB"):
+            assert np.array_equal(np.asarray(got[k][1][pol]), np.asarray(ref[k][1][pol])), (k, pol)
+            a, b = np.asarray(got[k][0][pol]), np.asarray(ref[k][0][pol])
+            assert a.shape == b.shape == (n_iter + 1, lmax + 1)
+            assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max(), (k, pol, np.abs(a - b).max())
