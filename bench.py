@@ -54,12 +54,54 @@ def fiducial(lmax):
     return dlE, dlB
 
 
-def make_mask(nside, fsky=0.8, edge_deg=2.0):
+def pixel_phi(nside):
+    """Longitude of every RING pixel (HEALPix geometry: caps (j + 1/2) pi / (2 i), belt rings alternately shifted)."""
+    npix = 12 * nside * nside
+    phi = np.empty(npix)
+    for i in range(1, nside):
+        s = 2 * i * (i - 1)
+        p = (np.arange(4 * i) + 0.5) * np.pi / (2 * i)
+        phi[s:s + 4 * i] = p
+        phi[npix - s - 4 * i:npix - s] = p
+    ncap = 2 * nside * (nside - 1)
+    ib = np.arange(nside, 3 * nside + 1)
+    shift = 0.5 * ((ib - nside + 1) & 1)
+    phi[ncap:npix - ncap] = ((np.arange(4 * nside)[None, :] + shift[:, None]) * np.pi / (2 * nside)).ravel()
+    return phi
+
+
+MASK_KINDS = ("galplane", "band")
+
+
+def make_mask(nside, fsky=0.8, kind="galplane", edge_deg=2.0):
+    """Synthetic stand-in for the reference's sky mask (config.py:26: HFI_Mask_GalPlane-apo0_2048_R2 80 %, a mask of the galactic
+    plane in galactic coordinates), cos-tapered over edge_deg, mean = fsky.
+    "galplane": |b| < b0(l) with a bulge around l = 0 and ripples (half width between about 3 and 33 degrees), so the rings
+    near the plane are CUT by the mask edge while the polar caps and the high-latitude belt stay whole, as under the Planck
+    mask; "band": the axisymmetric band |b| < asin(1 - fsky) of the earlier rounds (no ring is cut: every ring has one weight)."""
     z = pixel_z(nside)
     b = np.degrees(np.arcsin(np.abs(z)))        # |latitude|
-    b0 = np.degrees(np.arcsin(1.0 - fsky))      # band |b| < b0 removes 1 - fsky of the sky
-    t = np.clip((b - b0) / edge_deg + 0.5, 0.0, 1.0)
-    return 0.5 * (1 - np.cos(np.pi * t))
+    if kind == "band":
+        b0 = np.degrees(np.arcsin(1.0 - fsky))  # band |b| < b0 removes 1 - fsky of the sky
+        t = np.clip((b - b0) / edge_deg + 0.5, 0.0, 1.0)
+        return 0.5 * (1 - np.cos(np.pi * t))
+    if kind != "galplane":
+        raise ValueError("mask kind %r" % (kind,))
+    phi = pixel_phi(nside)
+    dl = np.degrees(np.angle(np.exp(1j * phi)))                      # longitude in (-180, 180]
+    shape = 22.0 * np.exp(-(dl / 40.0) ** 2) + 3.0 * np.cos(3 * phi + 1.0) + 1.5 * np.cos(7 * phi + 0.5)
+
+    def mask_for(c):
+        t = np.clip((b - (c + shape)) / edge_deg + 0.5, 0.0, 1.0)
+        return 0.5 * (1 - np.cos(np.pi * t))
+    lo, hi = 0.0, 40.0
+    for _ in range(40):                                              # base half width c: mean(mask) = fsky
+        c = 0.5 * (lo + hi)
+        if mask_for(c).mean() > fsky:
+            lo = c
+        else:
+            hi = c
+    return mask_for(0.5 * (lo + hi))
 
 
 def bins_for(lmax):

@@ -164,6 +164,7 @@ struct gs_plan {
     int* act_count;           // device int: entries of act_pairs
     double* act_red;          // [nring] sharded plans: ring flags as doubles for the sum over ranks
     int* act_slot0;           // [2][lmax+1] (spin 0, spin 2): first entry of act_pairs whose pair reaches m
+    double* ring_wconst;      // [nring] the pixel weight of a ring whose weights are all equal, NaN for any other ring (unsharded plans)
     bool use_act;
     // workspace
     double2* Fm;        // [2][nring][lmax+1] ring spectra
@@ -187,6 +188,7 @@ struct gs_plan {
     void* work_event;   // cudaEvent_t ordering work_stream after the caller's stream
 };
 
+extern int g_gs_ring_const;       // 1: rings of constant pixel weight take the transform-free path of ring_apply_kernel (PCG mat-vec)
 extern int g_gs_ring_skip;        // 1: rings whose pixel weights vanish identically are left out (PCG mat-vec, Metropolis sweep)
 extern int g_gs_ring_fused;       // 1: the PCG mat-vec runs its ring stage as one fused kernel (ring_apply_kernel)
 extern long long g_gs_launches;  // kernels launched by this library (bench.py's gpu_launches)

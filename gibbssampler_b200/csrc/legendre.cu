@@ -1436,17 +1436,24 @@ leg_finish_apq_kernel(PlanDev P, const double* __restrict__ partial, double* __r
 // (no host round trip); the Legendre kernels then walk that list and the fused ring stage drops the CTAs of idle rings.
 // SH: the weight map is this rank's ring-sharded local map; every rank marks its own rings in `actd` (doubles, summed over
 // the ranks by the caller), the others stay zero
+// wconst (unsharded, nullable): the ring's pixel weight when all its pixels carry the same one (isotropic noise outside the
+// mask: every ring that the mask edge does not cut), NaN otherwise; see the transform-free path of ring_apply_kernel
 template <bool SH>
 __global__ void __launch_bounds__(256) ring_active_kernel(PlanDev P, const double* __restrict__ pixw, unsigned char* __restrict__ act,
-                                                          double* __restrict__ actd)
+                                                          double* __restrict__ actd, double* __restrict__ wconst)
 {
     const int ring = blockIdx.x, n = P.ring_nphi[ring];
     if (SH && P.sh.ring_owner[ring] != P.sh.rank) { if (threadIdx.x == 0) actd[ring] = 0.0; return; }
     const double* w = pixw + (SH ? P.sh.ring_start_loc[ring] : P.ring_start[ring]);
-    int any = 0;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) any |= (w[j] != 0.0);
+    const double w0 = w[0];
+    int any = 0, differ = 0;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) { const double v = w[j]; any |= (v != 0.0); differ |= !(v == w0); }
     any = __syncthreads_or(any);
-    if (threadIdx.x == 0) { if (SH) actd[ring] = any ? 1.0 : 0.0; else act[ring] = any ? 1 : 0; }
+    if (!SH && wconst) differ = __syncthreads_or(differ);
+    if (threadIdx.x == 0) {
+        if (SH) actd[ring] = any ? 1.0 : 0.0; else act[ring] = any ? 1 : 0;
+        if (!SH && wconst) wconst[ring] = differ ? __longlong_as_double(0x7ff8000000000000LL) : w0;
+    }
 }
 
 __global__ void ring_flags_kernel(const double* __restrict__ actd, unsigned char* __restrict__ act, int n)
@@ -1501,13 +1508,13 @@ __global__ void __launch_bounds__(256) list_slot0_kernel(PlanDev P, const int* _
 int gs_active_rings_build(gs_plan* p, const double* pixw, cudaStream_t st)
 {
     if (p->world > 1) {   // ring-sharded weights: local flags, summed over the ranks (every rank builds the same lists)
-        ring_active_kernel<true><<<p->d.nring, 256, 0, st>>>(p->d, pixw, p->act_ring, p->act_red);
+        ring_active_kernel<true><<<p->d.nring, 256, 0, st>>>(p->d, pixw, p->act_ring, p->act_red, nullptr);
         GS_CHECK_LAUNCH();
         int rc = gs_shard_allreduce(p, p->act_red, p->d.nring, st);
         if (rc) return rc;
         ring_flags_kernel<<<(p->d.nring + 255) / 256, 256, 0, st>>>(p->act_red, p->act_ring, p->d.nring);
     } else {
-        ring_active_kernel<false><<<p->d.nring, 256, 0, st>>>(p->d, pixw, p->act_ring, nullptr);
+        ring_active_kernel<false><<<p->d.nring, 256, 0, st>>>(p->d, pixw, p->act_ring, nullptr, p->ring_wconst);
     }
     pair_compact_kernel<<<1, 1024, 0, st>>>(p->d, p->act_ring, p->act_pairs, p->act_count);
     list_slot0_kernel<<<(2 * (p->d.lmax + 1) * 32 + 255) / 256, 256, 0, st>>>(p->d, p->act_pairs, p->act_count, p->act_slot0);

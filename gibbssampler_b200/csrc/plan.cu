@@ -240,6 +240,7 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
     p->nsjobs0 = p->nsjobs2 = 0;
     p->ring_scratch = nullptr;
     p->act_ring = nullptr;
+    p->ring_wconst = nullptr;
     p->act_pairs = nullptr;
     p->act_count = nullptr;
     p->act_slot0 = nullptr;
@@ -288,6 +289,7 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)1, &p->act_count);
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)2 * (lmax + 1), &p->act_slot0);
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->d.nring, &p->act_red);
+        if (rc == GS_OK && world <= 1) rc = dev_alloc(p, (size_t)p->d.nring, &p->ring_wconst);
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->npix_loc, &p->mapQ_tmp);
         if (rc == GS_OK) rc = dev_alloc(p, (size_t)p->npix_loc, &p->mapU_tmp);
         const size_t nre = (size_t)p->nreal_loc;  // big enough for either layout

@@ -19,7 +19,12 @@
 
 #include "gs_internal.h"
 
-#define RF_NT 256
+#ifndef RING_R8
+#define RING_R8 0   // 1: radix-8 passes, 512 threads per CTA at <= 64 registers (32 warps per SM instead of 16)
+#endif
+#ifndef RF_NT
+#define RF_NT (RING_R8 ? 512 : 256)
+#endif
 #ifndef RING_UNPACK_CHIRP
 #define RING_UNPACK_CHIRP 1   // Bluestein rings: last chirp product taken while the spectrum is unpacked (no pass of its own)
 #endif
@@ -43,8 +48,14 @@ __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_doub
 // radix-2 and/or radix-4 pass at the top (DIF) / bottom (DIT).
 // Twiddles: quarter table twq[k] = exp(-2 pi i k / twn), k <= twn/4, in shared memory;
 // W^(k + twn/4) = -i W^k covers the second quadrant (indices stay below twn/2).
+#if RING_R8
+// radix-8 build: one pad per 8 elements (the stride-8 accesses of the final radix-8 pass), second level as above
+#define PADI(i) ((i) + ((i) >> 3) + ((i) >> 8))
+#define PADLEN(M) ((M) + ((M) >> 3) + ((M) >> 8) + 2)
+#else
 #define PADI(i) ((i) + ((i) >> 4) + ((i) >> 8))
 #define PADLEN(M) ((M) + ((M) >> 4) + ((M) >> 8) + 2)   // shared-memory slots of a padded M-point buffer
+#endif
 
 __device__ __forceinline__ double2 tw_get(const double2* twq, int idx, int quarter)
 {
@@ -145,8 +156,9 @@ __device__ __forceinline__ void pass4(double2* buf, int M, int N, const double2*
 // 2^(4k+3) (2048: the belt rings of nside 512 and the Bluestein length of the cap rings with 516..1024 pixels) used to take a
 // radix-2 AND a radix-4 trip through shared memory at the top (DIF) / bottom (DIT) of the transform; this is one trip.
 // PRE (DIF only): the loaded element idx is replaced by pre(idx, value) (fused pointwise products, see ring_apply_kernel).
-template <bool INV, class PRE = NoPre>
-__device__ __forceinline__ void pass8(double2* buf, int M, int N, const double2* twq, int twn, int tid, int nt, PRE pre = PRE())
+template <bool INV, class PRE = NoPre, bool POST = false>
+__device__ __forceinline__ void pass8(double2* buf, int M, int N, const double2* twq, int twn, int tid, int nt, PRE pre = PRE(),
+                                      const double2* __restrict__ post = nullptr)
 {
     const int s = N >> 3, ls = 31 - __clz(s), ts = twn / N, quarter = twn >> 2, ng = M >> 3;
     for (int t = tid; t < ng; t += nt) {
@@ -179,7 +191,11 @@ __device__ __forceinline__ void pass8(double2* buf, int M, int N, const double2*
             }
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) buf[PADI(i0 + k * s)] = x[k];
+        for (int k = 0; k < 8; ++k) {
+            double2 v = x[k];
+            if (POST) v = cmul(v, __ldg(&post[i0 + k * s]));
+            buf[PADI(i0 + k * s)] = v;
+        }
     }
     __syncthreads();
 }
@@ -209,6 +225,25 @@ template <bool POST, class PRE = NoPre>
 __device__ void fft_dif(double2* buf, int M, const double2* twq, int twn, const double2* __restrict__ post, int tid = threadIdx.x,
                         int nt = RF_NT, PRE pre = PRE())
 {
+#if RING_R8
+    {   // radix-8 passes below a radix-2 / radix-4 top pass (needs M >= 8)
+        const int lg = 31 - __clz(M), r = lg % 3;
+        int N = M;
+        bool first = true;
+        if (r == 1) { pass2<false, PRE>(buf, M, N, twq, twn, tid, nt, pre); N >>= 1; first = false; }
+        else if (r == 2) { pass4<false, PRE>(buf, M, N, twq, twn, tid, nt, pre); N >>= 2; first = false; }
+        while (N >= 8) {
+            if (first) {
+                if (POST && N == 8) pass8<false, PRE, true>(buf, M, N, twq, twn, tid, nt, pre, post);
+                else pass8<false, PRE, false>(buf, M, N, twq, twn, tid, nt, pre);
+            } else if (POST && N == 8) pass8<false, NoPre, true>(buf, M, N, twq, twn, tid, nt, NoPre(), post);
+            else pass8<false>(buf, M, N, twq, twn, tid, nt);
+            first = false;
+            N >>= 3;
+        }
+        return;
+    }
+#endif
     const int lg = 31 - __clz(M), r = lg & 3;
     int N = M;
     bool first = true;
@@ -234,6 +269,16 @@ __device__ void fft_dif(double2* buf, int M, const double2* twq, int twn, const 
 // In-place inverse DIT FFT (kernel exp(+2 pi i jk/M), unnormalised), bit-reversed in, natural out.
 __device__ void fft_dit_inv(double2* buf, int M, const double2* twq, int twn, int tid = threadIdx.x, int nt = RF_NT)
 {
+#if RING_R8
+    {
+        const int lg = 31 - __clz(M), r = lg % 3;
+        const int Ntop = M >> r;
+        for (int N = 8; N <= Ntop; N <<= 3) pass8<true>(buf, M, N, twq, twn, tid, nt);
+        if (r == 2) pass4<true>(buf, M, M, twq, twn, tid, nt);
+        else if (r == 1) pass2<true>(buf, M, M, twq, twn, tid, nt);
+        return;
+    }
+#endif
     const int lg = 31 - __clz(M), r = lg & 3;
     const int Ntop = M >> r;  // largest radix-16 sub-transform size
     for (int N = 16; N <= Ntop; N <<= 4) pass16<true, false>(buf, M, N, twq, twn, nullptr, tid, nt);
@@ -346,6 +391,19 @@ __device__ __forceinline__ bool group_idle(const unsigned char* __restrict__ rac
         any = any || ract[jb.ringA] || (jb.ringB >= 0 && ract[jb.ringB]);
     }
     return !any;
+}
+// Every ring of the CTA's group has one pixel weight for all its pixels (wconst from gs_active_rings_build, NaN = weights differ)
+__device__ __forceinline__ bool group_const(const double* __restrict__ wconst, const RingJob* __restrict__ jobs, const int2* __restrict__ groups)
+{
+    if (!wconst) return false;
+    const int2 g = groups[blockIdx.x];
+    bool all = true;
+    for (int s = 0; s < g.y; ++s) {
+        const RingJob jb = jobs[g.x + s];
+        const double a = wconst[jb.ringA], b = jb.ringB >= 0 ? wconst[jb.ringB] : 0.0;
+        all = all && a == a && b == b;
+    }
+    return all;
 }
 __device__ __forceinline__ bool split_idle(const unsigned char* __restrict__ ract, const SplitJob& jb)
 {
@@ -460,8 +518,8 @@ __device__ __forceinline__ void ring_fold(const PlanDev& P, const RingJob& job, 
 // Contains one CTA-wide barrier; all threads of the CTA must call.
 template <bool SH>
 __device__ __forceinline__ void ring_build_Z(const PlanDev& P, const RingSub& S, const double2* __restrict__ Fm, int mtop, double2* scratch,
-                                             bool interleaved = false)
-{
+                                             bool interleaved = false, bool plain = false)
+{   // plain: Z_k is stored at buf[PADI(k)], k < n, as it is (no bit reversal, chirp or padding: no transform follows)
     const RingJob& job = S.job;
     const int L = P.lmax, nm = L + 1, n = S.n, lg = 31 - __clz(n);
     // spectra layout [comp][ring][m], or (block-batched Metropolis sweep) [ring][m][comp] with Q and U of one (ring, m) adjacent
@@ -471,46 +529,48 @@ __device__ __forceinline__ void ring_build_Z(const PlanDev& P, const RingSub& S,
                         : interleaved ? Fm + (int64_t)job.ringB * nm * 2 + job.compB : Fm + ((int64_t)job.compB * P.nring + job.ringB) * nm;
     const int nterm = (mtop + n) / n;   // alias terms m = k + j n <= mtop, j < nterm
     const double2 zero = make_double2(0.0, 0.0);
+    const int Mz = plain ? n : S.M;
     auto put = [&](int k, double2 v) {
-        if (k >= S.M) return;
-        const int pos = PADI(S.bsi < 0 ? (int)(__brev((unsigned)k) >> (32 - lg)) : k);
+        if (k >= Mz) return;
+        const int pos = PADI((S.bsi < 0 && !plain) ? (int)(__brev((unsigned)k) >> (32 - lg)) : k);
         if (k >= n) v = zero;
-        else if (S.bsi >= 0) v = cmul(v, __ldg(&S.chirp[k]));
+        else if (S.bsi >= 0 && !plain) v = cmul(v, __ldg(&S.chirp[k]));
         S.buf[pos] = v;
     };
     const bool split = n <= S.nt;
     const double2 q = ring_phase(P, job.ringA, n);
+    constexpr int FK = RING_R8 ? 2 : 4;   // values of k (long rings) / alias terms (short rings) per step: 4 FK loads in flight per thread
     if (split) {
         const int J = S.nt / n, kq = S.tid % n, jq = S.tid / n;
         double2 z[1] = {zero};
-        if (jq < J) ring_fold<SH, 1, 4>(P, job, Fm, FA, FB, fs, n, mtop, nterm, kq, 1, jq, J, ring_phase(P, job.ringA, kq), zero, q, z);
+        if (jq < J) ring_fold<SH, 1, FK>(P, job, Fm, FA, FB, fs, n, mtop, nterm, kq, 1, jq, J, ring_phase(P, job.ringA, kq), zero, q, z);
         scratch[S.tid] = z[0];
-    } else if (n >= 4 * S.nt) {
+    } else if (n >= FK * S.nt) {
         double2 pk = ring_phase(P, job.ringA, S.tid);
-        const double2 step = ring_phase(P, job.ringA, S.nt), step4 = ring_phase(P, job.ringA, 4 * S.nt);
-        for (int k0 = S.tid; k0 < n; k0 += 4 * S.nt) {
-            double2 z[4];
-            ring_fold<SH, 4, 1>(P, job, Fm, FA, FB, fs, n, mtop, nterm, k0, S.nt, 0, 1, pk, step, q, z);
+        const double2 step = ring_phase(P, job.ringA, S.nt), step4 = ring_phase(P, job.ringA, FK * S.nt);
+        for (int k0 = S.tid; k0 < n; k0 += FK * S.nt) {
+            double2 z[FK];
+            ring_fold<SH, FK, 1>(P, job, Fm, FA, FB, fs, n, mtop, nterm, k0, S.nt, 0, 1, pk, step, q, z);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) put(k0 + u * S.nt, z[u]);
+            for (int u = 0; u < FK; ++u) put(k0 + u * S.nt, z[u]);
             pk = cmul(pk, step4);
         }
-        for (int k = S.tid + ((n - S.tid + 4 * S.nt - 1) / (4 * S.nt)) * 4 * S.nt; k < S.M; k += S.nt) put(k, zero);   // zero padding
+        for (int k = S.tid + ((n - S.tid + FK * S.nt - 1) / (FK * S.nt)) * FK * S.nt; k < Mz; k += S.nt) put(k, zero);   // zero padding
     } else {
         double2 pk = ring_phase(P, job.ringA, S.tid);
         const double2 step = ring_phase(P, job.ringA, S.nt);
         for (int k0 = S.tid; k0 < n; k0 += S.nt) {
             double2 z[1];
-            ring_fold<SH, 1, 4>(P, job, Fm, FA, FB, fs, n, mtop, nterm, k0, S.nt, 0, 1, pk, step, q, z);
+            ring_fold<SH, 1, FK>(P, job, Fm, FA, FB, fs, n, mtop, nterm, k0, S.nt, 0, 1, pk, step, q, z);
             put(k0, z[0]);
             pk = cmul(pk, step);
         }
-        for (int k = S.tid + ((n - S.tid + S.nt - 1) / S.nt) * S.nt; k < S.M; k += S.nt) put(k, zero);   // zero padding
+        for (int k = S.tid + ((n - S.tid + S.nt - 1) / S.nt) * S.nt; k < Mz; k += S.nt) put(k, zero);   // zero padding
     }
     __syncthreads();
     if (split) {
         const int J = S.nt / n;
-        for (int k = S.tid; k < S.M; k += S.nt) {
+        for (int k = S.tid; k < Mz; k += S.nt) {
             double2 v = zero;
             if (k < n) for (int i = 0; i < J; ++i) v = cadd(v, scratch[i * n + k]);
             put(k, v);
@@ -520,12 +580,14 @@ __device__ __forceinline__ void ring_build_Z(const PlanDev& P, const RingSub& S,
 
 // F_m of the two real sequences of a job from the length-n DFT held in buf, m = 0..lmax:
 //   Xa[k] = (Z[k] + conj Z[n-k]) / 2, Xb[k] = (Z[k] - conj Z[n-k]) / (2i), F_m = X[m mod n] e^{-i m phi0}.
-// br = false: buf[PADI(k)] = conj Z[k] (transform done as conj(idft(conj z))); br = true: buf holds Z[k] at the
-// bit-reversed position of k (forward DIF transform of a power-of-two ring).
-// chirp (br = false only, nullable): buf still lacks the final Bluestein product, buf[k] chirp[k] is taken on the fly
+// mode UNPACK_CONJ: buf[PADI(k)] = conj Z[k] (transform done as conj(idft(conj z))); UNPACK_BREV: buf holds Z[k] at the
+// bit-reversed position of k (forward DIF transform of a power-of-two ring); UNPACK_PLAIN: buf[PADI(k)] = Z[k].
+// chirp (UNPACK_CONJ only, nullable): buf still lacks the final Bluestein product, buf[k] chirp[k] is taken on the fly.
+// sa, sb: factors of the two sequences (the transform-free path of ring_apply_kernel puts n w there).
+enum { UNPACK_CONJ = 0, UNPACK_BREV = 1, UNPACK_PLAIN = 2 };
 template <bool SH>
-__device__ __forceinline__ void ring_unpack_F(const PlanDev& P, const RingSub& S, bool br, double2* __restrict__ Fm, int mtop,
-                                              const double2* __restrict__ chirp = nullptr)
+__device__ __forceinline__ void ring_unpack_F(const PlanDev& P, const RingSub& S, int mode, double2* __restrict__ Fm, int mtop,
+                                              const double2* __restrict__ chirp = nullptr, double sa = 0.5, double sb = 0.5)
 {
     const RingJob& job = S.job;
     const int L = P.lmax, nm = L + 1, n = S.n, lg = 31 - __clz(n);
@@ -537,17 +599,20 @@ __device__ __forceinline__ void ring_unpack_F(const PlanDev& P, const RingSub& S
     for (int m = S.tid; m <= mtop; m += S.nt) {
         const int k = m % n, kk = (n - k) % n;
         double2 z1, z2c;
-        if (br) {
+        if (mode == UNPACK_BREV) {
             const double2 c1 = buf[PADI((int)(__brev((unsigned)k) >> (32 - lg)))], c2 = buf[PADI((int)(__brev((unsigned)kk) >> (32 - lg)))];
+            z1 = c1; z2c = make_double2(c2.x, -c2.y);
+        } else if (mode == UNPACK_PLAIN) {
+            const double2 c1 = buf[PADI(k)], c2 = buf[PADI(kk)];
             z1 = c1; z2c = make_double2(c2.x, -c2.y);
         } else {
             double2 c1 = buf[PADI(k)], c2 = buf[PADI(kk)];
             if (chirp) { c1 = cmul(c1, __ldg(&chirp[k])); c2 = cmul(c2, __ldg(&chirp[kk])); }
             z1 = make_double2(c1.x, -c1.y); z2c = c2;
         }
-        const double2 xa = make_double2(0.5 * (z1.x + z2c.x), 0.5 * (z1.y + z2c.y));
+        const double2 xa = make_double2(sa * (z1.x + z2c.x), sa * (z1.y + z2c.y));
         const double2 d = csub(z1, z2c);
-        const double2 xb = make_double2(0.5 * d.y, -0.5 * d.x);
+        const double2 xb = make_double2(sb * d.y, -sb * d.x);
         if (SH) {
             Fm[fm_ring_index<true>(P, job.compA, job.ringA, m)] = cmulc(xa, pa);
             if (FB) Fm[fm_ring_index<true>(P, job.compB, job.ringB, m)] = cmulc(xb, pa);
@@ -622,7 +687,7 @@ ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __rest
     }
     ring_idft(P, S.buf, twq, n, S.bsi, S.tid, S.nt);
     // Bluestein: the last chirp product is taken as the spectrum is unpacked
-    ring_unpack_F<SH>(P, S, false, Fm, ring_mtop(P, job.ringA, spin2), S.bsi >= 0 ? S.chirp : nullptr);
+    ring_unpack_F<SH>(P, S, UNPACK_CONJ, Fm, ring_mtop(P, job.ringA, spin2), S.bsi >= 0 ? S.chirp : nullptr);
 }
 
 // Ring stage of the PCG mat-vec A^T N^-1 A in ONE kernel: F_m(ring) -> pixels of the ring (kept in shared memory) ->
@@ -642,13 +707,25 @@ template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
 ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __restrict__ groups, double2* __restrict__ Fm,
                   const double* __restrict__ pixw, const int* __restrict__ skip, const unsigned char* __restrict__ ract, int spin2,
-                  int64_t f_stride)
+                  int64_t f_stride, const double* __restrict__ wconst)
 {
     if (skip && *skip) return;
     if (group_idle(ract, jobs, groups)) return;
     extern __shared__ double2 smem[];
     Fm += blockIdx.y * f_stride;   // chain batch: blockIdx.y = chain, same pixel weights
     double2* twq = smem;
+    if (group_const(wconst, jobs, groups)) {
+        // Constant pixel weight w on each ring of the group: x_j = sum_k X_k e^{2 pi i jk/n} -> w x_j -> sum_j w x_j e^{-2 pi i jk/n}
+        // = n w X_k, so F'_m = n w X_{m mod n} e^{-i m phi0} follows from the alias-folded spectrum X without any transform
+        const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
+        const int mtop = ring_mtop(P, S.job.ringA, spin2);
+        ring_build_Z<SH>(P, S, Fm, mtop, S.scratch, false, true);
+        __syncthreads();
+        const double half_n = 0.5 * (double)S.n;
+        ring_unpack_F<SH>(P, S, UNPACK_PLAIN, Fm, mtop, nullptr, half_n * wconst[S.job.ringA],
+                          half_n * wconst[S.job.ringB >= 0 ? S.job.ringB : S.job.ringA]);
+        return;
+    }
     load_twq(P, twq);
     const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
     const int n = S.n;
@@ -665,7 +742,7 @@ ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
         // transform (bit-reversed output)
         auto weigh = [wa, wb](int j, double2 z) { return make_double2(z.x * wa[j], z.y * wb[j]); };
         fft_dif<false>(S.buf, n, twq, P.tw_n, nullptr, S.tid, S.nt, weigh);
-        ring_unpack_F<SH>(P, S, true, Fm, mtop);
+        ring_unpack_F<SH>(P, S, UNPACK_BREV, Fm, mtop);
     } else {
         // Bluestein both ways: Z = conj(idft(conj z)); the chirp of the synthesis output, the pixel weights, the chirp of the
         // analysis input and the zero padding are applied as the first pass of the second convolution loads its input, the last
@@ -691,11 +768,11 @@ ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
         ring_idft(P, S.buf, twq, n, S.bsi, S.tid, S.nt);
 #endif
 #if RING_UNPACK_CHIRP
-        ring_unpack_F<SH>(P, S, false, Fm, mtop, chirp);
+        ring_unpack_F<SH>(P, S, UNPACK_CONJ, Fm, mtop, chirp);
 #else
         for (int k = S.tid; k < n; k += S.nt) S.buf[PADI(k)] = cmul(S.buf[PADI(k)], __ldg(&chirp[k]));
         __syncthreads();
-        ring_unpack_F<SH>(P, S, false, Fm, mtop);
+        ring_unpack_F<SH>(P, S, UNPACK_CONJ, Fm, mtop);
 #endif
     }
     __syncthreads();
@@ -886,7 +963,7 @@ int gs_ring_setup(gs_plan* p)
     // direct path: transform buffer(s) + quarter twiddle table in one CTA; Mcap = largest power-of-two transform
     // length taken directly (two CTAs per SM).  Longer rings take the split path (n/4 per CTA).
     // (+ RF_NT entries: partial alias sums of rings shorter than their thread count, see ring_build_Z)
-    auto direct_smem = [&](int M, int twn) { return (size_t)((M + M / 16 + M / 256 + 16 + RF_NT) + twn / 4 + 1) * sizeof(double2); };
+    auto direct_smem = [&](int M, int twn) { return (size_t)((PADLEN(M) + 16 + RF_NT) + twn / 4 + 1) * sizeof(double2); };
     int Mcap = 4;
     while (2 * direct_smem(2 * Mcap, 2 * Mcap) <= smem_max) Mcap *= 2;
     (void)L;
@@ -1138,8 +1215,10 @@ int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, con
     if (nj <= 0) return GS_OK;
     const RingJob* jobs = spin == 0 ? p->jobs0 : p->jobs2;
     const int2* grp = spin == 0 ? p->groups0 : p->groups2;
-    if (p->world > 1) ring_apply_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fx, pixw, skip, p->use_act ? p->act_ring : nullptr, spin ? 1 : 0, 0);
-    else ring_apply_kernel<false><<<dim3(nj, nc), RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fm, pixw, skip, p->use_act ? p->act_ring : nullptr, spin ? 1 : 0, nc > 1 ? gs_fm_stride(p) : 0);
+    // ring_wconst is filled together with the active-ring flags (gs_active_rings_build), from the weight map of this call
+    const double* wconst = (p->use_act && g_gs_ring_const) ? p->ring_wconst : nullptr;
+    if (p->world > 1) ring_apply_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fx, pixw, skip, p->use_act ? p->act_ring : nullptr, spin ? 1 : 0, 0, nullptr);
+    else ring_apply_kernel<false><<<dim3(nj, nc), RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fm, pixw, skip, p->use_act ? p->act_ring : nullptr, spin ? 1 : 0, nc > 1 ? gs_fm_stride(p) : 0, wconst);
     GS_CHECK_LAUNCH();
     g_gs_launches += 1;
     return GS_OK;

@@ -412,6 +412,10 @@ extern "C" int gs_set_ring_fused(int fused) { const int old = g_gs_ring_fused; g
 // Rings whose N^-1 is identically zero (inside the mask) add nothing to A^T N^-1 A: the mat-vec walks the rings that carry
 // weight only (gs_active_rings_build; lists rebuilt from the weight map of each solve, on the device).
 int g_gs_ring_skip = 1;
+// Rings on which N^-1 is constant (isotropic noise, ring not cut by the mask edge): DFT^H diag(w) DFT = n w on the alias-folded
+// spectrum, so the fused ring stage of the mat-vec needs no transform there (ring_apply_kernel; flags from gs_active_rings_build).
+int g_gs_ring_const = 1;
+extern "C" int gs_set_ring_const(int on) { const int old = g_gs_ring_const; g_gs_ring_const = on ? 1 : 0; return old; }
 extern "C" int gs_set_ring_skip(int on) { const int old = g_gs_ring_skip; g_gs_ring_skip = on ? 1 : 0; return old; }
 
 struct ActiveRings {   // scope guard: the plan's launchers use the active lists while one of these lives
@@ -989,6 +993,19 @@ extern "C" int gs_measure_fp64_peak(double* tflops_out, void* stream)
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     *tflops_out = best;
+    return GS_OK;
+}
+
+extern "C" int gs_constant_rings(gs_plan* p, int* count_out)
+{
+    if (!p) { gs_set_error("null plan"); return GS_E_BADARG; }
+    GS_REQUIRE(count_out, "null output");
+    *count_out = 0;
+    if (!p->ring_wconst) return GS_OK;   // sharded plans do not flag constant rings
+    GS_CHECK_CUDA(cudaSetDevice(p->device));
+    std::vector<double> w(p->d.nring);
+    GS_CHECK_CUDA(cudaMemcpy(w.data(), p->ring_wconst, w.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (double v : w) *count_out += (v == v);
     return GS_OK;
 }
 

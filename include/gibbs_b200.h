@@ -442,10 +442,20 @@ int gs_set_ring_fused(int fused);
  * rings and sum the flags (one small all-reduce per call).  gs_mwg_sweep_blocks skips the ring FFTs of those rings too.
  * Returns the previous setting. */
 int gs_set_ring_skip(int on);
+/* Rings on which the pixel weights N^-1 are all equal (isotropic noise, noise_covar * ones in the reference's config.py, on
+ * every ring that the edge of the mask does not cut): for such a ring the middle of opfilt_pp.fwd_op (alm2map_spin -> N^-1 ->
+ * map2alm_spin, CenteredGibbs.py:629,653) is DFT^H diag(w) DFT = n w on the alias-folded ring spectrum.  on != 0 (default,
+ * unsharded plans, needs gs_set_ring_skip on): the fused ring stage of the mat-vec takes those rings without any transform,
+ * flagged from the weight map of each call; 0: every ring is transformed.  Same result to rounding.  Returns the previous setting. */
+int gs_set_ring_const(int on);
 /* on != 0: in gs_cr_pcg_* on unsharded plans the step  q += C^-1 p ; <p, q>  rides on the last kernel of the Legendre
  * analysis instead of a separate pass; 0 (default; the fused form measured 0.4 % slower at NSIDE 512): separate kernel.
  * Same numbers up to the summation order of the dot product.  Returns the previous setting. */
 int gs_set_fuse_apq(int on);
+/* Number of rings (of 4 nside - 1) whose pixel weights were all equal in the weight map of the last gs_cr_pcg_* /
+ * gs_cr_apply_q_* / gs_profile_matvec call on this plan (rings inside the mask count: their weight is the constant 0);
+ * 0 on sharded plans.  See gs_set_ring_const. */
+int gs_constant_rings(gs_plan* plan, int* count_out);
 /* Number of ring pairs (north/south) with a non-zero weight found by the last such call on this plan, and the total. */
 int gs_active_ring_pairs(gs_plan* plan, int* active_out, int* total_out);
 /* FP64 FMA throughput of the current device in TFLOP/s (DFMA microkernel; the roofline
