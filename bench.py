@@ -71,14 +71,21 @@ def pixel_phi(nside):
 
 
 MASK_KINDS = ("galplane", "band")
+MASK_KIND = "galplane"   # --mask; read by every make_mask(nside) of this run (both arms, config #4)
+MASK_NOTE = {
+    "galplane": "synthetic stand-in for the reference's HFI GalPlane 80 % mask (config.py:26): |b| < b0(l), bulge at l = 0 + ripples "
+                "(half width 3 to 33 deg), cos taper 2 deg, f_sky 0.8; the mask edge CUTS the rings near the plane",
+    "band": "axisymmetric band |b| < 11.5 deg, cos taper 2 deg, f_sky 0.8 (the mask of rounds 1-2a; no ring is cut by its edge)",
+}
 
 
-def make_mask(nside, fsky=0.8, kind="galplane", edge_deg=2.0):
+def make_mask(nside, fsky=0.8, kind=None, edge_deg=2.0):
     """Synthetic stand-in for the reference's sky mask (config.py:26: HFI_Mask_GalPlane-apo0_2048_R2 80 %, a mask of the galactic
     plane in galactic coordinates), cos-tapered over edge_deg, mean = fsky.
     "galplane": |b| < b0(l) with a bulge around l = 0 and ripples (half width between about 3 and 33 degrees), so the rings
     near the plane are CUT by the mask edge while the polar caps and the high-latitude belt stay whole, as under the Planck
     mask; "band": the axisymmetric band |b| < asin(1 - fsky) of the earlier rounds (no ring is cut: every ring has one weight)."""
+    kind = kind or MASK_KIND
     z = pixel_z(nside)
     b = np.degrees(np.arcsin(np.abs(z)))        # |latitude|
     if kind == "band":
@@ -87,21 +94,25 @@ def make_mask(nside, fsky=0.8, kind="galplane", edge_deg=2.0):
         return 0.5 * (1 - np.cos(np.pi * t))
     if kind != "galplane":
         raise ValueError("mask kind %r" % (kind,))
-    phi = pixel_phi(nside)
-    dl = np.degrees(np.angle(np.exp(1j * phi)))                      # longitude in (-180, 180]
-    shape = 22.0 * np.exp(-(dl / 40.0) ** 2) + 3.0 * np.cos(3 * phi + 1.0) + 1.5 * np.cos(7 * phi + 0.5)
+    def edge_of(ns):
+        phi = pixel_phi(ns)
+        dl = np.degrees(phi) - 360.0 * (phi > np.pi)                 # longitude in (-180, 180]
+        return 22.0 * np.exp(-(dl / 40.0) ** 2) + 3.0 * np.cos(3 * phi + 1.0) + 1.5 * np.cos(7 * phi + 0.5)
 
-    def mask_for(c):
-        t = np.clip((b - (c + shape)) / edge_deg + 0.5, 0.0, 1.0)
+    def mask_for(c, bb, shape):
+        t = np.clip((bb - (c + shape)) / edge_deg + 0.5, 0.0, 1.0)
         return 0.5 * (1 - np.cos(np.pi * t))
+    ns = min(nside, 128)                                             # base half width c: mean(mask) = fsky, solved at NSIDE <= 128
+    bs = b if ns == nside else np.degrees(np.arcsin(np.abs(pixel_z(ns))))
+    ss = edge_of(ns)
     lo, hi = 0.0, 40.0
-    for _ in range(40):                                              # base half width c: mean(mask) = fsky
+    for _ in range(40):
         c = 0.5 * (lo + hi)
-        if mask_for(c).mean() > fsky:
+        if mask_for(c, bs, ss).mean() > fsky:
             lo = c
         else:
             hi = c
-    return mask_for(0.5 * (lo + hi))
+    return mask_for(0.5 * (lo + hi), b, ss if ns == nside else edge_of(nside))
 
 
 def bins_for(lmax):
@@ -417,7 +428,8 @@ def workload_config(args):
         wl = ("CenteredGibbs polarised masked sky: PCG constrained realization (eps 1e-5, diag_cl precond) + inverse-gamma C_l draw; "
               "one independent chain per GPU")
     return {"workload": wl, "sampler": args.sampler,
-            "nside": args.nside, "lmax": args.lmax, "fsky": 0.8, "beam_fwhm_deg": 0.5 * max(1, 512 // args.nside) if args.nside < 512 else 0.5,
+            "nside": args.nside, "lmax": args.lmax, "fsky": 0.8, "mask": MASK_KIND + ": " + MASK_NOTE[MASK_KIND], "noise": "isotropic (noise_covar * ones, as config.py)",
+            "beam_fwhm_deg": 0.5 * max(1, 512 // args.nside) if args.nside < 512 else 0.5,
             "pcg": "eps 1e-5, diag_cl preconditioner, cold start", "chains_per_gpu": 1,
             "l2_policy": "inputs larger than L2: each PCG iteration streams the 67 MB ring-spectra intermediate, 50 MB of maps and 100 MB of "
                          "recurrence/alm vectors (126 MB L2)"}
@@ -543,7 +555,7 @@ def sharded_measure(nside, lmax, steps, warmup):
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "CenteredGibbs polarised masked sky, ONE chain, m-sharded SHT with NCCL all-to-all ring<->m transpose "
-                                   "(PCG eps 1e-5, diag_cl precond) + inverse-gamma C_l draw", "nside": nside, "lmax": lmax, "fsky": 0.8,
+                                   "(PCG eps 1e-5, diag_cl precond) + inverse-gamma C_l draw", "nside": nside, "lmax": lmax, "fsky": 0.8, "mask": MASK_KIND,
                        "beam_fwhm_deg": fwhm, "parallelism": "m-shard x%d" % world,
                        "l2_policy": "inputs larger than L2"},
             "pcg_iterations_mean": n_pcg, "gpu_launches": launches, "sht_pair_ms": sum(st), "sht_pairs_per_s": 1e3 / sum(st),
@@ -570,7 +582,9 @@ def main():
     ap.add_argument("--nside", type=int, default=512)
     ap.add_argument("--lmax", type=int, default=1024)
     ap.add_argument("--pcg-iters", type=int, default=0)
+    ap.add_argument("--mask", default="galplane", choices=list(MASK_KINDS), help="synthetic sky mask, f_sky 0.8 (see make_mask)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-band-mask", action="store_true", help="skip the secondary measurement under the band mask of rounds 1-2a")
     ap.add_argument("--no-chain-batch", action="store_true", help="skip the secondary measurement with two chains per GPU")
     ap.add_argument("--no-config4", action="store_true", help="N >= 2: skip the m-sharded single-chain measurement (BASELINE config #4)")
     ap.add_argument("--config4-nside", type=int, default=2048)
@@ -582,6 +596,8 @@ def main():
                     help="chains: one independent chain per GPU (weak scaling, the default and the driver's contract); "
                          "sharded: ONE chain whose SHTs are m-sharded over the GPUs (BASELINE config #4, strong scaling)")
     args = ap.parse_args()
+    global MASK_KIND
+    MASK_KIND = args.mask
     if args.impl == "reference":
         return run_reference(args)
     if args.mode == "sharded":
@@ -616,8 +632,9 @@ def main():
     sB = data_rng.normal(nre) * utils.expand_per_l(_dev.f64(dlB), 3)
     q, u = plan.alm2map_spin2(sE, sB, fl=_dev.f64(bl))
     mask_d = _dev.f64(mask)
-    dQ = (q + data_rng.normal(npix) * np.sqrt(noise_var)) * mask_d
-    dU = (u + data_rng.normal(npix) * np.sqrt(noise_var)) * mask_d
+    skyQ = q + data_rng.normal(npix) * np.sqrt(noise_var)
+    skyU = u + data_rng.normal(npix) * np.sqrt(noise_var)
+    dQ, dU = skyQ * mask_d, skyU * mask_d
     bins = bins_for(lmax)
     bl_map = utils.expand_per_l(_dev.f64(bl), 0)
     noise_pol = torch.full((npix,), noise_var, dtype=torch.float64, device=dev)
@@ -652,18 +669,21 @@ def main():
     def unfold(b):
         return {"EE": utils.unfold_bins(b["EE"], bins["EE"]), "BB": utils.unfold_bins(b["BB"], bins["BB"])}
 
-    def step_device():
-        b = state["binned"]
-        sky, _ = cr.sample_mask(unfold(b))
-        pcg_its.append(cr.last_pcg_iterations)
-        if not pncp:
-            state["binned"] = cls.sample(sky)
-            return
-        b = cls.sample_low_l(sky, b)                       # PNCPGibbs.run_polarization, one iteration
-        mixed = cr.to_mixed(sky, unfold(b))
-        b, acc = cls.sample_high_l(mixed, b)
-        accepts.append((sum(acc["EE"]) + sum(acc["BB"])) / max(1, len(acc["EE"]) + len(acc["BB"])))
-        state["binned"] = b
+    def make_step(cr, cls, state, pcg_its, accepts):
+        def step():
+            b = state["binned"]
+            sky, _ = cr.sample_mask(unfold(b))
+            pcg_its.append(cr.last_pcg_iterations)
+            if not pncp:
+                state["binned"] = cls.sample(sky)
+                return
+            b = cls.sample_low_l(sky, b)                       # PNCPGibbs.run_polarization, one iteration
+            mixed = cr.to_mixed(sky, unfold(b))
+            b, acc = cls.sample_high_l(mixed, b)
+            accepts.append((sum(acc["EE"]) + sum(acc["BB"])) / max(1, len(acc["EE"]) + len(acc["BB"])))
+            state["binned"] = b
+        return step
+    step_device = make_step(cr, cls, state, pcg_its, accepts)
 
     h2d = d2h = 0
 
@@ -725,6 +745,28 @@ def main():
 
     value = whole_job_value(world, args.steps, ms_total)
     n_pcg = int(round(float(np.mean(its_timed)))) if its_timed else 0
+
+    # ---- secondary measurement: the same sampler under the axisymmetric band mask of rounds 1-2a (continuity with BENCH_r01; there
+    # no ring is cut by the mask edge, so with isotropic noise every ring has one weight and the mat-vec's ring stage runs no FFT)
+    band_mask = None
+    if MASK_KIND != "band" and not args.no_band_mask:
+        mask_b = make_mask(nside, kind="band")
+        mb_d = _dev.f64(mask_b)
+        dQb, dUb = skyQ * mb_d, skyU * mb_d
+        if pncp:
+            crb = PNCPConstrainedRealization({"Q": dQb, "U": dUb}, noise_pol * 1e4, noise_pol, bl_map, lmax, npix, fwhm, mask=mask_b,
+                                             rng="philox", seed=chain_seed(rank), ula=False, l_cut=L_CUT)
+            clsb = PNCPClsSampler({"Q": dQb, "U": dUb}, lmax, nside, bins, bl_map, noise_pol * 1e4, noise_pol, blocks, pv, L_CUT, n_iter=1,
+                                  mask=mask_b, rng=crb.rng)
+        else:
+            crb = PolarizedCenteredConstrainedRealization({"Q": dQb, "U": dUb}, noise_pol * 1e4, noise_pol, bl_map, lmax, npix, fwhm,
+                                                          mask=mask_b, rng="philox", seed=chain_seed(rank))
+            clsb = PolarizedCenteredClsSampler({"Q": dQb, "U": dUb}, lmax, nside, bins, bl_map, noise_pol, mask=mask_b, rng=crb.rng)
+        st_b, its_b = {"binned": binned_init()}, []
+        ms_b = timed(make_step(crb, clsb, st_b, its_b, []), args.warmup, args.steps)
+        band_mask = {"mask": "band: " + MASK_NOTE["band"], "value": whole_job_value(world, args.steps, ms_b), "unit": "it/s",
+                     "ms_per_step": ms_b / args.steps, "pcg_iterations_per_step": its_b[args.warmup:], "gpu_launches": counted["launches"]}
+        del crb, clsb, dQb, dUb
 
     # ---- secondary measurement: TWO chains per GPU whose PCG mat-vecs run as chain batches (one Legendre recurrence for both
     # right-hand sides: gs_cr_pcg_pol_batch; BASELINE config #5 / north_star (a) "batched over chains").  `value` above stays the
@@ -790,9 +832,13 @@ def main():
     # all rings: the spin-2 SHT pair of the metric and the launch the roofline is quoted on; idle rings skipped: the mat-vec
     # as the PCG of this workload runs it (rings wholly inside the mask carry N^-1 = 0 and are left out)
     stage_ms = profile_matvec(False)
+    old_const = L.gs_set_ring_const(0)
+    matvec_tr_ms = profile_matvec(True)     # every ring with weight through its transforms (the mat-vec of r01 / r02a)
+    L.gs_set_ring_const(old_const)
     matvec_ms = profile_matvec(True)
-    act, tot = C.c_int(0), C.c_int(0)
+    act, tot, nconst = C.c_int(0), C.c_int(0), C.c_int(0)
     _lib.check(L.gs_active_ring_pairs(plan._h, C.byref(act), C.byref(tot)))
+    _lib.check(L.gs_constant_rings(plan._h, C.byref(nconst)))
     fused_ring = "ring_apply_fused" in stage_ms
     pair_ms = sum(stage_ms.values())
     peak = C.c_double(0.0)
@@ -838,7 +884,17 @@ def main():
     roofline_hbm = {"kernel": ring_kernel, "bound": "hbm", "achieved": ring_bytes / (ring_ms * 1e-3) * 1e-9,
                     "peak": hbm_peak, "unit": "GB/s", "frac": ring_bytes / (ring_ms * 1e-3) * 1e-9 / hbm_peak,
                     "traffic": ncu_traffic(ring_kernel) if at_bench_size else None,
-                    "peak_source": hbm_src, "algorithmic_bytes_per_launch": ring_bytes}
+                    "peak_source": hbm_src, "algorithmic_bytes_per_launch": ring_bytes,
+                    "note": "every ring through its transforms (random-like weights): the ring stage of a stand-alone SHT pair"}
+    if fused_ring and "ring_apply_fused" in matvec_ms:
+        # the same kernel as the PCG of this workload launches it: idle ring pairs dropped, constant-weight rings without transforms
+        frac_active = 2.0 * act.value / nring
+        pcg_ring_bytes = ring_bytes * frac_active
+        roofline_hbm["as_run_by_the_pcg"] = {
+            "ms": matvec_ms["ring_apply_fused"], "algorithmic_bytes_per_launch": pcg_ring_bytes,
+            "achieved": pcg_ring_bytes / (matvec_ms["ring_apply_fused"] * 1e-3) * 1e-9,
+            "frac": pcg_ring_bytes / (matvec_ms["ring_apply_fused"] * 1e-3) * 1e-9 / hbm_peak,
+            "constant_weight_rings": nconst.value, "rings_with_weight": 2 * act.value, "rings": nring}
 
     # the HBM-bound vector kernels of one PCG iteration (algorithmic bytes: 4 + 7 + 4 arrays of 8 N_re bytes per field)
     ms3 = (C.c_float * 3)()
@@ -880,10 +936,14 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args), "pcg_iterations_mean": n_pcg,
             "e2e": {"value": e2e_val, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "chain_batch": chain_batch, "config4_m_sharded": config4,
+            "gpu_launches": launches, "band_mask": band_mask, "chain_batch": chain_batch, "config4_m_sharded": config4,
             "sht_pairs_per_s": world * 1e3 / pair_ms_max, "sht_pair_ms": pair_ms_max, "stage_ms": stage_ms,
             "pcg_matvec": {"ms": sum(matvec_ms.values()), "stage_ms": matvec_ms, "active_ring_pairs": act.value, "ring_pairs": tot.value,
-                           "note": "mat-vec of the PCG: ring pairs wholly inside the mask (N^-1 = 0) are skipped, exact"},
+                           "constant_weight_rings": nconst.value, "rings": 4 * nside - 1,
+                           "stage_ms_all_transforms": matvec_tr_ms,
+                           "note": "mat-vec of the PCG: ring pairs wholly inside the mask (N^-1 = 0) are skipped, exact; rings whose N^-1 is "
+                                   "one number (isotropic noise, ring not cut by the mask edge; idle rings count) skip their FFTs: n w times "
+                                   "the alias-folded spectrum (gs_set_ring_const); stage_ms_all_transforms = the same mat-vec with that off"},
             "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_pcg": roofline_pcg, "cpu_baseline": cpu_baseline, "clocks": clocks.summary(),
             "pcg_iterations_per_step": its_timed,
         }

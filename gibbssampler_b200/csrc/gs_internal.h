@@ -155,6 +155,7 @@ struct gs_plan {
     double* mwg_maps;    // [G][2][npix]  (Q maps of all blocks, then U maps)
     int mwg_group;       // G
     double* mwg_small;   // reduction partials, likelihood pair, per-l filters
+    double* mwg_data;    // [2][npix] the data maps with the constant-weight rings in spectral storage (gs_ring_mwg_data)
     int* mwg_meta;       // bins / block boundaries / per-block mmax / flags (re-uploaded when the blocking changes)
     std::vector<int> mwg_meta_host;
     // rings / ring pairs that carry a non-zero pixel weight (gs_active_rings_build); use_act = the Legendre and fused
@@ -224,13 +225,17 @@ int gs_leg_prepare(gs_plan* p);   // per-device kernel attributes (dynamic share
 // ringfft.cu
 int gs_ring_setup(gs_plan* p);
 // nc > 1 (chain batch): chain c uses the spectra p->Fm + c gs_fm_stride(p) and the maps + c map_stride
+// wconst (spin 2, unsharded, no split rings; see gs_ring_mwg_data): rings with a constant pixel weight are written in spectral storage
 int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st, const int* skip = nullptr, int nc = 1,
-                  int64_t map_stride = 0);
+                  int64_t map_stride = 0, const double* wconst = nullptr);
 int gs_ring_anal(gs_plan* p, int spin, const double* mapQ, const double* mapU, const double* pixw, cudaStream_t st,
                  const int* skip = nullptr, int nc = 1, int64_t map_stride = 0);
 int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, const int* skip = nullptr, int nc = 1);
 int gs_ring_synth_batch(gs_plan* p, const double2* F, int64_t f_stride, const int* mmax, double* mapQ, double* mapU,
-                        int64_t map_stride, int nb, cudaStream_t st, const unsigned char* ract = nullptr);
+                        int64_t map_stride, int nb, cudaStream_t st, const unsigned char* ract = nullptr, const double* wconst = nullptr);
+// Spectral storage of constant-weight rings (Metropolis sweep): out = the Q/U maps with every ring whose wconst is a number replaced
+// by the unitary DFT of its pixels z_j = Q_j + i U_j (Re in the Q slots, Im in the U slots); other rings are copied.
+int gs_ring_mwg_data(gs_plan* p, const double* mapQ, const double* mapU, double* outQ, double* outU, const double* wconst, cudaStream_t st);
 // legendre.cu: block-batched spin-2 synthesis for the Metropolis-within-Gibbs sweep (see leg_synth_blocks_kernel)
 int gs_leg_synth_blocks(gs_plan* p, const double* almE, const double* almB, const double* dflE, const double* dflB,
                         const int* lbE, int e0, int e1, const int* lbB, int b0, int b1, int lend, double2* Fblk, cudaStream_t st);

@@ -250,6 +250,7 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
     p->mwg_maps = nullptr;
     p->mwg_group = 0;
     p->mwg_small = nullptr;
+    p->mwg_data = nullptr;
     p->mwg_meta = nullptr;
     p->world = world;
     p->rank = rank;
@@ -368,6 +369,7 @@ extern "C" int gs_plan_destroy(gs_plan* p)
     cudaFree(p->mwg_F);
     cudaFree(p->mwg_maps);
     cudaFree(p->mwg_small);
+    cudaFree(p->mwg_data);
     cudaFree(p->mwg_meta);
     delete p;
     return GS_OK;

@@ -628,7 +628,8 @@ template <bool SH>
 __global__ void __launch_bounds__(RF_NT, 2)
 ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __restrict__ groups, const double2* __restrict__ Fm,
                   double* __restrict__ mapQ, double* __restrict__ mapU, const int* __restrict__ skip, int64_t f_stride,
-                  int64_t map_stride, const int* __restrict__ mmax, int spin2, const unsigned char* __restrict__ ract)
+                  int64_t map_stride, const int* __restrict__ mmax, int spin2, const unsigned char* __restrict__ ract,
+                  const double* __restrict__ wconst)
 {
     if (skip && *skip) return;
     if (group_idle(ract, jobs, groups)) return;
@@ -639,6 +640,23 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
     mapU += blockIdx.y * map_stride;
     const int mcap = mmax ? min(mmax[blockIdx.y], P.lmax) : P.lmax;
     double2* twq = smem;
+    if (group_const(wconst, jobs, groups)) {
+        // Spectral storage (Metropolis sweep, spin 2: Q and U of ONE ring with ONE weight w): the sweep only ever forms
+        // w sum_j |z_j - z'_j|^2 over the ring, z = Q + i U, and the unitary DFT keeps that sum, so slot k of the ring receives
+        // sqrt(n) Z_k (the unitary DFT of the pixels this launch would have produced) and no transform runs
+        const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
+        ring_build_Z<SH>(P, S, Fm, min(mcap, ring_mtop(P, S.job.ringA, spin2)), S.scratch, mmax != nullptr, true);
+        __syncthreads();
+        const double sn = sqrt((double)S.n);
+        double* oa = mapQ + ring_first_pixel<SH>(P, S.job.ringA);
+        double* ob = mapU + ring_first_pixel<SH>(P, S.job.ringA);
+        for (int k = S.tid; k < S.n; k += S.nt) {
+            const double2 z = S.buf[PADI(k)];
+            oa[k] = sn * z.x;
+            ob[k] = sn * z.y;
+        }
+        return;
+    }
     load_twq(P, twq);
     const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
     ring_build_Z<SH>(P, S, Fm, min(mcap, ring_mtop(P, S.job.ringA, spin2)), S.scratch, mmax != nullptr);
@@ -688,6 +706,45 @@ ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __rest
     ring_idft(P, S.buf, twq, n, S.bsi, S.tid, S.nt);
     // Bluestein: the last chirp product is taken as the spectrum is unpacked
     ring_unpack_F<SH>(P, S, UNPACK_CONJ, Fm, ring_mtop(P, job.ringA, spin2), S.bsi >= 0 ? S.chirp : nullptr);
+}
+
+// Spin-2 maps -> the storage the Metropolis sweep compares in: groups of constant-weight rings get the unitary DFT of
+// z_j = Q_j + i U_j, Ztilde_k = n^-1/2 sum_j z_j e^{-2 pi i jk/n} (the counterpart of the spectral branch of ring_synth_kernel, whose
+// pixels would be z_j = sum_k Z_k e^{+2 pi i jk/n} = n^-1/2 sum_k Ztilde_k e^{..}); every other ring is copied.
+__global__ void __launch_bounds__(RF_NT, 2)
+ring_mwg_data_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __restrict__ groups, const double* __restrict__ mapQ,
+                     const double* __restrict__ mapU, double* __restrict__ outQ, double* __restrict__ outU, const double* __restrict__ wconst)
+{
+    extern __shared__ double2 smem[];
+    double2* twq = smem;
+    const bool spectral = group_const(wconst, jobs, groups);
+    if (spectral) load_twq(P, twq);
+    const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
+    const int n = S.n;
+    const int64_t s0 = P.ring_start[S.job.ringA];
+    const double* ia = mapQ + s0;
+    const double* ib = mapU + s0;
+    if (!spectral) {
+        for (int j = S.tid; j < n; j += S.nt) { outQ[s0 + j] = ia[j]; outU[s0 + j] = ib[j]; }
+        return;
+    }
+    const int lg = 31 - __clz(n);
+    // sum_j z_j e^{-2 pi i jk/n} = conj( idft( conj z ) ), as in ring_anal_kernel
+    for (int j = S.tid; j < S.M; j += S.nt) {
+        const int pos = PADI(S.bsi < 0 ? (int)(__brev((unsigned)j) >> (32 - lg)) : j);
+        if (j >= n) { S.buf[pos] = make_double2(0.0, 0.0); continue; }
+        double2 z = make_double2(ia[j], -ib[j]);
+        if (S.bsi >= 0) z = cmul(z, __ldg(&S.chirp[j]));
+        S.buf[pos] = z;
+    }
+    ring_idft(P, S.buf, twq, n, S.bsi, S.tid, S.nt);
+    const double s = rsqrt((double)n);
+    for (int k = S.tid; k < n; k += S.nt) {
+        double2 c = S.buf[PADI(k)];
+        if (S.bsi >= 0) c = cmul(c, __ldg(&S.chirp[k]));
+        outQ[s0 + k] = s * c.x;
+        outU[s0 + k] = -s * c.y;
+    }
 }
 
 // Ring stage of the PCG mat-vec A^T N^-1 A in ONE kernel: F_m(ring) -> pixels of the ring (kept in shared memory) ->
@@ -1028,6 +1085,7 @@ int gs_ring_setup(gs_plan* p)
     GS_CHECK_CUDA(cudaFuncSetAttribute(ring_anal_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GS_CHECK_CUDA(cudaFuncSetAttribute(ring_synth_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GS_CHECK_CUDA(cudaFuncSetAttribute(ring_anal_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GS_CHECK_CUDA(cudaFuncSetAttribute(ring_mwg_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GS_CHECK_CUDA(cudaFuncSetAttribute(ring_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GS_CHECK_CUDA(cudaFuncSetAttribute(ring_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     GS_CHECK_CUDA(cudaFuncSetAttribute(ring_synth_split_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1108,9 +1166,11 @@ int gs_ring_setup(gs_plan* p)
     return GS_OK;
 }
 
-int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st, const int* skip, int nc, int64_t map_stride)
+int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t st, const int* skip, int nc, int64_t map_stride,
+                  const double* wconst)
 {
     if (nc > 1 && p->world > 1) { gs_set_error("chain batches need an unsharded plan"); return GS_E_BADARG; }
+    if (wconst && (spin != 2 || p->world > 1 || p->nsjobs2 > 0 || nc > 1)) { gs_set_error("spectral ring storage: spin 2, unsharded plan without split rings"); return GS_E_BADARG; }
     const int nj = spin == 0 ? p->ngroups0 : p->ngroups2, ns = spin == 0 ? p->nsjobs0 : p->nsjobs2;
     if (nc > 1 && ns > 0) {   // rings on the split path (nside >= 1024) share one scratch buffer: the chains of a batch take turns
         double2* F0 = p->Fm;
@@ -1141,8 +1201,8 @@ int gs_ring_synth(gs_plan* p, int spin, double* mapQ, double* mapU, cudaStream_t
         g_gs_launches += 2;
     }
     if (nj > 0) {
-        if (sh) ring_synth_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr, spin ? 1 : 0, ract);
-        else ring_synth_kernel<false><<<dim3(nj, nc), RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, nc > 1 ? gs_fm_stride(p) : 0, nc > 1 ? map_stride : 0, nullptr, spin ? 1 : 0, ract);
+        if (sh) ring_synth_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, 0, 0, nullptr, spin ? 1 : 0, ract, nullptr);
+        else ring_synth_kernel<false><<<dim3(nj, nc), RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, F, mapQ, mu, skip, nc > 1 ? gs_fm_stride(p) : 0, nc > 1 ? map_stride : 0, nullptr, spin ? 1 : 0, ract, wconst);
         GS_CHECK_LAUNCH();
     }
     g_gs_launches += 1;
@@ -1225,13 +1285,23 @@ int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, con
 }
 
 // nb spin-2 ring syntheses in one launch: spectra F + k f_stride (m <= mmax[k]) -> maps Q/U + k map_stride
+int gs_ring_mwg_data(gs_plan* p, const double* mapQ, const double* mapU, double* outQ, double* outU, const double* wconst, cudaStream_t st)
+{
+    if (p->world > 1 || p->nsjobs2 > 0) { gs_set_error("spectral ring storage needs an unsharded plan without split rings"); return GS_E_BADARG; }
+    if (p->ngroups2 <= 0) return GS_OK;
+    ring_mwg_data_kernel<<<p->ngroups2, RF_NT, p->ring_smem, st>>>(p->d, p->jobs2, p->groups2, mapQ, mapU, outQ, outU, wconst);
+    GS_CHECK_LAUNCH();
+    g_gs_launches += 1;
+    return GS_OK;
+}
+
 int gs_ring_synth_batch(gs_plan* p, const double2* F, int64_t f_stride, const int* mmax, double* mapQ, double* mapU,
-                        int64_t map_stride, int nb, cudaStream_t st, const unsigned char* ract)
+                        int64_t map_stride, int nb, cudaStream_t st, const unsigned char* ract, const double* wconst)
 {
     if (p->world > 1 || p->nsjobs2 > 0) { gs_set_error("batched ring synthesis needs an unsharded plan without split rings"); return GS_E_BADARG; }
     if (nb <= 0 || p->ngroups2 <= 0) return GS_OK;
     ring_synth_kernel<false><<<dim3(p->ngroups2, nb), RF_NT, p->ring_smem, st>>>(p->d, p->jobs2, p->groups2, F, mapQ, mapU, nullptr, f_stride,
-                                                                                 map_stride, mmax, 1, ract);
+                                                                                 map_stride, mmax, 1, ract, wconst);
     GS_CHECK_LAUNCH();
     g_gs_launches += 1;
     return GS_OK;

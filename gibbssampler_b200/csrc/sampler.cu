@@ -593,11 +593,26 @@ extern "C" int gs_mwg_sweep_blocks(gs_plan* p, const double* snc_E, const double
 
     GS_CHECK_CUDA(cudaMemsetAsync(flags, 0, (ntot + 1) * sizeof(int), st));
     // block maps are only ever weighted by N^-1: the rings on which it vanishes identically need no ring FFT
+    // Rings on which N^-1 is one number w (isotropic noise, not cut by the mask edge; gs_set_ring_const): every quantity of the sweep
+    // on such a ring is w sum_j |z_j - z'_j|^2 with z = Q + i U, which the unitary DFT along the ring leaves unchanged.  Data, current
+    // model and all block maps of these rings are therefore kept as sqrt(n) times the alias-folded ring spectrum (what the ring FFT
+    // would start from) and their FFTs are never run; test / decide / apply kernels see ordinary arrays.
     const unsigned char* ract = nullptr;
+    const double* wconst = nullptr;
     if (g_gs_ring_skip) {
         int rc0 = gs_active_rings_build(p, inv_noise, st);
         if (rc0) return rc0;
         ract = p->act_ring;
+        if (g_gs_ring_const && p->ring_wconst) wconst = p->ring_wconst;
+    }
+    const double* dTQ = d_Q;
+    const double* dTU = d_U;
+    if (wconst) {
+        if (!p->mwg_data) GS_CHECK_CUDA(cudaMalloc(&p->mwg_data, (size_t)2 * npix * sizeof(double)));
+        int rc0 = gs_ring_mwg_data(p, d_Q, d_U, p->mwg_data, p->mwg_data + npix, wconst, st);
+        if (rc0) return rc0;
+        dTQ = p->mwg_data;
+        dTU = p->mwg_data + npix;
     }
     const int eb0 = nblk_E ? blocks_E_host[0] : 0, eb1 = nblk_E ? blocks_E_host[nblk_E] : 0;
     const int bb0 = nblk_B ? blocks_B_host[0] : 0, bb1 = nblk_B ? blocks_B_host[nblk_B] : 0;
@@ -606,8 +621,8 @@ extern "C" int gs_mwg_sweep_blocks(gs_plan* p, const double* snc_E, const double
     GS_CHECK_LAUNCH();
     int rc;
     if ((rc = gs_leg_synth(p, 2, snc_E, snc_B, GS_ALM_REAL, flE, st, nullptr, flB))) return rc;
-    if ((rc = gs_ring_synth(p, 2, rQ, rU, st))) return rc;
-    mwg_resid_kernel<<<SM_GRID, SM_NT, 0, st>>>(d_Q, d_U, rQ, rU, inv_noise, npix, partials);
+    if ((rc = gs_ring_synth(p, 2, rQ, rU, st, nullptr, 1, 0, wconst))) return rc;
+    mwg_resid_kernel<<<SM_GRID, SM_NT, 0, st>>>(dTQ, dTU, rQ, rU, inv_noise, npix, partials);
     mwg_first_lik_kernel<<<1, SM_NT, 0, st>>>(partials, SM_GRID, lik);
     GS_CHECK_LAUNCH();
     g_gs_launches += 4;
@@ -621,7 +636,7 @@ extern "C" int gs_mwg_sweep_blocks(gs_plan* p, const double* snc_E, const double
         if (b1 > b0) lend = std::max(lend, meta[off_lbB + b1]);
         lend = std::min(lend, L + 1);
         if ((rc = gs_leg_synth_blocks(p, snc_E, snc_B, dflE, dflB, lbE, e0, e1, lbB, b0, b1, lend, p->mwg_F, st))) return rc;
-        if ((rc = gs_ring_synth_batch(p, p->mwg_F, slotF, mmax + g0, p->mwg_maps, p->mwg_maps + (int64_t)G * npix, npix, ng, st, ract)))
+        if ((rc = gs_ring_synth_batch(p, p->mwg_F, slotF, mmax + g0, p->mwg_maps, p->mwg_maps + (int64_t)G * npix, npix, ng, st, ract, wconst)))
             return rc;
         for (int k = g0; k < g1; ++k) {
             const bool isE = k < nblk_E;

@@ -152,3 +152,61 @@ def test_pcg_solution_with_and_without_constant_rings(kind, eps, tol):
     (a, ia), (b, ib) = out
     assert abs(ia - ib) <= 3
     assert np.abs(a - b).max() <= tol * np.abs(b).max()
+
+
+@pytest.mark.parametrize("kind", ["band", "galplane", "south"])
+@pytest.mark.parametrize("nside,lmax", [(16, 32), (32, 80)])
+def test_metropolis_sweep_with_spectral_ring_storage(kind, nside, lmax):
+    """gs_mwg_sweep_blocks keeps data, model and block maps of constant-weight rings as the unitary DFT of Q + i U along the ring
+    (no ring FFT for them): same accept flags and the same tracked likelihood as with every ring in pixel space, and the tracked
+    likelihood equals a fresh evaluation (NonCenteredGibbs.py:401-445)."""
+    from gibbssampler_b200 import _lib
+    from gibbssampler_b200._dev import f64, ptr, stream
+    from tests.test_cr_gpu import make_problem
+    from tests.test_mwg_blocks_gpu import binned_start, build
+    L = _lib.lib()
+    P = make_problem(nside, lmax, seed=5)
+    z = np.cos(_angles(nside)[0])
+    mask = (z > -0.5).astype(float) if kind == "south" else (_weights(kind, nside, None) != 0).astype(float)
+    P["dQ"], P["dU"], P["mask"] = P["dQ"] * mask, P["dU"] * mask, mask   # make_problem's data under this test's mask
+    ee = np.arange(0, lmax + 2)
+    bins = {"EE": ee, "BB": ee.copy()}
+    blocks = {"EE": np.arange(2, lmax + 2), "BB": np.concatenate([[2, lmax // 2], np.arange(lmax // 2 + 1, lmax + 2)])}
+    rng = np.random.default_rng(2)
+    s = {p: f64(rng.standard_normal((lmax + 1) ** 2)) for p in ("EE", "BB")}
+    bh = {p: np.ascontiguousarray(bins[p], dtype=np.int32) for p in bins}
+    kh = {p: np.ascontiguousarray(blocks[p], dtype=np.int32) for p in blocks}
+    nblk = {p: len(blocks[p]) - 1 for p in blocks}
+    ntot = nblk["EE"] + nblk["BB"]
+    res = []
+    for on in (1, 0):
+        nc = build(P, bins, blocks, 1, 0, True)
+        cur = {p: f64(binned_start(P, bins)[p]) for p in ("EE", "BB")}
+        np.random.seed(5)
+        prop = nc.propose_dl(cur)
+        logr = {p: torch.zeros_like(cur[p]) for p in cur}
+        u = f64(np.random.uniform(size=ntot))
+        acc = torch.zeros(ntot, dtype=torch.int32, device="cuda")
+        out = torch.zeros(1, dtype=torch.float64, device="cuda")
+        old = L.gs_set_ring_const(on)
+        try:
+            _lib.check(L.gs_mwg_sweep_blocks(nc.plan._h, ptr(s["EE"]), ptr(s["BB"]), ptr(cur["EE"]), ptr(cur["BB"]), ptr(prop["EE"]),
+                                             ptr(prop["BB"]), ptr(logr["EE"]), ptr(logr["BB"]), bh["EE"].ctypes.data, lmax + 1,
+                                             bh["BB"].ctypes.data, lmax + 1, kh["EE"].ctypes.data, nblk["EE"], kh["BB"].ctypes.data,
+                                             nblk["BB"], 1, ptr(nc.bl_gauss_d), 0, ptr(nc.d_Q), ptr(nc.d_U), ptr(nc.inv_noise_pol), ptr(u),
+                                             ptr(acc), ptr(out), 0, stream()))
+            torch.cuda.synchronize()
+            nconst = C.c_int(-1)
+            _lib.check(L.gs_constant_rings(nc.plan._h, C.byref(nconst)))
+        finally:
+            L.gs_set_ring_const(old)
+        fresh = nc.compute_log_likelihood(cur, s)
+        assert abs(float(out.item()) - fresh) <= 1e-10 * abs(fresh)
+        res.append((acc.cpu().numpy(), float(out.item()), {p: cur[p].cpu().numpy() for p in cur}, nconst.value))
+    (a1, l1, c1, n1), (a0, l0, c0, _) = res
+    assert 0 < n1 <= 4 * nside - 1 and (kind != "galplane" or n1 < 4 * nside - 1)
+    assert 3 < int(a0.sum()) < ntot - 3
+    assert np.array_equal(a1, a0)
+    assert abs(l1 - l0) <= 1e-11 * abs(l0)
+    for p in c0:
+        assert np.array_equal(c1[p], c0[p])
