@@ -776,11 +776,41 @@ ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
         // = n w X_k, so F'_m = n w X_{m mod n} e^{-i m phi0} follows from the alias-folded spectrum X without any transform
         const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
         const int mtop = ring_mtop(P, S.job.ringA, spin2);
+        const double wA = wconst[S.job.ringA], wB = wconst[S.job.ringB >= 0 ? S.job.ringB : S.job.ringA];
+        // No ring of the group aliases (2 m_top <= n: every cap ring beyond the first quarter of the cap and the whole belt): X_k is
+        // the single term F_m e^{i m phi0}, the phases cancel and F'_m = n w F_m streams through registers; m = 0 keeps its real
+        // part (X_0 = G_0 + conj G_0 with weight 1/2) and m = n/2 (belt rings when lmax = 2 nside) meets its own mirror term.
+        bool direct = true;
+        {
+            const int2 g = groups[blockIdx.x];
+            for (int s = 0; s < g.y; ++s) {
+                const int ra = jobs[g.x + s].ringA;
+                direct = direct && 2 * ring_mtop(P, ra, spin2) <= P.ring_nphi[ra];
+            }
+        }
+        if (direct) {
+            const RingJob& job = S.job;
+            const double sa = (double)S.n * wA, sb = (double)S.n * wB;
+            for (int m = S.tid; m <= mtop; m += S.nt) {
+                const int64_t ia = fm_ring_index<SH>(P, job.compA, job.ringA, m);
+                const int64_t ib = job.ringB >= 0 ? fm_ring_index<SH>(P, job.compB, job.ringB, m) : ia;
+                double2 a = Fm[ia], b = job.ringB >= 0 ? Fm[ib] : make_double2(0.0, 0.0);
+                if (m == 0) { a.y = 0.0; b.y = 0.0; }
+                else if (2 * m == S.n) {
+                    const double2 e2 = ring_phase(P, job.ringA, 2 * m);   // F + conj(F e^{2 i m phi0})
+                    const double2 ta = cmul(a, e2), tb = cmul(b, e2);
+                    a = make_double2(a.x + ta.x, a.y - ta.y);
+                    b = make_double2(b.x + tb.x, b.y - tb.y);
+                }
+                Fm[ia] = make_double2(sa * a.x, sa * a.y);
+                if (job.ringB >= 0) Fm[ib] = make_double2(sb * b.x, sb * b.y);
+            }
+            return;
+        }
         ring_build_Z<SH>(P, S, Fm, mtop, S.scratch, false, true);
         __syncthreads();
         const double half_n = 0.5 * (double)S.n;
-        ring_unpack_F<SH>(P, S, UNPACK_PLAIN, Fm, mtop, nullptr, half_n * wconst[S.job.ringA],
-                          half_n * wconst[S.job.ringB >= 0 ? S.job.ringB : S.job.ringA]);
+        ring_unpack_F<SH>(P, S, UNPACK_PLAIN, Fm, mtop, nullptr, half_n * wA, half_n * wB);
         return;
     }
     load_twq(P, twq);
