@@ -40,7 +40,7 @@ struct gs_pcg_ws {
     double* fuse_out;       // its result
     double* red;       // sharded plans: local sums in, all-reduced sums out (NULL on one GPU)
     PcgState* state;
-    PcgState* host_state;  // pinned
+    PcgState* host_state;  // pinned, two slots (the graph path of a solve keeps two polls in flight)
 };
 
 // block-level sum of NR values, then the last block to finish adds the per-block partials in a
@@ -340,7 +340,7 @@ static gs_pcg_ws* get_ws(gs_plan* p)
     void* d = nullptr;
     ok = ok && cudaMalloc(&d, sizeof(PcgState)) == cudaSuccess;
     if (ok) { p->owned.push_back(d); w->state = (PcgState*)d; }
-    ok = ok && cudaMallocHost((void**)&w->host_state, sizeof(PcgState)) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&w->host_state, 2 * sizeof(PcgState)) == cudaSuccess;
     if (!ok) { gs_set_error("PCG workspace allocation failed: %s", cudaGetErrorString(cudaGetLastError())); delete w; return nullptr; }
     p->pcg_ws = w;
     return w;
@@ -375,7 +375,7 @@ static gs_pcg_ws* get_ws_batch(gs_plan* p)
         void* d = nullptr;
         ok = ok && cudaMalloc(&d, sizeof(PcgState)) == cudaSuccess;
         if (ok) { p->owned.push_back(d); w[k].state = (PcgState*)d; }
-        ok = ok && cudaMallocHost((void**)&w[k].host_state, sizeof(PcgState)) == cudaSuccess;
+        ok = ok && cudaMallocHost((void**)&w[k].host_state, 2 * sizeof(PcgState)) == cudaSuccess;
     }
     void* d = nullptr;
     ok = ok && cudaMalloc(&d, sizeof(int)) == cudaSuccess;
@@ -561,16 +561,48 @@ static int cr_pcg_impl(gs_plan* p, int spin, const double* dl_EE, const double* 
         cudaGraphDestroy(graph);
         if (ce != cudaSuccess) { gs_set_error("PCG graph instantiate: %s", cudaGetErrorString(ce)); return GS_E_CUDA; }
     }
-    while (!finished) {
-        if (gexec && launched + check_every <= itermax) {
-            cudaError_t ce = cudaGraphLaunch(gexec, st);
-            if (ce != cudaSuccess) { cudaGraphExecDestroy(gexec); gs_set_error("PCG graph launch: %s", cudaGetErrorString(ce)); return GS_E_CUDA; }
-            launched += check_every;
-            g_gs_launches += launches_per_graph;
-        } else {
-            for (int k = 0; k < check_every && launched < itermax; ++k, ++launched)
-                if ((rc = iteration(st))) { if (gexec) cudaGraphExecDestroy(gexec); return rc; }
+    if (gexec) {
+        // Two batches in flight: the host enqueues batch k + 1 (graph replay + copy of the solver state + event) BEFORE it waits for the
+        // state that follows batch k, so the wake-up after a poll and the next graph launch are hidden behind 8 iterations of GPU work
+        // (43 polls per solve at NSIDE 512; with 8 ranks on shared host cores this was the remaining loss of the chains mode).  Once
+        // the done flag is set every kernel of a later batch returns at once: at most one batch of no-ops per solve, same iterations.
+        PcgState* hs = w->host_state;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        cudaError_t ce = cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming);
+        if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming);
+        int cur = 0, inflight = 0;
+        while (ce == cudaSuccess && !finished) {
+            while (ce == cudaSuccess && inflight < 2 && launched + check_every <= itermax) {
+                const int sl = (cur + inflight) & 1;
+                ce = cudaGraphLaunch(gexec, st);
+                if (ce == cudaSuccess) ce = cudaMemcpyAsync(hs + sl, w->state, sizeof(PcgState), cudaMemcpyDeviceToHost, st);
+                if (ce == cudaSuccess) ce = cudaEventRecord(ev[sl], st);
+                launched += check_every;
+                g_gs_launches += launches_per_graph;
+                ++inflight;
+            }
+            if (ce != cudaSuccess || inflight == 0) break;   // fewer than check_every iterations left: the loop below runs them
+            ce = cudaEventSynchronize(ev[cur]);
+            if (ce != cudaSuccess) break;
+            --inflight;
+            if (hs[cur].done || launched >= itermax) {
+                if (inflight) ce = cudaStreamSynchronize(st);   // the batch behind it: no-ops after `done`, or the last iterations
+                if (inflight && ce == cudaSuccess) cur ^= 1;
+                hs[0] = hs[cur];
+                finished = hs[0].done || launched >= itermax;
+                inflight = 0;
+                if (!finished) cur = 0;
+                continue;
+            }
+            cur ^= 1;
         }
+        if (ev[0]) cudaEventDestroy(ev[0]);
+        if (ev[1]) cudaEventDestroy(ev[1]);
+        if (ce != cudaSuccess) { cudaGraphExecDestroy(gexec); gs_set_error("PCG graph loop: %s", cudaGetErrorString(ce)); return GS_E_CUDA; }
+    }
+    while (!finished) {
+        for (int k = 0; k < check_every && launched < itermax; ++k, ++launched)
+            if ((rc = iteration(st))) { if (gexec) cudaGraphExecDestroy(gexec); return rc; }
         cudaError_t ce = cudaMemcpyAsync(w->host_state, w->state, sizeof(PcgState), cudaMemcpyDeviceToHost, st);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
         if (ce != cudaSuccess) { if (gexec) cudaGraphExecDestroy(gexec); gs_set_error("PCG poll: %s", cudaGetErrorString(ce)); return GS_E_CUDA; }
