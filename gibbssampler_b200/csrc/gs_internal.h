@@ -144,6 +144,9 @@ struct gs_plan {
     int ngroups2;
     int2* groups0;
     int ngroups0;
+    // the same lists reordered for the weight map of the current call (gs_ring_order_build): groups that need transforms first
+    int2* groups2_dyn;
+    int2* groups0_dyn;
     SplitJob* sjobs2;   // rings of the spin-2 / spin-0 lists that take the split path (empty below nside 2048)
     int nsjobs2;
     SplitJob* sjobs0;
@@ -235,6 +238,9 @@ int gs_ring_synth_batch(gs_plan* p, const double2* F, int64_t f_stride, const in
                         int64_t map_stride, int nb, cudaStream_t st, const unsigned char* ract = nullptr, const double* wconst = nullptr);
 // Spectral storage of constant-weight rings (Metropolis sweep): out = the Q/U maps with every ring whose wconst is a number replaced
 // by the unitary DFT of its pixels z_j = Q_j + i U_j (Re in the Q slots, Im in the U slots); other rings are copied.
+// Launch order of the ring groups for the current weight map (after gs_active_rings_build filled act_ring / ring_wconst): groups with a
+// ring that needs its transforms first (they are the long CTAs), then constant-weight groups, then idle ones; stable within a class
+int gs_ring_order_build(gs_plan* p, cudaStream_t st);
 int gs_ring_mwg_data(gs_plan* p, const double* mapQ, const double* mapU, double* outQ, double* outU, const double* wconst, cudaStream_t st);
 // legendre.cu: block-batched spin-2 synthesis for the Metropolis-within-Gibbs sweep (see leg_synth_blocks_kernel)
 int gs_leg_synth_blocks(gs_plan* p, const double* almE, const double* almB, const double* dflE, const double* dflB,

@@ -1520,7 +1520,7 @@ int gs_active_rings_build(gs_plan* p, const double* pixw, cudaStream_t st)
     list_slot0_kernel<<<(2 * (p->d.lmax + 1) * 32 + 255) / 256, 256, 0, st>>>(p->d, p->act_pairs, p->act_count, p->act_slot0);
     GS_CHECK_LAUNCH();
     g_gs_launches += 3;
-    return GS_OK;
+    return gs_ring_order_build(p, st);
 }
 
 // ------------------------------------------------------------------ host launchers

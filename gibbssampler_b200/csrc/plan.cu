@@ -235,6 +235,7 @@ static int plan_create_impl(gs_plan** out, int nside, int lmax, int device, int 
     p->d.lmax = lmax;
     p->jobs0 = p->jobs2 = nullptr;
     p->groups0 = p->groups2 = nullptr;
+    p->groups0_dyn = p->groups2_dyn = nullptr;
     p->ngroups0 = p->ngroups2 = 0;
     p->sjobs0 = p->sjobs2 = nullptr;
     p->nsjobs0 = p->nsjobs2 = 0;

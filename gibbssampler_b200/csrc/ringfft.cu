@@ -405,6 +405,51 @@ __device__ __forceinline__ bool group_const(const double* __restrict__ wconst, c
     }
     return all;
 }
+// groups_out = groups, stably partitioned into (needs transforms | constant weights only | idle): one block
+__global__ void __launch_bounds__(1024) ring_order_kernel(const RingJob* __restrict__ jobs, const int2* __restrict__ groups, int ngroups,
+                                                          const unsigned char* __restrict__ ract, const double* __restrict__ wconst,
+                                                          int2* __restrict__ groups_out)
+{
+    __shared__ int wcount[32][3];
+    __shared__ int base[3], total[3];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    auto cls_of = [&](int gi) {
+        if (gi >= ngroups) return 3;
+        const int2 g = groups[gi];
+        bool any = false, allc = true;
+        for (int s = 0; s < g.y; ++s) {
+            const RingJob jb = jobs[g.x + s];
+            any = any || ract[jb.ringA] || (jb.ringB >= 0 && ract[jb.ringB]);
+            const double a = wconst[jb.ringA], b = jb.ringB >= 0 ? wconst[jb.ringB] : 0.0;
+            allc = allc && a == a && b == b;
+        }
+        return !any ? 2 : allc ? 1 : 0;
+    };
+    for (int pass = 0; pass < 2; ++pass) {
+        if (tid < 3) { if (pass == 0) total[tid] = 0; else base[tid] = tid == 0 ? 0 : tid == 1 ? total[0] : total[0] + total[1]; }
+        __syncthreads();
+        for (int g0 = 0; g0 < ngroups; g0 += 1024) {
+            const int gi = g0 + tid, c = cls_of(gi);
+            unsigned bal[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { bal[k] = __ballot_sync(0xffffffffu, c == k); if (lane == 0) wcount[w][k] = __popc(bal[k]); }
+            __syncthreads();
+            if (pass == 1 && c < 3) {
+                int off = base[c];
+                for (int i = 0; i < w; ++i) off += wcount[i][c];
+                groups_out[off + __popc(bal[c] & ((1u << lane) - 1u))] = groups[gi];
+            }
+            __syncthreads();
+            if (tid < 3) {
+                int t = 0;
+                for (int i = 0; i < 32; ++i) t += wcount[i][tid];
+                if (pass == 0) total[tid] += t; else base[tid] += t;
+            }
+            __syncthreads();
+        }
+    }
+}
+
 __device__ __forceinline__ bool split_idle(const unsigned char* __restrict__ ract, const SplitJob& jb)
 {
     return ract && !(ract[jb.ringA] || (jb.ringB >= 0 && ract[jb.ringB]));
@@ -1185,6 +1230,8 @@ int gs_ring_setup(gs_plan* p)
     if ((rc = put(s0.data(), s0.size() * sizeof(SplitJob), (void**)&p->sjobs0))) return rc;
     if ((rc = put(g2.data(), g2.size() * sizeof(int2), (void**)&p->groups2))) return rc;
     if ((rc = put(g0.data(), g0.size() * sizeof(int2), (void**)&p->groups0))) return rc;
+    if ((rc = put(g2.data(), g2.size() * sizeof(int2), (void**)&p->groups2_dyn))) return rc;
+    if ((rc = put(g0.data(), g0.size() * sizeof(int2), (void**)&p->groups0_dyn))) return rc;
     p->ngroups2 = (int)g2.size(); p->ngroups0 = (int)g0.size();
     p->njobs2 = (int)j2.size(); p->njobs0 = (int)j0.size();
     p->nsjobs2 = (int)s2.size(); p->nsjobs0 = (int)s0.size();
@@ -1307,6 +1354,7 @@ int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, con
     const int2* grp = spin == 0 ? p->groups0 : p->groups2;
     // ring_wconst is filled together with the active-ring flags (gs_active_rings_build), from the weight map of this call
     const double* wconst = (p->use_act && g_gs_ring_const) ? p->ring_wconst : nullptr;
+    if (wconst) grp = spin == 0 ? p->groups0_dyn : p->groups2_dyn;   // the CTAs that run transforms are dispatched first (gs_ring_order_build)
     if (p->world > 1) ring_apply_kernel<true><<<nj, RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fx, pixw, skip, p->use_act ? p->act_ring : nullptr, spin ? 1 : 0, 0, nullptr);
     else ring_apply_kernel<false><<<dim3(nj, nc), RF_NT, p->ring_smem, st>>>(p->d, jobs, grp, p->Fm, pixw, skip, p->use_act ? p->act_ring : nullptr, spin ? 1 : 0, nc > 1 ? gs_fm_stride(p) : 0, wconst);
     GS_CHECK_LAUNCH();
@@ -1315,6 +1363,16 @@ int gs_ring_apply(gs_plan* p, int spin, const double* pixw, cudaStream_t st, con
 }
 
 // nb spin-2 ring syntheses in one launch: spectra F + k f_stride (m <= mmax[k]) -> maps Q/U + k map_stride
+int gs_ring_order_build(gs_plan* p, cudaStream_t st)
+{
+    if (p->world > 1 || !p->ring_wconst) return GS_OK;
+    if (p->ngroups2 > 0) ring_order_kernel<<<1, 1024, 0, st>>>(p->jobs2, p->groups2, p->ngroups2, p->act_ring, p->ring_wconst, p->groups2_dyn);
+    if (p->ngroups0 > 0) ring_order_kernel<<<1, 1024, 0, st>>>(p->jobs0, p->groups0, p->ngroups0, p->act_ring, p->ring_wconst, p->groups0_dyn);
+    GS_CHECK_LAUNCH();
+    g_gs_launches += 2;
+    return GS_OK;
+}
+
 int gs_ring_mwg_data(gs_plan* p, const double* mapQ, const double* mapU, double* outQ, double* outU, const double* wconst, cudaStream_t st)
 {
     if (p->world > 1 || p->nsjobs2 > 0) { gs_set_error("spectral ring storage needs an unsharded plan without split rings"); return GS_E_BADARG; }
@@ -1330,8 +1388,8 @@ int gs_ring_synth_batch(gs_plan* p, const double2* F, int64_t f_stride, const in
 {
     if (p->world > 1 || p->nsjobs2 > 0) { gs_set_error("batched ring synthesis needs an unsharded plan without split rings"); return GS_E_BADARG; }
     if (nb <= 0 || p->ngroups2 <= 0) return GS_OK;
-    ring_synth_kernel<false><<<dim3(p->ngroups2, nb), RF_NT, p->ring_smem, st>>>(p->d, p->jobs2, p->groups2, F, mapQ, mapU, nullptr, f_stride,
-                                                                                 map_stride, mmax, 1, ract, wconst);
+    ring_synth_kernel<false><<<dim3(p->ngroups2, nb), RF_NT, p->ring_smem, st>>>(p->d, p->jobs2, wconst ? p->groups2_dyn : p->groups2, F, mapQ, mapU,
+                                                                                 nullptr, f_stride, map_stride, mmax, 1, ract, wconst);
     GS_CHECK_LAUNCH();
     g_gs_launches += 1;
     return GS_OK;
