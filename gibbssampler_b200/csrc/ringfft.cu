@@ -584,7 +584,10 @@ __device__ __forceinline__ void ring_build_Z(const PlanDev& P, const RingSub& S,
     };
     const bool split = n <= S.nt;
     const double2 q = ring_phase(P, job.ringA, n);
-    constexpr int FK = RING_R8 ? 2 : 4;   // values of k (long rings) / alias terms (short rings) per step: 4 FK loads in flight per thread
+#ifndef RING_FK
+#define RING_FK (RING_R8 ? 2 : 4)
+#endif
+    constexpr int FK = RING_FK;   // values of k (long rings) / alias terms (short rings) per step: 4 FK loads in flight per thread
     if (split) {
         const int J = S.nt / n, kq = S.tid % n, jq = S.tid / n;
         double2 z[1] = {zero};
