@@ -902,6 +902,26 @@ def main():
     # r02: C^-1_l and M_l come from per-l tables through a 2-byte multipole index per coefficient: 3 + 6 + 3 passes over 8 N_re bytes
     # per field (+ the index) instead of 4 + 7 + 4
     vec_bytes = [(3 * 8.0 + 2.0) * 2 * nre, (6 * 8.0 + 2.0) * 2 * nre, (3 * 8.0 + 2.0) * 2 * nre]
+
+    def copy_gbs(total_bytes, nrep=20):
+        """A plain device copy that moves the same number of bytes (half read, half written), timed like the kernels above: each
+        launch alone after a write larger than L2.  What a launch of this SIZE can reach on this GPU (the 6.5 TB/s of
+        MEASURED_PEAKS.json is a 4 GiB copy; a 50-100 MB launch lasts 10-20 us and pays its ramp and tail)."""
+        nn = int(total_bytes // 16)
+        a, b = torch.zeros(nn, dtype=torch.float64, device=dev), torch.empty(nn, dtype=torch.float64, device=dev)
+        flush = torch.empty(20_000_000, dtype=torch.float64, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        acc = 0.0
+        for rep in range(-2, nrep):
+            flush.fill_(0.0)
+            e0.record()
+            b.copy_(a)
+            e1.record()
+            e1.synchronize()
+            if rep >= 0:
+                acc += e0.elapsed_time(e1)
+        return 16.0 * nn / (acc / nrep * 1e-3) * 1e-9
+    copy_same = [copy_gbs(vb) for vb in vec_bytes]
     roofline_pcg = {"kernel": "pcg_apq + pcg_update + pcg_dir", "bound": "hbm",
                     "achieved": sum(vec_bytes) / (sum(ms3) * 1e-3) * 1e-9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": sum(vec_bytes) / (sum(ms3) * 1e-3) * 1e-9 / hbm_peak, "traffic": None, "peak_source": hbm_src,
@@ -910,7 +930,12 @@ def main():
                     "ms": {"pcg_apq": ms3[0], "pcg_update": ms3[1], "pcg_dir": ms3[2]},
                     "gb_per_s": {"pcg_apq": vec_bytes[0] / ms3[0] * 1e-6, "pcg_update": vec_bytes[1] / ms3[1] * 1e-6,
                                  "pcg_dir": vec_bytes[2] / ms3[2] * 1e-6},
-                    "note": "each launch timed alone after a write of the 134 MB analysis workspace (L2 flushed), as inside a PCG iteration"}
+                    "copy_of_the_same_size_gb_per_s": {"pcg_apq": copy_same[0], "pcg_update": copy_same[1], "pcg_dir": copy_same[2]},
+                    "frac_of_same_size_copy": sum(vec_bytes) / (sum(ms3) * 1e-3) * 1e-9
+                                              / (sum(vec_bytes) / sum(vb / cs for vb, cs in zip(vec_bytes, copy_same))),
+                    "note": "each launch timed alone after a write of the 134 MB analysis workspace (L2 flushed), as inside a PCG iteration; "
+                            "copy_of_the_same_size = torch copy_ moving as many bytes, timed the same way: the attainable rate of a launch "
+                            "of 50-100 MB"}
 
     # the SHT pair is timed on EVERY rank; the whole-job pairs/s uses the slowest rank's time
     pair_t = torch.tensor([pair_ms], device=dev, dtype=torch.float64)
