@@ -446,7 +446,9 @@ int gs_set_ring_skip(int on);
  * every ring that the edge of the mask does not cut): for such a ring the middle of opfilt_pp.fwd_op (alm2map_spin -> N^-1 ->
  * map2alm_spin, CenteredGibbs.py:629,653) is DFT^H diag(w) DFT = n w on the alias-folded ring spectrum.  on != 0 (default,
  * unsharded plans, needs gs_set_ring_skip on): the fused ring stage of the mat-vec takes those rings without any transform,
- * flagged from the weight map of each call; 0: every ring is transformed.  Same result to rounding.  Returns the previous setting. */
+ * flagged from the weight map of each call, and gs_mwg_sweep_blocks keeps data, model and block maps of those rings as the unitary
+ * DFT of Q + iU along the ring (the weighted sums of squares of NonCenteredGibbs.py:380-399 are invariant under it), so their ring
+ * FFTs are not run either; 0: every ring is transformed.  Same result to rounding.  Returns the previous setting. */
 int gs_set_ring_const(int on);
 /* on != 0: in gs_cr_pcg_* on unsharded plans the step  q += C^-1 p ; <p, q>  rides on the last kernel of the Legendre
  * analysis instead of a separate pass; 0 (default; the fused form measured 0.4 % slower at NSIDE 512): separate kernel.
