@@ -32,6 +32,18 @@
 #define RING_FUSE_MID 0   // Bluestein rings of ring_apply_kernel: pointwise chirp / weight product inside the next transform's first pass
 #endif
 
+#ifndef RING_SUBBAR
+#define RING_SUBBAR 0   // 1: the rings that share a CTA (groups of 2 / 4) synchronise among their own threads (named barriers)
+#endif
+// barrier among the nt threads that work on one transform (all RF_NT threads of the CTA when it holds one ring)
+__device__ __forceinline__ void ring_bar(int nt)
+{
+#if RING_SUBBAR
+    if (nt < RF_NT) { asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)threadIdx.x / nt), "r"(nt) : "memory"); return; }
+#endif
+    __syncthreads();
+}
+
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ double2 cmulc(double2 a, double2 b) { return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }  // a conj(b)
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
@@ -133,7 +145,7 @@ __device__ __forceinline__ void pass16(double2* buf, int M, int N, const double2
             buf[PADI(i0 + k * s)] = v;
         }
     }
-    __syncthreads();
+    ring_bar(nt);
 }
 
 // radix-4 pass over sub-transforms of size N (N >= 4)
@@ -149,7 +161,7 @@ __device__ __forceinline__ void pass4(double2* buf, int M, int N, const double2*
         if (!INV) bf4_dif(a0, a1, a2, a3, w1, w2); else bf4_dit(a0, a1, a2, a3, w1, w2);
         buf[PADI(i0)] = a0; buf[PADI(i0 + q)] = a1; buf[PADI(i0 + 2 * q)] = a2; buf[PADI(i0 + 3 * q)] = a3;
     }
-    __syncthreads();
+    ring_bar(nt);
 }
 
 // radix-8 pass over sub-transforms of size N (N >= 8) = one radix-2 level + one radix-4 level in registers.  Transform lengths
@@ -197,7 +209,7 @@ __device__ __forceinline__ void pass8(double2* buf, int M, int N, const double2*
             buf[PADI(i0 + k * s)] = v;
         }
     }
-    __syncthreads();
+    ring_bar(nt);
 }
 
 // radix-2 pass over sub-transforms of size N (N >= 2)
@@ -212,7 +224,7 @@ __device__ __forceinline__ void pass2(double2* buf, int M, int N, const double2*
         if (!INV) { buf[PADI(i0)] = cadd(a, b); buf[PADI(i0 + h)] = cmul(csub(a, b), w); }
         else { const double2 tb = cmulc(b, w); buf[PADI(i0)] = cadd(a, tb); buf[PADI(i0 + h)] = csub(a, tb); }
     }
-    __syncthreads();
+    ring_bar(nt);
 }
 
 // In-place forward DIF FFT (kernel exp(-2 pi i jk/M)), natural order in, bit-reversed order out;
@@ -309,7 +321,7 @@ __device__ __forceinline__ double2 chirp_val(int t, int n)
 // All threads of the CTA must call; begins and ends with a barrier.
 __device__ void ring_idft(const PlanDev& P, double2* buf, const double2* twq, int n, int bsi, int tid = threadIdx.x, int nt = RF_NT)
 {
-    __syncthreads();
+    ring_bar(nt);
     if (bsi < 0) { fft_dit_inv(buf, n, twq, P.tw_n, tid, nt); return; }
     const BluesteinDesc d = P.bs[bsi];
     fft_dif<true>(buf, d.M, twq, P.tw_n, P.bs_tab + d.bhat_off, tid, nt);
@@ -615,7 +627,7 @@ __device__ __forceinline__ void ring_build_Z(const PlanDev& P, const RingSub& S,
         }
         for (int k = S.tid + ((n - S.tid + S.nt - 1) / S.nt) * S.nt; k < Mz; k += S.nt) put(k, zero);   // zero padding
     }
-    __syncthreads();
+    ring_bar(S.nt);
     if (split) {
         const int J = S.nt / n;
         for (int k = S.tid; k < Mz; k += S.nt) {
@@ -694,7 +706,7 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
         // sqrt(n) Z_k (the unitary DFT of the pixels this launch would have produced) and no transform runs
         const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
         ring_build_Z<SH>(P, S, Fm, min(mcap, ring_mtop(P, S.job.ringA, spin2)), S.scratch, mmax != nullptr, true);
-        __syncthreads();
+        ring_bar(S.nt);
         const double sn = sqrt((double)S.n);
         double* oa = mapQ + ring_first_pixel<SH>(P, S.job.ringA);
         double* ob = mapU + ring_first_pixel<SH>(P, S.job.ringA);
@@ -706,6 +718,9 @@ ring_synth_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
         return;
     }
     load_twq(P, twq);
+#if RING_SUBBAR
+    __syncthreads();   // the twiddle table is loaded by the whole CTA; every later barrier may be a sub-ring one
+#endif
     const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
     ring_build_Z<SH>(P, S, Fm, min(mcap, ring_mtop(P, S.job.ringA, spin2)), S.scratch, mmax != nullptr);
     ring_idft(P, S.buf, twq, S.n, S.bsi, S.tid, S.nt);
@@ -734,6 +749,9 @@ ring_anal_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __rest
     mapU += blockIdx.y * map_stride;
     double2* twq = smem;
     load_twq(P, twq);
+#if RING_SUBBAR
+    __syncthreads();   // the twiddle table is loaded by the whole CTA; every later barrier may be a sub-ring one
+#endif
     const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
     const RingJob& job = S.job;
     const int n = S.n;
@@ -767,6 +785,9 @@ ring_mwg_data_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __
     double2* twq = smem;
     const bool spectral = group_const(wconst, jobs, groups);
     if (spectral) load_twq(P, twq);
+#if RING_SUBBAR
+    __syncthreads();
+#endif
     const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
     const int n = S.n;
     const int64_t s0 = P.ring_start[S.job.ringA];
@@ -856,12 +877,15 @@ ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
             return;
         }
         ring_build_Z<SH>(P, S, Fm, mtop, S.scratch, false, true);
-        __syncthreads();
+        ring_bar(S.nt);
         const double half_n = 0.5 * (double)S.n;
         ring_unpack_F<SH>(P, S, UNPACK_PLAIN, Fm, mtop, nullptr, half_n * wA, half_n * wB);
         return;
     }
     load_twq(P, twq);
+#if RING_SUBBAR
+    __syncthreads();   // the twiddle table is loaded by the whole CTA; every later barrier may be a sub-ring one
+#endif
     const RingSub S = ring_sub(P, jobs, groups, twq + (P.tw_n >> 2) + 1);
     const int n = S.n;
     const double* wa = pixw + ring_first_pixel<SH>(P, S.job.ringA);
@@ -869,7 +893,7 @@ ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
     RING_DBG(0); RING_DBG(3);
     const int mtop = ring_mtop(P, S.job.ringA, spin2);
     ring_build_Z<SH>(P, S, Fm, mtop, S.scratch);
-    __syncthreads();
+    ring_bar(S.nt);
     RING_DBG(1);
     ring_idft(P, S.buf, twq, n, S.bsi, S.tid, S.nt);
     if (S.bsi < 0) {
@@ -906,11 +930,11 @@ ring_apply_kernel(PlanDev P, const RingJob* __restrict__ jobs, const int2* __res
         ring_unpack_F<SH>(P, S, UNPACK_CONJ, Fm, mtop, chirp);
 #else
         for (int k = S.tid; k < n; k += S.nt) S.buf[PADI(k)] = cmul(S.buf[PADI(k)], __ldg(&chirp[k]));
-        __syncthreads();
+        ring_bar(S.nt);
         ring_unpack_F<SH>(P, S, UNPACK_CONJ, Fm, mtop);
 #endif
     }
-    __syncthreads();
+    ring_bar(S.nt);
     RING_DBG(2);
 }
 
