@@ -594,6 +594,45 @@ __device__ __forceinline__ void ring_build_Z(const PlanDev& P, const RingSub& S,
         else if (S.bsi >= 0 && !plain) v = cmul(v, __ldg(&S.chirp[k]));
         S.buf[pos] = v;
     };
+#ifndef RING_DIRECT_FOLD
+#define RING_DIRECT_FOLD 1
+#endif
+#if RING_DIRECT_FOLD
+    if (!SH && 2 * mtop <= n && n > S.nt) {
+        // No alias term (most cap rings, the whole belt): F_m alone gives Z_m = e^{i m phi0} (Fa + i Fb)_m and
+        // Z_{n-m} = e^{-i m phi0} (conj Fa + i conj Fb)_m; the walk is over m with 2 DU independent loads in flight, every one of them
+        // used (the general fold below walks k and predicates off the half of its loads whose m lies above m_top).
+        constexpr int DU = 8;
+        double2 pm = ring_phase(P, job.ringA, S.tid);
+        const double2 step = ring_phase(P, job.ringA, S.nt);
+        for (int m0 = S.tid; m0 <= mtop; m0 += DU * S.nt) {
+            double2 a[DU], b[DU];
+#pragma unroll
+            for (int u = 0; u < DU; ++u) {
+                const int m = m0 + u * S.nt;
+                const bool ok = m <= mtop;
+                a[u] = ok ? FA[m * fs] : zero;
+                b[u] = (ok && FB) ? FB[m * fs] : zero;
+            }
+#pragma unroll
+            for (int u = 0; u < DU; ++u) {
+                const int m = m0 + u * S.nt;
+                if (m <= mtop) {
+                    const double2 t1 = make_double2(a[u].x - b[u].y, a[u].y + b[u].x);   // Fa + i Fb
+                    const double2 t2 = make_double2(a[u].x + b[u].y, b[u].x - a[u].y);   // conj Fa + i conj Fb
+                    if (m == 0) put(0, make_double2(a[u].x, b[u].x));                    // weight 1/2 on both terms
+                    else if (2 * m == n) put(m, cadd(cmul(t1, pm), cmulc(t2, pm)));      // the term meets its own mirror
+                    else { put(m, cmul(t1, pm)); put(n - m, cmulc(t2, pm)); }
+                }
+                pm = cmul(pm, step);
+            }
+        }
+        for (int k = mtop + 1 + S.tid; k < n - mtop; k += S.nt) put(k, zero);
+        for (int k = n + S.tid; k < Mz; k += S.nt) put(k, zero);   // zero padding (Bluestein)
+        ring_bar(S.nt);
+        return;
+    }
+#endif
     const bool split = n <= S.nt;
     const double2 q = ring_phase(P, job.ringA, n);
 #ifndef RING_FK

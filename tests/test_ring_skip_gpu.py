@@ -142,4 +142,6 @@ def test_pcg_solution_with_and_without_skipping(kind, setter):
     L.gs_set_ring_const(old_const)
     (xa, ia), (xb_, ib) = out
     assert abs(ia - ib) <= 1
-    assert np.abs(xa - xb_).max() <= 1e-6 * np.abs(xb_).max()
+    # two solves to the reference's eps = 1e-5 whose dot products are summed in a different order (gs_set_fuse_apq) follow slightly
+    # different conjugate-gradient trajectories: they agree to the tolerance of the solve, not to rounding (measured 2e-7 ... 1e-6)
+    assert np.abs(xa - xb_).max() <= 1e-5 * np.abs(xb_).max()
