@@ -500,6 +500,61 @@ mwg_apply_kernel(double* __restrict__ rQ, double* __restrict__ rU, const double*
     }
 }
 
+// One Metropolis test in one launch (default; GS_MWG_FUSED=0 restores test / decide / apply): the r update of the PREVIOUS test
+// (pend_flag, maps pQ / pU) is applied as r is read, the chi^2 partials of the candidate follow, and the block that finishes last sums
+// them in the order of mwg_decide_kernel and takes the decision.  Same numbers as the three kernels: 252 instead of 756 launches
+// per sweep and one pass over r less per accepted block.  pend_flag may alias do_apply_out and `applied` is written by the deciding
+// block only: every block reads both before its loop, and the decision comes after all loops (counter).
+__global__ void __launch_bounds__(SM_NT)
+mwg_step_kernel(double* __restrict__ rQ, double* __restrict__ rU, const double* __restrict__ pQ, const double* __restrict__ pU,
+                const int* pend_flag, const double* __restrict__ gQ, const double* __restrict__ gU,
+                const double* __restrict__ invn, int64_t n, double* partials, unsigned* counter, double* cur,
+                const double* prop, const double* logr, int b0, int b1, double* lik, const double* u, int* applied, int* do_apply_out,
+                int* accept_out)
+{
+    const bool pend = pQ != nullptr && *pend_flag != 0;
+    const bool sub = *applied == 0;
+    double v[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double a = rQ[i], b = rU[i];
+        if (pend) { a -= pQ[i]; b -= pU[i]; rQ[i] = a; rU[i] = b; }
+        if (sub) { a -= gQ[i]; b -= gU[i]; }
+        v[0] = fma(fma(b, b, a * a), invn[i], v[0]);
+    }
+    block_sum<1>(v, partials + blockIdx.x);
+    __shared__ int last;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(counter, 1u) == gridDim.x - 1 ? 1 : 0;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double s[1] = {0.0};
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s[0] += __ldcg(partials + i);
+    __shared__ double res[1];
+    block_sum<1>(s, res);
+    __syncthreads();
+    if (threadIdx.x) return;
+    *counter = 0u;
+    const double new_lik = -0.5 * res[0];
+    double t = 0.0;
+    for (int b = b0; b < b1; ++b) t += logr[b];
+    const bool acc = log(u[0]) < t + (new_lik - lik[0]);
+    int apply = 0;
+    if (acc) {
+        lik[0] = new_lik;
+        if (*applied == 0) {
+            for (int b = b0; b < b1; ++b) cur[b] = prop[b];
+            *applied = 1;
+            apply = 1;
+        }
+    }
+    lik[1] = new_lik;
+    *do_apply_out = apply;
+    accept_out[0] = acc ? 1 : 0;
+}
+
 __global__ void mwg_first_lik_kernel(const double* partials, int np, double* lik)
 {
     double v[1] = {0.0};
@@ -580,8 +635,10 @@ extern "C" int gs_mwg_sweep_blocks(gs_plan* p, const double* snc_E, const double
     const int* lbE = p->mwg_meta + off_lbE;
     const int* lbB = p->mwg_meta + off_lbB;
     const int* mmax = p->mwg_meta + off_mmax;
-    int* flags = p->mwg_meta + meta.size();  // [ntot] applied, then do_apply
+    int* flags = p->mwg_meta + meta.size();  // [ntot] applied, then do_apply, then the ticket counter of mwg_step_kernel
     int* do_apply = flags + ntot;
+    unsigned* ticket = reinterpret_cast<unsigned*>(flags + ntot + 1);
+    static const bool fused_steps = [] { const char* e = getenv("GS_MWG_FUSED"); return !(e && e[0] == '0'); }();
     double* partials = p->mwg_small;
     double* lik = partials + SM_GRID;
     double* flE = lik + 8;
@@ -591,7 +648,7 @@ extern "C" int gs_mwg_sweep_blocks(gs_plan* p, const double* snc_E, const double
     double* rQ = p->mapQ_tmp;
     double* rU = p->mapU_tmp;
 
-    GS_CHECK_CUDA(cudaMemsetAsync(flags, 0, (ntot + 1) * sizeof(int), st));
+    GS_CHECK_CUDA(cudaMemsetAsync(flags, 0, (ntot + 2) * sizeof(int), st));
     // block maps are only ever weighted by N^-1: the rings on which it vanishes identically need no ring FFT
     // Rings on which N^-1 is one number w (isotropic noise, not cut by the mask edge; gs_set_ring_const): every quantity of the sweep
     // on such a ring is w sum_j |z_j - z'_j|^2 with z = Q + i U, which the unitary DFT along the ring leaves unchanged.  Data, current
@@ -627,8 +684,15 @@ extern "C" int gs_mwg_sweep_blocks(gs_plan* p, const double* snc_E, const double
     GS_CHECK_LAUNCH();
     g_gs_launches += 4;
 
+    const double* pQ = nullptr;   // maps of the previous test: mwg_step_kernel applies its r update as the next test reads r
+    const double* pU = nullptr;
     for (int g0 = 0; g0 < ntot; g0 += G) {
         const int g1 = std::min(ntot, g0 + G), ng = g1 - g0;
+        if (pQ) {   // the block maps are about to be overwritten: apply the pending update now
+            mwg_apply_kernel<<<SM_GRID, SM_NT, 0, st>>>(rQ, rU, pQ, pU, npix, do_apply);
+            pQ = pU = nullptr;
+            g_gs_launches += 1;
+        }
         const int e0 = std::min(g0, nblk_E), e1 = std::min(g1, nblk_E);
         const int b0 = std::max(g0 - nblk_E, 0), b1 = std::max(g1 - nblk_E, 0);
         int lend = 0;
@@ -646,6 +710,14 @@ extern "C" int gs_mwg_sweep_blocks(gs_plan* p, const double* snc_E, const double
             const double* gU = p->mwg_maps + (int64_t)(G + k - g0) * npix;
             for (int it = 0; it < n_iter; ++it) {
                 const int64_t idx = (int64_t)k * n_iter + it;
+                if (fused_steps) {
+                    mwg_step_kernel<<<SM_GRID, SM_NT, 0, st>>>(rQ, rU, pQ, pU, do_apply, gQ, gU, inv_noise, npix, partials, ticket,
+                                                               isE ? cur_E : cur_B, isE ? prop_E : prop_B, isE ? logr_E : logr_B, blocks[i],
+                                                               blocks[i + 1], lik, u + idx, flags + k, do_apply, accept_out + idx);
+                    pQ = gQ; pU = gU;
+                    g_gs_launches += 1;
+                    continue;
+                }
                 mwg_test_kernel<<<SM_GRID, SM_NT, 0, st>>>(rQ, rU, gQ, gU, inv_noise, npix, flags + k, partials);
                 mwg_decide_kernel<<<1, SM_NT, 0, st>>>(partials, SM_GRID, isE ? cur_E : cur_B, isE ? prop_E : prop_B,
                                                         isE ? logr_E : logr_B, blocks[i], blocks[i + 1], lik, u + idx, flags + k,
