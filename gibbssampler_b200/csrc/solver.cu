@@ -788,7 +788,6 @@ extern "C" int gs_cr_apply_q_pol(gs_plan* p, const double* dl_EE, const double* 
     cudaStream_t st = (cudaStream_t)stream;
     gs_pcg_ws* w = get_ws(p);
     if (!w) return GS_E_NOMEM;
-    const int L = p->d.lmax;
     const int64_t n = p->nreal_loc;
     int rc;
     ActiveRings act(p);
@@ -821,7 +820,6 @@ extern "C" int gs_cr_rhs_pol(gs_plan* p, const double* dl_EE, const double* dl_B
     cudaStream_t st = (cudaStream_t)stream;
     gs_pcg_ws* w = get_ws(p);
     if (!w) return GS_E_NOMEM;
-    const int L = p->d.lmax;
     const int64_t n = p->nreal_loc;
     int rc;
     // fluctuation term 1: utils.adjoint_synthesis_hp (utils.py:79-111) = bl * (Npix/4pi) * map2alm(iter=3)
