@@ -136,3 +136,46 @@ def test_direct_solve_and_cls_draw_vs_oracle():
         ref = b * invgamma.rvs(a=a)
         ref[:2] = 0
         assert relerr(got[pol], ref) < 1e-12
+
+
+@pytest.mark.parametrize("eps,check_every", [(3e-1, 8), (1e-1, 8), (1e-2, 8), (1e-3, 8), (1e-5, 8), (1e-3, 3), (1e-4, 1), (1e-5, 16)])
+def test_pcg_graph_replay_equals_plain_launches(eps, check_every):
+    """The iterations between two polls of the convergence flag are replayed from a CUDA graph with two batches in flight
+    (solver.cu, gs_set_pcg_graph, default on); the same solve with plain launches and one poll at a time runs the same kernels in the
+    same order: identical iteration count and bit-identical solution, whether the solve stops inside the first batch, at a batch
+    boundary or in the iterations left over before iter_max."""
+    from gibbssampler_b200 import _lib
+    L = _lib.lib()
+    P = make_problem(16, 32, seed=11)
+    ell = np.arange(P["lmax"] + 1)
+    dls = {"EE": P["dlE"], "BB": P["dlB"]}
+    rng = np.random.default_rng(4)
+    nre = (P["lmax"] + 1) ** 2
+    xi = (rng.standard_normal(P["npix"]), rng.standard_normal(P["npix"]), rng.standard_normal(nre), rng.standard_normal(nre))
+    del ell
+
+    def solve(graph, itermax):
+        old = L.gs_set_pcg_graph(graph)
+        try:
+            cr = gpu_cr(P)
+            cr.pcg_accuracy, cr.pcg_check_every, cr.pcg_itermax = eps, check_every, itermax
+            sol, _ = cr.sample_mask(dls, xi)
+            solve.residual = cr.last_pcg_residual
+            return np.concatenate([np.asarray(sol["EE"]), np.asarray(sol["BB"])]), cr.last_pcg_iterations
+        finally:
+            L.gs_set_pcg_graph(old)
+
+    xa, ia = solve(1, 4000)
+    xb, ib = solve(0, 4000)
+    assert ia == ib and ia >= 1
+    assert np.array_equal(xa, xb)
+    # iter_max exactly at the iteration that converges (the device stops there in both modes), one batch above, and not a multiple
+    # of check_every: the left-over iterations run as plain launches after the last whole batch
+    for itermax in sorted({ia, ia + check_every, ia + 1}):
+        xc, ic = solve(1, itermax)
+        assert ic == ia and np.array_equal(xc, xa)
+    if ia > 1:   # one iteration short: both modes stop at iter_max without having converged (as qcinv does, the residual says so)
+        (xd, idd), rd = solve(1, ia - 1), solve.residual
+        (xe_, ie), re_ = solve(0, ia - 1), solve.residual
+        assert idd == ie == ia - 1 and rd == re_ and rd > eps
+        assert np.array_equal(xd, xe_)
