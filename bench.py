@@ -70,21 +70,25 @@ def pixel_phi(nside):
     return phi
 
 
-MASK_KINDS = ("galplane", "band")
-MASK_KIND = "galplane"   # --mask; read by every make_mask(nside) of this run (both arms, config #4)
+MASK_KINDS = ("band", "galplane")
+MASK_KIND = "band"   # --mask; read by every make_mask(nside) of this run (both arms, config #4)
 MASK_NOTE = {
-    "galplane": "synthetic stand-in for the reference's HFI GalPlane 80 % mask (config.py:26): |b| < b0(l), bulge at l = 0 + ripples "
-                "(half width 3 to 33 deg), cos taper 2 deg, f_sky 0.8; the mask edge CUTS the rings near the plane",
-    "band": "axisymmetric band |b| < 11.5 deg, cos taper 2 deg, f_sky 0.8 (the mask of rounds 1-2a; no ring is cut by its edge)",
+    "band": "the synthetic input SURVEY.md 8(d) names (and BENCH_r01 ran): axisymmetric galactic band |b| < 11.5 deg, cos taper 2 deg, "
+            "f_sky 0.8.  No ring is cut by its edge, so with isotropic noise every ring has ONE pixel weight and the transform-free ring "
+            "paths (gs_set_ring_const) serve the whole sky: see the galplane_mask entry for a mask that cuts rings",
+    "galplane": "stand-in for the shape of the reference's HFI GalPlane 80 % mask (config.py:26): |b| < b0(l), bulge at l = 0 + ripples "
+                "(half width 3 to 33 deg), cos taper 2 deg, f_sky 0.8; its edge CUTS 735 of the 2047 rings at NSIDE 512 (they keep their "
+                "FFTs), 994 instead of 883 ring pairs carry weight, and the PCG needs about 3 % more iterations",
 }
 
 
 def make_mask(nside, fsky=0.8, kind=None, edge_deg=2.0):
     """Synthetic stand-in for the reference's sky mask (config.py:26: HFI_Mask_GalPlane-apo0_2048_R2 80 %, a mask of the galactic
     plane in galactic coordinates), cos-tapered over edge_deg, mean = fsky.
-    "galplane": |b| < b0(l) with a bulge around l = 0 and ripples (half width between about 3 and 33 degrees), so the rings
-    near the plane are CUT by the mask edge while the polar caps and the high-latitude belt stay whole, as under the Planck
-    mask; "band": the axisymmetric band |b| < asin(1 - fsky) of the earlier rounds (no ring is cut: every ring has one weight)."""
+    "band" (default; the input SURVEY.md 8(d) names): the axisymmetric band |b| < asin(1 - fsky); no ring is cut, every ring has one
+    weight.  "galplane": |b| < b0(l) with a bulge around l = 0 and ripples (half width between about 3 and 33 degrees), so the
+    rings near the plane are CUT by the mask edge while the polar caps and the high-latitude belt stay whole, as under the Planck
+    mask."""
     kind = kind or MASK_KIND
     z = pixel_z(nside)
     b = np.degrees(np.arcsin(np.abs(z)))        # |latitude|
@@ -582,9 +586,10 @@ def main():
     ap.add_argument("--nside", type=int, default=512)
     ap.add_argument("--lmax", type=int, default=1024)
     ap.add_argument("--pcg-iters", type=int, default=0)
-    ap.add_argument("--mask", default="galplane", choices=list(MASK_KINDS), help="synthetic sky mask, f_sky 0.8 (see make_mask)")
+    ap.add_argument("--mask", default="band", choices=list(MASK_KINDS), help="synthetic sky mask, f_sky 0.8 (see make_mask)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-band-mask", action="store_true", help="skip the secondary measurement under the band mask of rounds 1-2a")
+    ap.add_argument("--no-other-mask", "--no-band-mask", dest="no_other_mask", action="store_true",
+                    help="skip the secondary measurement under the other synthetic mask (galplane when --mask band, and vice versa)")
     ap.add_argument("--no-chain-batch", action="store_true", help="skip the secondary measurement with two chains per GPU")
     ap.add_argument("--no-config4", action="store_true", help="N >= 2: skip the m-sharded single-chain measurement (BASELINE config #4)")
     ap.add_argument("--config4-nside", type=int, default=2048)
@@ -746,11 +751,13 @@ def main():
     value = whole_job_value(world, args.steps, ms_total)
     n_pcg = int(round(float(np.mean(its_timed)))) if its_timed else 0
 
-    # ---- secondary measurement: the same sampler under the axisymmetric band mask of rounds 1-2a (continuity with BENCH_r01; there
-    # no ring is cut by the mask edge, so with isotropic noise every ring has one weight and the mat-vec's ring stage runs no FFT)
-    band_mask = None
-    if MASK_KIND != "band" and not args.no_band_mask:
-        mask_b = make_mask(nside, kind="band")
+    # ---- secondary measurement: the same sampler under the OTHER synthetic mask.  The default (band) mask cuts no ring, so with
+    # isotropic noise every ring has one weight and neither the mat-vec's ring stage nor the sweep runs an FFT; the galactic-plane-like
+    # mask cuts 735 rings, which keep their transforms: both numbers belong next to each other.
+    other_kind = "galplane" if MASK_KIND == "band" else "band"
+    other_mask = None
+    if not args.no_other_mask:
+        mask_b = make_mask(nside, kind=other_kind)
         mb_d = _dev.f64(mask_b)
         dQb, dUb = skyQ * mb_d, skyU * mb_d
         if pncp:
@@ -764,8 +771,8 @@ def main():
             clsb = PolarizedCenteredClsSampler({"Q": dQb, "U": dUb}, lmax, nside, bins, bl_map, noise_pol, mask=mask_b, rng=crb.rng)
         st_b, its_b = {"binned": binned_init()}, []
         ms_b = timed(make_step(crb, clsb, st_b, its_b, []), args.warmup, args.steps)
-        band_mask = {"mask": "band: " + MASK_NOTE["band"], "value": whole_job_value(world, args.steps, ms_b), "unit": "it/s",
-                     "ms_per_step": ms_b / args.steps, "pcg_iterations_per_step": its_b[args.warmup:], "gpu_launches": counted["launches"]}
+        other_mask = {"mask": other_kind + ": " + MASK_NOTE[other_kind], "value": whole_job_value(world, args.steps, ms_b), "unit": "it/s",
+                      "ms_per_step": ms_b / args.steps, "pcg_iterations_per_step": its_b[args.warmup:], "gpu_launches": counted["launches"]}
         del crb, clsb, dQb, dUb
 
     # ---- secondary measurement: TWO chains per GPU whose PCG mat-vecs run as chain batches (one Legendre recurrence for both
@@ -961,7 +968,7 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args), "pcg_iterations_mean": n_pcg,
             "e2e": {"value": e2e_val, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches, "band_mask": band_mask, "chain_batch": chain_batch, "config4_m_sharded": config4,
+            "gpu_launches": launches, other_kind + "_mask": other_mask, "chain_batch": chain_batch, "config4_m_sharded": config4,
             "sht_pairs_per_s": world * 1e3 / pair_ms_max, "sht_pair_ms": pair_ms_max, "stage_ms": stage_ms,
             "pcg_matvec": {"ms": sum(matvec_ms.values()), "stage_ms": matvec_ms, "active_ring_pairs": act.value, "ring_pairs": tot.value,
                            "constant_weight_rings": nconst.value, "rings": 4 * nside - 1,
