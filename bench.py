@@ -11,7 +11,9 @@ PolarizedCenteredClsSampler.sample), one independent chain per GPU (weak scaling
 collective).  Workload: NSIDE 512, lmax 1024, analytic fiducial spectra
 D^EE_l = exp(-(l/1200)^2) + 0.02, D^BB_l = 0.05 (l/80)^-0.5 exp(-(l/1500)^2) + 1e-3 (l >= 2),
 Gaussian 0.5 deg beam, white noise sigma^2_pol = 0.04 uK^2 (NSIDE 256) scaled with Npix, galactic
-band mask f_sky = 0.8 with a 2 deg cosine edge; data synthetic, seeds fixed.
+band mask f_sky = 0.8 with a 2 deg cosine edge; data synthetic, seeds fixed.  Every run also measures the same
+sampler under a galactic-plane-like mask whose edge depends on the longitude (--mask galplane; key `galplane_mask`
+of the JSON line): the band cuts no ring, that one cuts a third of them (see make_mask).
 """
 import argparse
 import ctypes as C
